@@ -1,0 +1,57 @@
+"""Counter-based streams shared by the device kernels and the host harness.
+
+The synthetic workload needs uniform controls 0..5 per ship per
+tick and a reset-pool pick per finished episode that can be regenerated on the
+host, bit for bit, for the oracle comparison.  Both are pure functions of small
+integer keys — no state, no ordering constraints between games.
+
+The same arithmetic lives in `csrc/astro_device.cuh` (`mix32`, `action_for`,
+`pool_pick`); this file is the host-side (numpy, vectorised) statement of it.
+"""
+import numpy as np
+
+_U32 = np.uint32
+_M1 = _U32(0x7FEB352D)
+_M2 = _U32(0x846CA68B)
+_GOLD = _U32(0x9E3779B1)
+_POOL_SALT = _U32(0xA5A5A5A5)
+
+
+def mix32(x):
+    """32-bit avalanche mixer (xorshift-multiply, "lowbias32" constants)."""
+    with np.errstate(over='ignore'):
+        x = np.asarray(x, dtype=_U32).copy()
+        x ^= x >> _U32(16)
+        x *= _M1
+        x ^= x >> _U32(15)
+        x *= _M2
+        x ^= x >> _U32(16)
+    return x
+
+
+def _mulhi(h, m):
+    return ((h.astype(np.uint64) * np.uint64(m)) >> np.uint64(32)).astype(np.int64)
+
+
+def actions(seed, game_ids, step, nships):
+    """Controls for `game_ids` at rollout step `step` -> int64 [len(game_ids), nships].
+
+    key = (seed, global game id, rollout step index, ship); value uniform in 0..5.
+    """
+    with np.errstate(over='ignore'):
+        g = np.asarray(game_ids, dtype=_U32)
+        h0 = mix32(_U32(seed) ^ (g * _GOLD))
+        out = np.empty((g.shape[0], nships), dtype=np.int64)
+        for s in range(nships):
+            k = _U32((int(step) * 2 + s) & 0xFFFFFFFF)
+            out[:, s] = _mulhi(mix32(h0 ^ k), 6)
+    return out
+
+
+def pool_pick(seed, game_ids, episode, pool_size):
+    """Reset-pool entry used by global game `g` for its `episode`-th game (episode>=0)."""
+    with np.errstate(over='ignore'):
+        g = np.asarray(game_ids, dtype=_U32)
+        e = np.asarray(episode, dtype=_U32)
+        h0 = mix32(_U32(seed) ^ _POOL_SALT ^ (g * _GOLD))
+        return _mulhi(mix32(h0 ^ e), pool_size)
