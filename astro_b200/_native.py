@@ -1,0 +1,86 @@
+"""ctypes binding of include/astro_b200.h.  There is no CPU fallback: if the CUDA library is
+missing this module raises, and every compute entry point needs a CUDA device."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libastro_b200.so')
+
+ABI_VERSION = 1
+TILE = 32
+MAX_PLANETS = 4
+MAX_BULLET_CAP = 1023
+MAX_TICKS = 262143
+N_STATS = 12
+STAT_NAMES = ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'env_steps', 'bullets_spawned',
+              'overflow', 'planets_live', 'bullets_in', 'bullets_out', 'skipped')
+
+EV_HIT0, EV_HIT1, EV_TIMEOUT, EV_FIRED, EV_OVERFLOW, EV_SKIPPED = 1, 2, 4, 8, 16, 32
+EV_DONE_MASK = 7
+TICK_AUTO_RESET, TICK_NO_STATS = 1, 2
+
+EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro_batch_destroy',
+           'astro_batch_bind', 'astro_set_schedule', 'astro_set_stream', 'astro_set_reset_pool',
+           'astro_tick', 'astro_tick_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
+           'astro_launch_count')
+
+
+class AstroConfig(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        'gravity', 'dt', 'max_time', 'reload_time', 'bullet_speed', 'ship_thrust', 'ship_rspeed',
+        'ship_radius', 'planet_mass', 'planet_radius')] + [('solo', C.c_int32), ('reserved', C.c_int32)]
+
+
+class AstroBuffers(C.Structure):
+    _fields_ = [('ships', C.c_void_p), ('ship_b', C.c_void_p), ('planets', C.c_void_p),
+                ('bullets', C.c_void_p), ('meta', C.c_void_p), ('episode', C.c_void_p)]
+
+
+class AstroResetPool(C.Structure):
+    _fields_ = [('ships', C.c_void_p), ('planets', C.c_void_p), ('np', C.c_void_p),
+                ('size', C.c_int32), ('reserved', C.c_int32)]
+
+
+class AstroError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded CUDA library.  Raises if it has not been built — there is no other path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'astro_b200: %s is missing. Build it with `python -m astro_b200.build` '
+            '(nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    L.astro_abi_version.restype = C.c_int
+    L.astro_last_error.restype = C.c_char_p
+    L.astro_batch_create.argtypes = [C.POINTER(AstroConfig), i32, i32, i32, i32, C.POINTER(vp)]
+    L.astro_batch_destroy.argtypes = [vp]
+    L.astro_batch_bind.argtypes = [vp, C.POINTER(AstroBuffers)]
+    L.astro_set_schedule.argtypes = [vp, vp, i32, i32]
+    L.astro_set_stream.argtypes = [vp, u32, i64, u32]
+    L.astro_set_reset_pool.argtypes = [vp, C.POINTER(AstroResetPool)]
+    L.astro_tick.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    L.astro_tick_host.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    L.astro_reset_done.argtypes = [vp, vp]
+    L.astro_observe.argtypes = [vp, vp, i32, vp]
+    L.astro_stats.argtypes = [vp, vp, i32, vp]
+    L.astro_launch_count.argtypes = [vp]
+    L.astro_launch_count.restype = i64
+    if L.astro_abi_version() != ABI_VERSION:
+        raise ImportError('astro_b200: %s has ABI %d, expected %d — rebuild it'
+                          % (LIB_PATH, L.astro_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise AstroError('astro_b200 error %d: %s' % (rc, lib().astro_last_error().decode()))

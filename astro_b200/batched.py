@@ -1,0 +1,321 @@
+"""BatchedGames — N independent Astro games resident in HBM, advanced by one CUDA launch per tick.
+
+Host side of the C ABI in include/astro_b200.h.  PyTorch owns the device memory and the stream;
+all arithmetic of the tick / observation path runs in csrc/astro_b200.cu.  There is no CPU
+implementation behind this class.
+
+Reference semantics: one `step()` here == `astro.core.step` (astro/core.py:215-303) applied to
+every game; `observe()` == `ValueNetwork.get_features_batch` (astro/rl.py:43-112) for every game
+and both ship perspectives (`core.roll_ships`, core.py:306-327).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+from . import core
+from .schedule import Schedule
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('astro_b200 needs a CUDA device: there is no CPU path for the game tick')
+    return torch
+
+
+class BatchedGames:
+    def __init__(self, config, n_games, bullet_cap=32, precision=32, device=None, seed=0, first_game=0):
+        torch = _torch()
+        if precision not in (32, 64):
+            raise ValueError('precision must be 32 or 64')
+        if not 0 <= bullet_cap <= nat.MAX_BULLET_CAP:
+            raise ValueError('bullet_cap out of range')
+        self.config = config
+        self.S = 1 if config.solo else 2
+        self.D = 1 + 5 * self.S + 4
+        self.n = int(n_games)
+        self.n_tiles = -(-self.n // nat.TILE)
+        self.n_pad = self.n_tiles * nat.TILE
+        self.K = int(bullet_cap)
+        self.precision = precision
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
+        self.rdtype = torch.float32 if precision == 32 else torch.float64
+        self.np_rdtype = np.float32 if precision == 32 else np.float64
+        self.seed, self.first_game = int(seed), int(first_game)
+        dev, T, S, K = self.device, self.n_tiles, self.S, self.K
+        self.ships = torch.zeros((T, S, 32, 4), dtype=self.rdtype, device=dev)
+        self.ship_b = torch.zeros((T, S, 32), dtype=self.rdtype, device=dev)
+        self.planets = torch.zeros((T, nat.MAX_PLANETS, 32, 4), dtype=self.rdtype, device=dev)
+        self.bullets = torch.zeros((T, max(K, 1), 32, 4), dtype=self.rdtype, device=dev)
+        # every slot starts finished (empty); meta = nb | np<<10 | finished<<13 | tick<<14
+        self.meta = torch.full((self.n_pad,), 1 << 13, dtype=torch.int32, device=dev)
+        self.episode = torch.zeros((self.n_pad,), dtype=torch.int32, device=dev)
+        self._reward = torch.zeros((self.n_pad, S), dtype=torch.float32, device=dev)
+        self._done = torch.zeros((self.n_pad,), dtype=torch.uint8, device=dev)
+        self._events = torch.zeros((self.n_pad,), dtype=torch.uint8, device=dev)
+        self._actions = torch.zeros((self.n_pad, S), dtype=torch.uint8, device=dev)
+        self._stats = torch.zeros((nat.N_STATS,), dtype=torch.int64, device=dev)
+        self._pool = None
+
+        L = nat.lib()
+        cfg = nat.AstroConfig()
+        for name, _ in nat.AstroConfig._fields_[:10]:
+            setattr(cfg, name, float(getattr(config, name)))
+        cfg.solo = int(bool(config.solo))
+        handle = C.c_void_p()
+        nat.check(L.astro_batch_create(C.byref(cfg), self.n_pad, self.K, precision, self.device.index, C.byref(handle)))
+        self._h = handle
+        bufs = nat.AstroBuffers(self.ships.data_ptr(), self.ship_b.data_ptr(), self.planets.data_ptr(),
+                                self.bullets.data_ptr(), self.meta.data_ptr(), self.episode.data_ptr())
+        nat.check(L.astro_batch_bind(self._h, C.byref(bufs)))
+        self.schedule = None
+        self.set_schedule_origin(0.0, 0.0)
+        self.step_index = 0
+        nat.check(L.astro_set_stream(self._h, self.seed, self.first_game, 0))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and nat._lib is not None:
+            nat._lib.astro_batch_destroy(h)
+            self._h = None
+
+    # ---- schedule / streams -------------------------------------------------------------------
+    def set_schedule_origin(self, reload0, t0):
+        """A game's tick counter 0 corresponds to (reload0, t0); see schedule.py."""
+        if self.schedule is not None and self._origin == (reload0, t0):
+            return
+        self.schedule = Schedule(self.config, reload0, t0)
+        self._origin = (reload0, t0)
+        s = self.schedule
+        nat.check(nat.lib().astro_set_schedule(self._h, s.fire_bits.ctypes.data_as(C.c_void_p), s.n_ticks, s.timeout_tick))
+
+    def set_stream(self, seed=None, first_game=None, step=None):
+        if seed is not None:
+            self.seed = int(seed)
+        if first_game is not None:
+            self.first_game = int(first_game)
+        if step is not None:
+            self.step_index = int(step)
+        nat.check(nat.lib().astro_set_stream(self._h, self.seed, self.first_game, self.step_index))
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    # ---- state in / out -------------------------------------------------------------------------
+    def _split(self, index):
+        index = np.asarray(index, dtype=np.int64)
+        return index // nat.TILE, index % nat.TILE
+
+    def set_arrays(self, ships, planets, n_planets, bullets=None, n_bullets=None, ticks=None, index=None,
+                   episode=None):
+        """Load games from game-major host arrays: ships [m,S,5] (x,y,dx,dy,b), planets [m,4,4],
+        n_planets [m], bullets [m,<=K,4], n_bullets [m], ticks [m] (default 0)."""
+        torch = _torch()
+        ships = np.asarray(ships, dtype=self.np_rdtype)
+        m = ships.shape[0]
+        index = np.arange(m) if index is None else np.asarray(index)
+        tiles, lanes = self._split(index)
+        dev = self.device
+        tt, ll = torch.from_numpy(tiles).to(dev), torch.from_numpy(lanes).to(dev)
+        planets = np.asarray(planets, dtype=self.np_rdtype)
+        n_planets = np.asarray(n_planets, dtype=np.int64)
+        n_bullets = np.zeros(m, dtype=np.int64) if n_bullets is None else np.asarray(n_bullets, dtype=np.int64)
+        ticks = np.zeros(m, dtype=np.int64) if ticks is None else np.asarray(ticks, dtype=np.int64)
+        if n_bullets.max(initial=0) > self.K:
+            raise ValueError('a state holds more bullets than bullet_cap=%d' % self.K)
+        if ticks.max(initial=0) > nat.MAX_TICKS:
+            raise ValueError('tick counter out of range')
+        self.ships[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(ships[:, :, :4])).to(dev)
+        self.ship_b[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(ships[:, :, 4])).to(dev)
+        self.planets[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(planets)).to(dev)
+        if bullets is not None and self.K > 0:
+            bullets = np.asarray(bullets, dtype=self.np_rdtype)
+            kb = bullets.shape[1]
+            if kb:
+                self.bullets[tt, :kb, ll] = torch.from_numpy(np.ascontiguousarray(bullets)).to(dev)
+        meta = (n_bullets | (n_planets << 10) | (ticks << 14)).astype(np.uint32).view(np.int32)
+        self.meta[torch.from_numpy(index.astype(np.int64)).to(dev)] = torch.from_numpy(meta).to(dev)
+        if episode is not None:
+            ep = np.asarray(episode, dtype=np.uint32).view(np.int32)
+            self.episode[torch.from_numpy(index.astype(np.int64)).to(dev)] = torch.from_numpy(ep).to(dev)
+
+    def set_states(self, states, index=None, ticks=None):
+        """Load reference `State`s (core.py:15-18).  Without `ticks`, each state's (reload, t) must
+        lie on this batch's schedule (true for anything produced by create + step)."""
+        m, S, K = len(states), self.S, self.K
+        ships = np.zeros((m, S, 5))
+        planets = np.zeros((m, nat.MAX_PLANETS, 4))
+        n_planets = np.zeros(m, dtype=np.int64)
+        n_bullets = np.zeros(m, dtype=np.int64)
+        kmax = max([np.shape(s.bullets.x)[0] for s in states] + [0])
+        if kmax > K:
+            raise ValueError('a state holds %d bullets, bullet_cap is %d' % (kmax, K))
+        bullets = np.zeros((m, kmax, 4))
+        tk = np.zeros(m, dtype=np.int64)
+        for i, s in enumerate(states):
+            if np.shape(s.ships.x)[0] != S:
+                raise ValueError('cannot mix solo and duel games in one batch')
+            ships[i, :, 0:2], ships[i, :, 2:4], ships[i, :, 4] = s.ships.x, s.ships.dx, s.ships.b
+            p = np.shape(s.planets.x)[0]
+            if not 1 <= p <= nat.MAX_PLANETS:
+                raise ValueError('a state needs 1..%d planets' % nat.MAX_PLANETS)
+            planets[i, :p, 0:2], planets[i, :p, 2:4] = s.planets.x, s.planets.dx
+            n_planets[i] = p
+            b = np.shape(s.bullets.x)[0]
+            if b:
+                bullets[i, :b, 0:2], bullets[i, :b, 2:4] = s.bullets.x, s.bullets.dx
+            n_bullets[i] = b
+            if ticks is None:
+                k = self.schedule.tick_of(s.reload, s.t)
+                if k is None:
+                    raise ValueError('state %d: (reload=%r, t=%r) is not on the schedule of this batch; '
+                                     'use set_schedule_origin() or pass ticks=' % (i, s.reload, s.t))
+                tk[i] = k
+        if ticks is not None:
+            tk[:] = ticks
+        self.set_arrays(ships, planets, n_planets, bullets, n_bullets, tk, index)
+
+    def get_arrays(self):
+        """Whole batch as game-major float64 host arrays (the inverse of set_arrays)."""
+        n = self.n
+        meta = self.meta.cpu().numpy().view(np.uint32)[:n]
+        sh = self.ships.permute(0, 2, 1, 3).reshape(self.n_pad, self.S, 4)[:n].double().cpu().numpy()
+        sb = self.ship_b.permute(0, 2, 1).reshape(self.n_pad, self.S)[:n].double().cpu().numpy()
+        pl = self.planets.permute(0, 2, 1, 3).reshape(self.n_pad, nat.MAX_PLANETS, 4)[:n].double().cpu().numpy()
+        bl = self.bullets.permute(0, 2, 1, 3).reshape(self.n_pad, -1, 4)[:n, :self.K].double().cpu().numpy()
+        return dict(ships=np.concatenate([sh, sb[:, :, None]], axis=2), planets=pl, bullets=bl,
+                    n_bullets=(meta & 1023).astype(np.int32), n_planets=((meta >> 10) & 7).astype(np.int32),
+                    finished=((meta >> 13) & 1).astype(bool), tick=(meta >> 14).astype(np.int64),
+                    episode=self.episode.cpu().numpy().view(np.uint32)[:n].copy())
+
+    def to_state(self, i):
+        """Game i as a reference `State` (float64 arrays), or None when the game has ended."""
+        tile, lane = divmod(int(i), nat.TILE)
+        meta = int(self.meta[i].item()) & 0xFFFFFFFF
+        if (meta >> 13) & 1:
+            return None
+        nb, npl, tick = meta & 1023, (meta >> 10) & 7, meta >> 14
+        sh = self.ships[tile, :, lane].double().cpu().numpy()
+        sb = self.ship_b[tile, :, lane].double().cpu().numpy()
+        pl = self.planets[tile, :npl, lane].double().cpu().numpy()
+        bl = self.bullets[tile, :nb, lane].double().cpu().numpy().reshape(nb, 4)
+        return core.State(
+            ships=core.Bodies(x=sh[:, 0:2].copy(), dx=sh[:, 2:4].copy(), b=sb.copy()),
+            planets=core.Bodies(x=pl[:, 0:2].copy(), dx=pl[:, 2:4].copy(), b=None),
+            bullets=core.Bodies(x=bl[:, 0:2].copy(), dx=bl[:, 2:4].copy(), b=None),
+            reload=float(self.schedule.reload[tick]), t=float(self.schedule.t[tick]))
+
+    # ---- reset pool ------------------------------------------------------------------------------
+    def set_reset_pool(self, states):
+        """Initial states (built by core.create) that finished games are re-created from."""
+        torch = _torch()
+        M, S = len(states), self.S
+        ships = np.zeros((M, S, 5), dtype=self.np_rdtype)
+        planets = np.zeros((M, nat.MAX_PLANETS, 4), dtype=self.np_rdtype)
+        npl = np.zeros(M, dtype=np.int32)
+        for i, s in enumerate(states):
+            ships[i, :, 0:2], ships[i, :, 2:4], ships[i, :, 4] = s.ships.x, s.ships.dx, s.ships.b
+            p = np.shape(s.planets.x)[0]
+            planets[i, :p, 0:2], planets[i, :p, 2:4] = s.planets.x, s.planets.dx
+            npl[i] = p
+        self.set_reset_pool_arrays(ships, planets, npl)
+
+    def set_reset_pool_arrays(self, ships, planets, n_planets):
+        torch = _torch()
+        dev = self.device
+        self._pool = (torch.from_numpy(np.ascontiguousarray(ships, dtype=self.np_rdtype)).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(planets, dtype=self.np_rdtype)).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(n_planets, dtype=np.int32)).to(dev))
+        pool = nat.AstroResetPool(self._pool[0].data_ptr(), self._pool[1].data_ptr(), self._pool[2].data_ptr(),
+                                  self._pool[0].shape[0], 0)
+        nat.check(nat.lib().astro_set_reset_pool(self._h, C.byref(pool)))
+
+    def reset_done(self):
+        """Re-create every finished game from the pool (episode counter + 1 picks the entry)."""
+        if self.n != self.n_pad:
+            raise ValueError('reset_done needs n_games to be a multiple of %d' % nat.TILE)
+        nat.check(nat.lib().astro_reset_done(self._h, self._stream()))
+
+    def reset_all(self):
+        """(Re)start every game from the pool: game g starts as pool[pick(seed, g, episode 0)]."""
+        self.meta.fill_(1 << 13)
+        self.episode.fill_(-1)
+        self.reset_done()
+
+    # ---- the tick ---------------------------------------------------------------------------------
+    def step(self, actions=None, auto_reset=False, stats=True, want_reward=True):
+        """One `core.step` for every game.
+
+        actions -- None (device counter stream, rng.actions), or uint8 cuda tensor / array
+                   [n, S] of control codes 0..5.
+        returns -- (reward f32 [n,S] or None, done u8 [n], events u8 [n]): views of buffers that
+                   the next step overwrites.
+        """
+        torch = _torch()
+        if actions is None:
+            a_ptr = None
+        else:
+            if not isinstance(actions, torch.Tensor):
+                actions = torch.from_numpy(np.ascontiguousarray(actions).astype(np.uint8))
+            actions = actions.to(device=self.device, dtype=torch.uint8).reshape(-1, self.S)
+            if actions.shape[0] == self.n_pad and actions.is_contiguous():
+                a_ptr = actions.data_ptr()
+            else:
+                if actions.shape[0] != self.n:
+                    raise ValueError('actions must have shape [%d, %d]' % (self.n, self.S))
+                self._actions[:self.n].copy_(actions)
+                a_ptr = self._actions.data_ptr()
+        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS)
+        nat.check(nat.lib().astro_tick(self._h, a_ptr, self._reward.data_ptr() if want_reward else None,
+                                       self._done.data_ptr(), self._events.data_ptr(), flags, self._stream()))
+        self.step_index += 1
+        n = self.n
+        return (self._reward[:n] if want_reward else None), self._done[:n], self._events[:n]
+
+    def step_raw(self, actions_ptr, flags):
+        """Bench path: a bare astro_tick with a caller-held device pointer (or 0), events only."""
+        nat.check(nat.lib().astro_tick(self._h, actions_ptr or None, None, None, self._events.data_ptr(), flags,
+                                       self._stream()))
+        self.step_index += 1
+
+    def step_host(self, actions_host, events_host, reward_host=None, done_host=None, auto_reset=False, stats=True):
+        """End-to-end tick with HOST buffers (torch pinned tensors or numpy arrays): copies the
+        actions in, ticks, copies events (and reward/done if given) out, synchronises."""
+        def ptr(x):
+            if x is None:
+                return None
+            return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
+        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS)
+        for x, nbytes in ((actions_host, self.n_pad * self.S), (events_host, self.n_pad)):
+            if x is not None and (x.numel() * x.element_size() if hasattr(x, 'numel') else x.nbytes) < nbytes:
+                raise ValueError('host buffer too small: need %d bytes' % nbytes)
+        nat.check(nat.lib().astro_tick_host(self._h, ptr(actions_host), ptr(reward_host), ptr(done_host),
+                                            ptr(events_host), flags, self._stream()))
+        self.step_index += 1
+
+    # ---- observations ----------------------------------------------------------------------------
+    def observe(self, n_rows=None, out=None):
+        """Feature batch [n, S, n_rows, D] float32: obs[g, k] is game g seen by ship k
+        (rl.py:43-99 + core.roll_ships); rows = planets, bullets, then -1 padding."""
+        torch = _torch()
+        if n_rows is None:
+            n_rows = -(-(nat.MAX_PLANETS + self.K) // 4) * 4
+        if out is None:
+            out = torch.empty((self.n_pad, self.S, n_rows, self.D), dtype=torch.float32, device=self.device)
+        nat.check(nat.lib().astro_observe(self._h, out.data_ptr(), n_rows, self._stream()))
+        return out[:self.n]
+
+    # ---- statistics ------------------------------------------------------------------------------
+    def stats_tensor(self, clear=False):
+        """Device int64 [12] counters (see _native.STAT_NAMES) — the input of the NCCL all-reduce."""
+        nat.check(nat.lib().astro_stats(self._h, self._stats.data_ptr(), int(clear), self._stream()))
+        return self._stats
+
+    def stats(self, clear=False):
+        v = self.stats_tensor(clear).cpu().numpy()
+        return dict(zip(nat.STAT_NAMES, (int(x) for x in v)))
+
+    @property
+    def launches(self):
+        return int(nat.lib().astro_launch_count(self._h))

@@ -1,0 +1,782 @@
+// astro_b200.cu — kernels and C ABI (include/astro_b200.h) of the batched Astro game tick.
+//
+// Replaces, for N independent games at once:
+//   astro/core.py:215-303  step            -> tick_kernel   (one fused launch per tick)
+//   astro/core.py:306-327  roll_ships  }
+//   astro/rl.py:43-99      get_features } -> observe_kernel
+//                          to_batch     }
+//   astro/core.py:86-135   create (host-built pool) -> reset inside tick_kernel / reset_kernel
+//
+// Thread-per-game over 32-game tiles: every global access is a coalesced 128-bit access across
+// the warp (see the layout comment in the header).  HBM-bound; no tensor cores (no contraction).
+#include "../../include/astro_b200.h"
+#include "astro_device.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace astro;
+
+namespace {
+
+constexpr int kTickThreads = 256;
+constexpr int kObserveWarps = 8;
+
+struct TickParams {
+    void* ships;
+    void* ship_b;
+    void* planets;
+    void* bullets;
+    uint32_t* meta;
+    uint32_t* episode;
+    const uint8_t* actions;
+    float* reward;
+    uint8_t* done;
+    uint8_t* events;
+    const uint32_t* fire_bits;
+    const void* pool_ships;
+    const void* pool_planets;
+    const int32_t* pool_np;
+    unsigned long long* stats;
+    int32_t n_games, K, timeout_tick, n_sched_ticks, pool_size, flags;
+    uint32_t seed, step, first_game, pad;
+    Consts c;
+};
+
+// ------------------------------------------------------------------------------------------
+// tick_kernel<R, S, STATS>: one thread = one game, one launch = one core.step for all games.
+//
+// Phase order follows core.py:215-303: accelerations (old state) -> collisions (old state) ->
+// collision terminal -> timeout terminal -> bullet despawn -> spawn -> integrate/cull.
+// Bullets are compacted in place, front to back, by their owning thread: survivors keep the
+// reference's order (old survivors, then ship 0's and ship 1's newborn).  When a game ends, its
+// bullet slots are dead (nb = 0); ships/planets keep the pre-step state unless AUTO_RESET
+// re-initialises the slot from the pool.
+// ------------------------------------------------------------------------------------------
+template <typename R, int S, bool STATS>
+__global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constant__ TickParams p) {
+    using B4 = Body4<R>;
+    __shared__ unsigned long long s_stats[ASTRO_N_STATS];
+    if (STATS) {
+        if (threadIdx.x < ASTRO_N_STATS) s_stats[threadIdx.x] = 0ull;
+        __syncthreads();
+    }
+    const int g = blockIdx.x * kTickThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in_range = g < p.n_games;  // whole warps: n_games % 32 == 0
+    const Consts& c = p.c;
+
+    uint32_t ev = 0;
+    int np = 0, nb = 0, m_out = 0;
+    bool active = false;
+    int spawned = 0;
+
+    if (in_range) {
+        const size_t tile = (size_t)(g >> 5);
+        B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
+        R* ship_b = reinterpret_cast<R*>(p.ship_b) + tile * (S * 32) + lane;
+        B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
+        B4* bullets = reinterpret_cast<B4*>(p.bullets) + tile * ((size_t)p.K * 32) + lane;
+
+        const uint32_t meta = p.meta[g];
+        // ships are loaded before meta is inspected: independent loads, one DRAM round trip
+        B4 sh[S];
+        R sb[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            sh[s] = ships[s * 32];
+            sb[s] = ship_b[s * 32];
+        }
+        nb = (int)ASTRO_META_NB(meta);
+        np = (int)ASTRO_META_NP(meta);
+        const uint32_t tick = ASTRO_META_TICK(meta);
+        active = !ASTRO_META_FINISHED(meta);
+
+        if (!active) {
+            ev = ASTRO_EV_SKIPPED;
+            np = 0; nb = 0;
+        } else {
+            B4 pl[ASTRO_MAX_PLANETS];
+#pragma unroll
+            for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
+                if (j < np) pl[j] = planets[j * 32];
+
+            // first group of bullets in flight while the ship/planet maths runs
+            B4 bq[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (u < nb) bq[u] = bullets[u * 32];
+
+            // ---- controls (core.py:220-227,234-239)
+            int ctl[S];
+            if (p.actions) {
+                if (S == 2) {
+                    uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
+                    ctl[0] = a & 0xff;
+                    ctl[S - 1] = a >> 8;
+                } else {
+                    ctl[0] = p.actions[g];
+                }
+            } else {
+                uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
+#pragma unroll
+                for (int s = 0; s < S; s++) ctl[s] = action_from_key(h0, p.step, (uint32_t)s);
+            }
+
+            // ---- accelerations and ship collisions on the OLD state
+            float dir0[S], dir1[S];
+            R a0[S], a1[S];
+            bool hit[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                np_sincos_f32((float)sb[s], dir0[s], dir1[s]);
+                R g0 = 0, g1 = 0;
+                bool h = false;
+#pragma unroll
+                for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+                    if (j < np) {
+                        R t0, t1;
+                        grav_term(pl[j].x, pl[j].y, sh[s].x, sh[s].y, c, t0, t1);
+                        if (j == 0) { g0 = t0; g1 = t1; } else { g0 = add_rn(g0, t0); g1 = add_rn(g1, t1); }
+                        h |= collide(sh[s].x, sh[s].y, pl[j].x, pl[j].y, c.r2_sp, c.r2f_sp);
+                    }
+                }
+                R th = mul_rn(Pick<R>::thrust(c), (R)(ctl[s] & 1));
+                a0[s] = add_rn(mul_rn(th, (R)dir0[s]), g0);
+                a1[s] = add_rn(mul_rn(th, (R)dir1[s]), g1);
+                hit[s] = h;
+            }
+            if (S == 2) {
+                bool h = collide(sh[0].x, sh[0].y, sh[S - 1].x, sh[S - 1].y, c.r2_ss, c.r2f_ss);
+                hit[0] |= h;
+                hit[S - 1] |= h;
+            }
+
+            // ---- bullets: hit test on old positions, integrate, cull, compact in place
+            int m = 0;
+            for (int j0 = 0; j0 < nb; j0 += 4) {
+                B4 cur[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) cur[u] = bq[u];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (j0 + 4 + u < nb) bq[u] = bullets[(j0 + 4 + u) * 32];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j0 + u < nb) {
+                        B4 b = cur[u];
+                        bool gone = false;
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            bool h = collide(sh[s].x, sh[s].y, b.x, b.y, c.r2_sb, c.r2f_sb);
+                            hit[s] |= h;
+                            gone |= h;
+                        }
+#pragma unroll
+                        for (int k = 0; k < ASTRO_MAX_PLANETS; k++)
+                            if (k < np) gone |= collide(pl[k].x, pl[k].y, b.x, b.y, c.r2_pb, c.r2f_pb);
+                        bool keep = advance_bullet(b, c);
+                        if (keep && !gone) {
+                            bullets[m * 32] = b;
+                            m++;
+                        }
+                    }
+                }
+            }
+
+            bool any_hit = hit[0];
+            if (S == 2) any_hit |= hit[S - 1];
+            const bool timeout = tick >= (uint32_t)p.timeout_tick;
+            float rw[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) rw[s] = 0.0f;
+
+            if (any_hit) {  // core.py:253-255
+                ev = (hit[0] ? ASTRO_EV_HIT0 : 0);
+                if (S == 2) ev |= (hit[S - 1] ? ASTRO_EV_HIT1 : 0);
+#pragma unroll
+                for (int s = 0; s < S; s++) rw[s] = hit[s] ? -1.0f : 1.0f;
+            } else if (timeout) {  // core.py:257-260
+                ev = ASTRO_EV_TIMEOUT;
+#pragma unroll
+                for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
+            } else {
+                // ---- spawn from the OLD ship state (core.py:267-280); float32 products
+                const bool fire = tick < (uint32_t)p.n_sched_ticks && ((p.fire_bits[tick >> 5] >> (tick & 31)) & 1u);
+                if (fire) {
+                    ev |= ASTRO_EV_FIRED;
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        Body4<double> nbl;
+                        nbl.x = __dadd_rn((double)sh[s].x, (double)__fmul_rn(c.off_f, dir0[s]));
+                        nbl.y = __dadd_rn((double)sh[s].y, (double)__fmul_rn(c.off_f, dir1[s]));
+                        nbl.dx = __dadd_rn((double)sh[s].dx, (double)__fmul_rn(c.spd_f, dir0[s]));
+                        nbl.dy = __dadd_rn((double)sh[s].dy, (double)__fmul_rn(c.spd_f, dir1[s]));
+                        bool keep = advance_bullet(nbl, c);
+                        if (keep) {
+                            if (m < p.K) {
+                                B4 o;
+                                o.x = (R)nbl.x; o.y = (R)nbl.y; o.dx = (R)nbl.dx; o.dy = (R)nbl.dy;
+                                bullets[m * 32] = o;
+                                m++;
+                            } else {
+                                ev |= ASTRO_EV_OVERFLOW;
+                            }
+                        }
+                    }
+                    spawned = S;
+                }
+                // ---- planets (core.py:289-294): gravity of every planet on every planet, the
+                // clamped self term included (f * 0 = 0)
+                R q0[ASTRO_MAX_PLANETS], q1[ASTRO_MAX_PLANETS];
+#pragma unroll
+                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
+                    q0[i] = 0; q1[i] = 0;
+                    if (i < np) {
+#pragma unroll
+                        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+                            if (j < np) {
+                                R t0, t1;
+                                grav_term(pl[j].x, pl[j].y, pl[i].x, pl[i].y, c, t0, t1);
+                                if (j == 0) { q0[i] = t0; q1[i] = t1; } else { q0[i] = add_rn(q0[i], t0); q1[i] = add_rn(q1[i], t1); }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
+                    if (i < np) {
+                        advance_body(pl[i], q0[i], q1[i], c);
+                        planets[i * 32] = pl[i];
+                    }
+                }
+                // ---- ships (core.py:283-288)
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    advance_body(sh[s], a0[s], a1[s], c);
+                    ships[s * 32] = sh[s];
+                    R db = mul_rn(Pick<R>::db_unit(c), (R)((ctl[s] >> 1) - 1));
+                    ship_b[s * 32] = add_rn(sb[s], db);
+                }
+                p.meta[g] = ASTRO_META_PACK(m, np, 0, tick + 1);
+                m_out = m;
+            }
+
+            if (ev & ASTRO_EV_DONE_MASK) {
+                if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0) {
+                    // re-create from the pool (core.create, core.py:86-135, evaluated on the host)
+                    uint32_t ep = p.episode[g] + 1;
+                    p.episode[g] = ep;
+                    uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, ep, (uint32_t)p.pool_size);
+                    const R* ps = reinterpret_cast<const R*>(p.pool_ships) + (size_t)k * (S * 5);
+                    const R* pp = reinterpret_cast<const R*>(p.pool_planets) + (size_t)k * (ASTRO_MAX_PLANETS * 4);
+                    int np_new = p.pool_np[k];
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        B4 o;
+                        o.x = ps[5 * s]; o.y = ps[5 * s + 1]; o.dx = ps[5 * s + 2]; o.dy = ps[5 * s + 3];
+                        ships[s * 32] = o;
+                        ship_b[s * 32] = ps[5 * s + 4];
+                    }
+#pragma unroll
+                    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+                        if (j < np_new) {
+                            B4 o;
+                            o.x = pp[4 * j]; o.y = pp[4 * j + 1]; o.dx = pp[4 * j + 2]; o.dy = pp[4 * j + 3];
+                            planets[j * 32] = o;
+                        }
+                    }
+                    p.meta[g] = ASTRO_META_PACK(0, np_new, 0, 0);
+                } else {
+                    p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
+                }
+            }
+            if (p.reward) {
+                if (S == 2) {
+                    reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
+                } else {
+                    p.reward[g] = rw[0];
+                }
+            }
+        }
+        if (!active && p.reward) {
+            if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(0.f, 0.f);
+            else p.reward[g] = 0.f;
+        }
+        if (p.events) p.events[g] = (uint8_t)ev;
+        if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
+    }
+
+    if (STATS) {
+        // warp-level reductions of the per-game flags and counts, then one shared-memory atomic
+        // per counter per warp and one global atomic per counter per block
+        const unsigned full = 0xffffffffu;
+        const bool coll = (ev & (ASTRO_EV_HIT0 | ASTRO_EV_HIT1)) != 0;
+        const bool h0 = ev & ASTRO_EV_HIT0, h1 = ev & ASTRO_EV_HIT1;
+        unsigned b_done = __ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0);
+        unsigned b_w0 = __ballot_sync(full, S == 2 && coll && !h0);
+        unsigned b_w1 = __ballot_sync(full, S == 2 && coll && !h1);
+        unsigned b_both = __ballot_sync(full, coll && (S == 1 || (h0 && h1)));
+        unsigned b_to = __ballot_sync(full, (ev & ASTRO_EV_TIMEOUT) != 0);
+        unsigned b_act = __ballot_sync(full, active);
+        unsigned b_ovf = __ballot_sync(full, (ev & ASTRO_EV_OVERFLOW) != 0);
+        unsigned b_skip = __ballot_sync(full, (ev & ASTRO_EV_SKIPPED) != 0);
+        unsigned n_spawn = __reduce_add_sync(full, (unsigned)spawned);
+        unsigned n_np = __reduce_add_sync(full, (unsigned)np);
+        unsigned n_in = __reduce_add_sync(full, (unsigned)nb);
+        unsigned n_out = __reduce_add_sync(full, (unsigned)m_out);
+        if (lane == 0) {
+            atomicAdd(&s_stats[0], (unsigned long long)__popc(b_done));
+            atomicAdd(&s_stats[1], (unsigned long long)__popc(b_w0));
+            atomicAdd(&s_stats[2], (unsigned long long)__popc(b_w1));
+            atomicAdd(&s_stats[3], (unsigned long long)__popc(b_both));
+            atomicAdd(&s_stats[4], (unsigned long long)__popc(b_to));
+            atomicAdd(&s_stats[5], (unsigned long long)__popc(b_act));
+            atomicAdd(&s_stats[6], (unsigned long long)n_spawn);
+            atomicAdd(&s_stats[7], (unsigned long long)__popc(b_ovf));
+            atomicAdd(&s_stats[8], (unsigned long long)n_np);
+            atomicAdd(&s_stats[9], (unsigned long long)n_in);
+            atomicAdd(&s_stats[10], (unsigned long long)n_out);
+            atomicAdd(&s_stats[11], (unsigned long long)__popc(b_skip));
+        }
+        __syncthreads();
+        if (threadIdx.x < ASTRO_N_STATS && s_stats[threadIdx.x]) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// reset_kernel: stand-alone form of AUTO_RESET — finished games are re-created from the pool.
+// ------------------------------------------------------------------------------------------
+template <typename R, int S>
+__global__ void __launch_bounds__(kTickThreads) reset_kernel(const __grid_constant__ TickParams p) {
+    using B4 = Body4<R>;
+    const int g = blockIdx.x * kTickThreads + threadIdx.x;
+    if (g >= p.n_games) return;
+    const uint32_t meta = p.meta[g];
+    if (!ASTRO_META_FINISHED(meta)) return;
+    const size_t tile = (size_t)(g >> 5);
+    const int lane = g & 31;
+    B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
+    R* ship_b = reinterpret_cast<R*>(p.ship_b) + tile * (S * 32) + lane;
+    B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
+    uint32_t ep = p.episode[g] + 1;
+    p.episode[g] = ep;
+    uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, ep, (uint32_t)p.pool_size);
+    const R* ps = reinterpret_cast<const R*>(p.pool_ships) + (size_t)k * (S * 5);
+    const R* pp = reinterpret_cast<const R*>(p.pool_planets) + (size_t)k * (ASTRO_MAX_PLANETS * 4);
+    int np_new = p.pool_np[k];
+    for (int s = 0; s < S; s++) {
+        B4 o;
+        o.x = ps[5 * s]; o.y = ps[5 * s + 1]; o.dx = ps[5 * s + 2]; o.dy = ps[5 * s + 3];
+        ships[s * 32] = o;
+        ship_b[s * 32] = ps[5 * s + 4];
+    }
+    for (int j = 0; j < np_new; j++) {
+        B4 o;
+        o.x = pp[4 * j]; o.y = pp[4 * j + 1]; o.dx = pp[4 * j + 2]; o.dy = pp[4 * j + 3];
+        planets[j * 32] = o;
+    }
+    p.meta[g] = ASTRO_META_PACK(0, np_new, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// observe_kernel<R, S>: one warp = one game.  The warp stages the game's feature rows
+// (rl.py:43-72: [flag | every ship's x,y,dx,dy,norm_angle(b)/pi | object x,y,dx,dy]) in shared
+// memory — lane r builds row r — then streams both perspectives (core.roll_ships: ship columns
+// rotated) to HBM as coalesced 128-bit stores; rows beyond P+B are the -1 padding of to_batch
+// (rl.py:91-98).
+// ------------------------------------------------------------------------------------------
+template <typename R, int S>
+__global__ void __launch_bounds__(kObserveWarps * 32)
+observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_, const void* __restrict__ planets_,
+               const void* __restrict__ bullets_, const uint32_t* __restrict__ meta_, float* __restrict__ obs,
+               int n_games, int K, int n_rows) {
+    using B4 = Body4<R>;
+    constexpr int D = 1 + 5 * S + 4;
+    extern __shared__ float s_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kObserveWarps + warp;
+    if (g >= n_games) return;
+    float* rows = s_all + (size_t)warp * ((size_t)n_rows * D + 5 * S);
+    float* sf = rows + (size_t)n_rows * D;  // ship features, ship 0 first
+
+    const size_t tile = (size_t)(g >> 5);
+    const int gl = g & 31;
+    const uint32_t meta = meta_[g];
+    const bool fin = ASTRO_META_FINISHED(meta);
+    const int np = fin ? 0 : (int)ASTRO_META_NP(meta);
+    const int nb = fin ? 0 : (int)ASTRO_META_NB(meta);
+
+    if (lane < S && !fin) {
+        B4 s = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + lane * 32 + gl];
+        R b = reinterpret_cast<const R*>(ship_b_)[tile * (S * 32) + lane * 32 + gl];
+        sf[5 * lane + 0] = (float)s.x;
+        sf[5 * lane + 1] = (float)s.y;
+        sf[5 * lane + 2] = (float)s.dx;
+        sf[5 * lane + 3] = (float)s.dy;
+        sf[5 * lane + 4] = norm_angle_over_pi((double)b);
+    }
+    __syncwarp();
+    const B4* planets = reinterpret_cast<const B4*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32) + gl;
+    const B4* bullets = reinterpret_cast<const B4*>(bullets_) + tile * ((size_t)K * 32) + gl;
+    for (int r = lane; r < n_rows; r += 32) {
+        float* row = rows + r * D;
+        if (r < np + nb) {
+            B4 o = r < np ? planets[r * 32] : bullets[(r - np) * 32];
+            row[0] = r < np ? 0.0f : 1.0f;
+#pragma unroll
+            for (int k = 0; k < 5 * S; k++) row[1 + k] = sf[k];
+            row[1 + 5 * S + 0] = (float)o.x;
+            row[1 + 5 * S + 1] = (float)o.y;
+            row[1 + 5 * S + 2] = (float)o.dx;
+            row[1 + 5 * S + 3] = (float)o.dy;
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; k++) row[k] = -1.0f;
+        }
+    }
+    __syncwarp();
+    // stream out: perspective 0 is the staged block; perspective 1 swaps the ship columns
+    const int per = n_rows * D;  // % 4 == 0 (checked on the host)
+    float4* out = reinterpret_cast<float4*>(obs + (size_t)g * S * per);
+    const float4* src4 = reinterpret_cast<const float4*>(rows);
+    for (int q = lane; q < per / 4; q += 32) out[q] = src4[q];
+    if (S == 2) {
+        float4* out1 = out + per / 4;
+        const int live = (np + nb) * D;
+        for (int q = lane; q < per / 4; q += 32) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int idx = 4 * q + e;
+                int col = idx % D;
+                int srci = idx;
+                if (idx < live) {
+                    if (col >= 1 && col <= 5) srci = idx + 5;
+                    else if (col >= 6 && col <= 10) srci = idx - 5;
+                }
+                v[e] = rows[srci];
+            }
+            out1[q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) return fail(ASTRO_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+}  // namespace
+
+struct AstroBatch {
+    AstroConfig cfg;
+    int32_t n_games, K, precision, device, S;
+    bool bound;
+    AstroBuffers bufs;
+    AstroResetPool pool;
+    uint32_t* d_fire_bits;
+    int32_t n_sched_ticks, timeout_tick;
+    unsigned long long* d_stats;
+    uint8_t* d_actions;  // staging for astro_tick_host
+    uint8_t* d_events;
+    uint8_t* d_done;
+    float* d_reward;
+    uint32_t seed, step;
+    int64_t first_game;
+    int64_t launches;
+    Consts c;
+};
+
+namespace {
+
+void fill_consts(const AstroConfig& cfg, Consts& c) {
+    // Python-float expressions of the reference, evaluated once in float64
+    c.gm = cfg.gravity * cfg.planet_mass;
+    c.dt = cfg.dt;
+    c.thrust = cfg.ship_thrust;
+    c.db_unit = cfg.dt * cfg.ship_rspeed;
+    c.zero_dt = 0.0 * cfg.dt;
+    const double rs = cfg.ship_radius, rp = cfg.planet_radius;
+    c.r2_ss = (rs + rs) * (rs + rs);
+    c.r2_sp = (rp + rs) * (rp + rs);
+    c.r2_sb = (0.0 + rs) * (0.0 + rs);
+    c.r2_pb = (0.0 + rp) * (0.0 + rp);
+    c.off_f = (float)(1.001 * cfg.ship_radius);
+    c.spd_f = (float)cfg.bullet_speed;
+    c.gm_f = (float)c.gm;
+    c.dt_f = (float)c.dt;
+    c.thrust_f = (float)c.thrust;
+    c.db_unit_f = (float)c.db_unit;
+    c.r2f_ss = (float)c.r2_ss;
+    c.r2f_sp = (float)c.r2_sp;
+    c.r2f_sb = (float)c.r2_sb;
+    c.r2f_pb = (float)c.r2_pb;
+    c.reward_timeout = cfg.solo ? 1.0f : 0.0f;
+}
+
+int check(const AstroBatch* b, bool need_bound) {
+    if (!b) return fail(ASTRO_E_INVALID, "null batch handle");
+    if (need_bound && !b->bound) return fail(ASTRO_E_STATE, "astro_batch_bind has not been called");
+    return ASTRO_OK;
+}
+
+void fill_params(const AstroBatch* b, TickParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.ships = b->bufs.ships;
+    p.ship_b = b->bufs.ship_b;
+    p.planets = b->bufs.planets;
+    p.bullets = b->bufs.bullets;
+    p.meta = b->bufs.meta;
+    p.episode = b->bufs.episode;
+    p.fire_bits = b->d_fire_bits;
+    p.pool_ships = b->pool.ships;
+    p.pool_planets = b->pool.planets;
+    p.pool_np = b->pool.np;
+    p.pool_size = b->pool.size;
+    p.stats = b->d_stats;
+    p.n_games = b->n_games;
+    p.K = b->K;
+    p.timeout_tick = b->timeout_tick;
+    p.n_sched_ticks = b->n_sched_ticks;
+    p.seed = b->seed;
+    p.step = b->step;
+    p.first_game = (uint32_t)b->first_game;
+    p.c = b->c;
+}
+
+template <typename R, int S>
+cudaError_t launch_tick(const TickParams& p, cudaStream_t st) {
+    const int grid = (p.n_games + kTickThreads - 1) / kTickThreads;
+    if (p.flags & ASTRO_TICK_NO_STATS)
+        tick_kernel<R, S, false><<<grid, kTickThreads, 0, st>>>(p);
+    else
+        tick_kernel<R, S, true><<<grid, kTickThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+int do_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t flags,
+            cudaStream_t st) {
+    if (b->n_sched_ticks <= 0) return fail(ASTRO_E_STATE, "astro_set_schedule has not been called");
+    if ((flags & ASTRO_TICK_AUTO_RESET) && b->pool.size <= 0)
+        return fail(ASTRO_E_STATE, "ASTRO_TICK_AUTO_RESET needs astro_set_reset_pool");
+    TickParams p;
+    fill_params(b, p);
+    p.actions = actions;
+    p.reward = reward;
+    p.done = done;
+    p.events = events;
+    p.flags = flags;
+    cudaError_t e;
+    if (b->precision == 32)
+        e = b->S == 2 ? launch_tick<float, 2>(p, st) : launch_tick<float, 1>(p, st);
+    else
+        e = b->S == 2 ? launch_tick<double, 2>(p, st) : launch_tick<double, 1>(p, st);
+    if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "tick_kernel launch: %s", cudaGetErrorString(e));
+    b->step += 1;
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int astro_abi_version(void) { return ASTRO_ABI_VERSION; }
+
+const char* astro_last_error(void) { return g_err; }
+
+int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_cap, int32_t precision,
+                       int32_t device, AstroBatch** out) {
+    if (!cfg || !out) return fail(ASTRO_E_INVALID, "null argument");
+    if (n_games <= 0 || n_games % ASTRO_TILE) return fail(ASTRO_E_INVALID, "n_games must be a positive multiple of %d", ASTRO_TILE);
+    if (bullet_cap < 0 || bullet_cap > ASTRO_MAX_BULLET_CAP) return fail(ASTRO_E_INVALID, "bullet_cap out of range 0..%d", ASTRO_MAX_BULLET_CAP);
+    if (precision != 32 && precision != 64) return fail(ASTRO_E_INVALID, "precision must be 32 or 64");
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(ASTRO_E_INVALID, "device %d out of range (%d visible)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    AstroBatch* b = new (std::nothrow) AstroBatch();
+    if (!b) return fail(ASTRO_E_NOMEM, "out of host memory");
+    memset(b, 0, sizeof(*b));
+    b->cfg = *cfg;
+    b->n_games = n_games;
+    b->K = bullet_cap;
+    b->precision = precision;
+    b->device = device;
+    b->S = cfg->solo ? 1 : 2;
+    fill_consts(*cfg, b->c);
+    cudaError_t e = cudaMalloc(&b->d_stats, sizeof(unsigned long long) * ASTRO_N_STATS);
+    if (e == cudaSuccess) e = cudaMemset(b->d_stats, 0, sizeof(unsigned long long) * ASTRO_N_STATS);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_actions, (size_t)n_games * b->S);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_events, (size_t)n_games);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_done, (size_t)n_games);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_reward, sizeof(float) * (size_t)n_games * b->S);
+    if (e != cudaSuccess) {
+        astro_batch_destroy(b);
+        return fail(ASTRO_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return ASTRO_OK;
+}
+
+int astro_batch_destroy(AstroBatch* b) {
+    if (!b) return ASTRO_OK;
+    cudaSetDevice(b->device);
+    cudaFree(b->d_stats);
+    cudaFree(b->d_actions);
+    cudaFree(b->d_events);
+    cudaFree(b->d_done);
+    cudaFree(b->d_reward);
+    cudaFree(b->d_fire_bits);
+    delete b;
+    return ASTRO_OK;
+}
+
+int astro_batch_bind(AstroBatch* b, const AstroBuffers* bufs) {
+    if (int r = check(b, false)) return r;
+    if (!bufs || !bufs->ships || !bufs->ship_b || !bufs->planets || !bufs->meta || !bufs->episode ||
+        (b->K > 0 && !bufs->bullets))
+        return fail(ASTRO_E_INVALID, "null buffer pointer");
+    const uintptr_t al = (uintptr_t)(b->precision == 32 ? 16 : 32);
+    if (((uintptr_t)bufs->ships | (uintptr_t)bufs->planets | (uintptr_t)bufs->bullets) & (al - 1))
+        return fail(ASTRO_E_INVALID, "ships/planets/bullets must be %d-byte aligned", (int)al);
+    b->bufs = *bufs;
+    b->bound = true;
+    return ASTRO_OK;
+}
+
+int astro_set_schedule(AstroBatch* b, const uint32_t* fire_bits_host, int32_t n_ticks, int32_t timeout_tick) {
+    if (int r = check(b, false)) return r;
+    if (!fire_bits_host || n_ticks <= 0 || n_ticks > ASTRO_MAX_TICKS + 1 || timeout_tick < 0 || timeout_tick >= n_ticks)
+        return fail(ASTRO_E_INVALID, "bad schedule (n_ticks %d, timeout_tick %d, max %d)", n_ticks, timeout_tick, ASTRO_MAX_TICKS);
+    CUDA_TRY(cudaSetDevice(b->device));
+    if (b->d_fire_bits) CUDA_TRY(cudaFree(b->d_fire_bits));
+    b->d_fire_bits = nullptr;
+    const size_t words = ((size_t)n_ticks + 31) / 32;
+    CUDA_TRY(cudaMalloc(&b->d_fire_bits, words * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpy(b->d_fire_bits, fire_bits_host, words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    b->n_sched_ticks = n_ticks;
+    b->timeout_tick = timeout_tick;
+    return ASTRO_OK;
+}
+
+int astro_set_stream(AstroBatch* b, uint32_t seed, int64_t first_game, uint32_t step) {
+    if (int r = check(b, false)) return r;
+    b->seed = seed;
+    b->first_game = first_game;
+    b->step = step;
+    return ASTRO_OK;
+}
+
+int astro_set_reset_pool(AstroBatch* b, const AstroResetPool* pool) {
+    if (int r = check(b, false)) return r;
+    if (!pool || pool->size <= 0 || !pool->ships || !pool->planets || !pool->np)
+        return fail(ASTRO_E_INVALID, "bad reset pool");
+    b->pool = *pool;
+    return ASTRO_OK;
+}
+
+int astro_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events,
+               int32_t flags, void* stream) {
+    if (int r = check(b, true)) return r;
+    CUDA_TRY(cudaSetDevice(b->device));
+    return do_tick(b, actions, reward, done, events, flags, (cudaStream_t)stream);
+}
+
+int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_host, uint8_t* done_host,
+                    uint8_t* events_host, int32_t flags, void* stream) {
+    if (int r = check(b, true)) return r;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)b->n_games;
+    if (actions_host) CUDA_TRY(cudaMemcpyAsync(b->d_actions, actions_host, n * b->S, cudaMemcpyHostToDevice, st));
+    if (int r = do_tick(b, actions_host ? b->d_actions : nullptr, reward_host ? b->d_reward : nullptr,
+                        done_host ? b->d_done : nullptr, events_host ? b->d_events : nullptr, flags, st))
+        return r;
+    if (events_host) CUDA_TRY(cudaMemcpyAsync(events_host, b->d_events, n, cudaMemcpyDeviceToHost, st));
+    if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, b->d_done, n, cudaMemcpyDeviceToHost, st));
+    if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, b->d_reward, n * b->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ASTRO_OK;
+}
+
+int astro_reset_done(AstroBatch* b, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (b->pool.size <= 0) return fail(ASTRO_E_STATE, "astro_set_reset_pool has not been called");
+    CUDA_TRY(cudaSetDevice(b->device));
+    TickParams p;
+    fill_params(b, p);
+    const int grid = (p.n_games + kTickThreads - 1) / kTickThreads;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b->precision == 32) {
+        if (b->S == 2) reset_kernel<float, 2><<<grid, kTickThreads, 0, st>>>(p);
+        else reset_kernel<float, 1><<<grid, kTickThreads, 0, st>>>(p);
+    } else {
+        if (b->S == 2) reset_kernel<double, 2><<<grid, kTickThreads, 0, st>>>(p);
+        else reset_kernel<double, 1><<<grid, kTickThreads, 0, st>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
+int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!obs) return fail(ASTRO_E_INVALID, "null obs");
+    const int D = 1 + 5 * b->S + 4;
+    if (n_rows < ASTRO_MAX_PLANETS + b->K) return fail(ASTRO_E_INVALID, "n_rows %d < 4 + bullet_cap %d", n_rows, b->K);
+    if ((n_rows * D) % 4) return fail(ASTRO_E_INVALID, "n_rows * %d must be a multiple of 4", D);
+    if ((uintptr_t)obs & 15) return fail(ASTRO_E_INVALID, "obs must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(b->device));
+    const size_t smem = (size_t)kObserveWarps * ((size_t)n_rows * D + 5 * b->S) * sizeof(float);
+    if (smem > 200 * 1024) return fail(ASTRO_E_INVALID, "n_rows %d too large for the staging buffer", n_rows);
+    const int grid = (b->n_games + kObserveWarps - 1) / kObserveWarps;
+    cudaStream_t st = (cudaStream_t)stream;
+    const AstroBuffers& u = b->bufs;
+#define LAUNCH_OBS(R, S_)                                                                                        \
+    do {                                                                                                         \
+        CUDA_TRY(cudaFuncSetAttribute(observe_kernel<R, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        observe_kernel<R, S_><<<grid, kObserveWarps * 32, smem, st>>>(u.ships, u.ship_b, u.planets, u.bullets, u.meta, \
+                                                                      obs, b->n_games, b->K, n_rows);             \
+    } while (0)
+    if (b->precision == 32) {
+        if (b->S == 2) LAUNCH_OBS(float, 2); else LAUNCH_OBS(float, 1);
+    } else {
+        if (b->S == 2) LAUNCH_OBS(double, 2); else LAUNCH_OBS(double, 1);
+    }
+#undef LAUNCH_OBS
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
+int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream) {
+    if (int r = check(b, false)) return r;
+    if (!counters_dev) return fail(ASTRO_E_INVALID, "null counters");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(counters_dev, b->d_stats, sizeof(int64_t) * ASTRO_N_STATS, cudaMemcpyDeviceToDevice, st));
+    if (clear) CUDA_TRY(cudaMemsetAsync(b->d_stats, 0, sizeof(int64_t) * ASTRO_N_STATS, st));
+    return ASTRO_OK;
+}
+
+int64_t astro_launch_count(const AstroBatch* b) { return b ? b->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+"""Observation extraction of `astro.rl.ValueNetwork` (reference: astro/rl.py:36-112) over the
+CUDA observe kernel.
+
+    ValueNetwork.get_features(state)         -> float32 [P+B, 1+5S+4]
+    ValueNetwork.to_batch(list of features)  -> float32 [n, max rows, D], -1 padded
+    ValueNetwork.get_features_batch(states)  -> the two combined
+
+Rows are planets then bullets (array order); column 0 is the type flag (0 planet / 1 bullet,
+-1 padding: consumers mask on `features[..., 0] < 0`, rl.py:126-128); columns 1..5S hold every
+ship's (x, y, dx, dy, norm_angle(b)/pi), ship 0 first; the last 4 the object's (x, y, dx, dy).
+For rollouts use `BatchedGames.observe()` directly: it writes the padded batch for every game
+and both perspectives in one launch and never leaves the GPU.
+"""
+import numpy as np
+
+from . import core
+from .batched import BatchedGames
+
+_CACHE = {}
+
+
+def _games(solo, n, cap):
+    n_pad = max(32, -(-n // 32) * 32)
+    key = (bool(solo), n_pad, cap)
+    g = _CACHE.get(key)
+    if g is None:
+        cfg = core.SOLO_CONFIG if solo else core.DEFAULT_CONFIG
+        g = _CACHE[key] = BatchedGames(cfg, n_pad, bullet_cap=cap, precision=64)
+    return g
+
+
+class ValueNetwork:
+    """Feature half of the reference's ValueNetwork; the torch network itself is unchanged
+    reference code and consumes these batches."""
+
+    @staticmethod
+    def get_features_shape(state):
+        return (state.planets.x.shape[0] + state.bullets.x.shape[0], 1 + 4 + 5 * state.ships.x.shape[0])
+
+    @classmethod
+    def get_features_batch(cls, states, perspective=0):
+        if not states:
+            raise ValueError('no states')
+        nships = {np.shape(s.ships.x)[0] for s in states}
+        if len(nships) != 1:
+            raise ValueError('Feature dimensions do not match - cannot mix solo & nonsolo games in a single batch')
+        solo = nships.pop() == 1
+        kmax = max(np.shape(s.bullets.x)[0] for s in states)
+        cap = max(32, -(-kmax // 32) * 32)
+        g = _games(solo, len(states), cap)
+        g.meta.fill_(1 << 13)
+        g.set_states(list(states), ticks=np.zeros(len(states), dtype=np.int64))
+        rows = max(np.shape(s.planets.x)[0] + np.shape(s.bullets.x)[0] for s in states)
+        obs = g.observe()[:len(states), perspective, :rows]
+        return obs.cpu().numpy()
+
+    @classmethod
+    def get_features(cls, state):
+        n_rows, _ = cls.get_features_shape(state)
+        return cls.get_features_batch([state])[0, :n_rows]
+
+    @staticmethod
+    def to_batch(features):
+        """Pad a list of [N_i, D] feature arrays to [n, max N_i, D] with -1 (rl.py:75-99)."""
+        if any(f.shape[1] != features[0].shape[1] for f in features):
+            raise ValueError('Feature dimensions do not match - cannot mix solo & nonsolo games in a single batch')
+        out = np.full((len(features), max(f.shape[0] for f in features), features[0].shape[1]), -1, dtype=np.float32)
+        for i, f in enumerate(features):
+            out[i, :f.shape[0]] = f
+        return out

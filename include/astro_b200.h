@@ -1,0 +1,165 @@
+/*
+ * astro_b200.h — C ABI of the B200-native batched Astro game tick.
+ *
+ * The reference (DouglasOrr/Astro) has no FFI layer: its boundary for this path is the
+ * Python game API of astro/core.py (create/step/roll_ships/play) and
+ * astro/rl.py ValueNetwork.get_features, get_features_batch and to_batch.  This header is the C-ABI a maintainer
+ * would bind (ctypes) to replace the bodies of those functions with the
+ * CUDA path; each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ASTRO_E_* code; no C++ exception
+ *     crosses the ABI; astro_last_error() gives the message of the calling thread's last
+ *     failure.
+ *   - all state memory is OWNED BY THE CALLER (PyTorch tensors in practice) and bound with
+ *     astro_batch_bind(); pointers must stay valid while bound.
+ *   - kernels are enqueued on the caller's CUDA stream (cudaStream_t passed as void*); calls
+ *     are asynchronous unless the name ends in _host.  One handle per device; a handle is not
+ *     re-entrant.
+ *   - one Config per batch (the reference also passes one config per game loop).
+ *
+ * Device data layout ("tiles"): games are grouped in tiles of ASTRO_TILE = 32 consecutive
+ * games (one warp).  R is float (precision 32) or double (precision 64); R4 = {x, y, dx, dy}.
+ *     ships    R4  [n_tiles][S][32]      ship s of game g  -> ((g/32)*S + s)*32 + g%32
+ *     ship_b   R   [n_tiles][S][32]      bearing
+ *     planets  R4  [n_tiles][4][32]      slots >= np are dead
+ *     bullets  R4  [n_tiles][K][32]      slots >= nb are dead; order = reference order
+ *     meta     u32 [n_tiles*32]          nb (bits 0-9) | np (10-12) | finished (13) | tick (14-31)
+ *     episode  u32 [n_tiles*32]          games finished in this slot (reset-pool stream key)
+ * A thread owns one game, so every load/store above is a fully coalesced 128-bit (R=float)
+ * access across the warp.
+ */
+#ifndef ASTRO_B200_H
+#define ASTRO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASTRO_ABI_VERSION 1
+#define ASTRO_TILE 32
+#define ASTRO_MAX_SHIPS 2
+#define ASTRO_MAX_PLANETS 4
+#define ASTRO_MAX_BULLET_CAP 1023
+#define ASTRO_MAX_TICKS 262143 /* 18-bit per-game tick counter */
+
+/* meta word */
+#define ASTRO_META_NB(m) ((m) & 1023u)
+#define ASTRO_META_NP(m) (((m) >> 10) & 7u)
+#define ASTRO_META_FINISHED(m) (((m) >> 13) & 1u)
+#define ASTRO_META_TICK(m) ((m) >> 14)
+#define ASTRO_META_PACK(nb, np, fin, tick) \
+    ((uint32_t)(nb) | ((uint32_t)(np) << 10) | ((uint32_t)(fin) << 13) | ((uint32_t)(tick) << 14))
+
+/* per-game event bits written by astro_tick (u8 per game) */
+#define ASTRO_EV_HIT0 1      /* ship 0 collided   (core.py:253-255) */
+#define ASTRO_EV_HIT1 2      /* ship 1 collided */
+#define ASTRO_EV_TIMEOUT 4   /* max_time reached  (core.py:257-260) */
+#define ASTRO_EV_FIRED 8     /* ships fired this tick (core.py:267-280) */
+#define ASTRO_EV_OVERFLOW 16 /* a newborn bullet was dropped: pool full */
+#define ASTRO_EV_SKIPPED 32  /* game was already finished; nothing done */
+#define ASTRO_EV_DONE_MASK 7
+
+/* astro_tick flags */
+#define ASTRO_TICK_AUTO_RESET 1 /* a game that ends is re-initialised from the reset pool in the same launch */
+#define ASTRO_TICK_NO_STATS 2   /* skip the astro_stats counters for this tick */
+
+/* error codes */
+#define ASTRO_OK 0
+#define ASTRO_E_INVALID (-1)
+#define ASTRO_E_CUDA (-2)
+#define ASTRO_E_STATE (-3)
+#define ASTRO_E_NOMEM (-4)
+
+/* World part of the reference Config (core.py:20-41; defaults core.py:52-74). */
+typedef struct AstroConfig {
+    double gravity, dt, max_time, reload_time, bullet_speed, ship_thrust, ship_rspeed, ship_radius,
+        planet_mass, planet_radius;
+    int32_t solo; /* 1 -> one ship per game */
+    int32_t reserved;
+} AstroConfig;
+
+/* Device pointers of the caller-owned state (layout above). */
+typedef struct AstroBuffers {
+    void* ships;
+    void* ship_b;
+    void* planets;
+    void* bullets;
+    uint32_t* meta;
+    uint32_t* episode;
+} AstroBuffers;
+
+/* Reset pool: M initial states built by create() (core.py:86-135) on the host, in device
+ * memory, game-major: ships R [M][S][5] = x,y,dx,dy,b ; planets R [M][4][4] ; np i32 [M]. */
+typedef struct AstroResetPool {
+    const void* ships;
+    const void* planets;
+    const int32_t* np;
+    int32_t size;
+    int32_t reserved;
+} AstroResetPool;
+
+#define ASTRO_N_STATS 12
+/* astro_stats counters (int64 each), summed over every astro_tick since the last clear:
+ *  0 episodes  1 wins0  2 wins1  3 both_lost (or solo crash)  4 timeouts  5 env_steps
+ *  6 bullets_spawned  7 overflow  8 planets_live (sum of np over env-steps)
+ *  9 bullets_in (sum of nb read)  10 bullets_out (sum of nb written)  11 skipped        */
+
+typedef struct AstroBatch AstroBatch;
+
+int astro_abi_version(void);
+const char* astro_last_error(void);
+
+/* Batch lifetime.  n_games is rounded up to whole tiles by the caller: n_games % 32 == 0.
+ * precision: 32 (float state; predicates exact via fp64 fallback) or 64 (double state, the
+ * validation build: bit-identical to the reference's float64 arithmetic). */
+int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_cap, int32_t precision,
+                       int32_t device, AstroBatch** out);
+int astro_batch_destroy(AstroBatch* b);
+int astro_batch_bind(AstroBatch* b, const AstroBuffers* bufs);
+
+/* reload / t are Python-float accumulators in the reference (core.py:257-280,302): a pure
+ * function of the tick index.  The host evaluates them once, in the reference's arithmetic,
+ * and hands over: bit k of fire_bits = "ships fire on a game's k-th tick", and the tick index
+ * on which the timeout terminal fires.  n_ticks = timeout_tick + 1. */
+int astro_set_schedule(AstroBatch* b, const uint32_t* fire_bits_host, int32_t n_ticks, int32_t timeout_tick);
+
+/* Counter-stream keys (astro_b200/rng.py): controls when actions == NULL, reset-pool picks. */
+int astro_set_stream(AstroBatch* b, uint32_t seed, int64_t first_game, uint32_t step);
+int astro_set_reset_pool(AstroBatch* b, const AstroResetPool* pool);
+
+/* core.step (core.py:215-303) for every game of the batch: one fused kernel.
+ *   actions  u8 [n_games][S] device, control codes 0..5 (core.py:220-227); NULL -> counter stream
+ *   reward   f32 [n_games][S] device or NULL   (core.py:255,260,303)
+ *   done     u8 [n_games] device or NULL       (reference returns state None)
+ *   events   u8 [n_games] device or NULL       (ASTRO_EV_*)
+ * Each call advances the batch's stream step by one. */
+int astro_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events,
+               int32_t flags, void* stream);
+
+/* Same call with HOST buffers (pinned for full speed): H2D actions, tick, D2H events (and
+ * reward/done when not NULL), then synchronises the stream. */
+int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_host, uint8_t* done_host,
+                    uint8_t* events_host, int32_t flags, void* stream);
+
+/* Re-initialise finished games from the reset pool (the stand-alone form of AUTO_RESET). */
+int astro_reset_done(AstroBatch* b, void* stream);
+
+/* rl.ValueNetwork.get_features + to_batch (rl.py:43-99) with core.roll_ships (core.py:306-327)
+ * for both perspectives: obs f32 [n_games][S][n_rows][1+5S+4] device; rows = planets then
+ * bullets, the rest filled with -1; n_rows >= 4 + bullet_cap.  Finished games: all -1. */
+int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream);
+
+/* Copies the ASTRO_N_STATS device counters into counters_dev (device pointer, e.g. the input of
+ * an NCCL all-reduce) on the stream; clear != 0 zeroes them afterwards. */
+int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream);
+
+/* Launch bookkeeping for bench.py: kernels launched by this handle since creation. */
+int64_t astro_launch_count(const AstroBatch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,437 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden
+vectors of the reference.  Bar: every discrete outcome (done, hit flags, timeout, fire ticks,
+bullet counts and order, rewards) bit-exact; continuous state bit-exact in the float64
+validation build and within |d| <= 1e-5 * max(1, |ref|) per tick in the float32 build
+(north-star tolerance; measured errors are ~1e-7)."""
+import collections
+import json
+import os
+
+import numpy as np
+import pytest
+
+from astro_b200 import core, rng
+from astro_b200 import _native as nat
+from oracle import astro_oracle as ao
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _games(*a, **k):
+    from astro_b200.batched import BatchedGames
+    return BatchedGames(*a, **k)
+
+
+def _close(got, ref):
+    return np.abs(got - ref) <= TOL * np.maximum(1.0, np.abs(ref))
+
+
+# ------------------------------------------------------------------ golden trajectories, f64
+
+def test_golden_trajectories_f64_free_running():
+    """All 39 reference games, replayed free-running from tick 0 in the float64 build: every
+    pre-step state, reward and terminal matches the reference bit for bit."""
+    z, meta = H.load_traj()
+    groups = collections.defaultdict(list)
+    for m in meta:
+        groups[tuple(sorted((k, v) for k, v in m['config'].items() if k != 'seed'))].append(m)
+    checked = 0
+    for _, ms in groups.items():
+        cfg = H.config_from(ms[0]['config'])
+        S = ms[0]['nships']
+        n = len(ms)
+        games = _games(cfg, n, bullet_cap=32, precision=64)
+        off = {m['game']: np.concatenate([[0], np.cumsum(z['g%d_nb' % m['game']])]) for m in ms}
+        games.set_states([H.state_from_arrays(z['g%d_ships' % m['game']][0], z['g%d_planets' % m['game']][0],
+                                              np.zeros((0, 4)), 0.0, 0.0) for m in ms])
+        T = max(m['nticks'] for m in ms)
+        for k in range(T):
+            arr = games.get_arrays()
+            ctl = np.full((n, S), 2, dtype=np.uint8)
+            for i, m in enumerate(ms):
+                g = m['game']
+                if k >= m['nticks']:
+                    continue
+                P, B = m['nplanets'], int(z['g%d_nb' % g][k])
+                assert not arr['finished'][i] and arr['n_bullets'][i] == B and arr['n_planets'][i] == P, (g, k)
+                assert H.same_bits(arr['ships'][i], z['g%d_ships' % g][k]), (g, k)
+                assert H.same_bits(arr['planets'][i, :P], z['g%d_planets' % g][k]), (g, k)
+                assert H.same_bits(arr['bullets'][i, :B], z['g%d_bullets' % g][off[g][k]:off[g][k + 1]]), (g, k)
+                assert games.schedule.reload[arr['tick'][i]] == z['g%d_reload' % g][k]
+                assert games.schedule.t[arr['tick'][i]] == z['g%d_t' % g][k]
+                ctl[i] = z['g%d_control' % g][k]
+                checked += 1
+            reward, done, events = games.step(ctl)
+            reward, done = reward.cpu().numpy(), done.cpu().numpy()
+            for i, m in enumerate(ms):
+                g = m['game']
+                if k >= m['nticks']:
+                    continue
+                assert H.same_bits(reward[i], z['g%d_reward' % g][k]), (g, k)
+                assert bool(done[i]) == (k == m['nticks'] - 1 and not m['truncated']), (g, k)
+            if k == T - 1:
+                arr = games.get_arrays()
+                for i, m in enumerate(ms):
+                    g = m['game']
+                    if m['truncated'] and m['nticks'] == T:
+                        assert H.same_bits(arr['ships'][i], z['g%d_final_ships' % g])
+                        B = arr['n_bullets'][i]
+                        assert H.same_bits(arr['bullets'][i, :B], z['g%d_final_bullets' % g].reshape(-1, 4))
+    assert checked > 6000
+
+
+def test_golden_edges_f64_through_core_step():
+    """70 single-step knife-edge / precedence cases through the drop-in core.step."""
+    z = np.load(os.path.join(H.G, 'edges.npz'))
+    meta = json.load(open(os.path.join(H.G, 'edges.json')))
+    for c in meta:
+        i = c['case']
+        cfg = H.config_from(c['config'])
+        state = H.state_from_arrays(z['c%d_ships' % i], z['c%d_planets' % i], z['c%d_bullets' % i], c['reload'], c['t'])
+        nxt, reward = core.step(state, np.array(c['control']), cfg)
+        assert (nxt is None) == c['done'], c['name']
+        assert H.same_bits(reward, c['reward']), c['name']
+        if nxt is not None:
+            o = z['c%d_o_ships' % i]
+            assert H.same_bits(nxt.ships.x, o[:, 0:2]) and H.same_bits(nxt.ships.dx, o[:, 2:4]), c['name']
+            assert H.same_bits(nxt.ships.b, o[:, 4]), c['name']
+            o = z['c%d_o_planets' % i]
+            assert H.same_bits(nxt.planets.x, o[:, 0:2]) and H.same_bits(nxt.planets.dx, o[:, 2:4]), c['name']
+            o = z['c%d_o_bullets' % i].reshape(-1, 4)
+            assert H.same_bits(nxt.bullets.x, o[:, 0:2]) and H.same_bits(nxt.bullets.dx, o[:, 2:4]), c['name']
+            assert nxt.reload == c['o_reload'] and nxt.t == c['o_t'], c['name']
+
+
+def test_golden_edges_f32_discrete():
+    """The same cases in the float32 build (inputs rounded to float32, oracle fed the rounded
+    inputs): done / reward / bullet count exact, state within tolerance."""
+    z = np.load(os.path.join(H.G, 'edges.npz'))
+    meta = json.load(open(os.path.join(H.G, 'edges.json')))
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    for c in meta:
+        i = c['case']
+        cfg = H.config_from(c['config'])
+        S = 1 if cfg.solo else 2
+        sh, pl, bl = f32(z['c%d_ships' % i]), f32(z['c%d_planets' % i]), f32(z['c%d_bullets' % i]).reshape(-1, 4)
+        games = _games(cfg, 32, bullet_cap=32, precision=32)
+        games.set_schedule_origin(c['reload'], c['t'])
+        games.set_states([H.state_from_arrays(sh, pl, bl, c['reload'], c['t'])], ticks=[0])
+        ref = ao.step_one(cfg, sh, pl, bl, c['reload'], c['t'], c['control'], bullet_cap=32)
+        reward, done, events = games.step(np.array(c['control']).reshape(1, S))
+        assert bool(done[0].item()) == ref['done'], c['name']
+        assert (reward[0].cpu().numpy().astype(np.float64) == ref['reward']).all(), c['name']
+        assert int(events[0].item()) == ref['events'], c['name']
+        if not ref['done']:
+            arr = games.get_arrays()
+            B = ref['bullets'].shape[0]
+            assert arr['n_bullets'][0] == B, c['name']
+            assert _close(arr['ships'][0], ref['ships']).all(), c['name']
+            assert _close(arr['planets'][0, :pl.shape[0]], ref['planets']).all(), c['name']
+            assert _close(arr['bullets'][0, :B], ref['bullets']).all(), c['name']
+
+
+# ------------------------------------------------------------------ config #2: 4,096 games
+
+def _teacher_forced(cfg, N, K, ticks, precision, pool_size=512, seed=0, first_game=0, start=None):
+    """GPU tick vs oracle, the oracle re-fed the GPU's state every tick; auto-reset on."""
+    S = 1 if cfg.solo else 2
+    pool = H.make_pool(cfg, pool_size)
+    games = _games(cfg, N, bullet_cap=K, precision=precision, seed=seed, first_game=first_game)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    if start is not None:
+        start(games)
+    rpool = {k: (v.astype(games.np_rdtype).astype(np.float64) if v.dtype != np.int32 else v) for k, v in pool.items()}
+    ids = first_game + np.arange(N)
+    arr = games.get_arrays()
+    if start is None:
+        pick = rng.pool_pick(seed, ids, np.zeros(N, dtype=np.uint32), pool_size)
+        assert (arr['episode'] == 0).all() and (arr['ships'] == rpool['ships'][pick]).all()
+        assert (arr['n_planets'] == rpool['np'][pick]).all() and (arr['n_bullets'] == 0).all()
+    worst = 0.0
+    n_done = n_fired = 0
+    for k in range(ticks):
+        ob, alive = H.oracle_batch_from(arr, S, K)
+        ob.reload[:] = games.schedule.reload[arr['tick']]
+        ob.t[:] = games.schedule.t[arr['tick']]
+        ctl = rng.actions(seed, ids, k, S)
+        o2, rew, done, ev = ao.step_batch(cfg, ob, ctl, alive)
+        r_gpu, d_gpu, e_gpu = games.step(None, auto_reset=True)
+        r_gpu, d_gpu, e_gpu = r_gpu.cpu().numpy(), d_gpu.cpu().numpy(), e_gpu.cpu().numpy()
+        assert (e_gpu == ev).all(), (k, np.nonzero(e_gpu != ev)[0][:8], e_gpu[e_gpu != ev][:8], ev[e_gpu != ev][:8])
+        assert (d_gpu == done).all(), k
+        assert (r_gpu.astype(np.float64) == rew).all(), k
+        new = games.get_arrays()
+        live = done == 0
+        assert (new['n_bullets'][live] == o2.nb[live]).all(), k
+        assert (new['tick'][live] == arr['tick'][live] + 1).all(), k
+        assert (new['n_planets'][live] == arr['n_planets'][live]).all(), k
+        pm = (np.arange(4)[None, :] < o2.np_[:, None])[live]
+        bm = (np.arange(K)[None, :] < o2.nb[:, None])[live]
+        for name, got, ref, mask in (('ships', new['ships'][live], o2.ships[live], None),
+                                     ('planets', new['planets'][live], o2.planets[live], pm),
+                                     ('bullets', new['bullets'][live], o2.bullets[live], bm)):
+            if mask is not None:
+                got, ref = got[mask], ref[mask]
+            if precision == 64:
+                assert (H.bits(got) == H.bits(ref)).all(), (k, name)
+            else:
+                err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+                if err.size:
+                    worst = max(worst, float(err.max()))
+                assert (err <= TOL).all(), (k, name, float(err.max()))
+        # games that ended were re-created from the pool in the same launch
+        dead = ~live
+        if dead.any():
+            ep = arr['episode'][dead] + 1
+            pick = rng.pool_pick(seed, ids[dead], ep, pool_size)
+            assert (new['episode'][dead] == ep).all(), k
+            assert (new['ships'][dead] == rpool['ships'][pick]).all(), k
+            assert (new['n_planets'][dead] == rpool['np'][pick]).all(), k
+            assert (new['n_bullets'][dead] == 0).all() and (new['tick'][dead] == 0).all(), k
+            for j, p in zip(np.nonzero(dead)[0], pick):
+                P = rpool['np'][p]
+                assert (new['planets'][j, :P] == rpool['planets'][p, :P]).all(), k
+        n_done += int(dead.sum())
+        n_fired += int(((ev & nat.EV_FIRED) != 0).sum())
+        arr = new
+    return games, worst, n_done, n_fired
+
+
+def test_config2_4096_games_f32_teacher_forced():
+    """BASELINE config #2: 4,096 duel games, random actions, default planets, 1,000 ticks:
+    discrete outcomes bit-exact against the oracle on identical inputs, continuous within 1e-5."""
+    games, worst, n_done, n_fired = _teacher_forced(core.DEFAULT_CONFIG, 4096, 32, 1000, 32)
+    assert n_done > 20000 and n_fired > 100000
+    assert worst < 2e-6, worst
+    st = games.stats()
+    assert st['env_steps'] == 4096 * 1000 and st['episodes'] == n_done
+    assert st['episodes'] == st['wins0'] + st['wins1'] + st['both_lost'] + st['timeouts']
+    assert st['overflow'] == 0 and st['bullets_spawned'] == 2 * n_fired
+
+
+def test_4096_games_f64_teacher_forced_bit_exact():
+    _teacher_forced(core.DEFAULT_CONFIG, 2048, 32, 300, 64)
+
+
+def test_solo_games_both_builds():
+    """Solo configs: one ship, no firing (reload_time=1000), timeout counts as a win."""
+    cfg = core.SOLO_CONFIG._replace(max_time=3)
+    for prec in (32, 64):
+        games, worst, n_done, n_fired = _teacher_forced(cfg, 1024, 32, 200, prec, pool_size=128)
+        assert n_fired == 0 and n_done > 0
+        assert games.stats()['timeouts'] > 0
+
+
+def test_f64_free_running_rollout_matches_oracle_rollout():
+    """400 ticks free-running (no teacher) with auto-reset: float64 build == oracle rollout,
+    bit for bit, and the device counters equal the oracle's."""
+    cfg, N, K, T, M = core.DEFAULT_CONFIG, 2048, 32, 400, 256
+    pool = H.make_pool(cfg, M)
+    games = _games(cfg, N, bullet_cap=K, precision=64, seed=5, first_game=1000)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    ob, _ = H.oracle_batch_from(games.get_arrays(), 2, K)
+    for _ in range(T):
+        games.step(None, auto_reset=True)
+    stats = ao.rollout(cfg, ob, pool, 5, 1000, 0, T, threads=4)
+    arr = games.get_arrays()
+    assert (arr['n_bullets'] == ob.nb).all() and (arr['episode'] == ob.episode).all()
+    assert (H.bits(arr['ships']) == H.bits(ob.ships)).all()
+    bm = np.arange(K)[None, :] < ob.nb[:, None]
+    assert (H.bits(arr['bullets'][bm]) == H.bits(ob.bullets[bm])).all()
+    pm = np.arange(4)[None, :] < ob.np_[:, None]
+    assert (H.bits(arr['planets'][pm]) == H.bits(ob.planets[pm])).all()
+    assert (games.schedule.t[arr['tick']] == ob.t).all() and (games.schedule.reload[arr['tick']] == ob.reload).all()
+    st = games.stats()
+    for i, name in enumerate(nat.STAT_NAMES[:8]):
+        assert st[name] == stats[i], name
+
+
+# ------------------------------------------------------------------ config #3: 65,536 games, full pools
+
+def _stress_fill(K, seed):
+    def fill(games):
+        r = np.random.RandomState(seed)
+        n = games.n
+        arr = games.get_arrays()
+        bl = np.concatenate([r.uniform(-1.3, 1.3, (n, K, 2)), r.uniform(-2.0, 2.0, (n, K, 2))], axis=2)
+        # a share of bullets parked exactly at / next to the arena bound and inside planets
+        edge = r.rand(n, K) < 0.05
+        bl[..., 0][edge] = np.where(r.rand(int(edge.sum())) < 0.5, 1.0, -1.0)
+        nb = r.randint(0, K + 1, n)
+        nb[r.rand(n) < 0.5] = K
+        # every 8th game: a full pool parked in a quiet corner (nothing despawns) -> overflow on fire ticks
+        quiet = np.arange(n) % 8 == 0
+        q = int(quiet.sum())
+        bl[quiet] = np.concatenate([0.95 + r.uniform(-0.01, 0.01, (q, K, 1)), r.uniform(-0.01, 0.01, (q, K, 1)),
+                                    np.zeros((q, K, 2))], axis=2)
+        nb[quiet] = K
+        ticks = r.randint(0, 40, n)       # spread over fire ticks (14, 29)
+        games.set_arrays(arr['ships'], arr['planets'], arr['n_planets'], bl, nb, ticks)
+    return fill
+
+
+@pytest.mark.parametrize('K', [400, 32])
+def test_config3_65536_games_max_bullet_pool(K):
+    """BASELINE config #3: 65,536 games with pre-filled bullet pools (K=400 is the lossless
+    bound of the default config, K=32 the production cap): despawn, spawn at capacity, cull and
+    compaction order checked element-wise against the oracle for several ticks."""
+    N = 65536 if K == 32 else 16384
+    games, worst, n_done, n_fired = _teacher_forced(core.DEFAULT_CONFIG, N, K, 6, 32, start=_stress_fill(K, 3))
+    assert n_done > 0 and n_fired > 0
+    st = games.stats()
+    assert st['overflow'] > 0 and st['bullets_in'] > st['bullets_out']
+
+
+def test_small_cap_overflow_policy():
+    """K=4: newborn bullets beyond the cap are dropped from the end and flagged."""
+    games, _, _, _ = _teacher_forced(core.DEFAULT_CONFIG, 2048, 4, 120, 32)
+    assert games.stats()['overflow'] > 0
+
+
+# ------------------------------------------------------------------ observations
+
+def test_observe_matches_oracle_features():
+    """observe() == get_features + roll_ships + to_batch for every game and both perspectives,
+    float32 bit-exact (rl.py:43-99)."""
+    cfg, N, K = core.DEFAULT_CONFIG, 2048, 32
+    for prec in (32, 64):
+        pool = H.make_pool(cfg, 256)
+        games = _games(cfg, N, bullet_cap=K, precision=prec, seed=1)
+        games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        games.reset_all()
+        for _ in range(90):
+            games.step(None, auto_reset=True)
+        games.step(None, auto_reset=False)       # leaves a few finished games behind
+        arr = games.get_arrays()
+        obs = games.observe().cpu().numpy()
+        assert obs.shape == (N, 2, 36, 15) and obs.dtype == np.float32
+        assert arr['finished'].any()
+        for g in range(N):
+            for me in range(2):
+                if arr['finished'][g]:
+                    assert (obs[g, me] == -1).all()
+                    continue
+                P, B = arr['n_planets'][g], arr['n_bullets'][g]
+                ref = ao.features(2, arr['ships'][g], arr['planets'][g, :P], arr['bullets'][g, :B], me, 36)
+                assert (obs[g, me].view(np.uint32) == ref.view(np.uint32)).all(), (prec, g, me)
+
+
+def test_features_api_matches_golden():
+    """astro_b200.rl.ValueNetwork.get_features / get_features_batch vs the reference's outputs."""
+    from astro_b200 import rl
+    z, meta = H.load_traj()
+    f = np.load(os.path.join(H.G, 'features.npz'))
+    fm = json.load(open(os.path.join(H.G, 'features.json')))
+    for e in fm[:12]:
+        g = e['game']
+        nb = z['g%d_nb' % g]
+        off = np.concatenate([[0], np.cumsum(nb)])
+        states = [H.state_from_arrays(z['g%d_ships' % g][k], z['g%d_planets' % g][k],
+                                      z['g%d_bullets' % g][off[k]:off[k + 1]], 0.0, 0.0) for k in e['ticks']]
+        for k, s in zip(e['ticks'], states):
+            got = rl.ValueNetwork.get_features(s)
+            ref = f['g%d_t%d_f0' % (g, k)]
+            assert got.shape == ref.shape and (got.view(np.uint32) == ref.view(np.uint32)).all(), (g, k)
+            if e['nships'] == 2:
+                got = rl.ValueNetwork.get_features(core.roll_ships(s, 1))
+                assert (got.view(np.uint32) == f['g%d_t%d_f1' % (g, k)].view(np.uint32)).all(), (g, k)
+        got = rl.ValueNetwork.get_features_batch(states)
+        assert (got.view(np.uint32) == f['g%d_batch' % g].view(np.uint32)).all(), g
+        assert (rl.ValueNetwork.to_batch([rl.ValueNetwork.get_features(s) for s in states]) == got).all()
+
+
+# ------------------------------------------------------------------ full-size properties
+
+def _events_digest(games, ticks, auto_reset=True):
+    import torch
+    acc = torch.zeros(games.n, dtype=torch.int64, device=games.device)
+    for k in range(ticks):
+        _, _, ev = games.step(None, auto_reset=auto_reset, want_reward=False)
+        acc = acc * 31 + ev.to(torch.int64) + 1
+    return acc
+
+
+def test_full_size_properties_1M_games():
+    """BASELINE config #4 size on one GPU (1,048,576 games): conservation laws of the device
+    counters, determinism, and shard-independence (a game's trajectory depends only on its
+    global id, not on which shard holds it)."""
+    cfg, N, K, T = core.DEFAULT_CONFIG, 1 << 20, 32, 150
+    pool = H.make_pool(cfg, 1024)
+
+    def run(n, first):
+        games = _games(cfg, n, bullet_cap=K, precision=32, seed=9, first_game=first)
+        games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        games.reset_all()
+        return games, _events_digest(games, T)
+
+    games, dig = run(N, 0)
+    st = games.stats()
+    assert st['env_steps'] == N * T and st['skipped'] == 0
+    assert st['episodes'] == st['wins0'] + st['wins1'] + st['both_lost'] + st['timeouts']
+    assert st['episodes'] > N // 2
+    arr_nb = (games.meta.cpu().numpy().view(np.uint32) & 1023).astype(np.int64)
+    # every bullet written by one tick is read by the next (games that end write none)
+    assert st['bullets_in'] == st['bullets_out'] - int(arr_nb.sum())
+    assert st['overflow'] == 0
+    _, dig2 = run(N, 0)
+    assert bool((dig == dig2).all())
+    half = N // 2
+    _, lo = run(half, 0)
+    _, hi = run(half, half)
+    assert bool((dig[:half] == lo).all()) and bool((dig[half:] == hi).all())
+
+
+# ------------------------------------------------------------------ drop-in API (reference tests)
+
+class _Nothing(core.Bot):
+    def __call__(self, state):
+        return 2
+
+
+def test_create_step_roll_like_reference():
+    """astro/test/test_core.py:20-52 against the drop-in module."""
+    import itertools as it
+    for base in (core.DEFAULT_CONFIG, core.SOLO_CONFIG, core.SOLO_EASY_CONFIG):
+        for config in it.islice(core.generate_configs(base), 4):
+            state = core.create(config)
+            nships = 1 if config.solo else 2
+            assert state.ships.x.shape == (nships, 2) and state.ships.b.shape == (nships,)
+            assert 1 <= state.planets.x.shape[0] <= config.max_planets
+            assert state.planets.b is None and state.bullets.b is None
+            nxt, reward = core.step(state, np.full(nships, 2), config)
+            assert nxt is not None and (reward == 0).all() and reward.shape == (nships,)
+            assert nxt.ships.x.shape == state.ships.x.shape and nxt.t == config.dt
+            rolled = core.roll_ships(nxt, nships - 1)
+            assert rolled.ships.x.shape == nxt.ships.x.shape
+            assert core.roll_ships(None, 0) is None
+
+
+def test_play_solo_easy_and_log_roundtrip(tmp_path):
+    """astro/test/test_core.py:55-64: a passive ship always falls into the planet."""
+    game = core.play(core.SOLO_EASY_CONFIG, [_Nothing()])
+    assert game.winner is None and len(game.ticks) > 10
+    path = str(tmp_path / 'log' / 'game.jsonl')
+    core.save_log(path, game)
+    back = core.load_log(path)
+    assert back.config == game.config and back.winner == game.winner and len(back.ticks) == len(game.ticks)
+    for a, b in zip(back.ticks, game.ticks):
+        assert np.array_equal(a.state.ships.x, b.state.ships.x) and np.array_equal(a.reward, b.reward)
+
+
+def test_abi_errors_are_reported_not_thrown():
+    import ctypes as C
+    L = nat.lib()
+    cfg = nat.AstroConfig()
+    h = C.c_void_p()
+    assert L.astro_batch_create(C.byref(cfg), 33, 32, 32, 0, C.byref(h)) == -1
+    assert b'multiple of 32' in L.astro_last_error()
+    assert L.astro_batch_create(C.byref(cfg), 32, 32, 16, 0, C.byref(h)) == -1
+    assert L.astro_batch_create(C.byref(cfg), 32, 32, 32, 0, C.byref(h)) == 0
+    assert L.astro_tick(h, None, None, None, None, 0, None) == -3      # not bound
+    assert b'bind' in L.astro_last_error()
+    assert L.astro_batch_destroy(h) == 0
