@@ -111,7 +111,7 @@ def step(state, control, config):
     key = _world_key(config) + (cap,)
     games = _SINGLE.get(key)
     if games is None:
-        games = _SINGLE[key] = BatchedGames(config, 32, bullet_cap=cap, precision=64)
+        games = _SINGLE[key] = BatchedGames(config, 1, bullet_cap=cap, precision=64)
     games.set_schedule_origin(state.reload, state.t)
     games.set_states([state], ticks=[0])
     reward, done, events = games.step(control.reshape(1, nships))

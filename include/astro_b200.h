@@ -65,6 +65,7 @@ extern "C" {
 /* astro_tick flags */
 #define ASTRO_TICK_AUTO_RESET 1 /* a game that ends is re-initialised from the reset pool in the same launch */
 #define ASTRO_TICK_NO_STATS 2   /* skip the astro_stats counters for this tick */
+#define ASTRO_TICK_GENERIC_KERNEL 4 /* precision 32 only: run the un-tuned template kernel (A/B checks) */
 
 /* error codes */
 #define ASTRO_OK 0

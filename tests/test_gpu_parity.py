@@ -116,7 +116,7 @@ def test_golden_edges_f32_discrete():
         cfg = H.config_from(c['config'])
         S = 1 if cfg.solo else 2
         sh, pl, bl = f32(z['c%d_ships' % i]), f32(z['c%d_planets' % i]), f32(z['c%d_bullets' % i]).reshape(-1, 4)
-        games = _games(cfg, 32, bullet_cap=32, precision=32)
+        games = _games(cfg, 1, bullet_cap=32, precision=32)
         games.set_schedule_origin(c['reload'], c['t'])
         games.set_states([H.state_from_arrays(sh, pl, bl, c['reload'], c['t'])], ticks=[0])
         ref = ao.step_one(cfg, sh, pl, bl, c['reload'], c['t'], c['control'], bullet_cap=32)
