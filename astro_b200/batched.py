@@ -47,7 +47,7 @@ class BatchedGames:
         self.ships = torch.zeros((T, S, 32, 4), dtype=self.rdtype, device=dev)
         self.ship_b = torch.zeros((T, S, 32), dtype=self.rdtype, device=dev)
         self.planets = torch.zeros((T, nat.MAX_PLANETS, 32, 4), dtype=self.rdtype, device=dev)
-        self.bullets = torch.zeros((T, max(K, 1), 32, 4), dtype=self.rdtype, device=dev)
+        self.bullets = torch.zeros((self.n_pad, max(K, 1), 4), dtype=self.rdtype, device=dev)   # game-major
         # every slot starts finished (empty); meta = nb | np<<10 | finished<<13 | tick<<14
         self.meta = torch.full((self.n_pad,), 1 << 13, dtype=torch.int32, device=dev)
         self.episode = torch.zeros((self.n_pad,), dtype=torch.int32, device=dev)
@@ -133,7 +133,8 @@ class BatchedGames:
             bullets = np.asarray(bullets, dtype=self.np_rdtype)
             kb = bullets.shape[1]
             if kb:
-                self.bullets[tt, :kb, ll] = torch.from_numpy(np.ascontiguousarray(bullets)).to(dev)
+                self.bullets[torch.from_numpy(index.astype(np.int64)).to(dev), :kb] = \
+                    torch.from_numpy(np.ascontiguousarray(bullets)).to(dev)
         meta = (n_bullets | (n_planets << 10) | (ticks << 14)).astype(np.uint32).view(np.int32)
         self.meta[torch.from_numpy(index.astype(np.int64)).to(dev)] = torch.from_numpy(meta).to(dev)
         if episode is not None:
@@ -183,7 +184,7 @@ class BatchedGames:
         sh = self.ships.permute(0, 2, 1, 3).reshape(self.n_pad, self.S, 4)[:n].double().cpu().numpy()
         sb = self.ship_b.permute(0, 2, 1).reshape(self.n_pad, self.S)[:n].double().cpu().numpy()
         pl = self.planets.permute(0, 2, 1, 3).reshape(self.n_pad, nat.MAX_PLANETS, 4)[:n].double().cpu().numpy()
-        bl = self.bullets.permute(0, 2, 1, 3).reshape(self.n_pad, -1, 4)[:n, :self.K].double().cpu().numpy()
+        bl = self.bullets[:n, :self.K].double().cpu().numpy()
         return dict(ships=np.concatenate([sh, sb[:, :, None]], axis=2), planets=pl, bullets=bl,
                     n_bullets=(meta & 1023).astype(np.int32), n_planets=((meta >> 10) & 7).astype(np.int32),
                     finished=((meta >> 13) & 1).astype(bool), tick=(meta >> 14).astype(np.int64),
@@ -199,7 +200,7 @@ class BatchedGames:
         sh = self.ships[tile, :, lane].double().cpu().numpy()
         sb = self.ship_b[tile, :, lane].double().cpu().numpy()
         pl = self.planets[tile, :npl, lane].double().cpu().numpy()
-        bl = self.bullets[tile, :nb, lane].double().cpu().numpy().reshape(nb, 4)
+        bl = self.bullets[int(i), :nb].double().cpu().numpy().reshape(nb, 4)
         return core.State(
             ships=core.Bodies(x=sh[:, 0:2].copy(), dx=sh[:, 2:4].copy(), b=sb.copy()),
             planets=core.Bodies(x=pl[:, 0:2].copy(), dx=pl[:, 2:4].copy(), b=None),

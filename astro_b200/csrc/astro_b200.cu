@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
         B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
         R* ship_b = reinterpret_cast<R*>(p.ship_b) + tile * (S * 32) + lane;
         B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
-        B4* bullets = reinterpret_cast<B4*>(p.bullets) + tile * ((size_t)p.K * 32) + lane;
+        B4* bullets = reinterpret_cast<B4*>(p.bullets) + (size_t)g * p.K;
 
         const uint32_t meta = p.meta[g];
         // ships are loaded before meta is inspected: independent loads, one DRAM round trip
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
             B4 bq[4];
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (u < nb) bq[u] = bullets[u * 32];
+                if (u < nb) bq[u] = bullets[u];
 
             // ---- controls (core.py:220-227,234-239)
             int ctl[S];
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                 for (int u = 0; u < 4; u++) cur[u] = bq[u];
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    if (j0 + 4 + u < nb) bq[u] = bullets[(j0 + 4 + u) * 32];
+                    if (j0 + 4 + u < nb) bq[u] = bullets[j0 + 4 + u];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (j0 + u < nb) {
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                             if (k < np) gone |= collide(pl[k].x, pl[k].y, b.x, b.y, c.r2_pb, c.r2f_pb);
                         bool keep = advance_bullet(b, c);
                         if (keep && !gone) {
-                            bullets[m * 32] = b;
+                            bullets[m] = b;
                             m++;
                         }
                     }
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                             if (m < p.K) {
                                 B4 o;
                                 o.x = (R)nbl.x; o.y = (R)nbl.y; o.dx = (R)nbl.dx; o.dy = (R)nbl.dy;
-                                bullets[m * 32] = o;
+                                bullets[m] = o;
                                 m++;
                             } else {
                                 ev |= ASTRO_EV_OVERFLOW;
@@ -360,312 +360,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
 }
 
 
-// ------------------------------------------------------------------------------------------
-// tick_f32_kernel<S, STATS>: the production tick.  Same phases and the same results policy as
-// tick_kernel<float> (fp32 state, reference-exact predicates) with the bullet loop cut to the
-// bone: per bullet the squared distances to both ships and to four planet slots (dead slots
-// hold a far-away sentinel, no predication) are reduced with min, and ONE band test per group
-// decides whether the fp32 comparison is provably the reference's float64 result; only a
-// bullet inside a band (|d2 - R2| <= 1e-6 R2, or |x'| within 4e-6 of the arena bound) takes
-// the float64 path.  A ship hit always takes it, so per-ship flags are exact.
-// ------------------------------------------------------------------------------------------
-constexpr float kFar = 1.0e18f;  // dead planet slot: d2 = 2e36, finite in fp32, never a minimum
-
-// Exact (reference float64) evaluation of one bullet against the OLD ship / planet positions:
-// despawn flags, per-ship hit bits, advance + cull.  Out of line: taken by ~1e-5 of bullets.
-// Everything travels by value (registers) so the hot loop keeps nothing in local memory.
-struct ExactResult {
-    float x, y;
-    unsigned flags;  // bit 0 keep, bits 1-2 ship hits
-};
-__device__ __noinline__ ExactResult bullet_exact(float bx, float by, float bdx, float bdy, float sx0, float sy0,
-                                                 float sx1, float sy1, float px0, float py0, float px1, float py1,
-                                                 float px2, float py2, float px3, float py3, int n_ships, int np,
-                                                 const Consts* cp) {
-    const Consts& c = *cp;
-    unsigned ship_hits = 0;
-    if (collide_exact((double)sx0, (double)sy0, (double)bx, (double)by, c.r2_sb)) ship_hits |= 1u;
-    if (n_ships > 1 && collide_exact((double)sx1, (double)sy1, (double)bx, (double)by, c.r2_sb)) ship_hits |= 2u;
-    bool gone = ship_hits != 0;
-    gone |= collide_exact((double)px0, (double)py0, (double)bx, (double)by, c.r2_pb);  // np >= 1
-    if (np > 1) gone |= collide_exact((double)px1, (double)py1, (double)bx, (double)by, c.r2_pb);
-    if (np > 2) gone |= collide_exact((double)px2, (double)py2, (double)bx, (double)by, c.r2_pb);
-    if (np > 3) gone |= collide_exact((double)px3, (double)py3, (double)bx, (double)by, c.r2_pb);
-    double v0 = __dadd_rn((double)bdx, c.zero_dt), v1 = __dadd_rn((double)bdy, c.zero_dt);
-    double e0 = __dadd_rn((double)bx, __dmul_rn(c.dt, v0)), e1 = __dadd_rn((double)by, __dmul_rn(c.dt, v1));
-    ExactResult r;
-    r.x = (float)e0;
-    r.y = (float)e1;
-    r.flags = ((in_arena(e0, e1) && !gone) ? 1u : 0u) | (ship_hits << 1);
-    return r;
-}
-
-template <int S>
-struct OldFrame {  // what the bullet loop reads: OLD positions only
-    float sx[S], sy[S];
-    float px[ASTRO_MAX_PLANETS], py[ASTRO_MAX_PLANETS];
-};
-
-template <int S>
-__device__ __forceinline__ bool bullet_step(Body4<float>& b, const OldFrame<S>& f, int np, const Consts& c,
-                                            unsigned& ship_hits) {
-    float ds = 3.0e38f, dp = 3.0e38f;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-        float d0 = __fsub_rn(f.sx[s], b.x), d1 = __fsub_rn(f.sy[s], b.y);
-        ds = fminf(ds, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
-    }
-#pragma unroll
-    for (int k = 0; k < ASTRO_MAX_PLANETS; k++) {
-        float d0 = __fsub_rn(f.px[k], b.x), d1 = __fsub_rn(f.py[k], b.y);
-        dp = fminf(dp, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
-    }
-    float x0 = __fmaf_rn(c.dt_f, b.dx, b.x), x1 = __fmaf_rn(c.dt_f, b.dy, b.y);
-    float a0 = fabsf(x0), a1 = fabsf(x1);
-    float edge = fminf(fabsf(a0 - 1.0f), fabsf(a1 - 1.0f));
-    bool unsure = (ds < c.r2f_sb * 1.000001f) | (fabsf(dp - c.r2f_pb) <= c.r2f_pb * 1e-6f) | (edge <= 4e-6f);
-    bool keep = ((a0 <= 1.0f) | (a1 <= 1.0f)) & (dp >= c.r2f_pb);
-    if (__builtin_expect(unsure, 0)) {
-        ExactResult r = bullet_exact(b.x, b.y, b.dx, b.dy, f.sx[0], f.sy[0], f.sx[S - 1], f.sy[S - 1], f.px[0], f.py[0],
-                                     f.px[1], f.py[1], f.px[2], f.py[2], f.px[3], f.py[3], S, np, &c);
-        x0 = r.x;
-        x1 = r.y;
-        keep = r.flags & 1u;
-        ship_hits |= r.flags >> 1;
-    }
-    b.x = x0;
-    b.y = x1;
-    return keep;
-}
-
-template <int S, bool STATS>
-__global__ void __launch_bounds__(kTickThreads, 4) tick_f32_kernel(const __grid_constant__ TickParams p) {
-    using B4 = Body4<float>;
-    __shared__ unsigned long long s_stats[ASTRO_N_STATS];
-    if (STATS) {
-        if (threadIdx.x < ASTRO_N_STATS) s_stats[threadIdx.x] = 0ull;
-        __syncthreads();
-    }
-    const int g = blockIdx.x * kTickThreads + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const Consts& c = p.c;
-    uint32_t ev = 0;
-    int np = 0, nb = 0, m_out = 0, spawned = 0;
-    bool active = false;
-
-    if (g < p.n_games) {
-        const size_t tile = (size_t)(g >> 5);
-        B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
-        float* ship_b = reinterpret_cast<float*>(p.ship_b) + tile * (S * 32) + lane;
-        B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
-        B4* bullets = reinterpret_cast<B4*>(p.bullets) + tile * ((size_t)p.K * 32) + lane;
-
-        const uint32_t meta = p.meta[g];
-        nb = (int)ASTRO_META_NB(meta);
-        np = (int)ASTRO_META_NP(meta);
-        const uint32_t tick = ASTRO_META_TICK(meta);
-        active = !ASTRO_META_FINISHED(meta);
-
-        if (!active) {
-            ev = ASTRO_EV_SKIPPED;
-            np = 0;
-            nb = 0;
-            if (p.reward) {
-                if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(0.f, 0.f);
-                else p.reward[g] = 0.f;
-            }
-        } else {
-            unsigned hits = 0;
-            int m = 0;
-            // ================= phase A: bullets against the OLD positions, compacted in place
-            {
-                B4 bq[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (u < nb) bq[u] = bullets[u * 32];
-                OldFrame<S> f;
-#pragma unroll
-                for (int s = 0; s < S; s++) {
-                    float2 xy = *reinterpret_cast<const float2*>(&ships[s * 32]);
-                    f.sx[s] = xy.x; f.sy[s] = xy.y;
-                }
-#pragma unroll
-                for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
-                    float2 xy = make_float2(kFar, kFar);
-                    if (j < np) xy = *reinterpret_cast<const float2*>(&planets[j * 32]);
-                    f.px[j] = xy.x; f.py[j] = xy.y;
-                }
-                for (int j0 = 0; j0 < nb; j0 += 4) {
-                    B4 cur[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) cur[u] = bq[u];
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (j0 + 4 + u < nb) bq[u] = bullets[(j0 + 4 + u) * 32];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (j0 + u < nb) {
-                            B4 b = cur[u];
-                            if (bullet_step<S>(b, f, np, c, hits)) {
-                                bullets[m * 32] = b;
-                                m++;
-                            }
-                        }
-                    }
-                }
-            }
-            // ================= phase B: ships and planets (their lines are L1-resident by now)
-            B4 sh[S];
-            float sb[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                sh[s] = ships[s * 32];
-                sb[s] = ship_b[s * 32];
-            }
-            B4 pl[ASTRO_MAX_PLANETS];
-#pragma unroll
-            for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
-                if (j < np) pl[j] = planets[j * 32];
-            int ctl[S];
-            if (p.actions) {
-                if (S == 2) {
-                    uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
-                    ctl[0] = a & 0xff;
-                    ctl[S - 1] = a >> 8;
-                } else {
-                    ctl[0] = p.actions[g];
-                }
-            } else {
-                uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
-#pragma unroll
-                for (int s = 0; s < S; s++) ctl[s] = action_from_key(h0, p.step, (uint32_t)s);
-            }
-            // direction, gravity, ship-planet and ship-ship collisions on the old state
-            float dir0[S], dir1[S], a0[S], a1[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                np_sincos_f32(sb[s], dir0[s], dir1[s]);
-                float g0 = 0.f, g1 = 0.f, dmin = 3.0e38f;
-#pragma unroll
-                for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
-                    if (j < np) {
-                        float r0 = __fsub_rn(pl[j].x, sh[s].x), r1 = __fsub_rn(pl[j].y, sh[s].y);
-                        float d2 = __fmaf_rn(r1, r1, __fmul_rn(r0, r0));
-                        float fj = __fdividef(c.gm_f, fmaxf(1e-12f, d2));
-                        g0 = __fmaf_rn(fj, r0, g0);
-                        g1 = __fmaf_rn(fj, r1, g1);
-                        dmin = fminf(dmin, d2);
-                    }
-                }
-                bool h = dmin < c.r2f_sp;
-                if (__builtin_expect(fabsf(dmin - c.r2f_sp) <= c.r2f_sp * 1e-6f, 0)) {
-                    h = false;
-#pragma unroll
-                    for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
-                        if (j < np)
-                            h |= collide_exact((double)sh[s].x, (double)sh[s].y, (double)pl[j].x, (double)pl[j].y, c.r2_sp);
-                }
-                hits |= h ? (1u << s) : 0u;
-                float th = (ctl[s] & 1) ? c.thrust_f : 0.f;
-                a0[s] = __fmaf_rn(th, dir0[s], g0);
-                a1[s] = __fmaf_rn(th, dir1[s], g1);
-            }
-            if (S == 2) {
-                if (collide(sh[0].x, sh[0].y, sh[S - 1].x, sh[S - 1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
-            }
-
-            const bool timeout = tick >= (uint32_t)p.timeout_tick;
-            float rw[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) rw[s] = 0.0f;
-            if (hits) {  // core.py:253-255
-                ev = hits;  // ASTRO_EV_HIT0 | ASTRO_EV_HIT1 are bits 0 and 1
-#pragma unroll
-                for (int s = 0; s < S; s++) rw[s] = ((hits >> s) & 1u) ? -1.0f : 1.0f;
-            } else if (timeout) {  // core.py:257-260
-                ev = ASTRO_EV_TIMEOUT;
-#pragma unroll
-                for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
-            } else {
-                const bool fire = tick < (uint32_t)p.n_sched_ticks && ((p.fire_bits[tick >> 5] >> (tick & 31)) & 1u);
-                if (fire) {  // core.py:267-280, float64 like the reference (1 tick in 15)
-                    ev |= ASTRO_EV_FIRED;
-#pragma unroll
-                    for (int s = 0; s < S; s++) {
-                        Body4<double> nbl;
-                        nbl.x = __dadd_rn((double)sh[s].x, (double)__fmul_rn(c.off_f, dir0[s]));
-                        nbl.y = __dadd_rn((double)sh[s].y, (double)__fmul_rn(c.off_f, dir1[s]));
-                        nbl.dx = __dadd_rn((double)sh[s].dx, (double)__fmul_rn(c.spd_f, dir0[s]));
-                        nbl.dy = __dadd_rn((double)sh[s].dy, (double)__fmul_rn(c.spd_f, dir1[s]));
-                        if (advance_bullet(nbl, c)) {
-                            if (m < p.K) {
-                                B4 o;
-                                o.x = (float)nbl.x; o.y = (float)nbl.y; o.dx = (float)nbl.dx; o.dy = (float)nbl.dy;
-                                bullets[m * 32] = o;
-                                m++;
-                            } else {
-                                ev |= ASTRO_EV_OVERFLOW;
-                            }
-                        }
-                    }
-                    spawned = S;
-                }
-#pragma unroll
-                for (int s = 0; s < S; s++) {  // core.py:283-288
-                    advance_body(sh[s], a0[s], a1[s], c);
-                    ships[s * 32] = sh[s];
-                    ship_b[s * 32] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
-                }
-                // planets (core.py:289-294): pair forces are antisymmetric, the clamped self term
-                // is exactly zero
-                float q0[ASTRO_MAX_PLANETS], q1[ASTRO_MAX_PLANETS];
-#pragma unroll
-                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) { q0[i] = 0.f; q1[i] = 0.f; }
-#pragma unroll
-                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
-#pragma unroll
-                    for (int j = i + 1; j < ASTRO_MAX_PLANETS; j++) {
-                        if (j < np) {
-                            float r0 = __fsub_rn(pl[j].x, pl[i].x), r1 = __fsub_rn(pl[j].y, pl[i].y);
-                            float d2 = __fmaf_rn(r1, r1, __fmul_rn(r0, r0));
-                            float fj = __fdividef(c.gm_f, fmaxf(1e-12f, d2));
-                            q0[i] = __fmaf_rn(fj, r0, q0[i]);
-                            q1[i] = __fmaf_rn(fj, r1, q1[i]);
-                            q0[j] = __fmaf_rn(-fj, r0, q0[j]);
-                            q1[j] = __fmaf_rn(-fj, r1, q1[j]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
-                    if (i < np) {
-                        advance_body(pl[i], q0[i], q1[i], c);
-                        planets[i * 32] = pl[i];
-                    }
-                }
-                p.meta[g] = ASTRO_META_PACK(m, np, 0, tick + 1);
-                m_out = m;
-            }
-            if (ev & ASTRO_EV_DONE_MASK) {
-                if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0)
-                    recreate_from_pool<float, S>(p, g, ships, ship_b, planets);
-                else
-                    p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
-            }
-            if (p.reward) {
-                if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
-                else p.reward[g] = rw[0];
-            }
-        }
-        if (p.events) p.events[g] = (uint8_t)ev;
-        if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
-    }
-    if (STATS) {
-        warp_stats(s_stats, lane, S, ev, active, spawned, np, nb, m_out);
-        __syncthreads();
-        if (threadIdx.x < ASTRO_N_STATS && s_stats[threadIdx.x]) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
-    }
-}
+#include "tick_f32.cuh"
 
 // ------------------------------------------------------------------------------------------
 // reset_kernel: stand-alone form of AUTO_RESET — finished games are re-created from the pool.
@@ -730,11 +425,11 @@ observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_
     }
     __syncwarp();
     const B4* planets = reinterpret_cast<const B4*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32) + gl;
-    const B4* bullets = reinterpret_cast<const B4*>(bullets_) + tile * ((size_t)K * 32) + gl;
+    const B4* bullets = reinterpret_cast<const B4*>(bullets_) + (size_t)g * K;  // game-major row
     for (int r = lane; r < n_rows; r += 32) {
         float* row = rows + r * D;
         if (r < np + nb) {
-            B4 o = r < np ? planets[r * 32] : bullets[(r - np) * 32];
+            B4 o = r < np ? planets[r * 32] : bullets[r - np];
             row[0] = r < np ? 0.0f : 1.0f;
 #pragma unroll
             for (int k = 0; k < 5 * S; k++) row[1 + k] = sf[k];

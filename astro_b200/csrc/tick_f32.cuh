@@ -1,0 +1,395 @@
+// tick_f32.cuh — the production tick kernel (included by astro_b200.cu inside its anonymous
+// namespace, after TickParams / recreate_from_pool / warp_stats).
+//
+// One warp owns one 32-game tile.  Two phases:
+//
+//  A. BULLETS, warp-cooperative.  Each lane stages its game's ships and planets in shared
+//     memory, the per-game bullet counts are prefix-summed across the warp, and the tile's
+//     bullets are processed as ONE flat list, 32 per iteration, whatever game they belong to —
+//     a warp with bullet counts (0, 17, 3, ...) runs ceil(sum/32) iterations, not max = 17.
+//     Per bullet: squared distances to both ships and four planet slots (dead slots hold a
+//     far-away sentinel) reduced with min, the advance, and ONE band test deciding whether the
+//     fp32 comparisons provably equal the reference's float64 results; only a bullet inside a
+//     band (|d2 - R2| <= 1e-6 R2, or |x'| within 4e-6 of the arena bound — ~1e-5 of bullets),
+//     and every ship hit, takes the float64 path.  Survivors are compacted in place with a
+//     warp ballot: rank inside the game's segment = popc(ballot & segment mask), so the
+//     reference order (stable) is kept.  Bullets are game-major in HBM (a game's pool is one
+//     contiguous row), so a window of 32 consecutive list items reads a few contiguous runs.
+//  B. SHIPS AND PLANETS, thread-per-game from the staged copies: direction, gravity, collisions,
+//     terminal logic, spawn, integration, reset — all coalesced 128-bit accesses.
+#pragma once
+
+constexpr float kFar = 1.0e18f;  // dead planet slot: d2 = 2e36, finite in fp32, never a minimum
+constexpr int kTickWarps = kTickThreads / 32;
+
+struct TileScratch {               // per warp
+    float4 ship[2][32];            // x, y, dx, dy   (lane-major: conflict-free 128-bit access)
+    float4 planet[4][32];
+    float4 sxy[32];                // ship0.xy, ship1.xy          } what phase A reads,
+    float4 pxy[2][32];             // planet0.xy planet1.xy / 2,3 } addressed by game
+    uint32_t excl[32];             // exclusive prefix of the bullet counts
+    uint32_t outn[32];             // survivors written so far
+    uint32_t hits[32];             // ship-hit bits found by phase A
+    uint32_t np[32];
+    uint8_t compact[32];           // non-empty games in order
+};
+
+// Exact (reference float64) evaluation of one bullet against the OLD ship / planet positions:
+// despawn flags, per-ship hit bits, advance + cull.  Out of line; everything by value.
+struct ExactResult {
+    float x, y;
+    unsigned flags;  // bit 0 keep, bits 1-2 ship hits
+};
+__device__ __noinline__ ExactResult bullet_exact(float bx, float by, float bdx, float bdy, float4 sxy, float4 p01,
+                                                 float4 p23, int n_ships, int np, const Consts* cp) {
+    const Consts& c = *cp;
+    unsigned ship_hits = 0;
+    if (collide_exact((double)sxy.x, (double)sxy.y, (double)bx, (double)by, c.r2_sb)) ship_hits |= 1u;
+    if (n_ships > 1 && collide_exact((double)sxy.z, (double)sxy.w, (double)bx, (double)by, c.r2_sb)) ship_hits |= 2u;
+    bool gone = ship_hits != 0;
+    gone |= collide_exact((double)p01.x, (double)p01.y, (double)bx, (double)by, c.r2_pb);  // np >= 1
+    if (np > 1) gone |= collide_exact((double)p01.z, (double)p01.w, (double)bx, (double)by, c.r2_pb);
+    if (np > 2) gone |= collide_exact((double)p23.x, (double)p23.y, (double)bx, (double)by, c.r2_pb);
+    if (np > 3) gone |= collide_exact((double)p23.z, (double)p23.w, (double)bx, (double)by, c.r2_pb);
+    double v0 = __dadd_rn((double)bdx, c.zero_dt), v1 = __dadd_rn((double)bdy, c.zero_dt);
+    double e0 = __dadd_rn((double)bx, __dmul_rn(c.dt, v0)), e1 = __dadd_rn((double)by, __dmul_rn(c.dt, v1));
+    ExactResult r;
+    r.x = (float)e0;
+    r.y = (float)e1;
+    r.flags = ((in_arena(e0, e1) && !gone) ? 1u : 0u) | (ship_hits << 1);
+    return r;
+}
+
+__device__ __forceinline__ float dist2(float ax, float ay, float bx, float by) {
+    float d0 = __fsub_rn(ax, bx), d1 = __fsub_rn(ay, by);
+    return __fmaf_rn(d1, d1, __fmul_rn(d0, d0));
+}
+
+// One bullet against its game's staged frame.  Returns keep; b.x/b.y advanced; ship_hits
+// receives bits 0/1 when the bullet touches ship 0/1 (always decided in float64).
+template <int S>
+__device__ __forceinline__ bool bullet_step(Body4<float>& b, float4 sxy, float4 p01, float4 p23, int np,
+                                            const Consts& c, unsigned& ship_hits) {
+    float ds = dist2(sxy.x, sxy.y, b.x, b.y);
+    if (S == 2) ds = fminf(ds, dist2(sxy.z, sxy.w, b.x, b.y));
+    float dp = fminf(fminf(dist2(p01.x, p01.y, b.x, b.y), dist2(p01.z, p01.w, b.x, b.y)),
+                     fminf(dist2(p23.x, p23.y, b.x, b.y), dist2(p23.z, p23.w, b.x, b.y)));
+    float x0 = __fmaf_rn(c.dt_f, b.dx, b.x), x1 = __fmaf_rn(c.dt_f, b.dy, b.y);
+    float a0 = fabsf(x0), a1 = fabsf(x1);
+    float edge = fminf(fabsf(a0 - 1.0f), fabsf(a1 - 1.0f));
+    bool unsure = (ds < c.r2f_sb * 1.000001f) | (fabsf(dp - c.r2f_pb) <= c.r2f_pb * 1e-6f) | (edge <= 4e-6f);
+    bool keep = ((a0 <= 1.0f) | (a1 <= 1.0f)) & (dp >= c.r2f_pb);
+    if (__builtin_expect(unsure, 0)) {
+        ExactResult r = bullet_exact(b.x, b.y, b.dx, b.dy, sxy, p01, p23, S, np, &c);
+        x0 = r.x;
+        x1 = r.y;
+        keep = r.flags & 1u;
+        ship_hits = r.flags >> 1;
+    }
+    b.x = x0;
+    b.y = x1;
+    return keep;
+}
+
+// Flat bullet list of a tile: item i of the list -> (game, slot).  `starts` = bit r set when a
+// non-empty game's first bullet is item base + r; c0 = non-empty games that start before base.
+struct ItemRef {
+    unsigned game, excl;
+    bool valid;
+};
+__device__ __forceinline__ ItemRef map_item(const TileScratch& t, unsigned base, unsigned total, unsigned my_excl,
+                                            bool my_nonempty, unsigned lane, unsigned& c0) {
+    const unsigned full = 0xffffffffu;
+    unsigned rel = my_excl - base;  // wraps to a huge value when the game starts before base
+    unsigned starts = __reduce_or_sync(full, (my_nonempty && rel < 32u) ? (1u << rel) : 0u);
+    unsigned le = full >> (31u - lane);
+    unsigned idx = c0 + __popc(starts & le);  // >= 1 for a valid item
+    c0 += __popc(starts);
+    ItemRef r;
+    r.valid = base + lane < total;
+    r.game = t.compact[(idx - 1u) & 31u] & 31u;  // (garbage only for invalid items)
+    r.excl = t.excl[r.game];
+    return r;
+}
+
+template <int S, bool STATS>
+__global__ void __launch_bounds__(kTickThreads, 4) tick_f32_kernel(const __grid_constant__ TickParams p) {
+    using B4 = Body4<float>;
+    const unsigned full = 0xffffffffu;
+    __shared__ unsigned long long s_stats[ASTRO_N_STATS];
+    __shared__ TileScratch s_tiles[kTickWarps];
+    if (STATS) {
+        if (threadIdx.x < ASTRO_N_STATS) s_stats[threadIdx.x] = 0ull;
+        __syncthreads();
+    }
+    const int g = blockIdx.x * kTickThreads + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const Consts& c = p.c;
+    TileScratch& t = s_tiles[threadIdx.x >> 5];
+    uint32_t ev = 0;
+    int np = 0, nb = 0, m_out = 0, spawned = 0;
+    bool active = false;
+
+    if (g < p.n_games) {  // whole warps: n_games % 32 == 0
+        const size_t tile = (size_t)(g >> 5);
+        B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
+        float* ship_b = reinterpret_cast<float*>(p.ship_b) + tile * (S * 32) + lane;
+        B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
+        B4* tile_bullets = reinterpret_cast<B4*>(p.bullets) + tile * 32 * (size_t)p.K;
+
+        // ---- loads of this lane's game (all independent of each other except via meta)
+        const uint32_t meta = p.meta[g];
+        float4 shv[S];
+        float sb[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            shv[s] = *reinterpret_cast<const float4*>(&ships[s * 32]);
+            sb[s] = ship_b[s * 32];
+        }
+        int ctl[S];
+        if (p.actions) {
+            if (S == 2) {
+                uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
+                ctl[0] = a & 0xff;
+                ctl[S - 1] = a >> 8;
+            } else {
+                ctl[0] = p.actions[g];
+            }
+        } else {
+            uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
+#pragma unroll
+            for (int s = 0; s < S; s++) ctl[s] = action_from_key(h0, p.step, (uint32_t)s);
+        }
+        active = !ASTRO_META_FINISHED(meta);
+        nb = active ? (int)ASTRO_META_NB(meta) : 0;
+        np = active ? (int)ASTRO_META_NP(meta) : 0;
+        const uint32_t tick = ASTRO_META_TICK(meta);
+        float4 plv[ASTRO_MAX_PLANETS];
+#pragma unroll
+        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+            plv[j] = make_float4(kFar, kFar, 0.f, 0.f);
+            if (j < np) plv[j] = *reinterpret_cast<const float4*>(&planets[j * 32]);
+        }
+
+        // ================= phase A: the tile's bullets as one flat list ======================
+        {
+#pragma unroll
+            for (int s = 0; s < S; s++) t.ship[s][lane] = shv[s];
+#pragma unroll
+            for (int j = 0; j < ASTRO_MAX_PLANETS; j++) t.planet[j][lane] = plv[j];
+            t.sxy[lane] = make_float4(shv[0].x, shv[0].y, shv[S - 1].x, shv[S - 1].y);
+            t.pxy[0][lane] = make_float4(plv[0].x, plv[0].y, plv[1].x, plv[1].y);
+            t.pxy[1][lane] = make_float4(plv[2].x, plv[2].y, plv[3].x, plv[3].y);
+            unsigned incl = (unsigned)nb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned v = __shfl_up_sync(full, incl, d);
+                if ((int)lane >= d) incl += v;
+            }
+            const unsigned my_excl = incl - (unsigned)nb;
+            const unsigned total = __shfl_sync(full, incl, 31);
+            const bool nonempty = nb > 0;
+            t.excl[lane] = my_excl;
+            t.outn[lane] = 0u;
+            t.hits[lane] = 0u;
+            t.np[lane] = (unsigned)np;
+            const unsigned ne = __ballot_sync(full, nonempty);
+            if (nonempty) t.compact[__popc(ne & ((1u << lane) - 1u))] = (uint8_t)lane;
+            __syncwarp();
+
+            unsigned c0 = 0;
+            ItemRef cur = map_item(t, 0u, total, my_excl, nonempty, lane, c0);
+            B4 bcur;
+            bcur.x = bcur.y = bcur.dx = bcur.dy = 0.f;
+            if (cur.valid) bcur = tile_bullets[(size_t)cur.game * p.K + (lane - cur.excl)];
+            for (unsigned base = 0; base < total; base += 32u) {
+                // software pipeline: the next window's bullets are in flight during this one.
+                // (They are later list items: never a slot this window's stores can touch.)
+                ItemRef nxt;
+                nxt.valid = false; nxt.game = 0; nxt.excl = 0;
+                B4 bnxt = bcur;
+                if (base + 32u < total) {
+                    nxt = map_item(t, base + 32u, total, my_excl, nonempty, lane, c0);
+                    if (nxt.valid) bnxt = tile_bullets[(size_t)nxt.game * p.K + (base + 32u + lane - nxt.excl)];
+                }
+                const unsigned gi = cur.game;
+                bool keep = false;
+                unsigned sh_hits = 0;
+                B4 b = bcur;
+                if (cur.valid) keep = bullet_step<S>(b, t.sxy[gi], t.pxy[0][gi], t.pxy[1][gi], (int)t.np[gi], c, sh_hits);
+                if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
+                // stable in-place compaction inside each game's segment of the window
+                const unsigned kb = __ballot_sync(full, keep);
+                const unsigned seg_lo = cur.excl > base ? cur.excl - base : 0u;  // < 32 for a valid item
+                const unsigned before = ((1u << lane) - 1u) & ~((1u << (seg_lo & 31u)) - 1u);
+                const unsigned rank = __popc(kb & before);
+                const unsigned ob = t.outn[gi];
+                const unsigned g_next = __shfl_down_sync(full, gi, 1);
+                const bool last = cur.valid && (lane == 31u || base + lane + 1u >= total || g_next != gi);
+                __syncwarp();
+                if (keep) tile_bullets[(size_t)gi * p.K + ob + rank] = b;
+                if (last) t.outn[gi] = ob + rank + (keep ? 1u : 0u);
+                __syncwarp();
+                cur = nxt;
+                bcur = bnxt;
+            }
+        }
+
+        // ================= phase B: ships and planets, thread-per-game ========================
+        if (!active) {
+            ev = ASTRO_EV_SKIPPED;
+            if (p.reward) {
+                if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(0.f, 0.f);
+                else p.reward[g] = 0.f;
+            }
+        } else {
+            int m = (int)t.outn[lane];
+            unsigned hits = t.hits[lane];
+            B4 sh[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                float4 v = t.ship[s][lane];
+                sh[s].x = v.x; sh[s].y = v.y; sh[s].dx = v.z; sh[s].dy = v.w;
+            }
+            B4 pl[ASTRO_MAX_PLANETS];
+#pragma unroll
+            for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+                float4 v = t.planet[j][lane];
+                pl[j].x = v.x; pl[j].y = v.y; pl[j].dx = v.z; pl[j].dy = v.w;
+            }
+            // direction, gravity, ship-planet and ship-ship collisions on the old state
+            float dir0[S], dir1[S], a0[S], a1[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                np_sincos_f32(sb[s], dir0[s], dir1[s]);
+                float g0 = 0.f, g1 = 0.f, dmin = 3.0e38f;
+#pragma unroll
+                for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+                    float r0 = __fsub_rn(pl[j].x, sh[s].x), r1 = __fsub_rn(pl[j].y, sh[s].y);
+                    float d2 = __fmaf_rn(r1, r1, __fmul_rn(r0, r0));
+                    float fj = (j < np) ? __fdividef(c.gm_f, fmaxf(1e-12f, d2)) : 0.f;
+                    g0 = __fmaf_rn(fj, r0, g0);
+                    g1 = __fmaf_rn(fj, r1, g1);
+                    dmin = fminf(dmin, d2);  // dead slots sit at kFar
+                }
+                bool h = dmin < c.r2f_sp;
+                if (__builtin_expect(fabsf(dmin - c.r2f_sp) <= c.r2f_sp * 1e-6f, 0)) {
+                    h = false;
+#pragma unroll
+                    for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
+                        if (j < np)
+                            h |= collide_exact((double)sh[s].x, (double)sh[s].y, (double)pl[j].x, (double)pl[j].y, c.r2_sp);
+                }
+                hits |= h ? (1u << s) : 0u;
+                float th = (ctl[s] & 1) ? c.thrust_f : 0.f;
+                a0[s] = __fmaf_rn(th, dir0[s], g0);
+                a1[s] = __fmaf_rn(th, dir1[s], g1);
+            }
+            if (S == 2) {
+                if (collide(sh[0].x, sh[0].y, sh[S - 1].x, sh[S - 1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
+            }
+
+            const bool timeout = tick >= (uint32_t)p.timeout_tick;
+            float rw[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) rw[s] = 0.0f;
+            if (hits) {  // core.py:253-255
+                ev = hits;  // ASTRO_EV_HIT0 | ASTRO_EV_HIT1 are bits 0 and 1
+#pragma unroll
+                for (int s = 0; s < S; s++) rw[s] = ((hits >> s) & 1u) ? -1.0f : 1.0f;
+            } else if (timeout) {  // core.py:257-260
+                ev = ASTRO_EV_TIMEOUT;
+#pragma unroll
+                for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
+            } else {
+                const bool fire = tick < (uint32_t)p.n_sched_ticks && ((p.fire_bits[tick >> 5] >> (tick & 31)) & 1u);
+                if (fire) {  // core.py:267-280
+                    ev |= ASTRO_EV_FIRED;
+                    B4* row = tile_bullets + (size_t)lane * p.K;
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        // fp32 products as in the reference; the sums and the advance in fp32 too,
+                        // unless the newborn lands within the band of the arena bound
+                        float o0 = __fmul_rn(c.off_f, dir0[s]), o1 = __fmul_rn(c.off_f, dir1[s]);
+                        float w0 = __fmul_rn(c.spd_f, dir0[s]), w1 = __fmul_rn(c.spd_f, dir1[s]);
+                        B4 o;
+                        o.dx = __fadd_rn(sh[s].dx, w0);
+                        o.dy = __fadd_rn(sh[s].dy, w1);
+                        o.x = __fmaf_rn(c.dt_f, o.dx, __fadd_rn(sh[s].x, o0));
+                        o.y = __fmaf_rn(c.dt_f, o.dy, __fadd_rn(sh[s].y, o1));
+                        float e0 = fabsf(o.x), e1 = fabsf(o.y);
+                        bool keep = (e0 <= 1.0f) | (e1 <= 1.0f);
+                        if (__builtin_expect(fminf(fabsf(e0 - 1.0f), fabsf(e1 - 1.0f)) <= 8e-6f, 0)) {
+                            Body4<double> nbl;
+                            nbl.x = __dadd_rn((double)sh[s].x, (double)o0);
+                            nbl.y = __dadd_rn((double)sh[s].y, (double)o1);
+                            nbl.dx = __dadd_rn((double)sh[s].dx, (double)w0);
+                            nbl.dy = __dadd_rn((double)sh[s].dy, (double)w1);
+                            keep = advance_bullet(nbl, c);
+                            o.x = (float)nbl.x; o.y = (float)nbl.y; o.dx = (float)nbl.dx; o.dy = (float)nbl.dy;
+                        }
+                        if (keep) {
+                            if (m < p.K) {
+                                row[m] = o;
+                                m++;
+                            } else {
+                                ev |= ASTRO_EV_OVERFLOW;
+                            }
+                        }
+                    }
+                    spawned = S;
+                }
+#pragma unroll
+                for (int s = 0; s < S; s++) {  // core.py:283-288
+                    advance_body(sh[s], a0[s], a1[s], c);
+                    ships[s * 32] = sh[s];
+                    ship_b[s * 32] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
+                }
+                // planets (core.py:289-294): pair forces are antisymmetric, the clamped self term
+                // is exactly zero
+                float q0[ASTRO_MAX_PLANETS], q1[ASTRO_MAX_PLANETS];
+#pragma unroll
+                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) { q0[i] = 0.f; q1[i] = 0.f; }
+#pragma unroll
+                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
+#pragma unroll
+                    for (int j = i + 1; j < ASTRO_MAX_PLANETS; j++) {
+                        float r0 = __fsub_rn(pl[j].x, pl[i].x), r1 = __fsub_rn(pl[j].y, pl[i].y);
+                        float d2 = __fmaf_rn(r1, r1, __fmul_rn(r0, r0));
+                        float fj = (j < np) ? __fdividef(c.gm_f, fmaxf(1e-12f, d2)) : 0.f;
+                        q0[i] = __fmaf_rn(fj, r0, q0[i]);
+                        q1[i] = __fmaf_rn(fj, r1, q1[i]);
+                        q0[j] = __fmaf_rn(-fj, r0, q0[j]);
+                        q1[j] = __fmaf_rn(-fj, r1, q1[j]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
+                    if (i < np) {
+                        advance_body(pl[i], q0[i], q1[i], c);
+                        planets[i * 32] = pl[i];
+                    }
+                }
+                p.meta[g] = ASTRO_META_PACK(m, np, 0, tick + 1);
+                m_out = m;
+            }
+            if (ev & ASTRO_EV_DONE_MASK) {
+                if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0)
+                    recreate_from_pool<float, S>(p, g, ships, ship_b, planets);
+                else
+                    p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
+            }
+            if (p.reward) {
+                if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
+                else p.reward[g] = rw[0];
+            }
+        }
+        if (p.events) p.events[g] = (uint8_t)ev;
+        if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
+    }
+    if (STATS) {
+        warp_stats(s_stats, (int)lane, S, ev, active, spawned, np, nb, m_out);
+        __syncthreads();
+        if (threadIdx.x < ASTRO_N_STATS && s_stats[threadIdx.x]) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
+    }
+}

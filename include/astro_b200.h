@@ -23,11 +23,13 @@
  *     ships    R4  [n_tiles][S][32]      ship s of game g  -> ((g/32)*S + s)*32 + g%32
  *     ship_b   R   [n_tiles][S][32]      bearing
  *     planets  R4  [n_tiles][4][32]      slots >= np are dead
- *     bullets  R4  [n_tiles][K][32]      slots >= nb are dead; order = reference order
+ *     bullets  R4  [n_games][K]          game-major: a game's pool is one contiguous row; slots
+ *                                        >= nb are dead; order = reference order
  *     meta     u32 [n_tiles*32]          nb (bits 0-9) | np (10-12) | finished (13) | tick (14-31)
  *     episode  u32 [n_tiles*32]          games finished in this slot (reset-pool stream key)
- * A thread owns one game, so every load/store above is a fully coalesced 128-bit (R=float)
- * access across the warp.
+ * Ships, planets and meta are accessed thread-per-game: every load/store is a fully coalesced
+ * 128-bit (R=float) access across the warp.  Bullets are processed by the warp as one flat list
+ * per tile (see csrc/tick_f32.cuh), 32 consecutive list items per step: contiguous runs.
  */
 #ifndef ASTRO_B200_H
 #define ASTRO_B200_H
