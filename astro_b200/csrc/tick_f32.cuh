@@ -19,30 +19,32 @@
 //     terminal logic, spawn, integration, reset — all coalesced 128-bit accesses.
 #pragma once
 
-constexpr float kFar = 1.0e18f;  // dead planet slot: d2 = 2e36, finite in fp32, never a minimum
+// Dead planet slots sit at kFar: the squared distance overflows to +inf, so a dead slot is never
+// a minimum, never inside a band, and its gravity G*M/inf is exactly 0 — no predication on np.
+constexpr float kFar = 1.0e20f;
 constexpr int kTickWarps = kTickThreads / 32;
 
 struct TileScratch {               // per warp
-    float4 ship[2][32];            // x, y, dx, dy   (lane-major: conflict-free 128-bit access)
-    float4 planet[4][32];
-    float4 sxy[32];                // ship0.xy, ship1.xy          } what phase A reads,
-    float4 pxy[2][32];             // planet0.xy planet1.xy / 2,3 } addressed by game
+    float4 ship[2][32];            // OLD x, y, dx, dy (lane-major: conflict-free 128-bit access)
+    float4 planet[4][32];          // OLD; dead slots at kFar
+    float4 sxy[32];                // OLD ship0.xy, ship1.xy          } what the bullet loop reads,
+    float4 pxy[2][32];             // OLD planet0.xy planet1.xy / 2,3 } addressed by game
+    float4 dir[32];                // sin/cos of both bearings (for the newborn bullets)
     uint32_t excl[32];             // exclusive prefix of the bullet counts
     uint32_t outn[32];             // survivors written so far
-    uint32_t hits[32];             // ship-hit bits found by phase A
+    uint32_t hits[32];             // ship-hit bits found by the bullet loop
     uint32_t np[32];
     uint8_t compact[32];           // non-empty games in order
 };
 
 // Exact (reference float64) evaluation of one bullet against the OLD ship / planet positions:
-// despawn flags, per-ship hit bits, advance + cull.  Out of line; everything by value.
+// despawn flags, per-ship hit bits, advance + cull.  Taken by ~1e-5 of bullets.
 struct ExactResult {
     float x, y;
     unsigned flags;  // bit 0 keep, bits 1-2 ship hits
 };
-__device__ __noinline__ ExactResult bullet_exact(float bx, float by, float bdx, float bdy, float4 sxy, float4 p01,
-                                                 float4 p23, int n_ships, int np, const Consts* cp) {
-    const Consts& c = *cp;
+__device__ __forceinline__ ExactResult bullet_exact(float bx, float by, float bdx, float bdy, float4 sxy, float4 p01,
+                                                    float4 p23, int n_ships, int np, const Consts& c) {
     unsigned ship_hits = 0;
     if (collide_exact((double)sxy.x, (double)sxy.y, (double)bx, (double)by, c.r2_sb)) ship_hits |= 1u;
     if (n_ships > 1 && collide_exact((double)sxy.z, (double)sxy.w, (double)bx, (double)by, c.r2_sb)) ship_hits |= 2u;
@@ -67,20 +69,21 @@ __device__ __forceinline__ float dist2(float ax, float ay, float bx, float by) {
 
 // One bullet against its game's staged frame.  Returns keep; b.x/b.y advanced; ship_hits
 // receives bits 0/1 when the bullet touches ship 0/1 (always decided in float64).
+// Arena test: keep iff (|x'| <= 1) or (|y'| <= 1)  <=>  min(|x'|, |y'|) <= 1, so only the
+// smaller magnitude can sit in the uncertainty band.
 template <int S>
-__device__ __forceinline__ bool bullet_step(Body4<float>& b, float4 sxy, float4 p01, float4 p23, int np,
-                                            const Consts& c, unsigned& ship_hits) {
+__device__ __forceinline__ bool bullet_step(Body4<float>& b, float4 sxy, float4 p01, float4 p23, const uint32_t* np_of,
+                                            unsigned gi, const Consts& c, unsigned& ship_hits) {
     float ds = dist2(sxy.x, sxy.y, b.x, b.y);
     if (S == 2) ds = fminf(ds, dist2(sxy.z, sxy.w, b.x, b.y));
     float dp = fminf(fminf(dist2(p01.x, p01.y, b.x, b.y), dist2(p01.z, p01.w, b.x, b.y)),
                      fminf(dist2(p23.x, p23.y, b.x, b.y), dist2(p23.z, p23.w, b.x, b.y)));
     float x0 = __fmaf_rn(c.dt_f, b.dx, b.x), x1 = __fmaf_rn(c.dt_f, b.dy, b.y);
-    float a0 = fabsf(x0), a1 = fabsf(x1);
-    float edge = fminf(fabsf(a0 - 1.0f), fabsf(a1 - 1.0f));
-    bool unsure = (ds < c.r2f_sb * 1.000001f) | (fabsf(dp - c.r2f_pb) <= c.r2f_pb * 1e-6f) | (edge <= 4e-6f);
-    bool keep = ((a0 <= 1.0f) | (a1 <= 1.0f)) & (dp >= c.r2f_pb);
-    if (__builtin_expect(unsure, 0)) {
-        ExactResult r = bullet_exact(b.x, b.y, b.dx, b.dy, sxy, p01, p23, S, np, &c);
+    float mn = fminf(fabsf(x0), fabsf(x1));
+    bool sure = (ds >= c.r2f_sb * 1.000001f) & (fabsf(dp - c.r2f_pb) > c.r2f_pb * 1e-6f) & (fabsf(mn - 1.0f) > 4e-6f);
+    bool keep = (mn <= 1.0f) & (dp >= c.r2f_pb);
+    if (__builtin_expect(!sure, 0)) {
+        ExactResult r = bullet_exact(b.x, b.y, b.dx, b.dy, sxy, p01, p23, S, (int)np_of[gi], c);
         x0 = r.x;
         x1 = r.y;
         keep = r.flags & 1u;
@@ -112,284 +115,299 @@ __device__ __forceinline__ ItemRef map_item(const TileScratch& t, unsigned base,
     return r;
 }
 
+#ifndef ASTRO_TICK_MIN_BLOCKS
+#define ASTRO_TICK_MIN_BLOCKS 8
+#endif
 template <int S, bool STATS>
-__global__ void __launch_bounds__(kTickThreads, 4) tick_f32_kernel(const __grid_constant__ TickParams p) {
+__global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
     using B4 = Body4<float>;
     const unsigned full = 0xffffffffu;
-    __shared__ unsigned long long s_stats[ASTRO_N_STATS];
     __shared__ TileScratch s_tiles[kTickWarps];
-    if (STATS) {
-        if (threadIdx.x < ASTRO_N_STATS) s_stats[threadIdx.x] = 0ull;
-        __syncthreads();
-    }
     const int g = blockIdx.x * kTickThreads + threadIdx.x;
+    if (g >= p.n_games) return;  // whole warps: n_games % 32 == 0
     const unsigned lane = threadIdx.x & 31u;
     const Consts& c = p.c;
     TileScratch& t = s_tiles[threadIdx.x >> 5];
-    uint32_t ev = 0;
-    int np = 0, nb = 0, m_out = 0, spawned = 0;
-    bool active = false;
+    const size_t tile = (size_t)(g >> 5);
+    B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
+    float* ship_b = reinterpret_cast<float*>(p.ship_b) + tile * (S * 32) + lane;
+    B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
+    B4* tile_bullets = reinterpret_cast<B4*>(p.bullets) + tile * 32 * (size_t)p.K;
+    const unsigned K = (unsigned)p.K;  // 32-bit slot arithmetic: a tile's pool is <= 32 * 1023 slots
 
-    if (g < p.n_games) {  // whole warps: n_games % 32 == 0
-        const size_t tile = (size_t)(g >> 5);
-        B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
-        float* ship_b = reinterpret_cast<float*>(p.ship_b) + tile * (S * 32) + lane;
-        B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
-        B4* tile_bullets = reinterpret_cast<B4*>(p.bullets) + tile * 32 * (size_t)p.K;
+    // ================= 1. this lane's game: loads (independent except planets <- meta) ========
+    const uint32_t meta = p.meta[g];
+    float4 shv[S];
+    float sb[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        shv[s] = *reinterpret_cast<const float4*>(&ships[s * 32]);
+        sb[s] = ship_b[s * 32];
+    }
+    int ctl[S];
+    if (p.actions) {
+        if (S == 2) {
+            uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
+            ctl[0] = a & 0xff;
+            ctl[S - 1] = a >> 8;
+        } else {
+            ctl[0] = p.actions[g];
+        }
+    } else {
+        uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
+#pragma unroll
+        for (int s = 0; s < S; s++) ctl[s] = action_from_key(h0, p.step, (uint32_t)s);
+    }
+    const bool active = !ASTRO_META_FINISHED(meta);
+    const int nb = active ? (int)ASTRO_META_NB(meta) : 0;
+    const int np = active ? (int)ASTRO_META_NP(meta) : 0;
+    const uint32_t tick = ASTRO_META_TICK(meta);
+    float4 plv[ASTRO_MAX_PLANETS];
+#pragma unroll
+    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+        plv[j] = make_float4(kFar, kFar, 0.f, 0.f);
+        if (j < np) plv[j] = *reinterpret_cast<const float4*>(&planets[j * 32]);
+    }
 
-        // ---- loads of this lane's game (all independent of each other except via meta)
-        const uint32_t meta = p.meta[g];
-        float4 shv[S];
-        float sb[S];
+    // ================= 2. flat bullet list of the tile: scan, map, first loads in flight =======
+    unsigned incl = (unsigned)nb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned v = __shfl_up_sync(full, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    const unsigned my_excl = incl - (unsigned)nb;
+    const unsigned total = __shfl_sync(full, incl, 31);
+    const bool nonempty = nb > 0;
+    t.excl[lane] = my_excl;
+    t.outn[lane] = 0u;
+    t.hits[lane] = 0u;
+    t.np[lane] = (unsigned)np;
+    const unsigned ne = __ballot_sync(full, nonempty);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    if (nonempty) t.compact[__popc(ne & lt_mask)] = (uint8_t)lane;
+    __syncwarp();
+    unsigned c0 = 0;
+    // One window = 32 consecutive list items.  Bullets are fetched two windows ahead of their
+    // use; prefetched items are later list items, never a slot an earlier window's stores touch.
+    auto fetch = [&](unsigned base, ItemRef& r, B4& b) {
+        r = map_item(t, base, total, my_excl, nonempty, lane, c0);
+        if (r.valid) b = tile_bullets[r.game * K + (base + lane - r.excl)];
+    };
+    ItemRef r0, r1, r2;
+    B4 b0, b1, b2;
+    b0.x = b0.y = b0.dx = b0.dy = 0.f;
+    b1 = b0;
+    b2 = b0;
+    fetch(0u, r0, b0);
+    fetch(32u, r1, b1);
+
+    // ================= 3. ships and planets while those loads fly ================================
+    // OLD positions staged for the bullet loop (addressed by game), OLD bodies kept for the
+    // newborn bullets and for restoring a game that ends without auto-reset.
+#pragma unroll
+    for (int s = 0; s < S; s++) t.ship[s][lane] = shv[s];
+#pragma unroll
+    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) t.planet[j][lane] = plv[j];
+    t.sxy[lane] = make_float4(shv[0].x, shv[0].y, shv[S - 1].x, shv[S - 1].y);
+    t.pxy[0][lane] = make_float4(plv[0].x, plv[0].y, plv[1].x, plv[1].y);
+    t.pxy[1][lane] = make_float4(plv[2].x, plv[2].y, plv[3].x, plv[3].y);
+    unsigned hits = 0;
+    if (active) {
+        B4 sh[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) { sh[s].x = shv[s].x; sh[s].y = shv[s].y; sh[s].dx = shv[s].z; sh[s].dy = shv[s].w; }
+        B4 pl[ASTRO_MAX_PLANETS];
+#pragma unroll
+        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) { pl[j].x = plv[j].x; pl[j].y = plv[j].y; pl[j].dx = plv[j].z; pl[j].dy = plv[j].w; }
+        float dirs[4] = {0.f, 0.f, 0.f, 0.f};
+        // direction, gravity, ship-planet and ship-ship collisions on the old state; then the
+        // new ship state goes straight to HBM (a game that ends is restored / re-created below)
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            shv[s] = *reinterpret_cast<const float4*>(&ships[s * 32]);
-            sb[s] = ship_b[s * 32];
-        }
-        int ctl[S];
-        if (p.actions) {
-            if (S == 2) {
-                uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
-                ctl[0] = a & 0xff;
-                ctl[S - 1] = a >> 8;
-            } else {
-                ctl[0] = p.actions[g];
-            }
-        } else {
-            uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
-#pragma unroll
-            for (int s = 0; s < S; s++) ctl[s] = action_from_key(h0, p.step, (uint32_t)s);
-        }
-        active = !ASTRO_META_FINISHED(meta);
-        nb = active ? (int)ASTRO_META_NB(meta) : 0;
-        np = active ? (int)ASTRO_META_NP(meta) : 0;
-        const uint32_t tick = ASTRO_META_TICK(meta);
-        float4 plv[ASTRO_MAX_PLANETS];
-#pragma unroll
-        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
-            plv[j] = make_float4(kFar, kFar, 0.f, 0.f);
-            if (j < np) plv[j] = *reinterpret_cast<const float4*>(&planets[j * 32]);
-        }
-
-        // ================= phase A: the tile's bullets as one flat list ======================
-        {
-#pragma unroll
-            for (int s = 0; s < S; s++) t.ship[s][lane] = shv[s];
-#pragma unroll
-            for (int j = 0; j < ASTRO_MAX_PLANETS; j++) t.planet[j][lane] = plv[j];
-            t.sxy[lane] = make_float4(shv[0].x, shv[0].y, shv[S - 1].x, shv[S - 1].y);
-            t.pxy[0][lane] = make_float4(plv[0].x, plv[0].y, plv[1].x, plv[1].y);
-            t.pxy[1][lane] = make_float4(plv[2].x, plv[2].y, plv[3].x, plv[3].y);
-            unsigned incl = (unsigned)nb;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned v = __shfl_up_sync(full, incl, d);
-                if ((int)lane >= d) incl += v;
-            }
-            const unsigned my_excl = incl - (unsigned)nb;
-            const unsigned total = __shfl_sync(full, incl, 31);
-            const bool nonempty = nb > 0;
-            t.excl[lane] = my_excl;
-            t.outn[lane] = 0u;
-            t.hits[lane] = 0u;
-            t.np[lane] = (unsigned)np;
-            const unsigned ne = __ballot_sync(full, nonempty);
-            if (nonempty) t.compact[__popc(ne & ((1u << lane) - 1u))] = (uint8_t)lane;
-            __syncwarp();
-
-            unsigned c0 = 0;
-            ItemRef cur = map_item(t, 0u, total, my_excl, nonempty, lane, c0);
-            B4 bcur;
-            bcur.x = bcur.y = bcur.dx = bcur.dy = 0.f;
-            if (cur.valid) bcur = tile_bullets[(size_t)cur.game * p.K + (lane - cur.excl)];
-            for (unsigned base = 0; base < total; base += 32u) {
-                // software pipeline: the next window's bullets are in flight during this one.
-                // (They are later list items: never a slot this window's stores can touch.)
-                ItemRef nxt;
-                nxt.valid = false; nxt.game = 0; nxt.excl = 0;
-                B4 bnxt = bcur;
-                if (base + 32u < total) {
-                    nxt = map_item(t, base + 32u, total, my_excl, nonempty, lane, c0);
-                    if (nxt.valid) bnxt = tile_bullets[(size_t)nxt.game * p.K + (base + 32u + lane - nxt.excl)];
-                }
-                const unsigned gi = cur.game;
-                bool keep = false;
-                unsigned sh_hits = 0;
-                B4 b = bcur;
-                if (cur.valid) keep = bullet_step<S>(b, t.sxy[gi], t.pxy[0][gi], t.pxy[1][gi], (int)t.np[gi], c, sh_hits);
-                if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
-                // stable in-place compaction inside each game's segment of the window
-                const unsigned kb = __ballot_sync(full, keep);
-                const unsigned seg_lo = cur.excl > base ? cur.excl - base : 0u;  // < 32 for a valid item
-                const unsigned before = ((1u << lane) - 1u) & ~((1u << (seg_lo & 31u)) - 1u);
-                const unsigned rank = __popc(kb & before);
-                const unsigned ob = t.outn[gi];
-                const unsigned g_next = __shfl_down_sync(full, gi, 1);
-                const bool last = cur.valid && (lane == 31u || base + lane + 1u >= total || g_next != gi);
-                __syncwarp();
-                if (keep) tile_bullets[(size_t)gi * p.K + ob + rank] = b;
-                if (last) t.outn[gi] = ob + rank + (keep ? 1u : 0u);
-                __syncwarp();
-                cur = nxt;
-                bcur = bnxt;
-            }
-        }
-
-        // ================= phase B: ships and planets, thread-per-game ========================
-        if (!active) {
-            ev = ASTRO_EV_SKIPPED;
-            if (p.reward) {
-                if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(0.f, 0.f);
-                else p.reward[g] = 0.f;
-            }
-        } else {
-            int m = (int)t.outn[lane];
-            unsigned hits = t.hits[lane];
-            B4 sh[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                float4 v = t.ship[s][lane];
-                sh[s].x = v.x; sh[s].y = v.y; sh[s].dx = v.z; sh[s].dy = v.w;
-            }
-            B4 pl[ASTRO_MAX_PLANETS];
+            float d0, d1;
+            np_sincos_f32(sb[s], d0, d1);
+            dirs[2 * s] = d0;
+            dirs[2 * s + 1] = d1;
+            float g0 = 0.f, g1 = 0.f, dmin = 3.0e38f;
 #pragma unroll
             for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
-                float4 v = t.planet[j][lane];
-                pl[j].x = v.x; pl[j].y = v.y; pl[j].dx = v.z; pl[j].dy = v.w;
+                float q0 = __fsub_rn(pl[j].x, sh[s].x), q1 = __fsub_rn(pl[j].y, sh[s].y);
+                float d2 = __fmaf_rn(q1, q1, __fmul_rn(q0, q0));
+                float fj = __fdividef(c.gm_f, fmaxf(1e-12f, d2));  // dead slot: G*M / inf = 0
+                g0 = __fmaf_rn(fj, q0, g0);
+                g1 = __fmaf_rn(fj, q1, g1);
+                dmin = fminf(dmin, d2);
             }
-            // direction, gravity, ship-planet and ship-ship collisions on the old state
-            float dir0[S], dir1[S], a0[S], a1[S];
+            bool h = dmin < c.r2f_sp;
+            if (__builtin_expect(fabsf(dmin - c.r2f_sp) <= c.r2f_sp * 1e-6f, 0)) {
+                h = false;
 #pragma unroll
-            for (int s = 0; s < S; s++) {
-                np_sincos_f32(sb[s], dir0[s], dir1[s]);
-                float g0 = 0.f, g1 = 0.f, dmin = 3.0e38f;
-#pragma unroll
-                for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
-                    float r0 = __fsub_rn(pl[j].x, sh[s].x), r1 = __fsub_rn(pl[j].y, sh[s].y);
-                    float d2 = __fmaf_rn(r1, r1, __fmul_rn(r0, r0));
-                    float fj = (j < np) ? __fdividef(c.gm_f, fmaxf(1e-12f, d2)) : 0.f;
-                    g0 = __fmaf_rn(fj, r0, g0);
-                    g1 = __fmaf_rn(fj, r1, g1);
-                    dmin = fminf(dmin, d2);  // dead slots sit at kFar
-                }
-                bool h = dmin < c.r2f_sp;
-                if (__builtin_expect(fabsf(dmin - c.r2f_sp) <= c.r2f_sp * 1e-6f, 0)) {
-                    h = false;
-#pragma unroll
-                    for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
-                        if (j < np)
-                            h |= collide_exact((double)sh[s].x, (double)sh[s].y, (double)pl[j].x, (double)pl[j].y, c.r2_sp);
-                }
-                hits |= h ? (1u << s) : 0u;
-                float th = (ctl[s] & 1) ? c.thrust_f : 0.f;
-                a0[s] = __fmaf_rn(th, dir0[s], g0);
-                a1[s] = __fmaf_rn(th, dir1[s], g1);
+                for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
+                    if (j < np)
+                        h |= collide_exact((double)sh[s].x, (double)sh[s].y, (double)pl[j].x, (double)pl[j].y, c.r2_sp);
             }
-            if (S == 2) {
-                if (collide(sh[0].x, sh[0].y, sh[S - 1].x, sh[S - 1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
-            }
-
-            const bool timeout = tick >= (uint32_t)p.timeout_tick;
-            float rw[S];
+            hits |= h ? (1u << s) : 0u;
+            float th = (ctl[s] & 1) ? c.thrust_f : 0.f;
+            B4 o = sh[s];
+            advance_body(o, __fmaf_rn(th, d0, g0), __fmaf_rn(th, d1, g1), c);  // core.py:283-288
+            ships[s * 32] = o;
+            ship_b[s * 32] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
+        }
+        t.dir[lane] = make_float4(dirs[0], dirs[1], dirs[2], dirs[3]);
+        if (S == 2) {
+            if (collide(sh[0].x, sh[0].y, sh[S - 1].x, sh[S - 1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
+        }
+        // planets (core.py:289-294): pair forces are antisymmetric, the clamped self term is zero
+        float q0[ASTRO_MAX_PLANETS], q1[ASTRO_MAX_PLANETS];
 #pragma unroll
-            for (int s = 0; s < S; s++) rw[s] = 0.0f;
-            if (hits) {  // core.py:253-255
-                ev = hits;  // ASTRO_EV_HIT0 | ASTRO_EV_HIT1 are bits 0 and 1
+        for (int i = 0; i < ASTRO_MAX_PLANETS; i++) { q0[i] = 0.f; q1[i] = 0.f; }
 #pragma unroll
-                for (int s = 0; s < S; s++) rw[s] = ((hits >> s) & 1u) ? -1.0f : 1.0f;
-            } else if (timeout) {  // core.py:257-260
-                ev = ASTRO_EV_TIMEOUT;
+        for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
 #pragma unroll
-                for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
-            } else {
-                const bool fire = tick < (uint32_t)p.n_sched_ticks && ((p.fire_bits[tick >> 5] >> (tick & 31)) & 1u);
-                if (fire) {  // core.py:267-280
-                    ev |= ASTRO_EV_FIRED;
-                    B4* row = tile_bullets + (size_t)lane * p.K;
-#pragma unroll
-                    for (int s = 0; s < S; s++) {
-                        // fp32 products as in the reference; the sums and the advance in fp32 too,
-                        // unless the newborn lands within the band of the arena bound
-                        float o0 = __fmul_rn(c.off_f, dir0[s]), o1 = __fmul_rn(c.off_f, dir1[s]);
-                        float w0 = __fmul_rn(c.spd_f, dir0[s]), w1 = __fmul_rn(c.spd_f, dir1[s]);
-                        B4 o;
-                        o.dx = __fadd_rn(sh[s].dx, w0);
-                        o.dy = __fadd_rn(sh[s].dy, w1);
-                        o.x = __fmaf_rn(c.dt_f, o.dx, __fadd_rn(sh[s].x, o0));
-                        o.y = __fmaf_rn(c.dt_f, o.dy, __fadd_rn(sh[s].y, o1));
-                        float e0 = fabsf(o.x), e1 = fabsf(o.y);
-                        bool keep = (e0 <= 1.0f) | (e1 <= 1.0f);
-                        if (__builtin_expect(fminf(fabsf(e0 - 1.0f), fabsf(e1 - 1.0f)) <= 8e-6f, 0)) {
-                            Body4<double> nbl;
-                            nbl.x = __dadd_rn((double)sh[s].x, (double)o0);
-                            nbl.y = __dadd_rn((double)sh[s].y, (double)o1);
-                            nbl.dx = __dadd_rn((double)sh[s].dx, (double)w0);
-                            nbl.dy = __dadd_rn((double)sh[s].dy, (double)w1);
-                            keep = advance_bullet(nbl, c);
-                            o.x = (float)nbl.x; o.y = (float)nbl.y; o.dx = (float)nbl.dx; o.dy = (float)nbl.dy;
-                        }
-                        if (keep) {
-                            if (m < p.K) {
-                                row[m] = o;
-                                m++;
-                            } else {
-                                ev |= ASTRO_EV_OVERFLOW;
-                            }
-                        }
-                    }
-                    spawned = S;
-                }
-#pragma unroll
-                for (int s = 0; s < S; s++) {  // core.py:283-288
-                    advance_body(sh[s], a0[s], a1[s], c);
-                    ships[s * 32] = sh[s];
-                    ship_b[s * 32] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
-                }
-                // planets (core.py:289-294): pair forces are antisymmetric, the clamped self term
-                // is exactly zero
-                float q0[ASTRO_MAX_PLANETS], q1[ASTRO_MAX_PLANETS];
-#pragma unroll
-                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) { q0[i] = 0.f; q1[i] = 0.f; }
-#pragma unroll
-                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
-#pragma unroll
-                    for (int j = i + 1; j < ASTRO_MAX_PLANETS; j++) {
-                        float r0 = __fsub_rn(pl[j].x, pl[i].x), r1 = __fsub_rn(pl[j].y, pl[i].y);
-                        float d2 = __fmaf_rn(r1, r1, __fmul_rn(r0, r0));
-                        float fj = (j < np) ? __fdividef(c.gm_f, fmaxf(1e-12f, d2)) : 0.f;
-                        q0[i] = __fmaf_rn(fj, r0, q0[i]);
-                        q1[i] = __fmaf_rn(fj, r1, q1[i]);
-                        q0[j] = __fmaf_rn(-fj, r0, q0[j]);
-                        q1[j] = __fmaf_rn(-fj, r1, q1[j]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
-                    if (i < np) {
-                        advance_body(pl[i], q0[i], q1[i], c);
-                        planets[i * 32] = pl[i];
-                    }
-                }
-                p.meta[g] = ASTRO_META_PACK(m, np, 0, tick + 1);
-                m_out = m;
-            }
-            if (ev & ASTRO_EV_DONE_MASK) {
-                if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0)
-                    recreate_from_pool<float, S>(p, g, ships, ship_b, planets);
-                else
-                    p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
-            }
-            if (p.reward) {
-                if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
-                else p.reward[g] = rw[0];
+            for (int j = i + 1; j < ASTRO_MAX_PLANETS; j++) {
+                float e0 = __fsub_rn(pl[j].x, pl[i].x), e1 = __fsub_rn(pl[j].y, pl[i].y);
+                float d2 = __fmaf_rn(e1, e1, __fmul_rn(e0, e0));
+                float fj = __fdividef(c.gm_f, fmaxf(1e-12f, d2));  // dead: 0, or e = 0
+                q0[i] = __fmaf_rn(fj, e0, q0[i]);
+                q1[i] = __fmaf_rn(fj, e1, q1[i]);
+                q0[j] = __fmaf_rn(-fj, e0, q0[j]);
+                q1[j] = __fmaf_rn(-fj, e1, q1[j]);
             }
         }
-        if (p.events) p.events[g] = (uint8_t)ev;
-        if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
+#pragma unroll
+        for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
+            if (i < np) {
+                advance_body(pl[i], q0[i], q1[i], c);
+                planets[i * 32] = pl[i];
+            }
+        }
     }
+    __syncwarp();
+
+    // ================= 4. the bullet loop ============================================================
+    auto process = [&](unsigned base, const ItemRef& r, B4 b) {
+        const unsigned gi = r.game;
+        bool keep = false;
+        unsigned sh_hits = 0;
+        if (r.valid) keep = bullet_step<S>(b, t.sxy[gi], t.pxy[0][gi], t.pxy[1][gi], t.np, gi, c, sh_hits);
+        if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
+        // stable in-place compaction inside each game's segment of the window
+        const unsigned kb = __ballot_sync(full, keep);
+        const unsigned seg_lo = r.excl > base ? r.excl - base : 0u;  // < 32 for a valid item
+        const unsigned rank = __popc(kb & (lt_mask & (full << seg_lo)));
+        const unsigned ob = t.outn[gi];
+        const unsigned g_next = __shfl_down_sync(full, gi, 1);
+        const bool last = r.valid && (lane == 31u || base + lane + 1u >= total || g_next != gi);
+        __syncwarp();
+        if (keep) tile_bullets[gi * K + ob + rank] = b;
+        if (last) t.outn[gi] = ob + rank + (keep ? 1u : 0u);
+        __syncwarp();
+    };
+    for (unsigned base = 0; base < total; base += 96u) {
+        fetch(base + 64u, r2, b2);
+        process(base, r0, b0);
+        if (base + 32u >= total) break;
+        fetch(base + 96u, r0, b0);
+        process(base + 32u, r1, b1);
+        if (base + 64u >= total) break;
+        fetch(base + 128u, r1, b1);
+        process(base + 64u, r2, b2);
+    }
+
+    // ================= 5. terminal logic, spawn, bookkeeping ==========================================
+    uint32_t ev = 0;
+    int m_out = 0, spawned = 0;
+    float rw[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) rw[s] = 0.0f;
+    if (!active) {
+        ev = ASTRO_EV_SKIPPED;
+    } else {
+        int m = (int)t.outn[lane];
+        hits |= t.hits[lane];
+        const bool timeout = tick >= (uint32_t)p.timeout_tick;
+        if (hits) {  // core.py:253-255
+            ev = hits;  // ASTRO_EV_HIT0 | ASTRO_EV_HIT1 are bits 0 and 1
+#pragma unroll
+            for (int s = 0; s < S; s++) rw[s] = ((hits >> s) & 1u) ? -1.0f : 1.0f;
+        } else if (timeout) {  // core.py:257-260
+            ev = ASTRO_EV_TIMEOUT;
+#pragma unroll
+            for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
+        } else {
+            const bool fire = tick < (uint32_t)p.n_sched_ticks && ((p.fire_bits[tick >> 5] >> (tick & 31)) & 1u);
+            if (fire) {  // core.py:267-280, from the OLD ship state
+                ev |= ASTRO_EV_FIRED;
+                B4* row = tile_bullets + lane * K;
+                const float4 dv = t.dir[lane];
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    const float4 o_ship = t.ship[s][lane];
+                    const float d0 = s == 0 ? dv.x : dv.z, d1 = s == 0 ? dv.y : dv.w;
+                    // fp32 products as in the reference; the sums and the advance in fp32 too,
+                    // unless the newborn lands within the band of the arena bound
+                    float o0 = __fmul_rn(c.off_f, d0), o1 = __fmul_rn(c.off_f, d1);
+                    float w0 = __fmul_rn(c.spd_f, d0), w1 = __fmul_rn(c.spd_f, d1);
+                    B4 o;
+                    o.dx = __fadd_rn(o_ship.z, w0);
+                    o.dy = __fadd_rn(o_ship.w, w1);
+                    o.x = __fmaf_rn(c.dt_f, o.dx, __fadd_rn(o_ship.x, o0));
+                    o.y = __fmaf_rn(c.dt_f, o.dy, __fadd_rn(o_ship.y, o1));
+                    float mn = fminf(fabsf(o.x), fabsf(o.y));
+                    bool keep = mn <= 1.0f;
+                    if (__builtin_expect(fabsf(mn - 1.0f) <= 8e-6f, 0)) {
+                        Body4<double> nbl;
+                        nbl.x = __dadd_rn((double)o_ship.x, (double)o0);
+                        nbl.y = __dadd_rn((double)o_ship.y, (double)o1);
+                        nbl.dx = __dadd_rn((double)o_ship.z, (double)w0);
+                        nbl.dy = __dadd_rn((double)o_ship.w, (double)w1);
+                        keep = advance_bullet(nbl, c);
+                        o.x = (float)nbl.x; o.y = (float)nbl.y; o.dx = (float)nbl.dx; o.dy = (float)nbl.dy;
+                    }
+                    if (keep) {
+                        if (m < (int)K) {
+                            row[m] = o;
+                            m++;
+                        } else {
+                            ev |= ASTRO_EV_OVERFLOW;
+                        }
+                    }
+                }
+                spawned = S;
+            }
+            p.meta[g] = ASTRO_META_PACK(m, np, 0, tick + 1);
+            m_out = m;
+        }
+        if (ev & ASTRO_EV_DONE_MASK) {
+            if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0) {
+                recreate_from_pool<float, S>(p, g, ships, ship_b, planets);
+            } else {
+                // the game ends here: put the pre-step ships and planets back
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    *reinterpret_cast<float4*>(&ships[s * 32]) = t.ship[s][lane];
+                    ship_b[s * 32] = sb[s];
+                }
+#pragma unroll
+                for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
+                    if (j < np) *reinterpret_cast<float4*>(&planets[j * 32]) = t.planet[j][lane];
+                p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
+            }
+        }
+    }
+    if (p.reward) {
+        if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
+        else p.reward[g] = rw[0];
+    }
+    if (p.events) p.events[g] = (uint8_t)ev;
+    if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
+
     if (STATS) {
-        warp_stats(s_stats, (int)lane, S, ev, active, spawned, np, nb, m_out);
-        __syncthreads();
-        if (threadIdx.x < ASTRO_N_STATS && s_stats[threadIdx.x]) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
+        // warp totals -> this warp's private slot row in HBM (no atomics, no block barrier);
+        // astro_stats() folds the rows
+        unsigned mine = warp_totals((int)lane, S, ev, active, spawned, np, nb, m_out);
+        unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
+        if (lane < ASTRO_N_STATS && mine) atomicAdd(slot, mine);  // RED: fire and forget, row is private
     }
 }
