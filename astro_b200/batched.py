@@ -233,15 +233,16 @@ class BatchedGames:
         nat.check(nat.lib().astro_set_reset_pool(self._h, C.byref(pool)))
 
     def reset_done(self):
-        """Re-create every finished game from the pool (episode counter + 1 picks the entry)."""
+        """Re-create every finished game from the pool (entry = pick(seed, game, current step))."""
         if self.n != self.n_pad:
             raise ValueError('reset_done needs n_games to be a multiple of %d' % nat.TILE)
         nat.check(nat.lib().astro_reset_done(self._h, self._stream()))
 
     def reset_all(self):
-        """(Re)start every game from the pool: game g starts as pool[pick(seed, g, episode 0)]."""
+        """(Re)start every game from the pool: game g starts as pool[pick(seed, g, key 0)]."""
         self.meta.fill_(1 << 13)
         self.episode.fill_(-1)
+        self.set_stream(step=0)
         self.reset_done()
 
     # ---- the tick ---------------------------------------------------------------------------------

@@ -54,14 +54,15 @@ struct TickParams {
 
 
 // Re-create game g from the reset pool (core.create, core.py:86-135, evaluated on the host):
-// entry pick(seed, global game id, episode + 1); bullets cleared, tick 0.
+// entry pick(seed, global game id, key) with key = 1 + the stream step of the tick that ended the
+// game (0 for the initial fill) — no dependent load on the way; bullets cleared, tick 0.  The
+// per-slot episode counter is bumped with a fire-and-forget RED.
 template <typename R, int S>
-__device__ __forceinline__ void recreate_from_pool(const TickParams& p, int g, Body4<R>* ships, R* ship_b,
-                                                   Body4<R>* planets) {
+__device__ __forceinline__ void recreate_from_pool(const TickParams& p, int g, uint32_t key, Body4<R>* ships,
+                                                   R* ship_b, Body4<R>* planets) {
     using B4 = Body4<R>;
-    uint32_t ep = p.episode[g] + 1;
-    p.episode[g] = ep;
-    uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, ep, (uint32_t)p.pool_size);
+    atomicAdd(&p.episode[g], 1u);
+    uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, key, (uint32_t)p.pool_size);
     const R* ps = reinterpret_cast<const R*>(p.pool_ships) + (size_t)k * (S * 5);
     const R* pp = reinterpret_cast<const R*>(p.pool_planets) + (size_t)k * (ASTRO_MAX_PLANETS * 4);
     int np_new = p.pool_np[k];
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
 
             if (ev & ASTRO_EV_DONE_MASK) {
                 if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0) {
-                    recreate_from_pool<R, S>(p, g, ships, ship_b, planets);
+                    recreate_from_pool<R, S>(p, g, p.step + 1u, ships, ship_b, planets);
                 } else {
                     p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
                 }
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(kTickThreads) reset_kernel(const __grid_consta
     B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
     R* ship_b = reinterpret_cast<R*>(p.ship_b) + tile * (S * 32) + lane;
     B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
-    recreate_from_pool<R, S>(p, g, ships, ship_b, planets);
+    recreate_from_pool<R, S>(p, g, p.step, ships, ship_b, planets);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -24,18 +24,26 @@
 constexpr float kFar = 1.0e20f;
 constexpr int kTickWarps = kTickThreads / 32;
 
+constexpr int kStageWindows = 8;   // bullets staged per round: 8 windows x 32 = 256 (4 KB per warp)
+
 struct TileScratch {               // per warp
-    float4 ship[2][32];            // OLD x, y, dx, dy (lane-major: conflict-free 128-bit access)
-    float4 planet[4][32];          // OLD; dead slots at kFar
+    float4 bul[kStageWindows * 32];  // the tile's bullets, staged by cp.async (flat list order)
     float4 sxy[32];                // OLD ship0.xy, ship1.xy          } what the bullet loop reads,
     float4 pxy[2][32];             // OLD planet0.xy planet1.xy / 2,3 } addressed by game
-    float4 dir[32];                // sin/cos of both bearings (for the newborn bullets)
-    uint32_t excl[32];             // exclusive prefix of the bullet counts
+    float4 svel[32];               // OLD ship velocities   } for the newborn bullets
+    float4 dir[32];                // sin/cos of both bearings }
+    uint32_t cinfo[32];            // k-th non-empty game: game | first list index << 5
     uint32_t outn[32];             // survivors written so far
-    uint32_t hits[32];             // ship-hit bits found by the bullet loop
-    uint32_t np[32];
-    uint8_t compact[32];           // non-empty games in order
+    uint32_t hits[32];             // bits 0-1: ship hits found by the bullet loop; bits 8+: np
+    uint16_t ref[kStageWindows * 32];  // staged item -> game | slot << 5 ; 0xFFFF = none
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Exact (reference float64) evaluation of one bullet against the OLD ship / planet positions:
 // despawn flags, per-ship hit bits, advance + cull.  Taken by ~1e-5 of bullets.
@@ -73,7 +81,7 @@ __device__ __forceinline__ float dist2(float ax, float ay, float bx, float by) {
 // smaller magnitude can sit in the uncertainty band.
 template <int S>
 __device__ __forceinline__ bool bullet_step(Body4<float>& b, float4 sxy, float4 p01, float4 p23, const uint32_t* np_of,
-                                            unsigned gi, const Consts& c, unsigned& ship_hits) {
+                                            unsigned gi, const Consts& c, unsigned& ship_hits) {  // np_of[g] >> 8 = np
     float ds = dist2(sxy.x, sxy.y, b.x, b.y);
     if (S == 2) ds = fminf(ds, dist2(sxy.z, sxy.w, b.x, b.y));
     float dp = fminf(fminf(dist2(p01.x, p01.y, b.x, b.y), dist2(p01.z, p01.w, b.x, b.y)),
@@ -83,7 +91,7 @@ __device__ __forceinline__ bool bullet_step(Body4<float>& b, float4 sxy, float4 
     bool sure = (ds >= c.r2f_sb * 1.000001f) & (fabsf(dp - c.r2f_pb) > c.r2f_pb * 1e-6f) & (fabsf(mn - 1.0f) > 4e-6f);
     bool keep = (mn <= 1.0f) & (dp >= c.r2f_pb);
     if (__builtin_expect(!sure, 0)) {
-        ExactResult r = bullet_exact(b.x, b.y, b.dx, b.dy, sxy, p01, p23, S, (int)np_of[gi], c);
+        ExactResult r = bullet_exact(b.x, b.y, b.dx, b.dy, sxy, p01, p23, S, (int)(np_of[gi] >> 8), c);
         x0 = r.x;
         x1 = r.y;
         keep = r.flags & 1u;
@@ -108,10 +116,11 @@ __device__ __forceinline__ ItemRef map_item(const TileScratch& t, unsigned base,
     unsigned le = full >> (31u - lane);
     unsigned idx = c0 + __popc(starts & le);  // >= 1 for a valid item
     c0 += __popc(starts);
+    unsigned ci = t.cinfo[(idx - 1u) & 31u];  // (stale only for invalid items)
     ItemRef r;
     r.valid = base + lane < total;
-    r.game = t.compact[(idx - 1u) & 31u] & 31u;  // (garbage only for invalid items)
-    r.excl = t.excl[r.game];
+    r.game = ci & 31u;
+    r.excl = ci >> 5;
     return r;
 }
 
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         if (j < np) plv[j] = *reinterpret_cast<const float4*>(&planets[j * 32]);
     }
 
-    // ================= 2. flat bullet list of the tile: scan, map, first loads in flight =======
+    // ================= 2. flat bullet list of the tile; stage it with cp.async =================
     unsigned incl = (unsigned)nb;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -179,37 +188,36 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     const unsigned my_excl = incl - (unsigned)nb;
     const unsigned total = __shfl_sync(full, incl, 31);
     const bool nonempty = nb > 0;
-    t.excl[lane] = my_excl;
     t.outn[lane] = 0u;
-    t.hits[lane] = 0u;
-    t.np[lane] = (unsigned)np;
+    t.hits[lane] = (unsigned)np << 8;
     const unsigned ne = __ballot_sync(full, nonempty);
     const unsigned lt_mask = (1u << lane) - 1u;
-    if (nonempty) t.compact[__popc(ne & lt_mask)] = (uint8_t)lane;
+    if (nonempty) t.cinfo[__popc(ne & lt_mask)] = lane | (my_excl << 5);
     __syncwarp();
     unsigned c0 = 0;
-    // One window = 32 consecutive list items.  Bullets are fetched two windows ahead of their
-    // use; prefetched items are later list items, never a slot an earlier window's stores touch.
-    auto fetch = [&](unsigned base, ItemRef& r, B4& b) {
-        r = map_item(t, base, total, my_excl, nonempty, lane, c0);
-        if (r.valid) b = tile_bullets[r.game * K + (base + lane - r.excl)];
+    // One window = 32 consecutive list items; a round = up to kStageWindows windows, all requested
+    // at once (16-byte cp.async each), so the whole tile's bullet traffic is in flight together.
+    auto stage_round = [&](unsigned round_base) {
+#pragma unroll 1
+        for (unsigned w = 0; w < (unsigned)kStageWindows; w++) {
+            const unsigned base = round_base + w * 32u;
+            if (base >= total) break;
+            ItemRef r = map_item(t, base, total, my_excl, nonempty, lane, c0);
+            const unsigned slot = base + lane - r.excl;
+            if (r.valid) cp_async16(&t.bul[w * 32u + lane], &tile_bullets[r.game * K + slot]);
+            t.ref[w * 32u + lane] = r.valid ? (uint16_t)(r.game | (slot << 5)) : (uint16_t)0xFFFFu;
+        }
+        cp_async_commit();
     };
-    ItemRef r0, r1, r2;
-    B4 b0, b1, b2;
-    b0.x = b0.y = b0.dx = b0.dy = 0.f;
-    b1 = b0;
-    b2 = b0;
-    fetch(0u, r0, b0);
-    fetch(32u, r1, b1);
+    stage_round(0u);
 
-    // ================= 3. ships and planets while those loads fly ================================
-    // OLD positions staged for the bullet loop (addressed by game), OLD bodies kept for the
-    // newborn bullets and for restoring a game that ends without auto-reset.
-#pragma unroll
-    for (int s = 0; s < S; s++) t.ship[s][lane] = shv[s];
-#pragma unroll
-    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) t.planet[j][lane] = plv[j];
+    // ================= 3. ships and planets while the bullets fly ===============================
+    // OLD positions are staged for the bullet loop (addressed by game); the new ship / planet state
+    // goes straight to HBM.  (A game that ends is re-created below; without auto-reset its
+    // ships and planets are left in this post-step state: the state of a finished game is
+    // unspecified, the reference has none.)
     t.sxy[lane] = make_float4(shv[0].x, shv[0].y, shv[S - 1].x, shv[S - 1].y);
+    t.svel[lane] = make_float4(shv[0].z, shv[0].w, shv[S - 1].z, shv[S - 1].w);
     t.pxy[0][lane] = make_float4(plv[0].x, plv[0].y, plv[1].x, plv[1].y);
     t.pxy[1][lane] = make_float4(plv[2].x, plv[2].y, plv[3].x, plv[3].y);
     unsigned hits = 0;
@@ -221,8 +229,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
 #pragma unroll
         for (int j = 0; j < ASTRO_MAX_PLANETS; j++) { pl[j].x = plv[j].x; pl[j].y = plv[j].y; pl[j].dx = plv[j].z; pl[j].dy = plv[j].w; }
         float dirs[4] = {0.f, 0.f, 0.f, 0.f};
-        // direction, gravity, ship-planet and ship-ship collisions on the old state; then the
-        // new ship state goes straight to HBM (a game that ends is restored / re-created below)
+        // direction, gravity, ship-planet and ship-ship collisions on the old state
 #pragma unroll
         for (int s = 0; s < S; s++) {
             float d0, d1;
@@ -283,36 +290,38 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
             }
         }
     }
-    __syncwarp();
 
-    // ================= 4. the bullet loop ============================================================
-    auto process = [&](unsigned base, const ItemRef& r, B4 b) {
-        const unsigned gi = r.game;
-        bool keep = false;
-        unsigned sh_hits = 0;
-        if (r.valid) keep = bullet_step<S>(b, t.sxy[gi], t.pxy[0][gi], t.pxy[1][gi], t.np, gi, c, sh_hits);
-        if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
-        // stable in-place compaction inside each game's segment of the window
-        const unsigned kb = __ballot_sync(full, keep);
-        const unsigned seg_lo = r.excl > base ? r.excl - base : 0u;  // < 32 for a valid item
-        const unsigned rank = __popc(kb & (lt_mask & (full << seg_lo)));
-        const unsigned ob = t.outn[gi];
-        const unsigned g_next = __shfl_down_sync(full, gi, 1);
-        const bool last = r.valid && (lane == 31u || base + lane + 1u >= total || g_next != gi);
+    // ================= 4. the bullet loop, from shared memory =======================================
+    for (unsigned round_base = 0; round_base < total; round_base += (unsigned)kStageWindows * 32u) {
+        if (round_base) stage_round(round_base);  // (tiles with more than 256 bullets: rare)
+        cp_async_wait_all();
         __syncwarp();
-        if (keep) tile_bullets[gi * K + ob + rank] = b;
-        if (last) t.outn[gi] = ob + rank + (keep ? 1u : 0u);
-        __syncwarp();
-    };
-    for (unsigned base = 0; base < total; base += 96u) {
-        fetch(base + 64u, r2, b2);
-        process(base, r0, b0);
-        if (base + 32u >= total) break;
-        fetch(base + 96u, r0, b0);
-        process(base + 32u, r1, b1);
-        if (base + 64u >= total) break;
-        fetch(base + 128u, r1, b1);
-        process(base + 64u, r2, b2);
+#pragma unroll 1
+        for (unsigned w = 0; w < (unsigned)kStageWindows; w++) {
+            const unsigned base = round_base + w * 32u;
+            if (base >= total) break;
+            const unsigned ref = t.ref[w * 32u + lane];
+            const bool valid = ref != 0xFFFFu;
+            const unsigned gi = ref & 31u, slot = (ref >> 5) & 1023u;
+            const float4 bv = t.bul[w * 32u + lane];
+            B4 b;
+            b.x = bv.x; b.y = bv.y; b.dx = bv.z; b.dy = bv.w;
+            bool keep = false;
+            unsigned sh_hits = 0;
+            if (valid) keep = bullet_step<S>(b, t.sxy[gi], t.pxy[0][gi], t.pxy[1][gi], t.hits, gi, c, sh_hits);
+            if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
+            // stable in-place compaction inside each game's segment of the window
+            const unsigned kb = __ballot_sync(full, keep);
+            const unsigned seg_lo = slot < lane ? lane - slot : 0u;  // first lane of this game's segment
+            const unsigned rank = __popc(kb & (lt_mask & (full << seg_lo)));
+            const unsigned ob = t.outn[gi];
+            const unsigned g_next = __shfl_down_sync(full, valid ? gi : 32u, 1);
+            const bool last = valid && (lane == 31u || g_next != gi);
+            __syncwarp();
+            if (keep) tile_bullets[gi * K + ob + rank] = b;
+            if (last) t.outn[gi] = ob + rank + (keep ? 1u : 0u);
+            __syncwarp();
+        }
     }
 
     // ================= 5. terminal logic, spawn, bookkeeping ==========================================
@@ -325,7 +334,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         ev = ASTRO_EV_SKIPPED;
     } else {
         int m = (int)t.outn[lane];
-        hits |= t.hits[lane];
+        hits |= t.hits[lane] & 3u;
         const bool timeout = tick >= (uint32_t)p.timeout_tick;
         if (hits) {  // core.py:253-255
             ev = hits;  // ASTRO_EV_HIT0 | ASTRO_EV_HIT1 are bits 0 and 1
@@ -340,28 +349,29 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
             if (fire) {  // core.py:267-280, from the OLD ship state
                 ev |= ASTRO_EV_FIRED;
                 B4* row = tile_bullets + lane * K;
-                const float4 dv = t.dir[lane];
+                const float4 dv = t.dir[lane], oxy = t.sxy[lane], ov = t.svel[lane];
 #pragma unroll
                 for (int s = 0; s < S; s++) {
-                    const float4 o_ship = t.ship[s][lane];
                     const float d0 = s == 0 ? dv.x : dv.z, d1 = s == 0 ? dv.y : dv.w;
+                    const float sx = s == 0 ? oxy.x : oxy.z, sy = s == 0 ? oxy.y : oxy.w;
+                    const float vx = s == 0 ? ov.x : ov.z, vy = s == 0 ? ov.y : ov.w;
                     // fp32 products as in the reference; the sums and the advance in fp32 too,
                     // unless the newborn lands within the band of the arena bound
                     float o0 = __fmul_rn(c.off_f, d0), o1 = __fmul_rn(c.off_f, d1);
                     float w0 = __fmul_rn(c.spd_f, d0), w1 = __fmul_rn(c.spd_f, d1);
                     B4 o;
-                    o.dx = __fadd_rn(o_ship.z, w0);
-                    o.dy = __fadd_rn(o_ship.w, w1);
-                    o.x = __fmaf_rn(c.dt_f, o.dx, __fadd_rn(o_ship.x, o0));
-                    o.y = __fmaf_rn(c.dt_f, o.dy, __fadd_rn(o_ship.y, o1));
+                    o.dx = __fadd_rn(vx, w0);
+                    o.dy = __fadd_rn(vy, w1);
+                    o.x = __fmaf_rn(c.dt_f, o.dx, __fadd_rn(sx, o0));
+                    o.y = __fmaf_rn(c.dt_f, o.dy, __fadd_rn(sy, o1));
                     float mn = fminf(fabsf(o.x), fabsf(o.y));
                     bool keep = mn <= 1.0f;
                     if (__builtin_expect(fabsf(mn - 1.0f) <= 8e-6f, 0)) {
                         Body4<double> nbl;
-                        nbl.x = __dadd_rn((double)o_ship.x, (double)o0);
-                        nbl.y = __dadd_rn((double)o_ship.y, (double)o1);
-                        nbl.dx = __dadd_rn((double)o_ship.z, (double)w0);
-                        nbl.dy = __dadd_rn((double)o_ship.w, (double)w1);
+                        nbl.x = __dadd_rn((double)sx, (double)o0);
+                        nbl.y = __dadd_rn((double)sy, (double)o1);
+                        nbl.dx = __dadd_rn((double)vx, (double)w0);
+                        nbl.dy = __dadd_rn((double)vy, (double)w1);
                         keep = advance_bullet(nbl, c);
                         o.x = (float)nbl.x; o.y = (float)nbl.y; o.dx = (float)nbl.dx; o.dy = (float)nbl.dy;
                     }
@@ -380,20 +390,10 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
             m_out = m;
         }
         if (ev & ASTRO_EV_DONE_MASK) {
-            if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0) {
-                recreate_from_pool<float, S>(p, g, ships, ship_b, planets);
-            } else {
-                // the game ends here: put the pre-step ships and planets back
-#pragma unroll
-                for (int s = 0; s < S; s++) {
-                    *reinterpret_cast<float4*>(&ships[s * 32]) = t.ship[s][lane];
-                    ship_b[s * 32] = sb[s];
-                }
-#pragma unroll
-                for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
-                    if (j < np) *reinterpret_cast<float4*>(&planets[j * 32]) = t.planet[j][lane];
+            if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0)
+                recreate_from_pool<float, S>(p, g, p.step + 1u, ships, ship_b, planets);
+            else
                 p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
-            }
         }
     }
     if (p.reward) {
@@ -404,10 +404,10 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
 
     if (STATS) {
-        // warp totals -> this warp's private slot row in HBM (no atomics, no block barrier);
+        // warp totals -> this warp's private slot row in HBM (no block barrier, no contention);
         // astro_stats() folds the rows
         unsigned mine = warp_totals((int)lane, S, ev, active, spawned, np, nb, m_out);
         unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
-        if (lane < ASTRO_N_STATS && mine) atomicAdd(slot, mine);  // RED: fire and forget, row is private
+        if (lane < ASTRO_N_STATS && mine) atomicAdd(slot, mine);  // RED: fire and forget
     }
 }

@@ -49,7 +49,8 @@ def actions(seed, game_ids, step, nships):
 
 
 def pool_pick(seed, game_ids, episode, pool_size):
-    """Reset-pool entry used by global game `g` for its `episode`-th game (episode>=0)."""
+    """Reset-pool entry for global game `g`; `episode` is the pick key: 0 for the initial fill,
+    1 + the stream step of the tick that ended the previous game afterwards."""
     with np.errstate(over='ignore'):
         g = np.asarray(game_ids, dtype=_U32)
         e = np.asarray(episode, dtype=_U32)

@@ -26,7 +26,7 @@
  *     bullets  R4  [n_games][K]          game-major: a game's pool is one contiguous row; slots
  *                                        >= nb are dead; order = reference order
  *     meta     u32 [n_tiles*32]          nb (bits 0-9) | np (10-12) | finished (13) | tick (14-31)
- *     episode  u32 [n_tiles*32]          games finished in this slot (reset-pool stream key)
+ *     episode  u32 [n_tiles*32]          games finished in this slot (a counter; bumped on reset)
  * Ships, planets and meta are accessed thread-per-game: every load/store is a fully coalesced
  * 128-bit (R=float) access across the warp.  Bullets are processed by the warp as one flat list
  * per tile (see csrc/tick_f32.cuh), 32 consecutive list items per step: contiguous runs.
@@ -147,7 +147,9 @@ int astro_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* do
 int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_host, uint8_t* done_host,
                     uint8_t* events_host, int32_t flags, void* stream);
 
-/* Re-initialise finished games from the reset pool (the stand-alone form of AUTO_RESET). */
+/* Re-initialise finished games from the reset pool (the stand-alone form of AUTO_RESET).
+ * Pool entry = pick(seed, global game id, key): key = 0 for the initial fill, 1 + the stream step of
+ * the tick that ended the game for AUTO_RESET, the current stream step here. */
 int astro_reset_done(AstroBatch* b, void* stream);
 
 /* rl.ValueNetwork.get_features + to_batch (rl.py:43-99) with core.roll_ships (core.py:306-327)

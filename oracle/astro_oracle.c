@@ -395,9 +395,9 @@ static inline int action_for(uint32_t seed, uint32_t game, uint32_t step, uint32
     uint32_t h = mix32(h0 ^ (step * 2u + ship));
     return (int)(((uint64_t)h * 6u) >> 32);
 }
-static inline uint32_t pool_pick(uint32_t seed, uint32_t game, uint32_t episode, uint32_t pool_size) {
+static inline uint32_t pool_pick(uint32_t seed, uint32_t game, uint32_t key, uint32_t pool_size) {
     uint32_t h0 = mix32(seed ^ 0xA5A5A5A5u ^ (game * 0x9E3779B1u));
-    uint32_t h = mix32(h0 ^ episode);
+    uint32_t h = mix32(h0 ^ key);
     return (uint32_t)(((uint64_t)h * pool_size) >> 32);
 }
 
@@ -445,7 +445,8 @@ int64_t ao_rollout(const ao_config* c, int64_t n, int S, int K, double* ships, d
                     else loc[3]++;
                     if (M > 0) {
                         episode[i]++;
-                        int64_t p = pool_pick(seed, g, episode[i], (uint32_t)M);
+                        /* key = 1 + the rollout step that ended the game (0 = initial fill) */
+                        int64_t p = pool_pick(seed, g, step0 + (uint32_t)k + 1u, (uint32_t)M);
                         memcpy(sh, pool_ships + p * S * 5, sizeof(double) * 5 * S);
                         memcpy(pl, pool_planets + p * AO_MAXP * 4, sizeof(double) * 4 * AO_MAXP);
                         np_[i] = pool_np[p]; nb[i] = 0; reload[i] = 0.0; t[i] = 0.0;

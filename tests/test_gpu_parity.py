@@ -186,9 +186,8 @@ def _teacher_forced(cfg, N, K, ticks, precision, pool_size=512, seed=0, first_ga
         # games that ended were re-created from the pool in the same launch
         dead = ~live
         if dead.any():
-            ep = arr['episode'][dead] + 1
-            pick = rng.pool_pick(seed, ids[dead], ep, pool_size)
-            assert (new['episode'][dead] == ep).all(), k
+            pick = rng.pool_pick(seed, ids[dead], np.full(int(dead.sum()), k + 1, dtype=np.uint32), pool_size)
+            assert (new['episode'][dead] == arr['episode'][dead] + 1).all(), k
             assert (new['ships'][dead] == rpool['ships'][pick]).all(), k
             assert (new['n_planets'][dead] == rpool['np'][pick]).all(), k
             assert (new['n_bullets'][dead] == 0).all() and (new['tick'][dead] == 0).all(), k
