@@ -57,6 +57,7 @@ class BatchedGames:
         self._actions = torch.zeros((self.n_pad, S), dtype=torch.uint8, device=dev)
         self._stats = torch.zeros((nat.N_STATS,), dtype=torch.int64, device=dev)
         self._pool = None
+        self.tick_flags = 0      # extra ASTRO_TICK_* bits OR-ed into every tick (kernel A/B selection)
 
         L = nat.lib()
         cfg = nat.AstroConfig()
@@ -268,7 +269,7 @@ class BatchedGames:
                     raise ValueError('actions must have shape [%d, %d]' % (self.n, self.S))
                 self._actions[:self.n].copy_(actions)
                 a_ptr = self._actions.data_ptr()
-        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS)
+        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
         nat.check(nat.lib().astro_tick(self._h, a_ptr, self._reward.data_ptr() if want_reward else None,
                                        self._done.data_ptr(), self._events.data_ptr(), flags, self._stream()))
         self.step_index += 1
@@ -288,7 +289,7 @@ class BatchedGames:
             if x is None:
                 return None
             return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
-        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS)
+        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
         for x, nbytes in ((actions_host, self.n_pad * self.S), (events_host, self.n_pad)):
             if x is not None and (x.numel() * x.element_size() if hasattr(x, 'numel') else x.nbytes) < nbytes:
                 raise ValueError('host buffer too small: need %d bytes' % nbytes)

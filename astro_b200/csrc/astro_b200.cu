@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <new>
 
 using namespace astro;
@@ -385,6 +386,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
 
 
 #include "tick_f32.cuh"
+#include "tick_f32_pipe.cuh"
 
 // ------------------------------------------------------------------------------------------
 // reset_kernel: stand-alone form of AUTO_RESET — finished games are re-created from the pool.
@@ -613,6 +615,37 @@ cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// Persistent pipelined kernel: one resident wave of CTAs, each warp walks tiles with stride W.
+template <int S, bool STATS, bool ROWS>
+cudaError_t launch_tick_pipe_one(const TickParams& p, cudaStream_t st) {
+    static int resident = 0;  // CTAs that fit on the device (per instantiation; one device type per process)
+    const size_t smem = sizeof(PipeScratch<ROWS>) * kPipeWarps;
+    auto kernel = tick_f32_pipe_kernel<S, STATS, ROWS>;
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPipeThreads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        resident = sms * per_sm;
+    }
+    const int n_tiles = p.n_games / ASTRO_TILE;
+    int grid = (n_tiles + kPipeWarps - 1) / kPipeWarps;
+    if (grid > resident) grid = resident;
+    kernel<<<grid, kPipeThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+template <int S>
+cudaError_t launch_tick_pipe(const TickParams& p, cudaStream_t st) {
+    const bool rows = (p.flags & ASTRO_TICK_PREFETCH_ROWS) != 0;
+    if (p.flags & ASTRO_TICK_NO_STATS)
+        return rows ? launch_tick_pipe_one<S, false, true>(p, st) : launch_tick_pipe_one<S, false, false>(p, st);
+    return rows ? launch_tick_pipe_one<S, true, true>(p, st) : launch_tick_pipe_one<S, true, false>(p, st);
+}
+
 cudaError_t fold_stats(AstroBatch* b, cudaStream_t st) {
     fold_stats_kernel<<<64, 256, 0, st>>>(b->d_stat_slots, b->n_games / ASTRO_TILE, b->d_stats);
     b->ticks_since_fold = 0;
@@ -635,6 +668,8 @@ int do_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done,
     cudaError_t e;
     if (b->precision == 32 && (flags & ASTRO_TICK_GENERIC_KERNEL))
         e = b->S == 2 ? launch_tick<float, 2>(p, st) : launch_tick<float, 1>(p, st);
+    else if (b->precision == 32 && (flags & (ASTRO_TICK_PERSISTENT | ASTRO_TICK_PREFETCH_ROWS)))
+        e = b->S == 2 ? launch_tick_pipe<2>(p, st) : launch_tick_pipe<1>(p, st);
     else if (b->precision == 32)
         e = b->S == 2 ? launch_tick_f32<2>(p, st) : launch_tick_f32<1>(p, st);
     else

@@ -125,7 +125,7 @@ __device__ __forceinline__ ItemRef map_item(const TileScratch& t, unsigned base,
 }
 
 #ifndef ASTRO_TICK_MIN_BLOCKS
-#define ASTRO_TICK_MIN_BLOCKS 8
+#define ASTRO_TICK_MIN_BLOCKS 7   /* shared memory admits 7 CTAs of 4 warps: 72 registers */
 #endif
 template <int S, bool STATS>
 __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
@@ -197,15 +197,28 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     unsigned c0 = 0;
     // One window = 32 consecutive list items; a round = up to kStageWindows windows, all requested
     // at once (16-byte cp.async each), so the whole tile's bullet traffic is in flight together.
+    const unsigned start_key = nonempty ? my_excl : 0x80000000u;  // empty games never "start"
+    const unsigned le_mask = full >> (31u - lane);
+    const unsigned bul_s = (unsigned)__cvta_generic_to_shared(&t.bul[lane]);
     auto stage_round = [&](unsigned round_base) {
+        const unsigned left = total - round_base;
+        const unsigned n_win = left >= (unsigned)kStageWindows * 32u ? (unsigned)kStageWindows : (left + 31u) >> 5;
 #pragma unroll 1
-        for (unsigned w = 0; w < (unsigned)kStageWindows; w++) {
+        for (unsigned w = 0; w < n_win; w++) {
             const unsigned base = round_base + w * 32u;
-            if (base >= total) break;
-            ItemRef r = map_item(t, base, total, my_excl, nonempty, lane, c0);
-            const unsigned slot = base + lane - r.excl;
-            if (r.valid) cp_async16(&t.bul[w * 32u + lane], &tile_bullets[r.game * K + slot]);
-            t.ref[w * 32u + lane] = r.valid ? (uint16_t)(r.game | (slot << 5)) : (uint16_t)0xFFFFu;
+            const unsigned rel = start_key - base;  // >= 32 unless this lane's game starts in the window
+            const unsigned starts = __reduce_or_sync(full, rel < 32u ? (1u << rel) : 0u);
+            const unsigned idx = c0 + __popc(starts & le_mask);  // >= 1 for a valid item
+            c0 += __popc(starts);
+            const unsigned ci = t.cinfo[(idx - 1u) & 31u];  // (stale only for invalid items)
+            const unsigned item = base + lane;
+            const bool valid = item < total;
+            const unsigned game = ci & 31u, slot = item - (ci >> 5);
+            if (valid)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bul_s + w * 512u),
+                             "l"(tile_bullets + (game * K + slot))
+                             : "memory");
+            t.ref[w * 32u + lane] = valid ? (uint16_t)(game | (slot << 5)) : (uint16_t)0xFFFFu;
         }
         cp_async_commit();
     };
@@ -296,10 +309,10 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         if (round_base) stage_round(round_base);  // (tiles with more than 256 bullets: rare)
         cp_async_wait_all();
         __syncwarp();
+        const unsigned left = total - round_base;
+        const unsigned n_win = left >= (unsigned)kStageWindows * 32u ? (unsigned)kStageWindows : (left + 31u) >> 5;
 #pragma unroll 1
-        for (unsigned w = 0; w < (unsigned)kStageWindows; w++) {
-            const unsigned base = round_base + w * 32u;
-            if (base >= total) break;
+        for (unsigned w = 0; w < n_win; w++) {
             const unsigned ref = t.ref[w * 32u + lane];
             const bool valid = ref != 0xFFFFu;
             const unsigned gi = ref & 31u, slot = (ref >> 5) & 1023u;

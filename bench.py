@@ -193,7 +193,7 @@ def run_ours(args):
     games = BatchedGames(cfg, n, bullet_cap=K, precision=32, device=local, seed=args.seed, first_game=plan['first_game'])
     games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
     games.reset_all()
-    flags = nat.TICK_AUTO_RESET
+    flags = nat.TICK_AUTO_RESET | args.tick_flags
     for _ in range(args.preroll):        # reach the stationary population (device counter-stream controls)
         games.step_raw(0, flags)
     torch.cuda.synchronize()
@@ -325,6 +325,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--ref-games', type=int, default=65536)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--tick-flags', type=int, default=0, help='extra ASTRO_TICK_* bits (kernel A/B)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':

@@ -68,6 +68,8 @@ extern "C" {
 #define ASTRO_TICK_AUTO_RESET 1 /* a game that ends is re-initialised from the reset pool in the same launch */
 #define ASTRO_TICK_NO_STATS 2   /* skip the astro_stats counters for this tick */
 #define ASTRO_TICK_GENERIC_KERNEL 4 /* precision 32 only: run the un-tuned template kernel (A/B checks) */
+#define ASTRO_TICK_PERSISTENT 8     /* precision 32 only: persistent kernel, meta word one tile ahead (A/B) */
+#define ASTRO_TICK_PREFETCH_ROWS 16 /* precision 32 only: persistent kernel, next tile's rows staged too (A/B) */
 
 /* error codes */
 #define ASTRO_OK 0

@@ -135,13 +135,14 @@ def test_golden_edges_f32_discrete():
 
 # ------------------------------------------------------------------ config #2: 4,096 games
 
-def _teacher_forced(cfg, N, K, ticks, precision, pool_size=512, seed=0, first_game=0, start=None):
+def _teacher_forced(cfg, N, K, ticks, precision, pool_size=512, seed=0, first_game=0, start=None, tick_flags=0):
     """GPU tick vs oracle, the oracle re-fed the GPU's state every tick; auto-reset on."""
     S = 1 if cfg.solo else 2
     pool = H.make_pool(cfg, pool_size)
     games = _games(cfg, N, bullet_cap=K, precision=precision, seed=seed, first_game=first_game)
     games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
     games.reset_all()
+    games.tick_flags = tick_flags
     if start is not None:
         start(games)
     rpool = {k: (v.astype(games.np_rdtype).astype(np.float64) if v.dtype != np.int32 else v) for k, v in pool.items()}
@@ -210,6 +211,14 @@ def test_config2_4096_games_f32_teacher_forced():
     assert st['env_steps'] == 4096 * 1000 and st['episodes'] == n_done
     assert st['episodes'] == st['wins0'] + st['wins1'] + st['both_lost'] + st['timeouts']
     assert st['overflow'] == 0 and st['bullets_spawned'] == 2 * n_fired
+
+
+@pytest.mark.parametrize('flags', [nat.TICK_PERSISTENT, nat.TICK_PREFETCH_ROWS, nat.TICK_GENERIC_KERNEL])
+def test_kernel_variants_hold_the_same_parity(flags):
+    """The A/B kernels (persistent; persistent with staged rows; generic template) pass
+    the same teacher-forced check as the default kernel, incl. a ragged tile count."""
+    _teacher_forced(core.DEFAULT_CONFIG, 4096 + 96, 32, 150, 32, tick_flags=flags)
+    _teacher_forced(core.DEFAULT_CONFIG, 2048, 400, 4, 32, start=_stress_fill(400, 5), tick_flags=flags)
 
 
 def test_4096_games_f64_teacher_forced_bit_exact():
