@@ -297,6 +297,21 @@ class BatchedGames:
                                             ptr(events_host), flags, self._stream()))
         self.step_index += 1
 
+    def rollout_host(self, actions_host, events_host, auto_reset=True, stats=True):
+        """Pipelined end-to-end rollout with HOST buffers: actions_host uint8 [T, n_pad, S], events_host
+        uint8 [T, n_pad] (pinned torch tensors or numpy arrays).  Every tick's controls are copied
+        in and its events copied out; copies of neighbouring ticks overlap the tick kernel."""
+        def ptr(x):
+            return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
+        T = int(actions_host.shape[0])
+        na = actions_host.numel() if hasattr(actions_host, 'numel') else actions_host.size
+        ne = events_host.numel() if hasattr(events_host, 'numel') else events_host.size
+        if na != T * self.n_pad * self.S or ne < T * self.n_pad:
+            raise ValueError('need actions [T, %d, %d] and events [T, %d]' % (self.n_pad, self.S, self.n_pad))
+        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
+        nat.check(nat.lib().astro_rollout_host(self._h, ptr(actions_host), ptr(events_host), T, flags, self._stream()))
+        self.step_index += T
+
     # ---- observations ----------------------------------------------------------------------------
     def observe(self, n_rows=None, out=None):
         """Feature batch [n, S, n_rows, D] float32: obs[g, k] is game g seen by ship k

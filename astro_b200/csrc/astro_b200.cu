@@ -529,6 +529,12 @@ struct AstroBatch {
     int64_t ticks_since_fold;
     uint8_t* d_actions;  // staging for astro_tick_host
     uint8_t* d_events;
+    // astro_rollout_host: double-buffered staging, copy streams and ordering events (created lazily)
+    uint8_t* d_actions2[2];
+    uint8_t* d_events2[2];
+    cudaStream_t copy_in, copy_out;
+    cudaEvent_t ev_in[2], ev_tick[2], ev_out[2];
+    bool pipe_ready;
     uint8_t* d_done;
     float* d_reward;
     uint32_t seed, step;
@@ -743,6 +749,17 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaFree(b->d_done);
     cudaFree(b->d_reward);
     cudaFree(b->d_fire_bits);
+    if (b->pipe_ready) {
+        for (int i = 0; i < 2; i++) {
+            cudaFree(b->d_actions2[i]);
+            cudaFree(b->d_events2[i]);
+            cudaEventDestroy(b->ev_in[i]);
+            cudaEventDestroy(b->ev_tick[i]);
+            cudaEventDestroy(b->ev_out[i]);
+        }
+        cudaStreamDestroy(b->copy_in);
+        cudaStreamDestroy(b->copy_out);
+    }
     delete b;
     return ASTRO_OK;
 }
@@ -811,6 +828,45 @@ int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_ho
     if (events_host) CUDA_TRY(cudaMemcpyAsync(events_host, b->d_events, n, cudaMemcpyDeviceToHost, st));
     if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, b->d_done, n, cudaMemcpyDeviceToHost, st));
     if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, b->d_reward, n * b->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ASTRO_OK;
+}
+
+int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* events_host, int32_t n_ticks, int32_t flags,
+                       void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!actions_host || !events_host || n_ticks < 0) return fail(ASTRO_E_INVALID, "bad rollout arguments");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)b->n_games, na = n * b->S;
+    if (!b->pipe_ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaMalloc(&b->d_actions2[i], na));
+            CUDA_TRY(cudaMalloc(&b->d_events2[i], n));
+            CUDA_TRY(cudaEventCreateWithFlags(&b->ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&b->ev_tick[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&b->ev_out[i], cudaEventDisableTiming));
+        }
+        b->pipe_ready = true;
+    }
+    // Three queues: controls of tick k+1 travel host->device while tick k runs and the events of
+    // tick k-1 travel device->host.  Buffer i = k % 2; an event per buffer and stage orders them.
+    for (int k = 0; k < n_ticks; k++) {
+        const int i = k & 1;
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(b->copy_in, b->ev_tick[i], 0));  // tick k-2 has read buffer i
+        CUDA_TRY(cudaMemcpyAsync(b->d_actions2[i], actions_host + (size_t)k * na, na, cudaMemcpyHostToDevice, b->copy_in));
+        CUDA_TRY(cudaEventRecord(b->ev_in[i], b->copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(st, b->ev_in[i], 0));
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_out[i], 0));  // events of tick k-2 have left buffer i
+        if (int r = do_tick(b, b->d_actions2[i], nullptr, nullptr, b->d_events2[i], flags, st)) return r;
+        CUDA_TRY(cudaEventRecord(b->ev_tick[i], st));
+        CUDA_TRY(cudaStreamWaitEvent(b->copy_out, b->ev_tick[i], 0));
+        CUDA_TRY(cudaMemcpyAsync(events_host + (size_t)k * n, b->d_events2[i], n, cudaMemcpyDeviceToHost, b->copy_out));
+        CUDA_TRY(cudaEventRecord(b->ev_out[i], b->copy_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(b->copy_out));
     CUDA_TRY(cudaStreamSynchronize(st));
     return ASTRO_OK;
 }

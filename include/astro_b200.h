@@ -149,6 +149,15 @@ int astro_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* do
 int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_host, uint8_t* done_host,
                     uint8_t* events_host, int32_t flags, void* stream);
 
+/* n_ticks consecutive astro_tick_host calls as one pipelined stream: actions_host u8
+ * [n_ticks][n_games][S], events_host u8 [n_ticks][n_games] (pinned).  The controls of tick k+1 are
+ * copied in while tick k runs and the events of tick k-1 are copied out (two internal copy
+ * streams, double-buffered staging).  Returns when every event byte is on the host.  This is
+ * the rollout loop of core.play / rl.train (core.py:388-404) for a host-side policy whose controls
+ * for a block of ticks are known up front (replays, scripted or random play). */
+int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* events_host, int32_t n_ticks,
+                       int32_t flags, void* stream);
+
 /* Re-initialise finished games from the reset pool (the stand-alone form of AUTO_RESET).
  * Pool entry = pick(seed, global game id, key): key = 0 for the initial fill, 1 + the stream step of
  * the tick that ended the game for AUTO_RESET, the current stream step here. */

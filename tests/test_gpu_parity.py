@@ -353,6 +353,35 @@ def test_features_api_matches_golden():
         assert (rl.ValueNetwork.to_batch([rl.ValueNetwork.get_features(s) for s in states]) == got).all()
 
 
+def test_rollout_host_pipelining_equals_tick_by_tick():
+    """astro_rollout_host (controls of tick k+1 / events of tick k-1 copied while tick k runs)
+    returns, tick for tick, the events of the unpipelined astro_tick_host and leaves the same state."""
+    import torch
+    cfg, N, K, T = core.DEFAULT_CONFIG, 8192, 32, 45
+    pool = H.make_pool(cfg, 256)
+    r = np.random.RandomState(3)
+    actions = torch.from_numpy(r.randint(0, 6, (T, N, 2)).astype(np.uint8)).pin_memory()
+
+    def fresh():
+        g = _games(cfg, N, bullet_cap=K, precision=32, seed=4)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        for _ in range(30):
+            g.step(None, auto_reset=True)
+        return g
+    a, b = fresh(), fresh()
+    ev_a = torch.empty((T, N), dtype=torch.uint8).pin_memory()
+    ev_b = torch.empty((T, N), dtype=torch.uint8).pin_memory()
+    a.rollout_host(actions, ev_a, auto_reset=True)
+    for k in range(T):
+        b.step_host(actions[k], ev_b[k], auto_reset=True)
+    assert bool((ev_a == ev_b).all()) and int((ev_a & 7).ne(0).sum()) > 100
+    xa, xb = a.get_arrays(), b.get_arrays()
+    for key in ('ships', 'n_bullets', 'tick', 'episode'):
+        assert (xa[key] == xb[key]).all(), key
+    assert a.stats() == b.stats()
+
+
 # ------------------------------------------------------------------ full-size properties
 
 def _events_digest(games, ticks, auto_reset=True):
