@@ -11,13 +11,14 @@ ship's (x, y, dx, dy, norm_angle(b)/pi), ship 0 first; the last 4 the object's (
 For rollouts use `BatchedGames.observe()` directly: it writes the padded batch for every game
 and both perspectives in one launch and never leaves the GPU.
 """
+
 import numpy as np
+import torch
 
 from . import core
 from .batched import BatchedGames
 
 _CACHE = {}
-
 
 def _games(solo, n, cap):
     n_pad = max(32, -(-n // 32) * 32)
@@ -28,10 +29,54 @@ def _games(solo, n, cap):
         g = _CACHE[key] = BatchedGames(cfg, n_pad, bullet_cap=cap, precision=64)
     return g
 
+class ValueNetwork(torch.nn.Module):
+    """The reference's Q-network (rl.py:32-165) with the feature extraction on the GPU.
 
-class ValueNetwork:
-    """Feature half of the reference's ValueNetwork; the torch network itself is unchanged
-    reference code and consumes these batches."""
+    Same constructor, layer names (`f0`, `f`, `v`, `v0` — state dicts interchange), feature
+    methods and `evaluate*` entry points.  The network body is the consumer of the observation
+    batches, plain PyTorch as in the reference: 15 (10 solo) -> 32, two softsign/linear blocks per
+    object, max-pool over the objects whose type flag is >= 0, two linear/softsign blocks,
+    linear -> tanh.  `forward` takes [..., N, D] feature batches on any device — for rollouts feed
+    it `BatchedGames.observe()` directly.
+    """
+
+    def __init__(self, solo, nout):
+        super().__init__()
+        width, depth = 32, 2
+        self.activation = torch.nn.functional.softsign
+        self.f0 = torch.nn.Linear(10 if solo else 15, width)
+        self.f = torch.nn.ModuleList([torch.nn.Linear(width, width) for _ in range(depth)])
+        self.pool = self.masked_max
+        self.v = torch.nn.ModuleList([torch.nn.Linear(width, width) for _ in range(depth)])
+        self.v0 = torch.nn.Linear(width, nout)
+
+    @staticmethod
+    def masked_max(x, features):
+        """Max over the object axis (-2), padding rows (type flag < 0) excluded (rl.py:115-128)."""
+        pad = (features[..., 0] < 0).unsqueeze(-1).to(x.dtype)
+        return torch.max(x - 1e9 * pad, dim=-2)[0]
+
+    @staticmethod
+    def masked_sum(x, features):
+        live = (features[..., 0] >= 0).unsqueeze(-1).to(x.dtype)
+        return torch.sum(x * live, dim=-2)
+
+    def forward(self, x):
+        h = self.f0(x)
+        for layer in self.f:
+            h = layer(self.activation(h))
+        h = self.pool(h, features=x)
+        for layer in self.v:
+            h = self.activation(layer(h))
+        return torch.tanh(self.v0(h))
+
+    def evaluate(self, state):
+        dev = next(self.parameters()).device
+        return self(torch.from_numpy(self.get_features(state)).to(dev))
+
+    def evaluate_batch(self, states):
+        dev = next(self.parameters()).device
+        return self(torch.from_numpy(self.get_features_batch(states)).to(dev))
 
     @staticmethod
     def get_features_shape(state):

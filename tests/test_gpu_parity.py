@@ -382,6 +382,31 @@ def test_rollout_host_pipelining_equals_tick_by_tick():
     assert a.stats() == b.stats()
 
 
+def test_value_network_single_vs_batch_and_padding_neutral():
+    """astro/test/test_rl.py:13-45 against the drop-in: single and batched evaluation agree, the
+    -1 padding is output-neutral, and BatchedGames.observe() feeds the same network on the GPU."""
+    import torch
+    from astro_b200 import rl
+    torch.manual_seed(1)
+    z, meta = H.load_traj()
+    g = 0
+    nb = z['g%d_nb' % g]
+    off = np.concatenate([[0], np.cumsum(nb)])
+    states = [H.state_from_arrays(z['g%d_ships' % g][k], z['g%d_planets' % g][k], z['g%d_bullets' % g][off[k]:off[k + 1]], 0.0, 0.0)
+              for k in (0, 20, 40, 60)]
+    net = rl.ValueNetwork(solo=False, nout=6).cuda()
+    single = torch.stack([net.evaluate(s) for s in states])
+    batch = net.evaluate_batch(states)
+    assert float((single - batch).abs().max()) < 1e-6
+    assert float((batch - net.evaluate_batch(states[::-1]).flip(0)).abs().max()) < 1e-6
+    games = _games(core.DEFAULT_CONFIG, len(states), bullet_cap=32, precision=64)
+    games.set_states(states, ticks=np.zeros(len(states), dtype=np.int64))
+    q = net(games.observe())                     # [n, 2, 6]: 36 rows incl. all -1 padding rows
+    assert float((q[:, 0] - batch).abs().max()) < 1e-6
+    rolled = net.evaluate_batch([core.roll_ships(s, 1) for s in states])
+    assert float((q[:, 1] - rolled).abs().max()) < 1e-6
+
+
 # ------------------------------------------------------------------ full-size properties
 
 def _events_digest(games, ticks, auto_reset=True):
