@@ -23,6 +23,9 @@
 // a minimum, never inside a band, and its gravity G*M/inf is exactly 0 — no predication on np.
 constexpr float kFar = 1.0e20f;
 constexpr int kTickWarps = kTickThreads / 32;
+#ifndef ASTRO_PREFETCH_PLANETS
+#define ASTRO_PREFETCH_PLANETS 4
+#endif
 
 constexpr int kStageWindows = 8;   // bullets staged per round: 8 windows x 32 = 256 (4 KB per warp)
 
@@ -125,7 +128,7 @@ __device__ __forceinline__ ItemRef map_item(const TileScratch& t, unsigned base,
 }
 
 #ifndef ASTRO_TICK_MIN_BLOCKS
-#define ASTRO_TICK_MIN_BLOCKS 7   /* shared memory admits 7 CTAs of 4 warps: 72 registers */
+#define ASTRO_TICK_MIN_BLOCKS 26  /* shared memory admits 26 one-warp CTAs per SM: 72 registers */
 #endif
 template <int S, bool STATS>
 __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
@@ -146,6 +149,12 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
 
     // ================= 1. this lane's game: loads (independent except planets <- meta) ========
     const uint32_t meta = p.meta[g];
+    // The planet slots to load depend on meta (np).  Warm L2 with the tile's planet rows meanwhile:
+    // the dependent loads below then take an L2 round trip instead of an HBM one (measured:
+    // 93.4 -> 91.4 us per 1M-game tick; sectors without a live lane are the price).
+#pragma unroll
+    for (int j = 0; j < ASTRO_PREFETCH_PLANETS; j++)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&planets[j * 32]));
     float4 shv[S];
     float sb[S];
 #pragma unroll

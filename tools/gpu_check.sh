@@ -11,5 +11,7 @@ tail -1 gpurun_out/bench_$TAG.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
 print('value %.4g  ms/step %.4f  frac %.3f  B/step %.1f  e2e %.4g  cpu %.3g' % (d['value'], d['ms_per_step'], r['frac'], r['bytes_per_env_step'], d['e2e']['value'], (d['cpu_baseline'] or {}).get('value', 0)))"
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 5 > gpurun_out/plain_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:tick_f32_kernel -s 610 -c 1 -f -o gpurun_out/prof_$TAG python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 5 > gpurun_out/ncu_$TAG.log 2>&1; echo "ncu rc=$?"
+# the profiled launch (index 1230) sits in the stationary population: 1,200 pre-roll ticks + warm-up + 25 timed
+CMD="python bench.py --steps 40 --warmup 5 --preroll 1200 --no-cpu-baseline --e2e-steps 8"
+$CMD > gpurun_out/plain_$TAG.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:tick_f32_kernel -s 1230 -c 1 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_$TAG.log 2>&1; echo "ncu rc=$?"
