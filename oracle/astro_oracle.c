@@ -385,6 +385,57 @@ int ao_features(int S, int P, int B, const double* ships, const double* planets,
     return P + B;
 }
 
+/*
+ * script.ScriptBot.__call__ (script.py:67-91) with _danger (:41-65) and _fly_to (:30-39) for the
+ * ship `me` of one game (the bot sees roll_ships(state, me), core.py:306-327).  float64 libm
+ * (sqrt, atan2, fmod) like numpy on this platform.  Returns the control code 0..5.
+ * Quirk kept: inside _danger the parameter `b` (bearing) is shadowed by the quadratic
+ * coefficient (script.py:54), so `rotation` uses that coefficient.
+ */
+static int fly_to(double target, double my_b, double t, int fwd) {
+    double angle = norm_angle(target - my_b);
+    if (angle < -t) return 0;
+    if (t < angle) return 4;
+    return fwd ? 3 : 2;
+}
+int ao_script_control(const ao_config* c, int S, int P, const double* ships, const double* planets, int me,
+                      double avoid_distance, double avoid_threshold) {
+    const double* my = ships + 5 * me;
+    for (int i = 0; i < P; i++) {
+        double x0 = my[0] - planets[4 * i], x1 = my[1] - planets[4 * i + 1];
+        double v0 = my[2] - planets[4 * i + 2], v1 = my[3] - planets[4 * i + 3];
+        double radius = c->planet_radius + c->ship_radius;
+        double speed = sqrt(v0 * v0 + v1 * v1);               /* util.mag(dx) */
+        double n0 = v0 / (speed + 1e-12), n1 = v1 / (speed + 1e-12); /* util.norm(dx) */
+        double b = 2 * (n0 * x0 + n1 * x1);                    /* 2 * dot(norm(dx), x) */
+        double mx = sqrt(x0 * x0 + x1 * x1);
+        double ra = radius + avoid_distance;
+        double cc = mx * mx - ra * ra;
+        double det = b * b - 4 * cc;
+        if (0 < det && 0 <= -b + sqrt(det)) {
+            double distance = -b - sqrt(det);
+            double bear = atan2(x0, x1);                       /* util.bearing(x) */
+            double rotation = fabs(norm_angle(bear - b));
+            if (distance < (speed / c->ship_thrust + c->ship_rspeed / rotation) * speed)
+                return fly_to(bear, my[4], avoid_threshold, 1);
+        }
+    }
+    if (c->solo || S < 2) return 2;
+    const double* en = ships + 5 * ((me + 1) % S);
+    double e0 = en[0] - my[0], e1 = en[1] - my[1];
+    double enemy_distance = sqrt(e0 * e0 + e1 * e1);
+    double bullet_time = enemy_distance / c->bullet_speed;
+    double f0 = en[0] + bullet_time * (en[2] - my[2]), f1 = en[1] + bullet_time * (en[3] - my[3]);
+    return fly_to(atan2(f0 - my[0], f1 - my[1]), my[4], c->ship_radius / enemy_distance, 0);
+}
+void ao_script_batch(const ao_config* c, int64_t n, int S, const double* ships, const double* planets,
+                     const int32_t* np_, double avoid_distance, double avoid_threshold, int64_t* out) {
+    for (int64_t i = 0; i < n; i++)
+        for (int me = 0; me < S; me++)
+            out[i * S + me] = ao_script_control(c, S, np_[i], ships + i * S * 5, planets + i * AO_MAXP * 4, me,
+                                                avoid_distance, avoid_threshold);
+}
+
 /* ---- counter-based streams (astro_b200/rng.py) --------------------------------------- */
 static uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;

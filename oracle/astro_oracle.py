@@ -59,6 +59,9 @@ def lib():
         L.ao_step_batch.argtypes = [C.POINTER(Config), i64, i32, i32] + [vp] * 18 + [i32]
         L.ao_features.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, vp]
         L.ao_features.restype = i32
+        L.ao_script_control.argtypes = [C.POINTER(Config), i32, i32, vp, vp, i32, f64, f64]
+        L.ao_script_control.restype = i32
+        L.ao_script_batch.argtypes = [C.POINTER(Config), i64, i32, vp, vp, vp, f64, f64, vp]
         L.ao_rollout.argtypes = [C.POINTER(Config), i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                  i64, vp, vp, vp, u32, i64, u32, i32, i32, vp]
         L.ao_rollout.restype = i64
@@ -168,6 +171,26 @@ def features(S, ships, planets, bullets, me, n_rows):
                           me, n_rows, _p(out))
     if r < 0:
         raise ValueError('n_rows too small')
+    return out
+
+
+SCRIPT_ARGS = dict(avoid_distance=0.1, avoid_threshold=0.45)   # script.py:16-20
+
+
+def script_control(cfg, ships, planets, me, avoid_distance=0.1, avoid_threshold=0.45):
+    c = cfg if isinstance(cfg, Config) else Config.from_any(cfg)
+    ships = np.ascontiguousarray(ships, dtype=np.float64).reshape(-1, 5)
+    planets = np.ascontiguousarray(planets, dtype=np.float64).reshape(-1, 4)
+    return lib().ao_script_control(C.byref(c), ships.shape[0], planets.shape[0], _p(ships), _p(planets), me,
+                                   avoid_distance, avoid_threshold)
+
+
+def script_batch(cfg, b, avoid_distance=0.1, avoid_threshold=0.45):
+    """ScriptBot controls for every ship of every game of a Batch -> int64 [n, S]."""
+    c = cfg if isinstance(cfg, Config) else Config.from_any(cfg)
+    out = np.zeros((b.n, b.S), dtype=np.int64)
+    lib().ao_script_batch(C.byref(c), b.n, b.S, _p(b.ships), _p(b.planets), _p(b.np_), avoid_distance,
+                          avoid_threshold, _p(out))
     return out
 
 

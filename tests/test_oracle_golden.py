@@ -148,6 +148,25 @@ def test_schedule():
         assert spawn == s['spawn_ticks'] and k == s['timeout_tick'], name
 
 
+def test_script_bot_controls():
+    """script.ScriptBot (script.py:13-91) on every tick of the reference's scripted games: the
+    oracle picks the control the reference's bot picked (both perspectives, solo too)."""
+    z, meta = _traj()
+    checked = 0
+    for m in meta:
+        if 'script' not in m['kind']:
+            continue
+        g, S = m['game'], m['nships']
+        ships, planets, ctrl = z['g%d_ships' % g], z['g%d_planets' % g], z['g%d_control' % g]
+        scripted = range(S) if m['kind'] != 'duel_nothing_vs_script' else [1]
+        for k in range(m['nticks']):
+            for me in scripted:
+                got = ao.script_control(m['config'], ships[k], planets[k], me)
+                assert got == ctrl[k][me], (g, k, me)
+                checked += 1
+    assert checked > 2000
+
+
 def test_features():
     """rl.ValueNetwork.get_features / roll_ships / get_features_batch (rl.py:43-112,
     core.py:306-327) on states sampled from the reference trajectories."""
