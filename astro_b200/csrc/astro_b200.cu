@@ -705,6 +705,8 @@ int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_c
     if (n_games <= 0 || n_games % ASTRO_TILE) return fail(ASTRO_E_INVALID, "n_games must be a positive multiple of %d", ASTRO_TILE);
     if (bullet_cap < 0 || bullet_cap > ASTRO_MAX_BULLET_CAP) return fail(ASTRO_E_INVALID, "bullet_cap out of range 0..%d", ASTRO_MAX_BULLET_CAP);
     if (precision != 32 && precision != 64) return fail(ASTRO_E_INVALID, "precision must be 32 or 64");
+    if ((int64_t)n_games * bullet_cap >= (int64_t)1 << 31)
+        return fail(ASTRO_E_INVALID, "n_games * bullet_cap must stay below 2^31 bullet slots per batch (32-bit slot indexing)");
     int count = 0;
     CUDA_TRY(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(ASTRO_E_INVALID, "device %d out of range (%d visible)", device, count);
@@ -804,6 +806,7 @@ int astro_set_reset_pool(AstroBatch* b, const AstroResetPool* pool) {
     if (int r = check(b, false)) return r;
     if (!pool || pool->size <= 0 || !pool->ships || !pool->planets || !pool->np)
         return fail(ASTRO_E_INVALID, "bad reset pool");
+    if ((uintptr_t)pool->planets & 15) return fail(ASTRO_E_INVALID, "reset pool planets must be 16-byte aligned");
     b->pool = *pool;
     return ASTRO_OK;
 }
@@ -933,5 +936,12 @@ int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* strea
 }
 
 int64_t astro_launch_count(const AstroBatch* b) { return b ? b->launches : 0; }
+
+#ifdef ASTRO_TIMELINE
+// experiment builds only (tools/exp_timeline.py): device buffer of 8 clock stamps per tile
+int astro_debug_set_timeline(long long* buf_dev) {
+    return cudaMemcpyToSymbol(g_timeline, &buf_dev, sizeof(buf_dev)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 }  // extern "C"

@@ -27,7 +27,10 @@ constexpr int kTickWarps = kTickThreads / 32;
 #define ASTRO_PREFETCH_PLANETS 4
 #endif
 
-constexpr int kStageWindows = 8;   // bullets staged per round: 8 windows x 32 = 256 (4 KB per warp)
+#ifndef ASTRO_STAGE_WINDOWS
+#define ASTRO_STAGE_WINDOWS 8
+#endif
+constexpr int kStageWindows = ASTRO_STAGE_WINDOWS;   // bullets staged per round: 8 windows x 32 = 256 (4 KB per warp)
 
 struct TileScratch {               // per warp
     float4 bul[kStageWindows * 32];  // the tile's bullets, staged by cp.async (flat list order)
@@ -35,7 +38,7 @@ struct TileScratch {               // per warp
     float4 pxy[2][32];             // OLD planet0.xy planet1.xy / 2,3 } addressed by game
     float4 svel[32];               // OLD ship velocities   } for the newborn bullets
     float4 dir[32];                // sin/cos of both bearings }
-    uint32_t cinfo[32];            // k-th non-empty game: game | first list index << 5
+    uint32_t cinfo[32];            // (persistent A/B kernels) k-th non-empty game: game | first list index << 5
     uint32_t outn[32];             // survivors written so far
     uint32_t hits[32];             // bits 0-1: ship hits found by the bullet loop; bits 8+: np
     uint16_t ref[kStageWindows * 32];  // staged item -> game | slot << 5 ; 0xFFFF = none
@@ -127,6 +130,171 @@ __device__ __forceinline__ ItemRef map_item(const TileScratch& t, unsigned base,
     return r;
 }
 
+// ---- packed fp32 pairs ------------------------------------------------------------------------
+// sm_100a issues FADD2 / FMUL2 / FFMA2: one issue slot, two IEEE fp32 operations, each half rounded
+// exactly like the scalar instruction.  The tick is bound by instruction issue as much as by HBM,
+// so the x/y halves of a body (the natural register pairs of its float4) and pairs of staged
+// objects go through them.
+#ifndef ASTRO_PACKED_F32
+#define ASTRO_PACKED_F32 0
+#endif
+#if ASTRO_PACKED_F32
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+#else
+// Scalar twin (same roundings): measured on B200, FADD2/FMUL2/FFMA2 hold the FMA pipe for two
+// cycles and their results come back through the scoreboard, which costs this latency-bound
+// kernel more than the saved issue slots (tools/ubench/f32x2.cu).
+struct f32x2 {
+    float lo, hi;
+};
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { return f32x2{lo, hi}; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { lo = v.lo; hi = v.hi; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { return f32x2{__fsub_rn(a.lo, b.lo), __fsub_rn(a.hi, b.hi)}; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { return f32x2{__fmul_rn(a.lo, b.lo), __fmul_rn(a.hi, b.hi)}; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    return f32x2{__fmaf_rn(a.lo, b.lo, c.lo), __fmaf_rn(a.hi, b.hi, c.hi)};
+}
+#endif
+__device__ __forceinline__ f32x2 bc2(float v) { return pk2(v, v); }
+__device__ __forceinline__ float min2(f32x2 v) {
+    float a, b;
+    upk2(v, a, b);
+    return fminf(a, b);
+}
+
+// Squared distances of one point (bx, by) to two staged objects held TRANSPOSED, o = (x0, x1, y0, y1):
+// d^2 = fma(dy, dy, dx * dx) per object — the rounding sequence of dist2().
+__device__ __forceinline__ f32x2 dist2_pair(float4 o, f32x2 bx, f32x2 by) {
+    f32x2 dx = sub2(pk2(o.x, o.y), bx), dy = sub2(pk2(o.z, o.w), by);
+    return fma2(dy, dy, mul2(dx, dx));
+}
+
+// bullet_exact() for the transposed staging.
+__device__ __forceinline__ ExactResult bullet_exact_t(float4 bv, float4 sT, float4 pA, float4 pB, int n_ships, int np,
+                                                      const Consts& c) {
+    return bullet_exact(bv.x, bv.y, bv.z, bv.w, make_float4(sT.x, sT.z, sT.y, sT.w), make_float4(pA.x, pA.z, pA.y, pA.w),
+                        make_float4(pB.x, pB.z, pB.y, pB.w), n_ships, np, c);
+}
+
+// One bullet bv = (x, y, dx, dy) against its game's staged frame (transposed pairs: both ships,
+// planets 0/1, planets 2/3).  Returns keep; bv.x / bv.y advanced; ship_hits receives bits 0/1 when
+// the bullet touches ship 0/1 (always decided in float64).  Arena test: keep iff (|x'| <= 1) or
+// (|y'| <= 1)  <=>  min(|x'|, |y'|) <= 1, so only the smaller magnitude can sit in the band.
+template <int S>
+__device__ __forceinline__ bool bullet_step_t(float4& bv, float4 sT, float4 pA, float4 pB, const uint32_t* np_of,
+                                              unsigned gi, const Consts& c, unsigned& ship_hits) {
+    const f32x2 bx = bc2(bv.x), by = bc2(bv.y);
+    const float ds = min2(dist2_pair(sT, bx, by));  // S == 1: both halves hold ship 0
+    const float dp = fminf(min2(dist2_pair(pA, bx, by)), min2(dist2_pair(pB, bx, by)));
+    float x0, x1;
+    upk2(fma2(bc2(c.dt_f), pk2(bv.z, bv.w), pk2(bv.x, bv.y)), x0, x1);
+    const float mn = fminf(fabsf(x0), fabsf(x1));
+    const bool sure = (ds >= c.r2f_sb * 1.000001f) & (fabsf(dp - c.r2f_pb) > c.r2f_pb * 1e-6f) & (fabsf(mn - 1.0f) > 4e-6f);
+    bool keep = (mn <= 1.0f) & (dp >= c.r2f_pb);
+    if (__builtin_expect(!sure, 0)) {
+        ExactResult r = bullet_exact_t(bv, sT, pA, pB, S, (int)(np_of[gi] >> 8), c);
+        x0 = r.x;
+        x1 = r.y;
+        keep = r.flags & 1u;
+        ship_hits = r.flags >> 1;
+    }
+    bv.x = x0;
+    bv.y = x1;
+    return keep;
+}
+
+// np_sincos_f32 for two bearings at once (same operations, same bits).
+__device__ __forceinline__ void np_sincos_f32x2(float xa, float xb, float& sna, float& csa, float& snb, float& csb) {
+    const f32x2 x = pk2(xa, xb), magic = bc2(12582912.0f);
+    const f32x2 q = sub2(fma2(x, bc2(0x1.45f306p-1f), magic), magic);
+    f32x2 r = fma2(q, bc2(-0x1.921fb0p+00f), x);
+    r = fma2(q, bc2(-0x1.5110b4p-22f), r);
+    r = fma2(q, bc2(-0x1.846988p-48f), r);
+    const f32x2 r2 = mul2(r, r);
+    f32x2 cc = fma2(bc2(0x1.98e616p-16f), r2, bc2(-0x1.6c06dcp-10f));
+    cc = fma2(cc, r2, bc2(0x1.55553cp-5f));
+    cc = fma2(cc, r2, bc2(-0x1.000000p-1f));
+    cc = fma2(cc, r2, bc2(0x1.000000p+0f));
+    f32x2 ss = fma2(bc2(0x1.7d3bbcp-19f), r2, bc2(-0x1.a06bbap-13f));
+    ss = fma2(ss, r2, bc2(0x1.11119ap-7f));
+    ss = fma2(ss, r2, bc2(-0x1.555556p-3f));
+    ss = fma2(ss, r2, bc2(0.0f));
+    ss = fma2(ss, r, r);
+    float qa, qb, ca, cb, sa, sb_;
+    upk2(q, qa, qb);
+    upk2(cc, ca, cb);
+    upk2(ss, sa, sb_);
+    {
+        const int iq = (int)qa, ic = iq + 1;
+        const float vs = (iq & 1) ? ca : sa, vc = (ic & 1) ? ca : sa;
+        sna = (iq & 2) ? -vs : vs;
+        csa = (ic & 2) ? -vc : vc;
+    }
+    {
+        const int iq = (int)qb, ic = iq + 1;
+        const float vs = (iq & 1) ? cb : sb_, vc = (ic & 1) ? cb : sb_;
+        snb = (iq & 2) ? -vs : vs;
+        csb = (ic & 2) ? -vc : vc;
+    }
+}
+
+// Symplectic Euler step of one body held as pairs xy = (x, y), v = (dx, dy) (core.py:189-197);
+// the wrap is evaluated only by a body that actually left the square (rare).
+__device__ __forceinline__ float4 advance_body2(f32x2 xy, f32x2 v, f32x2 acc, const Consts& c) {
+    const f32x2 dt2 = bc2(c.dt_f);
+    const f32x2 vn = fma2(acc, dt2, v);
+    const f32x2 xn = fma2(dt2, vn, xy);
+    float x0, x1, v0, v1;
+    upk2(xn, x0, x1);
+    upk2(vn, v0, v1);
+    if (__builtin_expect(fmaxf(fabsf(x0), fabsf(x1)) >= 1.0f, 0)) {
+        if (fabsf(x0) >= 1.0f) x0 = wrap_unit_f32(x0);
+        if (fabsf(x1) >= 1.0f) x1 = wrap_unit_f32(x1);
+    }
+    return make_float4(x0, x1, v0, v1);
+}
+
+// Gravity of a body at o on a body at xy (core.py:138-153): rx = o - xy, f = G*M / max(1e-12, |rx|^2),
+// acc += f * rx; returns |rx|^2 (for the collision test of the same pair).  A dead planet slot sits
+// at kFar: |rx|^2 = +inf, f = 0, no predication.
+__device__ __forceinline__ float grav_pair(f32x2 o, f32x2 xy, f32x2& acc, const Consts& c) {
+    const f32x2 q = sub2(o, xy);
+    float s0, s1;
+    upk2(mul2(q, q), s0, s1);
+    const float d2 = __fadd_rn(s0, s1);
+    const float f = __fdividef(c.gm_f, fmaxf(1e-12f, d2));
+    acc = fma2(bc2(f), q, acc);
+    return d2;
+}
+
+// -DASTRO_TIMELINE: every warp records clock64() at its phase boundaries (tools/exp_timeline.py)
+#ifdef ASTRO_TIMELINE
+__device__ long long* g_timeline = nullptr;
+#define TL(k) do { if (g_timeline && lane == 0) g_timeline[(size_t)(g >> 5) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TL(k) do { } while (0)
+#endif
 #ifndef ASTRO_TICK_MIN_BLOCKS
 #define ASTRO_TICK_MIN_BLOCKS 26  /* shared memory admits 26 one-warp CTAs per SM: 72 registers */
 #endif
@@ -135,47 +303,60 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     using B4 = Body4<float>;
     const unsigned full = 0xffffffffu;
     __shared__ TileScratch s_tiles[kTickWarps];
-    const int g = blockIdx.x * kTickThreads + threadIdx.x;
+    const unsigned bid = blockIdx.x;
+    const int g = (int)(bid * kTickThreads + threadIdx.x);
     if (g >= p.n_games) return;  // whole warps: n_games % 32 == 0
     const unsigned lane = threadIdx.x & 31u;
     const Consts& c = p.c;
     TileScratch& t = s_tiles[threadIdx.x >> 5];
     const size_t tile = (size_t)(g >> 5);
-    B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
+    float4* ships = reinterpret_cast<float4*>(p.ships) + tile * (S * 32) + lane;
     float* ship_b = reinterpret_cast<float*>(p.ship_b) + tile * (S * 32) + lane;
-    B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
-    B4* tile_bullets = reinterpret_cast<B4*>(p.bullets) + tile * 32 * (size_t)p.K;
-    const unsigned K = (unsigned)p.K;  // 32-bit slot arithmetic: a tile's pool is <= 32 * 1023 slots
+    float4* planets = reinterpret_cast<float4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
+    // 32-bit bullet indexing (astro_batch_create checks n_games * K < 2^31): one IMAD.WIDE per address
+    float4* const bullets = reinterpret_cast<float4*>(p.bullets);
+    const unsigned K = (unsigned)p.K;
+    const unsigned tile_off = (unsigned)(g >> 5) * 32u * K;
 
     // ================= 1. this lane's game: loads (independent except planets <- meta) ========
+    TL(0);
     const uint32_t meta = p.meta[g];
     // The planet slots to load depend on meta (np).  Warm L2 with the tile's planet rows meanwhile:
     // the dependent loads below then take an L2 round trip instead of an HBM one (measured:
     // 93.4 -> 91.4 us per 1M-game tick; sectors without a live lane are the price).
+    {
 #pragma unroll
-    for (int j = 0; j < ASTRO_PREFETCH_PLANETS; j++)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(&planets[j * 32]));
-    float4 shv[S];
-    float sb[S];
+        for (int j = 0; j < ASTRO_PREFETCH_PLANETS; j++)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&planets[j * 32]));
+    }
+    float4 shv[2];
+    float sb[2];
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        shv[s] = *reinterpret_cast<const float4*>(&ships[s * 32]);
+        shv[s] = ships[s * 32];
         sb[s] = ship_b[s * 32];
     }
-    int ctl[S];
+    if (S == 1) { shv[1] = shv[0]; sb[1] = sb[0]; }  // S == 1: the second half of every ship pair mirrors ship 0
+    int ctl[2];
     if (p.actions) {
         if (S == 2) {
             uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
             ctl[0] = a & 0xff;
-            ctl[S - 1] = a >> 8;
+            ctl[1] = a >> 8;
         } else {
-            ctl[0] = p.actions[g];
+            ctl[0] = ctl[1] = p.actions[g];
         }
     } else {
         uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
-#pragma unroll
-        for (int s = 0; s < S; s++) ctl[s] = action_from_key(h0, p.step, (uint32_t)s);
+        ctl[0] = action_from_key(h0, p.step, 0u);
+        ctl[1] = S == 2 ? action_from_key(h0, p.step, 1u) : ctl[0];
     }
+    // What the END of the tick will need from memory is requested now, off the critical path: the
+    // fire-schedule word of this game's tick and, with auto-reset, the planet count of the pool
+    // entry that would replace the game (the pick is keyed on the stream step, not on state).
+    const bool auto_reset = (p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0;
+    uint32_t pool_k = 0;
+    int np_new = 0;
     const bool active = !ASTRO_META_FINISHED(meta);
     const int nb = active ? (int)ASTRO_META_NB(meta) : 0;
     const int np = active ? (int)ASTRO_META_NP(meta) : 0;
@@ -184,10 +365,14 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
 #pragma unroll
     for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
         plv[j] = make_float4(kFar, kFar, 0.f, 0.f);
-        if (j < np) plv[j] = *reinterpret_cast<const float4*>(&planets[j * 32]);
+        if (j < np) plv[j] = planets[j * 32];
     }
 
     // ================= 2. flat bullet list of the tile; stage it with cp.async =================
+#ifdef ASTRO_TIMELINE
+    if (__shfl_xor_sync(full, meta, 1) == 0xdeadbeefu) return;  // consume meta: stamp 1 = meta has arrived
+    TL(1);
+#endif
     unsigned incl = (unsigned)nb;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -201,11 +386,17 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     t.hits[lane] = (unsigned)np << 8;
     const unsigned ne = __ballot_sync(full, nonempty);
     const unsigned lt_mask = (1u << lane) - 1u;
-    if (nonempty) t.cinfo[__popc(ne & lt_mask)] = lane | (my_excl << 5);
+    // k-th non-empty game: game (5 bits) | first list index (15) | bullet count (10)
+    if (nonempty) t.cinfo[__popc(ne & lt_mask)] = lane | (my_excl << 5) | ((unsigned)nb << 20);
     __syncwarp();
     unsigned c0 = 0;
     // One window = 32 consecutive list items; a round = up to kStageWindows windows, all requested
     // at once (16-byte cp.async each), so the whole tile's bullet traffic is in flight together.
+    // Item -> (game, slot): `starts` has bit r set when a non-empty game's first bullet is item
+    // base + r; c0 counts the non-empty games that start before the window.  Lanes past the end of
+    // the list stage a bullet that is certainly culled (no `valid` flag in the loop below).
+    // (A/B, 1M games: each lane requesting its own game's row instead — no cross-lane mapping, one
+    // request per bullet — 94.6 us against 91.0 us for these coalesced windows.)
     const unsigned start_key = nonempty ? my_excl : 0x80000000u;  // empty games never "start"
     const unsigned le_mask = full >> (31u - lane);
     const unsigned bul_s = (unsigned)__cvta_generic_to_shared(&t.bul[lane]);
@@ -221,137 +412,151 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
             c0 += __popc(starts);
             const unsigned ci = t.cinfo[(idx - 1u) & 31u];  // (stale only for invalid items)
             const unsigned item = base + lane;
-            const bool valid = item < total;
-            const unsigned game = ci & 31u, slot = item - (ci >> 5);
-            if (valid)
+            const unsigned game = ci & 31u, slot = item - ((ci >> 5) & 0x7fffu);
+            unsigned ref = 0u;
+            if (item < total) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bul_s + w * 512u),
-                             "l"(tile_bullets + (game * K + slot))
+                             "l"(bullets + (tile_off + game * K + slot))
                              : "memory");
-            t.ref[w * 32u + lane] = valid ? (uint16_t)(game | (slot << 5)) : (uint16_t)0xFFFFu;
+                ref = game | (slot << 5) | ((slot + 1u == (ci >> 20)) ? 0x8000u : 0u);  // bit 15: last of its game
+            } else {
+                t.bul[w * 32u + lane] = make_float4(4.0f, 4.0f, 0.0f, 0.0f);
+            }
+            t.ref[w * 32u + lane] = (uint16_t)ref;
         }
         cp_async_commit();
     };
     stage_round(0u);
+    TL(2);
 
     // ================= 3. ships and planets while the bullets fly ===============================
-    // OLD positions are staged for the bullet loop (addressed by game); the new ship / planet state
-    // goes straight to HBM.  (A game that ends is re-created below; without auto-reset its
-    // ships and planets are left in this post-step state: the state of a finished game is
-    // unspecified, the reference has none.)
-    t.sxy[lane] = make_float4(shv[0].x, shv[0].y, shv[S - 1].x, shv[S - 1].y);
-    t.svel[lane] = make_float4(shv[0].z, shv[0].w, shv[S - 1].z, shv[S - 1].w);
-    t.pxy[0][lane] = make_float4(plv[0].x, plv[0].y, plv[1].x, plv[1].y);
-    t.pxy[1][lane] = make_float4(plv[2].x, plv[2].y, plv[3].x, plv[3].y);
+    // OLD positions are staged for the bullet loop (addressed by game, transposed into the pairs
+    // the packed distance code wants); the new ship / planet state goes straight to HBM.  (A
+    // game that ends is re-created below; without auto-reset its ships and planets are left in
+    // this post-step state: the state of a finished game is unspecified, the reference has none.)
+    t.sxy[lane] = make_float4(shv[0].x, shv[1].x, shv[0].y, shv[1].y);
+    t.svel[lane] = make_float4(shv[0].z, shv[0].w, shv[1].z, shv[1].w);
+    t.pxy[0][lane] = make_float4(plv[0].x, plv[1].x, plv[0].y, plv[1].y);
+    t.pxy[1][lane] = make_float4(plv[2].x, plv[3].x, plv[2].y, plv[3].y);
+#ifdef ASTRO_TIMELINE
+    if (__shfl_xor_sync(full, __float_as_uint(shv[0].x) ^ __float_as_uint(sb[1]) ^ __float_as_uint(plv[0].x) ^ __float_as_uint(plv[3].x), 1) == 0xdeadbeefu) return;
+    TL(3);  // ships and planets have arrived
+#endif
     unsigned hits = 0;
     if (active) {
-        B4 sh[S];
+        f32x2 pxy[ASTRO_MAX_PLANETS];
 #pragma unroll
-        for (int s = 0; s < S; s++) { sh[s].x = shv[s].x; sh[s].y = shv[s].y; sh[s].dx = shv[s].z; sh[s].dy = shv[s].w; }
-        B4 pl[ASTRO_MAX_PLANETS];
-#pragma unroll
-        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) { pl[j].x = plv[j].x; pl[j].y = plv[j].y; pl[j].dx = plv[j].z; pl[j].dy = plv[j].w; }
-        float dirs[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) pxy[j] = pk2(plv[j].x, plv[j].y);
+        float dirs[4];
+        if (S == 2) np_sincos_f32x2(sb[0], sb[1], dirs[0], dirs[1], dirs[2], dirs[3]);
+        else { np_sincos_f32(sb[0], dirs[0], dirs[1]); dirs[2] = dirs[0]; dirs[3] = dirs[1]; }
+        t.dir[lane] = make_float4(dirs[0], dirs[1], dirs[2], dirs[3]);
         // direction, gravity, ship-planet and ship-ship collisions on the old state
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            float d0, d1;
-            np_sincos_f32(sb[s], d0, d1);
-            dirs[2 * s] = d0;
-            dirs[2 * s + 1] = d1;
-            float g0 = 0.f, g1 = 0.f, dmin = 3.0e38f;
+            const f32x2 sxy = pk2(shv[s].x, shv[s].y);
+            f32x2 acc = bc2(0.0f);
+            float dmin = 3.0e38f;
 #pragma unroll
-            for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
-                float q0 = __fsub_rn(pl[j].x, sh[s].x), q1 = __fsub_rn(pl[j].y, sh[s].y);
-                float d2 = __fmaf_rn(q1, q1, __fmul_rn(q0, q0));
-                float fj = __fdividef(c.gm_f, fmaxf(1e-12f, d2));  // dead slot: G*M / inf = 0
-                g0 = __fmaf_rn(fj, q0, g0);
-                g1 = __fmaf_rn(fj, q1, g1);
-                dmin = fminf(dmin, d2);
-            }
+            for (int j = 0; j < ASTRO_MAX_PLANETS; j++) dmin = fminf(dmin, grav_pair(pxy[j], sxy, acc, c));
             bool h = dmin < c.r2f_sp;
             if (__builtin_expect(fabsf(dmin - c.r2f_sp) <= c.r2f_sp * 1e-6f, 0)) {
                 h = false;
 #pragma unroll
                 for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
                     if (j < np)
-                        h |= collide_exact((double)sh[s].x, (double)sh[s].y, (double)pl[j].x, (double)pl[j].y, c.r2_sp);
+                        h |= collide_exact((double)shv[s].x, (double)shv[s].y, (double)plv[j].x, (double)plv[j].y, c.r2_sp);
             }
             hits |= h ? (1u << s) : 0u;
-            float th = (ctl[s] & 1) ? c.thrust_f : 0.f;
-            B4 o = sh[s];
-            advance_body(o, __fmaf_rn(th, d0, g0), __fmaf_rn(th, d1, g1), c);  // core.py:283-288
-            ships[s * 32] = o;
+            const float th = (ctl[s] & 1) ? c.thrust_f : 0.f;
+            acc = fma2(bc2(th), pk2(dirs[2 * s], dirs[2 * s + 1]), acc);
+            ships[s * 32] = advance_body2(sxy, pk2(shv[s].z, shv[s].w), acc, c);  // core.py:283-288
             ship_b[s * 32] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
         }
-        t.dir[lane] = make_float4(dirs[0], dirs[1], dirs[2], dirs[3]);
         if (S == 2) {
-            if (collide(sh[0].x, sh[0].y, sh[S - 1].x, sh[S - 1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
+            if (collide(shv[0].x, shv[0].y, shv[1].x, shv[1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
         }
         // planets (core.py:289-294): pair forces are antisymmetric, the clamped self term is zero
-        float q0[ASTRO_MAX_PLANETS], q1[ASTRO_MAX_PLANETS];
+        f32x2 q[ASTRO_MAX_PLANETS];
 #pragma unroll
-        for (int i = 0; i < ASTRO_MAX_PLANETS; i++) { q0[i] = 0.f; q1[i] = 0.f; }
+        for (int i = 0; i < ASTRO_MAX_PLANETS; i++) q[i] = bc2(0.0f);
 #pragma unroll
         for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
 #pragma unroll
             for (int j = i + 1; j < ASTRO_MAX_PLANETS; j++) {
-                float e0 = __fsub_rn(pl[j].x, pl[i].x), e1 = __fsub_rn(pl[j].y, pl[i].y);
-                float d2 = __fmaf_rn(e1, e1, __fmul_rn(e0, e0));
-                float fj = __fdividef(c.gm_f, fmaxf(1e-12f, d2));  // dead: 0, or e = 0
-                q0[i] = __fmaf_rn(fj, e0, q0[i]);
-                q1[i] = __fmaf_rn(fj, e1, q1[i]);
-                q0[j] = __fmaf_rn(-fj, e0, q0[j]);
-                q1[j] = __fmaf_rn(-fj, e1, q1[j]);
+                const f32x2 e = sub2(pxy[j], pxy[i]);
+                float s0, s1;
+                upk2(mul2(e, e), s0, s1);
+                const float fj = __fdividef(c.gm_f, fmaxf(1e-12f, __fadd_rn(s0, s1)));  // dead: 0, or e = 0
+                q[i] = fma2(bc2(fj), e, q[i]);
+                q[j] = fma2(bc2(-fj), e, q[j]);
             }
         }
 #pragma unroll
-        for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
-            if (i < np) {
-                advance_body(pl[i], q0[i], q1[i], c);
-                planets[i * 32] = pl[i];
-            }
-        }
+        for (int i = 0; i < ASTRO_MAX_PLANETS; i++)
+            if (i < np) planets[i * 32] = advance_body2(pxy[i], pk2(plv[i].z, plv[i].w), q[i], c);
     }
 
     // ================= 4. the bullet loop, from shared memory =======================================
+    // Survivors are compacted in place inside each game's row, in list order.  Only the game that
+    // straddles a window boundary carries a count from one window to the next: `carry` (warp-uniform).
+    unsigned carry = 0;
+    TL(4);  // physics done, new ship / planet state stored
     for (unsigned round_base = 0; round_base < total; round_base += (unsigned)kStageWindows * 32u) {
-        if (round_base) stage_round(round_base);  // (tiles with more than 256 bullets: rare)
+        if (round_base) {  // (tiles with more than kStageWindows * 32 bullets: rare)
+            __syncwarp();
+            stage_round(round_base);
+        }
         cp_async_wait_all();
         __syncwarp();
+        if (round_base == 0) TL(5);  // bullets have arrived
         const unsigned left = total - round_base;
         const unsigned n_win = left >= (unsigned)kStageWindows * 32u ? (unsigned)kStageWindows : (left + 31u) >> 5;
+        // One window: 32 list items.  Everything a window needs from shared memory is loaded first
+        // (Win), then compact() decides, compacts and stores.  (A/B: two windows per iteration, the
+        // loads of the second overlapping the arithmetic of the first: 94.7 against 95.2 us — noise.)
+        struct Win {
+            unsigned ref;
+            float4 bv, sT, pA, pB;
+        };
+        auto load_win = [&](unsigned w) {
+            Win x;
+            x.ref = t.ref[w * 32u + lane];
+            x.bv = t.bul[w * 32u + lane];
+            const unsigned gi = x.ref & 31u;
+            x.sT = t.sxy[gi];
+            x.pA = t.pxy[0][gi];
+            x.pB = t.pxy[1][gi];
+            return x;
+        };
+        auto compact = [&](Win& x) {
+            const unsigned gi = x.ref & 31u, slot = (x.ref >> 5) & 1023u;
+            unsigned sh_hits = 0;
+            const bool keep = bullet_step_t<S>(x.bv, x.sT, x.pA, x.pB, t.hits, gi, c, sh_hits);
+            if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
+            // stable compaction inside each game's segment of the window; only the game that
+            // straddles a window boundary carries a count over (`carry`, warp-uniform)
+            const unsigned kb = __ballot_sync(full, keep);
+            const unsigned seg_lo = lane - min(slot, lane);  // first lane of this game's segment
+            const unsigned pos = (slot > lane ? carry : 0u) + __popc(kb & lt_mask & (full << seg_lo));
+            if (keep) bullets[tile_off + gi * K + pos] = x.bv;
+            const unsigned tot = pos + (keep ? 1u : 0u);
+            if (x.ref & 0x8000u) t.outn[gi] = tot;
+            carry = __shfl_sync(full, tot, 31);
+        };
 #pragma unroll 1
         for (unsigned w = 0; w < n_win; w++) {
-            const unsigned ref = t.ref[w * 32u + lane];
-            const bool valid = ref != 0xFFFFu;
-            const unsigned gi = ref & 31u, slot = (ref >> 5) & 1023u;
-            const float4 bv = t.bul[w * 32u + lane];
-            B4 b;
-            b.x = bv.x; b.y = bv.y; b.dx = bv.z; b.dy = bv.w;
-            bool keep = false;
-            unsigned sh_hits = 0;
-            if (valid) keep = bullet_step<S>(b, t.sxy[gi], t.pxy[0][gi], t.pxy[1][gi], t.hits, gi, c, sh_hits);
-            if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
-            // stable in-place compaction inside each game's segment of the window
-            const unsigned kb = __ballot_sync(full, keep);
-            const unsigned seg_lo = slot < lane ? lane - slot : 0u;  // first lane of this game's segment
-            const unsigned rank = __popc(kb & (lt_mask & (full << seg_lo)));
-            const unsigned ob = t.outn[gi];
-            const unsigned g_next = __shfl_down_sync(full, valid ? gi : 32u, 1);
-            const bool last = valid && (lane == 31u || g_next != gi);
-            __syncwarp();
-            if (keep) tile_bullets[gi * K + ob + rank] = b;
-            if (last) t.outn[gi] = ob + rank + (keep ? 1u : 0u);
-            __syncwarp();
+            Win x = load_win(w);
+            compact(x);
         }
     }
+    __syncwarp();
+    TL(6);
 
     // ================= 5. terminal logic, spawn, bookkeeping ==========================================
     uint32_t ev = 0;
     int m_out = 0, spawned = 0;
-    float rw[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) rw[s] = 0.0f;
+    float rw[2] = {0.0f, 0.0f};
     if (!active) {
         ev = ASTRO_EV_SKIPPED;
     } else {
@@ -367,25 +572,26 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
 #pragma unroll
             for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
         } else {
-            const bool fire = tick < (uint32_t)p.n_sched_ticks && ((p.fire_bits[tick >> 5] >> (tick & 31)) & 1u);
+            const uint32_t fire_word = p.fire_bits[min(tick, (uint32_t)p.n_sched_ticks - 1u) >> 5];
+            const bool fire = tick < (uint32_t)p.n_sched_ticks && ((fire_word >> (tick & 31)) & 1u);
             if (fire) {  // core.py:267-280, from the OLD ship state
                 ev |= ASTRO_EV_FIRED;
-                B4* row = tile_bullets + lane * K;
+                float4* row = bullets + (tile_off + lane * K);
                 const float4 dv = t.dir[lane], oxy = t.sxy[lane], ov = t.svel[lane];
 #pragma unroll
                 for (int s = 0; s < S; s++) {
                     const float d0 = s == 0 ? dv.x : dv.z, d1 = s == 0 ? dv.y : dv.w;
-                    const float sx = s == 0 ? oxy.x : oxy.z, sy = s == 0 ? oxy.y : oxy.w;
+                    const float sx = s == 0 ? oxy.x : oxy.y, sy = s == 0 ? oxy.z : oxy.w;
                     const float vx = s == 0 ? ov.x : ov.z, vy = s == 0 ? ov.y : ov.w;
                     // fp32 products as in the reference; the sums and the advance in fp32 too,
                     // unless the newborn lands within the band of the arena bound
                     float o0 = __fmul_rn(c.off_f, d0), o1 = __fmul_rn(c.off_f, d1);
                     float w0 = __fmul_rn(c.spd_f, d0), w1 = __fmul_rn(c.spd_f, d1);
-                    B4 o;
-                    o.dx = __fadd_rn(vx, w0);
-                    o.dy = __fadd_rn(vy, w1);
-                    o.x = __fmaf_rn(c.dt_f, o.dx, __fadd_rn(sx, o0));
-                    o.y = __fmaf_rn(c.dt_f, o.dy, __fadd_rn(sy, o1));
+                    float4 o;
+                    o.z = __fadd_rn(vx, w0);
+                    o.w = __fadd_rn(vy, w1);
+                    o.x = __fmaf_rn(c.dt_f, o.z, __fadd_rn(sx, o0));
+                    o.y = __fmaf_rn(c.dt_f, o.w, __fadd_rn(sy, o1));
                     float mn = fminf(fabsf(o.x), fabsf(o.y));
                     bool keep = mn <= 1.0f;
                     if (__builtin_expect(fabsf(mn - 1.0f) <= 8e-6f, 0)) {
@@ -395,7 +601,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
                         nbl.dx = __dadd_rn((double)vx, (double)w0);
                         nbl.dy = __dadd_rn((double)vy, (double)w1);
                         keep = advance_bullet(nbl, c);
-                        o.x = (float)nbl.x; o.y = (float)nbl.y; o.dx = (float)nbl.dx; o.dy = (float)nbl.dy;
+                        o = make_float4((float)nbl.x, (float)nbl.y, (float)nbl.dx, (float)nbl.dy);
                     }
                     if (keep) {
                         if (m < (int)K) {
@@ -412,14 +618,31 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
             m_out = m;
         }
         if (ev & ASTRO_EV_DONE_MASK) {
-            if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0)
-                recreate_from_pool<float, S>(p, g, p.step + 1u, ships, ship_b, planets);
-            else
+            if (auto_reset) {
+                // Re-create the game from pool entry pool_k (core.create, core.py:86-135, evaluated
+                // on the host): bullets cleared, tick 0; the per-slot episode counter is bumped with
+                // a fire-and-forget RED.
+                atomicAdd(&p.episode[g], 1u);
+                pool_k = pool_pick(p.seed, p.first_game + (uint32_t)g, p.step + 1u, (uint32_t)p.pool_size);
+                np_new = p.pool_np[pool_k];
+                const float* ps = reinterpret_cast<const float*>(p.pool_ships) + (size_t)pool_k * (S * 5);
+                const float4* pp = reinterpret_cast<const float4*>(p.pool_planets) + (size_t)pool_k * ASTRO_MAX_PLANETS;
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    ships[s * 32] = make_float4(ps[5 * s], ps[5 * s + 1], ps[5 * s + 2], ps[5 * s + 3]);
+                    ship_b[s * 32] = ps[5 * s + 4];
+                }
+#pragma unroll
+                for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
+                    if (j < np_new) planets[j * 32] = pp[j];
+                p.meta[g] = ASTRO_META_PACK(0, np_new, 0, 0);
+            } else {
                 p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
+            }
         }
     }
     if (p.reward) {
-        if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
+        if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[1]);
         else p.reward[g] = rw[0];
     }
     if (p.events) p.events[g] = (uint8_t)ev;
@@ -432,4 +655,5 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
         if (lane < ASTRO_N_STATS && mine) atomicAdd(slot, mine);  // RED: fire and forget
     }
+    TL(7);
 }
