@@ -324,6 +324,19 @@ class BatchedGames:
         nat.check(nat.lib().astro_observe(self._h, out.data_ptr(), n_rows, self._stream()))
         return out[:self.n]
 
+    # ---- scripted bots ----------------------------------------------------------------------------
+    def script_controls(self, out=None, avoid_distance=0.1, avoid_threshold=0.45):
+        """`script.ScriptBot` (script.py:13-91) for every ship of every game, each from its own
+        perspective: uint8 cuda tensor [n, S] of control codes, ready to be passed to step()."""
+        torch = _torch()
+        if out is None:
+            out = torch.empty((self.n_pad, self.S), dtype=torch.uint8, device=self.device)
+        elif out.shape[0] != self.n_pad or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise ValueError('out must be a contiguous uint8 tensor [%d, %d]' % (self.n_pad, self.S))
+        nat.check(nat.lib().astro_script_controls(self._h, float(avoid_distance), float(avoid_threshold), out.data_ptr(),
+                                                  self._stream()))
+        return out
+
     # ---- statistics ------------------------------------------------------------------------------
     def stats_tensor(self, clear=False):
         """Device int64 [12] counters (see _native.STAT_NAMES) — the input of the NCCL all-reduce."""

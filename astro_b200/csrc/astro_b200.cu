@@ -495,6 +495,113 @@ observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// script_kernel<R, S>: script.ScriptBot.__call__ (script.py:67-91) with _danger (:41-65) and
+// _fly_to (:30-39) for every ship of every game — thread = game, both perspectives
+// (core.roll_ships, core.py:306-327: ship `me` sees itself as ship 0, the other as ship 1).
+// float64 throughout, the reference's operations in the reference's order (the bot reads a
+// float64 State; float32 state converts exactly).  sqrt, division and fmod are IEEE-exact;
+// atan2 is the device libm (<= 2 ulp) against glibc's (< 1 ulp), so a decision could differ from
+// the reference only when an angle sits within an ulp of its threshold.
+// Quirk kept: inside _danger the parameter `b` (my bearing) is shadowed by the quadratic
+// coefficient (script.py:54), so `rotation` uses that coefficient.
+// ------------------------------------------------------------------------------------------
+struct ScriptParams {
+    double radius;           // planet_radius + ship_radius                  script.py:53
+    double avoid_distance, avoid_threshold;
+    double ship_thrust, ship_rspeed, bullet_speed, ship_radius;
+    int32_t solo, n_games;
+};
+
+__device__ __forceinline__ double norm_angle_f64(double b) {  // util.norm_angle, util.py:125-132
+    const double PI = 3.141592653589793;
+    return __dsub_rn(np_remainder(__dadd_rn(b, PI), __dmul_rn(2.0, PI)), PI);
+}
+__device__ __forceinline__ int fly_to(double target, double my_b, double t, bool fwd) {  // script.py:30-39
+    const double angle = norm_angle_f64(__dsub_rn(target, my_b));
+    if (angle < -t) return 0;
+    if (t < angle) return 4;
+    return fwd ? 3 : 2;
+}
+
+template <typename R, int S>
+__global__ void __launch_bounds__(128) script_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
+                                                     const void* __restrict__ planets_, const uint32_t* __restrict__ meta_,
+                                                     uint8_t* __restrict__ actions, const __grid_constant__ ScriptParams q) {
+    using B4 = Body4<R>;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= q.n_games) return;
+    const size_t tile = (size_t)(g >> 5);
+    const int lane = g & 31;
+    const uint32_t meta = meta_[g];
+    if (ASTRO_META_FINISHED(meta)) {
+#pragma unroll
+        for (int me = 0; me < S; me++) actions[(size_t)g * S + me] = 2;
+        return;
+    }
+    const int np = (int)ASTRO_META_NP(meta);
+    double sx[S][5];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const B4 v = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + s * 32 + lane];
+        sx[s][0] = (double)v.x; sx[s][1] = (double)v.y; sx[s][2] = (double)v.dx; sx[s][3] = (double)v.dy;
+        sx[s][4] = (double)reinterpret_cast<const R*>(ship_b_)[tile * (S * 32) + s * 32 + lane];
+    }
+    double px[ASTRO_MAX_PLANETS][4];
+#pragma unroll
+    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+        if (j < np) {
+            const B4 v = reinterpret_cast<const B4*>(planets_)[tile * (ASTRO_MAX_PLANETS * 32) + j * 32 + lane];
+            px[j][0] = (double)v.x; px[j][1] = (double)v.y; px[j][2] = (double)v.dx; px[j][3] = (double)v.dy;
+        }
+    }
+#pragma unroll
+    for (int me = 0; me < S; me++) {
+        const double* my = sx[me];
+        int ctl = -1;
+#pragma unroll
+        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+            if (j < np && ctl < 0) {
+                const double x0 = __dsub_rn(my[0], px[j][0]), x1 = __dsub_rn(my[1], px[j][1]);
+                const double v0 = __dsub_rn(my[2], px[j][2]), v1 = __dsub_rn(my[3], px[j][3]);
+                const double speed = sqrt(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)));   // util.mag(dx)
+                const double den = __dadd_rn(speed, 1e-12);
+                const double n0 = __ddiv_rn(v0, den), n1 = __ddiv_rn(v1, den);                   // util.norm(dx)
+                const double b = __dmul_rn(2.0, __dadd_rn(__dmul_rn(n0, x0), __dmul_rn(n1, x1)));
+                const double mx = sqrt(__dadd_rn(__dmul_rn(x0, x0), __dmul_rn(x1, x1)));
+                const double ra = __dadd_rn(q.radius, q.avoid_distance);
+                const double cc = __dsub_rn(__dmul_rn(mx, mx), __dmul_rn(ra, ra));
+                const double det = __dsub_rn(__dmul_rn(b, b), __dmul_rn(4.0, cc));
+                if (0.0 < det) {
+                    const double sd = sqrt(det);
+                    if (0.0 <= __dadd_rn(-b, sd)) {
+                        const double distance = __dsub_rn(-b, sd);
+                        const double bear = atan2(x0, x1);                                        // util.bearing(x)
+                        const double rotation = fabs(norm_angle_f64(__dsub_rn(bear, b)));
+                        const double lim = __dmul_rn(__dadd_rn(__ddiv_rn(speed, q.ship_thrust), __ddiv_rn(q.ship_rspeed, rotation)), speed);
+                        if (distance < lim) ctl = fly_to(bear, my[4], q.avoid_threshold, true);
+                    }
+                }
+            }
+        }
+        if (ctl < 0) {
+            if (q.solo || S < 2) {
+                ctl = 2;
+            } else {
+                const double* en = sx[(me + 1) % S];
+                const double e0 = __dsub_rn(en[0], my[0]), e1 = __dsub_rn(en[1], my[1]);
+                const double enemy_distance = sqrt(__dadd_rn(__dmul_rn(e0, e0), __dmul_rn(e1, e1)));
+                const double bullet_time = __ddiv_rn(enemy_distance, q.bullet_speed);
+                const double f0 = __dadd_rn(en[0], __dmul_rn(bullet_time, __dsub_rn(en[2], my[2])));
+                const double f1 = __dadd_rn(en[1], __dmul_rn(bullet_time, __dsub_rn(en[3], my[3])));
+                ctl = fly_to(atan2(__dsub_rn(f0, my[0]), __dsub_rn(f1, my[1])), my[4], __ddiv_rn(q.ship_radius, enemy_distance), false);
+            }
+        }
+        actions[(size_t)g * S + me] = (uint8_t)ctl;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------
@@ -919,6 +1026,35 @@ int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream) {
         if (b->S == 2) LAUNCH_OBS(double, 2); else LAUNCH_OBS(double, 1);
     }
 #undef LAUNCH_OBS
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
+int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_threshold, uint8_t* actions, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!actions) return fail(ASTRO_E_INVALID, "null actions");
+    CUDA_TRY(cudaSetDevice(b->device));
+    ScriptParams q;
+    q.radius = b->cfg.planet_radius + b->cfg.ship_radius;
+    q.avoid_distance = avoid_distance;
+    q.avoid_threshold = avoid_threshold;
+    q.ship_thrust = b->cfg.ship_thrust;
+    q.ship_rspeed = b->cfg.ship_rspeed;
+    q.bullet_speed = b->cfg.bullet_speed;
+    q.ship_radius = b->cfg.ship_radius;
+    q.solo = b->cfg.solo;
+    q.n_games = b->n_games;
+    const int grid = (b->n_games + 127) / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    const AstroBuffers& u = b->bufs;
+    if (b->precision == 32) {
+        if (b->S == 2) script_kernel<float, 2><<<grid, 128, 0, st>>>(u.ships, u.ship_b, u.planets, u.meta, actions, q);
+        else script_kernel<float, 1><<<grid, 128, 0, st>>>(u.ships, u.ship_b, u.planets, u.meta, actions, q);
+    } else {
+        if (b->S == 2) script_kernel<double, 2><<<grid, 128, 0, st>>>(u.ships, u.ship_b, u.planets, u.meta, actions, q);
+        else script_kernel<double, 1><<<grid, 128, 0, st>>>(u.ships, u.ship_b, u.planets, u.meta, actions, q);
+    }
     CUDA_TRY(cudaGetLastError());
     b->launches += 1;
     return ASTRO_OK;

@@ -168,6 +168,13 @@ int astro_reset_done(AstroBatch* b, void* stream);
  * bullets, the rest filled with -1; n_rows >= 4 + bullet_cap.  Finished games: all -1. */
 int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream);
 
+/* script.ScriptBot.__call__ (script.py:13-91: _danger, _fly_to) for every ship of every game, each
+ * seeing the game from its own perspective (core.roll_ships, core.py:306-327):
+ * actions u8 [n_games][S] device, control codes 0..5; finished games get 2 (no-op).  The
+ * reference's tuned arguments are avoid_distance 0.1, avoid_threshold 0.45 (script.py:16-20).
+ * The output is directly the `actions` input of astro_tick: scripted games run without the host. */
+int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_threshold, uint8_t* actions, void* stream);
+
 /* Copies the ASTRO_N_STATS device counters into counters_dev (device pointer, e.g. the input of
  * an NCCL all-reduce) on the stream; clear != 0 zeroes them afterwards. */
 int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream);

@@ -497,3 +497,79 @@ def test_abi_errors_are_reported_not_thrown():
     assert L.astro_tick(h, None, None, None, None, 0, None) == -3      # not bound
     assert b'bind' in L.astro_last_error()
     assert L.astro_batch_destroy(h) == 0
+
+
+# ------------------------------------------------------------------ scripted bots on the device
+
+def test_script_controls_replay_golden_games_f64():
+    """BASELINE config #1 (script bot vs script bot) without the host in the loop: the reference's
+    scripted games are replayed free-running in the float64 build with the controls chosen by the
+    device ScriptBot kernel — every control equals the one the reference's bot chose and every
+    state stays bit-identical, to the last tick."""
+    z, meta = H.load_traj()
+    checked = 0
+    for m in meta:
+        if m['kind'] not in ('duel_script', 'solo_script_timeout', 'duel_nothing_vs_script'):
+            continue
+        g, S = m['game'], m['nships']
+        cfg = H.config_from(m['config'])
+        games = _games(cfg, 1, bullet_cap=32, precision=64)
+        games.set_states([H.state_from_arrays(z['g%d_ships' % g][0], z['g%d_planets' % g][0], np.zeros((0, 4)), 0.0, 0.0)])
+        for k in range(m['nticks']):
+            arr = games.get_arrays()
+            assert H.same_bits(arr['ships'][0], z['g%d_ships' % g][k]), (g, k)
+            ctl = games.script_controls()
+            if m['kind'] == 'duel_nothing_vs_script':
+                ctl[:, 0] = 2   # script.NothingBot (script.py:6-10) flies ship 0
+            assert (ctl[0].cpu().numpy() == z['g%d_control' % g][k]).all(), (g, k)
+            reward, done, _ = games.step(ctl)
+            assert H.same_bits(reward[0].cpu().numpy(), z['g%d_reward' % g][k]), (g, k)
+            checked += 1
+        assert bool(done[0].item()) == (not m['truncated'])
+    assert checked > 900
+
+
+@pytest.mark.parametrize('precision', [32, 64])
+def test_script_controls_match_oracle_on_batched_states(precision):
+    """4,096 games under random play, sampled every 7 ticks (so that planets, bullets and resets are in
+    every phase): the device bot's control of every ship == the oracle's on the same state."""
+    cfg = core.DEFAULT_CONFIG
+    N, K, S = 4096, 32, 2
+    pool = H.make_pool(cfg, 512)
+    games = _games(cfg, N, bullet_cap=K, precision=precision)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    seen = np.zeros(6, dtype=np.int64)
+    for k in range(140):
+        if k % 7 == 0:
+            arr = games.get_arrays()
+            ob, _ = H.oracle_batch_from(arr, S, K)
+            want = ao.script_batch(cfg, ob)
+            got = games.script_controls()[:N].cpu().numpy()
+            assert (got == want).all(), (k, np.nonzero((got != want).any(axis=1))[0][:8])
+            seen += np.bincount(got.ravel(), minlength=6)
+        games.step(None, auto_reset=True)
+    assert seen[0] > 0 and seen[2] > 0 and seen[3] > 0 and seen[4] > 0   # left / idle / forward / right all occur
+    # scripted self-play on the device: bot kernel -> tick kernel, no host in the loop
+    games.stats(clear=True)
+    for k in range(300):
+        games.step(games.script_controls(), auto_reset=True)
+    st = games.stats()
+    assert st['env_steps'] == N * 300 and st['episodes'] > 0 and st['bullets_spawned'] > 0
+    # finished games get the no-op control
+    g1 = _games(cfg, 64, bullet_cap=K, precision=precision)
+    assert (g1.script_controls().cpu().numpy() == 2).all()
+
+
+def test_script_controls_solo():
+    cfg = core.SOLO_CONFIG
+    pool = H.make_pool(cfg, 64)
+    games = _games(cfg, 512, bullet_cap=4, precision=32)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    for k in range(60):
+        arr = games.get_arrays()
+        ob, _ = H.oracle_batch_from(arr, 1, 4)
+        got = games.script_controls()[:512].cpu().numpy()
+        assert (got == ao.script_batch(cfg, ob)).all(), k
+        games.step(got, auto_reset=True)
