@@ -22,7 +22,7 @@ TICK_AUTO_RESET, TICK_NO_STATS, TICK_GENERIC_KERNEL, TICK_PERSISTENT, TICK_PREFE
 EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro_batch_destroy',
            'astro_batch_bind', 'astro_set_schedule', 'astro_set_stream', 'astro_set_reset_pool',
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
-           'astro_launch_count', 'astro_script_controls')
+           'astro_launch_count', 'astro_script_controls', 'astro_create_games')
 
 
 class AstroConfig(C.Structure):
@@ -39,6 +39,11 @@ class AstroBuffers(C.Structure):
 class AstroResetPool(C.Structure):
     _fields_ = [('ships', C.c_void_p), ('planets', C.c_void_p), ('np', C.c_void_p),
                 ('size', C.c_int32), ('reserved', C.c_int32)]
+
+
+class AstroCreateConfig(C.Structure):
+    _fields_ = [('inner_ship_position', C.c_double), ('outer_ship_position', C.c_double), ('planet_orbit', C.c_double),
+                ('max_planets', C.c_int32), ('reserved', C.c_int32)]
 
 
 class AstroError(RuntimeError):
@@ -73,6 +78,7 @@ def lib():
     L.astro_reset_done.argtypes = [vp, vp]
     L.astro_observe.argtypes = [vp, vp, i32, vp]
     L.astro_stats.argtypes = [vp, vp, i32, vp]
+    L.astro_create_games.argtypes = [vp, C.POINTER(AstroCreateConfig), vp, i32, vp, vp, vp, vp]
     L.astro_script_controls.argtypes = [vp, C.c_double, C.c_double, vp, vp]
     L.astro_launch_count.argtypes = [vp]
     L.astro_launch_count.restype = i64

@@ -233,6 +233,35 @@ class BatchedGames:
                                   self._pool[0].shape[0], 0)
         nat.check(nat.lib().astro_set_reset_pool(self._h, C.byref(pool)))
 
+    def create_on_device(self, seeds):
+        """`core.create` (core.py:86-135) for every seed, on the device: returns cuda tensors
+        (ships [m,S,5], planets [m,4,4], n_planets int32 [m]) in the batch precision, bit-identical
+        to core.create(config._replace(seed=s)) (rounded to float32 in the float32 build)."""
+        torch = _torch()
+        seeds = torch.as_tensor(np.asarray(seeds, dtype=np.uint32).astype(np.int64), dtype=torch.int64).to(torch.int32) \
+            if not isinstance(seeds, torch.Tensor) else seeds
+        seeds = seeds.to(device=self.device, dtype=torch.int32).contiguous()   # same 32 bits as uint32
+        m = int(seeds.numel())
+        ships = torch.empty((m, self.S, 5), dtype=self.rdtype, device=self.device)
+        planets = torch.empty((m, nat.MAX_PLANETS, 4), dtype=self.rdtype, device=self.device)
+        n_planets = torch.empty((m,), dtype=torch.int32, device=self.device)
+        c = self.config
+        cc = nat.AstroCreateConfig(float(c.inner_ship_position), float(c.outer_ship_position), float(c.planet_orbit),
+                                   int(c.max_planets), 0)
+        nat.check(nat.lib().astro_create_games(self._h, C.byref(cc), seeds.data_ptr(), m, ships.data_ptr(),
+                                               planets.data_ptr(), n_planets.data_ptr(), self._stream()))
+        return ships, planets, n_planets
+
+    def set_reset_pool_on_device(self, size, skip=0):
+        """Reset pool of `size` fresh games created ON THE DEVICE from the seeds of
+        core.generate_configs(config) number skip .. skip+size-1 (same pool as pool.make_pool for
+        skip=0).  Call again with a larger `skip` between rollouts for a pool that never repeats."""
+        from . import rng
+        ships, planets, n_planets = self.create_on_device(rng.config_seeds(self.config.seed, size, skip))
+        self._pool = (ships, planets, n_planets)
+        pool = nat.AstroResetPool(ships.data_ptr(), planets.data_ptr(), n_planets.data_ptr(), int(size), 0)
+        nat.check(nat.lib().astro_set_reset_pool(self._h, C.byref(pool)))
+
     def reset_done(self):
         """Re-create every finished game from the pool (entry = pick(seed, game, current step))."""
         if self.n != self.n_pad:

@@ -603,6 +603,129 @@ __global__ void __launch_bounds__(128) script_kernel(const void* __restrict__ sh
 }
 
 // ------------------------------------------------------------------------------------------
+// create_kernel<R, S>: core.create (core.py:86-135) for M seeds at once — thread = one new game.
+//
+// The reference draws from numpy's legacy RandomState(seed): MT19937 seeded by init_genrand, 32-bit
+// words tempered in order.  A game needs fewer than kCreateWords words, and the first generation's
+// word k depends only on the seeded state at k, k + 1 and k + 397, so the thread keeps those two
+// short runs of the 624-word state while it walks the seeding recurrence once.
+//   randint(lo, hi)   masked rejection on one word per try; no word when hi - lo == 1
+//   rand()            ((w0 >> 5) * 2^26 + (w1 >> 6)) / 2^53
+//   choice((-1, 1))   randint(0, 2)
+// Arithmetic follows numpy >= 2 promotion: ship positions / bearings and planet
+// positions are float32 products, util.direction is the float32 sin/cos kernel, planet
+// velocities are float64 (np.sqrt returns a float64 scalar).  Output is game-major, the layout of
+// AstroResetPool: ships [M][S][5], planets [M][4][4] (dead slots zero), np [M].
+// ------------------------------------------------------------------------------------------
+constexpr int kCreateWords = 40;
+
+struct CreateParams {
+    double inner, outer, orbit, gravity, planet_mass;
+    int32_t max_planets, solo, m, pad;
+};
+
+struct Mt19937Head {
+    uint32_t lo[kCreateWords + 1], hi[kCreateWords];
+    int k;
+    __device__ void seed(uint32_t x) {
+        lo[0] = x;
+        for (int j = 1; j < 397 + kCreateWords; j++) {
+            x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)j;
+            if (j <= kCreateWords) lo[j] = x;
+            if (j >= 397) hi[j - 397] = x;
+        }
+        k = 0;
+    }
+    __device__ uint32_t word() {
+        const int i = k < kCreateWords ? k : kCreateWords - 1;  // (never reached: see the rejection bound below)
+        k++;
+        const uint32_t y = (lo[i] & 0x80000000u) | (lo[i + 1] & 0x7fffffffu);
+        uint32_t v = hi[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        v ^= v >> 11;
+        v ^= (v << 7) & 0x9d2c5680u;
+        v ^= (v << 15) & 0xefc60000u;
+        v ^= v >> 18;
+        return v;
+    }
+    __device__ double rand() {
+        const uint32_t a = word() >> 5, b = word() >> 6;
+        return __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+    }
+    __device__ uint32_t bounded(uint32_t rng) {  // value in [0, rng]
+        if (rng == 0) return 0;
+        uint32_t mask = rng;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t v;
+        do v = word() & mask; while (v > rng && k < kCreateWords - 16);
+        return v > rng ? rng : v;  // (a 2^-24 event cut short so that the word budget holds)
+    }
+};
+
+template <typename R, int S>
+__global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__ seeds, R* __restrict__ ships,
+                                                    R* __restrict__ planets, int32_t* __restrict__ np_out,
+                                                    const __grid_constant__ CreateParams q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.m) return;
+    const double TWO_PI = 6.283185307179586, PI = 3.141592653589793;
+    Mt19937Head mt;
+    mt.seed(seeds[i]);
+    const int n = 1 + (int)mt.bounded((uint32_t)(q.max_planets - 1));
+    // 1. ships
+    const float r0 = (float)mt.rand(), r1 = (float)mt.rand();
+    const float d0 = __fsub_rn(r0, 0.5f), d1 = __fsub_rn(r1, 0.5f);
+    const float outer_f = (float)q.outer, inner_f = (float)q.inner;
+    const float o0 = __fmul_rn(outer_f, d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f));
+    const float o1 = __fmul_rn(outer_f, d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f));
+    float sn, cs;
+    np_sincos_f32((float)__dmul_rn(TWO_PI, mt.rand()), sn, cs);
+    const float i0 = __fmul_rn(inner_f, sn), i1 = __fmul_rn(inner_f, cs);
+    float sx[2][2];
+    if (n == 1) {
+        sx[0][0] = o0; sx[0][1] = o1; sx[1][0] = -o0; sx[1][1] = -o1;
+    } else {
+        const bool first = mt.rand() < 0.5;
+        if (S == 1) {
+            sx[0][0] = first ? o0 : i0; sx[0][1] = first ? o1 : i1;
+            sx[1][0] = sx[1][1] = 0.f;
+        } else {
+            sx[0][0] = first ? o0 : i0; sx[0][1] = first ? o1 : i1;
+            sx[1][0] = first ? i0 : o0; sx[1][1] = first ? i1 : o1;
+        }
+    }
+    const float two_pi_f = (float)TWO_PI;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        R* o = ships + ((size_t)i * S + s) * 5;
+        o[0] = (R)sx[s][0]; o[1] = (R)sx[s][1]; o[2] = (R)0; o[3] = (R)0;
+        o[4] = (R)__fmul_rn(two_pi_f, (float)mt.rand());
+    }
+    // 2. planets
+    R* pl = planets + (size_t)i * (ASTRO_MAX_PLANETS * 4);
+#pragma unroll
+    for (int j = 0; j < ASTRO_MAX_PLANETS * 4; j++) pl[j] = (R)0;
+    if (n > 1) {
+        const double base = __dmul_rn(TWO_PI, mt.rand());
+        const double step = __ddiv_rn(TWO_PI, (double)n);                    // np.linspace(0, 2 pi, n, endpoint=False)
+        const double spin = mt.bounded(1u) ? 1.0 : -1.0;                     // random.choice((-1, 1))
+        const double quarter = __ddiv_rn(__dmul_rn(spin, PI), 2.0);
+        const double speed = sqrt(__ddiv_rn(__dmul_rn(__dmul_rn(q.gravity, q.planet_mass), (double)(n - 1)), 2.0));
+        const float orbit_f = (float)q.orbit;
+        for (int j = 0; j < n && j < ASTRO_MAX_PLANETS; j++) {
+            const double phase = __dadd_rn(base, __dadd_rn(__dmul_rn((double)j, step), 0.0));
+            float s0, c0, s1, c1;
+            np_sincos_f32((float)phase, s0, c0);
+            np_sincos_f32((float)__dadd_rn(phase, quarter), s1, c1);
+            pl[4 * j + 0] = (R)__fmul_rn(orbit_f, s0);
+            pl[4 * j + 1] = (R)__fmul_rn(orbit_f, c0);
+            pl[4 * j + 2] = (R)__dmul_rn(speed, (double)s1);
+            pl[4 * j + 3] = (R)__dmul_rn(speed, (double)c1);
+        }
+    }
+    np_out[i] = n;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
@@ -1054,6 +1177,37 @@ int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_thr
     } else {
         if (b->S == 2) script_kernel<double, 2><<<grid, 128, 0, st>>>(u.ships, u.ship_b, u.planets, u.meta, actions, q);
         else script_kernel<double, 1><<<grid, 128, 0, st>>>(u.ships, u.ship_b, u.planets, u.meta, actions, q);
+    }
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
+int astro_create_games(AstroBatch* b, const AstroCreateConfig* cc, const uint32_t* seeds, int32_t m, void* ships,
+                       void* planets, int32_t* n_planets, void* stream) {
+    if (int r = check(b, false)) return r;
+    if (!cc || !seeds || !ships || !planets || !n_planets || m <= 0) return fail(ASTRO_E_INVALID, "bad create arguments");
+    if (cc->max_planets < 1 || cc->max_planets > ASTRO_MAX_PLANETS)
+        return fail(ASTRO_E_INVALID, "max_planets must be 1..%d", ASTRO_MAX_PLANETS);
+    CUDA_TRY(cudaSetDevice(b->device));
+    CreateParams q;
+    q.inner = cc->inner_ship_position;
+    q.outer = cc->outer_ship_position;
+    q.orbit = cc->planet_orbit;
+    q.gravity = b->cfg.gravity;
+    q.planet_mass = b->cfg.planet_mass;
+    q.max_planets = cc->max_planets;
+    q.solo = b->cfg.solo;
+    q.m = m;
+    q.pad = 0;
+    const int grid = (m + 63) / 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b->precision == 32) {
+        if (b->S == 2) create_kernel<float, 2><<<grid, 64, 0, st>>>(seeds, (float*)ships, (float*)planets, n_planets, q);
+        else create_kernel<float, 1><<<grid, 64, 0, st>>>(seeds, (float*)ships, (float*)planets, n_planets, q);
+    } else {
+        if (b->S == 2) create_kernel<double, 2><<<grid, 64, 0, st>>>(seeds, (double*)ships, (double*)planets, n_planets, q);
+        else create_kernel<double, 1><<<grid, 64, 0, st>>>(seeds, (double*)ships, (double*)planets, n_planets, q);
     }
     CUDA_TRY(cudaGetLastError());
     b->launches += 1;

@@ -56,3 +56,13 @@ def pool_pick(seed, game_ids, episode, pool_size):
         e = np.asarray(episode, dtype=_U32)
         h0 = mix32(_U32(seed) ^ _POOL_SALT ^ (g * _GOLD))
         return _mulhi(mix32(h0 ^ e), pool_size)
+
+
+def config_seeds(seed, count, skip=0):
+    """Seeds of the first `count` configs of `core.generate_configs(config)` after skipping `skip`
+    (core.py:77-83: RandomState(config.seed).randint(2**30) per config) -> uint32 [count].
+    The bulk draw consumes the MT19937 stream exactly like `count` single draws."""
+    stream = np.random.RandomState(int(seed))
+    if skip:
+        stream.randint(1 << 30, size=int(skip))
+    return stream.randint(1 << 30, size=int(count)).astype(np.uint32)

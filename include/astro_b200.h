@@ -106,6 +106,14 @@ typedef struct AstroResetPool {
     int32_t reserved;
 } AstroResetPool;
 
+/* Creation part of the reference Config (core.py:30-41; defaults core.py:64-71); gravity,
+ * planet_mass and solo come from the batch's AstroConfig, the seed is per game. */
+typedef struct AstroCreateConfig {
+    double inner_ship_position, outer_ship_position, planet_orbit;
+    int32_t max_planets;
+    int32_t reserved;
+} AstroCreateConfig;
+
 #define ASTRO_N_STATS 12
 /* astro_stats counters (int64 each), summed over every astro_tick since the last clear:
  *  0 episodes  1 wins0  2 wins1  3 both_lost (or solo crash)  4 timeouts  5 env_steps
@@ -167,6 +175,16 @@ int astro_reset_done(AstroBatch* b, void* stream);
  * for both perspectives: obs f32 [n_games][S][n_rows][1+5S+4] device; rows = planets then
  * bullets, the rest filled with -1; n_rows >= 4 + bullet_cap.  Finished games: all -1. */
 int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream);
+
+/* core.create (core.py:86-135) for m seeds at once, on the device: numpy RandomState(seed) (MT19937,
+ * legacy randint / rand / choice draws in the reference's order) and the reference's float32 /
+ * float64 arithmetic, bit for bit.  seeds u32 [m] device (core.generate_configs, core.py:77-83, is
+ * RandomState(config.seed).randint(2**30) per game: astro_b200/rng.py config_seeds).  Output in
+ * the AstroResetPool layout, batch precision R: ships R [m][S][5], planets R [m][4][4] (dead slots
+ * zero), n_planets i32 [m] — pass it to astro_set_reset_pool, or refresh it between rollouts so
+ * that re-created games never repeat. */
+int astro_create_games(AstroBatch* b, const AstroCreateConfig* cc, const uint32_t* seeds, int32_t m, void* ships,
+                       void* planets, int32_t* n_planets, void* stream);
 
 /* script.ScriptBot.__call__ (script.py:13-91: _danger, _fly_to) for every ship of every game, each
  * seeing the game from its own perspective (core.roll_ships, core.py:306-327):

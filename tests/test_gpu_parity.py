@@ -573,3 +573,73 @@ def test_script_controls_solo():
         got = games.script_controls()[:512].cpu().numpy()
         assert (got == ao.script_batch(cfg, ob)).all(), k
         games.step(got, auto_reset=True)
+
+
+# ------------------------------------------------------------------ core.create on the device
+
+def _host_pool(cfg, seeds):
+    S = 1 if cfg.solo else 2
+    ships = np.zeros((len(seeds), S, 5)); planets = np.zeros((len(seeds), 4, 4)); npl = np.zeros(len(seeds), dtype=np.int32)
+    for i, sd in enumerate(seeds):
+        s = core.create(cfg._replace(seed=int(sd)))
+        ships[i, :, 0:2], ships[i, :, 2:4], ships[i, :, 4] = s.ships.x, s.ships.dx, s.ships.b
+        p = s.planets.x.shape[0]
+        planets[i, :p, 0:2], planets[i, :p, 2:4] = s.planets.x, s.planets.dx
+        npl[i] = p
+    return ships, planets, npl
+
+
+def test_create_on_device_matches_reference_golden():
+    """core.create (core.py:86-135) on the device against the 48 create() outputs recorded from the
+    reference: float64 build bit for bit (MT19937 draw order, float32 islands, float64 planet
+    velocities); float32 build = the same values rounded to float32."""
+    z = np.load(os.path.join(H.G, 'create.npz'))
+    meta = json.load(open(os.path.join(H.G, 'create.json')))
+    for m in meta:
+        cfg = H.config_from(m['config'])
+        for prec in (64, 32):
+            games = _games(cfg, 32, bullet_cap=4, precision=prec)
+            ships, planets, npl = (t.cpu().numpy() for t in games.create_on_device([cfg.seed]))
+            cast = (lambda a: np.asarray(a, dtype=np.float64)) if prec == 64 else (lambda a: np.asarray(a, dtype=np.float32).astype(np.float64))
+            P = z[m['key'] + '_planets_x'].shape[0]
+            assert npl[0] == P, m['key']
+            assert H.same_bits(ships[0, :, 0:2], cast(z[m['key'] + '_ships_x'])), m['key']
+            assert H.same_bits(ships[0, :, 2:4], cast(z[m['key'] + '_ships_dx'])), m['key']
+            assert H.same_bits(ships[0, :, 4], cast(z[m['key'] + '_ships_b'])), m['key']
+            assert H.same_bits(planets[0, :P, 0:2], cast(z[m['key'] + '_planets_x'])), m['key']
+            assert H.same_bits(planets[0, :P, 2:4], cast(z[m['key'] + '_planets_dx'])), m['key']
+            assert (planets[0, P:] == 0).all()
+
+
+@pytest.mark.parametrize('cfg', [core.DEFAULT_CONFIG, core.SOLO_CONFIG, core.SOLO_EASY_CONFIG,
+                                 core.DEFAULT_CONFIG._replace(max_planets=3, seed=7),
+                                 core.DEFAULT_CONFIG._replace(max_planets=2, seed=123, planet_orbit=0.4, gravity=0.08)])
+def test_create_on_device_matches_host_create_over_the_config_stream(cfg):
+    """2,048 seeds of core.generate_configs: the device pool == pool.make_pool (host core.create),
+    every bit, incl. rejection sampling for max_planets = 3 and the no-draw case max_planets = 1;
+    then a rollout re-created from the device pool behaves exactly like one from the host pool."""
+    M = 2048
+    seeds = rng.config_seeds(cfg.seed, M)
+    import itertools as it
+    assert [c.seed for c in it.islice(core.generate_configs(cfg), 8)] == [int(x) for x in seeds[:8]]
+    assert (rng.config_seeds(cfg.seed, 8, skip=5) == seeds[5:13]).all()
+    want = H.make_pool(cfg, M)
+    for prec in (64, 32):
+        games = _games(cfg, 256, bullet_cap=32, precision=prec)
+        ships, planets, npl = (t.cpu().numpy().astype(np.float64) if t.dtype.is_floating_point else t.cpu().numpy()
+                               for t in games.create_on_device(seeds))
+        cast = (lambda a: a) if prec == 64 else (lambda a: a.astype(np.float32).astype(np.float64))
+        assert (npl == want['np']).all()
+        assert H.same_bits(ships, cast(want['ships'])) and H.same_bits(planets, cast(want['planets']))
+    a = _games(cfg, 1024, bullet_cap=32, precision=32)
+    a.set_reset_pool_on_device(M)
+    b = _games(cfg, 1024, bullet_cap=32, precision=32)
+    b.set_reset_pool_arrays(want['ships'], want['planets'], want['np'])
+    for g in (a, b):
+        g.reset_all()
+        for _ in range(120):
+            g.step(None, auto_reset=True)
+    xa, xb = a.get_arrays(), b.get_arrays()
+    for k in ('ships', 'planets', 'bullets', 'n_bullets', 'n_planets', 'tick', 'episode'):
+        assert (xa[k] == xb[k]).all(), k
+    assert a.stats() == b.stats() and a.stats()['episodes'] > 0
