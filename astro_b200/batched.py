@@ -342,15 +342,22 @@ class BatchedGames:
         self.step_index += T
 
     # ---- observations ----------------------------------------------------------------------------
-    def observe(self, n_rows=None, out=None):
-        """Feature batch [n, S, n_rows, D] float32: obs[g, k] is game g seen by ship k
-        (rl.py:43-99 + core.roll_ships); rows = planets, bullets, then -1 padding."""
+    def observe(self, n_rows=None, out=None, shared=False):
+        """Feature batch float32, rows = planets, bullets, then -1 padding (rl.py:43-99).
+
+        shared=False -- [n, S, n_rows, D]: obs[g, k] is game g seen by ship k (core.roll_ships).
+        shared=True  -- [n, n_rows, D]: ship 0's view only; ship 1's view is the same block with
+                        the ship column groups exchanged (see rl.ValueNetwork.forward_both)."""
         torch = _torch()
         if n_rows is None:
             n_rows = -(-(nat.MAX_PLANETS + self.K) // 4) * 4
+        shape = (self.n_pad, n_rows, self.D) if shared else (self.n_pad, self.S, n_rows, self.D)
         if out is None:
-            out = torch.empty((self.n_pad, self.S, n_rows, self.D), dtype=torch.float32, device=self.device)
-        nat.check(nat.lib().astro_observe(self._h, out.data_ptr(), n_rows, self._stream()))
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError('out must be a contiguous float32 tensor %r' % (shape,))
+        fn = nat.lib().astro_observe_shared if shared else nat.lib().astro_observe
+        nat.check(fn(self._h, out.data_ptr(), n_rows, self._stream()))
         return out[:self.n]
 
     # ---- scripted bots ----------------------------------------------------------------------------

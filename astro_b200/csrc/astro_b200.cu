@@ -418,7 +418,7 @@ __host__ __device__ inline size_t observe_warp_floats(int n_rows, int D, int S) 
     return (((size_t)n_rows * D + 5 * S) + 3) & ~(size_t)3;
 }
 
-template <typename R, int S>
+template <typename R, int S, bool BOTH>
 __global__ void __launch_bounds__(kObserveWarps * 32)
 observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_, const void* __restrict__ planets_,
                const void* __restrict__ bullets_, const uint32_t* __restrict__ meta_, float* __restrict__ obs,
@@ -471,10 +471,10 @@ observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_
     __syncwarp();
     // stream out: perspective 0 is the staged block; perspective 1 swaps the ship columns
     const int per = n_rows * D;  // % 4 == 0 (checked on the host)
-    float4* out = reinterpret_cast<float4*>(obs + (size_t)g * S * per);
+    float4* out = reinterpret_cast<float4*>(obs + (size_t)g * (BOTH ? S : 1) * per);
     const float4* src4 = reinterpret_cast<const float4*>(rows);
     for (int q = lane; q < per / 4; q += 32) out[q] = src4[q];
-    if (S == 2) {
+    if (S == 2 && BOTH) {
         float4* out1 = out + per / 4;
         const int live = (np + nb) * D;
         for (int q = lane; q < per / 4; q += 32) {
@@ -1124,7 +1124,7 @@ int astro_reset_done(AstroBatch* b, void* stream) {
     return ASTRO_OK;
 }
 
-int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream) {
+static int observe_impl(AstroBatch* b, float* obs, int32_t n_rows, bool both, void* stream) {
     if (int r = check(b, true)) return r;
     if (!obs) return fail(ASTRO_E_INVALID, "null obs");
     const int D = 1 + 5 * b->S + 4;
@@ -1137,21 +1137,29 @@ int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream) {
     const int grid = (b->n_games + kObserveWarps - 1) / kObserveWarps;
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;
-#define LAUNCH_OBS(R, S_)                                                                                        \
-    do {                                                                                                         \
-        CUDA_TRY(cudaFuncSetAttribute(observe_kernel<R, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        observe_kernel<R, S_><<<grid, kObserveWarps * 32, smem, st>>>(u.ships, u.ship_b, u.planets, u.bullets, u.meta, \
-                                                                      obs, b->n_games, b->K, n_rows);             \
+#define LAUNCH_OBS(R, S_, BOTH_)                                                                                       \
+    do {                                                                                                               \
+        CUDA_TRY(cudaFuncSetAttribute(observe_kernel<R, S_, BOTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        observe_kernel<R, S_, BOTH_><<<grid, kObserveWarps * 32, smem, st>>>(u.ships, u.ship_b, u.planets, u.bullets, u.meta, \
+                                                                             obs, b->n_games, b->K, n_rows);             \
     } while (0)
     if (b->precision == 32) {
-        if (b->S == 2) LAUNCH_OBS(float, 2); else LAUNCH_OBS(float, 1);
+        if (b->S == 2) { if (both) LAUNCH_OBS(float, 2, true); else LAUNCH_OBS(float, 2, false); }
+        else LAUNCH_OBS(float, 1, false);
     } else {
-        if (b->S == 2) LAUNCH_OBS(double, 2); else LAUNCH_OBS(double, 1);
+        if (b->S == 2) { if (both) LAUNCH_OBS(double, 2, true); else LAUNCH_OBS(double, 2, false); }
+        else LAUNCH_OBS(double, 1, false);
     }
 #undef LAUNCH_OBS
     CUDA_TRY(cudaGetLastError());
     b->launches += 1;
     return ASTRO_OK;
+}
+
+int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream) { return observe_impl(b, obs, n_rows, true, stream); }
+
+int astro_observe_shared(AstroBatch* b, float* obs, int32_t n_rows, void* stream) {
+    return observe_impl(b, obs, n_rows, false, stream);
 }
 
 int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_threshold, uint8_t* actions, void* stream) {

@@ -70,6 +70,27 @@ class ValueNetwork(torch.nn.Module):
             h = self.activation(layer(h))
         return torch.tanh(self.v0(h))
 
+    def forward_both(self, x):
+        """Both ships' values from ONE perspective-0 feature batch x [..., N, 15] -> [..., 2, nout].
+
+        Ship 1's features are ship 0's with the ship column groups exchanged (core.roll_ships,
+        core.py:306-327 + rl.py:62-70); exchanging the matching COLUMNS of the first layer's weight
+        gives the same pre-activations without a second observation tensor
+        (`BatchedGames.observe(shared=True)`)."""
+        if x.shape[-1] != 15:
+            raise ValueError('forward_both needs duel features [..., N, 15]')
+        swap = torch.tensor([0, 6, 7, 8, 9, 10, 1, 2, 3, 4, 5, 11, 12, 13, 14], device=x.device)
+        w = torch.cat((self.f0.weight, self.f0.weight[:, swap]), dim=0)           # [64, 15]
+        b = torch.cat((self.f0.bias, self.f0.bias), dim=0)
+        h = torch.nn.functional.linear(x, w, b)                                    # [..., N, 64]
+        h = h.unflatten(-1, (2, -1)).movedim(-2, -3)                               # [..., 2, N, 32]
+        for layer in self.f:
+            h = layer(self.activation(h))
+        h = self.pool(h, features=x.unsqueeze(-3))
+        for layer in self.v:
+            h = self.activation(layer(h))
+        return torch.tanh(self.v0(h))
+
     def evaluate(self, state):
         dev = next(self.parameters()).device
         return self(torch.from_numpy(self.get_features(state)).to(dev))

@@ -176,6 +176,14 @@ int astro_reset_done(AstroBatch* b, void* stream);
  * bullets, the rest filled with -1; n_rows >= 4 + bullet_cap.  Finished games: all -1. */
 int astro_observe(AstroBatch* b, float* obs, int32_t n_rows, void* stream);
 
+/* The same features written ONCE: obs f32 [n_games][n_rows][1+5S+4], ship 0's perspective only.
+ * Ship 1's view of the same game (core.roll_ships, core.py:306-327, then rl.py:62-70) is this block
+ * with the two ship column groups exchanged (columns 1..5 <-> 6..10), every other column and the
+ * -1 padding being perspective-free — a consumer applies the exchange to its first-layer weights
+ * instead of reading a second tensor (astro_b200/rl.py ValueNetwork.forward_both): half the
+ * observation bytes written and read. */
+int astro_observe_shared(AstroBatch* b, float* obs, int32_t n_rows, void* stream);
+
 /* core.create (core.py:86-135) for m seeds at once, on the device: numpy RandomState(seed) (MT19937,
  * legacy randint / rand / choice draws in the reference's order) and the reference's float32 /
  * float64 arithmetic, bit for bit.  seeds u32 [m] device (core.generate_configs, core.py:77-83, is

@@ -643,3 +643,35 @@ def test_create_on_device_matches_host_create_over_the_config_stream(cfg):
     for k in ('ships', 'planets', 'bullets', 'n_bullets', 'n_planets', 'tick', 'episode'):
         assert (xa[k] == xb[k]).all(), k
     assert a.stats() == b.stats() and a.stats()['episodes'] > 0
+
+
+# ------------------------------------------------------------------ one observation tensor for both ships
+
+def test_observe_shared_and_forward_both():
+    """observe(shared=True) is exactly perspective 0 of observe(); ValueNetwork.forward_both on it
+    gives both ships' values (fp32 tolerance 1e-6 against forward() on the two-perspective batch:
+    the same products summed in a different order inside the first layer)."""
+    import torch
+    from astro_b200 import rl
+    cfg, N, K = core.DEFAULT_CONFIG, 4096, 32
+    pool = H.make_pool(cfg, 256)
+    games = _games(cfg, N, bullet_cap=K, precision=32, seed=3)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    for _ in range(80):
+        games.step(None, auto_reset=True)
+    games.step(None, auto_reset=False)
+    full = games.observe()
+    shared = games.observe(shared=True)
+    assert shared.shape == (N, 36, 15)
+    assert torch.equal(shared, full[:, 0])
+    torch.manual_seed(0)
+    net = rl.ValueNetwork(solo=False, nout=6).to(full.device)
+    with torch.no_grad():
+        q_full = net(full)                   # [N, 2, 6]
+        q_both = net.forward_both(shared)    # [N, 2, 6]
+    assert q_both.shape == q_full.shape
+    assert float((q_both - q_full).abs().max()) <= 1e-6
+    live = (games.get_arrays()['finished'] == 0)
+    a_full, a_both = q_full.argmax(-1).cpu().numpy()[live], q_both.argmax(-1).cpu().numpy()[live]
+    assert (a_full == a_both).mean() > 0.999

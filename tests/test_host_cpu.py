@@ -178,3 +178,24 @@ def test_two_rank_gloo_sharding_and_stats_reduce():
     assert res[0]['first_game'] == 0 and res[1]['first_game'] == 256
     assert res[0]['single_process_digest'] == res[0]['sharded_digest'] == res[1]['sharded_digest']
     assert res[0]['max_ms'] == res[1]['max_ms'] >= max(res[0]['my_ms'], res[1]['my_ms']) - 1e-9
+
+
+def test_forward_both_equals_forward_on_rolled_features():
+    """rl.ValueNetwork.forward_both: ship 1's view = ship 0's features with the ship column groups
+    exchanged (core.roll_ships + rl.py:62-70), folded into the first layer's weights."""
+    import torch
+    from astro_b200 import rl
+    torch.manual_seed(1)
+    net = rl.ValueNetwork(solo=False, nout=6)
+    x = torch.randn(7, 12, 15)
+    x[:, :, 0] = (torch.rand(7, 12) < 0.5).float()
+    x[2, 5:] = -1.0
+    x[4, 1:] = -1.0
+    rolled = x.clone()
+    rolled[..., 1:6], rolled[..., 6:11] = x[..., 6:11], x[..., 1:6]
+    rolled[x[..., 0] < 0] = -1.0
+    with torch.no_grad():
+        both = net.forward_both(x)
+        assert both.shape == (7, 2, 6)
+        assert torch.allclose(both[:, 0], net(x), atol=1e-6)
+        assert torch.allclose(both[:, 1], net(rolled), atol=1e-6)

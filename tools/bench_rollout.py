@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--games', type=int, default=16384)
 ap.add_argument('--ticks', type=int, default=1000)
 ap.add_argument('--bullet-cap', type=int, default=32)
+ap.add_argument('--shared', action='store_true', help='one observation tensor for both ships (observe(shared=True) + forward_both)')
 args = ap.parse_args()
 torch.manual_seed(0)
 dev = torch.device('cuda', 0)
@@ -22,13 +23,13 @@ pool = make_pool(cfg, 4096)
 games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
 games.reset_all()
 net = rl.ValueNetwork(solo=False, nout=6).to(dev).eval()
-obs = torch.empty((games.n_pad, 2, 36, 15), dtype=torch.float32, device=dev)
+obs = torch.empty((games.n_pad, 36, 15) if args.shared else (games.n_pad, 2, 36, 15), dtype=torch.float32, device=dev)
 
 
 def tick():
     with torch.no_grad():
-        o = games.observe(out=obs)                       # [N, 2, 36, 15]
-        q = net(o)                                       # [N, 2, 6]
+        o = games.observe(out=obs, shared=args.shared)   # [N, 2, 36, 15] / [N, 36, 15]
+        q = net.forward_both(o) if args.shared else net(o)   # [N, 2, 6]
         a = q.argmax(-1).to(torch.uint8)                 # greedy controls for both ships
     games.step(a, auto_reset=True, want_reward=False)
 
@@ -42,7 +43,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 t_obs0, t_obs1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t_obs0.record()
 for _ in range(50):
-    games.observe(out=obs)
+    games.observe(out=obs, shared=args.shared)
 t_obs1.record()
 e0.record()
 for _ in range(args.ticks):
@@ -52,8 +53,8 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 st = games.stats()
 obs_us = 1e3 * t_obs0.elapsed_time(t_obs1) / 50
-obs_bytes = games.n_pad * 2 * 36 * 15 * 4
-print(json.dumps(dict(workload='configs[4]: %d games x %d ticks, observe -> ValueNetwork(6) -> greedy -> step' % (args.games, args.ticks),
+obs_bytes = obs.numel() * 4
+print(json.dumps(dict(shared=args.shared, workload='configs[4]: %d games x %d ticks, observe -> ValueNetwork(6) -> greedy -> step' % (args.games, args.ticks),
                       env_steps_per_s=st['env_steps'] / (ms * 1e-3), ms_per_tick=ms / args.ticks,
                       observe_us=obs_us, observe_write_GBps=obs_bytes / (obs_us * 1e-6) / 1e9,
                       episodes=st['episodes'], wins0=st['wins0'], wins1=st['wins1'], both_lost=st['both_lost'],
