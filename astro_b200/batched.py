@@ -208,6 +208,33 @@ class BatchedGames:
             bullets=core.Bodies(x=bl[:, 0:2].copy(), dx=bl[:, 2:4].copy(), b=None),
             reload=float(self.schedule.reload[tick]), t=float(self.schedule.t[tick]))
 
+    def get_states(self, indices):
+        """Reference `State`s (or None for finished games) of the listed games only: one gather per
+        array on the device, one small copy each — the read path of logs.GameRecorder."""
+        torch = _torch()
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+        tiles, lanes = self._split(idx)
+        tt, ll = torch.from_numpy(tiles).to(self.device), torch.from_numpy(lanes).to(self.device)
+        ii = torch.from_numpy(idx).to(self.device)
+        meta = self.meta[ii].cpu().numpy().view(np.uint32)
+        sh = self.ships[tt, :, ll].double().cpu().numpy()          # [m, S, 4]
+        sb = self.ship_b[tt, :, ll].double().cpu().numpy()         # [m, S]
+        pl = self.planets[tt, :, ll].double().cpu().numpy()        # [m, 4, 4]
+        bl = self.bullets[ii, :self.K].double().cpu().numpy()      # [m, K, 4]
+        out = []
+        for j in range(len(idx)):
+            m = int(meta[j])
+            if (m >> 13) & 1:
+                out.append(None)
+                continue
+            nb, npl, tick = m & 1023, (m >> 10) & 7, m >> 14
+            out.append(core.State(
+                ships=core.Bodies(x=sh[j, :, 0:2].copy(), dx=sh[j, :, 2:4].copy(), b=sb[j].copy()),
+                planets=core.Bodies(x=pl[j, :npl, 0:2].copy(), dx=pl[j, :npl, 2:4].copy(), b=None),
+                bullets=core.Bodies(x=bl[j, :nb, 0:2].copy(), dx=bl[j, :nb, 2:4].copy(), b=None),
+                reload=float(self.schedule.reload[tick]), t=float(self.schedule.t[tick])))
+        return out
+
     # ---- reset pool ------------------------------------------------------------------------------
     def set_reset_pool(self, states):
         """Initial states (built by core.create) that finished games are re-created from."""

@@ -191,7 +191,7 @@ def _to_jsonable(obj, module='astro.core'):
         d.update((k, _to_jsonable(getattr(obj, k), module)) for k in obj._fields)
         return d
     if isinstance(obj, np.ndarray):
-        return {'_values': obj.flatten().tolist(), '_shape': list(obj.shape)}
+        return {'_values': obj.tolist(), '_shape': list(obj.shape)}   # nested, as util.to_jsonable (util.py:24-26): astro.js indexes x[i][0]
     if isinstance(obj, dict):
         return {k: _to_jsonable(v, module) for k, v in obj.items()}
     if isinstance(obj, (list, tuple)):

@@ -675,3 +675,49 @@ def test_observe_shared_and_forward_both():
     live = (games.get_arrays()['finished'] == 0)
     a_full, a_both = q_full.argmax(-1).cpu().numpy()[live], q_both.argmax(-1).cpu().numpy()[live]
     assert (a_full == a_both).mean() > 0.999
+
+
+# ------------------------------------------------------------------ JSONL logs of batched rollouts
+
+def test_game_recorder_writes_reference_format_logs(tmp_path):
+    """logs.GameRecorder over a batched float64 rollout: the recorded games equal core.play-style
+    records — every Tick holds the pre-step state, replaying the logged controls through the
+    oracle reproduces each next state bit for bit, the winner follows core.py:409 — and the files
+    load back through load_log in the reference's JSONL format."""
+    from astro_b200 import logs
+    cfg = core.DEFAULT_CONFIG
+    N, K = 256, 32
+    pool = H.make_pool(cfg, 64)
+    games = _games(cfg, N, bullet_cap=K, precision=64, seed=5)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    follow = [0, 37, 255]
+    rec = logs.GameRecorder(games, follow, folder=str(tmp_path / 'logs'))
+    for k in range(400):
+        if k % 2:
+            rec.step(None, auto_reset=True)                       # device counter-stream controls
+        else:
+            rec.step(games.script_controls(), auto_reset=True)    # device ScriptBot controls
+    assert len(rec.finished) >= 3 and len(rec.paths) == len(rec.finished)
+    for game, path in zip(rec.finished, rec.paths):
+        assert game.ticks[0].state.t == 0.0 and game.ticks[0].state.bullets.x.shape == (0, 2)
+        for a, b in zip(game.ticks[:-1], game.ticks[1:]):
+            ob = ao.Batch(1, 2, K)
+            P, B = a.state.planets.x.shape[0], a.state.bullets.x.shape[0]
+            ob.ships[0, :, 0:2], ob.ships[0, :, 2:4], ob.ships[0, :, 4] = a.state.ships.x, a.state.ships.dx, a.state.ships.b
+            ob.planets[0, :P, 0:2], ob.planets[0, :P, 2:4] = a.state.planets.x, a.state.planets.dx
+            ob.bullets[0, :B, 0:2], ob.bullets[0, :B, 2:4] = a.state.bullets.x, a.state.bullets.dx
+            ob.np_[0], ob.nb[0], ob.reload[0], ob.t[0] = P, B, a.state.reload, a.state.t
+            o2, rew, done, ev = ao.step_batch(cfg, ob, a.control.reshape(1, 2))
+            assert not done[0] and (rew[0] == a.reward).all()
+            assert H.same_bits(o2.ships[0, :, 0:2], b.state.ships.x) and H.same_bits(o2.ships[0, :, 4], b.state.ships.b)
+            assert o2.nb[0] == b.state.bullets.x.shape[0]
+            assert H.same_bits(o2.bullets[0, :o2.nb[0], 0:2], b.state.bullets.x)
+        last = game.ticks[-1]
+        assert (last.reward != 0).any() or last.state.t + cfg.dt >= cfg.max_time
+        assert game.winner == (None if last.reward.max() < 1 else int(last.reward.argmax()))
+        back = core.load_log(path)
+        assert back.winner == game.winner and len(back.ticks) == len(game.ticks)
+        assert np.array_equal(back.ticks[3 % len(back.ticks)].state.ships.x, game.ticks[3 % len(game.ticks)].state.ships.x)
+        head = json.loads(open(path).readline())
+        assert head['config']['_type'] == 'astro.core:Config'

@@ -113,6 +113,9 @@ def test_log_roundtrip_and_reference_format(tmp_path):
     head, tick = json.loads(lines[0]), json.loads(lines[1])
     assert head['config']['_type'] == 'astro.core:Config' and head['winner'] == 1
     assert tick['_type'] == 'astro.core:Tick' and tick['state']['ships']['x']['_shape'] == [2, 2]
+    # arrays are NESTED lists, as the reference writes them (util.py:24-26): astro.js reads ships.x[i][0]
+    assert tick['state']['ships']['x']['_values'] == s.ships.x.tolist() and len(tick['state']['ships']['x']['_values'][0]) == 2
+    assert tick['control'] == {'_values': [2, 3], '_shape': [2]}
     back = core.load_log(path)
     assert back.config == game.config and back.winner == 1
     assert np.allclose(back.ticks[0].state.ships.x, s.ships.x) and back.ticks[0].state.planets.b is None
