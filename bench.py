@@ -262,7 +262,7 @@ def run_ours(args):
     except Exception:
         pass
     roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic,
-                    kernel='tick_kernel<float,2>', peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
+                    kernel='tick_f32_kernel<2,true>', peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
                     algorithmic_bytes_per_launch=alg / args.steps,
                     bytes_per_env_step=alg / max(1, games_stats_local['env_steps']),
                     mean_planets=games_stats_local['planets_live'] / max(1, games_stats_local['env_steps']),
