@@ -22,7 +22,8 @@ TICK_AUTO_RESET, TICK_NO_STATS, TICK_GENERIC_KERNEL, TICK_PERSISTENT, TICK_PREFE
 EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro_batch_destroy',
            'astro_batch_bind', 'astro_set_schedule', 'astro_set_stream', 'astro_set_reset_pool',
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
-           'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared')
+           'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
+           'astro_policy_controls')
 
 
 class AstroConfig(C.Structure):
@@ -79,6 +80,8 @@ def lib():
     L.astro_observe.argtypes = [vp, vp, i32, vp]
     L.astro_stats.argtypes = [vp, vp, i32, vp]
     L.astro_observe_shared.argtypes = [vp, vp, i32, vp]
+    L.astro_policy_set_weights.argtypes = [vp, vp, i32, i32]
+    L.astro_policy_controls.argtypes = [vp, vp, vp, i32, vp]
     L.astro_create_games.argtypes = [vp, C.POINTER(AstroCreateConfig), vp, i32, vp, vp, vp, vp]
     L.astro_script_controls.argtypes = [vp, C.c_double, C.c_double, vp, vp]
     L.astro_launch_count.argtypes = [vp]

@@ -400,6 +400,30 @@ class BatchedGames:
                                                   self._stream()))
         return out
 
+    # ---- value network on the device --------------------------------------------------------------
+    def set_policy(self, net):
+        """Load a `rl.ValueNetwork` (or any module with the reference's layers f0, f[0..1], v[0..1],
+        v0; rl.py:140-152) into the fused policy kernel."""
+        parts = []
+        for layer in (net.f0, net.f[0], net.f[1], net.v[0], net.v[1], net.v0):
+            parts += [layer.weight.detach().float().cpu().numpy().ravel(), layer.bias.detach().float().cpu().numpy().ravel()]
+        w = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+        self.policy_nout = int(net.v0.weight.shape[0])
+        nat.check(nat.lib().astro_policy_set_weights(self._h, w.ctypes.data_as(C.c_void_p), int(w.size), self.policy_nout))
+
+    def policy_controls(self, out=None, q_out=None, ships=None):
+        """Greedy controls argmax_a Q(s, a) of the loaded network for every ship of every game, each
+        from its own perspective (rl.QBot, rl.py:168-200) — features and network fused in one
+        kernel.  out: uint8 cuda [n_pad, S] (only the listed `ships` columns are written);
+        q_out: optional float32 cuda [n_pad, S, nout] receiving the network outputs."""
+        torch = _torch()
+        if out is None:
+            out = torch.full((self.n_pad, self.S), 2, dtype=torch.uint8, device=self.device)
+        mask = sum(1 << int(k) for k in (range(self.S) if ships is None else ships))
+        nat.check(nat.lib().astro_policy_controls(self._h, out.data_ptr(), None if q_out is None else q_out.data_ptr(),
+                                                  mask, self._stream()))
+        return out
+
     # ---- statistics ------------------------------------------------------------------------------
     def stats_tensor(self, clear=False):
         """Device int64 [12] counters (see _native.STAT_NAMES) — the input of the NCCL all-reduce."""

@@ -726,6 +726,162 @@ __global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// policy_kernel<R, S>: rl.ValueNetwork.forward (rl.py:140-165) on the features of rl.py:43-72,
+// fused — the observation tensor never exists.  For every game and both perspectives
+// (core.roll_ships): per live object row  h = f0(x); h = f[i](softsign(h)) x2 ; max over the rows ;
+// h = softsign(v[i](h)) x2 ; q = tanh(v0(h)) ; control = argmax q  (the greedy policy of
+// rl.QBot, rl.py:168-200).
+//
+// CTA = one tile of 32 games.  Thread = one (perspective, row) of the tile's flat row list
+// (planets then bullets of each game, live rows only: no padding work — 7.8 rows per game on
+// average against 36 padded).  The 4,934 weights sit in constant memory: every lane of a warp
+// needs the same weight at the same time, so each FMA takes its weight straight from the constant
+// bank, and the 32 accumulators of a layer give the ILP.  Rows of one game are pooled with an
+// order-preserving integer atomicMax in shared memory; 64 threads then run the head.
+// fp32 FMA arithmetic (CUDA cores): agrees with the PyTorch fp32 network to ~1e-6; tensor-core
+// formats (tf32 / bf16) would flip near-tied argmaxes, and the whole network is 90 kFLOP per game.
+// ------------------------------------------------------------------------------------------
+constexpr int kPolW = 32;           // layer width (rl.py:144)
+constexpr int kPolMaxOut = 8;
+struct PolicyWeights {              // torch.nn.Linear layout: weight[out][in], y = x W^T + b
+    float f0w[kPolW][15], f0b[kPolW];
+    float f1w[kPolW][kPolW], f1b[kPolW];
+    float f2w[kPolW][kPolW], f2b[kPolW];
+    float v1w[kPolW][kPolW], v1b[kPolW];
+    float v2w[kPolW][kPolW], v2b[kPolW];
+    float v0w[kPolMaxOut][kPolW], v0b[kPolMaxOut];
+};
+__constant__ PolicyWeights c_pol;
+
+__device__ __forceinline__ float softsign(float x) { return x / (1.0f + fabsf(x)); }
+__device__ __forceinline__ unsigned enc_max(float f) {  // order-preserving float -> unsigned
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_max(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+template <typename R, int S>
+__global__ void __launch_bounds__(256) policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
+                                                     const void* __restrict__ planets_, const void* __restrict__ bullets_,
+                                                     const uint32_t* __restrict__ meta_, uint8_t* __restrict__ actions,
+                                                     float* __restrict__ q_out, int K, int nout, int ship_mask) {
+    using B4 = Body4<R>;
+    constexpr int DIN = 1 + 5 * S + 4;
+    __shared__ unsigned s_pool[32][S][kPolW];   // encoded running max per game, perspective, unit
+    __shared__ float s_ship[32][S][5];          // x, y, dx, dy, norm_angle(b) / pi
+    __shared__ int s_excl[33];                  // first row of each game in the tile's flat row list
+    __shared__ int s_np[32];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < 32 * S * kPolW; i += blockDim.x) (&s_pool[0][0][0])[i] = 0u;
+    if (tid < 32) {
+        const int lane = tid;
+        const uint32_t meta = meta_[tile * 32 + lane];
+        const bool fin = ASTRO_META_FINISHED(meta);
+        const int np = fin ? 0 : (int)ASTRO_META_NP(meta), nb = fin ? 0 : (int)ASTRO_META_NB(meta);
+        int incl = np + nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        s_excl[lane + 1] = incl;
+        if (lane == 0) s_excl[0] = 0;
+        s_np[lane] = np;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const B4 v = reinterpret_cast<const B4*>(ships_)[(size_t)tile * (S * 32) + s * 32 + lane];
+            const R b = reinterpret_cast<const R*>(ship_b_)[(size_t)tile * (S * 32) + s * 32 + lane];
+            s_ship[lane][s][0] = (float)v.x; s_ship[lane][s][1] = (float)v.y;
+            s_ship[lane][s][2] = (float)v.dx; s_ship[lane][s][3] = (float)v.dy;
+            s_ship[lane][s][4] = norm_angle_over_pi((double)b);
+        }
+    }
+    __syncthreads();
+    const int T = s_excl[32];
+    for (int it = tid; it < S * T; it += blockDim.x) {
+        const int k = it >= T ? 1 : 0;      // perspective (S <= 2)
+        const int j = it - k * T;
+        int lo = 0;                         // game of row j: last g with excl[g] <= j
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (s_excl[lo + step] <= j) lo += step;
+        const int gl = lo, r = j - s_excl[gl], np = s_np[gl];
+        B4 o;
+        if (r < np) o = reinterpret_cast<const B4*>(planets_)[(size_t)tile * (ASTRO_MAX_PLANETS * 32) + r * 32 + gl];
+        else o = reinterpret_cast<const B4*>(bullets_)[((size_t)tile * 32 + gl) * K + (r - np)];
+        float x[DIN];
+        x[0] = r < np ? 0.0f : 1.0f;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+#pragma unroll
+            for (int c = 0; c < 5; c++) x[1 + 5 * s + c] = s_ship[gl][(s + k) % S][c];
+        x[1 + 5 * S + 0] = (float)o.x; x[1 + 5 * S + 1] = (float)o.y;
+        x[1 + 5 * S + 2] = (float)o.dx; x[1 + 5 * S + 3] = (float)o.dy;
+        float h[kPolW], a[kPolW];
+#pragma unroll
+        for (int u = 0; u < kPolW; u++) {
+            float acc = c_pol.f0b[u];
+#pragma unroll
+            for (int c = 0; c < DIN; c++) acc = __fmaf_rn(c_pol.f0w[u][c], x[c], acc);
+            h[u] = softsign(acc);
+        }
+#pragma unroll
+        for (int u = 0; u < kPolW; u++) {
+            float acc = c_pol.f1b[u];
+#pragma unroll
+            for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.f1w[u][c], h[c], acc);
+            a[u] = softsign(acc);
+        }
+#pragma unroll
+        for (int u = 0; u < kPolW; u++) {
+            float acc = c_pol.f2b[u];
+#pragma unroll
+            for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.f2w[u][c], a[c], acc);
+            atomicMax(&s_pool[gl][k][u], enc_max(acc));
+        }
+    }
+    __syncthreads();
+    if (tid < 32 * S) {
+        const int gl = tid / S, k = tid % S;
+        const size_t g = (size_t)tile * 32 + gl;
+        const bool live = s_excl[gl + 1] > s_excl[gl];
+        float h[kPolW], a[kPolW], q[kPolMaxOut];
+#pragma unroll
+        for (int u = 0; u < kPolW; u++) h[u] = dec_max(s_pool[gl][k][u]);
+#pragma unroll
+        for (int u = 0; u < kPolW; u++) {
+            float acc = c_pol.v1b[u];
+#pragma unroll
+            for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.v1w[u][c], h[c], acc);
+            a[u] = softsign(acc);
+        }
+#pragma unroll
+        for (int u = 0; u < kPolW; u++) {
+            float acc = c_pol.v2b[u];
+#pragma unroll
+            for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.v2w[u][c], a[c], acc);
+            h[u] = softsign(acc);
+        }
+        int best = 0;
+#pragma unroll
+        for (int u = 0; u < kPolMaxOut; u++) {
+            q[u] = 0.0f;
+            if (u < nout) {
+                float acc = c_pol.v0b[u];
+#pragma unroll
+                for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.v0w[u][c], h[c], acc);
+                q[u] = tanhf(acc);
+                if (q[u] > q[best]) best = u;   // first maximum, like torch.argmax
+            }
+        }
+        if (!live) best = 2;                     // finished game: the no-op control
+        if ((ship_mask >> k) & 1) actions[g * S + k] = (uint8_t)best;
+        if (q_out)
+            for (int u = 0; u < nout; u++) q_out[(g * S + k) * nout + u] = live ? q[u] : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
@@ -770,6 +926,7 @@ struct AstroBatch {
     uint32_t seed, step;
     int64_t first_game;
     int64_t launches;
+    int32_t policy_nout;  // > 0 once astro_policy_set_weights has been called
     Consts c;
 };
 
@@ -1217,6 +1374,58 @@ int astro_create_games(AstroBatch* b, const AstroCreateConfig* cc, const uint32_
         if (b->S == 2) create_kernel<double, 2><<<grid, 64, 0, st>>>(seeds, (double*)ships, (double*)planets, n_planets, q);
         else create_kernel<double, 1><<<grid, 64, 0, st>>>(seeds, (double*)ships, (double*)planets, n_planets, q);
     }
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
+int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n_floats, int32_t nout) {
+    if (int r = check(b, false)) return r;
+    const int din = 1 + 5 * b->S + 4;
+    if (nout < 1 || nout > kPolMaxOut) return fail(ASTRO_E_INVALID, "nout must be 1..%d", kPolMaxOut);
+    const int expect = kPolW * din + kPolW + 4 * (kPolW * kPolW + kPolW) + nout * kPolW + nout;
+    if (!weights_host || n_floats != expect)
+        return fail(ASTRO_E_INVALID, "expected %d floats (f0, f[0], f[1], v[0], v[1], v0: weight then bias each), got %d", expect, n_floats);
+    CUDA_TRY(cudaSetDevice(b->device));
+    PolicyWeights* w = new (std::nothrow) PolicyWeights();
+    if (!w) return fail(ASTRO_E_NOMEM, "out of host memory");
+    memset(w, 0, sizeof(*w));
+    const float* p = weights_host;
+    for (int u = 0; u < kPolW; u++) for (int c = 0; c < din; c++) w->f0w[u][c] = *p++;
+    memcpy(w->f0b, p, sizeof(w->f0b)); p += kPolW;
+    memcpy(w->f1w, p, sizeof(w->f1w)); p += kPolW * kPolW;
+    memcpy(w->f1b, p, sizeof(w->f1b)); p += kPolW;
+    memcpy(w->f2w, p, sizeof(w->f2w)); p += kPolW * kPolW;
+    memcpy(w->f2b, p, sizeof(w->f2b)); p += kPolW;
+    memcpy(w->v1w, p, sizeof(w->v1w)); p += kPolW * kPolW;
+    memcpy(w->v1b, p, sizeof(w->v1b)); p += kPolW;
+    memcpy(w->v2w, p, sizeof(w->v2w)); p += kPolW * kPolW;
+    memcpy(w->v2b, p, sizeof(w->v2b)); p += kPolW;
+    memcpy(w->v0w, p, sizeof(float) * nout * kPolW); p += nout * kPolW;
+    memcpy(w->v0b, p, sizeof(float) * nout);
+    cudaError_t e = cudaMemcpyToSymbol(c_pol, w, sizeof(*w));
+    delete w;
+    if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e));
+    b->policy_nout = nout;
+    return ASTRO_OK;
+}
+
+int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t ship_mask, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (b->policy_nout <= 0) return fail(ASTRO_E_STATE, "astro_policy_set_weights has not been called");
+    if (!actions) return fail(ASTRO_E_INVALID, "null actions");
+    CUDA_TRY(cudaSetDevice(b->device));
+    const int grid = b->n_games / ASTRO_TILE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const AstroBuffers& u = b->bufs;
+#define LAUNCH_POL(R, S_) \
+    policy_kernel<R, S_><<<grid, 256, 0, st>>>(u.ships, u.ship_b, u.planets, u.bullets, u.meta, actions, q_out, b->K, b->policy_nout, ship_mask)
+    if (b->precision == 32) {
+        if (b->S == 2) LAUNCH_POL(float, 2); else LAUNCH_POL(float, 1);
+    } else {
+        if (b->S == 2) LAUNCH_POL(double, 2); else LAUNCH_POL(double, 1);
+    }
+#undef LAUNCH_POL
     CUDA_TRY(cudaGetLastError());
     b->launches += 1;
     return ASTRO_OK;

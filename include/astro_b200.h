@@ -201,6 +201,18 @@ int astro_create_games(AstroBatch* b, const AstroCreateConfig* cc, const uint32_
  * The output is directly the `actions` input of astro_tick: scripted games run without the host. */
 int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_threshold, uint8_t* actions, void* stream);
 
+/* rl.ValueNetwork.forward (rl.py:140-165) over the features of rl.py:43-72 for every game and both
+ * ship perspectives, fused: no observation tensor is written.  Weights: the reference network's
+ * state_dict flattened in order — f0, f[0], f[1], v[0], v[1], v0, weight [out][in] then bias
+ * each; width 32, inputs 15 (10 solo), nout <= 8 outputs — copied to the device's constant
+ * memory (one network per device at a time).
+ *   actions  u8 [n_games][S] device: argmax_q per ship (the greedy control of rl.QBot, rl.py:168-200);
+ *            written only for the ships whose bit is set in ship_mask (bit k = ship k), so another
+ *            bot can fill the rest; finished games get 2 (no-op)
+ *   q_out    f32 [n_games][S][nout] device or NULL: the network outputs (tanh) */
+int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n_floats, int32_t nout);
+int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t ship_mask, void* stream);
+
 /* Copies the ASTRO_N_STATS device counters into counters_dev (device pointer, e.g. the input of
  * an NCCL all-reduce) on the stream; clear != 0 zeroes them afterwards. */
 int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream);

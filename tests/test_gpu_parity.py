@@ -721,3 +721,78 @@ def test_game_recorder_writes_reference_format_logs(tmp_path):
         assert np.array_equal(back.ticks[3 % len(back.ticks)].state.ships.x, game.ticks[3 % len(game.ticks)].state.ships.x)
         head = json.loads(open(path).readline())
         assert head['config']['_type'] == 'astro.core:Config'
+
+
+# ------------------------------------------------------------------ fused features + value network
+
+@pytest.mark.parametrize('solo', [False, True])
+def test_policy_kernel_matches_value_network(solo):
+    """astro_policy_controls == ValueNetwork.forward(observe()) -> argmax, for every game and both
+    perspectives: outputs within 2e-6 of the PyTorch fp32 network (same products, different
+    summation order), controls identical wherever the top two outputs are further apart than that."""
+    import torch
+    from astro_b200 import rl
+    cfg = core.SOLO_CONFIG if solo else core.DEFAULT_CONFIG
+    S, N, K = (1 if solo else 2), 4096 + 32, 32
+    pool = H.make_pool(cfg, 256)
+    games = _games(cfg, N, bullet_cap=K, precision=32, seed=4)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    for _ in range(70):
+        games.step(None, auto_reset=True)
+    games.step(None, auto_reset=False)            # leaves a few finished games behind
+    torch.manual_seed(2)
+    net = rl.ValueNetwork(solo=solo, nout=6).to(games.device)
+    with torch.no_grad():
+        for prm in net.parameters():              # livelier than the default init: spread the outputs
+            prm.mul_(3.0)
+        want = net(games.observe())               # [N, S, 6]
+    games.set_policy(net)
+    q = torch.empty((games.n_pad, S, 6), dtype=torch.float32, device=games.device)
+    act = games.policy_controls(q_out=q)
+    fin = torch.from_numpy(games.get_arrays()['finished']).to(games.device)
+    assert fin.any()
+    live = ~fin
+    err = (q[:N][live] - want[live]).abs().max().item()
+    assert err <= 2e-6, err
+    assert (q[:N][fin] == 0).all() and (act[:N][fin] == 2).all()
+    top2 = want.topk(2, dim=-1).values
+    clear = live.unsqueeze(-1) & ((top2[..., 0] - top2[..., 1]) > 1e-5)
+    assert clear.float().mean() > 0.9
+    assert (act[:N].long()[clear] == want.argmax(-1)[clear]).all()
+    assert len(torch.unique(act[:N][live])) >= 3
+    # ship_mask: only ship 0's column is written
+    if not solo:
+        out = torch.full((games.n_pad, 2), 9, dtype=torch.uint8, device=games.device)
+        games.policy_controls(out=out, ships=[0])
+        assert (out[:, 1] == 9).all() and (out[:N, 0] == act[:N, 0]).all()
+
+
+def test_policy_rollout_equals_torch_rollout():
+    """A self-play rollout driven by the fused kernel ends in the same statistics as one driven by
+    observe() -> ValueNetwork -> argmax (config #5 of BASELINE.json at reduced size)."""
+    import torch
+    from astro_b200 import rl
+    cfg, N, K = core.DEFAULT_CONFIG, 1024, 32
+    pool = H.make_pool(cfg, 256)
+    torch.manual_seed(5)
+    net = rl.ValueNetwork(solo=False, nout=6).cuda()
+    with torch.no_grad():
+        for prm in net.parameters():
+            prm.mul_(3.0)
+    runs = []
+    for fused in (False, True):
+        games = _games(cfg, N, bullet_cap=K, precision=32, seed=9)
+        games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        games.reset_all()
+        games.set_policy(net)
+        same = 0
+        for k in range(150):
+            with torch.no_grad():
+                a_torch = net(games.observe()).argmax(-1).to(torch.uint8)
+            a_fused = games.policy_controls()[:N]
+            same += int((a_torch == a_fused).sum())
+            games.step(a_fused if fused else a_torch, auto_reset=True)
+        runs.append((games.stats(), same / (150 * N * 2)))
+    assert runs[0][1] > 0.9995 and runs[1][1] > 0.9995          # controls agree except at near-ties
+    assert abs(runs[0][0]['episodes'] - runs[1][0]['episodes']) <= 0.05 * runs[0][0]['episodes'] + 5

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--games', type=int, default=16384)
 ap.add_argument('--ticks', type=int, default=1000)
 ap.add_argument('--bullet-cap', type=int, default=32)
+ap.add_argument('--fused', action='store_true', help='features + ValueNetwork + argmax in one CUDA kernel (astro_policy_controls)')
 ap.add_argument('--shared', action='store_true', help='one observation tensor for both ships (observe(shared=True) + forward_both)')
 args = ap.parse_args()
 torch.manual_seed(0)
@@ -26,7 +27,15 @@ net = rl.ValueNetwork(solo=False, nout=6).to(dev).eval()
 obs = torch.empty((games.n_pad, 36, 15) if args.shared else (games.n_pad, 2, 36, 15), dtype=torch.float32, device=dev)
 
 
+games.set_policy(net)
+act = torch.full((games.n_pad, 2), 2, dtype=torch.uint8, device=dev)
+
+
 def tick():
+    if args.fused:
+        games.policy_controls(out=act)
+        games.step(act, auto_reset=True, want_reward=False)
+        return
     with torch.no_grad():
         o = games.observe(out=obs, shared=args.shared)   # [N, 2, 36, 15] / [N, 36, 15]
         q = net.forward_both(o) if args.shared else net(o)   # [N, 2, 6]
@@ -54,7 +63,7 @@ ms = e0.elapsed_time(e1)
 st = games.stats()
 obs_us = 1e3 * t_obs0.elapsed_time(t_obs1) / 50
 obs_bytes = obs.numel() * 4
-print(json.dumps(dict(shared=args.shared, workload='configs[4]: %d games x %d ticks, observe -> ValueNetwork(6) -> greedy -> step' % (args.games, args.ticks),
+print(json.dumps(dict(fused=args.fused, shared=args.shared, workload='configs[4]: %d games x %d ticks, observe -> ValueNetwork(6) -> greedy -> step' % (args.games, args.ticks),
                       env_steps_per_s=st['env_steps'] / (ms * 1e-3), ms_per_tick=ms / args.ticks,
                       observe_us=obs_us, observe_write_GBps=obs_bytes / (obs_us * 1e-6) / 1e9,
                       episodes=st['episodes'], wins0=st['wins0'], wins1=st['wins1'], both_lost=st['both_lost'],
