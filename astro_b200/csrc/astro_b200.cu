@@ -732,153 +732,179 @@ __global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__
 // h = softsign(v[i](h)) x2 ; q = tanh(v0(h)) ; control = argmax q  (the greedy policy of
 // rl.QBot, rl.py:168-200).
 //
-// CTA = one tile of 32 games.  Thread = one (perspective, row) of the tile's flat row list
-// (planets then bullets of each game, live rows only: no padding work — 7.8 rows per game on
-// average against 36 padded).  The 4,934 weights sit in constant memory: every lane of a warp
-// needs the same weight at the same time, so each FMA takes its weight straight from the constant
-// bank, and the 32 accumulators of a layer give the ILP.  Rows of one game are pooled with an
-// order-preserving integer atomicMax in shared memory; 64 threads then run the head.
-// fp32 FMA arithmetic (CUDA cores): agrees with the PyTorch fp32 network to ~1e-6; tensor-core
-// formats (tf32 / bf16) would flip near-tied argmaxes, and the whole network is 90 kFLOP per game.
+// WARP = one game, BOTH perspectives at once; LANE = UNIT of the 32-wide layers, its rows of the
+// three per-object layers (15 + 32 + 32 weights) held in registers for the whole kernel.  The warp
+// walks the game's live rows (planets then bullets; 7.8 per game on average against 36 padded — no
+// padding work).  The two perspectives see the same objects and differ only in the order of the
+// ship columns, so the ship part of f0 is computed once per game and perspective, the object part
+// once per row for both; a row then costs 5 + 2 x (32 + 32) FMAs per lane, as two independent
+// chains.  Activations cross lanes through a 128-byte shared buffer per chain, read back as
+// broadcast LDS.128; the max-pool over rows is a register per lane — no atomics, no block barrier.
+// The head runs on the same lanes with its weights streamed from a transposed copy (coalesced,
+// L1-resident).  fp32 FMA arithmetic (CUDA cores): agrees with the PyTorch fp32 network to ~1e-6;
+// tensor-core formats (tf32 / bf16) would flip near-tied argmaxes.
 // ------------------------------------------------------------------------------------------
 constexpr int kPolW = 32;           // layer width (rl.py:144)
 constexpr int kPolMaxOut = 8;
-struct PolicyWeights {              // torch.nn.Linear layout: weight[out][in], y = x W^T + b
-    float f0w[kPolW][15], f0b[kPolW];
-    float f1w[kPolW][kPolW], f1b[kPolW];
-    float f2w[kPolW][kPolW], f2b[kPolW];
-    float v1w[kPolW][kPolW], v1b[kPolW];
-    float v2w[kPolW][kPolW], v2b[kPolW];
-    float v0w[kPolMaxOut][kPolW], v0b[kPolMaxOut];
+constexpr int kPolWarps = 4;
+constexpr int kPolGamesPerWarp = 2; // consecutive games per warp: the lane's 79 weights are loaded once for both
+struct PolicyWeights {              // every matrix TRANSPOSED, [in][out]: lane = unit reads it coalesced
+    float f0t[15][kPolW], f0b[kPolW];
+    float f1t[kPolW][kPolW], f1b[kPolW];
+    float f2t[kPolW][kPolW], f2b[kPolW];
+    float v1t[kPolW][kPolW], v1b[kPolW];
+    float v2t[kPolW][kPolW], v2b[kPolW];
+    float v0t[kPolW][kPolMaxOut], v0b[kPolMaxOut];
 };
-__constant__ PolicyWeights c_pol;
+__device__ PolicyWeights g_pol;
 
-__device__ __forceinline__ float softsign(float x) { return x / (1.0f + fabsf(x)); }
-__device__ __forceinline__ unsigned enc_max(float f) {  // order-preserving float -> unsigned
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+// x / (1 + |x|) with the fast reciprocal (2 ulp): the network's outputs stay within ~1e-6 of PyTorch's
+__device__ __forceinline__ float softsign(float x) { return __fdividef(x, 1.0f + fabsf(x)); }
+
+// One 32 -> 32 layer for two independent activation vectors held in shared memory (broadcast
+// LDS.128), this lane's weight row w in registers: returns both pre-activations of the lane's unit.
+__device__ __forceinline__ void layer2(const float (&w)[kPolW], float bias, const float4* xa, const float4* xb, float& ya, float& yb) {
+    float a0 = bias, a1 = 0.f, b0 = bias, b1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kPolW; c += 4) {
+        const float4 u = xa[c >> 2], v = xb[c >> 2];
+        a0 = __fmaf_rn(w[c], u.x, a0); a1 = __fmaf_rn(w[c + 1], u.y, a1);
+        b0 = __fmaf_rn(w[c], v.x, b0); b1 = __fmaf_rn(w[c + 1], v.y, b1);
+        a0 = __fmaf_rn(w[c + 2], u.z, a0); a1 = __fmaf_rn(w[c + 3], u.w, a1);
+        b0 = __fmaf_rn(w[c + 2], v.z, b0); b1 = __fmaf_rn(w[c + 3], v.w, b1);
+    }
+    ya = a0 + a1;
+    yb = b0 + b1;
 }
-__device__ __forceinline__ float dec_max(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+// The same with the weights streamed from a transposed matrix wt[in][out] (head layers).
+__device__ __forceinline__ void layer2_t(const float* __restrict__ wt, int stride, int lane, float bias, const float* xa,
+                                         const float* xb, float& ya, float& yb) {
+    float a0 = bias, a1 = 0.f, b0 = bias, b1 = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < kPolW; c += 2) {
+        const float w0 = __ldg(wt + c * stride + lane), w1 = __ldg(wt + (c + 1) * stride + lane);
+        a0 = __fmaf_rn(w0, xa[c], a0); a1 = __fmaf_rn(w1, xa[c + 1], a1);
+        b0 = __fmaf_rn(w0, xb[c], b0); b1 = __fmaf_rn(w1, xb[c + 1], b1);
+    }
+    ya = a0 + a1;
+    yb = b0 + b1;
+}
 
 template <typename R, int S>
-__global__ void __launch_bounds__(256) policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
-                                                     const void* __restrict__ planets_, const void* __restrict__ bullets_,
-                                                     const uint32_t* __restrict__ meta_, uint8_t* __restrict__ actions,
-                                                     float* __restrict__ q_out, int K, int nout, int ship_mask) {
+__global__ void __launch_bounds__(kPolWarps * 32, 4)
+policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_, const void* __restrict__ planets_,
+              const void* __restrict__ bullets_, const uint32_t* __restrict__ meta_, uint8_t* __restrict__ actions,
+              float* __restrict__ q_out, int n_games, int K, int nout, int ship_mask) {
     using B4 = Body4<R>;
     constexpr int DIN = 1 + 5 * S + 4;
-    __shared__ unsigned s_pool[32][S][kPolW];   // encoded running max per game, perspective, unit
-    __shared__ float s_ship[32][S][5];          // x, y, dx, dy, norm_angle(b) / pi
-    __shared__ int s_excl[33];                  // first row of each game in the tile's flat row list
-    __shared__ int s_np[32];
-    const int tile = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < 32 * S * kPolW; i += blockDim.x) (&s_pool[0][0][0])[i] = 0u;
-    if (tid < 32) {
-        const int lane = tid;
-        const uint32_t meta = meta_[tile * 32 + lane];
-        const bool fin = ASTRO_META_FINISHED(meta);
-        const int np = fin ? 0 : (int)ASTRO_META_NP(meta), nb = fin ? 0 : (int)ASTRO_META_NB(meta);
-        int incl = np + nb;
+    __shared__ float4 s_act[kPolWarps][2][kPolW / 4];   // activation exchange, one buffer per chain
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* actA = reinterpret_cast<float*>(s_act[warp][0]);
+    float* actB = reinterpret_cast<float*>(s_act[warp][1]);
+    // this lane's unit: its rows of the three per-object layers
+    float w0[DIN], w1[kPolW], w2[kPolW];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
+    for (int c = 0; c < DIN; c++) w0[c] = g_pol.f0t[c][lane];
+#pragma unroll
+    for (int c = 0; c < kPolW; c++) { w1[c] = g_pol.f1t[c][lane]; w2[c] = g_pol.f2t[c][lane]; }
+    const float b0 = g_pol.f0b[lane], b1 = g_pol.f1b[lane], b2 = g_pol.f2b[lane];
+    for (int gi = 0; gi < kPolGamesPerWarp; gi++) {
+    const int g = (blockIdx.x * kPolWarps + warp) * kPolGamesPerWarp + gi;
+    if (g >= n_games) return;
+    const size_t tile = (size_t)(g >> 5);
+    const int gl = g & 31;
+
+    const uint32_t meta = meta_[g];
+    const bool fin = ASTRO_META_FINISHED(meta);
+    const int np = fin ? 0 : (int)ASTRO_META_NP(meta);
+    const int rows = fin ? 0 : np + (int)ASTRO_META_NB(meta);
+    // ship features (x, y, dx, dy, norm_angle(b) / pi), ship 0 then ship 1: lane 5 s + c holds feature c of ship s
+    float feat = 0.f;
+    if (lane < 5 * S) {
+        const int s = lane / 5, c = lane % 5;
+        if (c < 4) feat = (float)reinterpret_cast<const R*>(ships_)[((size_t)tile * (S * 32) + s * 32 + gl) * 4 + c];
+        else feat = norm_angle_over_pi((double)reinterpret_cast<const R*>(ship_b_)[(size_t)tile * (S * 32) + s * 32 + gl]);
+    }
+    // the ship columns (1 .. 5S) are the same for every row: perspective A = ship order (0, 1), B = (1, 0)
+    float baseA = b0, baseB = baseA;
+#pragma unroll
+    for (int s = 0; s < S; s++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const float f = __shfl_sync(0xffffffffu, feat, 5 * s + c);
+            baseA = __fmaf_rn(w0[1 + 5 * s + c], f, baseA);
+            baseB = __fmaf_rn(w0[1 + 5 * ((s + 1) % S) + c], f, baseB);
         }
-        s_excl[lane + 1] = incl;
-        if (lane == 0) s_excl[0] = 0;
-        s_np[lane] = np;
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            const B4 v = reinterpret_cast<const B4*>(ships_)[(size_t)tile * (S * 32) + s * 32 + lane];
-            const R b = reinterpret_cast<const R*>(ship_b_)[(size_t)tile * (S * 32) + s * 32 + lane];
-            s_ship[lane][s][0] = (float)v.x; s_ship[lane][s][1] = (float)v.y;
-            s_ship[lane][s][2] = (float)v.dx; s_ship[lane][s][3] = (float)v.dy;
-            s_ship[lane][s][4] = norm_angle_over_pi((double)b);
+    const B4* pl = reinterpret_cast<const B4*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32) + gl;
+    const B4* bl = reinterpret_cast<const B4*>(bullets_) + (size_t)g * K;
+    // lane r fetches row r's object (coalesced for the bullets); rows beyond 32 are fetched in a second batch
+    float bestA = -3.0e38f, bestB = -3.0e38f;
+    for (int r0 = 0; r0 < rows; r0 += 32) {
+        B4 mine = B4();
+        if (r0 + lane < rows) mine = (r0 + lane < np) ? pl[(r0 + lane) * 32] : bl[r0 + lane - np];
+        const int n = min(32, rows - r0);
+        for (int r = 0; r < n; r++) {
+            const float ox = __shfl_sync(0xffffffffu, (float)mine.x, r), oy = __shfl_sync(0xffffffffu, (float)mine.y, r);
+            const float ovx = __shfl_sync(0xffffffffu, (float)mine.dx, r), ovy = __shfl_sync(0xffffffffu, (float)mine.dy, r);
+            float h = r0 + r < np ? 0.0f : w0[0];      // w0[0] * flag
+            h = __fmaf_rn(w0[1 + 5 * S + 0], ox, h);
+            h = __fmaf_rn(w0[1 + 5 * S + 1], oy, h);
+            h = __fmaf_rn(w0[1 + 5 * S + 2], ovx, h);
+            h = __fmaf_rn(w0[1 + 5 * S + 3], ovy, h);
+            actA[lane] = softsign(baseA + h);
+            actB[lane] = softsign(baseB + h);
+            __syncwarp();
+            float ya, yb;
+            layer2(w1, b1, s_act[warp][0], s_act[warp][1], ya, yb);
+            __syncwarp();
+            actA[lane] = softsign(ya);
+            actB[lane] = softsign(yb);
+            __syncwarp();
+            layer2(w2, b2, s_act[warp][0], s_act[warp][1], ya, yb);
+            __syncwarp();
+            bestA = fmaxf(bestA, ya);
+            bestB = fmaxf(bestB, yb);
         }
     }
-    __syncthreads();
-    const int T = s_excl[32];
-    for (int it = tid; it < S * T; it += blockDim.x) {
-        const int k = it >= T ? 1 : 0;      // perspective (S <= 2)
-        const int j = it - k * T;
-        int lo = 0;                         // game of row j: last g with excl[g] <= j
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1)
-            if (s_excl[lo + step] <= j) lo += step;
-        const int gl = lo, r = j - s_excl[gl], np = s_np[gl];
-        B4 o;
-        if (r < np) o = reinterpret_cast<const B4*>(planets_)[(size_t)tile * (ASTRO_MAX_PLANETS * 32) + r * 32 + gl];
-        else o = reinterpret_cast<const B4*>(bullets_)[((size_t)tile * 32 + gl) * K + (r - np)];
-        float x[DIN];
-        x[0] = r < np ? 0.0f : 1.0f;
-#pragma unroll
-        for (int s = 0; s < S; s++)
-#pragma unroll
-            for (int c = 0; c < 5; c++) x[1 + 5 * s + c] = s_ship[gl][(s + k) % S][c];
-        x[1 + 5 * S + 0] = (float)o.x; x[1 + 5 * S + 1] = (float)o.y;
-        x[1 + 5 * S + 2] = (float)o.dx; x[1 + 5 * S + 3] = (float)o.dy;
-        float h[kPolW], a[kPolW];
-#pragma unroll
-        for (int u = 0; u < kPolW; u++) {
-            float acc = c_pol.f0b[u];
-#pragma unroll
-            for (int c = 0; c < DIN; c++) acc = __fmaf_rn(c_pol.f0w[u][c], x[c], acc);
-            h[u] = softsign(acc);
-        }
-#pragma unroll
-        for (int u = 0; u < kPolW; u++) {
-            float acc = c_pol.f1b[u];
-#pragma unroll
-            for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.f1w[u][c], h[c], acc);
-            a[u] = softsign(acc);
-        }
-#pragma unroll
-        for (int u = 0; u < kPolW; u++) {
-            float acc = c_pol.f2b[u];
-#pragma unroll
-            for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.f2w[u][c], a[c], acc);
-            atomicMax(&s_pool[gl][k][u], enc_max(acc));
-        }
+    // head: v[0], v[1] (linear -> softsign), v0 -> tanh, argmax; lane = unit, both perspectives
+    actA[lane] = bestA;
+    actB[lane] = bestB;
+    __syncwarp();
+    float ya, yb;
+    layer2_t(&g_pol.v1t[0][0], kPolW, lane, g_pol.v1b[lane], actA, actB, ya, yb);
+    __syncwarp();
+    actA[lane] = softsign(ya);
+    actB[lane] = softsign(yb);
+    __syncwarp();
+    layer2_t(&g_pol.v2t[0][0], kPolW, lane, g_pol.v2b[lane], actA, actB, ya, yb);
+    __syncwarp();
+    actA[lane] = softsign(ya);
+    actB[lane] = softsign(yb);
+    __syncwarp();
+    float qa = -2.0f, qb = -2.0f;                    // lanes >= nout stay below any tanh value
+    if (lane < kPolMaxOut) {
+        layer2_t(&g_pol.v0t[0][0], kPolMaxOut, lane, g_pol.v0b[lane], actA, actB, ya, yb);
+        if (lane < nout) { qa = tanhf(ya); qb = tanhf(yb); }
     }
-    __syncthreads();
-    if (tid < 32 * S) {
-        const int gl = tid / S, k = tid % S;
-        const size_t g = (size_t)tile * 32 + gl;
-        const bool live = s_excl[gl + 1] > s_excl[gl];
-        float h[kPolW], a[kPolW], q[kPolMaxOut];
+    // argmax over lanes 0 .. nout-1, first maximum like torch.argmax
+    float ma = qa, mb = qb;
 #pragma unroll
-        for (int u = 0; u < kPolW; u++) h[u] = dec_max(s_pool[gl][k][u]);
-#pragma unroll
-        for (int u = 0; u < kPolW; u++) {
-            float acc = c_pol.v1b[u];
-#pragma unroll
-            for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.v1w[u][c], h[c], acc);
-            a[u] = softsign(acc);
-        }
-#pragma unroll
-        for (int u = 0; u < kPolW; u++) {
-            float acc = c_pol.v2b[u];
-#pragma unroll
-            for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.v2w[u][c], a[c], acc);
-            h[u] = softsign(acc);
-        }
-        int best = 0;
-#pragma unroll
-        for (int u = 0; u < kPolMaxOut; u++) {
-            q[u] = 0.0f;
-            if (u < nout) {
-                float acc = c_pol.v0b[u];
-#pragma unroll
-                for (int c = 0; c < kPolW; c++) acc = __fmaf_rn(c_pol.v0w[u][c], h[c], acc);
-                q[u] = tanhf(acc);
-                if (q[u] > q[best]) best = u;   // first maximum, like torch.argmax
-            }
-        }
-        if (!live) best = 2;                     // finished game: the no-op control
-        if ((ship_mask >> k) & 1) actions[g * S + k] = (uint8_t)best;
-        if (q_out)
-            for (int u = 0; u < nout; u++) q_out[(g * S + k) * nout + u] = live ? q[u] : 0.0f;
+    for (int d = 4; d > 0; d >>= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, d));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, d));
     }
+    const bool live = rows > 0;
+    int ctlA = __ffs(__ballot_sync(0xffffffffu, lane < nout && qa == ma)) - 1;
+    int ctlB = __ffs(__ballot_sync(0xffffffffu, lane < nout && qb == mb)) - 1;
+    if (!live) ctlA = ctlB = 2;                      // finished game: the no-op control
+    if (lane == 0 && (ship_mask & 1)) actions[(size_t)g * S] = (uint8_t)ctlA;
+    if (S == 2 && lane == 1 && (ship_mask & 2)) actions[(size_t)g * S + 1] = (uint8_t)ctlB;
+    if (q_out && lane < nout) {
+        q_out[((size_t)g * S) * nout + lane] = live ? qa : 0.0f;
+        if (S == 2) q_out[((size_t)g * S + 1) * nout + lane] = live ? qb : 0.0f;
+    }
+    __syncwarp();
+    }  // games of this warp
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1391,19 +1417,19 @@ int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n
     if (!w) return fail(ASTRO_E_NOMEM, "out of host memory");
     memset(w, 0, sizeof(*w));
     const float* p = weights_host;
-    for (int u = 0; u < kPolW; u++) for (int c = 0; c < din; c++) w->f0w[u][c] = *p++;
+    for (int u = 0; u < kPolW; u++) for (int c = 0; c < din; c++) w->f0t[c][u] = *p++;
     memcpy(w->f0b, p, sizeof(w->f0b)); p += kPolW;
-    memcpy(w->f1w, p, sizeof(w->f1w)); p += kPolW * kPolW;
+    for (int u = 0; u < kPolW; u++) for (int c = 0; c < kPolW; c++) w->f1t[c][u] = *p++;
     memcpy(w->f1b, p, sizeof(w->f1b)); p += kPolW;
-    memcpy(w->f2w, p, sizeof(w->f2w)); p += kPolW * kPolW;
+    for (int u = 0; u < kPolW; u++) for (int c = 0; c < kPolW; c++) w->f2t[c][u] = *p++;
     memcpy(w->f2b, p, sizeof(w->f2b)); p += kPolW;
-    memcpy(w->v1w, p, sizeof(w->v1w)); p += kPolW * kPolW;
+    for (int u = 0; u < kPolW; u++) for (int c = 0; c < kPolW; c++) w->v1t[c][u] = *p++;
     memcpy(w->v1b, p, sizeof(w->v1b)); p += kPolW;
-    memcpy(w->v2w, p, sizeof(w->v2w)); p += kPolW * kPolW;
+    for (int u = 0; u < kPolW; u++) for (int c = 0; c < kPolW; c++) w->v2t[c][u] = *p++;
     memcpy(w->v2b, p, sizeof(w->v2b)); p += kPolW;
-    memcpy(w->v0w, p, sizeof(float) * nout * kPolW); p += nout * kPolW;
+    for (int u = 0; u < nout; u++) for (int c = 0; c < kPolW; c++) w->v0t[c][u] = *p++;
     memcpy(w->v0b, p, sizeof(float) * nout);
-    cudaError_t e = cudaMemcpyToSymbol(c_pol, w, sizeof(*w));
+    cudaError_t e = cudaMemcpyToSymbol(g_pol, w, sizeof(*w));
     delete w;
     if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e));
     b->policy_nout = nout;
@@ -1415,11 +1441,11 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
     if (b->policy_nout <= 0) return fail(ASTRO_E_STATE, "astro_policy_set_weights has not been called");
     if (!actions) return fail(ASTRO_E_INVALID, "null actions");
     CUDA_TRY(cudaSetDevice(b->device));
-    const int grid = b->n_games / ASTRO_TILE;
+    const int grid = (b->n_games + kPolWarps * kPolGamesPerWarp - 1) / (kPolWarps * kPolGamesPerWarp);
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;
 #define LAUNCH_POL(R, S_) \
-    policy_kernel<R, S_><<<grid, 256, 0, st>>>(u.ships, u.ship_b, u.planets, u.bullets, u.meta, actions, q_out, b->K, b->policy_nout, ship_mask)
+    policy_kernel<R, S_><<<grid, kPolWarps * 32, 0, st>>>(u.ships, u.ship_b, u.planets, u.bullets, u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask)
     if (b->precision == 32) {
         if (b->S == 2) LAUNCH_POL(float, 2); else LAUNCH_POL(float, 1);
     } else {

@@ -204,7 +204,7 @@ int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_thr
 /* rl.ValueNetwork.forward (rl.py:140-165) over the features of rl.py:43-72 for every game and both
  * ship perspectives, fused: no observation tensor is written.  Weights: the reference network's
  * state_dict flattened in order — f0, f[0], f[1], v[0], v[1], v0, weight [out][in] then bias
- * each; width 32, inputs 15 (10 solo), nout <= 8 outputs — copied to the device's constant
+ * each; width 32, inputs 15 (10 solo), nout <= 8 outputs — copied to device
  * memory (one network per device at a time).
  *   actions  u8 [n_games][S] device: argmax_q per ship (the greedy control of rl.QBot, rl.py:168-200);
  *            written only for the ships whose bit is set in ship_mask (bit k = ship k), so another

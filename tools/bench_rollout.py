@@ -54,6 +54,17 @@ t_obs0.record()
 for _ in range(50):
     games.observe(out=obs, shared=args.shared)
 t_obs1.record()
+t_pol0, t_pol1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t_pol0.record()
+for _ in range(50):
+    games.policy_controls(out=act)
+t_pol1.record()
+t_tk0, t_tk1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+t_tk0.record()
+for _ in range(50):
+    games.step_raw(act.data_ptr(), 1)
+t_tk1.record()
 e0.record()
 for _ in range(args.ticks):
     tick()
@@ -65,6 +76,6 @@ obs_us = 1e3 * t_obs0.elapsed_time(t_obs1) / 50
 obs_bytes = obs.numel() * 4
 print(json.dumps(dict(fused=args.fused, shared=args.shared, workload='configs[4]: %d games x %d ticks, observe -> ValueNetwork(6) -> greedy -> step' % (args.games, args.ticks),
                       env_steps_per_s=st['env_steps'] / (ms * 1e-3), ms_per_tick=ms / args.ticks,
-                      observe_us=obs_us, observe_write_GBps=obs_bytes / (obs_us * 1e-6) / 1e9,
+                      observe_us=obs_us, policy_kernel_us=1e3 * t_pol0.elapsed_time(t_pol1) / 50, tick_kernel_us=1e3 * t_tk0.elapsed_time(t_tk1) / 50, observe_write_GBps=obs_bytes / (obs_us * 1e-6) / 1e9,
                       episodes=st['episodes'], wins0=st['wins0'], wins1=st['wins1'], both_lost=st['both_lost'],
                       timeouts=st['timeouts'], overflow=st['overflow'])))
