@@ -23,7 +23,7 @@ EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro
            'astro_batch_bind', 'astro_set_schedule', 'astro_set_stream', 'astro_set_reset_pool',
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
            'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
-           'astro_policy_controls')
+           'astro_policy_controls', 'astro_rollout_device')
 
 
 class AstroConfig(C.Structure):
@@ -45,6 +45,10 @@ class AstroResetPool(C.Structure):
 class AstroCreateConfig(C.Structure):
     _fields_ = [('inner_ship_position', C.c_double), ('outer_ship_position', C.c_double), ('planet_orbit', C.c_double),
                 ('max_planets', C.c_int32), ('reserved', C.c_int32)]
+
+
+BOT_STREAM, BOT_SCRIPT, BOT_POLICY, BOT_NOTHING = 0, 1, 2, 3
+BOT_MODES = {'stream': BOT_STREAM, 'random': BOT_STREAM, 'script': BOT_SCRIPT, 'policy': BOT_POLICY, 'nothing': BOT_NOTHING}
 
 
 class AstroError(RuntimeError):
@@ -82,6 +86,7 @@ def lib():
     L.astro_observe_shared.argtypes = [vp, vp, i32, vp]
     L.astro_policy_set_weights.argtypes = [vp, vp, i32, i32]
     L.astro_policy_controls.argtypes = [vp, vp, vp, i32, vp]
+    L.astro_rollout_device.argtypes = [vp, i32, i32, i32, C.c_double, C.c_double, vp, vp, i32, vp]
     L.astro_create_games.argtypes = [vp, C.POINTER(AstroCreateConfig), vp, i32, vp, vp, vp, vp]
     L.astro_script_controls.argtypes = [vp, C.c_double, C.c_double, vp, vp]
     L.astro_launch_count.argtypes = [vp]

@@ -424,6 +424,22 @@ class BatchedGames:
                                                   mask, self._stream()))
         return out
 
+    # ---- whole game loops on the device -------------------------------------------------------------
+    def rollout_device(self, n_ticks, bots=('stream', 'stream'), auto_reset=True, stats=True, avoid_distance=0.1,
+                       avoid_threshold=0.45):
+        """`n_ticks` of the play loop (core.play, core.py:377-410; rl.train's games, rl.py:350-374) for
+        every game without the host between ticks.  bots: one of 'stream' (counter-stream random
+        controls, both ships), 'script' (script.ScriptBot), 'policy' (greedy network loaded with
+        set_policy), 'nothing' (script.NothingBot) per ship.  Outcomes accumulate in stats()."""
+        if isinstance(bots, str):
+            bots = (bots,) * self.S
+        modes = [nat.BOT_MODES[b] for b in bots] + [0]
+        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
+        nat.check(nat.lib().astro_rollout_device(self._h, int(n_ticks), modes[0], modes[1], float(avoid_distance),
+                                                 float(avoid_threshold), self._actions.data_ptr(), self._events.data_ptr(),
+                                                 flags, self._stream()))
+        self.step_index += int(n_ticks)
+
     # ---- statistics ------------------------------------------------------------------------------
     def stats_tensor(self, clear=False):
         """Device int64 [12] counters (see _native.STAT_NAMES) — the input of the NCCL all-reduce."""

@@ -1457,6 +1457,46 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
     return ASTRO_OK;
 }
 
+int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int32_t ship1_mode, double avoid_distance,
+                         double avoid_threshold, uint8_t* actions, uint8_t* events, int32_t flags, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (n_ticks < 0) return fail(ASTRO_E_INVALID, "n_ticks < 0");
+    const int modes[2] = {ship0_mode, b->S == 2 ? ship1_mode : ship0_mode};
+    bool any_script = false, any_policy = false, any_stream = false, any_idle = false;
+    for (int k = 0; k < b->S; k++) {
+        if (modes[k] < ASTRO_BOT_STREAM || modes[k] > ASTRO_BOT_NOTHING) return fail(ASTRO_E_INVALID, "unknown bot mode %d", modes[k]);
+        any_stream |= modes[k] == ASTRO_BOT_STREAM;
+        any_script |= modes[k] == ASTRO_BOT_SCRIPT;
+        any_policy |= modes[k] == ASTRO_BOT_POLICY;
+        any_idle |= modes[k] == ASTRO_BOT_NOTHING;
+    }
+    const bool all_stream = any_stream && !any_script && !any_policy && !any_idle;
+    if (any_stream && !all_stream) return fail(ASTRO_E_INVALID, "ASTRO_BOT_STREAM drives every ship or none");
+    if (!all_stream && !actions) return fail(ASTRO_E_INVALID, "a scratch actions buffer [n_games][S] is needed for bot modes");
+    if (any_policy && b->policy_nout <= 0) return fail(ASTRO_E_STATE, "astro_policy_set_weights has not been called");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    if (any_idle) CUDA_TRY(cudaMemsetAsync(actions, 2, (size_t)b->n_games * b->S, st));  // script.NothingBot: control 2
+    for (int k = 0; k < n_ticks; k++) {
+        // a script bot writes every ship's control, the policy then overwrites the ships it drives
+        if (any_script)
+            if (int r = astro_script_controls(b, avoid_distance, avoid_threshold, actions, stream)) return r;
+        if (any_idle && any_script) {
+            // (NothingBot next to a ScriptBot: restore the idle column — one strided memset)
+            for (int s = 0; s < b->S; s++)
+                if (modes[s] == ASTRO_BOT_NOTHING)
+                    CUDA_TRY(cudaMemset2DAsync(actions + s, b->S, 2, 1, (size_t)b->n_games, st));
+        }
+        if (any_policy) {
+            int mask = 0;
+            for (int s = 0; s < b->S; s++) mask |= (modes[s] == ASTRO_BOT_POLICY) << s;
+            if (int r = astro_policy_controls(b, actions, nullptr, mask, stream)) return r;
+        }
+        if (int r = do_tick(b, all_stream ? nullptr : actions, nullptr, nullptr, events, flags, st)) return r;
+    }
+    return ASTRO_OK;
+}
+
 int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream) {
     if (int r = check(b, false)) return r;
     if (!counters_dev) return fail(ASTRO_E_INVALID, "null counters");

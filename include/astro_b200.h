@@ -213,6 +213,23 @@ int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_thr
 int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n_floats, int32_t nout);
 int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t ship_mask, void* stream);
 
+/* n_ticks of a whole game loop without the host between ticks (core.play, core.py:377-410, and the
+ * evaluation games of rl.train, rl.py:350-374, for N games at once): every tick the chosen bot of
+ * each ship writes its control, then astro_tick runs.  Asynchronous; episode outcomes accumulate in
+ * the astro_stats counters (wins0 / wins1 / both_lost / timeouts).
+ *   shipK_mode  ASTRO_BOT_STREAM  counter-stream random controls (both ships or none)
+ *               ASTRO_BOT_SCRIPT  script.ScriptBot        (astro_script_controls)
+ *               ASTRO_BOT_POLICY  greedy rl.ValueNetwork  (astro_policy_controls)
+ *               ASTRO_BOT_NOTHING script.NothingBot: control 2
+ *   actions     u8 [n_games][S] device scratch (may be NULL for ASTRO_BOT_STREAM); holds the last tick's controls
+ *   events      u8 [n_games] device or NULL: the last tick's events */
+#define ASTRO_BOT_STREAM 0
+#define ASTRO_BOT_SCRIPT 1
+#define ASTRO_BOT_POLICY 2
+#define ASTRO_BOT_NOTHING 3
+int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int32_t ship1_mode, double avoid_distance,
+                         double avoid_threshold, uint8_t* actions, uint8_t* events, int32_t flags, void* stream);
+
 /* Copies the ASTRO_N_STATS device counters into counters_dev (device pointer, e.g. the input of
  * an NCCL all-reduce) on the stream; clear != 0 zeroes them afterwards. */
 int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream);

@@ -796,3 +796,51 @@ def test_policy_rollout_equals_torch_rollout():
         runs.append((games.stats(), same / (150 * N * 2)))
     assert runs[0][1] > 0.9995 and runs[1][1] > 0.9995          # controls agree except at near-ties
     assert abs(runs[0][0]['episodes'] - runs[1][0]['episodes']) <= 0.05 * runs[0][0]['episodes'] + 5
+
+
+# ------------------------------------------------------------------ whole game loops on the device
+
+@pytest.mark.parametrize('bots', [('script', 'script'), ('policy', 'script'), ('nothing', 'script'), ('policy', 'policy'),
+                                  ('stream', 'stream')])
+def test_rollout_device_equals_tick_by_tick_loop(bots):
+    """astro_rollout_device == the same loop driven from Python one call at a time: identical final
+    state and statistics (the bot kernels write the controls the tick consumes, nothing else differs)."""
+    import torch
+    from astro_b200 import rl
+    cfg, N, K, T = core.DEFAULT_CONFIG, 2048, 32, 160
+    pool = H.make_pool(cfg, 256)
+    torch.manual_seed(11)
+    net = rl.ValueNetwork(solo=False, nout=6).cuda()
+    with torch.no_grad():
+        for prm in net.parameters():
+            prm.mul_(3.0)
+    out = []
+    for fused_loop in (True, False):
+        games = _games(cfg, N, bullet_cap=K, precision=32, seed=13)
+        games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        games.reset_all()
+        games.set_policy(net)
+        if fused_loop:
+            games.rollout_device(T, bots=bots)
+        else:
+            for k in range(T):
+                if bots[0] == 'stream':
+                    games.step(None, auto_reset=True)
+                    continue
+                a = games.script_controls() if 'script' in bots else torch.full((games.n_pad, 2), 2, dtype=torch.uint8, device='cuda')
+                for s, b in enumerate(bots):
+                    if b == 'nothing':
+                        a[:, s] = 2
+                ships = [s for s, b in enumerate(bots) if b == 'policy']
+                if ships:
+                    games.policy_controls(out=a, ships=ships)
+                games.step(a, auto_reset=True)
+        out.append((games.get_arrays(), games.stats()))
+    (xa, sa), (xb, sb) = out
+    assert sa == sb and sa['env_steps'] == N * T and sa['episodes'] > 0
+    for k in ('ships', 'planets', 'n_bullets', 'n_planets', 'tick', 'episode'):
+        assert (xa[k] == xb[k]).all(), k
+    live = np.arange(K)[None, :] < xa['n_bullets'][:, None]
+    assert (xa['bullets'][live] == xb['bullets'][live]).all()
+    if bots == ('nothing', 'script'):
+        assert sa['wins1'] > sa['wins0']       # the scripted ship beats the idle one
