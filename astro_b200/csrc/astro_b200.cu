@@ -48,6 +48,7 @@ struct TickParams {
     const int32_t* pool_np;
     unsigned long long* stats;
     unsigned* stat_slots;  // u32 [n_tiles][16]: per-warp partial counters (tick_f32_kernel)
+    unsigned* queue;       // u32 [2]: next tile / finished warps (tick_f32_queue_kernel)
     int32_t n_games, K, timeout_tick, n_sched_ticks, pool_size, flags;
     uint32_t seed, step, first_game, pad;
     Consts c;
@@ -938,6 +939,7 @@ struct AstroBatch {
     int32_t n_sched_ticks, timeout_tick;
     unsigned long long* d_stats;
     unsigned* d_stat_slots;  // per-warp partial counters, folded by astro_stats
+    unsigned* d_queue;       // tile queue of the persistent kernel
     int64_t ticks_since_fold;
     uint8_t* d_actions;  // staging for astro_tick_host
     uint8_t* d_events;
@@ -1004,6 +1006,7 @@ void fill_params(const AstroBatch* b, TickParams& p) {
     p.pool_size = b->pool.size;
     p.stats = b->d_stats;
     p.stat_slots = b->d_stat_slots;
+    p.queue = b->d_queue;
     p.n_games = b->n_games;
     p.K = b->K;
     p.timeout_tick = b->timeout_tick;
@@ -1031,6 +1034,28 @@ cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
         tick_f32_kernel<S, false><<<grid, kTickThreads, 0, st>>>(p);
     else
         tick_f32_kernel<S, true><<<grid, kTickThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// Queue kernel: one resident wave of one-warp CTAs drawing tiles from a device counter.
+template <int S>
+cudaError_t launch_tick_queue(const TickParams& p, cudaStream_t st) {
+    static int resident = 0;
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick_f32_queue_kernel<S, true>, 32, 0);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        resident = sms * per_sm;
+    }
+    const int n_tiles = p.n_games / ASTRO_TILE;
+    const int grid = n_tiles < resident ? n_tiles : resident;
+    if (p.flags & ASTRO_TICK_NO_STATS)
+        tick_f32_queue_kernel<S, false><<<grid, 32, 0, st>>>(p);
+    else
+        tick_f32_queue_kernel<S, true><<<grid, 32, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -1087,6 +1112,8 @@ int do_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done,
     cudaError_t e;
     if (b->precision == 32 && (flags & ASTRO_TICK_GENERIC_KERNEL))
         e = b->S == 2 ? launch_tick<float, 2>(p, st) : launch_tick<float, 1>(p, st);
+    else if (b->precision == 32 && (flags & ASTRO_TICK_QUEUE))
+        e = b->S == 2 ? launch_tick_queue<2>(p, st) : launch_tick_queue<1>(p, st);
     else if (b->precision == 32 && (flags & (ASTRO_TICK_PERSISTENT | ASTRO_TICK_PREFETCH_ROWS)))
         e = b->S == 2 ? launch_tick_pipe<2>(p, st) : launch_tick_pipe<1>(p, st);
     else if (b->precision == 32)
@@ -1142,6 +1169,8 @@ int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_c
     const size_t slot_bytes = (size_t)(n_games / ASTRO_TILE) * 16 * sizeof(unsigned);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_stat_slots, slot_bytes);
     if (e == cudaSuccess) e = cudaMemset(b->d_stat_slots, 0, slot_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_queue, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(b->d_queue, 0, 2 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_actions, (size_t)n_games * b->S);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_events, (size_t)n_games);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_done, (size_t)n_games);
@@ -1159,6 +1188,7 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_stats);
     cudaFree(b->d_stat_slots);
+    cudaFree(b->d_queue);
     cudaFree(b->d_actions);
     cudaFree(b->d_events);
     cudaFree(b->d_done);

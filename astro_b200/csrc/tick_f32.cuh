@@ -298,18 +298,46 @@ __device__ long long* g_timeline = nullptr;
 #ifndef ASTRO_TICK_MIN_BLOCKS
 #define ASTRO_TICK_MIN_BLOCKS 26  /* shared memory admits 26 one-warp CTAs per SM: 72 registers */
 #endif
+// What a tile's first round trip to HBM brings: the fixed-size rows that do not depend on meta.
+struct TileIn {
+    uint32_t meta;
+    float4 shv[2];
+    float sb[2];
+    uint32_t ctl_raw;   // the tile's control bytes of this lane's game (S bytes), when actions are given
+};
+template <int S, bool WARM_PLANETS = true>
+__device__ __forceinline__ void load_tile_in(const TickParams& p, unsigned tile, unsigned lane, TileIn& in) {
+    const size_t g = (size_t)tile * 32 + lane;
+    in.meta = p.meta[g];
+    const float4* ships = reinterpret_cast<const float4*>(p.ships) + (size_t)tile * (S * 32) + lane;
+    const float* ship_b = reinterpret_cast<const float*>(p.ship_b) + (size_t)tile * (S * 32) + lane;
+    // The planet slots to load depend on meta (np).  Warm L2 with the tile's planet rows meanwhile:
+    // the dependent loads then take an L2 round trip instead of an HBM one (measured:
+    // 93.4 -> 91.4 us per 1M-game tick; sectors without a live lane are the price).
+    const float4* planets = reinterpret_cast<const float4*>(p.planets) + (size_t)tile * (ASTRO_MAX_PLANETS * 32) + lane;
+    if (WARM_PLANETS) {
+#pragma unroll
+        for (int j = 0; j < ASTRO_PREFETCH_PLANETS; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(&planets[j * 32]));
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        in.shv[s] = ships[s * 32];
+        in.sb[s] = ship_b[s * 32];
+    }
+    if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }  // S == 1: the second half of every ship pair mirrors ship 0
+    in.ctl_raw = 0;
+    if (p.actions) in.ctl_raw = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(p.actions)[g] : (uint32_t)p.actions[g];
+}
+
+// One core.step for the 32 games of one tile, by one warp.
 template <int S, bool STATS>
-__global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
+__device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, const unsigned lane, const unsigned tile_index,
+                                          const TileIn& in) {
     using B4 = Body4<float>;
     const unsigned full = 0xffffffffu;
-    __shared__ TileScratch s_tiles[kTickWarps];
-    const unsigned bid = blockIdx.x;
-    const int g = (int)(bid * kTickThreads + threadIdx.x);
-    if (g >= p.n_games) return;  // whole warps: n_games % 32 == 0
-    const unsigned lane = threadIdx.x & 31u;
+    const int g = (int)(tile_index * 32u + lane);
     const Consts& c = p.c;
-    TileScratch& t = s_tiles[threadIdx.x >> 5];
-    const size_t tile = (size_t)(g >> 5);
+    const size_t tile = (size_t)tile_index;
     float4* ships = reinterpret_cast<float4*>(p.ships) + tile * (S * 32) + lane;
     float* ship_b = reinterpret_cast<float*>(p.ship_b) + tile * (S * 32) + lane;
     float4* planets = reinterpret_cast<float4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
@@ -318,34 +346,15 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     const unsigned K = (unsigned)p.K;
     const unsigned tile_off = (unsigned)(g >> 5) * 32u * K;
 
-    // ================= 1. this lane's game: loads (independent except planets <- meta) ========
+    // ================= 1. this lane's game (rows already loaded: TileIn) ========================
     TL(0);
-    const uint32_t meta = p.meta[g];
-    // The planet slots to load depend on meta (np).  Warm L2 with the tile's planet rows meanwhile:
-    // the dependent loads below then take an L2 round trip instead of an HBM one (measured:
-    // 93.4 -> 91.4 us per 1M-game tick; sectors without a live lane are the price).
-    {
-#pragma unroll
-        for (int j = 0; j < ASTRO_PREFETCH_PLANETS; j++)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(&planets[j * 32]));
-    }
-    float4 shv[2];
-    float sb[2];
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-        shv[s] = ships[s * 32];
-        sb[s] = ship_b[s * 32];
-    }
-    if (S == 1) { shv[1] = shv[0]; sb[1] = sb[0]; }  // S == 1: the second half of every ship pair mirrors ship 0
+    const uint32_t meta = in.meta;
+    float4 shv[2] = {in.shv[0], in.shv[1]};
+    float sb[2] = {in.sb[0], in.sb[1]};
     int ctl[2];
     if (p.actions) {
-        if (S == 2) {
-            uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
-            ctl[0] = a & 0xff;
-            ctl[1] = a >> 8;
-        } else {
-            ctl[0] = ctl[1] = p.actions[g];
-        }
+        ctl[0] = (int)(in.ctl_raw & 0xffu);
+        ctl[1] = S == 2 ? (int)(in.ctl_raw >> 8) : ctl[0];
     } else {
         uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
         ctl[0] = action_from_key(h0, p.step, 0u);
@@ -656,4 +665,81 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         if (lane < ASTRO_N_STATS && mine) atomicAdd(slot, mine);  // RED: fire and forget
     }
     TL(7);
+}
+
+// ---- the launchable forms ---------------------------------------------------------------------
+// Classic: one warp (= one CTA) per tile; the block scheduler balances the load.
+template <int S, bool STATS>
+__global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
+    __shared__ TileScratch s_tiles[kTickWarps];
+    const unsigned tile = (blockIdx.x * kTickThreads + threadIdx.x) >> 5;
+    if ((int)(tile * 32u) >= p.n_games) return;  // whole warps: n_games % 32 == 0
+    const unsigned lane = threadIdx.x & 31u;
+    TileIn in;
+    load_tile_in<S>(p, tile, lane, in);
+    tick_tile<S, STATS>(p, s_tiles[threadIdx.x >> 5], lane, tile, in);
+}
+
+// Queue: one resident wave of one-warp CTAs; each warp takes tiles from a device-wide counter and
+// loads the NEXT tile's rows (12 registers) before it starts on the current one, so the first
+// round trip to HBM of every tile but a warp's first is hidden behind a whole tile of work and the
+// warp keeps requests in flight all the time.  The tile after next is drawn from the counter one
+// tile early for the same reason.  The last warp to finish re-arms the counters for the next launch.
+#ifndef ASTRO_QUEUE_MIN_BLOCKS
+#define ASTRO_QUEUE_MIN_BLOCKS 24
+#endif
+#ifndef ASTRO_QUEUE_WARM_NEXT
+#define ASTRO_QUEUE_WARM_NEXT 0
+#endif
+#ifndef ASTRO_QUEUE_CHUNK
+#define ASTRO_QUEUE_CHUNK 2   /* consecutive tiles per draw: same-address atomics serialise in L2 */
+#endif
+template <int S, bool STATS>
+__global__ void __launch_bounds__(32, ASTRO_QUEUE_MIN_BLOCKS) tick_f32_queue_kernel(const __grid_constant__ TickParams p) {
+    __shared__ TileScratch s_tile;
+    constexpr unsigned CH = ASTRO_QUEUE_CHUNK;
+    const unsigned lane = threadIdx.x, W = gridDim.x, n_tiles = (unsigned)p.n_games >> 5;
+    unsigned tile = blockIdx.x;   // the first W tiles are dealt statically, the rest drawn in chunks of CH
+    if (tile < n_tiles) {
+        // A draw is issued by lane 0 and its result is only broadcast when the chunk is needed, a
+        // chunk of tiles later: the atomic's round trip (and its queueing behind the other warps'
+        // draws on the same address) stays off the critical path.
+        auto issue_draw = [&]() { return lane == 0 ? atomicAdd(&p.queue[0], 1u) : 0u; };
+        unsigned pending = issue_draw();          // chunk after the current one (raw, lane 0)
+        unsigned base = 0, pos = CH;              // current chunk: exhausted -> take `pending`
+        auto next_tile = [&]() {
+            if (pos == CH) {
+                base = W + CH * __shfl_sync(0xffffffffu, pending, 0);
+                pending = issue_draw();
+                pos = 0;
+            }
+            return base + pos++;
+        };
+        unsigned tile_next = next_tile();
+        TileIn cur, nxt;
+        load_tile_in<S>(p, tile, lane, cur);
+        while (true) {
+            const bool more = tile_next < n_tiles;
+#if ASTRO_QUEUE_WARM_NEXT
+            if (more) load_tile_in<S>(p, tile_next, lane, nxt);   // in flight during this whole tile
+#else
+            // (planet rows are NOT warmed a tile ahead: by the time they are wanted, ~10 us later, L2 has
+            // turned over and the rows would be fetched from HBM twice)
+            if (more) load_tile_in<S, false>(p, tile_next, lane, nxt);
+#endif
+            tick_tile<S, STATS>(p, s_tile, lane, tile, cur);
+            if (!more) break;
+            __syncwarp();
+            tile = tile_next;
+            tile_next = next_tile();
+            cur = nxt;
+        }
+    }
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(&p.queue[1], 1u) == W - 1u) {  // every warp is past its last draw
+            p.queue[0] = 0u;
+            p.queue[1] = 0u;
+        }
+    }
 }

@@ -69,6 +69,7 @@ extern "C" {
 #define ASTRO_TICK_NO_STATS 2   /* skip the astro_stats counters for this tick */
 #define ASTRO_TICK_GENERIC_KERNEL 4 /* precision 32 only: run the un-tuned template kernel (A/B checks) */
 #define ASTRO_TICK_PERSISTENT 8     /* precision 32 only: persistent kernel, meta word one tile ahead (A/B) */
+#define ASTRO_TICK_QUEUE 32         /* precision 32 only: resident warps draw tiles from a device queue, next tile's rows prefetched */
 #define ASTRO_TICK_PREFETCH_ROWS 16 /* precision 32 only: persistent kernel, next tile's rows staged too (A/B) */
 
 /* error codes */

@@ -1,8 +1,8 @@
 #!/bin/bash
-# A/B bench of library variants under build_ab/ (runs on the GPU box)
+# A/B bench of library variants under build_ab/ (runs on the GPU box); TICK_FLAGS = extra --tick-flags
 mkdir -p gpurun_out
 run() { name=$1; shift
-  out=$(env "$@" python bench.py --steps 400 --warmup 50 --no-cpu-baseline --e2e-steps 16 2>&1 | tail -1)
+  out=$(env "$@" python bench.py --steps 400 --warmup 50 --no-cpu-baseline --e2e-steps 16 --tick-flags ${TICK_FLAGS:-0} 2>&1 | tail -1)
   echo "$name $(echo "$out" | python -c "
 import json,sys
 try:

@@ -11,11 +11,12 @@ from astro_b200.pool import make_pool
 ap = argparse.ArgumentParser()
 ap.add_argument('--games', type=int, default=1 << 20)
 ap.add_argument('--preroll', type=int, default=600)
+ap.add_argument('--flags', type=int, default=0)
 a = ap.parse_args()
 games = BatchedGames(core.DEFAULT_CONFIG, a.games, bullet_cap=32, precision=32, device=0)
 pool = make_pool(core.DEFAULT_CONFIG, 4096)
 games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np']); games.reset_all()
-flags = nat.TICK_AUTO_RESET
+flags = nat.TICK_AUTO_RESET | a.flags
 ring = torch.randint(0, 6, (8, games.n_pad, 2), dtype=torch.uint8).cuda()
 for k in range(a.preroll): games.step_raw(ring[k % 8].data_ptr(), flags)
 buf = torch.zeros((a.games // 32, 8), dtype=torch.int64, device='cuda')
