@@ -298,6 +298,18 @@ __device__ long long* g_timeline = nullptr;
 #ifndef ASTRO_TICK_MIN_BLOCKS
 #define ASTRO_TICK_MIN_BLOCKS 26  /* shared memory admits 26 one-warp CTAs per SM: 72 registers */
 #endif
+// Cache hints for the once-per-tick streams (A/B: ASTRO_STREAM_HINTS = 1 -> ld.global.cs / st.global.cs)
+#ifndef ASTRO_STREAM_HINTS
+#define ASTRO_STREAM_HINTS 0
+#endif
+#if ASTRO_STREAM_HINTS
+#define LD_STREAM(ptr) __ldcs(ptr)
+#define ST_STREAM(ptr, v) __stcs(ptr, v)
+#else
+#define LD_STREAM(ptr) (*(ptr))
+#define ST_STREAM(ptr, v) (*(ptr) = (v))
+#endif
+
 // What a tile's first round trip to HBM brings: the fixed-size rows that do not depend on meta.
 struct TileIn {
     uint32_t meta;
@@ -308,7 +320,7 @@ struct TileIn {
 template <int S, bool WARM_PLANETS = true>
 __device__ __forceinline__ void load_tile_in(const TickParams& p, unsigned tile, unsigned lane, TileIn& in) {
     const size_t g = (size_t)tile * 32 + lane;
-    in.meta = p.meta[g];
+    in.meta = LD_STREAM(&p.meta[g]);
     const float4* ships = reinterpret_cast<const float4*>(p.ships) + (size_t)tile * (S * 32) + lane;
     const float* ship_b = reinterpret_cast<const float*>(p.ship_b) + (size_t)tile * (S * 32) + lane;
     // The planet slots to load depend on meta (np).  Warm L2 with the tile's planet rows meanwhile:
@@ -321,8 +333,8 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, unsigned tile,
     }
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        in.shv[s] = ships[s * 32];
-        in.sb[s] = ship_b[s * 32];
+        in.shv[s] = LD_STREAM(&ships[s * 32]);
+        in.sb[s] = LD_STREAM(&ship_b[s * 32]);
     }
     if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }  // S == 1: the second half of every ship pair mirrors ship 0
     in.ctl_raw = 0;
@@ -374,7 +386,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
 #pragma unroll
     for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
         plv[j] = make_float4(kFar, kFar, 0.f, 0.f);
-        if (j < np) plv[j] = planets[j * 32];
+        if (j < np) plv[j] = LD_STREAM(&planets[j * 32]);
     }
 
     // ================= 2. flat bullet list of the tile; stage it with cp.async =================
@@ -479,8 +491,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             hits |= h ? (1u << s) : 0u;
             const float th = (ctl[s] & 1) ? c.thrust_f : 0.f;
             acc = fma2(bc2(th), pk2(dirs[2 * s], dirs[2 * s + 1]), acc);
-            ships[s * 32] = advance_body2(sxy, pk2(shv[s].z, shv[s].w), acc, c);  // core.py:283-288
-            ship_b[s * 32] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
+            ST_STREAM(&ships[s * 32], advance_body2(sxy, pk2(shv[s].z, shv[s].w), acc, c));  // core.py:283-288
+            ST_STREAM(&ship_b[s * 32], __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]));
         }
         if (S == 2) {
             if (collide(shv[0].x, shv[0].y, shv[1].x, shv[1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
@@ -503,7 +515,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
         }
 #pragma unroll
         for (int i = 0; i < ASTRO_MAX_PLANETS; i++)
-            if (i < np) planets[i * 32] = advance_body2(pxy[i], pk2(plv[i].z, plv[i].w), q[i], c);
+            if (i < np) ST_STREAM(&planets[i * 32], advance_body2(pxy[i], pk2(plv[i].z, plv[i].w), q[i], c));
     }
 
     // ================= 4. the bullet loop, from shared memory =======================================
@@ -548,7 +560,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             const unsigned kb = __ballot_sync(full, keep);
             const unsigned seg_lo = lane - min(slot, lane);  // first lane of this game's segment
             const unsigned pos = (slot > lane ? carry : 0u) + __popc(kb & lt_mask & (full << seg_lo));
-            if (keep) bullets[tile_off + gi * K + pos] = x.bv;
+            if (keep) ST_STREAM(&bullets[tile_off + gi * K + pos], x.bv);
             const unsigned tot = pos + (keep ? 1u : 0u);
             if (x.ref & 0x8000u) t.outn[gi] = tot;
             carry = __shfl_sync(full, tot, 31);
@@ -623,7 +635,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
                 }
                 spawned = S;
             }
-            p.meta[g] = ASTRO_META_PACK(m, np, 0, tick + 1);
+            ST_STREAM(&p.meta[g], ASTRO_META_PACK(m, np, 0, tick + 1));
             m_out = m;
         }
         if (ev & ASTRO_EV_DONE_MASK) {
@@ -654,7 +666,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
         if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[1]);
         else p.reward[g] = rw[0];
     }
-    if (p.events) p.events[g] = (uint8_t)ev;
+    if (p.events) ST_STREAM(&p.events[g], (uint8_t)ev);
     if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
 
     if (STATS) {

@@ -844,3 +844,57 @@ def test_rollout_device_equals_tick_by_tick_loop(bots):
     assert (xa['bullets'][live] == xb['bullets'][live]).all()
     if bots == ('nothing', 'script'):
         assert sa['wins1'] > sa['wins0']       # the scripted ship beats the idle one
+
+
+def test_abi_errors_of_the_bot_and_create_entry_points():
+    """Every new entry point reports misuse through its return code and astro_last_error()."""
+    import ctypes as C
+    import torch
+    L = nat.lib()
+    games = _games(core.DEFAULT_CONFIG, 64, bullet_cap=8, precision=32)
+    h, st = games._h, games._stream()
+    act = torch.zeros((64, 2), dtype=torch.uint8, device='cuda')
+    assert L.astro_script_controls(h, 0.1, 0.45, None, st) == -1 and b'null' in L.astro_last_error()
+    assert L.astro_policy_controls(h, act.data_ptr(), None, 3, st) == -3 and b'astro_policy_set_weights' in L.astro_last_error()
+    w = np.zeros(10, dtype=np.float32)
+    assert L.astro_policy_set_weights(h, w.ctypes.data_as(C.c_void_p), 10, 6) == -1 and b'expected 4934 floats' in L.astro_last_error()
+    assert L.astro_policy_set_weights(h, w.ctypes.data_as(C.c_void_p), 10, 9) == -1
+    assert L.astro_rollout_device(h, 4, 2, 1, 0.1, 0.45, act.data_ptr(), None, 0, st) == -3      # policy without weights
+    assert L.astro_rollout_device(h, 4, 0, 1, 0.1, 0.45, act.data_ptr(), None, 0, st) == -1      # stream mixed with a bot
+    assert L.astro_rollout_device(h, 4, 1, 1, 0.1, 0.45, None, None, 0, st) == -1                # bots need the scratch buffer
+    assert L.astro_rollout_device(h, 4, 7, 1, 0.1, 0.45, act.data_ptr(), None, 0, st) == -1
+    cc = nat.AstroCreateConfig(0.2, 0.9, 0.5, 5, 0)
+    seeds = torch.zeros(4, dtype=torch.int32, device='cuda')
+    buf = torch.zeros(4 * 2 * 5 + 4 * 16 + 4, dtype=torch.float32, device='cuda')
+    assert L.astro_create_games(h, C.byref(cc), seeds.data_ptr(), 4, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), st) == -1
+    assert b'max_planets' in L.astro_last_error()
+    assert L.astro_observe_shared(h, None, 12, st) == -1
+    big = nat.AstroConfig()
+    hh = C.c_void_p()
+    assert L.astro_batch_create(C.byref(big), 1 << 26, 64, 32, 0, C.byref(hh)) == -1 and b'2^31' in L.astro_last_error()
+    # a working call after the failures
+    assert L.astro_script_controls(h, 0.1, 0.45, act.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    assert (act.cpu().numpy() == 2).all()      # every slot is still finished: no-op controls
+
+
+def test_policy_kernel_float64_state():
+    """The fused policy kernel on the float64 validation build: features are cast to float32 exactly
+    as rl.py:62-70 casts them, so the outputs match the network on observe() of the same batch."""
+    import torch
+    from astro_b200 import rl
+    cfg, N = core.DEFAULT_CONFIG, 512
+    pool = H.make_pool(cfg, 64)
+    games = _games(cfg, N, bullet_cap=32, precision=64, seed=8)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    for _ in range(60):
+        games.step(None, auto_reset=True)
+    torch.manual_seed(3)
+    net = rl.ValueNetwork(solo=False, nout=6).cuda()
+    games.set_policy(net)
+    q = torch.empty((games.n_pad, 2, 6), dtype=torch.float32, device='cuda')
+    games.policy_controls(q_out=q)
+    with torch.no_grad():
+        want = net(games.observe())
+    assert float((q[:N] - want).abs().max()) <= 2e-6
