@@ -408,15 +408,17 @@ __global__ void __launch_bounds__(kTickThreads) reset_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// observe_kernel<R, S>: one warp = one game.  The warp stages the game's feature rows
+// observe_kernel<R, S, BOTH>: one warp = one game.  The warp builds the game's feature rows
 // (rl.py:43-72: [flag | every ship's x,y,dx,dy,norm_angle(b)/pi | object x,y,dx,dy]) in shared
-// memory — lane r builds row r — then streams both perspectives (core.roll_ships: ship columns
-// rotated) to HBM as coalesced 128-bit stores; rows beyond P+B are the -1 padding of to_batch
-// (rl.py:91-98).
+// memory — lane r builds row r, for ship 0's perspective and, with BOTH, for ship 1's
+// (core.roll_ships: the ship column groups exchanged); rows beyond P+B are the -1 padding of
+// to_batch (rl.py:91-98).  The finished block (both perspectives are adjacent in the output) then
+// leaves as ONE bulk copy through the TMA engine (cp.async.bulk shared -> global): the kernel is a
+// pure stream of writes, and this keeps the LSU out of it.
 // ------------------------------------------------------------------------------------------
-// per-warp staging: n_rows*D feature floats + 5*S ship features, padded to a 16-byte multiple
-__host__ __device__ inline size_t observe_warp_floats(int n_rows, int D, int S) {
-    return (((size_t)n_rows * D + 5 * S) + 3) & ~(size_t)3;
+// per-warp staging: P perspectives x n_rows*D feature floats + 5*S ship features, padded to a 16-byte multiple
+__host__ __device__ inline size_t observe_warp_floats(int n_rows, int D, int S, int P) {
+    return (((size_t)P * n_rows * D + 5 * S) + 3) & ~(size_t)3;
 }
 
 template <typename R, int S, bool BOTH>
@@ -426,13 +428,15 @@ observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_
                int n_games, int K, int n_rows) {
     using B4 = Body4<R>;
     constexpr int D = 1 + 5 * S + 4;
+    constexpr int P = (BOTH && S == 2) ? 2 : 1;
     extern __shared__ float4 s_all4[];
     float* s_all = reinterpret_cast<float*>(s_all4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * kObserveWarps + warp;
     if (g >= n_games) return;
-    float* rows = s_all + (size_t)warp * observe_warp_floats(n_rows, D, S);
-    float* sf = rows + (size_t)n_rows * D;  // ship features, ship 0 first
+    const int per = n_rows * D;  // % 4 == 0 (checked on the host)
+    float* rows = s_all + (size_t)warp * observe_warp_floats(n_rows, D, S, P);
+    float* sf = rows + (size_t)P * per;  // ship features, ship 0 first
 
     const size_t tile = (size_t)(g >> 5);
     const int gl = g & 31;
@@ -457,45 +461,39 @@ observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_
         float* row = rows + r * D;
         if (r < np + nb) {
             B4 o = r < np ? planets[r * 32] : bullets[r - np];
-            row[0] = r < np ? 0.0f : 1.0f;
+            const float flag = r < np ? 0.0f : 1.0f;
 #pragma unroll
-            for (int k = 0; k < 5 * S; k++) row[1 + k] = sf[k];
-            row[1 + 5 * S + 0] = (float)o.x;
-            row[1 + 5 * S + 1] = (float)o.y;
-            row[1 + 5 * S + 2] = (float)o.dx;
-            row[1 + 5 * S + 3] = (float)o.dy;
+            for (int q = 0; q < P; q++) {
+                float* dst = row + q * per;
+                dst[0] = flag;
+#pragma unroll
+                for (int s = 0; s < S; s++)
+#pragma unroll
+                    for (int k = 0; k < 5; k++) dst[1 + 5 * s + k] = sf[5 * ((s + q) % S) + k];
+                dst[1 + 5 * S + 0] = (float)o.x;
+                dst[1 + 5 * S + 1] = (float)o.y;
+                dst[1 + 5 * S + 2] = (float)o.dx;
+                dst[1 + 5 * S + 3] = (float)o.dy;
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < D; k++) row[k] = -1.0f;
+            for (int q = 0; q < P; q++)
+#pragma unroll
+                for (int k = 0; k < D; k++) row[q * per + k] = -1.0f;
         }
     }
+    // hand the block to the TMA engine: generic-proxy writes -> async proxy, then one bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    // stream out: perspective 0 is the staged block; perspective 1 swaps the ship columns
-    const int per = n_rows * D;  // % 4 == 0 (checked on the host)
-    float4* out = reinterpret_cast<float4*>(obs + (size_t)g * (BOTH ? S : 1) * per);
-    const float4* src4 = reinterpret_cast<const float4*>(rows);
-    for (int q = lane; q < per / 4; q += 32) out[q] = src4[q];
-    if (S == 2 && BOTH) {
-        float4* out1 = out + per / 4;
-        const int live = (np + nb) * D;
-        for (int q = lane; q < per / 4; q += 32) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int idx = 4 * q + e;
-                int col = idx % D;
-                int srci = idx;
-                if (idx < live) {
-                    if (col >= 1 && col <= 5) srci = idx + 5;
-                    else if (col >= 6 && col <= 10) srci = idx - 5;
-                }
-                v[e] = rows[srci];
-            }
-            out1[q] = make_float4(v[0], v[1], v[2], v[3]);
-        }
+    if (lane == 0) {
+        float* out = obs + (size_t)g * P * per;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out),
+                     "r"((unsigned)__cvta_generic_to_shared(rows)), "r"((unsigned)(P * per * 4))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
     }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // script_kernel<R, S>: script.ScriptBot.__call__ (script.py:67-91) with _danger (:41-65) and
@@ -1345,7 +1343,7 @@ static int observe_impl(AstroBatch* b, float* obs, int32_t n_rows, bool both, vo
     if ((n_rows * D) % 4) return fail(ASTRO_E_INVALID, "n_rows * %d must be a multiple of 4", D);
     if ((uintptr_t)obs & 15) return fail(ASTRO_E_INVALID, "obs must be 16-byte aligned");
     CUDA_TRY(cudaSetDevice(b->device));
-    const size_t smem = (size_t)kObserveWarps * observe_warp_floats(n_rows, D, b->S) * sizeof(float);
+    const size_t smem = (size_t)kObserveWarps * observe_warp_floats(n_rows, D, b->S, (both && b->S == 2) ? 2 : 1) * sizeof(float);
     if (smem > 200 * 1024) return fail(ASTRO_E_INVALID, "n_rows %d too large for the staging buffer", n_rows);
     const int grid = (b->n_games + kObserveWarps - 1) / kObserveWarps;
     cudaStream_t st = (cudaStream_t)stream;
