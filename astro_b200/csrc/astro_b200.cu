@@ -513,9 +513,23 @@ struct ScriptParams {
     int32_t solo, n_games;
 };
 
+// fmod(a, m) for m > 0 and |a / m| < 2^52, exact like the library routine but in a few operations: with
+// the right integer quotient q, a - q m is representable (it is the result) and fma(-q, m, a) rounds
+// once, i.e. not at all; a quotient off by one after the division's rounding is corrected and redone.
+__device__ __forceinline__ double fmod_small(double a, double m) {
+    const double x = fabs(a);
+    double q = floor(__ddiv_rn(x, m));
+    double r = fma(-q, m, x);
+    if (r < 0.0) { q -= 1.0; r = fma(-q, m, x); }
+    else if (r >= m) { q += 1.0; r = fma(-q, m, x); }
+    return copysign(r, a);   // sign of the dividend (C fmod), -0.0 kept
+}
 __device__ __forceinline__ double norm_angle_f64(double b) {  // util.norm_angle, util.py:125-132
-    const double PI = 3.141592653589793;
-    return __dsub_rn(np_remainder(__dadd_rn(b, PI), __dmul_rn(2.0, PI)), PI);
+    const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
+    const double a = __dadd_rn(b, PI);
+    double m = fmod_small(a, TWO_PI);          // numpy's floored remainder (divisor > 0)
+    if (m != 0.0) { if (m < 0.0) m = __dadd_rn(m, TWO_PI); } else m = 0.0;
+    return __dsub_rn(m, PI);
 }
 __device__ __forceinline__ int fly_to(double target, double my_b, double t, bool fwd) {  // script.py:30-39
     const double angle = norm_angle_f64(__dsub_rn(target, my_b));
@@ -524,81 +538,86 @@ __device__ __forceinline__ int fly_to(double target, double my_b, double t, bool
     return fwd ? 3 : 2;
 }
 
+// thread = one ship of one game (its own perspective).  The cheap part of _danger — two square
+// roots, two divisions, the discriminant — runs for every planet without divergence and leaves a
+// bit mask of the planets on a collision course; only those go through the atan2 / norm_angle
+// test, in planet order (the first dangerous planet decides, script.py:69-76), so the warp executes
+// that code as often as its worst lane needs it (usually once), from one copy of it.
 template <typename R, int S>
 __global__ void __launch_bounds__(128) script_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
                                                      const void* __restrict__ planets_, const uint32_t* __restrict__ meta_,
                                                      uint8_t* __restrict__ actions, const __grid_constant__ ScriptParams q) {
     using B4 = Body4<R>;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = idx / S, me = idx % S;
     if (g >= q.n_games) return;
     const size_t tile = (size_t)(g >> 5);
     const int lane = g & 31;
     const uint32_t meta = meta_[g];
     if (ASTRO_META_FINISHED(meta)) {
-#pragma unroll
-        for (int me = 0; me < S; me++) actions[(size_t)g * S + me] = 2;
+        actions[idx] = 2;
         return;
     }
     const int np = (int)ASTRO_META_NP(meta);
-    double sx[S][5];
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-        const B4 v = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + s * 32 + lane];
-        sx[s][0] = (double)v.x; sx[s][1] = (double)v.y; sx[s][2] = (double)v.dx; sx[s][3] = (double)v.dy;
-        sx[s][4] = (double)reinterpret_cast<const R*>(ship_b_)[tile * (S * 32) + s * 32 + lane];
-    }
-    double px[ASTRO_MAX_PLANETS][4];
+    const B4 mv = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + me * 32 + lane];
+    const double my[5] = {(double)mv.x, (double)mv.y, (double)mv.dx, (double)mv.dy,
+                          (double)reinterpret_cast<const R*>(ship_b_)[tile * (S * 32) + me * 32 + lane]};
+    unsigned cand = 0;
+    double cx0[ASTRO_MAX_PLANETS], cx1[ASTRO_MAX_PLANETS], cb[ASTRO_MAX_PLANETS], csd[ASTRO_MAX_PLANETS], cspeed[ASTRO_MAX_PLANETS];
+    const double ra = __dadd_rn(q.radius, q.avoid_distance);
+    const double ra2 = __dmul_rn(ra, ra);
 #pragma unroll
     for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+        cx0[j] = cx1[j] = cb[j] = csd[j] = cspeed[j] = 0.0;
         if (j < np) {
             const B4 v = reinterpret_cast<const B4*>(planets_)[tile * (ASTRO_MAX_PLANETS * 32) + j * 32 + lane];
-            px[j][0] = (double)v.x; px[j][1] = (double)v.y; px[j][2] = (double)v.dx; px[j][3] = (double)v.dy;
-        }
-    }
-#pragma unroll
-    for (int me = 0; me < S; me++) {
-        const double* my = sx[me];
-        int ctl = -1;
-#pragma unroll
-        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
-            if (j < np && ctl < 0) {
-                const double x0 = __dsub_rn(my[0], px[j][0]), x1 = __dsub_rn(my[1], px[j][1]);
-                const double v0 = __dsub_rn(my[2], px[j][2]), v1 = __dsub_rn(my[3], px[j][3]);
-                const double speed = sqrt(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)));   // util.mag(dx)
-                const double den = __dadd_rn(speed, 1e-12);
-                const double n0 = __ddiv_rn(v0, den), n1 = __ddiv_rn(v1, den);                   // util.norm(dx)
-                const double b = __dmul_rn(2.0, __dadd_rn(__dmul_rn(n0, x0), __dmul_rn(n1, x1)));
-                const double mx = sqrt(__dadd_rn(__dmul_rn(x0, x0), __dmul_rn(x1, x1)));
-                const double ra = __dadd_rn(q.radius, q.avoid_distance);
-                const double cc = __dsub_rn(__dmul_rn(mx, mx), __dmul_rn(ra, ra));
-                const double det = __dsub_rn(__dmul_rn(b, b), __dmul_rn(4.0, cc));
-                if (0.0 < det) {
-                    const double sd = sqrt(det);
-                    if (0.0 <= __dadd_rn(-b, sd)) {
-                        const double distance = __dsub_rn(-b, sd);
-                        const double bear = atan2(x0, x1);                                        // util.bearing(x)
-                        const double rotation = fabs(norm_angle_f64(__dsub_rn(bear, b)));
-                        const double lim = __dmul_rn(__dadd_rn(__ddiv_rn(speed, q.ship_thrust), __ddiv_rn(q.ship_rspeed, rotation)), speed);
-                        if (distance < lim) ctl = fly_to(bear, my[4], q.avoid_threshold, true);
-                    }
+            const double x0 = __dsub_rn(my[0], (double)v.x), x1 = __dsub_rn(my[1], (double)v.y);
+            const double v0 = __dsub_rn(my[2], (double)v.dx), v1 = __dsub_rn(my[3], (double)v.dy);
+            const double speed = sqrt(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)));   // util.mag(dx)
+            const double den = __dadd_rn(speed, 1e-12);
+            const double n0 = __ddiv_rn(v0, den), n1 = __ddiv_rn(v1, den);                   // util.norm(dx)
+            const double b = __dmul_rn(2.0, __dadd_rn(__dmul_rn(n0, x0), __dmul_rn(n1, x1)));
+            const double mx = sqrt(__dadd_rn(__dmul_rn(x0, x0), __dmul_rn(x1, x1)));
+            const double cc = __dsub_rn(__dmul_rn(mx, mx), ra2);
+            const double det = __dsub_rn(__dmul_rn(b, b), __dmul_rn(4.0, cc));
+            if (0.0 < det) {
+                const double sd = sqrt(det);
+                if (0.0 <= __dadd_rn(-b, sd)) {       // real roots, at least one positive (script.py:57)
+                    cand |= 1u << j;
+                    cx0[j] = x0; cx1[j] = x1; cb[j] = b; csd[j] = sd; cspeed[j] = speed;
                 }
             }
         }
-        if (ctl < 0) {
-            if (q.solo || S < 2) {
-                ctl = 2;
-            } else {
-                const double* en = sx[(me + 1) % S];
-                const double e0 = __dsub_rn(en[0], my[0]), e1 = __dsub_rn(en[1], my[1]);
-                const double enemy_distance = sqrt(__dadd_rn(__dmul_rn(e0, e0), __dmul_rn(e1, e1)));
-                const double bullet_time = __ddiv_rn(enemy_distance, q.bullet_speed);
-                const double f0 = __dadd_rn(en[0], __dmul_rn(bullet_time, __dsub_rn(en[2], my[2])));
-                const double f1 = __dadd_rn(en[1], __dmul_rn(bullet_time, __dsub_rn(en[3], my[3])));
-                ctl = fly_to(atan2(__dsub_rn(f0, my[0]), __dsub_rn(f1, my[1])), my[4], __ddiv_rn(q.ship_radius, enemy_distance), false);
-            }
-        }
-        actions[(size_t)g * S + me] = (uint8_t)ctl;
     }
+    int ctl = -1;
+    while (cand && ctl < 0) {
+        const int j = __ffs(cand) - 1;
+        cand &= cand - 1u;
+        double x0 = cx0[0], x1 = cx1[0], b = cb[0], sd = csd[0], speed = cspeed[0];
+#pragma unroll
+        for (int k = 1; k < ASTRO_MAX_PLANETS; k++)
+            if (j == k) { x0 = cx0[k]; x1 = cx1[k]; b = cb[k]; sd = csd[k]; speed = cspeed[k]; }
+        const double distance = __dsub_rn(-b, sd);
+        const double bear = atan2(x0, x1);                                        // util.bearing(x)
+        const double rotation = fabs(norm_angle_f64(__dsub_rn(bear, b)));         // (`b` shadowed: script.py:54)
+        const double lim = __dmul_rn(__dadd_rn(__ddiv_rn(speed, q.ship_thrust), __ddiv_rn(q.ship_rspeed, rotation)), speed);
+        if (distance < lim) ctl = fly_to(bear, my[4], q.avoid_threshold, true);
+    }
+    if (ctl < 0) {
+        if (q.solo || S < 2) {
+            ctl = 2;
+        } else {
+            const B4 ev = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + ((me + 1) % S) * 32 + lane];
+            const double en[4] = {(double)ev.x, (double)ev.y, (double)ev.dx, (double)ev.dy};
+            const double e0 = __dsub_rn(en[0], my[0]), e1 = __dsub_rn(en[1], my[1]);
+            const double enemy_distance = sqrt(__dadd_rn(__dmul_rn(e0, e0), __dmul_rn(e1, e1)));
+            const double bullet_time = __ddiv_rn(enemy_distance, q.bullet_speed);
+            const double f0 = __dadd_rn(en[0], __dmul_rn(bullet_time, __dsub_rn(en[2], my[2])));
+            const double f1 = __dadd_rn(en[1], __dmul_rn(bullet_time, __dsub_rn(en[3], my[3])));
+            ctl = fly_to(atan2(__dsub_rn(f0, my[0]), __dsub_rn(f1, my[1])), my[4], __ddiv_rn(q.ship_radius, enemy_distance), false);
+        }
+    }
+    actions[idx] = (uint8_t)ctl;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1387,7 +1406,7 @@ int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_thr
     q.ship_radius = b->cfg.ship_radius;
     q.solo = b->cfg.solo;
     q.n_games = b->n_games;
-    const int grid = (b->n_games + 127) / 128;
+    const int grid = (b->n_games * b->S + 127) / 128;
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;
     if (b->precision == 32) {
