@@ -1047,10 +1047,12 @@ cudaError_t launch_tick(const TickParams& p, cudaStream_t st) {
 template <int S>
 cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
     const int grid = (p.n_games + kTickThreads - 1) / kTickThreads;
+    // experiment knob (tools/exp_tick.py): unused dynamic shared memory caps the resident CTAs per SM
+    static const size_t extra = getenv("ASTRO_EXTRA_SMEM") ? (size_t)atoi(getenv("ASTRO_EXTRA_SMEM")) : 0;
     if (p.flags & ASTRO_TICK_NO_STATS)
-        tick_f32_kernel<S, false><<<grid, kTickThreads, 0, st>>>(p);
+        tick_f32_kernel<S, false><<<grid, kTickThreads, extra, st>>>(p);
     else
-        tick_f32_kernel<S, true><<<grid, kTickThreads, 0, st>>>(p);
+        tick_f32_kernel<S, true><<<grid, kTickThreads, extra, st>>>(p);
     return cudaGetLastError();
 }
 
