@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('ASTRO_B200_LIB') or os.path.join(HERE, 'libastro_b200.so')   # env: A/B builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 TILE = 32
 MAX_PLANETS = 4
 MAX_BULLET_CAP = 1023
@@ -17,13 +17,13 @@ STAT_NAMES = ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'env_steps'
 
 EV_HIT0, EV_HIT1, EV_TIMEOUT, EV_FIRED, EV_OVERFLOW, EV_SKIPPED = 1, 2, 4, 8, 16, 32
 EV_DONE_MASK = 7
-TICK_AUTO_RESET, TICK_NO_STATS, TICK_GENERIC_KERNEL, TICK_PERSISTENT, TICK_PREFETCH_ROWS, TICK_QUEUE = 1, 2, 4, 8, 16, 32
+TICK_AUTO_RESET, TICK_NO_STATS, TICK_GENERIC_KERNEL = 1, 2, 4
 
 EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro_batch_destroy',
            'astro_batch_bind', 'astro_set_schedule', 'astro_set_stream', 'astro_set_reset_pool',
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
            'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
-           'astro_policy_controls', 'astro_rollout_device')
+           'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer')
 
 
 class AstroConfig(C.Structure):
@@ -89,6 +89,8 @@ def lib():
     L.astro_rollout_device.argtypes = [vp, i32, i32, i32, C.c_double, C.c_double, vp, vp, i32, vp]
     L.astro_create_games.argtypes = [vp, C.POINTER(AstroCreateConfig), vp, i32, vp, vp, vp, vp]
     L.astro_script_controls.argtypes = [vp, C.c_double, C.c_double, vp, vp]
+    L.astro_bullet_buffer.argtypes = [vp]
+    L.astro_set_bullet_buffer.argtypes = [vp, i32]
     L.astro_launch_count.argtypes = [vp]
     L.astro_launch_count.restype = i64
     if L.astro_abi_version() != ABI_VERSION:

@@ -47,7 +47,8 @@ class BatchedGames:
         self.ships = torch.zeros((T, S, 32, 4), dtype=self.rdtype, device=dev)
         self.ship_b = torch.zeros((T, S, 32), dtype=self.rdtype, device=dev)
         self.planets = torch.zeros((T, nat.MAX_PLANETS, 32, 4), dtype=self.rdtype, device=dev)
-        self.bullets = torch.zeros((self.n_pad, max(K, 1), 4), dtype=self.rdtype, device=dev)   # game-major
+        # tile lists, two buffers (include/astro_b200.h): the current one is astro_bullet_buffer()
+        self.bullets = torch.zeros((2, T, 32 * max(K, 1), 4), dtype=self.rdtype, device=dev)
         # every slot starts finished (empty); meta = nb | np<<10 | finished<<13 | tick<<14
         self.meta = torch.full((self.n_pad,), 1 << 13, dtype=torch.int32, device=dev)
         self.episode = torch.zeros((self.n_pad,), dtype=torch.int32, device=dev)
@@ -108,6 +109,41 @@ class BatchedGames:
         index = np.asarray(index, dtype=np.int64)
         return index // nat.TILE, index % nat.TILE
 
+    @property
+    def bullet_buffer(self):
+        """Which half of `self.bullets` holds the tile lists now (flips every tick)."""
+        return int(nat.lib().astro_bullet_buffer(self._h))
+
+    def _tile_counts(self, tiles):
+        """Bullet counts [m, 32] of the listed tiles (finished games own none) and each game's first list item."""
+        meta = self.meta.view(self.n_tiles, nat.TILE)[tiles].to(_torch().int64) & 0xFFFFFFFF
+        nb = (meta & 1023) * (1 - ((meta >> 13) & 1))
+        return nb, nb.cumsum(1) - nb
+
+    def _unpack_tiles(self, tiles):
+        """The bullet lists of the listed tiles as padded game-major rows [m, 32, K, 4] (dead slots 0)
+        and the counts [m, 32]."""
+        torch = _torch()
+        K, m = max(self.K, 1), int(tiles.numel())
+        nb, first = self._tile_counts(tiles)
+        k = torch.arange(K, device=self.device)
+        idx = (first[:, :, None] + k).clamp_(max=32 * K - 1).reshape(m, 32 * K)
+        lists = self.bullets[self.bullet_buffer][tiles]                              # [m, 32K, 4]
+        rows = torch.gather(lists, 1, idx[:, :, None].expand(-1, -1, 4)).reshape(m, 32, K, 4)
+        return torch.where((k < nb[:, :, None])[..., None], rows, torch.zeros((), dtype=rows.dtype, device=self.device)), nb
+
+    def _pack_tiles(self, tiles, rows, nb):
+        """Inverse of _unpack_tiles: writes the dense lists of the listed tiles (current buffer)."""
+        torch = _torch()
+        K, m = max(self.K, 1), int(tiles.numel())
+        first = nb.cumsum(1) - nb
+        k = torch.arange(K, device=self.device)
+        live = k < nb[:, :, None]                                                    # [m, 32, K]
+        dst = (torch.arange(m, device=self.device)[:, None, None] * (32 * K) + first[:, :, None] + k)[live]
+        lists = torch.zeros((m * 32 * K, 4), dtype=self.rdtype, device=self.device)
+        lists[dst] = rows[live]
+        self.bullets[self.bullet_buffer][tiles] = lists.view(m, 32 * K, 4)
+
     def set_arrays(self, ships, planets, n_planets, bullets=None, n_bullets=None, ticks=None, index=None,
                    episode=None):
         """Load games from game-major host arrays: ships [m,S,5] (x,y,dx,dy,b), planets [m,4,4],
@@ -130,14 +166,21 @@ class BatchedGames:
         self.ships[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(ships[:, :, :4])).to(dev)
         self.ship_b[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(ships[:, :, 4])).to(dev)
         self.planets[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(planets)).to(dev)
+        # bullets: the lists of the touched tiles are unpacked, the listed games replaced, and packed again
+        ut, inv = np.unique(tiles, return_inverse=True)
+        ut_t, inv_t = torch.from_numpy(ut).to(dev), torch.from_numpy(inv.astype(np.int64)).to(dev)
+        rows, nb_t = self._unpack_tiles(ut_t)
+        new_rows = torch.zeros((m, max(self.K, 1), 4), dtype=self.rdtype, device=dev)
         if bullets is not None and self.K > 0:
             bullets = np.asarray(bullets, dtype=self.np_rdtype)
             kb = bullets.shape[1]
             if kb:
-                self.bullets[torch.from_numpy(index.astype(np.int64)).to(dev), :kb] = \
-                    torch.from_numpy(np.ascontiguousarray(bullets)).to(dev)
+                new_rows[:, :kb] = torch.from_numpy(np.ascontiguousarray(bullets)).to(dev)
+        rows[inv_t, ll] = new_rows
+        nb_t[inv_t, ll] = torch.from_numpy(n_bullets).to(dev)
         meta = (n_bullets | (n_planets << 10) | (ticks << 14)).astype(np.uint32).view(np.int32)
         self.meta[torch.from_numpy(index.astype(np.int64)).to(dev)] = torch.from_numpy(meta).to(dev)
+        self._pack_tiles(ut_t, rows, nb_t)
         if episode is not None:
             ep = np.asarray(episode, dtype=np.uint32).view(np.int32)
             self.episode[torch.from_numpy(index.astype(np.int64)).to(dev)] = torch.from_numpy(ep).to(dev)
@@ -185,7 +228,8 @@ class BatchedGames:
         sh = self.ships.permute(0, 2, 1, 3).reshape(self.n_pad, self.S, 4)[:n].double().cpu().numpy()
         sb = self.ship_b.permute(0, 2, 1).reshape(self.n_pad, self.S)[:n].double().cpu().numpy()
         pl = self.planets.permute(0, 2, 1, 3).reshape(self.n_pad, nat.MAX_PLANETS, 4)[:n].double().cpu().numpy()
-        bl = self.bullets[:n, :self.K].double().cpu().numpy()
+        rows, _ = self._unpack_tiles(_torch().arange(self.n_tiles, device=self.device))
+        bl = rows.reshape(self.n_pad, max(self.K, 1), 4)[:n, :self.K].double().cpu().numpy()
         return dict(ships=np.concatenate([sh, sb[:, :, None]], axis=2), planets=pl, bullets=bl,
                     n_bullets=(meta & 1023).astype(np.int32), n_planets=((meta >> 10) & 7).astype(np.int32),
                     finished=((meta >> 13) & 1).astype(bool), tick=(meta >> 14).astype(np.int64),
@@ -201,7 +245,9 @@ class BatchedGames:
         sh = self.ships[tile, :, lane].double().cpu().numpy()
         sb = self.ship_b[tile, :, lane].double().cpu().numpy()
         pl = self.planets[tile, :npl, lane].double().cpu().numpy()
-        bl = self.bullets[int(i), :nb].double().cpu().numpy().reshape(nb, 4)
+        row = self.meta[tile * nat.TILE:tile * nat.TILE + lane].cpu().numpy().view(np.uint32)
+        first = int(((row & 1023) * (1 - ((row >> 13) & 1))).sum())            # bullets of the tile's lower games
+        bl = self.bullets[self.bullet_buffer, tile, first:first + nb].double().cpu().numpy().reshape(nb, 4)
         return core.State(
             ships=core.Bodies(x=sh[:, 0:2].copy(), dx=sh[:, 2:4].copy(), b=sb.copy()),
             planets=core.Bodies(x=pl[:, 0:2].copy(), dx=pl[:, 2:4].copy(), b=None),
@@ -220,7 +266,10 @@ class BatchedGames:
         sh = self.ships[tt, :, ll].double().cpu().numpy()          # [m, S, 4]
         sb = self.ship_b[tt, :, ll].double().cpu().numpy()         # [m, S]
         pl = self.planets[tt, :, ll].double().cpu().numpy()        # [m, 4, 4]
-        bl = self.bullets[ii, :self.K].double().cpu().numpy()      # [m, K, 4]
+        _, first = self._tile_counts(tt)
+        k = torch.arange(max(self.K, 1), device=self.device)
+        item = (first[torch.arange(len(idx), device=self.device), ll][:, None] + k).clamp_(max=32 * max(self.K, 1) - 1)
+        bl = self.bullets[self.bullet_buffer][tt[:, None], item].double().cpu().numpy()      # [m, K, 4]
         out = []
         for j in range(len(idx)):
             m = int(meta[j])

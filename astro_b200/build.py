@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'astro_b200.cu')
-DEPS = [SRC, os.path.join(HERE, 'csrc', 'astro_device.cuh'), os.path.join(HERE, 'csrc', 'tick_f32.cuh'), os.path.join(HERE, 'csrc', 'tick_f32_pipe.cuh'),
+DEPS = [SRC, os.path.join(HERE, 'csrc', 'astro_device.cuh'), os.path.join(HERE, 'csrc', 'tick_f32.cuh'),
         os.path.join(os.path.dirname(HERE), 'include', 'astro_b200.h')]
 LIB = os.path.join(HERE, 'libastro_b200.so')
 

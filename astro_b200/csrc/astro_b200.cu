@@ -35,7 +35,8 @@ struct TickParams {
     void* ships;
     void* ship_b;
     void* planets;
-    void* bullets;
+    void* bullets_in;   // the buffer holding the tiles' bullet lists, read by this tick
+    void* bullets_out;  // the other buffer: receives the new lists
     uint32_t* meta;
     uint32_t* episode;
     const uint8_t* actions;
@@ -48,7 +49,6 @@ struct TickParams {
     const int32_t* pool_np;
     unsigned long long* stats;
     unsigned* stat_slots;  // u32 [n_tiles][16]: per-warp partial counters (tick_f32_kernel)
-    unsigned* queue;       // u32 [2]: next tile / finished warps (tick_f32_queue_kernel)
     int32_t n_games, K, timeout_tick, n_sched_ticks, pool_size, flags;
     uint32_t seed, step, first_game, pad;
     Consts c;
@@ -135,14 +135,32 @@ __global__ void fold_stats_kernel(unsigned* slots, int n_tiles, unsigned long lo
     if (threadIdx.x < ASTRO_N_STATS && acc[threadIdx.x]) atomicAdd(&stats[threadIdx.x], acc[threadIdx.x]);
 }
 
+// First list item of game `gl` (0..31) of a tile: the bullet counts of the tile's lower games,
+// summed by the warp (finished games own no items).  meta_tile = the tile's 32 meta words.
+__device__ __forceinline__ unsigned tile_list_offset(const uint32_t* __restrict__ meta_tile, int gl, int lane) {
+    const uint32_t m = meta_tile[lane];
+    const unsigned nb = (lane < gl && !ASTRO_META_FINISHED(m)) ? ASTRO_META_NB(m) : 0u;
+    return __reduce_add_sync(0xffffffffu, nb);
+}
+__device__ __forceinline__ unsigned warp_exclusive_sum(unsigned v, int lane) {
+    unsigned incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned u = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    return incl - v;
+}
+
 // ------------------------------------------------------------------------------------------
 // tick_kernel<R, S, STATS>: one thread = one game, one launch = one core.step for all games.
 //
 // Phase order follows core.py:215-303: accelerations (old state) -> collisions (old state) ->
 // collision terminal -> timeout terminal -> bullet despawn -> spawn -> integrate/cull.
-// Bullets are compacted in place, front to back, by their owning thread: survivors keep the
-// reference's order (old survivors, then ship 0's and ship 1's newborn).  When a game ends, its
-// bullet slots are dead (nb = 0); ships/planets keep the pre-step state unless AUTO_RESET
+// Bullets: a warp is a tile; each thread walks its game's run of the tile's list, compacting the
+// survivors front to back inside that run (reference order: old survivors, then ship 0's and ship
+// 1's newborn), then the runs move — dense again — to the tile's list in the other buffer.  When a
+// game ends it owns no bullets (nb = 0); ships/planets keep the pre-step state unless AUTO_RESET
 // re-initialises the slot from the pool.
 // ------------------------------------------------------------------------------------------
 template <typename R, int S, bool STATS>
@@ -163,12 +181,11 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
     bool active = false;
     int spawned = 0;
 
-    if (in_range) {
+    if (in_range) {   // (warp-uniform)
         const size_t tile = (size_t)(g >> 5);
         B4* ships = reinterpret_cast<B4*>(p.ships) + tile * (S * 32) + lane;
         R* ship_b = reinterpret_cast<R*>(p.ship_b) + tile * (S * 32) + lane;
         B4* planets = reinterpret_cast<B4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
-        B4* bullets = reinterpret_cast<B4*>(p.bullets) + (size_t)g * p.K;
 
         const uint32_t meta = p.meta[g];
         // ships are loaded before meta is inspected: independent loads, one DRAM round trip
@@ -179,14 +196,21 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
             sh[s] = ships[s * 32];
             sb[s] = ship_b[s * 32];
         }
-        nb = (int)ASTRO_META_NB(meta);
-        np = (int)ASTRO_META_NP(meta);
-        const uint32_t tick = ASTRO_META_TICK(meta);
         active = !ASTRO_META_FINISHED(meta);
+        nb = active ? (int)ASTRO_META_NB(meta) : 0;
+        np = active ? (int)ASTRO_META_NP(meta) : 0;
+        const uint32_t tick = ASTRO_META_TICK(meta);
+        // this game's run of the tile's list (read buffer); survivors are compacted inside it
+        B4* const bullets = reinterpret_cast<B4*>(p.bullets_in) + tile * (size_t)(32 * p.K) + warp_exclusive_sum((unsigned)nb, lane);
+        int m = 0, n_born = 0;
+        B4 born[2];
+        born[0] = born[1] = B4();
+        float rw[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) rw[s] = 0.0f;
 
         if (!active) {
             ev = ASTRO_EV_SKIPPED;
-            np = 0; nb = 0;
         } else {
             B4 pl[ASTRO_MAX_PLANETS];
 #pragma unroll
@@ -244,8 +268,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                 hit[S - 1] |= h;
             }
 
-            // ---- bullets: hit test on old positions, integrate, cull, compact in place
-            int m = 0;
+            // ---- bullets: hit test on old positions, integrate, cull, compact inside the run
             for (int j0 = 0; j0 < nb; j0 += 4) {
                 B4 cur[4];
 #pragma unroll
@@ -279,19 +302,18 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
             bool any_hit = hit[0];
             if (S == 2) any_hit |= hit[S - 1];
             const bool timeout = tick >= (uint32_t)p.timeout_tick;
-            float rw[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) rw[s] = 0.0f;
 
             if (any_hit) {  // core.py:253-255
                 ev = (hit[0] ? ASTRO_EV_HIT0 : 0);
                 if (S == 2) ev |= (hit[S - 1] ? ASTRO_EV_HIT1 : 0);
 #pragma unroll
                 for (int s = 0; s < S; s++) rw[s] = hit[s] ? -1.0f : 1.0f;
+                m = 0;
             } else if (timeout) {  // core.py:257-260
                 ev = ASTRO_EV_TIMEOUT;
 #pragma unroll
                 for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
+                m = 0;
             } else {
                 // ---- spawn from the OLD ship state (core.py:267-280); float32 products
                 const bool fire = tick < (uint32_t)p.n_sched_ticks && ((p.fire_bits[tick >> 5] >> (tick & 31)) & 1u);
@@ -306,11 +328,11 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                         nbl.dy = __dadd_rn((double)sh[s].dy, (double)__fmul_rn(c.spd_f, dir1[s]));
                         bool keep = advance_bullet(nbl, c);
                         if (keep) {
-                            if (m < p.K) {
+                            if (m + n_born < p.K) {
                                 B4 o;
                                 o.x = (R)nbl.x; o.y = (R)nbl.y; o.dx = (R)nbl.dx; o.dy = (R)nbl.dy;
-                                bullets[m] = o;
-                                m++;
+                                if (n_born == 0) born[0] = o; else born[1] = o;
+                                n_born++;
                             } else {
                                 ev |= ASTRO_EV_OVERFLOW;
                             }
@@ -350,8 +372,8 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                     R db = mul_rn(Pick<R>::db_unit(c), (R)((ctl[s] >> 1) - 1));
                     ship_b[s * 32] = add_rn(sb[s], db);
                 }
-                p.meta[g] = ASTRO_META_PACK(m, np, 0, tick + 1);
-                m_out = m;
+                m_out = m + n_born;
+                p.meta[g] = ASTRO_META_PACK(m_out, np, 0, tick + 1);
             }
 
             if (ev & ASTRO_EV_DONE_MASK) {
@@ -361,17 +383,17 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                     p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
                 }
             }
-            if (p.reward) {
-                if (S == 2) {
-                    reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
-                } else {
-                    p.reward[g] = rw[0];
-                }
-            }
         }
-        if (!active && p.reward) {
-            if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(0.f, 0.f);
-            else p.reward[g] = 0.f;
+        // ---- the new list of the tile: every game's survivors and newborn, dense, other buffer
+        __syncwarp();
+        B4* const out = reinterpret_cast<B4*>(p.bullets_out) + tile * (size_t)(32 * p.K) + warp_exclusive_sum((unsigned)m_out, lane);
+        for (int k = 0; k < m; k++) out[k] = bullets[k];
+        if (n_born > 0) out[m] = born[0];
+        if (n_born > 1) out[m + 1] = born[1];
+
+        if (p.reward) {
+            if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
+            else p.reward[g] = rw[0];
         }
         if (p.events) p.events[g] = (uint8_t)ev;
         if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
@@ -387,7 +409,6 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
 
 
 #include "tick_f32.cuh"
-#include "tick_f32_pipe.cuh"
 
 // ------------------------------------------------------------------------------------------
 // reset_kernel: stand-alone form of AUTO_RESET — finished games are re-created from the pool.
@@ -456,7 +477,8 @@ observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_
     }
     __syncwarp();
     const B4* planets = reinterpret_cast<const B4*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32) + gl;
-    const B4* bullets = reinterpret_cast<const B4*>(bullets_) + (size_t)g * K;  // game-major row
+    // the game's run of its tile's bullet list
+    const B4* bullets = reinterpret_cast<const B4*>(bullets_) + tile * (size_t)(32 * K) + tile_list_offset(meta_ + tile * 32, gl, lane);
     for (int r = lane; r < n_rows; r += 32) {
         float* row = rows + r * D;
         if (r < np + nb) {
@@ -854,7 +876,7 @@ policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
             baseB = __fmaf_rn(w0[1 + 5 * ((s + 1) % S) + c], f, baseB);
         }
     const B4* pl = reinterpret_cast<const B4*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32) + gl;
-    const B4* bl = reinterpret_cast<const B4*>(bullets_) + (size_t)g * K;
+    const B4* bl = reinterpret_cast<const B4*>(bullets_) + tile * (size_t)(32 * K) + tile_list_offset(meta_ + tile * 32, gl, lane);
     // lane r fetches row r's object (coalesced for the bullets); rows beyond 32 are fetched in a second batch
     float bestA = -3.0e38f, bestB = -3.0e38f;
     for (int r0 = 0; r0 < rows; r0 += 32) {
@@ -956,7 +978,7 @@ struct AstroBatch {
     int32_t n_sched_ticks, timeout_tick;
     unsigned long long* d_stats;
     unsigned* d_stat_slots;  // per-warp partial counters, folded by astro_stats
-    unsigned* d_queue;       // tile queue of the persistent kernel
+    int32_t cur;             // which of the two bullet buffers holds the lists (flips every tick)
     int64_t ticks_since_fold;
     uint8_t* d_actions;  // staging for astro_tick_host
     uint8_t* d_events;
@@ -1008,12 +1030,19 @@ int check(const AstroBatch* b, bool need_bound) {
     return ASTRO_OK;
 }
 
+const void* current_bullets(const AstroBatch* b) {
+    const size_t buf_bytes = (size_t)b->n_games * b->K * 4 * (b->precision == 32 ? sizeof(float) : sizeof(double));
+    return (const char*)b->bufs.bullets + (size_t)b->cur * buf_bytes;
+}
+
 void fill_params(const AstroBatch* b, TickParams& p) {
     memset(&p, 0, sizeof(p));
     p.ships = b->bufs.ships;
     p.ship_b = b->bufs.ship_b;
     p.planets = b->bufs.planets;
-    p.bullets = b->bufs.bullets;
+    const size_t buf_bytes = (size_t)b->n_games * b->K * 4 * (b->precision == 32 ? sizeof(float) : sizeof(double));
+    p.bullets_in = (char*)b->bufs.bullets + (size_t)b->cur * buf_bytes;
+    p.bullets_out = (char*)b->bufs.bullets + (size_t)(b->cur ^ 1) * buf_bytes;
     p.meta = b->bufs.meta;
     p.episode = b->bufs.episode;
     p.fire_bits = b->d_fire_bits;
@@ -1023,7 +1052,6 @@ void fill_params(const AstroBatch* b, TickParams& p) {
     p.pool_size = b->pool.size;
     p.stats = b->d_stats;
     p.stat_slots = b->d_stat_slots;
-    p.queue = b->d_queue;
     p.n_games = b->n_games;
     p.K = b->K;
     p.timeout_tick = b->timeout_tick;
@@ -1056,59 +1084,6 @@ cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// Queue kernel: one resident wave of one-warp CTAs drawing tiles from a device counter.
-template <int S>
-cudaError_t launch_tick_queue(const TickParams& p, cudaStream_t st) {
-    static int resident = 0;
-    if (!resident) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick_f32_queue_kernel<S, true>, 32, 0);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        resident = sms * per_sm;
-    }
-    const int n_tiles = p.n_games / ASTRO_TILE;
-    const int grid = n_tiles < resident ? n_tiles : resident;
-    if (p.flags & ASTRO_TICK_NO_STATS)
-        tick_f32_queue_kernel<S, false><<<grid, 32, 0, st>>>(p);
-    else
-        tick_f32_queue_kernel<S, true><<<grid, 32, 0, st>>>(p);
-    return cudaGetLastError();
-}
-
-// Persistent pipelined kernel: one resident wave of CTAs, each warp walks tiles with stride W.
-template <int S, bool STATS, bool ROWS>
-cudaError_t launch_tick_pipe_one(const TickParams& p, cudaStream_t st) {
-    static int resident = 0;  // CTAs that fit on the device (per instantiation; one device type per process)
-    const size_t smem = sizeof(PipeScratch<ROWS>) * kPipeWarps;
-    auto kernel = tick_f32_pipe_kernel<S, STATS, ROWS>;
-    if (!resident) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPipeThreads, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        resident = sms * per_sm;
-    }
-    const int n_tiles = p.n_games / ASTRO_TILE;
-    int grid = (n_tiles + kPipeWarps - 1) / kPipeWarps;
-    if (grid > resident) grid = resident;
-    kernel<<<grid, kPipeThreads, smem, st>>>(p);
-    return cudaGetLastError();
-}
-template <int S>
-cudaError_t launch_tick_pipe(const TickParams& p, cudaStream_t st) {
-    const bool rows = (p.flags & ASTRO_TICK_PREFETCH_ROWS) != 0;
-    if (p.flags & ASTRO_TICK_NO_STATS)
-        return rows ? launch_tick_pipe_one<S, false, true>(p, st) : launch_tick_pipe_one<S, false, false>(p, st);
-    return rows ? launch_tick_pipe_one<S, true, true>(p, st) : launch_tick_pipe_one<S, true, false>(p, st);
-}
-
 cudaError_t fold_stats(AstroBatch* b, cudaStream_t st) {
     fold_stats_kernel<<<64, 256, 0, st>>>(b->d_stat_slots, b->n_games / ASTRO_TILE, b->d_stats);
     b->ticks_since_fold = 0;
@@ -1131,16 +1106,13 @@ int do_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done,
     cudaError_t e;
     if (b->precision == 32 && (flags & ASTRO_TICK_GENERIC_KERNEL))
         e = b->S == 2 ? launch_tick<float, 2>(p, st) : launch_tick<float, 1>(p, st);
-    else if (b->precision == 32 && (flags & ASTRO_TICK_QUEUE))
-        e = b->S == 2 ? launch_tick_queue<2>(p, st) : launch_tick_queue<1>(p, st);
-    else if (b->precision == 32 && (flags & (ASTRO_TICK_PERSISTENT | ASTRO_TICK_PREFETCH_ROWS)))
-        e = b->S == 2 ? launch_tick_pipe<2>(p, st) : launch_tick_pipe<1>(p, st);
     else if (b->precision == 32)
         e = b->S == 2 ? launch_tick_f32<2>(p, st) : launch_tick_f32<1>(p, st);
     else
         e = b->S == 2 ? launch_tick<double, 2>(p, st) : launch_tick<double, 1>(p, st);
     if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "tick_kernel launch: %s", cudaGetErrorString(e));
     b->step += 1;
+    b->cur ^= 1;   // the lists now live in the other buffer
     b->launches += 1;
     // 32-bit slot rows: fold long before a row can wrap (<= 32 * 1023 per tick)
     if (!(flags & ASTRO_TICK_NO_STATS) && ++b->ticks_since_fold >= 65536) {
@@ -1188,8 +1160,6 @@ int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_c
     const size_t slot_bytes = (size_t)(n_games / ASTRO_TILE) * 16 * sizeof(unsigned);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_stat_slots, slot_bytes);
     if (e == cudaSuccess) e = cudaMemset(b->d_stat_slots, 0, slot_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_queue, 2 * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemset(b->d_queue, 0, 2 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_actions, (size_t)n_games * b->S);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_events, (size_t)n_games);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_done, (size_t)n_games);
@@ -1207,7 +1177,6 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_stats);
     cudaFree(b->d_stat_slots);
-    cudaFree(b->d_queue);
     cudaFree(b->d_actions);
     cudaFree(b->d_events);
     cudaFree(b->d_done);
@@ -1237,6 +1206,7 @@ int astro_batch_bind(AstroBatch* b, const AstroBuffers* bufs) {
     if (((uintptr_t)bufs->ships | (uintptr_t)bufs->planets | (uintptr_t)bufs->bullets) & (al - 1))
         return fail(ASTRO_E_INVALID, "ships/planets/bullets must be %d-byte aligned", (int)al);
     b->bufs = *bufs;
+    b->cur = 0;
     b->bound = true;
     return ASTRO_OK;
 }
@@ -1369,10 +1339,11 @@ static int observe_impl(AstroBatch* b, float* obs, int32_t n_rows, bool both, vo
     const int grid = (b->n_games + kObserveWarps - 1) / kObserveWarps;
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;
+    const void* cur_bullets = current_bullets(b);
 #define LAUNCH_OBS(R, S_, BOTH_)                                                                                       \
     do {                                                                                                               \
         CUDA_TRY(cudaFuncSetAttribute(observe_kernel<R, S_, BOTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        observe_kernel<R, S_, BOTH_><<<grid, kObserveWarps * 32, smem, st>>>(u.ships, u.ship_b, u.planets, u.bullets, u.meta, \
+        observe_kernel<R, S_, BOTH_><<<grid, kObserveWarps * 32, smem, st>>>(u.ships, u.ship_b, u.planets, cur_bullets, u.meta, \
                                                                              obs, b->n_games, b->K, n_rows);             \
     } while (0)
     if (b->precision == 32) {
@@ -1494,7 +1465,7 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;
 #define LAUNCH_POL(R, S_) \
-    policy_kernel<R, S_><<<grid, kPolWarps * 32, 0, st>>>(u.ships, u.ship_b, u.planets, u.bullets, u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask)
+    policy_kernel<R, S_><<<grid, kPolWarps * 32, 0, st>>>(u.ships, u.ship_b, u.planets, current_bullets(b), u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask)
     if (b->precision == 32) {
         if (b->S == 2) LAUNCH_POL(float, 2); else LAUNCH_POL(float, 1);
     } else {
@@ -1558,6 +1529,15 @@ int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* strea
 }
 
 int64_t astro_launch_count(const AstroBatch* b) { return b ? b->launches : 0; }
+
+int astro_bullet_buffer(const AstroBatch* b) { return b ? b->cur : ASTRO_E_INVALID; }
+
+int astro_set_bullet_buffer(AstroBatch* b, int32_t which) {
+    if (int r = check(b, false)) return r;
+    if (which != 0 && which != 1) return fail(ASTRO_E_INVALID, "bullet buffer must be 0 or 1");
+    b->cur = which;
+    return ASTRO_OK;
+}
 
 #ifdef ASTRO_TIMELINE
 // experiment builds only (tools/exp_timeline.py): device buffer of 8 clock stamps per tile

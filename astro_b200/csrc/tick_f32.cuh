@@ -11,10 +11,11 @@
 //     far-away sentinel) reduced with min, the advance, and ONE band test deciding whether the
 //     fp32 comparisons provably equal the reference's float64 results; only a bullet inside a
 //     band (|d2 - R2| <= 1e-6 R2, or |x'| within 4e-6 of the arena bound — ~1e-5 of bullets),
-//     and every ship hit, takes the float64 path.  Survivors are compacted in place with a
-//     warp ballot: rank inside the game's segment = popc(ballot & segment mask), so the
-//     reference order (stable) is kept.  Bullets are game-major in HBM (a game's pool is one
-//     contiguous row), so a window of 32 consecutive list items reads a few contiguous runs.
+//     and every ship hit, takes the float64 path.  Survivors are compacted with a warp ballot:
+//     rank inside the game's segment = popc(ballot & segment mask), so the reference order
+//     (stable) is kept.  In HBM the flat list IS the storage order (one dense run per tile, see
+//     the header): a window of 32 list items is one contiguous 512-byte read, and the new list —
+//     survivors and newborn, dense again — is written to the tile's run in the other buffer.
 //  B. SHIPS AND PLANETS, thread-per-game from the staged copies: direction, gravity, collisions,
 //     terminal logic, spawn, integration, reset — all coalesced 128-bit accesses.
 #pragma once
@@ -33,16 +34,18 @@ constexpr int kTickWarps = kTickThreads / 32;
 constexpr int kStageWindows = ASTRO_STAGE_WINDOWS;   // bullets staged per round: 8 windows x 32 = 256 (4 KB per warp)
 
 struct TileScratch {               // per warp
-    float4 bul[kStageWindows * 32];  // the tile's bullets, staged by cp.async (flat list order)
+    float4 bul[kStageWindows * 32];  // the tile's bullet list, staged by cp.async; survivors are compacted here
     float4 sxy[32];                // OLD ship0.xy, ship1.xy          } what the bullet loop reads,
     float4 pxy[2][32];             // OLD planet0.xy planet1.xy / 2,3 } addressed by game
     float4 svel[32];               // OLD ship velocities   } for the newborn bullets
     float4 dir[32];                // sin/cos of both bearings }
-    uint32_t cinfo[32];            // (persistent A/B kernels) k-th non-empty game: game | first list index << 5
-    uint32_t outn[32];             // survivors written so far
+    uint32_t cinfo[32];            // k-th non-empty game: game | first list item << 5 | bullet count << 20
+    uint32_t outn[32];             // survivors of the game
     uint32_t hits[32];             // bits 0-1: ship hits found by the bullet loop; bits 8+: np
-    uint16_t ref[kStageWindows * 32];  // staged item -> game | slot << 5 ; 0xFFFF = none
+    uint32_t ginfo[32];            // first item of the game in the NEW list | survivors to copy << 16
+    uint16_t ref[kStageWindows * 32];  // staged item -> game | slot << 5 | last-of-game << 15 ; kNoItem = none
 };
+constexpr unsigned kNoItem = 1023u << 5;   // slot 1023 never exists (nb <= 1023): never a survivor to copy
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -353,10 +356,13 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     float4* ships = reinterpret_cast<float4*>(p.ships) + tile * (S * 32) + lane;
     float* ship_b = reinterpret_cast<float*>(p.ship_b) + tile * (S * 32) + lane;
     float4* planets = reinterpret_cast<float4*>(p.planets) + tile * (ASTRO_MAX_PLANETS * 32) + lane;
-    // 32-bit bullet indexing (astro_batch_create checks n_games * K < 2^31): one IMAD.WIDE per address
-    float4* const bullets = reinterpret_cast<float4*>(p.bullets);
+    // The tile's bullet list: a dense run of capacity 32 K in the buffer being read, rewritten dense
+    // into the same run of the other buffer.  32-bit indexing (astro_batch_create checks
+    // n_games * K < 2^31): one IMAD.WIDE per address.
     const unsigned K = (unsigned)p.K;
     const unsigned tile_off = (unsigned)(g >> 5) * 32u * K;
+    float4* const list_in = reinterpret_cast<float4*>(p.bullets_in) + tile_off;
+    float4* const list_out = reinterpret_cast<float4*>(p.bullets_out) + tile_off;
 
     // ================= 1. this lane's game (rows already loaded: TileIn) ========================
     TL(0);
@@ -411,13 +417,12 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     if (nonempty) t.cinfo[__popc(ne & lt_mask)] = lane | (my_excl << 5) | ((unsigned)nb << 20);
     __syncwarp();
     unsigned c0 = 0;
-    // One window = 32 consecutive list items; a round = up to kStageWindows windows, all requested
-    // at once (16-byte cp.async each), so the whole tile's bullet traffic is in flight together.
-    // Item -> (game, slot): `starts` has bit r set when a non-empty game's first bullet is item
-    // base + r; c0 counts the non-empty games that start before the window.  Lanes past the end of
-    // the list stage a bullet that is certainly culled (no `valid` flag in the loop below).
-    // (A/B, 1M games: each lane requesting its own game's row instead — no cross-lane mapping, one
-    // request per bullet — 94.6 us against 91.0 us for these coalesced windows.)
+    // One window = 32 consecutive list items = 512 contiguous bytes; a round = up to kStageWindows
+    // windows, all requested at once (16-byte cp.async each), so the whole tile's bullet traffic is
+    // in flight together.  Item -> (game, slot), for the frame lookup and the compaction: `starts` has
+    // bit r set when a non-empty game's first bullet is item base + r; c0 counts the non-empty games
+    // that start before the window.  Lanes past the end of the list stage a bullet that is certainly
+    // culled (no `valid` flag in the loop below).
     const unsigned start_key = nonempty ? my_excl : 0x80000000u;  // empty games never "start"
     const unsigned le_mask = full >> (31u - lane);
     const unsigned bul_s = (unsigned)__cvta_generic_to_shared(&t.bul[lane]);
@@ -434,10 +439,9 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             const unsigned ci = t.cinfo[(idx - 1u) & 31u];  // (stale only for invalid items)
             const unsigned item = base + lane;
             const unsigned game = ci & 31u, slot = item - ((ci >> 5) & 0x7fffu);
-            unsigned ref = 0u;
+            unsigned ref = kNoItem;
             if (item < total) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bul_s + w * 512u),
-                             "l"(bullets + (tile_off + game * K + slot))
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bul_s + w * 512u), "l"(list_in + item)
                              : "memory");
                 ref = game | (slot << 5) | ((slot + 1u == (ci >> 20)) ? 0x8000u : 0u);  // bit 15: last of its game
             } else {
@@ -519,12 +523,16 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     }
 
     // ================= 4. the bullet loop, from shared memory =======================================
-    // Survivors are compacted in place inside each game's row, in list order.  Only the game that
-    // straddles a window boundary carries a count from one window to the next: `carry` (warp-uniform).
+    // Survivors are compacted inside each game's segment of the staged list, in list order.  Only the
+    // game that straddles a window boundary carries a count from one window to the next: `carry`
+    // (warp-uniform).  A tile whose list does not fit the staging buffer (`multi`: more than
+    // kStageWindows * 32 bullets, rare) compacts into the list it is reading instead — writes only
+    // land on items already consumed — and copies from there.
     unsigned carry = 0;
+    const bool multi = total > (unsigned)kStageWindows * 32u;
     TL(4);  // physics done, new ship / planet state stored
     for (unsigned round_base = 0; round_base < total; round_base += (unsigned)kStageWindows * 32u) {
-        if (round_base) {  // (tiles with more than kStageWindows * 32 bullets: rare)
+        if (round_base) {
             __syncwarp();
             stage_round(round_base);
         }
@@ -550,17 +558,21 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             x.pB = t.pxy[1][gi];
             return x;
         };
-        auto compact = [&](Win& x) {
+        auto compact = [&](Win& x, unsigned w) {
             const unsigned gi = x.ref & 31u, slot = (x.ref >> 5) & 1023u;
             unsigned sh_hits = 0;
             const bool keep = bullet_step_t<S>(x.bv, x.sT, x.pA, x.pB, t.hits, gi, c, sh_hits);
             if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
             // stable compaction inside each game's segment of the window; only the game that
             // straddles a window boundary carries a count over (`carry`, warp-uniform)
-            const unsigned kb = __ballot_sync(full, keep);
+            const unsigned kb = __ballot_sync(full, keep);   // (every lane has loaded its window item by now)
             const unsigned seg_lo = lane - min(slot, lane);  // first lane of this game's segment
             const unsigned pos = (slot > lane ? carry : 0u) + __popc(kb & lt_mask & (full << seg_lo));
-            if (keep) ST_STREAM(&bullets[tile_off + gi * K + pos], x.bv);
+            if (keep) {
+                const unsigned dst = w * 32u + lane - slot + pos;   // the game's first item + rank, <= this item
+                if (!multi) t.bul[dst] = x.bv;
+                else list_in[round_base + dst] = x.bv;
+            }
             const unsigned tot = pos + (keep ? 1u : 0u);
             if (x.ref & 0x8000u) t.outn[gi] = tot;
             carry = __shfl_sync(full, tot, 31);
@@ -568,7 +580,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
 #pragma unroll 1
         for (unsigned w = 0; w < n_win; w++) {
             Win x = load_win(w);
-            compact(x);
+            compact(x, w);
         }
     }
     __syncwarp();
@@ -577,6 +589,9 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     // ================= 5. terminal logic, spawn, bookkeeping ==========================================
     uint32_t ev = 0;
     int m_out = 0, spawned = 0;
+    unsigned surv = 0, n_born = 0;      // what this game contributes to the new list: survivors, then newborn
+    float4 born[2];
+    born[0] = born[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     float rw[2] = {0.0f, 0.0f};
     if (!active) {
         ev = ASTRO_EV_SKIPPED;
@@ -593,11 +608,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
 #pragma unroll
             for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
         } else {
+            surv = (unsigned)m;
             const uint32_t fire_word = p.fire_bits[min(tick, (uint32_t)p.n_sched_ticks - 1u) >> 5];
             const bool fire = tick < (uint32_t)p.n_sched_ticks && ((fire_word >> (tick & 31)) & 1u);
             if (fire) {  // core.py:267-280, from the OLD ship state
                 ev |= ASTRO_EV_FIRED;
-                float4* row = bullets + (tile_off + lane * K);
                 const float4 dv = t.dir[lane], oxy = t.sxy[lane], ov = t.svel[lane];
 #pragma unroll
                 for (int s = 0; s < S; s++) {
@@ -626,7 +641,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
                     }
                     if (keep) {
                         if (m < (int)K) {
-                            row[m] = o;
+                            if (n_born == 0) born[0] = o; else born[1] = o;
+                            n_born++;
                             m++;
                         } else {
                             ev |= ASTRO_EV_OVERFLOW;
@@ -662,6 +678,36 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             }
         }
     }
+
+    // ================= 6. the new list: survivors and newborn, dense, into the other buffer =========
+    // Game order, the game's survivors (reference order) then its newborn.  Each staged position
+    // knows its game and rank (ref): position p of game gi moves to new_first[gi] + rank when
+    // rank < survivors[gi] — consecutive survivors land on consecutive items, so a window stores
+    // one contiguous run.
+    unsigned oincl = (unsigned)m_out;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned v = __shfl_up_sync(full, oincl, d);
+        if ((int)lane >= d) oincl += v;
+    }
+    const unsigned oexcl = oincl - (unsigned)m_out;
+    if (n_born > 0) ST_STREAM(&list_out[oexcl + surv], born[0]);
+    if (n_born > 1) ST_STREAM(&list_out[oexcl + surv + 1u], born[1]);
+    if (!multi) {
+        t.ginfo[lane] = oexcl | (surv << 16);
+        __syncwarp();
+        const unsigned n_win = (total + 31u) >> 5;
+#pragma unroll 1
+        for (unsigned w = 0; w < n_win; w++) {
+            const unsigned ref = t.ref[w * 32u + lane];
+            const float4 bv = t.bul[w * 32u + lane];
+            const unsigned gin = t.ginfo[ref & 31u], rank = (ref >> 5) & 1023u;
+            if (rank < (gin >> 16)) ST_STREAM(&list_out[(gin & 0xffffu) + rank], bv);
+        }
+    } else {
+        // (rare) the survivors sit compacted in the list that was read: every lane copies its game's run
+        for (unsigned k = 0; k < surv; k++) list_out[oexcl + k] = list_in[my_excl + k];
+    }
     if (p.reward) {
         if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[1]);
         else p.reward[g] = rw[0];
@@ -679,8 +725,10 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     TL(7);
 }
 
-// ---- the launchable forms ---------------------------------------------------------------------
-// Classic: one warp (= one CTA) per tile; the block scheduler balances the load.
+// ---- the launchable form ----------------------------------------------------------------------
+// One warp (= one CTA) per tile; the block scheduler balances the load.  (Persistent forms — static
+// tile striding, a device-side tile queue with the next tile's rows prefetched, a fully staged
+// software pipeline — were built and measured 12-48 % slower: profiles/r1_ab_v6_experiments.md.)
 template <int S, bool STATS>
 __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
     __shared__ TileScratch s_tiles[kTickWarps];
@@ -690,68 +738,4 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     TileIn in;
     load_tile_in<S>(p, tile, lane, in);
     tick_tile<S, STATS>(p, s_tiles[threadIdx.x >> 5], lane, tile, in);
-}
-
-// Queue: one resident wave of one-warp CTAs; each warp takes tiles from a device-wide counter and
-// loads the NEXT tile's rows (12 registers) before it starts on the current one, so the first
-// round trip to HBM of every tile but a warp's first is hidden behind a whole tile of work and the
-// warp keeps requests in flight all the time.  The tile after next is drawn from the counter one
-// tile early for the same reason.  The last warp to finish re-arms the counters for the next launch.
-#ifndef ASTRO_QUEUE_MIN_BLOCKS
-#define ASTRO_QUEUE_MIN_BLOCKS 24
-#endif
-#ifndef ASTRO_QUEUE_WARM_NEXT
-#define ASTRO_QUEUE_WARM_NEXT 0
-#endif
-#ifndef ASTRO_QUEUE_CHUNK
-#define ASTRO_QUEUE_CHUNK 2   /* consecutive tiles per draw: same-address atomics serialise in L2 */
-#endif
-template <int S, bool STATS>
-__global__ void __launch_bounds__(32, ASTRO_QUEUE_MIN_BLOCKS) tick_f32_queue_kernel(const __grid_constant__ TickParams p) {
-    __shared__ TileScratch s_tile;
-    constexpr unsigned CH = ASTRO_QUEUE_CHUNK;
-    const unsigned lane = threadIdx.x, W = gridDim.x, n_tiles = (unsigned)p.n_games >> 5;
-    unsigned tile = blockIdx.x;   // the first W tiles are dealt statically, the rest drawn in chunks of CH
-    if (tile < n_tiles) {
-        // A draw is issued by lane 0 and its result is only broadcast when the chunk is needed, a
-        // chunk of tiles later: the atomic's round trip (and its queueing behind the other warps'
-        // draws on the same address) stays off the critical path.
-        auto issue_draw = [&]() { return lane == 0 ? atomicAdd(&p.queue[0], 1u) : 0u; };
-        unsigned pending = issue_draw();          // chunk after the current one (raw, lane 0)
-        unsigned base = 0, pos = CH;              // current chunk: exhausted -> take `pending`
-        auto next_tile = [&]() {
-            if (pos == CH) {
-                base = W + CH * __shfl_sync(0xffffffffu, pending, 0);
-                pending = issue_draw();
-                pos = 0;
-            }
-            return base + pos++;
-        };
-        unsigned tile_next = next_tile();
-        TileIn cur, nxt;
-        load_tile_in<S>(p, tile, lane, cur);
-        while (true) {
-            const bool more = tile_next < n_tiles;
-#if ASTRO_QUEUE_WARM_NEXT
-            if (more) load_tile_in<S>(p, tile_next, lane, nxt);   // in flight during this whole tile
-#else
-            // (planet rows are NOT warmed a tile ahead: by the time they are wanted, ~10 us later, L2 has
-            // turned over and the rows would be fetched from HBM twice)
-            if (more) load_tile_in<S, false>(p, tile_next, lane, nxt);
-#endif
-            tick_tile<S, STATS>(p, s_tile, lane, tile, cur);
-            if (!more) break;
-            __syncwarp();
-            tile = tile_next;
-            tile_next = next_tile();
-            cur = nxt;
-        }
-    }
-    if (lane == 0) {
-        __threadfence();
-        if (atomicAdd(&p.queue[1], 1u) == W - 1u) {  // every warp is past its last draw
-            p.queue[0] = 0u;
-            p.queue[1] = 0u;
-        }
-    }
 }

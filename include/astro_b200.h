@@ -23,13 +23,20 @@
  *     ships    R4  [n_tiles][S][32]      ship s of game g  -> ((g/32)*S + s)*32 + g%32
  *     ship_b   R   [n_tiles][S][32]      bearing
  *     planets  R4  [n_tiles][4][32]      slots >= np are dead
- *     bullets  R4  [n_games][K]          game-major: a game's pool is one contiguous row; slots
- *                                        >= nb are dead; order = reference order
+ *     bullets  R4  [2][n_tiles][32*K]    TILE LISTS, two buffers.  In the current buffer
+ *                                        (astro_bullet_buffer()) tile t's run holds the bullets of its
+ *                                        32 games back to back, no gaps: game g's bullets are items
+ *                                        first(g) .. first(g)+nb(g)-1 with first(g) = sum of nb over
+ *                                        the tile's lower games (finished games: nb = 0), in
+ *                                        reference order; the rest of the run (capacity 32*K) is
+ *                                        dead.  Every astro_tick reads the current buffer, writes
+ *                                        the tile's new list into the other one and flips.
  *     meta     u32 [n_tiles*32]          nb (bits 0-9) | np (10-12) | finished (13) | tick (14-31)
  *     episode  u32 [n_tiles*32]          games finished in this slot (a counter; bumped on reset)
  * Ships, planets and meta are accessed thread-per-game: every load/store is a fully coalesced
- * 128-bit (R=float) access across the warp.  Bullets are processed by the warp as one flat list
- * per tile (see csrc/tick_f32.cuh), 32 consecutive list items per step: contiguous runs.
+ * 128-bit (R=float) access across the warp.  A tile's bullets are one contiguous run in HBM (3 KB
+ * on average instead of 32 runs of ~90 B): the warp reads it 512 B per step and writes the new
+ * list the same way (see csrc/tick_f32.cuh).
  */
 #ifndef ASTRO_B200_H
 #define ASTRO_B200_H
@@ -40,7 +47,7 @@
 extern "C" {
 #endif
 
-#define ASTRO_ABI_VERSION 1
+#define ASTRO_ABI_VERSION 2
 #define ASTRO_TILE 32
 #define ASTRO_MAX_SHIPS 2
 #define ASTRO_MAX_PLANETS 4
@@ -68,9 +75,6 @@ extern "C" {
 #define ASTRO_TICK_AUTO_RESET 1 /* a game that ends is re-initialised from the reset pool in the same launch */
 #define ASTRO_TICK_NO_STATS 2   /* skip the astro_stats counters for this tick */
 #define ASTRO_TICK_GENERIC_KERNEL 4 /* precision 32 only: run the un-tuned template kernel (A/B checks) */
-#define ASTRO_TICK_PERSISTENT 8     /* precision 32 only: persistent kernel, meta word one tile ahead (A/B) */
-#define ASTRO_TICK_QUEUE 32         /* precision 32 only: resident warps draw tiles from a device queue, next tile's rows prefetched */
-#define ASTRO_TICK_PREFETCH_ROWS 16 /* precision 32 only: persistent kernel, next tile's rows staged too (A/B) */
 
 /* error codes */
 #define ASTRO_OK 0
@@ -87,7 +91,7 @@ typedef struct AstroConfig {
     int32_t reserved;
 } AstroConfig;
 
-/* Device pointers of the caller-owned state (layout above). */
+/* Device pointers of the caller-owned state (layout above; bullets = both buffers, contiguous). */
 typedef struct AstroBuffers {
     void* ships;
     void* ship_b;
@@ -132,7 +136,13 @@ const char* astro_last_error(void);
 int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_cap, int32_t precision,
                        int32_t device, AstroBatch** out);
 int astro_batch_destroy(AstroBatch* b);
-int astro_batch_bind(AstroBatch* b, const AstroBuffers* bufs);
+int astro_batch_bind(AstroBatch* b, const AstroBuffers* bufs);   /* the lists are in bullet buffer 0 after a bind */
+
+/* Which of the two bullet buffers holds the tile lists right now (0 or 1): what a host-side reader or
+ * writer of `bullets` (to_state, set_states) must index with.  astro_set_bullet_buffer declares where
+ * the caller has put them (e.g. after restoring a saved batch). */
+int astro_bullet_buffer(const AstroBatch* b);
+int astro_set_bullet_buffer(AstroBatch* b, int32_t which);
 
 /* reload / t are Python-float accumulators in the reference (core.py:257-280,302): a pure
  * function of the tick index.  The host evaluates them once, in the reference's arithmetic,

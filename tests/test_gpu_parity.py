@@ -213,7 +213,7 @@ def test_config2_4096_games_f32_teacher_forced():
     assert st['overflow'] == 0 and st['bullets_spawned'] == 2 * n_fired
 
 
-@pytest.mark.parametrize('flags', [nat.TICK_QUEUE, nat.TICK_PERSISTENT, nat.TICK_PREFETCH_ROWS, nat.TICK_GENERIC_KERNEL])
+@pytest.mark.parametrize('flags', [nat.TICK_GENERIC_KERNEL])
 def test_kernel_variants_hold_the_same_parity(flags):
     """The A/B kernels (persistent; persistent with staged rows; generic template) pass
     the same teacher-forced check as the default kernel, incl. a ragged tile count."""

@@ -9,7 +9,7 @@ from astro_b200 import _native as nat
 from astro_b200.batched import BatchedGames
 from astro_b200.pool import make_pool
 pool = make_pool(core.DEFAULT_CONFIG, 64)
-for prec, flags in ((32, 0), (32, nat.TICK_PERSISTENT), (32, nat.TICK_PREFETCH_ROWS), (32, nat.TICK_GENERIC_KERNEL), (64, 0)):
+for prec, flags in ((32, 0), (32, nat.TICK_GENERIC_KERNEL), (64, 0)):
     g = BatchedGames(core.DEFAULT_CONFIG, 256, bullet_cap=32, precision=prec, device=0, seed=1)
     g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
     g.reset_all()
