@@ -33,19 +33,21 @@ constexpr int kTickWarps = kTickThreads / 32;
 #endif
 constexpr int kStageWindows = ASTRO_STAGE_WINDOWS;   // bullets staged per round: 8 windows x 32 = 256 (4 KB per warp)
 
+// Per-game entries used by the bullet loop are indexed by the game's rank among the tile's games
+// that own bullets (`cid`): item -> cid comes out of one ballot per window, no lookup table.
 struct TileScratch {               // per warp
     float4 bul[kStageWindows * 32];  // the tile's bullet list, staged by cp.async; survivors are compacted here
-    float4 sxy[32];                // OLD ship0.xy, ship1.xy          } what the bullet loop reads,
-    float4 pxy[2][32];             // OLD planet0.xy planet1.xy / 2,3 } addressed by game
-    float4 svel[32];               // OLD ship velocities   } for the newborn bullets
-    float4 dir[32];                // sin/cos of both bearings }
-    uint32_t cinfo[32];            // k-th non-empty game: game | first list item << 5 | bullet count << 20
-    uint32_t outn[32];             // survivors of the game
-    uint32_t hits[32];             // bits 0-1: ship hits found by the bullet loop; bits 8+: np
-    uint32_t ginfo[32];            // first item of the game in the NEW list | survivors to copy << 16
-    uint16_t ref[kStageWindows * 32];  // staged item -> game | slot << 5 | last-of-game << 15 ; kNoItem = none
+    float4 fsxy[32];               // [cid] OLD ship0.xy, ship1.xy          } what the bullet loop reads
+    float4 fpxy[2][32];            // [cid] OLD planet0.xy planet1.xy / 2,3 } (transposed pairs)
+    float4 sxy[32];                // [lane] OLD ship positions  }
+    float4 svel[32];               // [lane] OLD ship velocities } for the newborn bullets
+    float4 dir[32];                // [lane] sin/cos of both bearings
+    uint32_t hits[32];             // [cid] bits 0-1: ship hits found by the bullet loop; bits 8+: np
+    int32_t shift[32];             // [cid] new list: item j of the compacted list moves to j + shift (kDrop: game over)
+    uint16_t gstart[34];           // [cid] first survivor of the game in the compacted list; [n] = survivors of the tile
+    uint8_t ref[kStageWindows * 32];   // compacted item -> cid
 };
-constexpr unsigned kNoItem = 1023u << 5;   // slot 1023 never exists (nb <= 1023): never a survivor to copy
+constexpr int kDrop = 0x40000000;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -111,35 +113,13 @@ __device__ __forceinline__ bool bullet_step(Body4<float>& b, float4 sxy, float4 
     return keep;
 }
 
-// Flat bullet list of a tile: item i of the list -> (game, slot).  `starts` = bit r set when a
-// non-empty game's first bullet is item base + r; c0 = non-empty games that start before base.
-struct ItemRef {
-    unsigned game, excl;
-    bool valid;
-};
-__device__ __forceinline__ ItemRef map_item(const TileScratch& t, unsigned base, unsigned total, unsigned my_excl,
-                                            bool my_nonempty, unsigned lane, unsigned& c0) {
-    const unsigned full = 0xffffffffu;
-    unsigned rel = my_excl - base;  // wraps to a huge value when the game starts before base
-    unsigned starts = __reduce_or_sync(full, (my_nonempty && rel < 32u) ? (1u << rel) : 0u);
-    unsigned le = full >> (31u - lane);
-    unsigned idx = c0 + __popc(starts & le);  // >= 1 for a valid item
-    c0 += __popc(starts);
-    unsigned ci = t.cinfo[(idx - 1u) & 31u];  // (stale only for invalid items)
-    ItemRef r;
-    r.valid = base + lane < total;
-    r.game = ci & 31u;
-    r.excl = ci >> 5;
-    return r;
-}
-
 // ---- packed fp32 pairs ------------------------------------------------------------------------
 // sm_100a issues FADD2 / FMUL2 / FFMA2: one issue slot, two IEEE fp32 operations, each half rounded
 // exactly like the scalar instruction.  The tick is bound by instruction issue as much as by HBM,
 // so the x/y halves of a body (the natural register pairs of its float4) and pairs of staged
 // objects go through them.
 #ifndef ASTRO_PACKED_F32
-#define ASTRO_PACKED_F32 0
+#define ASTRO_PACKED_F32 1
 #endif
 #if ASTRO_PACKED_F32
 typedef unsigned long long f32x2;
@@ -165,9 +145,10 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     return d;
 }
 #else
-// Scalar twin (same roundings): measured on B200, FADD2/FMUL2/FFMA2 hold the FMA pipe for two
-// cycles and their results come back through the scoreboard, which costs this latency-bound
-// kernel more than the saved issue slots (tools/ubench/f32x2.cu).
+// Scalar twin (same roundings), -DASTRO_PACKED_F32=0.  FADD2/FMUL2/FFMA2 hold the FMA pipe for two
+// cycles (tools/ubench/f32x2.cu), which made them neutral while the tick waited on scattered HBM
+// runs; with the tile lists the tick is a chain of dependent instructions per warp and the ~150
+// saved issue slots per tile are worth 10 % (88.3 -> 79.0 us per 1M-game tick).
 struct f32x2 {
     float lo, hi;
 };
@@ -408,46 +389,30 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     }
     const unsigned my_excl = incl - (unsigned)nb;
     const unsigned total = __shfl_sync(full, incl, 31);
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = full >> (31u - lane);
     const bool nonempty = nb > 0;
-    t.outn[lane] = 0u;
-    t.hits[lane] = (unsigned)np << 8;
     const unsigned ne = __ballot_sync(full, nonempty);
-    const unsigned lt_mask = (1u << lane) - 1u;
-    // k-th non-empty game: game (5 bits) | first list index (15) | bullet count (10)
-    if (nonempty) t.cinfo[__popc(ne & lt_mask)] = lane | (my_excl << 5) | ((unsigned)nb << 20);
-    __syncwarp();
-    unsigned c0 = 0;
-    // One window = 32 consecutive list items = 512 contiguous bytes; a round = up to kStageWindows
-    // windows, all requested at once (16-byte cp.async each), so the whole tile's bullet traffic is
-    // in flight together.  Item -> (game, slot), for the frame lookup and the compaction: `starts` has
-    // bit r set when a non-empty game's first bullet is item base + r; c0 counts the non-empty games
-    // that start before the window.  Lanes past the end of the list stage a bullet that is certainly
-    // culled (no `valid` flag in the loop below).
+    const unsigned cid = __popc(ne & lt_mask);                    // this game's rank among the games with bullets
     const unsigned start_key = nonempty ? my_excl : 0x80000000u;  // empty games never "start"
-    const unsigned le_mask = full >> (31u - lane);
+    if (nonempty) t.hits[cid] = (unsigned)np << 8;
+    // One window = 32 consecutive list items = 512 contiguous bytes; a round = up to kStageWindows
+    // windows, all requested at once (16-byte cp.async each) and as early as possible — nothing
+    // else sits between the arrival of meta and these requests (measured: working out the item ->
+    // game labels here instead of in the bullet loop costs 10 % of the tick).  Lanes past the end of
+    // the list stage a bullet that is certainly culled (no `valid` flag in the loop below).
     const unsigned bul_s = (unsigned)__cvta_generic_to_shared(&t.bul[lane]);
     auto stage_round = [&](unsigned round_base) {
         const unsigned left = total - round_base;
         const unsigned n_win = left >= (unsigned)kStageWindows * 32u ? (unsigned)kStageWindows : (left + 31u) >> 5;
 #pragma unroll 1
         for (unsigned w = 0; w < n_win; w++) {
-            const unsigned base = round_base + w * 32u;
-            const unsigned rel = start_key - base;  // >= 32 unless this lane's game starts in the window
-            const unsigned starts = __reduce_or_sync(full, rel < 32u ? (1u << rel) : 0u);
-            const unsigned idx = c0 + __popc(starts & le_mask);  // >= 1 for a valid item
-            c0 += __popc(starts);
-            const unsigned ci = t.cinfo[(idx - 1u) & 31u];  // (stale only for invalid items)
-            const unsigned item = base + lane;
-            const unsigned game = ci & 31u, slot = item - ((ci >> 5) & 0x7fffu);
-            unsigned ref = kNoItem;
+            const unsigned item = round_base + w * 32u + lane;
             if (item < total) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bul_s + w * 512u), "l"(list_in + item)
                              : "memory");
-                ref = game | (slot << 5) | ((slot + 1u == (ci >> 20)) ? 0x8000u : 0u);  // bit 15: last of its game
             } else {
                 t.bul[w * 32u + lane] = make_float4(4.0f, 4.0f, 0.0f, 0.0f);
             }
-            t.ref[w * 32u + lane] = (uint16_t)ref;
         }
         cp_async_commit();
     };
@@ -461,8 +426,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     // this post-step state: the state of a finished game is unspecified, the reference has none.)
     t.sxy[lane] = make_float4(shv[0].x, shv[1].x, shv[0].y, shv[1].y);
     t.svel[lane] = make_float4(shv[0].z, shv[0].w, shv[1].z, shv[1].w);
-    t.pxy[0][lane] = make_float4(plv[0].x, plv[1].x, plv[0].y, plv[1].y);
-    t.pxy[1][lane] = make_float4(plv[2].x, plv[3].x, plv[2].y, plv[3].y);
+    if (nonempty) {
+        t.fsxy[cid] = make_float4(shv[0].x, shv[1].x, shv[0].y, shv[1].y);
+        t.fpxy[0][cid] = make_float4(plv[0].x, plv[1].x, plv[0].y, plv[1].y);
+        t.fpxy[1][cid] = make_float4(plv[2].x, plv[3].x, plv[2].y, plv[3].y);
+    }
 #ifdef ASTRO_TIMELINE
     if (__shfl_xor_sync(full, __float_as_uint(shv[0].x) ^ __float_as_uint(sb[1]) ^ __float_as_uint(plv[0].x) ^ __float_as_uint(plv[3].x), 1) == 0xdeadbeefu) return;
     TL(3);  // ships and planets have arrived
@@ -523,12 +491,13 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     }
 
     // ================= 4. the bullet loop, from shared memory =======================================
-    // Survivors are compacted inside each game's segment of the staged list, in list order.  Only the
-    // game that straddles a window boundary carries a count from one window to the next: `carry`
-    // (warp-uniform).  A tile whose list does not fit the staging buffer (`multi`: more than
-    // kStageWindows * 32 bullets, rare) compacts into the list it is reading instead — writes only
-    // land on items already consumed — and copies from there.
-    unsigned carry = 0;
+    // Survivors are compacted over the WHOLE staged list, in list order (stable), labels along with
+    // them: survivor number `pos` of the tile = survivors before the window (`carry`, warp-uniform) +
+    // popc of the keep ballot below the lane.  Each game's first item records where the game's
+    // survivors begin (and the previous game's end).  A tile whose list does not fit the staging
+    // buffer (`multi`: more than kStageWindows * 32 bullets, rare) compacts into the list it is
+    // reading instead — writes only land on items already consumed — and copies from there.
+    unsigned carry = 0, c0 = 0;
     const bool multi = total > (unsigned)kStageWindows * 32u;
     TL(4);  // physics done, new ship / planet state stored
     for (unsigned round_base = 0; round_base < total; round_base += (unsigned)kStageWindows * 32u) {
@@ -541,48 +510,34 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
         if (round_base == 0) TL(5);  // bullets have arrived
         const unsigned left = total - round_base;
         const unsigned n_win = left >= (unsigned)kStageWindows * 32u ? (unsigned)kStageWindows : (left + 31u) >> 5;
-        // One window: 32 list items.  Everything a window needs from shared memory is loaded first
-        // (Win), then compact() decides, compacts and stores.  (A/B: two windows per iteration, the
-        // loads of the second overlapping the arithmetic of the first: 94.7 against 95.2 us — noise.)
-        struct Win {
-            unsigned ref;
-            float4 bv, sT, pA, pB;
-        };
-        auto load_win = [&](unsigned w) {
-            Win x;
-            x.ref = t.ref[w * 32u + lane];
-            x.bv = t.bul[w * 32u + lane];
-            const unsigned gi = x.ref & 31u;
-            x.sT = t.sxy[gi];
-            x.pA = t.pxy[0][gi];
-            x.pB = t.pxy[1][gi];
-            return x;
-        };
-        auto compact = [&](Win& x, unsigned w) {
-            const unsigned gi = x.ref & 31u, slot = (x.ref >> 5) & 1023u;
-            unsigned sh_hits = 0;
-            const bool keep = bullet_step_t<S>(x.bv, x.sT, x.pA, x.pB, t.hits, gi, c, sh_hits);
-            if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
-            // stable compaction inside each game's segment of the window; only the game that
-            // straddles a window boundary carries a count over (`carry`, warp-uniform)
-            const unsigned kb = __ballot_sync(full, keep);   // (every lane has loaded its window item by now)
-            const unsigned seg_lo = lane - min(slot, lane);  // first lane of this game's segment
-            const unsigned pos = (slot > lane ? carry : 0u) + __popc(kb & lt_mask & (full << seg_lo));
-            if (keep) {
-                const unsigned dst = w * 32u + lane - slot + pos;   // the game's first item + rank, <= this item
-                if (!multi) t.bul[dst] = x.bv;
-                else list_in[round_base + dst] = x.bv;
-            }
-            const unsigned tot = pos + (keep ? 1u : 0u);
-            if (x.ref & 0x8000u) t.outn[gi] = tot;
-            carry = __shfl_sync(full, tot, 31);
-        };
 #pragma unroll 1
         for (unsigned w = 0; w < n_win; w++) {
-            Win x = load_win(w);
-            compact(x, w);
+            // item -> game: bit r of `starts` = a game's first bullet is item r of this window; c0 =
+            // games that started before it (warp-uniform)
+            const unsigned rel = start_key - (round_base + w * 32u);   // >= 32 unless this lane's game starts here
+            const unsigned starts = __reduce_or_sync(full, rel < 32u ? (1u << rel) : 0u);
+            const unsigned gi = c0 + __popc(starts & le_mask) - 1u;    // (items past the end: the last game)
+            c0 += __popc(starts);
+            float4 bv = t.bul[w * 32u + lane];
+            const float4 sT = t.fsxy[gi], pA = t.fpxy[0][gi], pB = t.fpxy[1][gi];
+            unsigned sh_hits = 0;
+            const bool keep = bullet_step_t<S>(bv, sT, pA, pB, t.hits, gi, c, sh_hits);
+            if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
+            const unsigned kb = __ballot_sync(full, keep);   // (every lane has loaded its window item by now)
+            const unsigned pos = carry + __popc(kb & lt_mask);
+            if (keep) {
+                if (!multi) {
+                    t.bul[pos] = bv;
+                    t.ref[pos] = (uint8_t)gi;
+                } else {
+                    list_in[pos] = bv;
+                }
+            }
+            if ((starts >> lane) & 1u) t.gstart[gi] = (uint16_t)pos;
+            carry += __popc(kb);
         }
     }
+    if (lane == 0) t.gstart[__popc(ne)] = (uint16_t)carry;
     __syncwarp();
     TL(6);
 
@@ -596,8 +551,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     if (!active) {
         ev = ASTRO_EV_SKIPPED;
     } else {
-        int m = (int)t.outn[lane];
-        hits |= t.hits[lane] & 3u;
+        int m = 0;   // survivors of this game
+        if (nonempty) {
+            m = (int)t.gstart[cid + 1u] - (int)t.gstart[cid];
+            hits |= t.hits[cid] & 3u;
+        }
         const bool timeout = tick >= (uint32_t)p.timeout_tick;
         if (hits) {  // core.py:253-255
             ev = hits;  // ASTRO_EV_HIT0 | ASTRO_EV_HIT1 are bits 0 and 1
@@ -680,33 +638,39 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     }
 
     // ================= 6. the new list: survivors and newborn, dense, into the other buffer =========
-    // Game order, the game's survivors (reference order) then its newborn.  Each staged position
-    // knows its game and rank (ref): position p of game gi moves to new_first[gi] + rank when
-    // rank < survivors[gi] — consecutive survivors land on consecutive items, so a window stores
-    // one contiguous run.
-    unsigned oincl = (unsigned)m_out;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned v = __shfl_up_sync(full, oincl, d);
-        if ((int)lane >= d) oincl += v;
-    }
-    const unsigned oexcl = oincl - (unsigned)m_out;
-    if (n_born > 0) ST_STREAM(&list_out[oexcl + surv], born[0]);
-    if (n_born > 1) ST_STREAM(&list_out[oexcl + surv + 1u], born[1]);
-    if (!multi) {
-        t.ginfo[lane] = oexcl | (surv << 16);
-        __syncwarp();
-        const unsigned n_win = (total + 31u) >> 5;
+    // Game order, the game's survivors (reference order) then its newborn.  The compacted list in
+    // shared memory is already that, except for the survivors of games that just ended (dropped)
+    // and the newborn (inserted after their game): when the tile has neither, the compacted list
+    // is copied out as it is; otherwise every survivor moves by its game's shift.  Either way a
+    // step stores (nearly) contiguous 512 bytes.
+    const unsigned n_surv = carry;
+    const bool moves = __ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0 || n_born != 0) != 0;
+    if (!moves && !multi) {
 #pragma unroll 1
-        for (unsigned w = 0; w < n_win; w++) {
-            const unsigned ref = t.ref[w * 32u + lane];
-            const float4 bv = t.bul[w * 32u + lane];
-            const unsigned gin = t.ginfo[ref & 31u], rank = (ref >> 5) & 1023u;
-            if (rank < (gin >> 16)) ST_STREAM(&list_out[(gin & 0xffffu) + rank], bv);
-        }
+        for (unsigned j = lane; j < n_surv; j += 32u) ST_STREAM(&list_out[j], t.bul[j]);
     } else {
-        // (rare) the survivors sit compacted in the list that was read: every lane copies its game's run
-        for (unsigned k = 0; k < surv; k++) list_out[oexcl + k] = list_in[my_excl + k];
+        unsigned oincl = (unsigned)m_out;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned v = __shfl_up_sync(full, oincl, d);
+            if ((int)lane >= d) oincl += v;
+        }
+        const unsigned oexcl = oincl - (unsigned)m_out;
+        if (n_born > 0) ST_STREAM(&list_out[oexcl + surv], born[0]);
+        if (n_born > 1) ST_STREAM(&list_out[oexcl + surv + 1u], born[1]);
+        if (!multi) {
+            if (nonempty) t.shift[cid] = (ev & ASTRO_EV_DONE_MASK) ? kDrop : (int)oexcl - (int)t.gstart[cid];
+            __syncwarp();
+#pragma unroll 1
+            for (unsigned j = lane; j < n_surv; j += 32u) {
+                const int sh = t.shift[t.ref[j]];
+                if (sh != kDrop) ST_STREAM(&list_out[(int)j + sh], t.bul[j]);
+            }
+        } else {
+            // (rare) the survivors sit compacted in the list that was read: every lane copies its game's run
+            const unsigned from = nonempty ? (unsigned)t.gstart[cid] : 0u;
+            for (unsigned k = 0; k < surv; k++) list_out[oexcl + k] = list_in[from + k];
+        }
     }
     if (p.reward) {
         if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[1]);
