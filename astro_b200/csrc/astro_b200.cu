@@ -47,6 +47,7 @@ struct TickParams {
     const void* pool_ships;
     const void* pool_planets;
     const int32_t* pool_np;
+    const float4* pool_rec;  // precision 32: the pool as one 128-byte record per entry (pack_pool_kernel)
     unsigned long long* stats;
     unsigned* stat_slots;  // u32 [n_tiles][16]: per-warp partial counters (tick_f32_kernel)
     int32_t n_games, K, timeout_tick, n_sched_ticks, pool_size, flags;
@@ -86,6 +87,21 @@ __device__ __forceinline__ void recreate_from_pool(const TickParams& p, int g, u
     p.meta[g] = ASTRO_META_PACK(0, np_new, 0, 0);
 }
 
+// The reset pool as one 128-byte record per entry, so that re-creating a game inside the tick is ONE
+// round trip (the three pool arrays need the planet count first): floats 0 .. 5S-1 = ships
+// (x, y, dx, dy, b each), word 10 = planet count, floats 16 .. 31 = planets.
+template <int S>
+__global__ void pack_pool_kernel(const float* __restrict__ ships, const float* __restrict__ planets,
+                                 const int32_t* __restrict__ np, float* __restrict__ rec, int m) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    float* r = rec + (size_t)k * 32;
+    for (int i = 0; i < 32; i++) r[i] = 0.f;
+    for (int i = 0; i < 5 * S; i++) r[i] = ships[(size_t)k * (5 * S) + i];
+    r[10] = __int_as_float(np[k]);
+    for (int i = 0; i < 16; i++) r[16 + i] = planets[(size_t)k * 16 + i];
+}
+
 // Warp-level reduction of the per-game flags and counts into the block's shared counters:
 // ballots / REDUX give warp-uniform totals, lane k keeps counter k, ONE shared atomic per warp.
 // (32-bit shared counters: a block's per-tick totals are < 2^19.)
@@ -95,18 +111,23 @@ __device__ __forceinline__ unsigned warp_totals(int lane, int S, uint32_t ev, bo
     const bool coll = (ev & (ASTRO_EV_HIT0 | ASTRO_EV_HIT1)) != 0;
     const bool h0 = ev & ASTRO_EV_HIT0, h1 = ev & ASTRO_EV_HIT1;
     unsigned v[ASTRO_N_STATS];
-    v[0] = __popc(__ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0));
-    v[1] = __popc(__ballot_sync(full, S == 2 && coll && !h0));
-    v[2] = __popc(__ballot_sync(full, S == 2 && coll && !h1));
-    v[3] = __popc(__ballot_sync(full, coll && (S == 1 || (h0 && h1))));
-    v[4] = __popc(__ballot_sync(full, (ev & ASTRO_EV_TIMEOUT) != 0));
+#pragma unroll
+    for (int k = 0; k < ASTRO_N_STATS; k++) v[k] = 0u;
+    // most tiles, most ticks: nobody ended, overflowed or was skipped, nobody fired
+    if (__ballot_sync(full, (ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_OVERFLOW | ASTRO_EV_SKIPPED)) != 0)) {
+        v[0] = __popc(__ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0));
+        v[1] = __popc(__ballot_sync(full, S == 2 && coll && !h0));
+        v[2] = __popc(__ballot_sync(full, S == 2 && coll && !h1));
+        v[3] = __popc(__ballot_sync(full, coll && (S == 1 || (h0 && h1))));
+        v[4] = __popc(__ballot_sync(full, (ev & ASTRO_EV_TIMEOUT) != 0));
+        v[7] = __popc(__ballot_sync(full, (ev & ASTRO_EV_OVERFLOW) != 0));
+        v[11] = __popc(__ballot_sync(full, (ev & ASTRO_EV_SKIPPED) != 0));
+    }
     v[5] = __popc(__ballot_sync(full, active));
-    v[6] = __reduce_add_sync(full, (unsigned)spawned);
-    v[7] = __popc(__ballot_sync(full, (ev & ASTRO_EV_OVERFLOW) != 0));
+    v[6] = (unsigned)S * __popc(__ballot_sync(full, spawned != 0));
     v[8] = __reduce_add_sync(full, (unsigned)np);
     v[9] = __reduce_add_sync(full, (unsigned)nb);
     v[10] = __reduce_add_sync(full, (unsigned)m_out);
-    v[11] = __popc(__ballot_sync(full, (ev & ASTRO_EV_SKIPPED) != 0));
     unsigned mine = 0;
 #pragma unroll
     for (int k = 0; k < ASTRO_N_STATS; k++) mine = (lane == k) ? v[k] : mine;
@@ -979,6 +1000,7 @@ struct AstroBatch {
     unsigned long long* d_stats;
     unsigned* d_stat_slots;  // per-warp partial counters, folded by astro_stats
     int32_t cur;             // which of the two bullet buffers holds the lists (flips every tick)
+    float4* d_pool_rec;      // precision 32: packed copy of the reset pool (astro_set_reset_pool)
     int64_t ticks_since_fold;
     uint8_t* d_actions;  // staging for astro_tick_host
     uint8_t* d_events;
@@ -1050,6 +1072,7 @@ void fill_params(const AstroBatch* b, TickParams& p) {
     p.pool_planets = b->pool.planets;
     p.pool_np = b->pool.np;
     p.pool_size = b->pool.size;
+    p.pool_rec = b->d_pool_rec;
     p.stats = b->d_stats;
     p.stat_slots = b->d_stat_slots;
     p.n_games = b->n_games;
@@ -1182,6 +1205,7 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaFree(b->d_done);
     cudaFree(b->d_reward);
     cudaFree(b->d_fire_bits);
+    cudaFree(b->d_pool_rec);
     if (b->pipe_ready) {
         for (int i = 0; i < 2; i++) {
             cudaFree(b->d_actions2[i]);
@@ -1240,6 +1264,20 @@ int astro_set_reset_pool(AstroBatch* b, const AstroResetPool* pool) {
         return fail(ASTRO_E_INVALID, "bad reset pool");
     if ((uintptr_t)pool->planets & 15) return fail(ASTRO_E_INVALID, "reset pool planets must be 16-byte aligned");
     b->pool = *pool;
+    if (b->precision == 32) {
+        // the tick kernel reads a packed snapshot (one 128-byte record per entry)
+        CUDA_TRY(cudaSetDevice(b->device));
+        CUDA_TRY(cudaDeviceSynchronize());   // the pool may just have been written on another stream
+        if (b->d_pool_rec) CUDA_TRY(cudaFree(b->d_pool_rec));
+        b->d_pool_rec = nullptr;
+        CUDA_TRY(cudaMalloc(&b->d_pool_rec, (size_t)pool->size * 128));
+        const int grid = (pool->size + 127) / 128;
+        if (b->S == 2) pack_pool_kernel<2><<<grid, 128>>>((const float*)pool->ships, (const float*)pool->planets, pool->np, (float*)b->d_pool_rec, pool->size);
+        else pack_pool_kernel<1><<<grid, 128>>>((const float*)pool->ships, (const float*)pool->planets, pool->np, (float*)b->d_pool_rec, pool->size);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        b->launches += 1;
+    }
     return ASTRO_OK;
 }
 

@@ -363,12 +363,12 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     // fire-schedule word of this game's tick and, with auto-reset, the planet count of the pool
     // entry that would replace the game (the pick is keyed on the stream step, not on state).
     const bool auto_reset = (p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0;
-    uint32_t pool_k = 0;
-    int np_new = 0;
     const bool active = !ASTRO_META_FINISHED(meta);
     const int nb = active ? (int)ASTRO_META_NB(meta) : 0;
     const int np = active ? (int)ASTRO_META_NP(meta) : 0;
     const uint32_t tick = ASTRO_META_TICK(meta);
+    // the fire-schedule word of this game's tick (a 376-byte table): requested now, wanted at the end
+    const uint32_t fire_word = __ldg(&p.fire_bits[min(tick, (uint32_t)p.n_sched_ticks - 1u) >> 5]);
     float4 plv[ASTRO_MAX_PLANETS];
 #pragma unroll
     for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
@@ -381,19 +381,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     if (__shfl_xor_sync(full, meta, 1) == 0xdeadbeefu) return;  // consume meta: stamp 1 = meta has arrived
     TL(1);
 #endif
-    unsigned incl = (unsigned)nb;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned v = __shfl_up_sync(full, incl, d);
-        if ((int)lane >= d) incl += v;
-    }
-    const unsigned my_excl = incl - (unsigned)nb;
-    const unsigned total = __shfl_sync(full, incl, 31);
+    const unsigned total = __reduce_add_sync(full, (unsigned)nb);   // all the requests need; the prefix sums follow them
     const unsigned lt_mask = (1u << lane) - 1u, le_mask = full >> (31u - lane);
     const bool nonempty = nb > 0;
     const unsigned ne = __ballot_sync(full, nonempty);
     const unsigned cid = __popc(ne & lt_mask);                    // this game's rank among the games with bullets
-    const unsigned start_key = nonempty ? my_excl : 0x80000000u;  // empty games never "start"
     if (nonempty) t.hits[cid] = (unsigned)np << 8;
     // One window = 32 consecutive list items = 512 contiguous bytes; a round = up to kStageWindows
     // windows, all requested at once (16-byte cp.async each) and as early as possible — nothing
@@ -417,6 +409,14 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
         cp_async_commit();
     };
     stage_round(0u);
+    unsigned incl = (unsigned)nb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned v = __shfl_up_sync(full, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    const unsigned my_excl = incl - (unsigned)nb;
+    const unsigned start_key = nonempty ? my_excl : 0x80000000u;  // empty games never "start"
     TL(2);
 
     // ================= 3. ships and planets while the bullets fly ===============================
@@ -436,7 +436,24 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     TL(3);  // ships and planets have arrived
 #endif
     unsigned hits = 0;
+#ifdef ASTRO_EXPERIMENTS
+    // experiment builds only (flag 64): the tick's memory traffic without its arithmetic — every load
+    // and store of a tick whose games neither move nor end (tools/ab_repeat.sh)
+    const bool freeze = (p.flags & 64) != 0;
+    if (freeze && active) {
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            ST_STREAM(&ships[s * 32], shv[s]);
+            ST_STREAM(&ship_b[s * 32], sb[s]);
+        }
+#pragma unroll
+        for (int i = 0; i < ASTRO_MAX_PLANETS; i++)
+            if (i < np) ST_STREAM(&planets[i * 32], plv[i]);
+    }
+    if (active && !freeze) {
+#else
     if (active) {
+#endif
         f32x2 pxy[ASTRO_MAX_PLANETS];
 #pragma unroll
         for (int j = 0; j < ASTRO_MAX_PLANETS; j++) pxy[j] = pk2(plv[j].x, plv[j].y);
@@ -490,6 +507,12 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             if (i < np) ST_STREAM(&planets[i * 32], advance_body2(pxy[i], pk2(plv[i].z, plv[i].w), q[i], c));
     }
 
+    // A game that ends here and now (ship hit a planet / the other ship, or timeout) will be re-created
+    // from its pool record at the end: pull the record towards L2 while the bullet loop runs.
+    const uint32_t pool_k = auto_reset ? pool_pick(p.seed, p.first_game + (uint32_t)g, p.step + 1u, (uint32_t)p.pool_size) : 0u;
+    const float4* const pool_rec = p.pool_rec + (size_t)pool_k * 8;
+    if (auto_reset && active && (hits || tick >= (uint32_t)p.timeout_tick)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pool_rec));
+
     // ================= 4. the bullet loop, from shared memory =======================================
     // Survivors are compacted over the WHOLE staged list, in list order (stable), labels along with
     // them: survivor number `pos` of the tile = survivors before the window (`carry`, warp-uniform) +
@@ -521,7 +544,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             float4 bv = t.bul[w * 32u + lane];
             const float4 sT = t.fsxy[gi], pA = t.fpxy[0][gi], pB = t.fpxy[1][gi];
             unsigned sh_hits = 0;
+#ifdef ASTRO_EXPERIMENTS
+            const bool keep = freeze ? (bv.x + sT.x + pA.x + pB.x != 123456.0f) : bullet_step_t<S>(bv, sT, pA, pB, t.hits, gi, c, sh_hits);
+#else
             const bool keep = bullet_step_t<S>(bv, sT, pA, pB, t.hits, gi, c, sh_hits);
+#endif
             if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
             const unsigned kb = __ballot_sync(full, keep);   // (every lane has loaded its window item by now)
             const unsigned pos = carry + __popc(kb & lt_mask);
@@ -556,7 +583,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             m = (int)t.gstart[cid + 1u] - (int)t.gstart[cid];
             hits |= t.hits[cid] & 3u;
         }
+#ifdef ASTRO_EXPERIMENTS
+        const bool timeout = !freeze && tick >= (uint32_t)p.timeout_tick;
+#else
         const bool timeout = tick >= (uint32_t)p.timeout_tick;
+#endif
         if (hits) {  // core.py:253-255
             ev = hits;  // ASTRO_EV_HIT0 | ASTRO_EV_HIT1 are bits 0 and 1
 #pragma unroll
@@ -567,8 +598,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
         } else {
             surv = (unsigned)m;
-            const uint32_t fire_word = p.fire_bits[min(tick, (uint32_t)p.n_sched_ticks - 1u) >> 5];
+#ifdef ASTRO_EXPERIMENTS
+            const bool fire = !freeze && tick < (uint32_t)p.n_sched_ticks && ((fire_word >> (tick & 31)) & 1u);
+#else
             const bool fire = tick < (uint32_t)p.n_sched_ticks && ((fire_word >> (tick & 31)) & 1u);
+#endif
             if (fire) {  // core.py:267-280, from the OLD ship state
                 ev |= ASTRO_EV_FIRED;
                 const float4 dv = t.dir[lane], oxy = t.sxy[lane], ov = t.svel[lane];
@@ -618,18 +652,19 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
                 // on the host): bullets cleared, tick 0; the per-slot episode counter is bumped with
                 // a fire-and-forget RED.
                 atomicAdd(&p.episode[g], 1u);
-                pool_k = pool_pick(p.seed, p.first_game + (uint32_t)g, p.step + 1u, (uint32_t)p.pool_size);
-                np_new = p.pool_np[pool_k];
-                const float* ps = reinterpret_cast<const float*>(p.pool_ships) + (size_t)pool_k * (S * 5);
-                const float4* pp = reinterpret_cast<const float4*>(p.pool_planets) + (size_t)pool_k * ASTRO_MAX_PLANETS;
+                float4 r[8];   // the 128-byte record: ships (5 floats each), planet count (word 10), planets (floats 16..31)
 #pragma unroll
-                for (int s = 0; s < S; s++) {
-                    ships[s * 32] = make_float4(ps[5 * s], ps[5 * s + 1], ps[5 * s + 2], ps[5 * s + 3]);
-                    ship_b[s * 32] = ps[5 * s + 4];
+                for (int j = 0; j < 8; j++) r[j] = __ldg(&pool_rec[j]);
+                const int np_new = __float_as_int(r[2].z);
+                ships[0] = r[0];
+                ship_b[0] = r[1].x;
+                if (S == 2) {
+                    ships[32] = make_float4(r[1].y, r[1].z, r[1].w, r[2].x);
+                    ship_b[32] = r[2].y;
                 }
 #pragma unroll
                 for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
-                    if (j < np_new) planets[j * 32] = pp[j];
+                    if (j < np_new) planets[j * 32] = r[4 + j];
                 p.meta[g] = ASTRO_META_PACK(0, np_new, 0, 0);
             } else {
                 p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
@@ -661,7 +696,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
         if (!multi) {
             if (nonempty) t.shift[cid] = (ev & ASTRO_EV_DONE_MASK) ? kDrop : (int)oexcl - (int)t.gstart[cid];
             __syncwarp();
-#pragma unroll 1
+#pragma unroll 2
             for (unsigned j = lane; j < n_surv; j += 32u) {
                 const int sh = t.shift[t.ref[j]];
                 if (sh != kDrop) ST_STREAM(&list_out[(int)j + sh], t.bul[j]);

@@ -197,6 +197,7 @@ def run_ours(args):
     for _ in range(args.preroll):        # reach the stationary population (device counter-stream controls)
         games.step_raw(0, flags)
     torch.cuda.synchronize()
+    flags |= args.timed_flags            # (experiment builds: bits that only apply after the pre-roll)
 
     # ring of control arrays resident in HBM / in pinned host memory
     R = 8
@@ -335,6 +336,7 @@ def main():
     ap.add_argument('--ref-games', type=int, default=65536)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tick-flags', type=int, default=0, help='extra ASTRO_TICK_* bits (kernel A/B)')
+    ap.add_argument('--timed-flags', type=int, default=0, help='extra tick bits after the pre-roll (experiment builds)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':

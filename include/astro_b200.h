@@ -152,6 +152,8 @@ int astro_set_schedule(AstroBatch* b, const uint32_t* fire_bits_host, int32_t n_
 
 /* Counter-stream keys (astro_b200/rng.py): controls when actions == NULL, reset-pool picks. */
 int astro_set_stream(AstroBatch* b, uint32_t seed, int64_t first_game, uint32_t step);
+/* The pool is SNAPSHOT by this call (precision 32: repacked into one 128-byte record per entry, which the
+ * tick kernel reads); call it again after changing the pool's contents.  Synchronises the device. */
 int astro_set_reset_pool(AstroBatch* b, const AstroResetPool* pool);
 
 /* core.step (core.py:215-303) for every game of the batch: one fused kernel.
