@@ -323,6 +323,11 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, unsigned tile,
     if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }  // S == 1: the second half of every ship pair mirrors ship 0
     in.ctl_raw = 0;
     if (p.actions) in.ctl_raw = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(p.actions)[g] : (uint32_t)p.actions[g];
+    // Everything above is ONE round trip to HBM only if it is requested before the first use of meta.
+    // ptxas is free to hoist meta-dependent code (it drags a later load and its address arithmetic up)
+    // above these requests, which then leave a whole round trip late — seen at random from build to
+    // build, 10 % of the tick (profiles/r1_ab_v6_experiments.md, session 4).  A warp barrier pins them.
+    __syncwarp();
 }
 
 // One core.step for the 32 games of one tile, by one warp.
@@ -367,8 +372,6 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     const int nb = active ? (int)ASTRO_META_NB(meta) : 0;
     const int np = active ? (int)ASTRO_META_NP(meta) : 0;
     const uint32_t tick = ASTRO_META_TICK(meta);
-    // the fire-schedule word of this game's tick (a 376-byte table): requested now, wanted at the end
-    const uint32_t fire_word = __ldg(&p.fire_bits[min(tick, (uint32_t)p.n_sched_ticks - 1u) >> 5]);
     float4 plv[ASTRO_MAX_PLANETS];
 #pragma unroll
     for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
@@ -598,6 +601,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
         } else {
             surv = (unsigned)m;
+            const uint32_t fire_word = p.fire_bits[min(tick, (uint32_t)p.n_sched_ticks - 1u) >> 5];
 #ifdef ASTRO_EXPERIMENTS
             const bool fire = !freeze && tick < (uint32_t)p.n_sched_ticks && ((fire_word >> (tick & 31)) & 1u);
 #else
