@@ -202,3 +202,26 @@ def test_forward_both_equals_forward_on_rolled_features():
         assert both.shape == (7, 2, 6)
         assert torch.allclose(both[:, 0], net(x), atol=1e-6)
         assert torch.allclose(both[:, 1], net(rolled), atol=1e-6)
+
+
+def test_tick_kernel_requests_its_rows_before_it_uses_meta():
+    """The tick's first batch of loads (meta, ship rows, bearings, controls) is one round trip to HBM only
+    if all of them are issued before the first meta-dependent load (planet rows are predicated on the
+    planet count; the bullet list is requested with LDGSTS).  ptxas used to reorder this at random,
+    costing 10 % of the tick — pinned with a warp barrier in load_tile_in (csrc/tick_f32.cuh); checked
+    here on the SASS of the built library (no GPU needed)."""
+    import shutil
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([cuobjdump, '-sass', nat.LIB_PATH], capture_output=True, text=True).stdout
+    for name in ('tick_f32_kernelILi2ELb1', 'tick_f32_kernelILi2ELb0', 'tick_f32_kernelILi1ELb1'):
+        body = sass.split('Function : ')
+        body = [b for b in body if name in b.split('\n', 1)[0]]
+        assert len(body) == 1, name
+        ops = [l for l in body[0].split('\n') if re.search(r'/\*[0-9a-f]{4}\*/', l) and re.search(r'\b(LDG|LDGSTS)\b', l.replace('.', ' '))]
+        first_dependent = next(i for i, l in enumerate(ops) if 'LDGSTS' in l or re.search(r'@!?P\d+\s+LDG\.E\.128', l))
+        head = ops[:first_dependent]
+        n_ships = 2 if 'Li2E' in name else 1
+        assert sum('LDG.E.128' in l for l in head) == n_ships, (name, head)            # ship rows
+        assert sum(bool(re.search(r'LDG\.E\s', l)) for l in head) >= 1 + n_ships, (name, head)   # meta + bearings
