@@ -1010,6 +1010,7 @@ struct AstroBatch {
     cudaStream_t copy_in, copy_out;
     cudaEvent_t ev_in[2], ev_tick[2], ev_out[2];
     bool pipe_ready;
+    int32_t pipe_chunk;      // ticks per copy of astro_rollout_host
     uint8_t* d_done;
     float* d_reward;
     uint32_t seed, step;
@@ -1312,31 +1313,48 @@ int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* even
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)b->n_games, na = n * b->S;
+    // Ticks travel in chunks of C: one host->device copy brings the controls of C ticks, one device->host
+    // copy takes their events.  C = 1 by default: on the pool's B200 boxes larger copies are SLOWER end to
+    // end (1M games, e2e env-steps/s: C = 1 1.12e10, 2 1.07e10, 4 9.3e9, 8 7.5e9 — host->device copies
+    // of 16 MB run at 14 GB/s against 51 GB/s for 2 MB, tools/ubench/pcie.py).  ASTRO_ROLLOUT_CHUNK overrides.
+    static const int chunk_env = getenv("ASTRO_ROLLOUT_CHUNK") ? atoi(getenv("ASTRO_ROLLOUT_CHUNK")) : 0;
+    const int C = chunk_env > 0 ? chunk_env : 1;
+    if (b->pipe_ready && b->pipe_chunk != C) {
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaFree(b->d_actions2[i]));
+            CUDA_TRY(cudaFree(b->d_events2[i]));
+            CUDA_TRY(cudaMalloc(&b->d_actions2[i], na * C));
+            CUDA_TRY(cudaMalloc(&b->d_events2[i], n * C));
+        }
+        b->pipe_chunk = C;
+    }
     if (!b->pipe_ready) {
         CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_out, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
-            CUDA_TRY(cudaMalloc(&b->d_actions2[i], na));
-            CUDA_TRY(cudaMalloc(&b->d_events2[i], n));
+            CUDA_TRY(cudaMalloc(&b->d_actions2[i], na * C));
+            CUDA_TRY(cudaMalloc(&b->d_events2[i], n * C));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_tick[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_out[i], cudaEventDisableTiming));
         }
+        b->pipe_chunk = C;
         b->pipe_ready = true;
     }
-    // Three queues: controls of tick k+1 travel host->device while tick k runs and the events of
-    // tick k-1 travel device->host.  Buffer i = k % 2; an event per buffer and stage orders them.
-    for (int k = 0; k < n_ticks; k++) {
-        const int i = k & 1;
-        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(b->copy_in, b->ev_tick[i], 0));  // tick k-2 has read buffer i
-        CUDA_TRY(cudaMemcpyAsync(b->d_actions2[i], actions_host + (size_t)k * na, na, cudaMemcpyHostToDevice, b->copy_in));
+    // Three queues: the controls of chunk c+1 travel host->device while the ticks of chunk c run and the
+    // events of chunk c-1 travel device->host.  Buffer i = c % 2; an event per buffer and stage orders them.
+    for (int c = 0, k0 = 0; k0 < n_ticks; c++, k0 += C) {
+        const int i = c & 1, kc = n_ticks - k0 < C ? n_ticks - k0 : C;
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(b->copy_in, b->ev_tick[i], 0));  // chunk c-2 has read buffer i
+        CUDA_TRY(cudaMemcpyAsync(b->d_actions2[i], actions_host + (size_t)k0 * na, na * kc, cudaMemcpyHostToDevice, b->copy_in));
         CUDA_TRY(cudaEventRecord(b->ev_in[i], b->copy_in));
         CUDA_TRY(cudaStreamWaitEvent(st, b->ev_in[i], 0));
-        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_out[i], 0));  // events of tick k-2 have left buffer i
-        if (int r = do_tick(b, b->d_actions2[i], nullptr, nullptr, b->d_events2[i], flags, st)) return r;
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_out[i], 0));  // events of chunk c-2 have left buffer i
+        for (int j = 0; j < kc; j++)
+            if (int r = do_tick(b, b->d_actions2[i] + (size_t)j * na, nullptr, nullptr, b->d_events2[i] + (size_t)j * n, flags, st)) return r;
         CUDA_TRY(cudaEventRecord(b->ev_tick[i], st));
         CUDA_TRY(cudaStreamWaitEvent(b->copy_out, b->ev_tick[i], 0));
-        CUDA_TRY(cudaMemcpyAsync(events_host + (size_t)k * n, b->d_events2[i], n, cudaMemcpyDeviceToHost, b->copy_out));
+        CUDA_TRY(cudaMemcpyAsync(events_host + (size_t)k0 * n, b->d_events2[i], n * kc, cudaMemcpyDeviceToHost, b->copy_out));
         CUDA_TRY(cudaEventRecord(b->ev_out[i], b->copy_out));
     }
     CUDA_TRY(cudaStreamSynchronize(b->copy_out));

@@ -173,7 +173,7 @@ int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_ho
 /* n_ticks consecutive astro_tick_host calls as one pipelined stream: actions_host u8
  * [n_ticks][n_games][S], events_host u8 [n_ticks][n_games] (pinned).  The controls of tick k+1 are
  * copied in while tick k runs and the events of tick k-1 are copied out (two internal copy
- * streams, double-buffered staging).  Returns when every event byte is on the host.  This is
+ * streams, double-buffered staging; ASTRO_ROLLOUT_CHUNK=C moves C ticks per copy instead of one).  Returns when every event byte is on the host.  This is
  * the rollout loop of core.play / rl.train (core.py:388-404) for a host-side policy whose controls
  * for a block of ticks are known up front (replays, scripted or random play). */
 int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* events_host, int32_t n_ticks,
