@@ -823,30 +823,40 @@ __device__ PolicyWeights g_pol;
 __device__ __forceinline__ float softsign(float x) { return __fdividef(x, 1.0f + fabsf(x)); }
 
 // One 32 -> 32 layer for two independent activation vectors held in shared memory (broadcast
-// LDS.128), this lane's weight row w in registers: returns both pre-activations of the lane's unit.
-__device__ __forceinline__ void layer2(const float (&w)[kPolW], float bias, const float4* xa, const float4* xb, float& ya, float& yb) {
-    float a0 = bias, a1 = 0.f, b0 = bias, b1 = 0.f;
+// LDS.128), this lane's weight row in registers as PAIRS (w[c], w[c+1]): each FFMA2 advances the even
+// and the odd partial sum of one chain at once — the same sums, in the same order, as two scalar
+// FMAs (each half of a packed operation rounds like the scalar one).  Returns both pre-activations
+// of the lane's unit.
+__device__ __forceinline__ void layer2(const f32x2 (&w)[kPolW / 2], float bias, const float4* xa, const float4* xb, float& ya, float& yb) {
+    f32x2 a = pk2(bias, 0.f), b = pk2(bias, 0.f);
 #pragma unroll
-    for (int c = 0; c < kPolW; c += 4) {
-        const float4 u = xa[c >> 2], v = xb[c >> 2];
-        a0 = __fmaf_rn(w[c], u.x, a0); a1 = __fmaf_rn(w[c + 1], u.y, a1);
-        b0 = __fmaf_rn(w[c], v.x, b0); b1 = __fmaf_rn(w[c + 1], v.y, b1);
-        a0 = __fmaf_rn(w[c + 2], u.z, a0); a1 = __fmaf_rn(w[c + 3], u.w, a1);
-        b0 = __fmaf_rn(w[c + 2], v.z, b0); b1 = __fmaf_rn(w[c + 3], v.w, b1);
+    for (int c = 0; c < kPolW / 4; c++) {
+        const float4 u = xa[c], v = xb[c];
+        a = fma2(w[2 * c], pk2(u.x, u.y), a);
+        b = fma2(w[2 * c], pk2(v.x, v.y), b);
+        a = fma2(w[2 * c + 1], pk2(u.z, u.w), a);
+        b = fma2(w[2 * c + 1], pk2(v.z, v.w), b);
     }
+    float a0, a1, b0, b1;
+    upk2(a, a0, a1);
+    upk2(b, b0, b1);
     ya = a0 + a1;
     yb = b0 + b1;
 }
 // The same with the weights streamed from a transposed matrix wt[in][out] (head layers).
 __device__ __forceinline__ void layer2_t(const float* __restrict__ wt, int stride, int lane, float bias, const float* xa,
                                          const float* xb, float& ya, float& yb) {
-    float a0 = bias, a1 = 0.f, b0 = bias, b1 = 0.f;
+    f32x2 a = pk2(bias, 0.f), b = pk2(bias, 0.f);
 #pragma unroll 8
     for (int c = 0; c < kPolW; c += 2) {
-        const float w0 = __ldg(wt + c * stride + lane), w1 = __ldg(wt + (c + 1) * stride + lane);
-        a0 = __fmaf_rn(w0, xa[c], a0); a1 = __fmaf_rn(w1, xa[c + 1], a1);
-        b0 = __fmaf_rn(w0, xb[c], b0); b1 = __fmaf_rn(w1, xb[c + 1], b1);
+        const f32x2 w = pk2(__ldg(wt + c * stride + lane), __ldg(wt + (c + 1) * stride + lane));
+        const float2 u = *reinterpret_cast<const float2*>(xa + c), v = *reinterpret_cast<const float2*>(xb + c);
+        a = fma2(w, pk2(u.x, u.y), a);
+        b = fma2(w, pk2(v.x, v.y), b);
     }
+    float a0, a1, b0, b1;
+    upk2(a, a0, a1);
+    upk2(b, b0, b1);
     ya = a0 + a1;
     yb = b0 + b1;
 }
@@ -863,11 +873,15 @@ policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
     float* actA = reinterpret_cast<float*>(s_act[warp][0]);
     float* actB = reinterpret_cast<float*>(s_act[warp][1]);
     // this lane's unit: its rows of the three per-object layers
-    float w0[DIN], w1[kPolW], w2[kPolW];
+    float w0[DIN];
+    f32x2 w1[kPolW / 2], w2[kPolW / 2];   // (w[c], w[c+1]) pairs for the packed FMAs
 #pragma unroll
     for (int c = 0; c < DIN; c++) w0[c] = g_pol.f0t[c][lane];
 #pragma unroll
-    for (int c = 0; c < kPolW; c++) { w1[c] = g_pol.f1t[c][lane]; w2[c] = g_pol.f2t[c][lane]; }
+    for (int c = 0; c < kPolW; c += 2) {
+        w1[c >> 1] = pk2(g_pol.f1t[c][lane], g_pol.f1t[c + 1][lane]);
+        w2[c >> 1] = pk2(g_pol.f2t[c][lane], g_pol.f2t[c + 1][lane]);
+    }
     const float b0 = g_pol.f0b[lane], b1 = g_pol.f1b[lane], b2 = g_pol.f2b[lane];
     for (int gi = 0; gi < kPolGamesPerWarp; gi++) {
     const int g = (blockIdx.x * kPolWarps + warp) * kPolGamesPerWarp + gi;
@@ -904,6 +918,8 @@ policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
         B4 mine = B4();
         if (r0 + lane < rows) mine = (r0 + lane < np) ? pl[(r0 + lane) * 32] : bl[r0 + lane - np];
         const int n = min(32, rows - r0);
+        // (A/B: two rows per step as four independent chains — 82.9 us against 76.4 per 16,384 games: an odd
+        // row count repeats a row, and the kernel is bound by its 16 warps per SM, not by the chains' latency)
         for (int r = 0; r < n; r++) {
             const float ox = __shfl_sync(0xffffffffu, (float)mine.x, r), oy = __shfl_sync(0xffffffffu, (float)mine.y, r);
             const float ovx = __shfl_sync(0xffffffffu, (float)mine.dx, r), ovy = __shfl_sync(0xffffffffu, (float)mine.dy, r);
