@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__
 constexpr int kPolW = 32;           // layer width (rl.py:144)
 constexpr int kPolMaxOut = 8;
 constexpr int kPolWarps = 4;
-constexpr int kPolGamesPerWarp = 2; // consecutive games per warp: the lane's 79 weights are loaded once for both
+constexpr int kPolGamesPerWarp = 2; // at least this many games per warp: the lane's 79 weights are loaded once for all of them
 struct PolicyWeights {              // every matrix TRANSPOSED, [in][out]: lane = unit reads it coalesced
     float f0t[15][kPolW], f0b[kPolW];
     float f1t[kPolW][kPolW], f1b[kPolW];
@@ -883,9 +883,8 @@ policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
         w2[c >> 1] = pk2(g_pol.f2t[c][lane], g_pol.f2t[c + 1][lane]);
     }
     const float b0 = g_pol.f0b[lane], b1 = g_pol.f1b[lane], b2 = g_pol.f2b[lane];
-    for (int gi = 0; gi < kPolGamesPerWarp; gi++) {
-    const int g = (blockIdx.x * kPolWarps + warp) * kPolGamesPerWarp + gi;
-    if (g >= n_games) return;
+    // grid-stride over games: one resident wave of CTAs (launch side), no partial last wave
+    for (int g = blockIdx.x * kPolWarps + warp; g < n_games; g += gridDim.x * kPolWarps) {
     const size_t tile = (size_t)(g >> 5);
     const int gl = g & 31;
 
@@ -1533,7 +1532,12 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
     if (b->policy_nout <= 0) return fail(ASTRO_E_STATE, "astro_policy_set_weights has not been called");
     if (!actions) return fail(ASTRO_E_INVALID, "null actions");
     CUDA_TRY(cudaSetDevice(b->device));
-    const int grid = (b->n_games + kPolWarps * kPolGamesPerWarp - 1) / (kPolWarps * kPolGamesPerWarp);
+    int grid = (b->n_games + kPolWarps * kPolGamesPerWarp - 1) / (kPolWarps * kPolGamesPerWarp);
+    {   // one resident wave: 4 CTAs of 128 threads per SM (128 registers per thread)
+        int sms = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+        if (grid > sms * 4) grid = sms * 4;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;
 #define LAUNCH_POL(R, S_) \
