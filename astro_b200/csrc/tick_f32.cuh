@@ -512,9 +512,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
 
     // A game that ends here and now (ship hit a planet / the other ship, or timeout) will be re-created
     // from its pool record at the end: pull the record towards L2 while the bullet loop runs.
-    const uint32_t pool_k = auto_reset ? pool_pick(p.seed, p.first_game + (uint32_t)g, p.step + 1u, (uint32_t)p.pool_size) : 0u;
-    const float4* const pool_rec = p.pool_rec + (size_t)pool_k * 8;
-    if (auto_reset && active && (hits || tick >= (uint32_t)p.timeout_tick)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pool_rec));
+    // (the pick is a few dozen integer instructions: only the rare lanes that need it work it out)
+    if (auto_reset && active && (hits || tick >= (uint32_t)p.timeout_tick)) {
+        const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, p.step + 1u, (uint32_t)p.pool_size);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pool_rec + (size_t)k * 8));
+    }
 
     // ================= 4. the bullet loop, from shared memory =======================================
     // Survivors are compacted over the WHOLE staged list, in list order (stable), labels along with
@@ -656,6 +658,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
                 // on the host): bullets cleared, tick 0; the per-slot episode counter is bumped with
                 // a fire-and-forget RED.
                 atomicAdd(&p.episode[g], 1u);
+                const uint32_t pool_k = pool_pick(p.seed, p.first_game + (uint32_t)g, p.step + 1u, (uint32_t)p.pool_size);
+                const float4* const pool_rec = p.pool_rec + (size_t)pool_k * 8;
                 float4 r[8];   // the 128-byte record: ships (5 floats each), planet count (word 10), planets (floats 16..31)
 #pragma unroll
                 for (int j = 0; j < 8; j++) r[j] = __ldg(&pool_rec[j]);
@@ -700,10 +704,14 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
         if (!multi) {
             if (nonempty) t.shift[cid] = (ev & ASTRO_EV_DONE_MASK) ? kDrop : (int)oexcl - (int)t.gstart[cid];
             __syncwarp();
-#pragma unroll 2
+            // (byte offsets from the two shared arrays and the list base: 9 instructions per step)
+            const char* const bul_b = reinterpret_cast<const char*>(t.bul);
+            char* const out_b = reinterpret_cast<char*>(list_out);
+#pragma unroll 1
             for (unsigned j = lane; j < n_surv; j += 32u) {
                 const int sh = t.shift[t.ref[j]];
-                if (sh != kDrop) ST_STREAM(&list_out[(int)j + sh], t.bul[j]);
+                const float4 bv = *reinterpret_cast<const float4*>(bul_b + j * 16u);
+                if (sh != kDrop) ST_STREAM(reinterpret_cast<float4*>(out_b + (size_t)((j + (unsigned)sh) * 16u)), bv);
             }
         } else {
             // (rare) the survivors sit compacted in the list that was read: every lane copies its game's run
