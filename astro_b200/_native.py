@@ -23,7 +23,7 @@ EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro
            'astro_batch_bind', 'astro_set_schedule', 'astro_set_stream', 'astro_set_reset_pool',
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
            'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
-           'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer')
+           'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer', 'astro_tick_many')
 
 
 class AstroConfig(C.Structure):
@@ -79,6 +79,7 @@ def lib():
     L.astro_set_reset_pool.argtypes = [vp, C.POINTER(AstroResetPool)]
     L.astro_tick.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.astro_tick_host.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    L.astro_tick_many.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     L.astro_rollout_host.argtypes = [vp, vp, vp, i32, i32, vp]
     L.astro_reset_done.argtypes = [vp, vp]
     L.astro_observe.argtypes = [vp, vp, i32, vp]

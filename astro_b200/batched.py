@@ -381,6 +381,36 @@ class BatchedGames:
         n = self.n
         return (self._reward[:n] if want_reward else None), self._done[:n], self._events[:n]
 
+    def step_many(self, n_ticks, actions=None, events=None, reward=None, done=None, auto_reset=True, stats=True):
+        """`n_ticks` consecutive `step()`s in as few launches as possible (astro_tick_many): the ticks of a tile run
+        back to back inside a launch, state going from one tick to the next through L2.  For loops whose controls
+        do not depend on the states inside the block (replays, random exploration, the counter stream).
+
+        actions -- None (device counter stream) or uint8 cuda tensor [n_ticks, n_pad, S]
+        events / reward / done -- optional cuda tensors [n_ticks, n_pad] (uint8) / [n_ticks, n_pad, S] (float32) /
+                   [n_ticks, n_pad] (uint8) receiving every tick's outputs"""
+        torch = _torch()
+        T = int(n_ticks)
+
+        def ptr(x, shape, dtype, name):
+            if x is None:
+                return None
+            if tuple(x.shape) != shape or x.dtype != dtype or not x.is_contiguous() or x.device != self.device:
+                raise ValueError('%s must be a contiguous %s cuda tensor %r' % (name, dtype, shape))
+            return x.data_ptr()
+        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
+        nat.check(nat.lib().astro_tick_many(
+            self._h, ptr(actions, (T, self.n_pad, self.S), torch.uint8, 'actions'),
+            ptr(reward, (T, self.n_pad, self.S), torch.float32, 'reward'), ptr(done, (T, self.n_pad), torch.uint8, 'done'),
+            ptr(events, (T, self.n_pad), torch.uint8, 'events'), T, flags, self._stream()))
+        self.step_index += T
+
+    def step_many_raw(self, actions_ptr, events_ptr, n_ticks, flags):
+        """Bench path: a bare astro_tick_many with caller-held device pointers (or 0)."""
+        nat.check(nat.lib().astro_tick_many(self._h, actions_ptr or None, None, None, events_ptr or None, int(n_ticks), flags,
+                                            self._stream()))
+        self.step_index += int(n_ticks)
+
     def step_raw(self, actions_ptr, flags):
         """Bench path: a bare astro_tick with a caller-held device pointer (or 0), events only."""
         nat.check(nat.lib().astro_tick(self._h, actions_ptr or None, None, None, self._events.data_ptr(), flags,

@@ -51,7 +51,8 @@ struct TickParams {
     unsigned long long* stats;
     unsigned* stat_slots;  // u32 [n_tiles][16]: per-warp partial counters (tick_f32_kernel)
     int32_t n_games, K, timeout_tick, n_sched_ticks, pool_size, flags;
-    uint32_t seed, step, first_game, pad;
+    uint32_t seed, step, first_game;
+    int32_t n_fused;     // ticks per launch (tick_f32_kernel; 1 everywhere else)
     Consts c;
 };
 
@@ -1116,10 +1117,13 @@ cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
     const int grid = (p.n_games + kTickThreads - 1) / kTickThreads;
     // experiment knob (tools/exp_tick.py): unused dynamic shared memory caps the resident CTAs per SM
     static const size_t extra = getenv("ASTRO_EXTRA_SMEM") ? (size_t)atoi(getenv("ASTRO_EXTRA_SMEM")) : 0;
-    if (p.flags & ASTRO_TICK_NO_STATS)
-        tick_f32_kernel<S, false><<<grid, kTickThreads, extra, st>>>(p);
-    else
-        tick_f32_kernel<S, true><<<grid, kTickThreads, extra, st>>>(p);
+    if (p.n_fused > 1) {
+        if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, true><<<grid, kTickThreads, extra, st>>>(p);
+        else tick_f32_kernel<S, true, true><<<grid, kTickThreads, extra, st>>>(p);
+    } else {
+        if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, false><<<grid, kTickThreads, extra, st>>>(p);
+        else tick_f32_kernel<S, true, false><<<grid, kTickThreads, extra, st>>>(p);
+    }
     return cudaGetLastError();
 }
 
@@ -1130,35 +1134,50 @@ cudaError_t fold_stats(AstroBatch* b, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-int do_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t flags,
-            cudaStream_t st) {
+// n_ticks consecutive ticks.  actions [n_ticks][n_games][S] (or NULL: counter stream), reward / done / events
+// [n_ticks][...] (or NULL).  The production fp32 kernel runs up to kMaxFused of them per launch, each tile
+// back to back (tick_f32_kernel); the generic / float64 kernels run one launch per tick.
+constexpr int kMaxFused = 64;
+int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t flags,
+             cudaStream_t st, int32_t n_ticks) {
     if (b->n_sched_ticks <= 0) return fail(ASTRO_E_STATE, "astro_set_schedule has not been called");
     if ((flags & ASTRO_TICK_AUTO_RESET) && b->pool.size <= 0)
         return fail(ASTRO_E_STATE, "ASTRO_TICK_AUTO_RESET needs astro_set_reset_pool");
-    TickParams p;
-    fill_params(b, p);
-    p.actions = actions;
-    p.reward = reward;
-    p.done = done;
-    p.events = events;
-    p.flags = flags;
-    cudaError_t e;
-    if (b->precision == 32 && (flags & ASTRO_TICK_GENERIC_KERNEL))
-        e = b->S == 2 ? launch_tick<float, 2>(p, st) : launch_tick<float, 1>(p, st);
-    else if (b->precision == 32)
-        e = b->S == 2 ? launch_tick_f32<2>(p, st) : launch_tick_f32<1>(p, st);
-    else
-        e = b->S == 2 ? launch_tick<double, 2>(p, st) : launch_tick<double, 1>(p, st);
-    if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "tick_kernel launch: %s", cudaGetErrorString(e));
-    b->step += 1;
-    b->cur ^= 1;   // the lists now live in the other buffer
-    b->launches += 1;
-    // 32-bit slot rows: fold long before a row can wrap (<= 32 * 1023 per tick)
-    if (!(flags & ASTRO_TICK_NO_STATS) && ++b->ticks_since_fold >= 65536) {
-        cudaError_t fe = fold_stats(b, st);
-        if (fe != cudaSuccess) return fail(ASTRO_E_CUDA, "fold_stats_kernel launch: %s", cudaGetErrorString(fe));
+    const bool fused = b->precision == 32 && !(flags & ASTRO_TICK_GENERIC_KERNEL);
+    const size_t n = (size_t)b->n_games;
+    for (int32_t k0 = 0; k0 < n_ticks;) {
+        const int32_t kc = fused ? (n_ticks - k0 < kMaxFused ? n_ticks - k0 : kMaxFused) : 1;
+        TickParams p;
+        fill_params(b, p);
+        p.actions = actions ? actions + (size_t)k0 * n * b->S : nullptr;
+        p.reward = reward ? reward + (size_t)k0 * n * b->S : nullptr;
+        p.done = done ? done + (size_t)k0 * n : nullptr;
+        p.events = events ? events + (size_t)k0 * n : nullptr;
+        p.flags = flags;
+        p.n_fused = kc;
+        cudaError_t e;
+        if (fused)
+            e = b->S == 2 ? launch_tick_f32<2>(p, st) : launch_tick_f32<1>(p, st);
+        else if (b->precision == 32)
+            e = b->S == 2 ? launch_tick<float, 2>(p, st) : launch_tick<float, 1>(p, st);
+        else
+            e = b->S == 2 ? launch_tick<double, 2>(p, st) : launch_tick<double, 1>(p, st);
+        if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "tick_kernel launch: %s", cudaGetErrorString(e));
+        b->step += (uint32_t)kc;
+        b->cur ^= kc & 1;   // the lists now live in the buffer the last tick wrote
+        b->launches += 1;
+        k0 += kc;
+        // 32-bit slot rows: fold long before a row can wrap (<= 32 * 1023 per tick)
+        if (!(flags & ASTRO_TICK_NO_STATS) && (b->ticks_since_fold += kc) >= 65536) {
+            cudaError_t fe = fold_stats(b, st);
+            if (fe != cudaSuccess) return fail(ASTRO_E_CUDA, "fold_stats_kernel launch: %s", cudaGetErrorString(fe));
+        }
     }
     return ASTRO_OK;
+}
+int do_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t flags,
+            cudaStream_t st) {
+    return do_ticks(b, actions, reward, done, events, flags, st, 1);
 }
 
 }  // namespace
@@ -1304,6 +1323,14 @@ int astro_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* do
     return do_tick(b, actions, reward, done, events, flags, (cudaStream_t)stream);
 }
 
+int astro_tick_many(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t n_ticks,
+                    int32_t flags, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (n_ticks < 0) return fail(ASTRO_E_INVALID, "n_ticks < 0");
+    CUDA_TRY(cudaSetDevice(b->device));
+    return do_ticks(b, actions, reward, done, events, flags, (cudaStream_t)stream, n_ticks);
+}
+
 int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_host, uint8_t* done_host,
                     uint8_t* events_host, int32_t flags, void* stream) {
     if (int r = check(b, true)) return r;
@@ -1365,8 +1392,7 @@ int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* even
         CUDA_TRY(cudaEventRecord(b->ev_in[i], b->copy_in));
         CUDA_TRY(cudaStreamWaitEvent(st, b->ev_in[i], 0));
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_out[i], 0));  // events of chunk c-2 have left buffer i
-        for (int j = 0; j < kc; j++)
-            if (int r = do_tick(b, b->d_actions2[i] + (size_t)j * na, nullptr, nullptr, b->d_events2[i] + (size_t)j * n, flags, st)) return r;
+        if (int r = do_ticks(b, b->d_actions2[i], nullptr, nullptr, b->d_events2[i], flags, st, kc)) return r;
         CUDA_TRY(cudaEventRecord(b->ev_tick[i], st));
         CUDA_TRY(cudaStreamWaitEvent(b->copy_out, b->ev_tick[i], 0));
         CUDA_TRY(cudaMemcpyAsync(events_host + (size_t)k0 * n, b->d_events2[i], n * kc, cudaMemcpyDeviceToHost, b->copy_out));
@@ -1573,6 +1599,11 @@ int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(b->device));
     if (any_idle) CUDA_TRY(cudaMemsetAsync(actions, 2, (size_t)b->n_games * b->S, st));  // script.NothingBot: control 2
+    if (all_stream) {
+        // no bot between the ticks: the ticks of a tile run back to back inside the launches; `events` keeps the last tick's
+        if (n_ticks > 1) if (int r = do_ticks(b, nullptr, nullptr, nullptr, nullptr, flags, st, n_ticks - 1)) return r;
+        return n_ticks > 0 ? do_ticks(b, nullptr, nullptr, nullptr, events, flags, st, 1) : ASTRO_OK;
+    }
     for (int k = 0; k < n_ticks; k++) {
         // a script bot writes every ship's control, the policy then overwrites the ships it drives
         if (any_script)

@@ -298,6 +298,30 @@ __device__ long long* g_timeline = nullptr;
 #endif
 
 // What a tile's first round trip to HBM brings: the fixed-size rows that do not depend on meta.
+// What changes from one tick to the next inside a launch that runs several ticks (astro_tick_many):
+// the stream step, the per-tick inputs / outputs, and which bullet buffer is read.
+struct TickVar {
+    uint32_t step;
+    const uint8_t* actions;
+    float* reward;
+    uint8_t* done;
+    uint8_t* events;
+    float4* bullets_in;
+    float4* bullets_out;
+};
+template <int S>
+__device__ __forceinline__ TickVar tick_var(const TickParams& p, unsigned k) {
+    TickVar v;
+    const size_t n = (size_t)p.n_games;
+    v.step = p.step + k;
+    v.actions = p.actions ? p.actions + k * n * S : nullptr;
+    v.reward = p.reward ? p.reward + k * n * S : nullptr;
+    v.done = p.done ? p.done + k * n : nullptr;
+    v.events = p.events ? p.events + k * n : nullptr;
+    v.bullets_in = reinterpret_cast<float4*>((k & 1u) ? p.bullets_out : p.bullets_in);
+    v.bullets_out = reinterpret_cast<float4*>((k & 1u) ? p.bullets_in : p.bullets_out);
+    return v;
+}
 struct TileIn {
     uint32_t meta;
     float4 shv[2];
@@ -305,7 +329,7 @@ struct TileIn {
     uint32_t ctl_raw;   // the tile's control bytes of this lane's game (S bytes), when actions are given
 };
 template <int S, bool WARM_PLANETS = true>
-__device__ __forceinline__ void load_tile_in(const TickParams& p, unsigned tile, unsigned lane, TileIn& in) {
+__device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar& v, unsigned tile, unsigned lane, TileIn& in) {
     const size_t g = (size_t)tile * 32 + lane;
     in.meta = LD_STREAM(&p.meta[g]);
     const float4* ships = reinterpret_cast<const float4*>(p.ships) + (size_t)tile * (S * 32) + lane;
@@ -325,7 +349,7 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, unsigned tile,
     }
     if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }  // S == 1: the second half of every ship pair mirrors ship 0
     in.ctl_raw = 0;
-    if (p.actions) in.ctl_raw = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(p.actions)[g] : (uint32_t)p.actions[g];
+    if (v.actions) in.ctl_raw = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(v.actions)[g] : (uint32_t)v.actions[g];
     // Everything above is ONE round trip to HBM only if it is requested before the first use of meta.
     // ptxas is free to hoist meta-dependent code (it drags a later load and its address arithmetic up)
     // above these requests, which then leave a whole round trip late — seen at random from build to
@@ -335,8 +359,8 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, unsigned tile,
 
 // One core.step for the 32 games of one tile, by one warp.
 template <int S, bool STATS>
-__device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, const unsigned lane, const unsigned tile_index,
-                                          const TileIn& in) {
+__device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratch& t, const unsigned lane,
+                                          const unsigned tile_index, const TileIn& in) {
     using B4 = Body4<float>;
     const unsigned full = 0xffffffffu;
     const int g = (int)(tile_index * 32u + lane);
@@ -350,8 +374,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     // n_games * K < 2^31): one IMAD.WIDE per address.
     const unsigned K = (unsigned)p.K;
     const unsigned tile_off = (unsigned)(g >> 5) * 32u * K;
-    float4* const list_in = reinterpret_cast<float4*>(p.bullets_in) + tile_off;
-    float4* const list_out = reinterpret_cast<float4*>(p.bullets_out) + tile_off;
+    float4* const list_in = v.bullets_in + tile_off;
+    float4* const list_out = v.bullets_out + tile_off;
 
     // ================= 1. this lane's game (rows already loaded: TileIn) ========================
     TL(0);
@@ -359,13 +383,13 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     float4 shv[2] = {in.shv[0], in.shv[1]};
     float sb[2] = {in.sb[0], in.sb[1]};
     int ctl[2];
-    if (p.actions) {
+    if (v.actions) {
         ctl[0] = (int)(in.ctl_raw & 0xffu);
         ctl[1] = S == 2 ? (int)(in.ctl_raw >> 8) : ctl[0];
     } else {
         uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
-        ctl[0] = action_from_key(h0, p.step, 0u);
-        ctl[1] = S == 2 ? action_from_key(h0, p.step, 1u) : ctl[0];
+        ctl[0] = action_from_key(h0, v.step, 0u);
+        ctl[1] = S == 2 ? action_from_key(h0, v.step, 1u) : ctl[0];
     }
     // What the END of the tick will need from memory is requested now, off the critical path: the
     // fire-schedule word of this game's tick and, with auto-reset, the planet count of the pool
@@ -517,7 +541,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
     // from its pool record at the end: pull the record towards L2 while the bullet loop runs.
     // (the pick is a few dozen integer instructions: only the rare lanes that need it work it out)
     if (auto_reset && active && (hits || tick >= (uint32_t)p.timeout_tick)) {
-        const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, p.step + 1u, (uint32_t)p.pool_size);
+        const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pool_rec + (size_t)k * 8));
     }
 
@@ -661,7 +685,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
                 // on the host): bullets cleared, tick 0; the per-slot episode counter is bumped with
                 // a fire-and-forget RED.
                 atomicAdd(&p.episode[g], 1u);
-                const uint32_t pool_k = pool_pick(p.seed, p.first_game + (uint32_t)g, p.step + 1u, (uint32_t)p.pool_size);
+                const uint32_t pool_k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size);
                 const float4* const pool_rec = p.pool_rec + (size_t)pool_k * 8;
                 float4 r[8];   // the 128-byte record: ships (5 floats each), planet count (word 10), planets (floats 16..31)
 #pragma unroll
@@ -722,12 +746,12 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
             for (unsigned k = 0; k < surv; k++) list_out[oexcl + k] = list_in[from + k];
         }
     }
-    if (p.reward) {
-        if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[1]);
-        else p.reward[g] = rw[0];
+    if (v.reward) {
+        if (S == 2) reinterpret_cast<float2*>(v.reward)[g] = make_float2(rw[0], rw[1]);
+        else v.reward[g] = rw[0];
     }
-    if (p.events) ST_STREAM(&p.events[g], (uint8_t)ev);
-    if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
+    if (v.events) ST_STREAM(&v.events[g], (uint8_t)ev);
+    if (v.done) v.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
 
     if (STATS) {
         // warp totals -> this warp's private slot row in HBM (no block barrier, no contention);
@@ -743,18 +767,29 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, TileScratch& t, c
 // One warp (= one CTA) per tile; the block scheduler balances the load.  (Persistent forms — static
 // tile striding, a device-side tile queue with the next tile's rows prefetched, a fully staged
 // software pipeline — were built and measured 12-48 % slower: profiles/r1_ab_v6_experiments.md.)
-template <int S, bool STATS>
+template <int S, bool STATS, bool MANY>
 __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
     __shared__ TileScratch s_tiles[kTickWarps];
     unsigned tile = (blockIdx.x * kTickThreads + threadIdx.x) >> 5;
     if ((int)(tile * 32u) >= p.n_games) return;  // whole warps: n_games % 32 == 0
 #if ASTRO_BOUSTROPHEDON
-    // Odd ticks walk the tiles backwards: what the previous tick wrote last — still in the 126 MB L2 — is
-    // read first, and rewritten there before it ever went to HBM.
+    // Odd launches walk the tiles backwards: what the previous launch wrote last — still in the 126 MB L2 —
+    // is read first, and rewritten there before it ever went to HBM.
     if (p.step & 1u) tile = ((unsigned)p.n_games >> 5) - 1u - tile;
 #endif
     const unsigned lane = threadIdx.x & 31u;
-    TileIn in;
-    load_tile_in<S>(p, tile, lane, in);
-    tick_tile<S, STATS>(p, s_tiles[threadIdx.x >> 5], lane, tile, in);
+    // n_fused consecutive ticks of this tile, back to back (astro_tick_many): games do not interact, so a
+    // tile can run ahead of the others; what tick k wrote is what tick k + 1 reads — from L2, not from HBM.
+    // The rows are lane-private; the bullet list is written by some lanes and read by others: the warp
+    // barrier orders those accesses.
+    // (MANY = false: the one-tick launch, without the loop around it — the loop form costs a single tick 6 %)
+#pragma unroll 1
+    for (unsigned k = 0; k < (MANY ? (unsigned)p.n_fused : 1u); k++) {
+        const TickVar v = tick_var<S>(p, MANY ? k : 0u);
+        TileIn in;
+        load_tile_in<S>(p, v, tile, lane, in);
+        tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in);
+        if (MANY) __syncwarp();   // (orders this tick's list stores before the next tick's requests; no fence: a fence
+                        // would hold the warp until its last stores are acknowledged, 10 % of a single tick)
+    }
 }

@@ -10,11 +10,15 @@ One "step" = one game tick (astro.core.step) of every game of the batch.  Worklo
 configs[3] shape, weak scaling): 1,048,576 duel games PER GPU, default planets (max_planets=4),
 uniform random controls, bullet pool K=32, finished games re-created from a 4,096-state pool built
 by core.create; the population is pre-rolled to its stationary bullet count before timing.  The
-per-tick working set (~0.35 GB) exceeds the 126 MB L2, so no flush is needed between steps.
+state (0.67 GB per GPU) and the controls exceed the 126 MB L2, so no flush is needed between steps.
 
 Numbers on the JSON line:
   value     whole-job env-steps/s, controls already resident in HBM (a ring of pre-generated
-            [games, 2] u8 arrays), events written to HBM; CUDA events, max over ranks.
+            [games, 2] u8 arrays, a different one every tick), every tick's events written to HBM;
+            CUDA events, max over ranks.  The ticks go through astro_tick_many, --fuse ticks per
+            launch: games do not interact, so the kernel runs the ticks of a tile back to back and
+            the state travels from one tick to the next through L2.  `per_tick_launch` is the same
+            loop as one launch per tick (what a policy in the loop needs).
   e2e       the same through BatchedGames.step_host(): pinned HOST controls in, events out,
             copies inside the timed region.
   roofline  algorithmic bytes of the tick kernel per launch (from the device counters of the timed
@@ -163,7 +167,9 @@ def workload_config(args):
                          % (args.games_per_gpu, args.pool),
                 games_per_gpu=args.games_per_gpu, bullet_cap=args.bullet_cap, reset_pool=args.pool,
                 preroll_ticks=args.preroll, state_precision='fp32 state, fp64-exact predicates',
-                l2_policy='per-tick working set (~0.35 GB/GPU) exceeds the 126 MB L2; no flush between steps',
+                ticks_per_launch=args.fuse,
+                l2_policy='state (0.67 GB/GPU) and controls exceed the 126 MB L2; no flush between steps; inside a launch the '
+                          'ticks of a tile run back to back, so a tile\'s state deliberately stays in L2 from one tick to the next',
                 parallelism='env-parallel shards, one process per GPU, NCCL only for the stats reduce')
 
 
@@ -199,18 +205,29 @@ def run_ours(args):
     torch.cuda.synchronize()
     flags |= args.timed_flags            # (experiment builds: bits that only apply after the pre-roll)
 
-    # ring of control arrays resident in HBM / in pinned host memory
-    R = 8
+    # ring of control arrays resident in HBM / in pinned host memory: R different arrays, one per tick
+    R = max(8, args.fuse)
     gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
     host_ring = torch.randint(0, 6, (R, games.n_pad, S), dtype=torch.uint8, generator=gen).pin_memory()
     dev_ring = host_ring.to(dev)
     ptrs = [dev_ring[i].data_ptr() for i in range(R)]
     events_host = torch.empty(games.n_pad, dtype=torch.uint8).pin_memory()
+    events_dev = torch.empty((R, games.n_pad), dtype=torch.uint8, device=dev)
+
+    def run_steps(k_steps):
+        """k_steps ticks, args.fuse per launch, tick k reading control array k % R; returns the launches."""
+        done, n_launch = 0, 0
+        while done < k_steps:
+            r0 = done % R
+            t = min(args.fuse, k_steps - done, R - r0)
+            games.step_many_raw(ptrs[r0], events_dev[r0].data_ptr(), t, flags)
+            done += t
+            n_launch += 1
+        return n_launch
 
     sampler = ClockSampler(local)
     sampler.start()
-    for k in range(args.warmup):
-        games.step_raw(ptrs[k % R], flags)
+    run_steps(args.warmup)
     games.stats_tensor(clear=True)
     launches0 = games.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -218,8 +235,7 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
-    for k in range(args.steps):
-        games.step_raw(ptrs[k % R], flags)
+    n_launches = run_steps(args.steps)
     st_t = games.stats_tensor(clear=True).clone()
     reduce_stats(st_t, dist)             # NCCL: the episode-statistics reduction, once per rollout
     e1.record()
@@ -240,8 +256,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
-        for k in range(args.steps):
-            games.step_raw(ptrs[k % R], flags)
+        run_steps(args.steps)
         r1.record()
         torch.cuda.synchronize()
         kern_ms = r0.elapsed_time(r1)
@@ -263,12 +278,31 @@ def run_ours(args):
     except Exception:
         pass
     roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic,
-                    kernel='tick_f32_kernel<2,true>', peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
-                    algorithmic_bytes_per_launch=alg / args.steps,
+                    kernel='tick_f32_kernel<2,true,%s>' % ('true' if args.fuse > 1 else 'false'),
+                    peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
+                    ticks_per_launch=args.steps / n_launches,
+                    algorithmic_bytes_per_launch=alg / n_launches,
                     bytes_per_env_step=alg / max(1, games_stats_local['env_steps']),
                     mean_planets=games_stats_local['planets_live'] / max(1, games_stats_local['env_steps']),
                     mean_bullets=games_stats_local['bullets_in'] / max(1, games_stats_local['env_steps']),
-                    avg_launch_us=1e3 * kern_ms / args.steps)
+                    avg_launch_us=1e3 * kern_ms / n_launches,
+                    note='algorithmic bytes = every live byte of state read and written once PER TICK; with several ticks '
+                         'of a tile per launch most of that traffic stays in L2 (traffic = DRAM bytes per launch, ncu)')
+
+    # the same loop as one launch per tick (a policy between the ticks needs this form)
+    pt_steps = max(R, min(args.steps, 400))
+    games.stats_tensor(clear=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(pt_steps):
+        games.step_raw(ptrs[k % R], flags)
+    e1.record()
+    torch.cuda.synchronize()
+    pt_ms = reduce_max(e0.elapsed_time(e1), dev, dist)
+    pt_stats = games.stats(clear=True)
+    per_tick = dict(value=world * n * pt_steps / (pt_ms * 1e-3), unit=UNIT, ms_per_step=pt_ms / pt_steps, steps=pt_steps,
+                    frac_of_hbm_peak=algorithmic_bytes(pt_stats, S) / (pt_ms * 1e-3) / 1e9 / peak,
+                    kernel='tick_f32_kernel<2,true,false>')
 
     # e2e: the public API with HOST buffers; every tick's controls are copied in from pinned host
     # memory and its events copied out, all inside the timed region (copies of neighbouring ticks
@@ -313,7 +347,7 @@ def run_ours(args):
                              d2h_bytes_per_step=games.n_pad, steps=e2e_steps,
                              api='BatchedGames.rollout_host -> astro_rollout_host (copies overlap the kernel)',
                              unpipelined_value=e2e_sync_value, unpipelined_api='BatchedGames.step_host -> astro_tick_host'),
-                    gpu_launches=launches,
+                    gpu_launches=launches, per_tick_launch=per_tick,
                     episode_stats={k: total[k] for k in ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'overflow')})
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -335,6 +369,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--ref-games', type=int, default=65536)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--fuse', type=int, default=32, help='ticks per launch of the timed loop (astro_tick_many); 1 = one launch per tick')
     ap.add_argument('--tick-flags', type=int, default=0, help='extra ASTRO_TICK_* bits (kernel A/B)')
     ap.add_argument('--timed-flags', type=int, default=0, help='extra tick bits after the pre-roll (experiment builds)')
     args = ap.parse_args()

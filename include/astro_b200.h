@@ -165,6 +165,16 @@ int astro_set_reset_pool(AstroBatch* b, const AstroResetPool* pool);
 int astro_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events,
                int32_t flags, void* stream);
 
+/* n_ticks consecutive astro_tick calls in as few launches as possible: actions u8 [n_ticks][n_games][S] (NULL ->
+ * counter stream), reward f32 [n_ticks][n_games][S], done / events u8 [n_ticks][n_games] (each may be NULL), all on
+ * the device.  Games do not interact, so the production kernel (precision 32) runs up to 64 ticks of a tile back to
+ * back inside one launch: what tick k wrote is what tick k+1 reads, from L2 instead of HBM, and there is no launch
+ * boundary between them.  Results are identical to n_ticks separate astro_tick calls.  This is the loop of core.play /
+ * rl.train (core.py:388-404) whenever the controls of a block of ticks do not depend on the states inside the block
+ * (replays, random or pre-computed exploration, the counter stream). */
+int astro_tick_many(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t n_ticks,
+                    int32_t flags, void* stream);
+
 /* Same call with HOST buffers (pinned for full speed): H2D actions, tick, D2H events (and
  * reward/done when not NULL), then synchronises the stream. */
 int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_host, uint8_t* done_host,

@@ -898,3 +898,43 @@ def test_policy_kernel_float64_state():
     with torch.no_grad():
         want = net(games.observe())
     assert float((q[:N] - want).abs().max()) <= 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('with_actions', [False, True])
+def test_tick_many_equals_tick_by_tick(with_actions):
+    """astro_tick_many (ticks of a tile back to back inside one launch, state handed on through L2) against the
+    same ticks as separate launches: every tick's events, rewards and done flags, the final state bit for bit and
+    the episode statistics — over fire ticks, deaths, re-creations and a launch boundary (70 ticks > 64 per launch)."""
+    import torch
+    cfg, N, K, T = core.DEFAULT_CONFIG, 4096, 32, 70
+    pool = H.make_pool(cfg, 512)
+    runs = []
+    for fused in (False, True):
+        g = _games(cfg, N, bullet_cap=K, precision=32, seed=5)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        for _ in range(40):                      # bullets in the air before the comparison starts
+            g.step(None, auto_reset=True)
+        g.stats(clear=True)
+        gen = torch.Generator(device='cpu').manual_seed(11)
+        acts = torch.randint(0, 6, (T, g.n_pad, 2), dtype=torch.uint8, generator=gen).cuda() if with_actions else None
+        ev = torch.zeros((T, g.n_pad), dtype=torch.uint8, device='cuda')
+        rw = torch.zeros((T, g.n_pad, 2), dtype=torch.float32, device='cuda')
+        dn = torch.zeros((T, g.n_pad), dtype=torch.uint8, device='cuda')
+        if fused:
+            g.step_many(T, acts, events=ev, reward=rw, done=dn, auto_reset=True)
+        else:
+            for k in range(T):
+                r, d, e = g.step(None if acts is None else acts[k], auto_reset=True)
+                ev[k], rw[k], dn[k] = e, r, d
+        runs.append((g.get_arrays(), ev.cpu().numpy(), rw.cpu().numpy(), dn.cpu().numpy(), g.stats()))
+    (a0, e0, r0, d0, s0), (a1, e1, r1, d1, s1) = runs
+    assert (e0 == e1).all() and (r0 == r1).all() and (d0 == d1).all()
+    assert s0 == s1 and s0['episodes'] > 1000 and s0['bullets_spawned'] > 10000
+    for k in ('n_bullets', 'n_planets', 'tick', 'episode', 'finished'):
+        assert (a0[k] == a1[k]).all(), k
+    assert H.same_bits(a0['ships'], a1['ships'])
+    pm = np.arange(4)[None, :] < a0['n_planets'][:, None]
+    bm = np.arange(K)[None, :] < a0['n_bullets'][:, None]
+    assert H.same_bits(a0['planets'][pm], a1['planets'][pm]) and H.same_bits(a0['bullets'][bm], a1['bullets'][bm])
