@@ -821,7 +821,7 @@ struct PolicyWeights {              // every matrix TRANSPOSED, [in][out]: lane 
 __device__ PolicyWeights g_pol;
 
 // x / (1 + |x|) with the fast reciprocal (2 ulp): the network's outputs stay within ~1e-6 of PyTorch's
-__device__ __forceinline__ float softsign(float x) { return __fdividef(x, 1.0f + fabsf(x)); }
+__device__ __forceinline__ float softsign(float x) { return div_fast_normal(x, 1.0f + fabsf(x)); }
 
 // One 32 -> 32 layer for two independent activation vectors held in shared memory (broadcast
 // LDS.128), this lane's weight row in registers as PAIRS (w[c], w[c+1]): each FFMA2 advances the even

@@ -267,7 +267,7 @@ __device__ __forceinline__ float grav_pair(f32x2 o, f32x2 xy, f32x2& acc, const 
     float s0, s1;
     upk2(mul2(q, q), s0, s1);
     const float d2 = __fadd_rn(s0, s1);
-    const float f = __fdividef(c.gm_f, fmaxf(1e-12f, d2));
+    const float f = div_fast_normal(c.gm_f, fmaxf(1e-12f, d2));
     acc = fma2(bc2(f), q, acc);
     return d2;
 }
@@ -527,7 +527,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 const f32x2 e = sub2(pxy[j], pxy[i]);
                 float s0, s1;
                 upk2(mul2(e, e), s0, s1);
-                const float fj = __fdividef(c.gm_f, fmaxf(1e-12f, __fadd_rn(s0, s1)));  // dead: 0, or e = 0
+                const float fj = div_fast_normal(c.gm_f, fmaxf(1e-12f, __fadd_rn(s0, s1)));  // dead: 0, or e = 0
                 q[i] = fma2(bc2(fj), e, q[i]);
                 q[j] = fma2(bc2(-fj), e, q[j]);
             }
