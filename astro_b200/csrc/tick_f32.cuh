@@ -358,9 +358,11 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar&
 }
 
 // One core.step for the 32 games of one tile, by one warp.
+// `next` receives what the following tick of the same tile would load from the rows this tick wrote (meta, ships,
+// bearings): inside a launch that runs several ticks they are handed on in registers.
 template <int S, bool STATS>
 __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratch& t, const unsigned lane,
-                                          const unsigned tile_index, const TileIn& in) {
+                                          const unsigned tile_index, const TileIn& in, TileIn& next) {
     using B4 = Body4<float>;
     const unsigned full = 0xffffffffu;
     const int g = (int)(tile_index * 32u + lane);
@@ -466,6 +468,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     TL(3);  // ships and planets have arrived
 #endif
     unsigned hits = 0;
+    next.shv[0] = shv[0]; next.shv[1] = shv[1];   // (finished games: rows untouched)
+    next.sb[0] = sb[0]; next.sb[1] = sb[1];
 #ifdef ASTRO_EXPERIMENTS
     // experiment builds only (flag 64): the tick's memory traffic without its arithmetic — every load
     // and store of a tick whose games neither move nor end (tools/ab_repeat.sh)
@@ -510,8 +514,10 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             hits |= h ? (1u << s) : 0u;
             const float th = (ctl[s] & 1) ? c.thrust_f : 0.f;
             acc = fma2(bc2(th), pk2(dirs[2 * s], dirs[2 * s + 1]), acc);
-            ST_STREAM(&ships[s * 32], advance_body2(sxy, pk2(shv[s].z, shv[s].w), acc, c));  // core.py:283-288
-            ST_STREAM(&ship_b[s * 32], __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]));
+            next.shv[s] = advance_body2(sxy, pk2(shv[s].z, shv[s].w), acc, c);  // core.py:283-288
+            next.sb[s] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
+            ST_STREAM(&ships[s * 32], next.shv[s]);
+            ST_STREAM(&ship_b[s * 32], next.sb[s]);
         }
         if (S == 2) {
             if (collide(shv[0].x, shv[0].y, shv[1].x, shv[1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
@@ -602,6 +608,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
 
     // ================= 5. terminal logic, spawn, bookkeeping ==========================================
     uint32_t ev = 0;
+    next.meta = meta;
     int m_out = 0, spawned = 0;
     unsigned surv = 0, n_born = 0;      // what this game contributes to the new list: survivors, then newborn
     float4 born[2];
@@ -676,7 +683,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 }
                 spawned = S;
             }
-            ST_STREAM(&p.meta[g], ASTRO_META_PACK(m, np, 0, tick + 1));
+            next.meta = ASTRO_META_PACK(m, np, 0, tick + 1);
+            ST_STREAM(&p.meta[g], next.meta);
             m_out = m;
         }
         if (ev & ASTRO_EV_DONE_MASK) {
@@ -691,18 +699,24 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
 #pragma unroll
                 for (int j = 0; j < 8; j++) r[j] = __ldg(&pool_rec[j]);
                 const int np_new = __float_as_int(r[2].z);
+                next.shv[0] = r[0];
+                next.sb[0] = r[1].x;
                 ships[0] = r[0];
                 ship_b[0] = r[1].x;
                 if (S == 2) {
-                    ships[32] = make_float4(r[1].y, r[1].z, r[1].w, r[2].x);
-                    ship_b[32] = r[2].y;
+                    next.shv[1] = make_float4(r[1].y, r[1].z, r[1].w, r[2].x);
+                    next.sb[1] = r[2].y;
+                    ships[32] = next.shv[1];
+                    ship_b[32] = next.sb[1];
                 }
 #pragma unroll
                 for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
                     if (j < np_new) planets[j * 32] = r[4 + j];
-                p.meta[g] = ASTRO_META_PACK(0, np_new, 0, 0);
+                next.meta = ASTRO_META_PACK(0, np_new, 0, 0);
+                p.meta[g] = next.meta;
             } else {
-                p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
+                next.meta = ASTRO_META_PACK(0, np, 1, tick);
+                p.meta[g] = next.meta;
             }
         }
     }
@@ -783,13 +797,26 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     // The rows are lane-private; the bullet list is written by some lanes and read by others: the warp
     // barrier orders those accesses.
     // (MANY = false: the one-tick launch, without the loop around it — the loop form costs a single tick 6 %)
+    TileIn in, next;
+    load_tile_in<S>(p, tick_var<S>(p, 0u), tile, lane, in);
 #pragma unroll 1
     for (unsigned k = 0; k < (MANY ? (unsigned)p.n_fused : 1u); k++) {
         const TickVar v = tick_var<S>(p, MANY ? k : 0u);
-        TileIn in;
-        load_tile_in<S>(p, v, tile, lane, in);
-        tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in);
-        if (MANY) __syncwarp();   // (orders this tick's list stores before the next tick's requests; no fence: a fence
-                        // would hold the warp until its last stores are acknowledged, 10 % of a single tick)
+        tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in, next);
+        if (MANY) {
+            // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
+            // well), so it starts its prefix sums and list requests at once; only the controls and the planet rows
+            // are loaded.  The warp barrier orders this tick's list stores before the next tick's requests (no
+            // fence: a fence would hold the warp until its last stores are acknowledged).
+            in = next;
+            in.ctl_raw = 0;
+            if (p.actions && k + 1u < (unsigned)p.n_fused) {
+                const size_t g = (size_t)tile * 32 + lane;
+                const uint8_t* a = p.actions + (size_t)(k + 1u) * (size_t)p.n_games * S;
+                in.ctl_raw = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(a)[g] : (uint32_t)a[g];
+            }
+            if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }
+            __syncwarp();
+        }
     }
 }
