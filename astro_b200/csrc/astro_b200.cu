@@ -1355,12 +1355,13 @@ int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* even
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)b->n_games, na = n * b->S;
-    // Ticks travel in chunks of C: one host->device copy brings the controls of C ticks, one device->host
-    // copy takes their events.  C = 1 by default: on the pool's B200 boxes larger copies are SLOWER end to
-    // end (1M games, e2e env-steps/s: C = 1 1.12e10, 2 1.07e10, 4 9.3e9, 8 7.5e9 — host->device copies
-    // of 16 MB run at 14 GB/s against 51 GB/s for 2 MB, tools/ubench/pcie.py).  ASTRO_ROLLOUT_CHUNK overrides.
+    // Ticks travel in chunks of C: the controls of C ticks are copied in (one copy per tick: 2 MB copies run at
+    // 51 GB/s on the pool's boxes, 16 MB ones at 14 — tools/ubench/pcie.py), the C ticks run as ONE launch
+    // (do_ticks: a tile's ticks back to back), their events are copied out.  1M games, 32 ticks per call, e2e
+    // env-steps/s: C = 1 1.42e10, 4 1.48e10, 8 1.35e10, 16 1.13e10 (the pipeline is two chunks deep: large
+    // chunks leave little to overlap within a call).  ASTRO_ROLLOUT_CHUNK overrides.
     static const int chunk_env = getenv("ASTRO_ROLLOUT_CHUNK") ? atoi(getenv("ASTRO_ROLLOUT_CHUNK")) : 0;
-    const int C = chunk_env > 0 ? chunk_env : 1;
+    const int C = chunk_env > 0 ? chunk_env : 4;
     if (b->pipe_ready && b->pipe_chunk != C) {
         for (int i = 0; i < 2; i++) {
             CUDA_TRY(cudaFree(b->d_actions2[i]));
@@ -1388,14 +1389,16 @@ int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* even
     for (int c = 0, k0 = 0; k0 < n_ticks; c++, k0 += C) {
         const int i = c & 1, kc = n_ticks - k0 < C ? n_ticks - k0 : C;
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(b->copy_in, b->ev_tick[i], 0));  // chunk c-2 has read buffer i
-        CUDA_TRY(cudaMemcpyAsync(b->d_actions2[i], actions_host + (size_t)k0 * na, na * kc, cudaMemcpyHostToDevice, b->copy_in));
+        for (int j = 0; j < kc; j++)   // (one copy per tick: 2 MB copies run at 51 GB/s on this pool, 16 MB ones at 14)
+            CUDA_TRY(cudaMemcpyAsync(b->d_actions2[i] + (size_t)j * na, actions_host + (size_t)(k0 + j) * na, na, cudaMemcpyHostToDevice, b->copy_in));
         CUDA_TRY(cudaEventRecord(b->ev_in[i], b->copy_in));
         CUDA_TRY(cudaStreamWaitEvent(st, b->ev_in[i], 0));
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_out[i], 0));  // events of chunk c-2 have left buffer i
         if (int r = do_ticks(b, b->d_actions2[i], nullptr, nullptr, b->d_events2[i], flags, st, kc)) return r;
         CUDA_TRY(cudaEventRecord(b->ev_tick[i], st));
         CUDA_TRY(cudaStreamWaitEvent(b->copy_out, b->ev_tick[i], 0));
-        CUDA_TRY(cudaMemcpyAsync(events_host + (size_t)k0 * n, b->d_events2[i], n * kc, cudaMemcpyDeviceToHost, b->copy_out));
+        for (int j = 0; j < kc; j++)
+            CUDA_TRY(cudaMemcpyAsync(events_host + (size_t)(k0 + j) * n, b->d_events2[i] + (size_t)j * n, n, cudaMemcpyDeviceToHost, b->copy_out));
         CUDA_TRY(cudaEventRecord(b->ev_out[i], b->copy_out));
     }
     CUDA_TRY(cudaStreamSynchronize(b->copy_out));

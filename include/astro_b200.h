@@ -181,9 +181,9 @@ int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_ho
                     uint8_t* events_host, int32_t flags, void* stream);
 
 /* n_ticks consecutive astro_tick_host calls as one pipelined stream: actions_host u8
- * [n_ticks][n_games][S], events_host u8 [n_ticks][n_games] (pinned).  The controls of tick k+1 are
- * copied in while tick k runs and the events of tick k-1 are copied out (two internal copy
- * streams, double-buffered staging; ASTRO_ROLLOUT_CHUNK=C moves C ticks per copy instead of one).  Returns when every event byte is on the host.  This is
+ * [n_ticks][n_games][S], events_host u8 [n_ticks][n_games] (pinned).  Ticks travel in chunks of 4: the
+ * controls of the next chunk are copied in while this chunk runs as one launch (astro_tick_many) and the events of
+ * the previous chunk are copied out (two internal copy streams, double-buffered staging; ASTRO_ROLLOUT_CHUNK overrides).  Returns when every event byte is on the host.  This is
  * the rollout loop of core.play / rl.train (core.py:388-404) for a host-side policy whose controls
  * for a block of ticks are known up front (replays, scripted or random play). */
 int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* events_host, int32_t n_ticks,
