@@ -307,15 +307,18 @@ def run_ours(args):
     # e2e: the public API with HOST buffers; every tick's controls are copied in from pinned host
     # memory and its events copied out, all inside the timed region (copies of neighbouring ticks
     # overlap the kernel: BatchedGames.rollout_host -> astro_rollout_host)
-    e2e_steps = max(R, (max(3, min(args.steps, args.e2e_steps)) // R) * R)
-    events_ring = torch.empty((R, games.n_pad), dtype=torch.uint8).pin_memory()
-    games.rollout_host(host_ring, events_ring, auto_reset=True)      # warm-up: R ticks
+    # (a call covers E ticks: E different control arrays in pinned host memory, E event arrays back)
+    E = max(R, (args.e2e_call // R) * R) if args.e2e_steps >= args.e2e_call else R
+    e2e_steps = max(E, (max(3, min(args.steps, args.e2e_steps)) // E) * E)
+    e2e_ring = host_ring if E == R else host_ring.repeat(E // R, 1, 1).pin_memory()
+    events_ring = torch.empty((E, games.n_pad), dtype=torch.uint8).pin_memory()
+    games.rollout_host(e2e_ring, events_ring, auto_reset=True)      # warm-up: E ticks
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
-    for k in range(e2e_steps // R):
-        games.rollout_host(host_ring, events_ring, auto_reset=True)
+    for k in range(e2e_steps // E):
+        games.rollout_host(e2e_ring, events_ring, auto_reset=True)
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = reduce_max(e0.elapsed_time(e1), dev, dist)
@@ -345,7 +348,7 @@ def run_ours(args):
                     cpu_baseline=cpu, clocks=clocks,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=games.n_pad * S,
                              d2h_bytes_per_step=games.n_pad, steps=e2e_steps,
-                             api='BatchedGames.rollout_host -> astro_rollout_host (copies overlap the kernel)',
+                             api='BatchedGames.rollout_host -> astro_rollout_host (copies overlap the kernel)', ticks_per_call=E,
                              unpipelined_value=e2e_sync_value, unpipelined_api='BatchedGames.step_host -> astro_tick_host'),
                     gpu_launches=launches, per_tick_launch=per_tick,
                     episode_stats={k: total[k] for k in ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'overflow')})
@@ -365,7 +368,8 @@ def main():
     ap.add_argument('--pool', type=int, default=4096)
     ap.add_argument('--preroll', type=int, default=600)
     ap.add_argument('--seed', type=int, default=0)
-    ap.add_argument('--e2e-steps', type=int, default=200)
+    ap.add_argument('--e2e-steps', type=int, default=256)
+    ap.add_argument('--e2e-call', type=int, default=128, help='ticks per rollout_host call of the e2e leg')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--ref-games', type=int, default=65536)
     ap.add_argument('--no-cpu-baseline', action='store_true')
