@@ -373,7 +373,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--ref-games', type=int, default=65536)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--fuse', type=int, default=32, help='ticks per launch of the timed loop (astro_tick_many); 1 = one launch per tick')
+    ap.add_argument('--fuse', type=int, default=64, help='ticks per launch of the timed loop (astro_tick_many); 1 = one launch per tick')
     ap.add_argument('--tick-flags', type=int, default=0, help='extra ASTRO_TICK_* bits (kernel A/B)')
     ap.add_argument('--timed-flags', type=int, default=0, help='extra tick bits after the pre-roll (experiment builds)')
     args = ap.parse_args()

@@ -872,6 +872,13 @@ def test_abi_errors_of_the_bot_and_create_entry_points():
     big = nat.AstroConfig()
     hh = C.c_void_p()
     assert L.astro_batch_create(C.byref(big), 1 << 26, 64, 32, 0, C.byref(hh)) == -1 and b'2^31' in L.astro_last_error()
+    # astro_tick_many / bullet buffer entry points
+    assert L.astro_tick_many(h, None, None, None, None, -1, 0, st) == -1 and b'n_ticks' in L.astro_last_error()
+    assert L.astro_tick_many(h, None, None, None, None, 3, nat.TICK_AUTO_RESET, st) == -3 and b'astro_set_reset_pool' in L.astro_last_error()
+    assert L.astro_tick_many(h, None, None, None, None, 0, 0, st) == 0                    # zero ticks: nothing to do
+    assert L.astro_bullet_buffer(h) == 0 and L.astro_set_bullet_buffer(h, 2) == -1
+    assert L.astro_tick_many(h, None, None, None, None, 3, 0, st) == 0 and L.astro_bullet_buffer(h) == 1   # odd count: flipped
+    assert L.astro_set_bullet_buffer(h, 0) == 0                                          # (all slots finished: the lists are empty)
     # a working call after the failures
     assert L.astro_script_controls(h, 0.1, 0.45, act.data_ptr(), st) == 0
     torch.cuda.synchronize()
@@ -898,6 +905,29 @@ def test_policy_kernel_float64_state():
     with torch.no_grad():
         want = net(games.observe())
     assert float((q[:N] - want).abs().max()) <= 2e-6
+
+
+def test_tick_many_solo_and_float64_fall_back_to_single_launches():
+    """astro_tick_many on the builds without the fused kernel (float64 state: one launch per tick inside the call) and on
+    solo games (S = 1 instantiation of the fused kernel): same outcome as separate ticks."""
+    import torch
+    for cfg, prec in ((core.DEFAULT_CONFIG, 64), (core.SOLO_CONFIG, 32)):
+        pool = H.make_pool(cfg, 256)
+        outs = []
+        for fused in (False, True):
+            g = _games(cfg, 1024, bullet_cap=32, precision=prec, seed=3)
+            g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+            g.reset_all()
+            ev = torch.zeros((40, g.n_pad), dtype=torch.uint8, device='cuda')
+            if fused:
+                g.step_many(40, None, events=ev, auto_reset=True)
+            else:
+                for k in range(40):
+                    ev[k] = g.step(None, auto_reset=True)[2]
+            outs.append((g.get_arrays(), ev.cpu().numpy(), g.stats()))
+        (a0, e0, s0), (a1, e1, s1) = outs
+        assert (e0 == e1).all() and s0 == s1 and s0['env_steps'] == 1024 * 40
+        assert H.same_bits(a0['ships'], a1['ships']) and (a0['tick'] == a1['tick']).all() and (a0['n_bullets'] == a1['n_bullets']).all()
 
 
 @pytest.mark.gpu
