@@ -862,8 +862,11 @@ __device__ __forceinline__ void layer2_t(const float* __restrict__ wt, int strid
     yb = b0 + b1;
 }
 
+#ifndef ASTRO_POL_MIN_BLOCKS
+#define ASTRO_POL_MIN_BLOCKS 4
+#endif
 template <typename R, int S>
-__global__ void __launch_bounds__(kPolWarps * 32, 4)
+__global__ void __launch_bounds__(kPolWarps * 32, ASTRO_POL_MIN_BLOCKS)
 policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_, const void* __restrict__ planets_,
               const void* __restrict__ bullets_, const uint32_t* __restrict__ meta_, uint8_t* __restrict__ actions,
               float* __restrict__ q_out, int n_games, int K, int nout, int ship_mask) {
@@ -1565,7 +1568,7 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
     {   // one resident wave: 4 CTAs of 128 threads per SM (128 registers per thread)
         int sms = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
-        if (grid > sms * 4) grid = sms * 4;
+        if (grid > sms * ASTRO_POL_MIN_BLOCKS) grid = sms * ASTRO_POL_MIN_BLOCKS;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;

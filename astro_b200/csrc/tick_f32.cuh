@@ -49,10 +49,6 @@ struct TileScratch {               // per warp
 };
 constexpr int kDrop = 0x40000000;
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -79,38 +75,6 @@ __device__ __forceinline__ ExactResult bullet_exact(float bx, float by, float bd
     r.y = (float)e1;
     r.flags = ((in_arena(e0, e1) && !gone) ? 1u : 0u) | (ship_hits << 1);
     return r;
-}
-
-__device__ __forceinline__ float dist2(float ax, float ay, float bx, float by) {
-    float d0 = __fsub_rn(ax, bx), d1 = __fsub_rn(ay, by);
-    return __fmaf_rn(d1, d1, __fmul_rn(d0, d0));
-}
-
-// One bullet against its game's staged frame.  Returns keep; b.x/b.y advanced; ship_hits
-// receives bits 0/1 when the bullet touches ship 0/1 (always decided in float64).
-// Arena test: keep iff (|x'| <= 1) or (|y'| <= 1)  <=>  min(|x'|, |y'|) <= 1, so only the
-// smaller magnitude can sit in the uncertainty band.
-template <int S>
-__device__ __forceinline__ bool bullet_step(Body4<float>& b, float4 sxy, float4 p01, float4 p23, const uint32_t* np_of,
-                                            unsigned gi, const Consts& c, unsigned& ship_hits) {  // np_of[g] >> 8 = np
-    float ds = dist2(sxy.x, sxy.y, b.x, b.y);
-    if (S == 2) ds = fminf(ds, dist2(sxy.z, sxy.w, b.x, b.y));
-    float dp = fminf(fminf(dist2(p01.x, p01.y, b.x, b.y), dist2(p01.z, p01.w, b.x, b.y)),
-                     fminf(dist2(p23.x, p23.y, b.x, b.y), dist2(p23.z, p23.w, b.x, b.y)));
-    float x0 = __fmaf_rn(c.dt_f, b.dx, b.x), x1 = __fmaf_rn(c.dt_f, b.dy, b.y);
-    float mn = fminf(fabsf(x0), fabsf(x1));
-    bool sure = (ds >= c.r2f_sb * 1.000001f) & (fabsf(dp - c.r2f_pb) > c.r2f_pb * 1e-6f) & (fabsf(mn - 1.0f) > 4e-6f);
-    bool keep = (mn <= 1.0f) & (dp >= c.r2f_pb);
-    if (__builtin_expect(!sure, 0)) {
-        ExactResult r = bullet_exact(b.x, b.y, b.dx, b.dy, sxy, p01, p23, S, (int)(np_of[gi] >> 8), c);
-        x0 = r.x;
-        x1 = r.y;
-        keep = r.flags & 1u;
-        ship_hits = r.flags >> 1;
-    }
-    b.x = x0;
-    b.y = x1;
-    return keep;
 }
 
 // ---- packed fp32 pairs ------------------------------------------------------------------------
@@ -168,7 +132,7 @@ __device__ __forceinline__ float min2(f32x2 v) {
 }
 
 // Squared distances of one point (bx, by) to two staged objects held TRANSPOSED, o = (x0, x1, y0, y1):
-// d^2 = fma(dy, dy, dx * dx) per object — the rounding sequence of dist2().
+// d^2 = fma(dy, dy, dx * dx) per object (one subtraction per axis, one product, one FMA).
 __device__ __forceinline__ f32x2 dist2_pair(float4 o, f32x2 bx, f32x2 by) {
     f32x2 dx = sub2(pk2(o.x, o.y), bx), dy = sub2(pk2(o.z, o.w), by);
     return fma2(dy, dy, mul2(dx, dx));
