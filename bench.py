@@ -337,7 +337,7 @@ def run_ours(args):
             threads = os.cpu_count() or 1
             n_cpu = 16384
             rate, _, _ = cpu_rollout_rate(n_cpu, 20, 40, threads)           # calibrate
-            ticks = int(max(50, min(20000, args.cpu_seconds * rate / n_cpu)))
+            ticks = int(max(50, min(100000, args.cpu_seconds * rate / n_cpu)))
             rate, dt, steps = cpu_rollout_rate(n_cpu, 20, ticks, threads)
             cpu = dict(value=rate, unit=UNIT, cores=threads, kind='port',
                        sample='%d games x %d ticks of the same workload (%.1f s), oracle C port of astro/core.py '
