@@ -446,6 +446,19 @@ def test_full_size_properties_1M_games():
     _, lo = run(half, 0)
     _, hi = run(half, half)
     assert bool((dig[:half] == lo).all()) and bool((dig[half:] == hi).all())
+    # the same 150 ticks through astro_tick_many (64 + 64 + 22 ticks per launch): every game's event history and the
+    # counters are those of 150 separate launches
+    import torch
+    fused = _games(cfg, N, bullet_cap=K, precision=32, seed=9, first_game=0)
+    fused.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    fused.reset_all()
+    ev = torch.empty((T, fused.n_pad), dtype=torch.uint8, device='cuda')
+    fused.step_many(T, None, events=ev, auto_reset=True)
+    acc = torch.zeros(N, dtype=torch.int64, device='cuda')
+    for k in range(T):
+        acc = acc * 31 + ev[k, :N].to(torch.int64) + 1
+    assert bool((acc == dig).all())
+    assert fused.stats() == st
 
 
 # ------------------------------------------------------------------ drop-in API (reference tests)
