@@ -766,19 +766,22 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
 #pragma unroll 1
     for (unsigned k = 0; k < (MANY ? (unsigned)p.n_fused : 1u); k++) {
         const TickVar v = tick_var<S>(p, MANY ? k : 0u);
+        // (several ticks per launch) the NEXT tick's controls are requested now — a different array every tick,
+        // straight from HBM — so that they have arrived when this tick is done
+        uint32_t ctl_next = 0;
+        if (MANY && p.actions && k + 1u < (unsigned)p.n_fused) {
+            const size_t g = (size_t)tile * 32 + lane;
+            const uint8_t* a = p.actions + (size_t)(k + 1u) * (size_t)p.n_games * S;
+            ctl_next = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(a)[g] : (uint32_t)a[g];
+        }
         tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in, next);
         if (MANY) {
             // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
-            // well), so it starts its prefix sums and list requests at once; only the controls and the planet rows
-            // are loaded.  The warp barrier orders this tick's list stores before the next tick's requests (no
-            // fence: a fence would hold the warp until its last stores are acknowledged).
+            // well), so it starts its prefix sums and list requests at once; only the planet rows are loaded.  The
+            // warp barrier orders this tick's list stores before the next tick's requests (no fence: a fence would
+            // hold the warp until its last stores are acknowledged).
             in = next;
-            in.ctl_raw = 0;
-            if (p.actions && k + 1u < (unsigned)p.n_fused) {
-                const size_t g = (size_t)tile * 32 + lane;
-                const uint8_t* a = p.actions + (size_t)(k + 1u) * (size_t)p.n_games * S;
-                in.ctl_raw = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(a)[g] : (uint32_t)a[g];
-            }
+            in.ctl_raw = ctl_next;
             if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }
             __syncwarp();
         }
