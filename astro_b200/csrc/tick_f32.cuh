@@ -325,8 +325,11 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar&
 // `next` receives what the following tick of the same tile would load from the rows this tick wrote (meta, ships,
 // bearings): inside a launch that runs several ticks they are handed on in registers.
 template <int S, bool STATS>
+// `last` = no further tick of this tile follows in this launch: only then do meta, ships and bearings go to memory
+// (planets and the bullet list always do), and the tile's statistics (`stat_acc`, summed over the launch's ticks).
 __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratch& t, const unsigned lane,
-                                          const unsigned tile_index, const TileIn& in, TileIn& next) {
+                                          const unsigned tile_index, const TileIn& in, TileIn& next, const bool last,
+                                          unsigned& stat_acc) {
     using B4 = Body4<float>;
     const unsigned full = 0xffffffffu;
     const int g = (int)(tile_index * 32u + lane);
@@ -480,8 +483,10 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             acc = fma2(bc2(th), pk2(dirs[2 * s], dirs[2 * s + 1]), acc);
             next.shv[s] = advance_body2(sxy, pk2(shv[s].z, shv[s].w), acc, c);  // core.py:283-288
             next.sb[s] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
-            ST_STREAM(&ships[s * 32], next.shv[s]);
-            ST_STREAM(&ship_b[s * 32], next.sb[s]);
+            if (last) {
+                ST_STREAM(&ships[s * 32], next.shv[s]);
+                ST_STREAM(&ship_b[s * 32], next.sb[s]);
+            }
         }
         if (S == 2) {
             if (collide(shv[0].x, shv[0].y, shv[1].x, shv[1].y, c.r2_ss, c.r2f_ss)) hits |= 3u;
@@ -648,7 +653,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 spawned = S;
             }
             next.meta = ASTRO_META_PACK(m, np, 0, tick + 1);
-            ST_STREAM(&p.meta[g], next.meta);
+            if (last) ST_STREAM(&p.meta[g], next.meta);
             m_out = m;
         }
         if (ev & ASTRO_EV_DONE_MASK) {
@@ -665,22 +670,26 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 const int np_new = __float_as_int(r[2].z);
                 next.shv[0] = r[0];
                 next.sb[0] = r[1].x;
-                ships[0] = r[0];
-                ship_b[0] = r[1].x;
+                if (last) {
+                    ships[0] = r[0];
+                    ship_b[0] = r[1].x;
+                }
                 if (S == 2) {
                     next.shv[1] = make_float4(r[1].y, r[1].z, r[1].w, r[2].x);
                     next.sb[1] = r[2].y;
-                    ships[32] = next.shv[1];
-                    ship_b[32] = next.sb[1];
+                    if (last) {
+                        ships[32] = next.shv[1];
+                        ship_b[32] = next.sb[1];
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
                     if (j < np_new) planets[j * 32] = r[4 + j];
                 next.meta = ASTRO_META_PACK(0, np_new, 0, 0);
-                p.meta[g] = next.meta;
+                if (last) p.meta[g] = next.meta;
             } else {
                 next.meta = ASTRO_META_PACK(0, np, 1, tick);
-                p.meta[g] = next.meta;
+                if (last) p.meta[g] = next.meta;
             }
         }
     }
@@ -734,9 +743,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     if (STATS) {
         // warp totals -> this warp's private slot row in HBM (no block barrier, no contention);
         // astro_stats() folds the rows
-        unsigned mine = warp_totals((int)lane, S, ev, active, spawned, np, nb, m_out);
-        unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
-        if (lane < ASTRO_N_STATS && mine) atomicAdd(slot, mine);  // RED: fire and forget
+        stat_acc += warp_totals((int)lane, S, ev, active, spawned, np, nb, m_out);
+        if (last) {
+            unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
+            if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(slot, stat_acc);  // RED: fire and forget
+        }
     }
     TL(7);
 }
@@ -762,6 +773,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     // barrier orders those accesses.
     // (MANY = false: the one-tick launch, without the loop around it — the loop form costs a single tick 6 %)
     TileIn in, next;
+    unsigned stat_acc = 0;
     load_tile_in<S>(p, tick_var<S>(p, 0u), tile, lane, in);
 #pragma unroll 1
     for (unsigned k = 0; k < (MANY ? (unsigned)p.n_fused : 1u); k++) {
@@ -774,7 +786,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
             const uint8_t* a = p.actions + (size_t)(k + 1u) * (size_t)p.n_games * S;
             ctl_next = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(a)[g] : (uint32_t)a[g];
         }
-        tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in, next);
+        tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc);
         if (MANY) {
             // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
             // well), so it starts its prefix sums and list requests at once; only the planet rows are loaded.  The
