@@ -291,6 +291,7 @@ struct TileIn {
     float4 shv[2];
     float sb[2];
     uint32_t ctl_raw;   // the tile's control bytes of this lane's game (S bytes), when actions are given
+    uint32_t fire_word; // (several ticks per launch) the fire-schedule word of this game's tick, requested at the top
 };
 template <int S, bool WARM_PLANETS = true>
 __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar& v, unsigned tile, unsigned lane, TileIn& in) {
@@ -329,7 +330,7 @@ template <int S, bool STATS>
 // (planets and the bullet list always do), and the tile's statistics (`stat_acc`, summed over the launch's ticks).
 __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratch& t, const unsigned lane,
                                           const unsigned tile_index, const TileIn& in, TileIn& next, const bool last,
-                                          unsigned& stat_acc) {
+                                          unsigned& stat_acc, const bool have_fire_word) {
     using B4 = Body4<float>;
     const unsigned full = 0xffffffffu;
     const int g = (int)(tile_index * 32u + lane);
@@ -606,7 +607,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             for (int s = 0; s < S; s++) rw[s] = c.reward_timeout;
         } else {
             surv = (unsigned)m;
-            const uint32_t fire_word = p.fire_bits[min(tick, (uint32_t)p.n_sched_ticks - 1u) >> 5];
+            const uint32_t fire_word = have_fire_word ? in.fire_word : p.fire_bits[min(tick, (uint32_t)p.n_sched_ticks - 1u) >> 5];
 #ifdef ASTRO_EXPERIMENTS
             const bool fire = !freeze && tick < (uint32_t)p.n_sched_ticks && ((fire_word >> (tick & 31)) & 1u);
 #else
@@ -786,7 +787,8 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
             const uint8_t* a = p.actions + (size_t)(k + 1u) * (size_t)p.n_games * S;
             ctl_next = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(a)[g] : (uint32_t)a[g];
         }
-        tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc);
+        if (MANY) in.fire_word = p.fire_bits[min(ASTRO_META_TICK(in.meta), (uint32_t)p.n_sched_ticks - 1u) >> 5];
+        tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
         if (MANY) {
             // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
             // well), so it starts its prefix sums and list requests at once; only the planet rows are loaded.  The
