@@ -23,7 +23,7 @@ EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro
            'astro_batch_bind', 'astro_set_schedule', 'astro_set_stream', 'astro_set_reset_pool',
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
            'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
-           'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer', 'astro_tick_many')
+           'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer', 'astro_tick_many', 'astro_explore_controls', 'astro_set_exploration')
 
 
 class AstroConfig(C.Structure):
@@ -47,8 +47,8 @@ class AstroCreateConfig(C.Structure):
                 ('max_planets', C.c_int32), ('reserved', C.c_int32)]
 
 
-BOT_STREAM, BOT_SCRIPT, BOT_POLICY, BOT_NOTHING = 0, 1, 2, 3
-BOT_MODES = {'stream': BOT_STREAM, 'random': BOT_STREAM, 'script': BOT_SCRIPT, 'policy': BOT_POLICY, 'nothing': BOT_NOTHING}
+BOT_STREAM, BOT_SCRIPT, BOT_POLICY, BOT_NOTHING, BOT_EXPLORE = 0, 1, 2, 3, 4
+BOT_MODES = {'stream': BOT_STREAM, 'random': BOT_STREAM, 'script': BOT_SCRIPT, 'policy': BOT_POLICY, 'nothing': BOT_NOTHING, 'explore': BOT_EXPLORE}
 
 
 class AstroError(RuntimeError):
@@ -80,6 +80,8 @@ def lib():
     L.astro_tick.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.astro_tick_host.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.astro_tick_many.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+    L.astro_explore_controls.argtypes = [vp, C.c_double, C.c_double, u32, vp, vp, i32, vp]
+    L.astro_set_exploration.argtypes = [vp, C.c_double, C.c_double, u32, vp]
     L.astro_rollout_host.argtypes = [vp, vp, vp, i32, i32, vp]
     L.astro_reset_done.argtypes = [vp, vp]
     L.astro_observe.argtypes = [vp, vp, i32, vp]

@@ -503,13 +503,36 @@ class BatchedGames:
                                                   mask, self._stream()))
         return out
 
+    def explore_controls(self, actions, state=None, t_in=1.0, t_out=0.1, seed=0, ships=None):
+        """`rl.EpsilonGreedy` (rl.py:10-30) laid over `actions` (uint8 cuda [n_pad, S], e.g. from policy_controls) the way
+        `rl.QBotTrainer.__call__` does (rl.py:249-258): where a ship's random policy is active its control replaces the
+        greedy one.  `state`: int32 cuda [n_pad, S] exploration state (created zeroed when None); returns it."""
+        torch = _torch()
+        if state is None:
+            state = torch.zeros((self.n_pad, self.S), dtype=torch.int32, device=self.device)
+        mask = sum(1 << int(k) for k in (range(self.S) if ships is None else ships))
+        nat.check(nat.lib().astro_explore_controls(self._h, float(t_in), float(t_out), int(seed) & 0xFFFFFFFF, state.data_ptr(),
+                                                   actions.data_ptr(), mask, self._stream()))
+        return state
+
+    def set_exploration(self, t_in=1.0, t_out=0.1, seed=0, state=None):
+        """Parameters and state of the 'explore' bots of rollout_device (the greedy network with rl.EpsilonGreedy laid
+        over it, rl.QBotTrainer's acting policy; the reference's t_in = 1.0, t_out = 0.1).  Returns the state tensor."""
+        torch = _torch()
+        if state is None:
+            state = torch.zeros((self.n_pad, self.S), dtype=torch.int32, device=self.device)
+        self._explore_state = state
+        nat.check(nat.lib().astro_set_exploration(self._h, float(t_in), float(t_out), int(seed) & 0xFFFFFFFF, state.data_ptr()))
+        return state
+
     # ---- whole game loops on the device -------------------------------------------------------------
     def rollout_device(self, n_ticks, bots=('stream', 'stream'), auto_reset=True, stats=True, avoid_distance=0.1,
                        avoid_threshold=0.45):
         """`n_ticks` of the play loop (core.play, core.py:377-410; rl.train's games, rl.py:350-374) for
         every game without the host between ticks.  bots: one of 'stream' (counter-stream random
         controls, both ships), 'script' (script.ScriptBot), 'policy' (greedy network loaded with
-        set_policy), 'nothing' (script.NothingBot) per ship.  Outcomes accumulate in stats()."""
+        set_policy), 'explore' (that network with rl.EpsilonGreedy laid over it: set_exploration), 'nothing'
+        (script.NothingBot) per ship.  Outcomes accumulate in stats()."""
         if isinstance(bots, str):
             bots = (bots,) * self.S
         modes = [nat.BOT_MODES[b] for b in bots] + [0]

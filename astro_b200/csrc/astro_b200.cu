@@ -988,6 +988,44 @@ policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
 }
 
 // ------------------------------------------------------------------------------------------
+// explore_kernel: rl.EpsilonGreedy.__call__ (rl.py:10-30) for every ship — the random policy that
+// rl.QBotTrainer lays over the greedy network (rl.py:249-258: action = greedy if greedy is not None
+// else argmax q).  Per ship a two-state process: idle -> a random control 0..4 (randint(0, 5): never 5)
+// when exp(-dt / t_in) < u, random control -> idle when exp(-dt / t_out) < u, one uniform u per call;
+// dt = state.t - the t of the previous call, so the first call of a new game (t back to 0: dt < 0)
+// never switches.  State per ship, caller-owned: (tick of the previous call) << 8 | (control + 1, 0 =
+// idle).  The reference draws from a numpy RandomState per bot; here u and the control come from the
+// counter stream keyed on (seed, global game, stream step, ship) — the same process, not the same
+// sequence (host twin: astro_b200/rng.py explore_step).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t explore_key(uint32_t seed, uint32_t game, uint32_t step, uint32_t ship) {
+    return mix32(mix32(seed ^ 0x3C6EF372u ^ (game * 0x9E3779B1u)) ^ (step * 2u + ship));
+}
+template <int S>
+__global__ void __launch_bounds__(128) explore_kernel(const uint32_t* __restrict__ meta_, int32_t* __restrict__ state,
+                                                      uint8_t* __restrict__ actions, int n_games, int ship_mask, double dt,
+                                                      double t_in, double t_out, uint32_t seed, uint32_t first_game, uint32_t step) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = idx / S, me = idx % S;
+    if (g >= n_games || !((ship_mask >> me) & 1)) return;
+    const uint32_t meta = meta_[g];
+    if (ASTRO_META_FINISHED(meta)) return;
+    const int tick = (int)ASTRO_META_TICK(meta);
+    const int32_t st = state[idx];
+    int policy = (st & 0xff) - 1;                     // -1 = idle
+    const double gap = __dmul_rn(dt, (double)(tick - (st >> 8)));
+    const uint32_t h = explore_key(seed, first_game + (uint32_t)g, step, (uint32_t)me);
+    const double u = (double)(h >> 8) * (1.0 / 16777216.0);
+    if (policy < 0) {
+        if (exp(-gap / t_in) < u) policy = (int)__umulhi(mix32(h ^ 0x85EBCA6Bu), 5u);
+    } else if (exp(-gap / t_out) < u) {
+        policy = -1;
+    }
+    state[idx] = (tick << 8) | (policy + 1);
+    if (policy >= 0) actions[idx] = (uint8_t)policy;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
@@ -1036,6 +1074,9 @@ struct AstroBatch {
     int64_t first_game;
     int64_t launches;
     int32_t policy_nout;  // > 0 once astro_policy_set_weights has been called
+    double explore_t_in, explore_t_out;   // astro_set_exploration (ASTRO_BOT_EXPLORE)
+    uint32_t explore_seed;
+    int32_t* explore_state;
     Consts c;
 };
 
@@ -1585,23 +1626,55 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
     return ASTRO_OK;
 }
 
+int astro_set_exploration(AstroBatch* b, double t_in, double t_out, uint32_t seed, int32_t* state) {
+    if (int r = check(b, false)) return r;
+    if (!state) return fail(ASTRO_E_INVALID, "null exploration state");
+    if (!(t_in > 0.0) || !(t_out > 0.0)) return fail(ASTRO_E_INVALID, "t_in and t_out must be positive");
+    b->explore_t_in = t_in;
+    b->explore_t_out = t_out;
+    b->explore_seed = seed;
+    b->explore_state = state;
+    return ASTRO_OK;
+}
+
+int astro_explore_controls(AstroBatch* b, double t_in, double t_out, uint32_t seed, int32_t* state, uint8_t* actions,
+                           int32_t ship_mask, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!state || !actions) return fail(ASTRO_E_INVALID, "null state / actions");
+    if (!(t_in > 0.0) || !(t_out > 0.0)) return fail(ASTRO_E_INVALID, "t_in and t_out must be positive");
+    CUDA_TRY(cudaSetDevice(b->device));
+    const int grid = (b->n_games * b->S + 127) / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b->S == 2)
+        explore_kernel<2><<<grid, 128, 0, st>>>(b->bufs.meta, state, actions, b->n_games, ship_mask, b->cfg.dt, t_in, t_out, seed,
+                                                (uint32_t)b->first_game, b->step);
+    else
+        explore_kernel<1><<<grid, 128, 0, st>>>(b->bufs.meta, state, actions, b->n_games, ship_mask, b->cfg.dt, t_in, t_out, seed,
+                                                (uint32_t)b->first_game, b->step);
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
 int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int32_t ship1_mode, double avoid_distance,
                          double avoid_threshold, uint8_t* actions, uint8_t* events, int32_t flags, void* stream) {
     if (int r = check(b, true)) return r;
     if (n_ticks < 0) return fail(ASTRO_E_INVALID, "n_ticks < 0");
     const int modes[2] = {ship0_mode, b->S == 2 ? ship1_mode : ship0_mode};
-    bool any_script = false, any_policy = false, any_stream = false, any_idle = false;
+    bool any_script = false, any_policy = false, any_stream = false, any_idle = false, any_explore = false;
     for (int k = 0; k < b->S; k++) {
-        if (modes[k] < ASTRO_BOT_STREAM || modes[k] > ASTRO_BOT_NOTHING) return fail(ASTRO_E_INVALID, "unknown bot mode %d", modes[k]);
+        if (modes[k] < ASTRO_BOT_STREAM || modes[k] > ASTRO_BOT_EXPLORE) return fail(ASTRO_E_INVALID, "unknown bot mode %d", modes[k]);
         any_stream |= modes[k] == ASTRO_BOT_STREAM;
         any_script |= modes[k] == ASTRO_BOT_SCRIPT;
-        any_policy |= modes[k] == ASTRO_BOT_POLICY;
+        any_policy |= modes[k] == ASTRO_BOT_POLICY || modes[k] == ASTRO_BOT_EXPLORE;
+        any_explore |= modes[k] == ASTRO_BOT_EXPLORE;
         any_idle |= modes[k] == ASTRO_BOT_NOTHING;
     }
     const bool all_stream = any_stream && !any_script && !any_policy && !any_idle;
     if (any_stream && !all_stream) return fail(ASTRO_E_INVALID, "ASTRO_BOT_STREAM drives every ship or none");
     if (!all_stream && !actions) return fail(ASTRO_E_INVALID, "a scratch actions buffer [n_games][S] is needed for bot modes");
     if (any_policy && b->policy_nout <= 0) return fail(ASTRO_E_STATE, "astro_policy_set_weights has not been called");
+    if (any_explore && !b->explore_state) return fail(ASTRO_E_STATE, "astro_set_exploration has not been called");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(b->device));
     if (any_idle) CUDA_TRY(cudaMemsetAsync(actions, 2, (size_t)b->n_games * b->S, st));  // script.NothingBot: control 2
@@ -1622,8 +1695,13 @@ int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int
         }
         if (any_policy) {
             int mask = 0;
-            for (int s = 0; s < b->S; s++) mask |= (modes[s] == ASTRO_BOT_POLICY) << s;
+            for (int s = 0; s < b->S; s++) mask |= (modes[s] == ASTRO_BOT_POLICY || modes[s] == ASTRO_BOT_EXPLORE) << s;
             if (int r = astro_policy_controls(b, actions, nullptr, mask, stream)) return r;
+        }
+        if (any_explore) {   // rl.QBotTrainer.__call__: the random policy, where active, replaces the greedy control
+            int mask = 0;
+            for (int s = 0; s < b->S; s++) mask |= (modes[s] == ASTRO_BOT_EXPLORE) << s;
+            if (int r = astro_explore_controls(b, b->explore_t_in, b->explore_t_out, b->explore_seed, b->explore_state, actions, mask, stream)) return r;
         }
         if (int r = do_tick(b, all_stream ? nullptr : actions, nullptr, nullptr, events, flags, st)) return r;
     }

@@ -66,3 +66,34 @@ def config_seeds(seed, count, skip=0):
     if skip:
         stream.randint(1 << 30, size=int(skip))
     return stream.randint(1 << 30, size=int(count)).astype(np.uint32)
+
+
+_EXPLORE_SALT = _U32(0x3C6EF372)
+_EXPLORE_PICK = _U32(0x85EBCA6B)
+
+
+def explore_step(seed, game_ids, step, ticks, state, dt, t_in, t_out, live=None):
+    """Host twin of csrc explore_kernel (rl.EpsilonGreedy.__call__, rl.py:10-30) for every ship.
+
+    state  int32 [n, S]: (tick of the previous call) << 8 | (control + 1), 0 = idle; updated in place
+    ticks  int   [n]: the games' tick counters; live bool [n] (finished games are skipped)
+    returns int64 [n, S]: the random control where a ship's random policy is active, else -1."""
+    g = np.asarray(game_ids, dtype=_U32)
+    n, S = state.shape
+    live = np.ones(n, dtype=bool) if live is None else np.asarray(live, dtype=bool)
+    out = np.full((n, S), -1, dtype=np.int64)
+    with np.errstate(over='ignore'):
+        base = mix32(_U32(seed) ^ _EXPLORE_SALT ^ (g * _GOLD))
+        for s in range(S):
+            h = mix32(base ^ _U32((int(step) * 2 + s) & 0xFFFFFFFF))
+            u = (h >> _U32(8)).astype(np.float64) * (1.0 / 16777216.0)
+            policy = (state[:, s] & 0xff) - 1
+            gap = dt * (np.asarray(ticks, dtype=np.int64) - (state[:, s] >> 8)).astype(np.float64)
+            enter = (policy < 0) & (np.exp(-gap / t_in) < u)
+            leave = (policy >= 0) & (np.exp(-gap / t_out) < u)
+            pick = _mulhi(mix32(h ^ _EXPLORE_PICK), 5)
+            policy = np.where(enter, pick, np.where(leave, -1, policy))
+            new_state = ((np.asarray(ticks, dtype=np.int64) << 8) | (policy + 1)).astype(np.int32)
+            state[:, s] = np.where(live, new_state, state[:, s])
+            out[:, s] = np.where(live, policy, -1)
+    return out

@@ -236,6 +236,19 @@ int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_thr
 int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n_floats, int32_t nout);
 int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t ship_mask, void* stream);
 
+/* rl.EpsilonGreedy.__call__ (rl.py:10-30) for every ship whose bit is set in ship_mask: the random policy that
+ * rl.QBotTrainer lays over the greedy network (rl.py:249-258).  Per ship a two-state process — idle -> a random
+ * control 0..4 when exp(-dt / t_in) < u, random control -> idle when exp(-dt / t_out) < u, dt = the game time since
+ * the previous call — whose draws come from the counter stream (seed, global game, stream step, ship) instead of a
+ * numpy RandomState per bot: the same process, not the same sequence.
+ *   state    i32 [n_games][S] device, caller-owned, zero-initialised: (tick of the previous call) << 8 | (control + 1)
+ *   actions  u8 [n_games][S] device: overwritten with the random control where a ship's random policy is active
+ * Call it after astro_policy_controls and before astro_tick (the reference's t_in = 1.0, t_out = 0.1). */
+int astro_explore_controls(AstroBatch* b, double t_in, double t_out, uint32_t seed, int32_t* state, uint8_t* actions,
+                           int32_t ship_mask, void* stream);
+/* The same parameters and state buffer for ASTRO_BOT_EXPLORE ships of astro_rollout_device. */
+int astro_set_exploration(AstroBatch* b, double t_in, double t_out, uint32_t seed, int32_t* state);
+
 /* n_ticks of a whole game loop without the host between ticks (core.play, core.py:377-410, and the
  * evaluation games of rl.train, rl.py:350-374, for N games at once): every tick the chosen bot of
  * each ship writes its control, then astro_tick runs.  Asynchronous; episode outcomes accumulate in
@@ -244,12 +257,15 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
  *               ASTRO_BOT_SCRIPT  script.ScriptBot        (astro_script_controls)
  *               ASTRO_BOT_POLICY  greedy rl.ValueNetwork  (astro_policy_controls)
  *               ASTRO_BOT_NOTHING script.NothingBot: control 2
+ *               ASTRO_BOT_EXPLORE the greedy network with rl.EpsilonGreedy laid over it, like rl.QBotTrainer
+ *                                 (astro_policy_controls, then astro_explore_controls; needs astro_set_exploration)
  *   actions     u8 [n_games][S] device scratch (may be NULL for ASTRO_BOT_STREAM); holds the last tick's controls
  *   events      u8 [n_games] device or NULL: the last tick's events */
 #define ASTRO_BOT_STREAM 0
 #define ASTRO_BOT_SCRIPT 1
 #define ASTRO_BOT_POLICY 2
 #define ASTRO_BOT_NOTHING 3
+#define ASTRO_BOT_EXPLORE 4
 int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int32_t ship1_mode, double avoid_distance,
                          double avoid_threshold, uint8_t* actions, uint8_t* events, int32_t flags, void* stream);
 

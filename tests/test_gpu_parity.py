@@ -814,7 +814,7 @@ def test_policy_rollout_equals_torch_rollout():
 # ------------------------------------------------------------------ whole game loops on the device
 
 @pytest.mark.parametrize('bots', [('script', 'script'), ('policy', 'script'), ('nothing', 'script'), ('policy', 'policy'),
-                                  ('stream', 'stream')])
+                                  ('stream', 'stream'), ('explore', 'script'), ('explore', 'explore')])
 def test_rollout_device_equals_tick_by_tick_loop(bots):
     """astro_rollout_device == the same loop driven from Python one call at a time: identical final
     state and statistics (the bot kernels write the controls the tick consumes, nothing else differs)."""
@@ -833,6 +833,7 @@ def test_rollout_device_equals_tick_by_tick_loop(bots):
         games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
         games.reset_all()
         games.set_policy(net)
+        xstate = games.set_exploration(1.0, 0.1, seed=5)
         if fused_loop:
             games.rollout_device(T, bots=bots)
         else:
@@ -844,9 +845,12 @@ def test_rollout_device_equals_tick_by_tick_loop(bots):
                 for s, b in enumerate(bots):
                     if b == 'nothing':
                         a[:, s] = 2
-                ships = [s for s, b in enumerate(bots) if b == 'policy']
+                ships = [s for s, b in enumerate(bots) if b in ('policy', 'explore')]
                 if ships:
                     games.policy_controls(out=a, ships=ships)
+                ships = [s for s, b in enumerate(bots) if b == 'explore']
+                if ships:
+                    games.explore_controls(a, xstate, 1.0, 0.1, seed=5, ships=ships)
                 games.step(a, auto_reset=True)
         out.append((games.get_arrays(), games.stats()))
     (xa, sa), (xb, sb) = out
@@ -981,3 +985,48 @@ def test_tick_many_equals_tick_by_tick(with_actions):
     pm = np.arange(4)[None, :] < a0['n_planets'][:, None]
     bm = np.arange(K)[None, :] < a0['n_bullets'][:, None]
     assert H.same_bits(a0['planets'][pm], a1['planets'][pm]) and H.same_bits(a0['bullets'][bm], a1['bullets'][bm])
+
+
+def test_explore_controls_match_host_twin_and_the_reference_process():
+    """astro_explore_controls (rl.EpsilonGreedy, rl.py:10-30, as rl.QBotTrainer lays it over the greedy control,
+    rl.py:249-258): every ship's state and control equal the host twin (astro_b200/rng.py explore_step, same counter
+    stream) tick by tick, through deaths and re-creations (dt < 0 on a new game's first call); and the process has
+    the reference's statistics: stationary active fraction p_in / (p_in + p_out) with p = 1 - exp(-dt / t), random
+    controls uniform on 0..4 (randint(0, 5) never draws 5)."""
+    import torch
+    cfg, N, T, seed = core.DEFAULT_CONFIG, 4096, 400, 7
+    pool = H.make_pool(cfg, 256)
+    g = _games(cfg, N, bullet_cap=32, precision=32, seed=2, first_game=1000)
+    g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    g.reset_all()
+    state = torch.zeros((g.n_pad, 2), dtype=torch.int32, device='cuda')
+    host_state = np.zeros((N, 2), dtype=np.int32)
+    ids = 1000 + np.arange(N)
+    active = 0
+    hist = np.zeros(6, dtype=np.int64)
+    entered = left = idle_calls = active_calls = 0
+    for k in range(T):
+        acts = torch.full((g.n_pad, 2), 2, dtype=torch.uint8, device='cuda')
+        arr_tick = (g.meta.cpu().numpy().view(np.uint32)[:N] >> 14).astype(np.int64)
+        before = (host_state & 0xff) - 1
+        ref = rng.explore_step(seed, ids, g.step_index, arr_tick, host_state, cfg.dt, 1.0, 0.1)
+        g.explore_controls(acts, state, t_in=1.0, t_out=0.1, seed=seed)
+        got = acts.cpu().numpy()[:N].astype(np.int64)
+        assert (got == np.where(ref >= 0, ref, 2)).all(), k
+        assert (state.cpu().numpy()[:N] == host_state).all(), k
+        active += int((ref >= 0).sum())
+        hist += np.bincount(ref[ref >= 0], minlength=6)
+        same_game = (arr_tick[:, None] > 0) | (k == 0)
+        idle_calls += int(((before < 0) & same_game).sum())
+        entered += int(((before < 0) & (ref >= 0) & same_game).sum())
+        active_calls += int(((before >= 0) & same_game).sum())
+        left += int(((before >= 0) & (ref < 0) & same_game).sum())
+        g.step(acts, auto_reset=True)
+    p_in, p_out = 1 - np.exp(-cfg.dt / 1.0), 1 - np.exp(-cfg.dt / 0.1)
+    assert abs(entered / idle_calls - p_in) < 0.1 * p_in and abs(left / active_calls - p_out) < 0.05 * p_out
+    frac = active / (N * 2 * T)
+    assert abs(frac - p_in / (p_in + p_out)) < 0.01, frac
+    assert hist[5] == 0 and hist[:5].min() > 0.9 * hist[:5].mean()
+    L = nat.lib()
+    assert L.astro_explore_controls(g._h, 0.0, 0.1, 0, state.data_ptr(), state.data_ptr(), 3, g._stream()) == -1
+    assert L.astro_explore_controls(g._h, 1.0, 0.1, 0, None, state.data_ptr(), 3, g._stream()) == -1
