@@ -587,8 +587,11 @@ __device__ __forceinline__ int fly_to(double target, double my_b, double t, bool
 // bit mask of the planets on a collision course; only those go through the atan2 / norm_angle
 // test, in planet order (the first dangerous planet decides, script.py:69-76), so the warp executes
 // that code as often as its worst lane needs it (usually once), from one copy of it.
+#ifndef ASTRO_SCRIPT_MIN_BLOCKS
+#define ASTRO_SCRIPT_MIN_BLOCKS 6   /* 80 registers: 41.1 -> 32.9 us per 262,144 games (the kernel waits on its loads: more warps) */
+#endif
 template <typename R, int S>
-__global__ void __launch_bounds__(128) script_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
+__global__ void __launch_bounds__(128, ASTRO_SCRIPT_MIN_BLOCKS) script_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
                                                      const void* __restrict__ planets_, const uint32_t* __restrict__ meta_,
                                                      uint8_t* __restrict__ actions, const __grid_constant__ ScriptParams q) {
     using B4 = Body4<R>;
