@@ -173,6 +173,26 @@ def workload_config(args):
                 parallelism='env-parallel shards, one process per GPU, NCCL only for the stats reduce')
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs NVML lists as local to its GPU, BEFORE the pinned host buffers are allocated
+    (first touch puts them on that NUMA node): the end-to-end leg moves 3 MB per tick and GPU through host memory,
+    and with several ranks per box a buffer on the far socket costs every copy a trip over the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < n_cpu}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -188,6 +208,7 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N>1)' % (args.gpus, world))
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
