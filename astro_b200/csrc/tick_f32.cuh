@@ -761,6 +761,12 @@ template <int S, bool STATS, bool MANY>
 __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
     __shared__ TileScratch s_tiles[kTickWarps];
     unsigned tile = (blockIdx.x * kTickThreads + threadIdx.x) >> 5;
+#if ASTRO_PDL
+    if (!MANY) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's CTAs may take the slots this grid frees
+        asm volatile("griddepcontrol.wait;" ::: "memory");                // ... and the previous kernel's stores are visible from here
+    }
+#endif
     if ((int)(tile * 32u) >= p.n_games) return;  // whole warps: n_games % 32 == 0
 #if ASTRO_BOUSTROPHEDON
     // Odd launches walk the tiles backwards: what the previous launch wrote last — still in the 126 MB L2 —
