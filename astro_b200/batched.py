@@ -340,9 +340,9 @@ class BatchedGames:
 
     def reset_done(self):
         """Re-create every finished game from the pool (entry = pick(seed, game, current step))."""
-        if self.n != self.n_pad:
-            raise ValueError('reset_done needs n_games to be a multiple of %d' % nat.TILE)
         nat.check(nat.lib().astro_reset_done(self._h, self._stream()))
+        if self.n != self.n_pad:
+            self.meta[self.n:] = 1 << 13      # the padding slots of the last tile stay finished (empty)
 
     def reset_all(self):
         """(Re)start every game from the pool: game g starts as pool[pick(seed, g, key 0)]."""

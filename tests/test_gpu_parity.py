@@ -1030,3 +1030,33 @@ def test_explore_controls_match_host_twin_and_the_reference_process():
     L = nat.lib()
     assert L.astro_explore_controls(g._h, 0.0, 0.1, 0, state.data_ptr(), state.data_ptr(), 3, g._stream()) == -1
     assert L.astro_explore_controls(g._h, 1.0, 0.1, 0, None, state.data_ptr(), 3, g._stream()) == -1
+
+
+@pytest.mark.parametrize('N,K', [(45, 3), (32, 1023), (7, 0), (1, 32)])
+def test_extreme_sizes_teacher_forced_and_fused(N, K):
+    """Ragged and extreme shapes: a game count that is not a multiple of the 32-game tile (padding slots stay finished),
+    one game, the largest bullet pool the meta word can count (K = 1023), no pool at all (K = 0: every newborn
+    overflows) — the same teacher-forced check against the oracle, and astro_tick_many against separate launches."""
+    import torch
+    cfg = core.DEFAULT_CONFIG
+    games, worst, n_done, n_fired = _teacher_forced(cfg, N, K, 90, 32, pool_size=64)
+    assert n_fired > 0
+    if K == 0:
+        assert games.stats()['overflow'] > 0 and games.stats()['bullets_out'] == 0
+    pool = H.make_pool(cfg, 64)
+    outs = []
+    for fused in (False, True):
+        g = _games(cfg, N, bullet_cap=K, precision=32, seed=1)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        ev = torch.zeros((70, g.n_pad), dtype=torch.uint8, device='cuda')
+        if fused:
+            g.step_many(70, None, events=ev, auto_reset=True)
+        else:
+            for k in range(70):
+                ev[k, :N] = g.step(None, auto_reset=True)[2]
+        outs.append((g.get_arrays(), ev.cpu().numpy()[:, :N], g.stats()))
+    (a0, e0, s0), (a1, e1, s1) = outs
+    assert (e0 == e1).all() and s0 == s1 and s0['env_steps'] == N * 70
+    for key in ('ships', 'n_bullets', 'n_planets', 'tick', 'episode'):
+        assert (a0[key] == a1[key]).all(), key
