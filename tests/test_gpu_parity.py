@@ -1060,3 +1060,33 @@ def test_extreme_sizes_teacher_forced_and_fused(N, K):
     assert (e0 == e1).all() and s0 == s1 and s0['env_steps'] == N * 70
     for key in ('ships', 'n_bullets', 'n_planets', 'tick', 'episode'):
         assert (a0[key] == a1[key]).all(), key
+
+
+def test_timeouts_inside_fused_launches():
+    """A short max_time (timeout on a game's 50th tick; ticks are per game, so re-created games time out at different
+    launch ticks): timeout terminal, its reward and the re-creation — against the oracle tick by tick, and the same
+    through astro_tick_many."""
+    import torch
+    cfg = core.DEFAULT_CONFIG._replace(max_time=1.0)
+    games, worst, n_done, n_fired = _teacher_forced(cfg, 256, 32, 130, 32, pool_size=64)
+    assert games.stats()['timeouts'] > 100
+    pool = H.make_pool(cfg, 64)
+    outs = []
+    for fused in (False, True):
+        g = _games(cfg, 256, bullet_cap=32, precision=32, seed=1)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        ev = torch.zeros((130, g.n_pad), dtype=torch.uint8, device='cuda')
+        rw = torch.zeros((130, g.n_pad, 2), dtype=torch.float32, device='cuda')
+        if fused:
+            g.step_many(130, None, events=ev, reward=rw, auto_reset=True)
+        else:
+            for k in range(130):
+                r, _, e = g.step(None, auto_reset=True)
+                ev[k], rw[k] = e, r
+        outs.append((g.get_arrays(), ev.cpu().numpy(), rw.cpu().numpy(), g.stats()))
+    (a0, e0, r0, s0), (a1, e1, r1, s1) = outs
+    assert (e0 == e1).all() and (r0 == r1).all() and s0 == s1 and s0['timeouts'] > 100
+    assert ((e0 & nat.EV_TIMEOUT) != 0).sum() == s0['timeouts']
+    for key in ('ships', 'n_bullets', 'tick', 'episode'):
+        assert (a0[key] == a1[key]).all(), key
