@@ -1090,3 +1090,45 @@ def test_timeouts_inside_fused_launches():
     assert ((e0 & nat.EV_TIMEOUT) != 0).sum() == s0['timeouts']
     for key in ('ships', 'n_bullets', 'tick', 'episode'):
         assert (a0[key] == a1[key]).all(), key
+
+
+def test_set_states_inside_live_tiles_keeps_the_other_games_lists():
+    """Writing single games into tiles that hold other games' bullets (the tile list is unpacked, edited and packed
+    again, batched.set_arrays): the other games are untouched, the written ones read back exactly, and the batch
+    ticks on from there like a batch built from scratch with the same states."""
+    cfg, N, K = core.DEFAULT_CONFIG, 96, 32
+    pool = H.make_pool(cfg, 64)
+    a = _games(cfg, N, bullet_cap=K, precision=32, seed=3)
+    a.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    a.reset_all()
+    for _ in range(60):
+        a.step(None, auto_reset=True)
+    before = a.get_arrays()
+    assert before['n_bullets'].sum() > 100
+    src, dst = [70, 71, 5], [3, 35, 36]
+    donors = a.get_states(src)
+    a.set_states(donors, index=dst)
+    after = a.get_arrays()
+    keep = np.ones(N, dtype=bool)
+    keep[dst] = False
+    live = np.arange(K)[None, :] < before['n_bullets'][:, None]
+    for key in ('ships', 'planets', 'n_bullets', 'n_planets', 'tick'):
+        assert (after[key][keep] == before[key][keep]).all(), key
+    assert (after['bullets'][keep][live[keep]] == before['bullets'][keep][live[keep]]).all()
+    for s, d in zip(src, dst):
+        assert (after['ships'][d] == before['ships'][s]).all() and after['n_bullets'][d] == before['n_bullets'][s]
+        nb = before['n_bullets'][s]
+        assert (after['bullets'][d, :nb] == before['bullets'][s, :nb]).all()
+        assert (after['planets'][d, :before['n_planets'][s]] == before['planets'][s, :before['n_planets'][s]]).all()
+    # a twin built from scratch with the same states ticks identically
+    b = _games(cfg, N, bullet_cap=K, precision=32, seed=3)
+    b.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    b.set_arrays(after['ships'], after['planets'], after['n_planets'], after['bullets'], after['n_bullets'], after['tick'])
+    b.set_stream(step=a.step_index)
+    for _ in range(30):
+        ea = a.step(None, auto_reset=False)[2].cpu().numpy()
+        eb = b.step(None, auto_reset=False)[2].cpu().numpy()
+        assert (ea == eb).all()
+    xa, xb = a.get_arrays(), b.get_arrays()
+    ok = ~xa['finished']
+    assert (xa['finished'] == xb['finished']).all() and (xa['ships'][ok] == xb['ships'][ok]).all() and (xa['n_bullets'][ok] == xb['n_bullets'][ok]).all()
