@@ -1204,7 +1204,7 @@ cudaError_t fold_stats(AstroBatch* b, cudaStream_t st) {
 // n_ticks consecutive ticks.  actions [n_ticks][n_games][S] (or NULL: counter stream), reward / done / events
 // [n_ticks][...] (or NULL).  The production fp32 kernel runs up to kMaxFused of them per launch, each tile
 // back to back (tick_f32_kernel); the generic / float64 kernels run one launch per tick.
-constexpr int kMaxFused = 64;
+constexpr int kMaxFused = 256;
 int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t flags,
              cudaStream_t st, int32_t n_ticks) {
     if (b->n_sched_ticks <= 0) return fail(ASTRO_E_STATE, "astro_set_schedule has not been called");

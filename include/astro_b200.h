@@ -167,7 +167,7 @@ int astro_tick(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* do
 
 /* n_ticks consecutive astro_tick calls in as few launches as possible: actions u8 [n_ticks][n_games][S] (NULL ->
  * counter stream), reward f32 [n_ticks][n_games][S], done / events u8 [n_ticks][n_games] (each may be NULL), all on
- * the device.  Games do not interact, so the production kernel (precision 32) runs up to 64 ticks of a tile back to
+ * the device.  Games do not interact, so the production kernel (precision 32) runs up to 256 ticks of a tile back to
  * back inside one launch: what tick k wrote is what tick k+1 reads, from L2 instead of HBM, and there is no launch
  * boundary between them.  Results are identical to n_ticks separate astro_tick calls.  This is the loop of core.play /
  * rl.train (core.py:388-404) whenever the controls of a block of ticks do not depend on the states inside the block

@@ -446,7 +446,7 @@ def test_full_size_properties_1M_games():
     _, lo = run(half, 0)
     _, hi = run(half, half)
     assert bool((dig[:half] == lo).all()) and bool((dig[half:] == hi).all())
-    # the same 150 ticks through astro_tick_many (64 + 64 + 22 ticks per launch): every game's event history and the
+    # the same 150 ticks through astro_tick_many (one launch): every game's event history and the
     # counters are those of 150 separate launches
     import torch
     fused = _games(cfg, N, bullet_cap=K, precision=32, seed=9, first_game=0)
@@ -952,9 +952,9 @@ def test_tick_many_solo_and_float64_fall_back_to_single_launches():
 def test_tick_many_equals_tick_by_tick(with_actions):
     """astro_tick_many (ticks of a tile back to back inside one launch, state handed on through L2) against the
     same ticks as separate launches: every tick's events, rewards and done flags, the final state bit for bit and
-    the episode statistics — over fire ticks, deaths, re-creations and a launch boundary (70 ticks > 64 per launch)."""
+    the episode statistics — over fire ticks, deaths, re-creations and a launch boundary (270 ticks > 256 per launch)."""
     import torch
-    cfg, N, K, T = core.DEFAULT_CONFIG, 4096, 32, 70
+    cfg, N, K, T = core.DEFAULT_CONFIG, 4096, 32, 270
     pool = H.make_pool(cfg, 512)
     runs = []
     for fused in (False, True):
