@@ -6,24 +6,26 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('ASTRO_B200_LIB') or os.path.join(HERE, 'libastro_b200.so')   # env: A/B builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 TILE = 32
 MAX_PLANETS = 4
 MAX_BULLET_CAP = 1023
 MAX_TICKS = 262143
-N_STATS = 12
+SINCOS_RANGE = 71476       # |bearing| over which util.direction (numpy float32 sin/cos) is reproduced bit for bit
+N_STATS = 13
 STAT_NAMES = ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'env_steps', 'bullets_spawned',
-              'overflow', 'planets_live', 'bullets_in', 'bullets_out', 'skipped')
+              'overflow', 'planets_live', 'bullets_in', 'bullets_out', 'skipped', 'bad_controls')
 
-EV_HIT0, EV_HIT1, EV_TIMEOUT, EV_FIRED, EV_OVERFLOW, EV_SKIPPED = 1, 2, 4, 8, 16, 32
+EV_HIT0, EV_HIT1, EV_TIMEOUT, EV_FIRED, EV_OVERFLOW, EV_SKIPPED, EV_BAD_CONTROL = 1, 2, 4, 8, 16, 32, 64
 EV_DONE_MASK = 7
-TICK_AUTO_RESET, TICK_NO_STATS, TICK_GENERIC_KERNEL = 1, 2, 4
+TICK_AUTO_RESET, TICK_NO_STATS, TICK_GENERIC_KERNEL, TICK_CREATE_DTYPES, TICK_ALL_CREATE_DTYPES = 1, 2, 4, 8, 16
 
 EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro_batch_destroy',
            'astro_batch_bind', 'astro_set_schedule', 'astro_set_stream', 'astro_set_reset_pool',
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
            'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
-           'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer', 'astro_tick_many', 'astro_explore_controls', 'astro_set_exploration')
+           'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer', 'astro_tick_many', 'astro_explore_controls', 'astro_set_exploration',
+           'astro_export_games', 'astro_import_games', 'astro_single_game_bytes', 'astro_step_single_host')
 
 
 class AstroConfig(C.Structure):
@@ -45,6 +47,19 @@ class AstroResetPool(C.Structure):
 class AstroCreateConfig(C.Structure):
     _fields_ = [('inner_ship_position', C.c_double), ('outer_ship_position', C.c_double), ('planet_orbit', C.c_double),
                 ('max_planets', C.c_int32), ('reserved', C.c_int32)]
+
+
+class AstroGameArrays(C.Structure):
+    _fields_ = [('ships', C.c_void_p), ('planets', C.c_void_p), ('bullets', C.c_void_p), ('n_planets', C.c_void_p),
+                ('n_bullets', C.c_void_p), ('tick', C.c_void_p), ('finished', C.c_void_p), ('episode', C.c_void_p),
+                ('bullet_rows', C.c_int32), ('reserved', C.c_int32)]
+
+
+class AstroSingleGame(C.Structure):
+    _fields_ = [('ships', C.c_double * 5 * 2), ('planets', C.c_double * 4 * MAX_PLANETS),
+                ('n_planets', C.c_int32), ('n_bullets', C.c_int32), ('tick', C.c_int32), ('reserved', C.c_int32),
+                ('episode', C.c_uint32), ('finished', C.c_uint8 * 4), ('control', C.c_uint8 * (TILE * 2)),
+                ('events', C.c_uint8 * TILE)]
 
 
 BOT_STREAM, BOT_SCRIPT, BOT_POLICY, BOT_NOTHING, BOT_EXPLORE = 0, 1, 2, 3, 4
@@ -92,6 +107,11 @@ def lib():
     L.astro_rollout_device.argtypes = [vp, i32, i32, i32, C.c_double, C.c_double, vp, vp, i32, vp]
     L.astro_create_games.argtypes = [vp, C.POINTER(AstroCreateConfig), vp, i32, vp, vp, vp, vp]
     L.astro_script_controls.argtypes = [vp, C.c_double, C.c_double, vp, vp]
+    L.astro_export_games.argtypes = [vp, vp, i32, C.POINTER(AstroGameArrays), vp]
+    L.astro_import_games.argtypes = [vp, vp, i32, C.POINTER(AstroGameArrays), vp]
+    L.astro_single_game_bytes.argtypes = [i32]
+    L.astro_single_game_bytes.restype = i64
+    L.astro_step_single_host.argtypes = [vp, vp, vp, i32, vp]
     L.astro_bullet_buffer.argtypes = [vp]
     L.astro_set_bullet_buffer.argtypes = [vp, i32]
     L.astro_launch_count.argtypes = [vp]

@@ -114,48 +114,42 @@ class BatchedGames:
         """Which half of `self.bullets` holds the tile lists now (flips every tick)."""
         return int(nat.lib().astro_bullet_buffer(self._h))
 
-    def _tile_counts(self, tiles):
-        """Bullet counts [m, 32] of the listed tiles (finished games own none) and each game's first list item."""
-        meta = self.meta.view(self.n_tiles, nat.TILE)[tiles].to(_torch().int64) & 0xFFFFFFFF
-        nb = (meta & 1023) * (1 - ((meta >> 13) & 1))
-        return nb, nb.cumsum(1) - nb
-
-    def _unpack_tiles(self, tiles):
-        """The bullet lists of the listed tiles as padded game-major rows [m, 32, K, 4] (dead slots 0)
-        and the counts [m, 32]."""
+    def _game_arrays(self, m, rows, episode=True):
+        """Device tensors in the AstroGameArrays layout (float64, game-major) and the ctypes view of them."""
         torch = _torch()
-        K, m = max(self.K, 1), int(tiles.numel())
-        nb, first = self._tile_counts(tiles)
-        k = torch.arange(K, device=self.device)
-        idx = (first[:, :, None] + k).clamp_(max=32 * K - 1).reshape(m, 32 * K)
-        lists = self.bullets[self.bullet_buffer][tiles]                              # [m, 32K, 4]
-        rows = torch.gather(lists, 1, idx[:, :, None].expand(-1, -1, 4)).reshape(m, 32, K, 4)
-        return torch.where((k < nb[:, :, None])[..., None], rows, torch.zeros((), dtype=rows.dtype, device=self.device)), nb
+        dev, f64, i32 = self.device, torch.float64, torch.int32
+        t = dict(ships=torch.empty((m, self.S, 5), dtype=f64, device=dev),
+                 planets=torch.empty((m, nat.MAX_PLANETS, 4), dtype=f64, device=dev),
+                 bullets=torch.empty((m, max(rows, 1), 4), dtype=f64, device=dev),
+                 n_planets=torch.empty((m,), dtype=i32, device=dev), n_bullets=torch.empty((m,), dtype=i32, device=dev),
+                 tick=torch.empty((m,), dtype=i32, device=dev), finished=torch.empty((m,), dtype=torch.uint8, device=dev),
+                 episode=torch.empty((m,), dtype=i32, device=dev) if episode else None)
+        return t, self._arrays_struct(t, rows)
 
-    def _pack_tiles(self, tiles, rows, nb):
-        """Inverse of _unpack_tiles: writes the dense lists of the listed tiles (current buffer)."""
+    @staticmethod
+    def _arrays_struct(t, rows):
+        ptr = lambda x: None if x is None else x.data_ptr()
+        return nat.AstroGameArrays(ptr(t['ships']), ptr(t['planets']), ptr(t['bullets']), ptr(t['n_planets']), ptr(t['n_bullets']),
+                                   ptr(t['tick']), ptr(t['finished']), ptr(t.get('episode')), int(rows), 0)
+
+    def _index_tensor(self, index):
         torch = _torch()
-        K, m = max(self.K, 1), int(tiles.numel())
-        first = nb.cumsum(1) - nb
-        k = torch.arange(K, device=self.device)
-        live = k < nb[:, :, None]                                                    # [m, 32, K]
-        dst = (torch.arange(m, device=self.device)[:, None, None] * (32 * K) + first[:, :, None] + k)[live]
-        lists = torch.zeros((m * 32 * K, 4), dtype=self.rdtype, device=self.device)
-        lists[dst] = rows[live]
-        self.bullets[self.bullet_buffer][tiles] = lists.view(m, 32 * K, 4)
+        idx = np.asarray(index, dtype=np.int64).reshape(-1)
+        if idx.size and (idx.min() < 0 or idx.max() >= self.n_pad):
+            raise IndexError('game index out of range 0..%d' % (self.n_pad - 1))
+        return idx, torch.from_numpy(idx.astype(np.int32)).to(self.device)
 
     def set_arrays(self, ships, planets, n_planets, bullets=None, n_bullets=None, ticks=None, index=None,
-                   episode=None):
+                   episode=None, finished=None):
         """Load games from game-major host arrays: ships [m,S,5] (x,y,dx,dy,b), planets [m,4,4],
-        n_planets [m], bullets [m,<=K,4], n_bullets [m], ticks [m] (default 0)."""
+        n_planets [m], bullets [m,<=K,4], n_bullets [m], ticks [m] (default 0) — ONE kernel
+        (astro_import_games): the touched tiles' bullet lists are rebuilt on the device, every other
+        game keeps its state."""
         torch = _torch()
-        ships = np.asarray(ships, dtype=self.np_rdtype)
-        m = ships.shape[0]
-        index = np.arange(m) if index is None else np.asarray(index)
-        tiles, lanes = self._split(index)
         dev = self.device
-        tt, ll = torch.from_numpy(tiles).to(dev), torch.from_numpy(lanes).to(dev)
-        planets = np.asarray(planets, dtype=self.np_rdtype)
+        ships = np.ascontiguousarray(ships, dtype=np.float64)
+        m = ships.shape[0]
+        planets = np.ascontiguousarray(planets, dtype=np.float64)
         n_planets = np.asarray(n_planets, dtype=np.int64)
         n_bullets = np.zeros(m, dtype=np.int64) if n_bullets is None else np.asarray(n_bullets, dtype=np.int64)
         ticks = np.zeros(m, dtype=np.int64) if ticks is None else np.asarray(ticks, dtype=np.int64)
@@ -163,27 +157,28 @@ class BatchedGames:
             raise ValueError('a state holds more bullets than bullet_cap=%d' % self.K)
         if ticks.max(initial=0) > nat.MAX_TICKS:
             raise ValueError('tick counter out of range')
-        self.ships[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(ships[:, :, :4])).to(dev)
-        self.ship_b[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(ships[:, :, 4])).to(dev)
-        self.planets[tt, :, ll] = torch.from_numpy(np.ascontiguousarray(planets)).to(dev)
-        # bullets: the lists of the touched tiles are unpacked, the listed games replaced, and packed again
-        ut, inv = np.unique(tiles, return_inverse=True)
-        ut_t, inv_t = torch.from_numpy(ut).to(dev), torch.from_numpy(inv.astype(np.int64)).to(dev)
-        rows, nb_t = self._unpack_tiles(ut_t)
-        new_rows = torch.zeros((m, max(self.K, 1), 4), dtype=self.rdtype, device=dev)
-        if bullets is not None and self.K > 0:
-            bullets = np.asarray(bullets, dtype=self.np_rdtype)
-            kb = bullets.shape[1]
-            if kb:
-                new_rows[:, :kb] = torch.from_numpy(np.ascontiguousarray(bullets)).to(dev)
-        rows[inv_t, ll] = new_rows
-        nb_t[inv_t, ll] = torch.from_numpy(n_bullets).to(dev)
-        meta = (n_bullets | (n_planets << 10) | (ticks << 14)).astype(np.uint32).view(np.int32)
-        self.meta[torch.from_numpy(index.astype(np.int64)).to(dev)] = torch.from_numpy(meta).to(dev)
-        self._pack_tiles(ut_t, rows, nb_t)
-        if episode is not None:
-            ep = np.asarray(episode, dtype=np.uint32).view(np.int32)
-            self.episode[torch.from_numpy(index.astype(np.int64)).to(dev)] = torch.from_numpy(ep).to(dev)
+        if m and not (np.abs(ships[:, :, 4]) <= nat.SINCOS_RANGE).all():
+            raise ValueError('a bearing lies beyond the +-%d rad over which util.direction is reproduced' % nat.SINCOS_RANGE)
+        rows = int(n_bullets.max(initial=0))
+        bl = np.zeros((m, max(rows, 1), 4))
+        if bullets is not None and rows:
+            bl[:, :rows] = np.asarray(bullets, dtype=np.float64)[:, :rows]
+        t = dict(ships=torch.from_numpy(ships).to(dev), planets=torch.from_numpy(planets).to(dev),
+                 bullets=torch.from_numpy(bl).to(dev),
+                 n_planets=torch.from_numpy(n_planets.astype(np.int32)).to(dev),
+                 n_bullets=torch.from_numpy(n_bullets.astype(np.int32)).to(dev),
+                 tick=torch.from_numpy(ticks.astype(np.int32)).to(dev),
+                 finished=None if finished is None else torch.from_numpy(np.asarray(finished, dtype=np.uint8)).to(dev),
+                 episode=None if episode is None else torch.from_numpy(np.asarray(episode, dtype=np.uint32).view(np.int32).copy()).to(dev))
+        arrays = self._arrays_struct(t, rows)
+        if index is None:
+            idx_t = None
+        else:
+            idx, idx_t = self._index_tensor(index)
+            if idx.size != m or np.unique(idx).size != m:
+                raise ValueError('index must list %d distinct games' % m)
+        nat.check(nat.lib().astro_import_games(self._h, None if idx_t is None else idx_t.data_ptr(), m, C.byref(arrays), self._stream()))
+        _torch().cuda.current_stream(self.device).synchronize()   # the staging tensors die with this frame
 
     def set_states(self, states, index=None, ticks=None):
         """Load reference `State`s (core.py:15-18).  Without `ticks`, each state's (reload, t) must
@@ -221,68 +216,50 @@ class BatchedGames:
             tk[:] = ticks
         self.set_arrays(ships, planets, n_planets, bullets, n_bullets, tk, index)
 
-    def get_arrays(self):
-        """Whole batch as game-major float64 host arrays (the inverse of set_arrays)."""
-        n = self.n
-        meta = self.meta.cpu().numpy().view(np.uint32)[:n]
-        sh = self.ships.permute(0, 2, 1, 3).reshape(self.n_pad, self.S, 4)[:n].double().cpu().numpy()
-        sb = self.ship_b.permute(0, 2, 1).reshape(self.n_pad, self.S)[:n].double().cpu().numpy()
-        pl = self.planets.permute(0, 2, 1, 3).reshape(self.n_pad, nat.MAX_PLANETS, 4)[:n].double().cpu().numpy()
-        rows, _ = self._unpack_tiles(_torch().arange(self.n_tiles, device=self.device))
-        bl = rows.reshape(self.n_pad, max(self.K, 1), 4)[:n, :self.K].double().cpu().numpy()
-        return dict(ships=np.concatenate([sh, sb[:, :, None]], axis=2), planets=pl, bullets=bl,
-                    n_bullets=(meta & 1023).astype(np.int32), n_planets=((meta >> 10) & 7).astype(np.int32),
-                    finished=((meta >> 13) & 1).astype(bool), tick=(meta >> 14).astype(np.int64),
-                    episode=self.episode.cpu().numpy().view(np.uint32)[:n].copy())
+    def export_arrays(self, index=None, rows=None):
+        """Games `index` (default: all) as game-major float64 DEVICE tensors, one kernel (astro_export_games)."""
+        if index is None:
+            m, idx_t = self.n, None
+        else:
+            idx, idx_t = self._index_tensor(index)
+            m = idx.size
+        rows = self.K if rows is None else int(rows)
+        t, arrays = self._game_arrays(m, rows)
+        nat.check(nat.lib().astro_export_games(self._h, None if idx_t is None else idx_t.data_ptr(), m, C.byref(arrays), self._stream()))
+        if idx_t is not None:
+            _torch().cuda.current_stream(self.device).synchronize()   # the index tensor dies with this frame
+        return t
+
+    def get_arrays(self, index=None):
+        """Whole batch (or the listed games) as game-major float64 host arrays (the inverse of set_arrays)."""
+        t = self.export_arrays(index)
+        K = self.K
+        return dict(ships=t['ships'].cpu().numpy(), planets=t['planets'].cpu().numpy(), bullets=t['bullets'].cpu().numpy()[:, :K],
+                    n_bullets=t['n_bullets'].cpu().numpy(), n_planets=t['n_planets'].cpu().numpy(),
+                    finished=t['finished'].cpu().numpy().astype(bool), tick=t['tick'].cpu().numpy().astype(np.int64),
+                    episode=t['episode'].cpu().numpy().view(np.uint32).copy())
+
+    def get_states(self, indices):
+        """Reference `State`s (or None for finished games) of the listed games only — the read path of
+        logs.GameRecorder and of the drop-in core.play."""
+        a = self.get_arrays(np.asarray(indices, dtype=np.int64).reshape(-1))
+        out = []
+        for j in range(a['tick'].shape[0]):
+            if a['finished'][j]:
+                out.append(None)
+                continue
+            nb, npl, tick = int(a['n_bullets'][j]), int(a['n_planets'][j]), int(a['tick'][j])
+            sh, pl, bl = a['ships'][j], a['planets'][j], a['bullets'][j]
+            out.append(core.State(
+                ships=core.Bodies(x=sh[:, 0:2].copy(), dx=sh[:, 2:4].copy(), b=sh[:, 4].copy()),
+                planets=core.Bodies(x=pl[:npl, 0:2].copy(), dx=pl[:npl, 2:4].copy(), b=None),
+                bullets=core.Bodies(x=bl[:nb, 0:2].copy(), dx=bl[:nb, 2:4].copy(), b=None),
+                reload=float(self.schedule.reload[tick]), t=float(self.schedule.t[tick])))
+        return out
 
     def to_state(self, i):
         """Game i as a reference `State` (float64 arrays), or None when the game has ended."""
-        tile, lane = divmod(int(i), nat.TILE)
-        meta = int(self.meta[i].item()) & 0xFFFFFFFF
-        if (meta >> 13) & 1:
-            return None
-        nb, npl, tick = meta & 1023, (meta >> 10) & 7, meta >> 14
-        sh = self.ships[tile, :, lane].double().cpu().numpy()
-        sb = self.ship_b[tile, :, lane].double().cpu().numpy()
-        pl = self.planets[tile, :npl, lane].double().cpu().numpy()
-        row = self.meta[tile * nat.TILE:tile * nat.TILE + lane].cpu().numpy().view(np.uint32)
-        first = int(((row & 1023) * (1 - ((row >> 13) & 1))).sum())            # bullets of the tile's lower games
-        bl = self.bullets[self.bullet_buffer, tile, first:first + nb].double().cpu().numpy().reshape(nb, 4)
-        return core.State(
-            ships=core.Bodies(x=sh[:, 0:2].copy(), dx=sh[:, 2:4].copy(), b=sb.copy()),
-            planets=core.Bodies(x=pl[:, 0:2].copy(), dx=pl[:, 2:4].copy(), b=None),
-            bullets=core.Bodies(x=bl[:, 0:2].copy(), dx=bl[:, 2:4].copy(), b=None),
-            reload=float(self.schedule.reload[tick]), t=float(self.schedule.t[tick]))
-
-    def get_states(self, indices):
-        """Reference `State`s (or None for finished games) of the listed games only: one gather per
-        array on the device, one small copy each — the read path of logs.GameRecorder."""
-        torch = _torch()
-        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
-        tiles, lanes = self._split(idx)
-        tt, ll = torch.from_numpy(tiles).to(self.device), torch.from_numpy(lanes).to(self.device)
-        ii = torch.from_numpy(idx).to(self.device)
-        meta = self.meta[ii].cpu().numpy().view(np.uint32)
-        sh = self.ships[tt, :, ll].double().cpu().numpy()          # [m, S, 4]
-        sb = self.ship_b[tt, :, ll].double().cpu().numpy()         # [m, S]
-        pl = self.planets[tt, :, ll].double().cpu().numpy()        # [m, 4, 4]
-        _, first = self._tile_counts(tt)
-        k = torch.arange(max(self.K, 1), device=self.device)
-        item = (first[torch.arange(len(idx), device=self.device), ll][:, None] + k).clamp_(max=32 * max(self.K, 1) - 1)
-        bl = self.bullets[self.bullet_buffer][tt[:, None], item].double().cpu().numpy()      # [m, K, 4]
-        out = []
-        for j in range(len(idx)):
-            m = int(meta[j])
-            if (m >> 13) & 1:
-                out.append(None)
-                continue
-            nb, npl, tick = m & 1023, (m >> 10) & 7, m >> 14
-            out.append(core.State(
-                ships=core.Bodies(x=sh[j, :, 0:2].copy(), dx=sh[j, :, 2:4].copy(), b=sb[j].copy()),
-                planets=core.Bodies(x=pl[j, :npl, 0:2].copy(), dx=pl[j, :npl, 2:4].copy(), b=None),
-                bullets=core.Bodies(x=bl[j, :nb, 0:2].copy(), dx=bl[j, :nb, 2:4].copy(), b=None),
-                reload=float(self.schedule.reload[tick]), t=float(self.schedule.t[tick])))
-        return out
+        return self.get_states([int(i)])[0]
 
     # ---- reset pool ------------------------------------------------------------------------------
     def set_reset_pool(self, states):
@@ -365,7 +342,10 @@ class BatchedGames:
             a_ptr = None
         else:
             if not isinstance(actions, torch.Tensor):
-                actions = torch.from_numpy(np.ascontiguousarray(actions).astype(np.uint8))
+                actions = np.ascontiguousarray(actions)
+                if actions.size and (actions.min() < 0 or actions.max() > 5):
+                    raise ValueError('control codes must be 0..5 (core.py:220-227)')   # (device tensors: ASTRO_EV_BAD_CONTROL)
+                actions = torch.from_numpy(actions.astype(np.uint8))
             actions = actions.to(device=self.device, dtype=torch.uint8).reshape(-1, self.S)
             if actions.shape[0] == self.n_pad and actions.is_contiguous():
                 a_ptr = actions.data_ptr()
@@ -381,7 +361,7 @@ class BatchedGames:
         n = self.n
         return (self._reward[:n] if want_reward else None), self._done[:n], self._events[:n]
 
-    def step_many(self, n_ticks, actions=None, events=None, reward=None, done=None, auto_reset=True, stats=True):
+    def step_many(self, n_ticks, actions=None, events=None, reward=None, done=None, auto_reset=False, stats=True):
         """`n_ticks` consecutive `step()`s in as few launches as possible (astro_tick_many): the ticks of a tile run
         back to back inside a launch, state going from one tick to the next through L2.  For loops whose controls
         do not depend on the states inside the block (replays, random exploration, the counter stream).
@@ -432,7 +412,7 @@ class BatchedGames:
                                             ptr(events_host), flags, self._stream()))
         self.step_index += 1
 
-    def rollout_host(self, actions_host, events_host, auto_reset=True, stats=True):
+    def rollout_host(self, actions_host, events_host, auto_reset=False, stats=True):
         """Pipelined end-to-end rollout with HOST buffers: actions_host uint8 [T, n_pad, S], events_host
         uint8 [T, n_pad] (pinned torch tensors or numpy arrays).  Every tick's controls are copied
         in and its events copied out; copies of neighbouring ticks overlap the tick kernel."""

@@ -7,7 +7,8 @@ and `astro.server` style code can drive it unchanged:
     generate_configs, create, step, roll_ships, Bot, Bots, play, save_log, load_log
 
 `step` runs the game tick on the GPU (float64 validation arithmetic: results are bit-identical
-to the reference on float64 inputs); there is no CPU implementation of the tick in this package.
+to the reference — on float64 states, and on the float32 arrays `create` returns, whose first tick
+the reference evaluates partly in float32); there is no CPU implementation of the tick in this package.
 For throughput use `astro_b200.batched.BatchedGames`, which steps N games per launch.
 """
 import collections
@@ -94,6 +95,71 @@ def _world_key(config):
             float(config.ship_radius), float(config.planet_mass), float(config.planet_radius), bool(config.solo))
 
 
+def _native():
+    from . import _native as nat
+    return nat
+
+
+class _SingleGame:
+    """One game on the GPU for `step`: a one-tile float64 batch driven through astro_step_single_host — one pinned
+    record in, import -> tick -> export on the stream, one pinned record out.  No tensor indexing, no schedule
+    rebuild: reload / t stay Python floats on the host (as in the reference, core.py:257-280,302) and the device is
+    told the outcome of their two predicates through a fixed four-entry schedule
+    (entry 0, 1: nothing fires; 2: the ships fire; 3: the game times out)."""
+    PLAIN, FIRE, TIMEOUT = 1, 2, 3
+
+    def __init__(self, config, cap):
+        import ctypes as C
+        import torch
+        from . import _native as nat
+        from .batched import BatchedGames
+        self.nat, self.C = nat, C
+        self.S = 1 if config.solo else 2
+        self.cap = cap
+        self.games = BatchedGames(config, nat.TILE, bullet_cap=cap, precision=64)
+        fire = np.array([1 << self.FIRE], dtype=np.uint32)
+        nat.check(nat.lib().astro_set_schedule(self.games._h, fire.ctypes.data_as(C.c_void_p), 4, self.TIMEOUT))
+        self.games.schedule = None       # (the batch's own reload / t tables do not apply to this handle)
+        nbytes = int(nat.lib().astro_single_game_bytes(cap))
+        self._pin = [torch.zeros(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        views = []
+        for buf in self._pin:
+            raw = buf.numpy()
+            rec = nat.AstroSingleGame.from_address(buf.data_ptr())
+            head = C.sizeof(nat.AstroSingleGame)
+            views.append(dict(rec=rec, ptr=C.c_void_p(buf.data_ptr()),
+                              ships=raw[0:80].view(np.float64).reshape(2, 5),
+                              planets=raw[80:208].view(np.float64).reshape(4, 4),
+                              bullets=raw[head:].view(np.float64).reshape(cap, 4)))
+        self.inp, self.out = views
+
+    def step(self, state, control, code, flags=0):
+        a, o, S = self.inp, self.out, self.S
+        a['ships'][:S, 0:2], a['ships'][:S, 2:4], a['ships'][:S, 4] = state.ships.x, state.ships.dx, state.ships.b
+        p, nb = np.shape(state.planets.x)[0], np.shape(state.bullets.x)[0]
+        a['planets'][:p, 0:2], a['planets'][:p, 2:4] = state.planets.x, state.planets.dx
+        if nb:
+            a['bullets'][:nb, 0:2], a['bullets'][:nb, 2:4] = state.bullets.x, state.bullets.dx
+        rec = a['rec']
+        rec.n_planets, rec.n_bullets, rec.tick = p, nb, code
+        for s in range(S):
+            rec.control[s] = int(control[s])
+        g = self.games
+        self.nat.check(self.nat.lib().astro_step_single_host(g._h, a['ptr'], o['ptr'], flags, g._stream()))
+        out = o['rec']
+        return int(out.events[0]), out.n_bullets, o
+
+
+def _single_game(config, n_bullets):
+    nships = 1 if config.solo else 2
+    cap = max(32, -(-(n_bullets + nships) // 32) * 32)
+    key = _world_key(config) + (cap,)
+    single = _SINGLE.get(key)
+    if single is None:
+        single = _SINGLE[key] = _SingleGame(config, cap)
+    return single
+
+
 def step(state, control, config):
     """Advance one game by one tick on the GPU (core.py:215-303).
 
@@ -101,27 +167,39 @@ def step(state, control, config):
     returns (State or None, reward array [nships]) exactly like the reference: None when the
     game ended; reward is int64 (1 - 2*hit) after a collision and float32 otherwise.
     """
-    from .batched import BatchedGames
     control = np.asarray(control)
     nships = np.shape(state.ships.x)[0]
     if nships != (1 if config.solo else 2):
         raise ValueError('state has %d ships but config.solo=%r' % (nships, config.solo))
-    nb = np.shape(state.bullets.x)[0]
-    cap = max(32, -(-(nb + nships) // 32) * 32)
-    key = _world_key(config) + (cap,)
-    games = _SINGLE.get(key)
-    if games is None:
-        games = _SINGLE[key] = BatchedGames(config, 1, bullet_cap=cap, precision=64)
-    games.set_schedule_origin(state.reload, state.t)
-    games.set_states([state], ticks=[0])
-    reward, done, events = games.step(control.reshape(1, nships))
-    ev = int(events[0].item())
+    if control.shape != (nships,) or control.min() < 0 or control.max() > 5:
+        raise ValueError('control must hold %d codes 0..5 (core.py:220-227), got %r' % (nships, control))
+    npl = np.shape(state.planets.x)[0]
+    if not 1 <= npl <= 4:
+        raise ValueError('a state needs 1..4 planets')
+    # reload / t: Python floats, the reference's operations (core.py:257, 263, 267, 280, 302)
+    timeout = config.max_time <= state.t + config.dt
+    next_reload = state.reload + config.dt
+    fire = config.reload_time <= next_reload
+    if fire:
+        next_reload -= config.reload_time
+    single = _single_game(config, np.shape(state.bullets.x)[0])
+    code = _SingleGame.TIMEOUT if timeout else (_SingleGame.FIRE if fire else _SingleGame.PLAIN)
+    # A state straight from create() holds float32 arrays: the reference's first tick then runs partly in float32
+    # (NEP 50 promotion) — reproduced by the kernel's ASTRO_TICK_ALL_CREATE_DTYPES arithmetic.
+    raw = (np.shape(state.bullets.x)[0] == 0 and np.asarray(state.ships.x).dtype == np.float32
+           and np.asarray(state.planets.x).dtype == np.float32)
+    ev, nb, o = single.step(state, control, code, _native().TICK_ALL_CREATE_DTYPES if raw else 0)
     if ev & 3:      # collision: 1 - 2 * hit (core.py:255), int64
         hit = np.array([(ev >> s) & 1 for s in range(nships)], dtype=np.int64)
         return None, 1 - 2 * hit
     if ev & 4:      # timeout (core.py:260)
         return None, np.full(nships, 1 if config.solo else 0, dtype=np.float32)
-    return games.to_state(0), np.zeros(nships, dtype=np.float32)
+    sh, pl, bl = o['ships'], o['planets'], o['bullets']
+    new = State(ships=Bodies(x=sh[:nships, 0:2].copy(), dx=sh[:nships, 2:4].copy(), b=sh[:nships, 4].copy()),
+                planets=Bodies(x=pl[:npl, 0:2].copy(), dx=pl[:npl, 2:4].copy(), b=None),
+                bullets=Bodies(x=bl[:nb, 0:2].copy(), dx=bl[:nb, 2:4].copy(), b=None),
+                reload=next_reload, t=state.t + config.dt)
+    return new, np.zeros(nships, dtype=np.float32)
 
 
 def roll_ships(state, index):

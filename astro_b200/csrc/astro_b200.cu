@@ -118,7 +118,7 @@ __device__ __forceinline__ unsigned warp_totals(int lane, int S, uint32_t ev, bo
 #pragma unroll
     for (int k = 0; k < ASTRO_N_STATS; k++) v[k] = 0u;
     // most tiles, most ticks: nobody ended, overflowed or was skipped, nobody fired
-    if (__ballot_sync(full, (ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_OVERFLOW | ASTRO_EV_SKIPPED)) != 0)) {
+    if (__ballot_sync(full, (ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_OVERFLOW | ASTRO_EV_SKIPPED | ASTRO_EV_BAD_CONTROL)) != 0)) {
         v[0] = __popc(__ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0));
         v[1] = __popc(__ballot_sync(full, S == 2 && coll && !h0));
         v[2] = __popc(__ballot_sync(full, S == 2 && coll && !h1));
@@ -126,6 +126,7 @@ __device__ __forceinline__ unsigned warp_totals(int lane, int S, uint32_t ev, bo
         v[4] = __popc(__ballot_sync(full, (ev & ASTRO_EV_TIMEOUT) != 0));
         v[7] = __popc(__ballot_sync(full, (ev & ASTRO_EV_OVERFLOW) != 0));
         v[11] = __popc(__ballot_sync(full, (ev & ASTRO_EV_SKIPPED) != 0));
+        v[12] = __popc(__ballot_sync(full, (ev & ASTRO_EV_BAD_CONTROL) != 0));
     }
     v[5] = __popc(__ballot_sync(full, active));
     v[6] = (unsigned)S * __popc(__ballot_sync(full, spawned != 0));
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
 
             // ---- controls (core.py:220-227,234-239)
             int ctl[S];
+            bool bad_ctl = false;
             if (p.actions) {
                 if (S == 2) {
                     uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
@@ -258,6 +260,9 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                 } else {
                     ctl[0] = p.actions[g];
                 }
+#pragma unroll
+                for (int s = 0; s < S; s++)   // codes above 5: outside the reference's table (core.py:220-227)
+                    if (ctl[s] > 5) { ctl[s] = 2; bad_ctl = true; }
             } else {
                 uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
 #pragma unroll
@@ -265,6 +270,9 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
             }
 
             // ---- accelerations and ship collisions on the OLD state
+            // (raw: the game holds core.create's float32 arrays — the reference's first-tick arithmetic, see the header)
+            const bool raw = std::is_same<R, double>::value && nb == 0 &&
+                             ((p.flags & ASTRO_TICK_ALL_CREATE_DTYPES) || ((p.flags & ASTRO_TICK_CREATE_DTYPES) && tick == 0));
             float dir0[S], dir1[S];
             R a0[S], a1[S];
             bool hit[S];
@@ -273,6 +281,19 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                 np_sincos_f32((float)sb[s], dir0[s], dir1[s]);
                 R g0 = 0, g1 = 0;
                 bool h = false;
+                if (raw) {
+                    float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+                        if (j < np) {
+                            float t0, t1;
+                            grav_term_np32((float)pl[j].x, (float)pl[j].y, (float)sh[s].x, (float)sh[s].y, c.gm_f, t0, t1);
+                            if (j == 0) { f0 = t0; f1 = t1; } else { f0 = __fadd_rn(f0, t0); f1 = __fadd_rn(f1, t1); }
+                            h |= collide_np32((float)sh[s].x, (float)sh[s].y, (float)pl[j].x, (float)pl[j].y, c.r2_sp);
+                        }
+                    }
+                    g0 = (R)f0; g1 = (R)f1;
+                } else {
 #pragma unroll
                 for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
                     if (j < np) {
@@ -282,13 +303,15 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                         h |= collide(sh[s].x, sh[s].y, pl[j].x, pl[j].y, c.r2_sp, c.r2f_sp);
                     }
                 }
+                }
                 R th = mul_rn(Pick<R>::thrust(c), (R)(ctl[s] & 1));
                 a0[s] = add_rn(mul_rn(th, (R)dir0[s]), g0);
                 a1[s] = add_rn(mul_rn(th, (R)dir1[s]), g1);
                 hit[s] = h;
             }
             if (S == 2) {
-                bool h = collide(sh[0].x, sh[0].y, sh[S - 1].x, sh[S - 1].y, c.r2_ss, c.r2f_ss);
+                bool h = raw ? collide_np32((float)sh[0].x, (float)sh[0].y, (float)sh[S - 1].x, (float)sh[S - 1].y, c.r2_ss)
+                             : collide(sh[0].x, sh[0].y, sh[S - 1].x, sh[S - 1].y, c.r2_ss, c.r2f_ss);
                 hit[0] |= h;
                 hit[S - 1] |= h;
             }
@@ -347,11 +370,24 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
 #pragma unroll
                     for (int s = 0; s < S; s++) {
                         Body4<double> nbl;
+                        bool keep;
+                        if (raw) {   // float32 ship state + float32 products, advanced in float32 (weak scalars)
+                            const float x0 = __fadd_rn((float)sh[s].x, __fmul_rn(c.off_f, dir0[s]));
+                            const float x1 = __fadd_rn((float)sh[s].y, __fmul_rn(c.off_f, dir1[s]));
+                            const float w0 = __fadd_rn(__fadd_rn((float)sh[s].dx, __fmul_rn(c.spd_f, dir0[s])), (float)c.zero_dt);
+                            const float w1 = __fadd_rn(__fadd_rn((float)sh[s].dy, __fmul_rn(c.spd_f, dir1[s])), (float)c.zero_dt);
+                            nbl.x = (double)__fadd_rn(x0, __fmul_rn(c.dt_f, w0));
+                            nbl.y = (double)__fadd_rn(x1, __fmul_rn(c.dt_f, w1));
+                            nbl.dx = (double)w0;
+                            nbl.dy = (double)w1;
+                            keep = in_arena(nbl.x, nbl.y);
+                        } else {
                         nbl.x = __dadd_rn((double)sh[s].x, (double)__fmul_rn(c.off_f, dir0[s]));
                         nbl.y = __dadd_rn((double)sh[s].y, (double)__fmul_rn(c.off_f, dir1[s]));
                         nbl.dx = __dadd_rn((double)sh[s].dx, (double)__fmul_rn(c.spd_f, dir0[s]));
                         nbl.dy = __dadd_rn((double)sh[s].dy, (double)__fmul_rn(c.spd_f, dir1[s]));
-                        bool keep = advance_bullet(nbl, c);
+                        keep = advance_bullet(nbl, c);
+                        }
                         if (keep) {
                             if (m + n_born < p.K) {
                                 B4 o;
@@ -382,12 +418,41 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                         }
                     }
                 }
+                if (raw) {   // float32 field, float32 a * dt (a float32 array times the weak scalar dt), then float64
+                    float f0[ASTRO_MAX_PLANETS], f1[ASTRO_MAX_PLANETS];
+#pragma unroll
+                    for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
+                        f0[i] = f1[i] = 0.f;
+                        if (i < np) {
+#pragma unroll
+                            for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+                                if (j < np) {
+                                    float t0, t1;
+                                    grav_term_np32((float)pl[j].x, (float)pl[j].y, (float)pl[i].x, (float)pl[i].y, c.gm_f, t0, t1);
+                                    if (j == 0) { f0[i] = t0; f1[i] = t1; } else { f0[i] = __fadd_rn(f0[i], t0); f1[i] = __fadd_rn(f1[i], t1); }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
+                        if (i < np) {
+                            const double v0 = __dadd_rn((double)pl[i].dx, (double)__fmul_rn(f0[i], c.dt_f));
+                            const double v1 = __dadd_rn((double)pl[i].dy, (double)__fmul_rn(f1[i], c.dt_f));
+                            pl[i].x = (R)wrap_unit_f64(__dadd_rn((double)pl[i].x, __dmul_rn(c.dt, v0)));
+                            pl[i].y = (R)wrap_unit_f64(__dadd_rn((double)pl[i].y, __dmul_rn(c.dt, v1)));
+                            pl[i].dx = (R)v0; pl[i].dy = (R)v1;
+                            planets[i * 32] = pl[i];
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int i = 0; i < ASTRO_MAX_PLANETS; i++) {
                     if (i < np) {
                         advance_body(pl[i], q0[i], q1[i], c);
                         planets[i * 32] = pl[i];
                     }
+                }
                 }
                 // ---- ships (core.py:283-288)
 #pragma unroll
@@ -401,6 +466,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
                 p.meta[g] = ASTRO_META_PACK(m_out, np, 0, tick + 1);
             }
 
+            if (bad_ctl) ev |= ASTRO_EV_BAD_CONTROL;
             if (ev & ASTRO_EV_DONE_MASK) {
                 if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0) {
                     recreate_from_pool<R, S>(p, g, p.step + 1u, ships, ship_b, planets);
@@ -824,7 +890,7 @@ struct PolicyWeights {              // every matrix TRANSPOSED, [in][out]: lane 
     float v2t[kPolW][kPolW], v2b[kPolW];
     float v0t[kPolW][kPolMaxOut], v0b[kPolMaxOut];
 };
-__device__ PolicyWeights g_pol;
+// (the weights live in device memory owned by the batch handle: every batch has its own network)
 
 // x / (1 + |x|) with the fast reciprocal (2 ulp): the network's outputs stay within ~1e-6 of PyTorch's
 __device__ __forceinline__ float softsign(float x) { return div_fast_normal(x, 1.0f + fabsf(x)); }
@@ -875,9 +941,10 @@ template <typename R, int S>
 __global__ void __launch_bounds__(kPolWarps * 32, ASTRO_POL_MIN_BLOCKS)
 policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_, const void* __restrict__ planets_,
               const void* __restrict__ bullets_, const uint32_t* __restrict__ meta_, uint8_t* __restrict__ actions,
-              float* __restrict__ q_out, int n_games, int K, int nout, int ship_mask) {
+              float* __restrict__ q_out, int n_games, int K, int nout, int ship_mask, const PolicyWeights* __restrict__ pol) {
     using B4 = Body4<R>;
     constexpr int DIN = 1 + 5 * S + 4;
+    const PolicyWeights& g_pol = *pol;
     __shared__ float4 s_act[kPolWarps][2][kPolW / 4];   // activation exchange, one buffer per chain
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* actA = reinterpret_cast<float*>(s_act[warp][0]);
@@ -1032,6 +1099,144 @@ __global__ void __launch_bounds__(128) explore_kernel(const uint32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// export_kernel / import_kernel: the batch <-> game-major float64 arrays (AstroGameArrays), the
+// form the host-side readers and writers of single games want: State conversion for the drop-in
+// core.step / core.play (core.py:11-18, :215-303, :377-410), the JSONL logs (core.py:413-443),
+// tests.  One kernel each instead of a chain of gathers: the tile lists are unpacked / packed on
+// the device.
+//   export: warp = one listed game; lane k copies bullet k, k + 32, ... of the game's run of its
+//           tile's list; dead planet / bullet slots are written as zeros.
+//   import: warp = one tile.  src[g] = the row of the arrays that replaces game g (-1: keep).  A
+//           tile with a replaced game rebuilds its list — kept games' runs and the new games'
+//           bullets, dense, in game order — in the tile's run of the OTHER buffer (dead between
+//           ticks, so a free scratch area) and copies it back; then the rows and meta words of the
+//           replaced games are written.
+// ------------------------------------------------------------------------------------------
+struct GameArrays {          // device pointers, see AstroGameArrays
+    double* ships;
+    double* planets;
+    double* bullets;
+    int32_t* n_planets;
+    int32_t* n_bullets;
+    int32_t* tick;
+    uint8_t* finished;
+    uint32_t* episode;
+};
+
+template <typename R, int S>
+__global__ void __launch_bounds__(128) export_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
+                                                     const void* __restrict__ planets_, const void* __restrict__ bullets_,
+                                                     const uint32_t* __restrict__ meta_, const uint32_t* __restrict__ episode_,
+                                                     const int32_t* __restrict__ index, int m, int n_games, int K, int k_out,
+                                                     const __grid_constant__ GameArrays a) {
+    using B4 = Body4<R>;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= m) return;
+    const int g = index ? index[row] : row;
+    if (g < 0 || g >= n_games) return;   // (checked on the host for host-side indices)
+    const size_t tile = (size_t)(g >> 5);
+    const int gl = g & 31;
+    const uint32_t meta = meta_[g];
+    const bool fin = ASTRO_META_FINISHED(meta);
+    const int np = (int)ASTRO_META_NP(meta), nb = fin ? 0 : (int)ASTRO_META_NB(meta);
+    if (lane < S) {
+        const B4 v = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + lane * 32 + gl];
+        double* o = a.ships + ((size_t)row * S + lane) * 5;
+        o[0] = (double)v.x; o[1] = (double)v.y; o[2] = (double)v.dx; o[3] = (double)v.dy;
+        o[4] = (double)reinterpret_cast<const R*>(ship_b_)[tile * (S * 32) + lane * 32 + gl];
+    }
+    if (lane < ASTRO_MAX_PLANETS) {
+        B4 v = B4();
+        if (lane < np) v = reinterpret_cast<const B4*>(planets_)[tile * (ASTRO_MAX_PLANETS * 32) + lane * 32 + gl];
+        double* o = a.planets + ((size_t)row * ASTRO_MAX_PLANETS + lane) * 4;
+        o[0] = (double)v.x; o[1] = (double)v.y; o[2] = (double)v.dx; o[3] = (double)v.dy;
+    }
+    const unsigned first = tile_list_offset(meta_ + tile * 32, gl, lane);
+    const B4* run = reinterpret_cast<const B4*>(bullets_) + tile * (size_t)(32 * K) + first;
+    for (int k = lane; k < k_out; k += 32) {
+        B4 v = B4();
+        if (k < nb) v = run[k];
+        double* o = a.bullets + ((size_t)row * k_out + k) * 4;
+        o[0] = (double)v.x; o[1] = (double)v.y; o[2] = (double)v.dx; o[3] = (double)v.dy;
+    }
+    if (lane == 0) {
+        a.n_planets[row] = np;
+        a.n_bullets[row] = nb;
+        a.tick[row] = (int32_t)ASTRO_META_TICK(meta);
+        a.finished[row] = fin ? 1 : 0;
+        if (a.episode) a.episode[row] = episode_[g];
+    }
+}
+
+__global__ void import_map_kernel(const int32_t* __restrict__ index, int m, int n_games, int32_t* __restrict__ src) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int g = index[i];
+    if (g >= 0 && g < n_games) src[g] = i;
+}
+
+template <typename R, int S>
+__global__ void __launch_bounds__(128) import_kernel(void* __restrict__ ships_, void* __restrict__ ship_b_, void* __restrict__ planets_,
+                                                     void* bullets_cur_, void* bullets_other_, uint32_t* __restrict__ meta_,
+                                                     uint32_t* __restrict__ episode_, const int32_t* __restrict__ src, int m,
+                                                     int n_games, int K, int k_in, const __grid_constant__ GameArrays a) {
+    using B4 = Body4<R>;
+    const unsigned full = 0xffffffffu;
+    const int tile_i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile_i * 32 >= n_games) return;
+    const int g = tile_i * 32 + lane;
+    const int row = src ? src[g] : (g < m ? g : -1);          // src == NULL: rows 0..m-1 replace games 0..m-1
+    if (!__ballot_sync(full, row >= 0)) return;
+    const size_t tile = (size_t)tile_i;
+    const uint32_t meta = meta_[g];
+    const unsigned old_nb = ASTRO_META_FINISHED(meta) ? 0u : ASTRO_META_NB(meta);
+    unsigned new_nb = old_nb;
+    bool fin = false;
+    if (row >= 0) {
+        fin = a.finished && a.finished[row];
+        const int want = a.n_bullets ? a.n_bullets[row] : 0;
+        new_nb = fin ? 0u : (unsigned)min(max(want, 0), min(K, k_in));
+    }
+    const unsigned old_first = warp_exclusive_sum(old_nb, lane), new_first = warp_exclusive_sum(new_nb, lane);
+    const unsigned new_total = __reduce_add_sync(full, new_nb);
+    B4* const cur = reinterpret_cast<B4*>(bullets_cur_) + tile * (size_t)(32 * K);
+    B4* const scratch = reinterpret_cast<B4*>(bullets_other_) + tile * (size_t)(32 * K);
+    if (row >= 0) {
+        const double* bsrc = a.bullets + (size_t)row * k_in * 4;
+        for (unsigned k = 0; k < new_nb; k++) {
+            B4 v;
+            v.x = (R)bsrc[4 * k]; v.y = (R)bsrc[4 * k + 1]; v.dx = (R)bsrc[4 * k + 2]; v.dy = (R)bsrc[4 * k + 3];
+            scratch[new_first + k] = v;
+        }
+    } else {
+        for (unsigned k = 0; k < new_nb; k++) scratch[new_first + k] = cur[old_first + k];
+    }
+    __syncwarp();
+    for (unsigned j = lane; j < new_total; j += 32u) cur[j] = scratch[j];
+    if (row >= 0) {
+        const int np = min(max(a.n_planets[row], 0), ASTRO_MAX_PLANETS);
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const double* o = a.ships + ((size_t)row * S + s) * 5;
+            B4 v;
+            v.x = (R)o[0]; v.y = (R)o[1]; v.dx = (R)o[2]; v.dy = (R)o[3];
+            reinterpret_cast<B4*>(ships_)[tile * (S * 32) + s * 32 + lane] = v;
+            reinterpret_cast<R*>(ship_b_)[tile * (S * 32) + s * 32 + lane] = (R)o[4];
+        }
+#pragma unroll
+        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+            const double* o = a.planets + ((size_t)row * ASTRO_MAX_PLANETS + j) * 4;
+            B4 v = B4();
+            if (j < np) { v.x = (R)o[0]; v.y = (R)o[1]; v.dx = (R)o[2]; v.dy = (R)o[3]; }
+            reinterpret_cast<B4*>(planets_)[tile * (ASTRO_MAX_PLANETS * 32) + j * 32 + lane] = v;
+        }
+        const uint32_t tick = a.tick ? (uint32_t)a.tick[row] : 0u;
+        meta_[g] = ASTRO_META_PACK(new_nb, np, fin ? 1 : 0, tick);
+        if (a.episode) episode_[g] = a.episode[row];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
@@ -1080,6 +1285,10 @@ struct AstroBatch {
     int64_t first_game;
     int64_t launches;
     int32_t policy_nout;  // > 0 once astro_policy_set_weights has been called
+    PolicyWeights* d_pol; // this batch's network (astro_policy_set_weights)
+    int32_t* d_src;       // astro_import_games: game -> row map
+    char* d_single;       // astro_step_single_host: device staging, in record then out record
+    int64_t single_bytes;
     double explore_t_in, explore_t_out;   // astro_set_exploration (ASTRO_BOT_EXPLORE)
     uint32_t explore_seed;
     int32_t* explore_state;
@@ -1205,6 +1414,7 @@ cudaError_t fold_stats(AstroBatch* b, cudaStream_t st) {
 // [n_ticks][...] (or NULL).  The production fp32 kernel runs up to kMaxFused of them per launch, each tile
 // back to back (tick_f32_kernel); the generic / float64 kernels run one launch per tick.
 constexpr int kMaxFused = 256;
+constexpr double kSinCosRange = 71476.0;   // np_sincos_f32 (astro_device.cuh)
 int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t flags,
              cudaStream_t st, int32_t n_ticks) {
     if (b->n_sched_ticks <= 0) return fail(ASTRO_E_STATE, "astro_set_schedule has not been called");
@@ -1308,6 +1518,9 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaFree(b->d_reward);
     cudaFree(b->d_fire_bits);
     cudaFree(b->d_pool_rec);
+    cudaFree(b->d_pol);
+    cudaFree(b->d_src);
+    cudaFree(b->d_single);
     if (b->pipe_ready) {
         for (int i = 0; i < 2; i++) {
             cudaFree(b->d_actions2[i]);
@@ -1341,6 +1554,13 @@ int astro_set_schedule(AstroBatch* b, const uint32_t* fire_bits_host, int32_t n_
     if (int r = check(b, false)) return r;
     if (!fire_bits_host || n_ticks <= 0 || n_ticks > ASTRO_MAX_TICKS + 1 || timeout_tick < 0 || timeout_tick >= n_ticks)
         return fail(ASTRO_E_INVALID, "bad schedule (n_ticks %d, timeout_tick %d, max %d)", n_ticks, timeout_tick, ASTRO_MAX_TICKS);
+    // util.direction (util.py:87-92) is restated for |b| <= 71476 (np_sincos_f32); beyond that numpy takes another
+    // reduction path and the results would silently differ.  Bearings start below 2 pi (core.py:113) and turn by at
+    // most dt * ship_rspeed per tick.
+    if (6.283185307179586 + (double)n_ticks * fabs(b->cfg.dt * b->cfg.ship_rspeed) > kSinCosRange)
+        return fail(ASTRO_E_INVALID, "a bearing could reach %.0f rad within %d ticks (dt * ship_rspeed = %g): beyond the %.0f rad range "
+                    "over which util.direction is reproduced", 6.283185307179586 + (double)n_ticks * fabs(b->cfg.dt * b->cfg.ship_rspeed),
+                    n_ticks, b->cfg.dt * b->cfg.ship_rspeed, kSinCosRange);
     CUDA_TRY(cudaSetDevice(b->device));
     if (b->d_fire_bits) CUDA_TRY(cudaFree(b->d_fire_bits));
     b->d_fire_bits = nullptr;
@@ -1616,9 +1836,11 @@ int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n
     memcpy(w->v2b, p, sizeof(w->v2b)); p += kPolW;
     for (int u = 0; u < nout; u++) for (int c = 0; c < kPolW; c++) w->v0t[c][u] = *p++;
     memcpy(w->v0b, p, sizeof(float) * nout);
-    cudaError_t e = cudaMemcpyToSymbol(g_pol, w, sizeof(*w));
+    cudaError_t e = b->d_pol ? cudaSuccess : cudaMalloc(&b->d_pol, sizeof(PolicyWeights));
+    // (pageable source: the copy has left `w` when the call returns; stream-ordered before later launches)
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_pol, w, sizeof(*w), cudaMemcpyHostToDevice);
     delete w;
-    if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "policy weights upload: %s", cudaGetErrorString(e));
     b->policy_nout = nout;
     return ASTRO_OK;
 }
@@ -1637,7 +1859,7 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;
 #define LAUNCH_POL(R, S_) \
-    policy_kernel<R, S_><<<grid, kPolWarps * 32, 0, st>>>(u.ships, u.ship_b, u.planets, current_bullets(b), u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask)
+    policy_kernel<R, S_><<<grid, kPolWarps * 32, 0, st>>>(u.ships, u.ship_b, u.planets, current_bullets(b), u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask, b->d_pol)
     if (b->precision == 32) {
         if (b->S == 2) LAUNCH_POL(float, 2); else LAUNCH_POL(float, 1);
     } else {
@@ -1728,6 +1950,126 @@ int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int
         }
         if (int r = do_tick(b, all_stream ? nullptr : actions, nullptr, nullptr, events, flags, st)) return r;
     }
+    return ASTRO_OK;
+}
+
+static GameArrays to_dev_arrays(const AstroGameArrays* a) {
+    GameArrays d;
+    d.ships = a->ships; d.planets = a->planets; d.bullets = a->bullets;
+    d.n_planets = a->n_planets; d.n_bullets = a->n_bullets; d.tick = a->tick;
+    d.finished = a->finished; d.episode = a->episode;
+    return d;
+}
+
+int astro_export_games(AstroBatch* b, const int32_t* index, int32_t m, const AstroGameArrays* out, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!out || m < 0 || !out->ships || !out->planets || !out->n_planets || !out->n_bullets || !out->tick || !out->finished ||
+        out->bullet_rows < 0 || (out->bullet_rows > 0 && !out->bullets))
+        return fail(ASTRO_E_INVALID, "bad export arguments");
+    if (!index && m > b->n_games) return fail(ASTRO_E_INVALID, "m %d > n_games %d", m, b->n_games);
+    if (m == 0) return ASTRO_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    const GameArrays a = to_dev_arrays(out);
+    const AstroBuffers& u = b->bufs;
+    const int grid = (m + 3) / 4;
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_EXP(R, S_) \
+    export_kernel<R, S_><<<grid, 128, 0, st>>>(u.ships, u.ship_b, u.planets, current_bullets(b), u.meta, u.episode, index, m, b->n_games, b->K, out->bullet_rows, a)
+    if (b->precision == 32) { if (b->S == 2) LAUNCH_EXP(float, 2); else LAUNCH_EXP(float, 1); }
+    else { if (b->S == 2) LAUNCH_EXP(double, 2); else LAUNCH_EXP(double, 1); }
+#undef LAUNCH_EXP
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
+int astro_import_games(AstroBatch* b, const int32_t* index, int32_t m, const AstroGameArrays* in, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!in || m < 0 || !in->ships || !in->planets || !in->n_planets || in->bullet_rows < 0 ||
+        (in->bullet_rows > 0 && in->n_bullets && !in->bullets))
+        return fail(ASTRO_E_INVALID, "bad import arguments");
+    if (!index && m > b->n_games) return fail(ASTRO_E_INVALID, "m %d > n_games %d", m, b->n_games);
+    if (m == 0) return ASTRO_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t* src = nullptr;
+    if (index) {
+        if (!b->d_src) CUDA_TRY(cudaMalloc(&b->d_src, sizeof(int32_t) * (size_t)b->n_games));
+        CUDA_TRY(cudaMemsetAsync(b->d_src, 0xff, sizeof(int32_t) * (size_t)b->n_games, st));
+        import_map_kernel<<<(m + 255) / 256, 256, 0, st>>>(index, m, b->n_games, b->d_src);
+        CUDA_TRY(cudaGetLastError());
+        b->launches += 1;
+        src = b->d_src;
+    }
+    const GameArrays a = to_dev_arrays(in);
+    const AstroBuffers& u = b->bufs;
+    const size_t buf_bytes = (size_t)b->n_games * b->K * 4 * (b->precision == 32 ? sizeof(float) : sizeof(double));
+    void* cur = (char*)u.bullets + (size_t)b->cur * buf_bytes;
+    void* other = (char*)u.bullets + (size_t)(b->cur ^ 1) * buf_bytes;
+    const int grid = (b->n_games / ASTRO_TILE + 3) / 4;
+#define LAUNCH_IMP(R, S_) \
+    import_kernel<R, S_><<<grid, 128, 0, st>>>(u.ships, u.ship_b, u.planets, cur, other, u.meta, u.episode, src, m, b->n_games, b->K, in->bullet_rows, a)
+    if (b->precision == 32) { if (b->S == 2) LAUNCH_IMP(float, 2); else LAUNCH_IMP(float, 1); }
+    else { if (b->S == 2) LAUNCH_IMP(double, 2); else LAUNCH_IMP(double, 1); }
+#undef LAUNCH_IMP
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+}
+
+int64_t astro_single_game_bytes(int32_t bullet_cap) {
+    return (int64_t)sizeof(AstroSingleGame) + (int64_t)(bullet_cap > 0 ? bullet_cap : 0) * 4 * (int64_t)sizeof(double);
+}
+
+static AstroGameArrays single_arrays(char* rec, int32_t rows) {
+    AstroSingleGame* g = reinterpret_cast<AstroSingleGame*>(rec);
+    AstroGameArrays a;
+    a.ships = &g->ships[0][0];
+    a.planets = &g->planets[0][0];
+    a.bullets = reinterpret_cast<double*>(rec + sizeof(AstroSingleGame));
+    a.n_planets = &g->n_planets;
+    a.n_bullets = &g->n_bullets;
+    a.tick = &g->tick;
+    a.finished = &g->finished[0];
+    a.episode = &g->episode;
+    a.bullet_rows = rows;
+    a.reserved = 0;
+    return a;
+}
+
+int astro_step_single_host(AstroBatch* b, const AstroSingleGame* in_host, AstroSingleGame* out_host, int32_t flags, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!in_host || !out_host) return fail(ASTRO_E_INVALID, "null record");
+    if (b->n_games != ASTRO_TILE) return fail(ASTRO_E_INVALID, "astro_step_single_host needs a one-tile batch (n_games = %d)", ASTRO_TILE);
+    const int32_t nb = in_host->n_bullets;
+    if (nb < 0 || nb > b->K) return fail(ASTRO_E_INVALID, "the game holds %d bullets, bullet_cap is %d", nb, b->K);
+    if (in_host->n_planets < 1 || in_host->n_planets > ASTRO_MAX_PLANETS) return fail(ASTRO_E_INVALID, "a game needs 1..%d planets", ASTRO_MAX_PLANETS);
+    if (b->n_sched_ticks <= 0) return fail(ASTRO_E_STATE, "astro_set_schedule has not been called");
+    if (in_host->tick < 0 || in_host->tick >= b->n_sched_ticks) return fail(ASTRO_E_INVALID, "tick %d is not on the schedule", in_host->tick);
+    for (int s = 0; s < b->S; s++) {
+        if (in_host->control[s] > 5) return fail(ASTRO_E_INVALID, "control code %d of ship %d is not one of 0..5", (int)in_host->control[s], s);
+        if (!(fabs(in_host->ships[s][4]) <= kSinCosRange)) return fail(ASTRO_E_INVALID, "bearing %g of ship %d is beyond the range over which util.direction is reproduced", in_host->ships[s][4], s);
+    }
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rec = (astro_single_game_bytes(b->K) + 63) & ~(int64_t)63;
+    if (!b->d_single) {
+        CUDA_TRY(cudaMalloc(&b->d_single, (size_t)(2 * rec)));
+        b->single_bytes = rec;
+    }
+    char* d_in = b->d_single;
+    char* d_out = b->d_single + rec;
+    CUDA_TRY(cudaMemcpyAsync(d_in, in_host, (size_t)astro_single_game_bytes(nb), cudaMemcpyHostToDevice, st));
+    const AstroGameArrays ain = single_arrays(d_in, nb);
+    if (int r = astro_import_games(b, nullptr, 1, &ain, stream)) return r;
+    AstroSingleGame* g_in = reinterpret_cast<AstroSingleGame*>(d_in);
+    AstroSingleGame* g_out = reinterpret_cast<AstroSingleGame*>(d_out);
+    if (int r = do_tick(b, g_in->control, nullptr, nullptr, g_out->events, flags | ASTRO_TICK_NO_STATS, st)) return r;
+    const int32_t rows_out = nb + b->S < b->K ? nb + b->S : b->K;
+    const AstroGameArrays aout = single_arrays(d_out, rows_out);
+    if (int r = astro_export_games(b, nullptr, 1, &aout, stream)) return r;
+    CUDA_TRY(cudaMemcpyAsync(out_host, d_out, (size_t)astro_single_game_bytes(rows_out), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return ASTRO_OK;
 }
 

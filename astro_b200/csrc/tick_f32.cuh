@@ -353,9 +353,17 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     float4 shv[2] = {in.shv[0], in.shv[1]};
     float sb[2] = {in.sb[0], in.sb[1]};
     int ctl[2];
+    bool bad_ctl = false;
     if (v.actions) {
         ctl[0] = (int)(in.ctl_raw & 0xffu);
         ctl[1] = S == 2 ? (int)(in.ctl_raw >> 8) : ctl[0];
+        // codes above 5 are outside the reference's table (core.py:220-227): no-op control, tick flagged.
+        // (a byte is 0..5 iff neither it nor it + 2 has a bit above the low three)
+        bad_ctl = ((in.ctl_raw | (in.ctl_raw + 0x0202u)) & 0xf8f8u) != 0u;
+        if (__builtin_expect(bad_ctl, 0)) {
+            if (ctl[0] > 5) ctl[0] = 2;
+            if (ctl[1] > 5) ctl[1] = 2;
+        }
     } else {
         uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
         ctl[0] = action_from_key(h0, v.step, 0u);
@@ -484,7 +492,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             acc = fma2(bc2(th), pk2(dirs[2 * s], dirs[2 * s + 1]), acc);
             next.shv[s] = advance_body2(sxy, pk2(shv[s].z, shv[s].w), acc, c);  // core.py:283-288
             next.sb[s] = __fmaf_rn(c.db_unit_f, (float)((ctl[s] >> 1) - 1), sb[s]);
-            if (last) {
+            if (last | !auto_reset) {   // (without auto-reset a game may end — and freeze — on any tick of the launch)
                 ST_STREAM(&ships[s * 32], next.shv[s]);
                 ST_STREAM(&ship_b[s * 32], next.sb[s]);
             }
@@ -657,6 +665,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             if (last) ST_STREAM(&p.meta[g], next.meta);
             m_out = m;
         }
+        if (__builtin_expect(bad_ctl, 0)) ev |= ASTRO_EV_BAD_CONTROL;
         if (ev & ASTRO_EV_DONE_MASK) {
             if (auto_reset) {
                 // Re-create the game from pool entry pool_k (core.create, core.py:86-135, evaluated
@@ -689,8 +698,12 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 next.meta = ASTRO_META_PACK(0, np_new, 0, 0);
                 if (last) p.meta[g] = next.meta;
             } else {
+                // Frozen from here on: the later ticks of this launch skip the game without touching its rows,
+                // so the finished word goes to memory now, whichever tick of the launch this is (the ships were
+                // stored by the physics above: without auto-reset every tick stores them) — identical to
+                // separate astro_tick calls.
                 next.meta = ASTRO_META_PACK(0, np, 1, tick);
-                if (last) p.meta[g] = next.meta;
+                p.meta[g] = next.meta;
             }
         }
     }

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define ASTRO_ABI_VERSION 2
+#define ASTRO_ABI_VERSION 3
 #define ASTRO_TILE 32
 #define ASTRO_MAX_SHIPS 2
 #define ASTRO_MAX_PLANETS 4
@@ -69,12 +69,21 @@ extern "C" {
 #define ASTRO_EV_FIRED 8     /* ships fired this tick (core.py:267-280) */
 #define ASTRO_EV_OVERFLOW 16 /* a newborn bullet was dropped: pool full */
 #define ASTRO_EV_SKIPPED 32  /* game was already finished; nothing done */
+#define ASTRO_EV_BAD_CONTROL 64 /* a control code above 5 was given (out of the reference's contract, core.py:220-227):
+                                   the ship was flown with control 2 (no thrust, no turn) and the tick flagged */
 #define ASTRO_EV_DONE_MASK 7
 
 /* astro_tick flags */
 #define ASTRO_TICK_AUTO_RESET 1 /* a game that ends is re-initialised from the reset pool in the same launch */
 #define ASTRO_TICK_NO_STATS 2   /* skip the astro_stats counters for this tick */
 #define ASTRO_TICK_GENERIC_KERNEL 4 /* precision 32 only: run the un-tuned template kernel (A/B checks) */
+/* precision 64 only: a game on its tick 0 (bit 8) / every game of this call (bit 16) that owns no bullets is taken to
+ * hold the arrays core.create returned (core.py:86-135: float32 ship / planet positions) and runs the reference's
+ * first-tick arithmetic — _gravity, the squared distances of _collisions and the planets' a * dt in float32, bullets
+ * born on that tick float32 throughout — so that a game played from create() equals the reference's core.play bit for
+ * bit.  Without it tick 0 treats its inputs as float64 like every other tick (states canonicalised to float64). */
+#define ASTRO_TICK_CREATE_DTYPES 8
+#define ASTRO_TICK_ALL_CREATE_DTYPES 16
 
 /* error codes */
 #define ASTRO_OK 0
@@ -119,11 +128,12 @@ typedef struct AstroCreateConfig {
     int32_t reserved;
 } AstroCreateConfig;
 
-#define ASTRO_N_STATS 12
+#define ASTRO_N_STATS 13
 /* astro_stats counters (int64 each), summed over every astro_tick since the last clear:
  *  0 episodes  1 wins0  2 wins1  3 both_lost (or solo crash)  4 timeouts  5 env_steps
  *  6 bullets_spawned  7 overflow  8 planets_live (sum of np over env-steps)
- *  9 bullets_in (sum of nb read)  10 bullets_out (sum of nb written)  11 skipped        */
+ *  9 bullets_in (sum of nb read)  10 bullets_out (sum of nb written)  11 skipped
+ *  12 bad_controls (env-steps that saw a control code above 5)                          */
 
 typedef struct AstroBatch AstroBatch;
 
@@ -228,7 +238,7 @@ int astro_script_controls(AstroBatch* b, double avoid_distance, double avoid_thr
  * ship perspectives, fused: no observation tensor is written.  Weights: the reference network's
  * state_dict flattened in order — f0, f[0], f[1], v[0], v[1], v0, weight [out][in] then bias
  * each; width 32, inputs 15 (10 solo), nout <= 8 outputs — copied to device
- * memory (one network per device at a time).
+ * memory owned by the handle (every batch has its own network).
  *   actions  u8 [n_games][S] device: argmax_q per ship (the greedy control of rl.QBot, rl.py:168-200);
  *            written only for the ships whose bit is set in ship_mask (bit k = ship k), so another
  *            bot can fill the rest; finished games get 2 (no-op)
@@ -268,6 +278,51 @@ int astro_set_exploration(AstroBatch* b, double t_in, double t_out, uint32_t see
 #define ASTRO_BOT_EXPLORE 4
 int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int32_t ship1_mode, double avoid_distance,
                          double avoid_threshold, uint8_t* actions, uint8_t* events, int32_t flags, void* stream);
+
+/* Game-major float64 view of games, the layout host-side code wants (State conversion for the drop-in core.step /
+ * core.play, core.py:11-18 and :377-410; JSONL logs, core.py:413-443): row i describes one game.  DEVICE pointers.
+ *   ships R [m][S][5] = x, y, dx, dy, b    planets [m][4][4] (dead slots zero)    bullets [m][k][4] (dead slots zero)
+ *   n_planets / n_bullets / tick i32 [m]   finished u8 [m]   episode u32 [m] (may be NULL) */
+typedef struct AstroGameArrays {
+    double* ships;
+    double* planets;
+    double* bullets;
+    int32_t* n_planets;
+    int32_t* n_bullets;
+    int32_t* tick;
+    uint8_t* finished;
+    uint32_t* episode;
+    int32_t bullet_rows; /* k: rows per game of `bullets` (export: >= the largest live count wanted; import: <= bullet_cap) */
+    int32_t reserved;
+} AstroGameArrays;
+
+/* Games index[0..m-1] (device i32; NULL: games 0..m-1) -> rows 0..m-1 of `out`, one kernel: the tile lists are unpacked
+ * on the device.  Float32 state converts exactly.  A finished game exports finished = 1, n_bullets = 0. */
+int astro_export_games(AstroBatch* b, const int32_t* index, int32_t m, const AstroGameArrays* out, void* stream);
+/* The inverse: rows 0..m-1 of `in` replace games index[0..m-1] (NULL: games 0..m-1; an index must not repeat), every
+ * other game — including the bullets of the other games of a touched tile — is kept.  Float32 batches round the values
+ * to float32.  n_bullets is clipped to bullet_cap.  `tick` = the game's index on the batch's schedule (astro_set_schedule). */
+int astro_import_games(AstroBatch* b, const int32_t* index, int32_t m, const AstroGameArrays* in, void* stream);
+
+/* core.step (core.py:215-303) for ONE game with HOST buffers — the body of the drop-in astro_b200.core.step: one pinned
+ * record in, import -> tick -> export on the stream, one record out, then a stream synchronise.  The batch must hold
+ * exactly one tile (n_games = 32); game 0 is used.  The record is followed in memory by double bullets[bullet_cap][4]
+ * (astro_single_game_bytes); only the live rows travel.
+ *   in:  ships / planets / bullets / n_planets / n_bullets, control[s], tick = where the game stands on the batch's
+ *        schedule (the host evaluates the reload / timeout predicates of core.py:257-267 in Python floats and picks
+ *        the index of a schedule entry with that outcome)
+ *   out: the new state (tick + 1), events[0] = ASTRO_EV_* of the tick, finished = 1 when the game ended */
+typedef struct AstroSingleGame {
+    double ships[ASTRO_MAX_SHIPS][5];
+    double planets[ASTRO_MAX_PLANETS][4];
+    int32_t n_planets, n_bullets, tick, reserved;
+    uint32_t episode;
+    uint8_t finished[4];
+    uint8_t control[ASTRO_TILE * ASTRO_MAX_SHIPS]; /* [0..S-1] are read; the rest belongs to the tile's empty slots */
+    uint8_t events[ASTRO_TILE];                    /* [0] is the game's */
+} AstroSingleGame;
+int64_t astro_single_game_bytes(int32_t bullet_cap);
+int astro_step_single_host(AstroBatch* b, const AstroSingleGame* in_host, AstroSingleGame* out_host, int32_t flags, void* stream);
 
 /* Copies the ASTRO_N_STATS device counters into counters_dev (device pointer, e.g. the input of
  * an NCCL all-reduce) on the stream; clear != 0 zeroes them afterwards. */

@@ -136,6 +136,32 @@ static void gravity(const ao_config* c, int P, const double* planets /*[P][4]*/,
     *a1 = s1;
 }
 
+/* The same on the arrays core.create returns (core.py:86-135): positions are float32 there, so on a game's FIRST
+ * tick numpy evaluates _gravity in float32 (NEP 50: the Python-float constants are weak scalars) — rx, rx**2,
+ * the sum, maximum(1e-12, .), the division and the products are float32 operations, one rounding each. */
+static void gravity_f32(const ao_config* c, int P, const double* planets /*[P][4], float32 values*/, float x0, float x1,
+                        float* a0, float* a1) {
+    float gm = (float)(c->gravity * c->planet_mass);
+    float s0 = 0, s1 = 0;
+    for (int j = 0; j < P; j++) {
+        float r0 = (float)planets[4 * j] - x0, r1 = (float)planets[4 * j + 1] - x1;
+        float q0 = r0 * r0, q1 = r1 * r1;
+        float d2 = q0 + q1;
+        float f = gm / (1e-12f > d2 ? 1e-12f : d2);
+        float t0 = f * r0, t1 = f * r1;
+        if (j == 0) { s0 = t0; s1 = t1; } else { s0 = s0 + t0; s1 = s1 + t1; }
+    }
+    *a0 = s0;
+    *a1 = s1;
+}
+/* |b - a|^2 of float32 positions, evaluated in float32 (core.py:210 on create()'s arrays); the comparison with the
+ * float64 r2 promotes it exactly. */
+static double dist2_f32(double ax, double ay, double bx, double by) {
+    float d0 = (float)bx - (float)ax, d1 = (float)by - (float)ay;
+    float q0 = d0 * d0, q1 = d1 * d1;
+    return (double)(q0 + q1);
+}
+
 static int in_arena(double x0, double x1) {
     /* core.py:195: (([-1,-1] <= x) & (x <= [1,1])).any(axis=1) */
     return ((-1.0 <= x0) & (x0 <= 1.0)) | ((-1.0 <= x1) & (x1 <= 1.0));
@@ -149,10 +175,14 @@ static int in_arena(double x0, double x1) {
  * from the END of the reference order (they can only be newborn) and OVERFLOW is flagged —
  * the device pool policy.
  */
-int ao_step_one(const ao_config* c, int S, int P, int B, int bullet_cap, const double* ships,
+/* raw != 0: the state holds the arrays core.create returned (float32 ships, planet positions, no bullets): the
+ * reference's first tick then runs _gravity and the squared distances of _collisions in float32, the planets'
+ * a * dt too (float32 array times a Python float), and a bullet born on that very tick (reload_time <= dt) is
+ * float32 throughout.  Everything else promotes to float64 as on any other tick. */
+static int step_impl(const ao_config* c, int S, int P, int B, int bullet_cap, const double* ships,
                 const double* planets, const double* bullets, double reload, double t,
                 const int64_t* control, double* ships_o, double* planets_o, double* bullets_o,
-                int32_t* B_o, double* reload_o, double* t_o, double* reward, int32_t* events) {
+                int32_t* B_o, double* reload_o, double* t_o, double* reward, int32_t* events, int raw) {
     float dir[AO_MAXS][2];
     double acc[AO_MAXS][2], db[AO_MAXS];
     int ev = 0;
@@ -161,7 +191,14 @@ int ao_step_one(const ao_config* c, int S, int P, int B, int bullet_cap, const d
     for (int i = 0; i < S; i++) {
         np_sincos_f32((float)ships[5 * i + 4], &dir[i][0], &dir[i][1]);
         double g0, g1;
-        gravity(c, P, planets, ships[5 * i], ships[5 * i + 1], &g0, &g1);
+        if (raw) {
+            float f0, f1;
+            gravity_f32(c, P, planets, (float)ships[5 * i], (float)ships[5 * i + 1], &f0, &f1);
+            g0 = (double)f0;
+            g1 = (double)f1;
+        } else {
+            gravity(c, P, planets, ships[5 * i], ships[5 * i + 1], &g0, &g1);
+        }
         /* floor mod / floor div of the control code, as numpy % and // on int64 */
         int64_t ctl = control[i];
         int64_t m2 = ((ctl % 2) + 2) % 2;
@@ -183,11 +220,13 @@ int ao_step_one(const ao_config* c, int S, int P, int B, int bullet_cap, const d
         for (int j = 0; j < S; j++) {
             if (j == i) continue;
             double d0 = ships[5 * j] - x0, d1 = ships[5 * j + 1] - x1;
-            ship_hit[i] |= (d0 * d0 + d1 * d1 < R_ss);
+            double rx2 = raw ? dist2_f32(x0, x1, ships[5 * j], ships[5 * j + 1]) : d0 * d0 + d1 * d1;
+            ship_hit[i] |= (rx2 < R_ss);
         }
         for (int j = 0; j < P; j++) {
             double d0 = planets[4 * j] - x0, d1 = planets[4 * j + 1] - x1;
-            ship_hit[i] |= (d0 * d0 + d1 * d1 < R_sp);
+            double rx2 = raw ? dist2_f32(x0, x1, planets[4 * j], planets[4 * j + 1]) : d0 * d0 + d1 * d1;
+            ship_hit[i] |= (rx2 < R_sp);
         }
         for (int j = 0; j < B; j++) {
             double d0 = bullets[4 * j] - x0, d1 = bullets[4 * j + 1] - x1;
@@ -244,10 +283,17 @@ int ao_step_one(const ao_config* c, int S, int P, int B, int bullet_cap, const d
         for (int i = 0; i < S; i++) {
             float o0 = off * dir[i][0], o1 = off * dir[i][1]; /* float32 products */
             float v0 = spd * dir[i][0], v1 = spd * dir[i][1];
-            bullets_o[4 * n + 0] = ships[5 * i + 0] + (double)o0;
-            bullets_o[4 * n + 1] = ships[5 * i + 1] + (double)o1;
-            bullets_o[4 * n + 2] = ships[5 * i + 2] + (double)v0;
-            bullets_o[4 * n + 3] = ships[5 * i + 3] + (double)v1;
+            if (raw) { /* float32 ship state + float32 product: a float32 sum */
+                bullets_o[4 * n + 0] = (double)((float)ships[5 * i + 0] + o0);
+                bullets_o[4 * n + 1] = (double)((float)ships[5 * i + 1] + o1);
+                bullets_o[4 * n + 2] = (double)((float)ships[5 * i + 2] + v0);
+                bullets_o[4 * n + 3] = (double)((float)ships[5 * i + 3] + v1);
+            } else {
+                bullets_o[4 * n + 0] = ships[5 * i + 0] + (double)o0;
+                bullets_o[4 * n + 1] = ships[5 * i + 1] + (double)o1;
+                bullets_o[4 * n + 2] = ships[5 * i + 2] + (double)v0;
+                bullets_o[4 * n + 3] = ships[5 * i + 3] + (double)v1;
+            }
             n++;
         }
         next_reload -= c->reload_time;
@@ -266,9 +312,18 @@ int ao_step_one(const ao_config* c, int S, int P, int B, int bullet_cap, const d
         ships_o[5 * i + 4] = ships[5 * i + 4] + db[i];
     }
     for (int i = 0; i < P; i++) {
-        double g0, g1;
-        gravity(c, P, planets, planets[4 * i], planets[4 * i + 1], &g0, &g1);
-        double v0 = planets[4 * i + 2] + g0 * dt, v1 = planets[4 * i + 3] + g1 * dt;
+        double g0, g1, v0, v1;
+        if (raw) { /* float32 field times the weak scalar dt: a float32 product, then the float64 sum */
+            float f0, f1;
+            gravity_f32(c, P, planets, (float)planets[4 * i], (float)planets[4 * i + 1], &f0, &f1);
+            float p0 = f0 * (float)dt, p1 = f1 * (float)dt;
+            v0 = planets[4 * i + 2] + (double)p0;
+            v1 = planets[4 * i + 3] + (double)p1;
+        } else {
+            gravity(c, P, planets, planets[4 * i], planets[4 * i + 1], &g0, &g1);
+            v0 = planets[4 * i + 2] + g0 * dt;
+            v1 = planets[4 * i + 3] + g1 * dt;
+        }
         double x0 = planets[4 * i + 0] + dt * v0, x1 = planets[4 * i + 1] + dt * v1;
         planets_o[4 * i + 0] = wrap_unit(x0);
         planets_o[4 * i + 1] = wrap_unit(x1);
@@ -280,6 +335,12 @@ int ao_step_one(const ao_config* c, int S, int P, int B, int bullet_cap, const d
     for (int i = 0; i < n; i++) {
         double v0 = bullets_o[4 * i + 2] + zero_dt, v1 = bullets_o[4 * i + 3] + zero_dt;
         double x0 = bullets_o[4 * i + 0] + dt * v0, x1 = bullets_o[4 * i + 1] + dt * v1;
+        if (raw) { /* (only newborn exist on a first tick) float32 arrays and weak scalars: float32 operations */
+            float w0 = (float)bullets_o[4 * i + 2] + (float)zero_dt, w1 = (float)bullets_o[4 * i + 3] + (float)zero_dt;
+            float m0 = (float)dt * w0, m1 = (float)dt * w1;
+            float y0 = (float)bullets_o[4 * i + 0] + m0, y1 = (float)bullets_o[4 * i + 1] + m1;
+            v0 = (double)w0; v1 = (double)w1; x0 = (double)y0; x1 = (double)y1;
+        }
         if (!in_arena(x0, x1)) continue;
         bullets_o[4 * m + 0] = x0;
         bullets_o[4 * m + 1] = x1;
@@ -297,6 +358,22 @@ int ao_step_one(const ao_config* c, int S, int P, int B, int bullet_cap, const d
     for (int i = 0; i < S; i++) reward[i] = 0.0;
     *events = ev;
     return 0;
+}
+
+int ao_step_one(const ao_config* c, int S, int P, int B, int bullet_cap, const double* ships,
+                const double* planets, const double* bullets, double reload, double t,
+                const int64_t* control, double* ships_o, double* planets_o, double* bullets_o,
+                int32_t* B_o, double* reload_o, double* t_o, double* reward, int32_t* events) {
+    return step_impl(c, S, P, B, bullet_cap, ships, planets, bullets, reload, t, control, ships_o, planets_o, bullets_o, B_o,
+                     reload_o, t_o, reward, events, 0);
+}
+/* The first tick after core.create, on create()'s own dtypes (see step_impl). */
+int ao_step_one_raw(const ao_config* c, int S, int P, int B, int bullet_cap, const double* ships,
+                    const double* planets, const double* bullets, double reload, double t,
+                    const int64_t* control, double* ships_o, double* planets_o, double* bullets_o,
+                    int32_t* B_o, double* reload_o, double* t_o, double* reward, int32_t* events) {
+    return step_impl(c, S, P, B, bullet_cap, ships, planets, bullets, reload, t, control, ships_o, planets_o, bullets_o, B_o,
+                     reload_o, t_o, reward, events, 1);
 }
 
 /*

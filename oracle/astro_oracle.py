@@ -56,6 +56,8 @@ def lib():
         L.ao_step_one.argtypes = [C.POINTER(Config), i32, i32, i32, i32, vp, vp, vp, f64, f64, vp,
                                   vp, vp, vp, vp, vp, vp, vp, vp]
         L.ao_step_one.restype = i32
+        L.ao_step_one_raw.argtypes = L.ao_step_one.argtypes
+        L.ao_step_one_raw.restype = i32
         L.ao_step_batch.argtypes = [C.POINTER(Config), i64, i32, i32] + [vp] * 18 + [i32]
         L.ao_features.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, vp]
         L.ao_features.restype = i32
@@ -104,8 +106,9 @@ def collisions(x, r):
     return hit.astype(bool)
 
 
-def step_one(cfg, ships, planets, bullets, reload, t, control, bullet_cap=-1):
-    """One game, one tick.  Returns dict(done, reward, events[, ships, planets, bullets, reload, t])."""
+def step_one(cfg, ships, planets, bullets, reload, t, control, bullet_cap=-1, raw=False):
+    """One game, one tick.  Returns dict(done, reward, events[, ships, planets, bullets, reload, t]).
+    raw=True: the state is what core.create returned (float32 arrays): the reference's first-tick arithmetic."""
     c = cfg if isinstance(cfg, Config) else Config.from_any(cfg)
     ships = np.ascontiguousarray(ships, dtype=np.float64).reshape(-1, 5)
     planets = np.ascontiguousarray(planets, dtype=np.float64).reshape(-1, 4)
@@ -115,7 +118,7 @@ def step_one(cfg, ships, planets, bullets, reload, t, control, bullet_cap=-1):
     so, po, bo = np.empty_like(ships), np.empty_like(planets), np.empty((B + S, 4))
     nb, ro, to = C.c_int32(0), C.c_double(0), C.c_double(0)
     rew, ev = np.zeros(S), C.c_int32(0)
-    term = lib().ao_step_one(C.byref(c), S, P, B, bullet_cap, _p(ships), _p(planets), _p(bullets),
+    term = (lib().ao_step_one_raw if raw else lib().ao_step_one)(C.byref(c), S, P, B, bullet_cap, _p(ships), _p(planets), _p(bullets),
                              float(reload), float(t), _p(control), _p(so), _p(po), _p(bo),
                              C.byref(nb), C.byref(ro), C.byref(to), _p(rew), C.byref(ev))
     out = dict(done=bool(term), reward=rew, events=ev.value)

@@ -18,6 +18,9 @@ this file:
   edges.npz/.json hand-built knife-edge and terminal-precedence cases through core.step
   schedule.json   spawn ticks / timeout tick observed by running core.step itself
   features.npz    rl.ValueNetwork.get_features / get_features_batch (rl.py:43-112)
+  traj_raw.npz/.json  trajectories from core.create's RAW float32 arrays (the first tick's float32 arithmetic)
+  network.npz     rl.ValueNetwork (rl.py:115-165) with seeded weights: evaluate / evaluate_batch outputs + state_dict
+  explore.json    rl.EpsilonGreedy (rl.py:10-30): empirical transition rates and control histogram
 
 Everything downstream (oracle/, tests/) reads only these files.
 """
@@ -136,9 +139,11 @@ def make_create():
 
 # ------------------------------------------------------------------ trajectories
 
-def run_game(config, control_fn, state0=None, max_ticks=None):
-    """Teacher = the reference.  Returns dict of per-tick arrays (pre-step states)."""
-    state = f64_state(core.create(config) if state0 is None else state0)
+def run_game(config, control_fn, state0=None, max_ticks=None, raw=False):
+    """Teacher = the reference.  Returns dict of per-tick arrays (pre-step states).
+    raw=True: the game starts from core.create's own arrays (float32 positions), NOT canonicalised:
+    the reference's first tick then runs partly in float32 (recorded values are exact in float64)."""
+    state = core.create(config) if raw else f64_state(core.create(config) if state0 is None else state0)
     ships, planets, nb, bullets, reload_, t_, ctrl, rew = [], [], [], [], [], [], [], []
     k = 0
     while True:
@@ -157,7 +162,7 @@ def run_game(config, control_fn, state0=None, max_ticks=None):
         if nxt is None:
             truncated = False
             break
-        assert nxt.ships.x.dtype == np.float64 and nxt.planets.x.dtype == np.float64
+        assert nxt.ships.x.dtype == np.float64 and (raw or nxt.planets.x.dtype == np.float64)
         state = nxt
         if max_ticks is not None and k >= max_ticks:
             truncated = True
@@ -214,6 +219,33 @@ def make_traj():
         add('solo_script_timeout', c, lambda s, k, bot=bot: np.array([bot(s)]))
     np.savez_compressed(os.path.join(HERE, 'traj.npz'), **arrays)
     with open(os.path.join(HERE, 'traj.json'), 'w') as f:
+        json.dump(meta, f, indent=1)
+
+
+def make_traj_raw():
+    """Games played by the reference from core.create's RAW output (float32 ships / planet positions): pins the
+    float32 arithmetic of the first tick (core.py:138-153, :200-212 on float32 arrays) and everything after it."""
+    arrays, meta = {}, []
+
+    def add(kind, config, control_fn, **kw):
+        g = len(meta)
+        data, truncated = run_game(config, control_fn, raw=True, **kw)
+        for k, v in data.items():
+            arrays['g%d_%s' % (g, k)] = v
+        meta.append(dict(game=g, kind=kind, config=cfg_dict(config), nships=int(data['ships'].shape[1]),
+                         nplanets=int(data['planets'].shape[1]), nticks=int(data['ships'].shape[0]),
+                         truncated=bool(truncated), max_bullets=int(data['nb'].max())))
+        print('raw', kind, meta[-1]['nticks'], 'ticks, P =', meta[-1]['nplanets'])
+
+    for g, c in enumerate(it.islice(core.generate_configs(core.DEFAULT_CONFIG._replace(seed=7)), 12)):
+        add('duel_random_raw', c, lambda s, k, g=g: rng.actions(3, np.array([g]), k, 2)[0], max_ticks=120)
+    # ships fire on the very first tick (reload_time <= dt): the newborn are float32 throughout
+    for g, c in enumerate(it.islice(core.generate_configs(core.DEFAULT_CONFIG._replace(seed=8, reload_time=0.02)), 4)):
+        add('duel_fire_every_tick_raw', c, lambda s, k, g=g: rng.actions(4, np.array([g]), k, 2)[0], max_ticks=40)
+    for c in it.islice(core.generate_configs(core.SOLO_CONFIG._replace(seed=9)), 3):
+        add('solo_nothing_raw', c, lambda s, k: np.array([3]), max_ticks=80)
+    np.savez_compressed(os.path.join(HERE, 'traj_raw.npz'), **arrays)
+    with open(os.path.join(HERE, 'traj_raw.json'), 'w') as f:
         json.dump(meta, f, indent=1)
 
 
@@ -418,7 +450,81 @@ def make_features():
     print(len(arrays), 'feature arrays')
 
 
+def make_network():
+    """The reference's ValueNetwork (rl.py:32-165) with seeded weights on the states of features.npz:
+    evaluate / evaluate_batch outputs for ship 0's perspective and (duel) the rolled perspective of ship 1,
+    plus the flattened state_dict — pins forward, forward_both and the fused policy kernel."""
+    import torch
+    z = np.load(os.path.join(HERE, 'traj.npz'))
+    fmeta = json.load(open(os.path.join(HERE, 'features.json')))
+    arrays = {}
+    nets = {}
+    for solo in (False, True):
+        torch.manual_seed(1234 + int(solo))
+        net = rl.ValueNetwork(solo=solo, nout=6)
+        with torch.no_grad():                 # (default init is small: widen it so that the outputs spread over (-1, 1))
+            for p_ in net.parameters():
+                p_.mul_(3.0)
+        nets[solo] = net
+        for name, v in net.state_dict().items():
+            arrays['%s_%s' % ('solo' if solo else 'duel', name.replace('.', '_'))] = v.numpy().copy()
+    for m in fmeta:
+        g, solo = m['game'], m['nships'] == 1
+        nb = z['g%d_nb' % g]
+        off = np.concatenate([[0], np.cumsum(nb)])
+        states = []
+        for k in m['ticks']:
+            sh, pl, bl = z['g%d_ships' % g][k], z['g%d_planets' % g][k], z['g%d_bullets' % g][off[k]:off[k + 1]]
+            states.append(core.State(ships=core.Bodies(sh[:, 0:2], sh[:, 2:4], sh[:, 4]),
+                                     planets=core.Bodies(pl[:, 0:2], pl[:, 2:4], None),
+                                     bullets=core.Bodies(bl[:, 0:2], bl[:, 2:4], None),
+                                     reload=float(z['g%d_reload' % g][k]), t=float(z['g%d_t' % g][k])))
+        net = nets[solo]
+        with torch.no_grad():
+            arrays['g%d_q0' % g] = net.evaluate_batch(states).numpy()
+            arrays['g%d_q0_single' % g] = np.stack([net.evaluate(s).numpy() for s in states])
+            if not solo:
+                arrays['g%d_q1' % g] = net.evaluate_batch([core.roll_ships(s, 1) for s in states]).numpy()
+    np.savez_compressed(os.path.join(HERE, 'network.npz'), **arrays)
+    print(len(arrays), 'network arrays; torch', torch.__version__)
+
+
+def make_explore():
+    """rl.EpsilonGreedy (rl.py:10-30) run by the reference itself over many calls at the game's dt: the empirical
+    enter / leave rates, the active fraction and the histogram of its random controls — what the device-side
+    process (another random stream) has to reproduce statistically."""
+    State = core.State
+    out = []
+    for t_in, t_out in ((1.0, 0.1), (0.5, 0.5)):
+        eg = rl.EpsilonGreedy(t_in, t_out, seed=5)
+        dt, n = 0.02, 400000
+        idle_calls = active_calls = entered = left = 0
+        hist = [0] * 6
+        t = 0.0
+        for k in range(n):
+            was = eg._policy
+            now = eg(State(None, None, None, 0.0, t))
+            t += dt
+            if was is None:
+                idle_calls += 1
+                entered += now is not None
+            else:
+                active_calls += 1
+                left += now is None
+            if now is not None:
+                hist[int(now)] += 1
+        out.append(dict(t_in=t_in, t_out=t_out, dt=dt, calls=n, idle_calls=idle_calls, active_calls=active_calls,
+                        entered=int(entered), left=int(left), hist=hist))
+    with open(os.path.join(HERE, 'explore.json'), 'w') as f:
+        json.dump(out, f, indent=1)
+    print('explore', out)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1:          # python make_golden.py make_network make_explore ...: only the named parts
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     make_kat()
     make_sincos()
     make_create()
@@ -426,4 +532,7 @@ if __name__ == '__main__':
     make_edges()
     make_schedule()
     make_features()
+    make_traj_raw()
+    make_network()
+    make_explore()
     print('numpy', np.__version__)

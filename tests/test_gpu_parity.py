@@ -285,10 +285,10 @@ def _stress_fill(K, seed):
 
 @pytest.mark.parametrize('K', [400, 32])
 def test_config3_65536_games_max_bullet_pool(K):
-    """BASELINE config #3: 65,536 games with pre-filled bullet pools (K=400 is the lossless
+    """BASELINE config #3 at its stated size: 65,536 games with pre-filled bullet pools (K=400 is the lossless
     bound of the default config, K=32 the production cap): despawn, spawn at capacity, cull and
     compaction order checked element-wise against the oracle for several ticks."""
-    N = 65536 if K == 32 else 16384
+    N = 65536
     games, worst, n_done, n_fired = _teacher_forced(core.DEFAULT_CONFIG, N, K, 6, 32, start=_stress_fill(K, 3))
     assert n_done > 0 and n_fired > 0
     st = games.stats()
@@ -781,12 +781,14 @@ def test_policy_kernel_matches_value_network(solo):
         assert (out[:, 1] == 9).all() and (out[:N, 0] == act[:N, 0]).all()
 
 
-def test_policy_rollout_equals_torch_rollout():
+@pytest.mark.parametrize('N,T', [(1024, 150), (16384, 1000)])
+def test_policy_rollout_equals_torch_rollout(N, T):
     """A self-play rollout driven by the fused kernel ends in the same statistics as one driven by
-    observe() -> ValueNetwork -> argmax (config #5 of BASELINE.json at reduced size)."""
+    observe() -> ValueNetwork -> argmax — BASELINE config #5, at a reduced size and at its stated size
+    (16,384 games x 1,000 ticks, observation extraction feeding the policy batch every tick)."""
     import torch
     from astro_b200 import rl
-    cfg, N, K = core.DEFAULT_CONFIG, 1024, 32
+    cfg, K = core.DEFAULT_CONFIG, 32
     pool = H.make_pool(cfg, 256)
     torch.manual_seed(5)
     net = rl.ValueNetwork(solo=False, nout=6).cuda()
@@ -800,14 +802,15 @@ def test_policy_rollout_equals_torch_rollout():
         games.reset_all()
         games.set_policy(net)
         same = 0
-        for k in range(150):
+        for k in range(T):
             with torch.no_grad():
                 a_torch = net(games.observe()).argmax(-1).to(torch.uint8)
             a_fused = games.policy_controls()[:N]
             same += int((a_torch == a_fused).sum())
             games.step(a_fused if fused else a_torch, auto_reset=True)
-        runs.append((games.stats(), same / (150 * N * 2)))
+        runs.append((games.stats(), same / (T * N * 2)))
     assert runs[0][1] > 0.9995 and runs[1][1] > 0.9995          # controls agree except at near-ties
+    assert runs[0][0]['env_steps'] == N * T
     assert abs(runs[0][0]['episodes'] - runs[1][0]['episodes']) <= 0.05 * runs[0][0]['episodes'] + 5
 
 
@@ -987,6 +990,57 @@ def test_tick_many_equals_tick_by_tick(with_actions):
     assert H.same_bits(a0['planets'][pm], a1['planets'][pm]) and H.same_bits(a0['bullets'][bm], a1['bullets'][bm])
 
 
+@pytest.mark.parametrize('with_actions', [False, True])
+def test_tick_many_without_auto_reset_freezes_games_like_separate_ticks(with_actions):
+    """astro_tick_many with auto-reset OFF (replays, rollout_host(auto_reset=False)): a game that ends on a non-last
+    tick of a launch must leave its finished word (and the ending tick's ships) in memory at once — the later ticks of
+    the launch skip it.  A short max_time makes every game end mid-launch; compared with separate astro_tick calls on
+    meta, ships, bullets, events, done — and the launch that follows must skip the frozen games, not resurrect them."""
+    import torch
+    cfg, N, K, T = core.DEFAULT_CONFIG._replace(max_time=0.9), 2048, 32, 48     # timeout on a game's 45th tick
+    pool = H.make_pool(cfg, 256)
+    runs = []
+    for fused in (False, True):
+        g = _games(cfg, N, bullet_cap=K, precision=32, seed=9)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        for _ in range(20):
+            g.step(None, auto_reset=True)                 # games now sit at different ticks: they time out on ticks 25..45 of T
+        g.stats(clear=True)
+        gen = torch.Generator(device='cpu').manual_seed(3)
+        acts = torch.randint(0, 6, (T + 8, g.n_pad, 2), dtype=torch.uint8, generator=gen).cuda() if with_actions else None
+        ev = torch.zeros((T + 8, g.n_pad), dtype=torch.uint8, device='cuda')
+        dn = torch.zeros((T + 8, g.n_pad), dtype=torch.uint8, device='cuda')
+        if fused:
+            g.step_many(T, None if acts is None else acts[:T].contiguous(), events=ev[:T], done=dn[:T], auto_reset=False)
+        else:
+            for k in range(T):
+                _, d, e = g.step(None if acts is None else acts[k], auto_reset=False)
+                ev[k], dn[k] = e, d
+        mid = g.get_arrays()
+        # the follow-up launch: frozen games are skipped (ASTRO_EV_SKIPPED), the others carry on
+        if fused:
+            g.step_many(8, None if acts is None else acts[T:].contiguous(), events=ev[T:], done=dn[T:], auto_reset=False)
+        else:
+            for k in range(T, T + 8):
+                _, d, e = g.step(None if acts is None else acts[k], auto_reset=False)
+                ev[k], dn[k] = e, d
+        runs.append((mid, g.get_arrays(), ev.cpu().numpy(), dn.cpu().numpy(), g.stats(), g.observe().cpu().numpy()))
+    (m0, a0, e0, d0, s0, o0), (m1, a1, e1, d1, s1, o1) = runs
+    assert (e0 == e1).all() and (d0 == d1).all() and s0 == s1
+    assert m0['finished'].sum() > N // 2 and s0['skipped'] > 0
+    assert ((e0[T:] & nat.EV_SKIPPED) != 0).sum() >= m0['finished'].sum() * 8
+    for a, b in ((m0, m1), (a0, a1)):
+        for k in ('n_bullets', 'n_planets', 'tick', 'episode', 'finished'):
+            assert (a[k] == b[k]).all(), k
+        assert H.same_bits(a['ships'], b['ships'])        # finished games included: the ending tick's post-step ships
+        live = ~a['finished']
+        pm = (np.arange(4)[None, :] < a['n_planets'][:, None]) & live[:, None]
+        bm = (np.arange(K)[None, :] < a['n_bullets'][:, None]) & live[:, None]
+        assert H.same_bits(a['planets'][pm], b['planets'][pm]) and H.same_bits(a['bullets'][bm], b['bullets'][bm])
+    assert H.same_bits(o0, o1)
+
+
 def test_explore_controls_match_host_twin_and_the_reference_process():
     """astro_explore_controls (rl.EpsilonGreedy, rl.py:10-30, as rl.QBotTrainer lays it over the greedy control,
     rl.py:249-258): every ship's state and control equal the host twin (astro_b200/rng.py explore_step, same counter
@@ -1132,3 +1186,234 @@ def test_set_states_inside_live_tiles_keeps_the_other_games_lists():
     xa, xb = a.get_arrays(), b.get_arrays()
     ok = ~xa['finished']
     assert (xa['finished'] == xb['finished']).all() and (xa['ships'][ok] == xb['ships'][ok]).all() and (xa['n_bullets'][ok] == xb['n_bullets'][ok]).all()
+
+
+# ------------------------------------------------------------------ round 2: reference-pinned network, raw create(), guards
+
+def _golden_states(z, e):
+    g = e['game']
+    nb = z['g%d_nb' % g]
+    off = np.concatenate([[0], np.cumsum(nb)])
+    return [H.state_from_arrays(z['g%d_ships' % g][k], z['g%d_planets' % g][k], z['g%d_bullets' % g][off[k]:off[k + 1]], 0.0, 0.0)
+            for k in e['ticks']]
+
+
+@pytest.mark.parametrize('precision', [64, 32])
+def test_policy_kernel_matches_reference_network_outputs(precision):
+    """The fused policy kernel (features + network, no observation tensor) against outputs of the UNMODIFIED
+    reference: rl.ValueNetwork.evaluate_batch (rl.py:140-165) with seeded weights on states of the golden games,
+    ship 0's perspective and ship 1's (core.roll_ships) — tests/golden/network.npz.  float64 state: q within 2e-6
+    and the argmax equal off ties; float32 state (bearings rounded to float32 before norm_angle): within 2e-5."""
+    import torch
+    from astro_b200 import rl
+    z, _ = H.load_traj()
+    gold = np.load(os.path.join(H.G, 'network.npz'))
+    fm = json.load(open(os.path.join(H.G, 'features.json')))
+    tol = 2e-6 if precision == 64 else 2e-5
+    for solo in (False, True):
+        entries = [e for e in fm if (e['nships'] == 1) == solo]
+        states, want0, want1 = [], [], []
+        for e in entries:
+            states += _golden_states(z, e)
+            want0.append(gold['g%d_q0' % e['game']])
+            if not solo:
+                want1.append(gold['g%d_q1' % e['game']])
+        want = np.concatenate(want0)[:, None, :] if solo else np.stack([np.concatenate(want0), np.concatenate(want1)], axis=1)
+        net = rl.ValueNetwork(solo=solo, nout=6)
+        pre = 'solo_' if solo else 'duel_'
+        net.load_state_dict({k: torch.from_numpy(gold[pre + k.replace('.', '_')]) for k in net.state_dict()})
+        cfg = core.SOLO_CONFIG if solo else core.DEFAULT_CONFIG
+        cap = max(32, max(s.bullets.x.shape[0] for s in states))
+        games = _games(cfg, len(states), bullet_cap=cap, precision=precision)
+        games.set_states(states, ticks=np.zeros(len(states), dtype=np.int64))
+        games.set_policy(net)
+        S = 1 if solo else 2
+        q = torch.empty((games.n_pad, S, 6), dtype=torch.float32, device='cuda')
+        act = games.policy_controls(q_out=q).cpu().numpy()[:len(states)]
+        got = q.cpu().numpy()[:len(states)]
+        assert np.abs(got - want).max() <= tol, (solo, np.abs(got - want).max())
+        top = np.sort(want, axis=-1)
+        clear = (top[..., -1] - top[..., -2]) > 10 * tol
+        assert clear.mean() > 0.8 and (act[clear] == want.argmax(-1)[clear]).all()
+        # the PyTorch twin on the device's own observation: forward (both perspectives) and forward_both
+        net = net.cuda()
+        with torch.no_grad():
+            obs = games.observe()
+            assert float((net(obs)[:len(states)].cpu() - torch.from_numpy(want)).abs().max()) <= tol
+            if not solo:
+                both = net.forward_both(games.observe(shared=True))
+                assert float((both[:len(states)].cpu() - torch.from_numpy(want)).abs().max()) <= tol
+
+
+def test_two_batches_hold_two_networks():
+    """The policy weights belong to the batch handle: two batches with different networks do not share the last one set."""
+    import torch
+    from astro_b200 import rl
+    cfg = core.DEFAULT_CONFIG
+    pool = H.make_pool(cfg, 64)
+    outs = []
+    batches = []
+    for seed in (1, 2):
+        g = _games(cfg, 256, bullet_cap=32, precision=32, seed=0)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        torch.manual_seed(seed)
+        net = rl.ValueNetwork(solo=False, nout=6).cuda()
+        g.set_policy(net)
+        batches.append((g, net))
+    for g, net in batches:      # both networks were loaded before either is used
+        q = torch.empty((g.n_pad, 2, 6), dtype=torch.float32, device='cuda')
+        g.policy_controls(q_out=q)
+        with torch.no_grad():
+            assert float((q[:256] - net(g.observe())).abs().max()) <= 2e-6
+        outs.append(q)
+    assert float((outs[0] - outs[1]).abs().max()) > 1e-3
+
+
+def test_core_step_from_raw_create_matches_reference_play():
+    """core.play's loop from core.create's RAW arrays (float32): the reference runs the first tick partly in float32
+    (NEP 50), which astro_b200.core.step reproduces (ASTRO_TICK_ALL_CREATE_DTYPES) — every state of the reference's
+    games, bit for bit, free-running from create() (tests/golden/traj_raw.npz), fire-on-the-first-tick included."""
+    z = np.load(os.path.join(H.G, 'traj_raw.npz'))
+    meta = json.load(open(os.path.join(H.G, 'traj_raw.json')))
+    total = 0
+    for m in meta:
+        g = m['game']
+        cfg = H.config_from(m['config'])
+        ships, planets, nb, bullets = z['g%d_ships' % g], z['g%d_planets' % g], z['g%d_nb' % g], z['g%d_bullets' % g]
+        off = np.concatenate([[0], np.cumsum(nb)])
+        state = core.create(cfg)
+        assert state.ships.x.dtype == np.float32
+        n = min(m['nticks'], 60)
+        for k in range(n):
+            assert H.same_bits(np.concatenate([state.ships.x, state.ships.dx, np.asarray(state.ships.b)[:, None]], 1), ships[k]), (g, k)
+            assert H.same_bits(np.concatenate([state.planets.x, state.planets.dx], 1), planets[k]), (g, k)
+            assert H.same_bits(np.concatenate([state.bullets.x, state.bullets.dx], 1).reshape(-1, 4), bullets[off[k]:off[k + 1]]), (g, k)
+            assert state.reload == z['g%d_reload' % g][k] and state.t == z['g%d_t' % g][k]
+            state, reward = core.step(state, z['g%d_control' % g][k], cfg)
+            assert (np.asarray(reward, dtype=np.float64) == z['g%d_reward' % g][k]).all()
+            total += 1
+            if state is None:
+                assert k == m['nticks'] - 1 and not m['truncated']
+                break
+    assert total > 600
+
+
+def test_batched_float64_create_dtypes_flag():
+    """ASTRO_TICK_CREATE_DTYPES on a float64 batch: games on their tick 0 (as re-created from a create() pool) run the
+    reference's first-tick arithmetic, every other game the float64 one — against the oracle's raw / plain modes."""
+    cfg, N, K = core.DEFAULT_CONFIG, 512, 32
+    pool = H.make_pool(cfg, 256)
+    games = _games(cfg, N, bullet_cap=K, precision=64, seed=2)
+    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+    games.reset_all()
+    games.tick_flags = nat.TICK_CREATE_DTYPES
+    ids = np.arange(N)
+    n_raw = 0
+    for k in range(150):
+        arr = games.get_arrays()
+        ctl = rng.actions(2, ids, k, 2)
+        want = [ao.step_one(cfg, arr['ships'][g], arr['planets'][g, :arr['n_planets'][g]], arr['bullets'][g, :arr['n_bullets'][g]],
+                            games.schedule.reload[arr['tick'][g]], games.schedule.t[arr['tick'][g]], ctl[g], bullet_cap=K,
+                            raw=bool(arr['tick'][g] == 0)) for g in range(0, N, 4)]
+        n_raw += int((arr['tick'][::4] == 0).sum())
+        _, done, ev = games.step(None, auto_reset=True)
+        done, new = done.cpu().numpy(), games.get_arrays()
+        for w, g in zip(want, range(0, N, 4)):
+            assert bool(done[g]) == w['done'], (k, g)
+            if not w['done']:
+                assert H.same_bits(new['ships'][g], w['ships']) and H.same_bits(new['planets'][g, :w['planets'].shape[0]], w['planets']), (k, g)
+                assert new['n_bullets'][g] == w['bullets'].shape[0] and H.same_bits(new['bullets'][g, :w['bullets'].shape[0]], w['bullets'])
+    assert n_raw > 200
+
+
+def test_control_codes_above_5_are_flagged_and_flown_as_no_op():
+    """Control codes outside the reference's table (core.py:220-227): the tick flags the game (ASTRO_EV_BAD_CONTROL,
+    counted in stats) and flies the ship with control 2 — in every kernel form; core.step rejects them."""
+    import torch
+    cfg, N, K = core.DEFAULT_CONFIG, 1024, 32
+    pool = H.make_pool(cfg, 128)
+    gen = torch.Generator(device='cpu').manual_seed(5)
+    T = 12
+    acts = torch.randint(0, 6, (T, N, 2), dtype=torch.uint8, generator=gen)
+    bad = acts.clone()
+    where = torch.rand((T, N, 2), generator=gen) < 0.05
+    bad[where] = torch.randint(6, 256, (int(where.sum()),), dtype=torch.int64, generator=gen).to(torch.uint8)
+    clean = acts.clone()
+    clean[where] = 2
+    for prec, flags, fused in ((32, 0, False), (32, 0, True), (32, nat.TICK_GENERIC_KERNEL, False), (64, 0, False)):
+        outs = []
+        for a in (bad, clean):
+            g = _games(cfg, N, bullet_cap=K, precision=prec, seed=1)
+            g.tick_flags = flags
+            g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+            g.reset_all()
+            ev = torch.zeros((T, g.n_pad), dtype=torch.uint8, device='cuda')
+            if fused:
+                g.step_many(T, a.cuda(), events=ev, auto_reset=True)
+            else:
+                for k in range(T):
+                    ev[k] = g.step(a[k].cuda(), auto_reset=True)[2]
+            outs.append((g.get_arrays(), ev.cpu().numpy(), g.stats()))
+        (a0, e0, s0), (a1, e1, s1) = outs
+        flagged = where.any(-1).numpy()
+        assert ((e0 & nat.EV_BAD_CONTROL) != 0)[flagged].all() and not ((e0 & nat.EV_BAD_CONTROL) != 0)[~flagged].any()
+        assert (e0 & ~nat.EV_BAD_CONTROL == e1).all() and s0['bad_controls'] == int(flagged.sum()) and s1['bad_controls'] == 0
+        assert H.same_bits(a0['ships'], a1['ships']) and (a0['n_bullets'] == a1['n_bullets']).all()
+    with pytest.raises(ValueError):
+        core.step(core.create(cfg), np.array([6, 0]), cfg)
+    g = _games(cfg, 64, bullet_cap=K, precision=32)
+    with pytest.raises(ValueError):
+        g.step(np.full((64, 2), 7))
+
+
+def test_bearings_beyond_the_sincos_range_are_rejected():
+    """util.direction is reproduced for |b| <= 71476 (numpy switches to another reduction beyond): a config whose
+    bearings could get there is refused when the schedule is set, and so are states that already are."""
+    cfg = core.DEFAULT_CONFIG._replace(ship_rspeed=4000.0, max_time=40.0)      # 2000 ticks x 80 rad
+    with pytest.raises(nat.AstroError, match='util.direction'):
+        _games(cfg, 32, bullet_cap=32, precision=32)
+    g = _games(core.DEFAULT_CONFIG, 32, bullet_cap=32, precision=32)
+    pool = H.make_pool(core.DEFAULT_CONFIG, 32)
+    ships = pool['ships'].copy()
+    ships[3, 1, 4] = 1.0e5
+    with pytest.raises(ValueError, match='util.direction'):
+        g.set_arrays(ships, pool['planets'], pool['np'])
+    s = core.create(core.DEFAULT_CONFIG)
+    s = s._replace(ships=s.ships._replace(b=np.array([0.0, -8.0e4])))
+    with pytest.raises(nat.AstroError, match='util.direction'):
+        core.step(s, np.array([2, 2]), core.DEFAULT_CONFIG)
+
+
+def test_explore_process_matches_the_reference_statistics():
+    """rl.EpsilonGreedy run by the reference itself (tests/golden/explore.json: 400k calls per setting) against the
+    device process on another random stream: enter / leave rates, active fraction, control histogram (never 5)."""
+    import torch
+    gold = json.load(open(os.path.join(H.G, 'explore.json')))
+    cfg, N, T = core.DEFAULT_CONFIG._replace(max_time=1e4), 4096, 120
+    pool = H.make_pool(cfg, 64)
+    for e in gold:
+        g = _games(cfg, N, bullet_cap=32, precision=32, seed=2)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        state = torch.zeros((g.n_pad, 2), dtype=torch.int32, device='cuda')
+        idle = active = entered = left = 0
+        hist = np.zeros(6, dtype=np.int64)
+        prev = np.zeros((N, 2), dtype=np.int64)
+        tick_prev = None
+        for k in range(T):
+            acts = torch.full((g.n_pad, 2), 2, dtype=torch.uint8, device='cuda')
+            tick = (g.meta.cpu().numpy().view(np.uint32)[:N] >> 14).astype(np.int64)
+            g.explore_controls(acts, state, t_in=e['t_in'], t_out=e['t_out'], seed=11)
+            now = (state.cpu().numpy()[:N] & 0xff).astype(np.int64)
+            same = (tick > 0)[:, None] if k else np.zeros((N, 1), dtype=bool)    # (a re-created game's first call never switches)
+            idle += int(((prev == 0) & same).sum()); entered += int(((prev == 0) & (now > 0) & same).sum())
+            active += int(((prev > 0) & same).sum()); left += int(((prev > 0) & (now == 0) & same).sum())
+            hist += np.bincount((now[now > 0] - 1).ravel(), minlength=6)
+            prev = now
+            g.step(torch.full((g.n_pad, 2), 2, dtype=torch.uint8, device='cuda'), auto_reset=True)
+        ref_in, ref_out = e['entered'] / e['idle_calls'], e['left'] / e['active_calls']
+        assert abs(entered / idle - ref_in) < 0.08 * ref_in and abs(left / active - ref_out) < 0.05 * ref_out, (entered / idle, ref_in, left / active, ref_out)
+        assert hist[5] == 0 and e['hist'][5] == 0
+        ref_h = np.array(e['hist'][:5]) / sum(e['hist'])
+        assert np.abs(hist[:5] / hist.sum() - ref_h).max() < 0.02

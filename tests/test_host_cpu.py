@@ -225,3 +225,42 @@ def test_tick_kernel_requests_its_rows_before_it_uses_meta():
         n_ships = 2 if 'Li2E' in name else 1
         assert sum('LDG.E.128' in l for l in head) == n_ships, (name, head)            # ship rows
         assert sum(bool(re.search(r'LDG\.E\s', l)) for l in head) >= 1 + n_ships, (name, head)   # meta + bearings
+
+
+def _golden_net(solo):
+    import torch
+    from astro_b200 import rl
+    z = np.load(os.path.join(H.G, 'network.npz'))
+    net = rl.ValueNetwork(solo=solo, nout=6)
+    pre = 'solo_' if solo else 'duel_'
+    sd = {k: torch.from_numpy(z[pre + k.replace('.', '_')]) for k in net.state_dict()}
+    net.load_state_dict(sd)
+    return net, z
+
+
+def test_value_network_matches_reference_outputs():
+    """astro_b200.rl.ValueNetwork.forward / forward_both with the reference's seeded weights (tests/golden/network.npz,
+    produced by the unmodified rl.ValueNetwork.evaluate_batch / evaluate, rl.py:115-165) on the reference's own feature
+    batches: outputs within 2e-6 (|q| <= 1), both perspectives, -1 padding neutral."""
+    import torch
+    f = np.load(os.path.join(H.G, 'features.npz'))
+    fm = json.load(open(os.path.join(H.G, 'features.json')))
+    n_duel = n_solo = 0
+    for e in fm:
+        g, solo = e['game'], e['nships'] == 1
+        net, z = _golden_net(solo)
+        batch = torch.from_numpy(f['g%d_batch' % g])
+        with torch.no_grad():
+            got = net(batch).numpy()
+            assert np.abs(got - z['g%d_q0' % g]).max() <= 2e-6, g
+            assert np.abs(got - z['g%d_q0_single' % g]).max() <= 2e-6, g
+            if not solo:
+                both = net.forward_both(batch).numpy()
+                assert np.abs(both[:, 0] - z['g%d_q0' % g]).max() <= 2e-6 and np.abs(both[:, 1] - z['g%d_q1' % g]).max() <= 2e-6, g
+                padded = torch.cat([batch, torch.full((batch.shape[0], 5, 15), -1.0)], dim=1)
+                assert np.abs(net(padded).numpy() - z['g%d_q0' % g]).max() <= 2e-6
+                n_duel += 1
+            else:
+                n_solo += 1
+    assert n_duel >= 10 and n_solo >= 1
+    assert np.abs(np.load(os.path.join(H.G, 'network.npz'))['g0_q0']).max() > 0.05      # (the outputs are not all ~0)

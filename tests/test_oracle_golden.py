@@ -105,6 +105,52 @@ def test_trajectories_teacher_forced_and_free_running():
     assert total > 6000
 
 
+def test_raw_create_trajectories_first_tick_float32():
+    """Games the reference played from core.create's RAW arrays (float32 ships and planet positions, not
+    canonicalised): on the first tick numpy runs _gravity, the squared distances of _collisions and the planets'
+    a * dt in float32 (core.py:138-153, :200-212, :189), and bullets born on that tick are float32 throughout.  The
+    oracle's raw mode reproduces the first tick bit for bit, the plain mode every later tick — teacher-forced and
+    free-running; and the plain mode must NOT match the raw first tick of a multi-planet game (the pin is real)."""
+    z = np.load(os.path.join(G, 'traj_raw.npz'))
+    meta = json.load(open(os.path.join(G, 'traj_raw.json')))
+    total, plain_differs = 0, 0
+    for m in meta:
+        g = m['game']
+        ships, planets = z['g%d_ships' % g], z['g%d_planets' % g]
+        nb, bullets = z['g%d_nb' % g], z['g%d_bullets' % g]
+        reload_, t_, ctrl, rew = z['g%d_reload' % g], z['g%d_t' % g], z['g%d_control' % g], z['g%d_reward' % g]
+        off = np.concatenate([[0], np.cumsum(nb)])
+        cfg = ao.Config.from_any(m['config'])
+        n = m['nticks']
+        assert nb[0] == 0 and (ships[0].astype(np.float32) == ships[0]).all() and (planets[0][:, :2].astype(np.float32) == planets[0][:, :2]).all()
+        free = None
+        for k in range(n):
+            cur = (ships[k], planets[k], bullets[off[k]:off[k + 1]], reload_[k], t_[k])
+            if free is not None:
+                assert all(_same(a, b) for a, b in zip(free, cur)), (g, k, 'free-running drifted')
+            out = ao.step_one(cfg, *cur, ctrl[k], raw=(k == 0))
+            assert _same(out['reward'], rew[k]), (g, k)
+            last = k == n - 1
+            if last and not m['truncated']:
+                assert out['done'], (g, k)
+                continue
+            assert not out['done'], (g, k)
+            if last:
+                nxt = (z['g%d_final_ships' % g], z['g%d_final_planets' % g], z['g%d_final_bullets' % g],
+                       z['g%d_final_reload_t' % g][0], z['g%d_final_reload_t' % g][1])
+            else:
+                nxt = (ships[k + 1], planets[k + 1], bullets[off[k + 1]:off[k + 2]], reload_[k + 1], t_[k + 1])
+            got = (out['ships'], out['planets'], out['bullets'], out['reload'], out['t'])
+            for name, a, b in zip(('ships', 'planets', 'bullets', 'reload', 't'), got, nxt):
+                assert _same(a, b), (g, k, name)
+            if k == 0:
+                plain = ao.step_one(cfg, *cur, ctrl[k])
+                plain_differs += not (_same(plain['ships'], nxt[0]) and _same(plain['planets'], nxt[1]) and _same(plain['bullets'], nxt[2]))
+            free = got
+            total += 1
+    assert total > 1000 and plain_differs >= 8
+
+
 def test_edge_cases():
     """70 hand-built single-step cases through the reference: predicate knife edges, the
     bullet-cull .any quirk, terminal precedence, firing order, wrap, all 36 control pairs."""
