@@ -361,14 +361,44 @@ class BatchedGames:
         n = self.n
         return (self._reward[:n] if want_reward else None), self._done[:n], self._events[:n]
 
-    def step_many(self, n_ticks, actions=None, events=None, reward=None, done=None, auto_reset=False, stats=True):
+    # ---- compact host traffic: one control byte per game, three event bit planes per tick ------------
+    @staticmethod
+    def pack_controls(actions):
+        """[..., 2] control codes 0..5 -> [...] uint8, ship 0 in bits 0-2 and ship 1 in bits 3-5 (TICK_PACKED_CONTROLS)."""
+        a = actions
+        if hasattr(a, 'numpy') or hasattr(a, 'device'):
+            return (a[..., 0] | (a[..., 1] << 3)).to(a.dtype)
+        a = np.asarray(a)
+        return (a[..., 0] | (a[..., 1] << 3)).astype(np.uint8)
+
+    def planes_shape(self, n_ticks=None):
+        """Shape of an int32 event-plane buffer (TICK_EVENT_PLANES): [3, n_tiles] per tick."""
+        return (3, self.n_tiles) if n_ticks is None else (int(n_ticks), 3, self.n_tiles)
+
+    def unpack_event_planes(self, planes):
+        """int32 / uint32 [..., 3, n_tiles] bit planes (ended / ship 0 hit / ship 1 hit) -> uint8 events [..., n] with
+        the ASTRO_EV_HIT0 / HIT1 / TIMEOUT bits of the byte-per-game form (host side, numpy)."""
+        p = np.ascontiguousarray(planes.cpu().numpy() if hasattr(planes, 'cpu') else planes).view(np.uint32)
+        bits = np.unpackbits(p.view(np.uint8).reshape(p.shape + (4,)), axis=-1, bitorder='little').reshape(p.shape[:-1] + (-1,))
+        done, h0, h1 = bits[..., 0, :], bits[..., 1, :], bits[..., 2, :]
+        ev = h0 | (h1 << 1) | ((done & (1 - (h0 | h1))) << 2)
+        return ev[..., :self.n].astype(np.uint8)
+
+    def _io_flags(self, auto_reset, stats, packed, planes):
+        if packed and self.S != 2:
+            raise ValueError('packed controls are for duel games')
+        return ((nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
+                | (nat.TICK_PACKED_CONTROLS if packed else 0) | (nat.TICK_EVENT_PLANES if planes else 0))
+
+    def step_many(self, n_ticks, actions=None, events=None, reward=None, done=None, auto_reset=False, stats=True,
+                  packed=False, planes=False):
         """`n_ticks` consecutive `step()`s in as few launches as possible (astro_tick_many): the ticks of a tile run
         back to back inside a launch, state going from one tick to the next through L2.  For loops whose controls
         do not depend on the states inside the block (replays, random exploration, the counter stream).
 
-        actions -- None (device counter stream) or uint8 cuda tensor [n_ticks, n_pad, S]
-        events / reward / done -- optional cuda tensors [n_ticks, n_pad] (uint8) / [n_ticks, n_pad, S] (float32) /
-                   [n_ticks, n_pad] (uint8) receiving every tick's outputs"""
+        actions -- None (device counter stream) or uint8 cuda tensor [n_ticks, n_pad, S] ([n_ticks, n_pad] with packed=True)
+        events / reward / done -- optional cuda tensors [n_ticks, n_pad] (uint8; int32 [n_ticks, 3, n_tiles] with planes=True)
+                   / [n_ticks, n_pad, S] (float32) / [n_ticks, n_pad] (uint8) receiving every tick's outputs"""
         torch = _torch()
         T = int(n_ticks)
 
@@ -378,11 +408,13 @@ class BatchedGames:
             if tuple(x.shape) != shape or x.dtype != dtype or not x.is_contiguous() or x.device != self.device:
                 raise ValueError('%s must be a contiguous %s cuda tensor %r' % (name, dtype, shape))
             return x.data_ptr()
-        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
+        flags = self._io_flags(auto_reset, stats, packed, planes)
+        a_shape = (T, self.n_pad) if packed else (T, self.n_pad, self.S)
+        e_shape, e_dtype = ((T, 3, self.n_tiles), torch.int32) if planes else ((T, self.n_pad), torch.uint8)
         nat.check(nat.lib().astro_tick_many(
-            self._h, ptr(actions, (T, self.n_pad, self.S), torch.uint8, 'actions'),
+            self._h, ptr(actions, a_shape, torch.uint8, 'actions'),
             ptr(reward, (T, self.n_pad, self.S), torch.float32, 'reward'), ptr(done, (T, self.n_pad), torch.uint8, 'done'),
-            ptr(events, (T, self.n_pad), torch.uint8, 'events'), T, flags, self._stream()))
+            ptr(events, e_shape, e_dtype, 'events'), T, flags, self._stream()))
         self.step_index += T
 
     def step_many_raw(self, actions_ptr, events_ptr, n_ticks, flags):
@@ -397,33 +429,38 @@ class BatchedGames:
                                        self._stream()))
         self.step_index += 1
 
-    def step_host(self, actions_host, events_host, reward_host=None, done_host=None, auto_reset=False, stats=True):
+    def step_host(self, actions_host, events_host, reward_host=None, done_host=None, auto_reset=False, stats=True,
+                  packed=False, planes=False):
         """End-to-end tick with HOST buffers (torch pinned tensors or numpy arrays): copies the
-        actions in, ticks, copies events (and reward/done if given) out, synchronises."""
+        actions in, ticks, copies events (and reward/done if given) out, synchronises.
+        packed=True: actions_host is uint8 [n_pad] (pack_controls); planes=True: events_host is int32 [3, n_tiles]
+        (unpack_event_planes) — 1.4 bytes per game and tick through host memory instead of 3."""
         def ptr(x):
             if x is None:
                 return None
             return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
-        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
-        for x, nbytes in ((actions_host, self.n_pad * self.S), (events_host, self.n_pad)):
+        flags = self._io_flags(auto_reset, stats, packed, planes)
+        for x, nbytes in ((actions_host, self.n_pad * (1 if packed else self.S)), (events_host, self.n_tiles * 12 if planes else self.n_pad)):
             if x is not None and (x.numel() * x.element_size() if hasattr(x, 'numel') else x.nbytes) < nbytes:
                 raise ValueError('host buffer too small: need %d bytes' % nbytes)
         nat.check(nat.lib().astro_tick_host(self._h, ptr(actions_host), ptr(reward_host), ptr(done_host),
                                             ptr(events_host), flags, self._stream()))
         self.step_index += 1
 
-    def rollout_host(self, actions_host, events_host, auto_reset=False, stats=True):
-        """Pipelined end-to-end rollout with HOST buffers: actions_host uint8 [T, n_pad, S], events_host
-        uint8 [T, n_pad] (pinned torch tensors or numpy arrays).  Every tick's controls are copied
-        in and its events copied out; copies of neighbouring ticks overlap the tick kernel."""
+    def rollout_host(self, actions_host, events_host, auto_reset=False, stats=True, packed=False, planes=False):
+        """Pipelined end-to-end rollout with HOST buffers: actions_host uint8 [T, n_pad, S] ([T, n_pad] with
+        packed=True), events_host uint8 [T, n_pad] (int32 [T, 3, n_tiles] with planes=True) — pinned torch tensors
+        or numpy arrays.  Every tick's controls are copied in and its events copied out; copies of neighbouring
+        ticks overlap the tick kernel."""
         def ptr(x):
             return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
+        def nbytes(x):
+            return x.numel() * x.element_size() if hasattr(x, 'numel') else x.nbytes
         T = int(actions_host.shape[0])
-        na = actions_host.numel() if hasattr(actions_host, 'numel') else actions_host.size
-        ne = events_host.numel() if hasattr(events_host, 'numel') else events_host.size
-        if na != T * self.n_pad * self.S or ne < T * self.n_pad:
-            raise ValueError('need actions [T, %d, %d] and events [T, %d]' % (self.n_pad, self.S, self.n_pad))
-        flags = (nat.TICK_AUTO_RESET if auto_reset else 0) | (0 if stats else nat.TICK_NO_STATS) | self.tick_flags
+        need_a, need_e = T * self.n_pad * (1 if packed else self.S), T * (self.n_tiles * 12 if planes else self.n_pad)
+        if nbytes(actions_host) != need_a or nbytes(events_host) < need_e:
+            raise ValueError('need %d bytes of controls and %d bytes of events for %d ticks' % (need_a, need_e, T))
+        flags = self._io_flags(auto_reset, stats, packed, planes)
         nat.check(nat.lib().astro_rollout_host(self._h, ptr(actions_host), ptr(events_host), T, flags, self._stream()))
         self.step_index += T
 

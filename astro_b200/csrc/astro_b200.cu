@@ -56,6 +56,8 @@ struct TickParams {
     int32_t n_games, K, timeout_tick, n_sched_ticks, pool_size, flags;
     uint32_t seed, step, first_game;
     int32_t n_fused;     // ticks per launch (tick_f32_kernel; 1 everywhere else)
+    uint32_t act_stride, ev_stride;   // bytes from one tick's controls / events to the next tick's
+    int32_t tile0, tiles;             // tick_f32_kernel: the launch covers tiles tile0 .. tile0 + tiles - 1
     Consts c;
 };
 
@@ -253,7 +255,11 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
             int ctl[S];
             bool bad_ctl = false;
             if (p.actions) {
-                if (S == 2) {
+                if (S == 2 && (p.flags & ASTRO_TICK_PACKED_CONTROLS)) {   // one byte per game: ship 0 bits 0-2, ship 1 bits 3-7
+                    const uint8_t a = p.actions[g];
+                    ctl[0] = a & 7;
+                    ctl[S - 1] = a >> 3;
+                } else if (S == 2) {
                     uint16_t a = reinterpret_cast<const uint16_t*>(p.actions)[g];
                     ctl[0] = a & 0xff;
                     ctl[S - 1] = a >> 8;
@@ -486,7 +492,16 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
             if (S == 2) reinterpret_cast<float2*>(p.reward)[g] = make_float2(rw[0], rw[S - 1]);
             else p.reward[g] = rw[0];
         }
-        if (p.events) p.events[g] = (uint8_t)ev;
+        if (p.events) {
+            if (p.flags & ASTRO_TICK_EVENT_PLANES) {   // three bit planes u32 [3][n_tiles]: ended / ship 0 hit / ship 1 hit
+                const unsigned b_done = __ballot_sync(0xffffffffu, (ev & ASTRO_EV_DONE_MASK) != 0);
+                const unsigned b_h0 = __ballot_sync(0xffffffffu, (ev & ASTRO_EV_HIT0) != 0), b_h1 = __ballot_sync(0xffffffffu, (ev & ASTRO_EV_HIT1) != 0);
+                if (lane < 3)
+                    reinterpret_cast<uint32_t*>(p.events)[(size_t)lane * (p.n_games >> 5) + (g >> 5)] = lane == 0 ? b_done : (lane == 1 ? b_h0 : b_h1);
+            } else {
+                p.events[g] = (uint8_t)ev;
+            }
+        }
         if (p.done) p.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
     }
 
@@ -1278,6 +1293,10 @@ struct AstroBatch {
     cudaStream_t copy_in, copy_out;
     cudaEvent_t ev_in[2], ev_tick[2], ev_out[2];
     bool pipe_ready;
+    // astro_tick_host: the tick cut into slices of tiles (copy streams and ordering events, created lazily)
+    cudaStream_t slice_in, slice_out;
+    cudaEvent_t ev_slice_in[8], ev_slice_tick[8], ev_slice_start;
+    bool slice_ready;
     int32_t pipe_chunk;      // ticks per copy of astro_rollout_host
     uint8_t* d_done;
     float* d_reward;
@@ -1373,7 +1392,7 @@ cudaError_t launch_tick(const TickParams& p, cudaStream_t st) {
 
 template <int S>
 cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
-    const int grid = (p.n_games + kTickThreads - 1) / kTickThreads;
+    const int grid = (p.tiles * 32 + kTickThreads - 1) / kTickThreads;
     // experiment knob (tools/exp_tick.py): unused dynamic shared memory caps the resident CTAs per SM
     static const size_t extra = getenv("ASTRO_EXTRA_SMEM") ? (size_t)atoi(getenv("ASTRO_EXTRA_SMEM")) : 0;
     if (p.n_fused > 1) {
@@ -1414,10 +1433,23 @@ cudaError_t fold_stats(AstroBatch* b, cudaStream_t st) {
 // [n_ticks][...] (or NULL).  The production fp32 kernel runs up to kMaxFused of them per launch, each tile
 // back to back (tick_f32_kernel); the generic / float64 kernels run one launch per tick.
 constexpr int kMaxFused = 256;
+constexpr int kMaxSlices = 8;
 constexpr double kSinCosRange = 71476.0;   // np_sincos_f32 (astro_device.cuh)
+// bytes of one tick's controls / events in the form `flags` selects (include/astro_b200.h)
+size_t actions_bytes(const AstroBatch* b, int32_t flags) {
+    return (flags & ASTRO_TICK_PACKED_CONTROLS) && b->S == 2 ? (size_t)b->n_games : (size_t)b->n_games * b->S;
+}
+size_t events_bytes(const AstroBatch* b, int32_t flags) {
+    return (flags & ASTRO_TICK_EVENT_PLANES) ? (size_t)(b->n_games / ASTRO_TILE) * 12 : (size_t)b->n_games;
+}
+
+// (tile0, tiles): the float32 kernel can run a launch over a sub-range of tiles (astro_tick_host slices a tick so that
+// the copies of one slice overlap the kernel of another); tiles = 0: the whole batch.  A sliced call advances the
+// stream step and flips the bullet buffers only with its LAST slice (`advance`).
 int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done, uint8_t* events, int32_t flags,
-             cudaStream_t st, int32_t n_ticks) {
+             cudaStream_t st, int32_t n_ticks, int32_t tile0 = 0, int32_t tiles = 0, bool advance = true) {
     if (b->n_sched_ticks <= 0) return fail(ASTRO_E_STATE, "astro_set_schedule has not been called");
+    if ((flags & ASTRO_TICK_PACKED_CONTROLS) && b->S != 2) return fail(ASTRO_E_INVALID, "ASTRO_TICK_PACKED_CONTROLS is for duel games");
     if ((flags & ASTRO_TICK_AUTO_RESET) && b->pool.size <= 0)
         return fail(ASTRO_E_STATE, "ASTRO_TICK_AUTO_RESET needs astro_set_reset_pool");
     const bool fused = b->precision == 32 && !(flags & ASTRO_TICK_GENERIC_KERNEL);
@@ -1426,12 +1458,16 @@ int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done
         const int32_t kc = fused ? (n_ticks - k0 < kMaxFused ? n_ticks - k0 : kMaxFused) : 1;
         TickParams p;
         fill_params(b, p);
-        p.actions = actions ? actions + (size_t)k0 * n * b->S : nullptr;
+        p.act_stride = (uint32_t)actions_bytes(b, flags);
+        p.ev_stride = (uint32_t)events_bytes(b, flags);
+        p.actions = actions ? actions + (size_t)k0 * p.act_stride : nullptr;
         p.reward = reward ? reward + (size_t)k0 * n * b->S : nullptr;
         p.done = done ? done + (size_t)k0 * n : nullptr;
-        p.events = events ? events + (size_t)k0 * n : nullptr;
+        p.events = events ? events + (size_t)k0 * p.ev_stride : nullptr;
         p.flags = flags;
         p.n_fused = kc;
+        p.tile0 = tile0;
+        p.tiles = tiles > 0 ? tiles : b->n_games / ASTRO_TILE;
         cudaError_t e;
         if (fused)
             e = b->S == 2 ? launch_tick_f32<2>(p, st) : launch_tick_f32<1>(p, st);
@@ -1440,10 +1476,11 @@ int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done
         else
             e = b->S == 2 ? launch_tick<double, 2>(p, st) : launch_tick<double, 1>(p, st);
         if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "tick_kernel launch: %s", cudaGetErrorString(e));
-        b->step += (uint32_t)kc;
-        b->cur ^= kc & 1;   // the lists now live in the buffer the last tick wrote
         b->launches += 1;
         k0 += kc;
+        if (!advance) continue;
+        b->step += (uint32_t)kc;
+        b->cur ^= kc & 1;   // the lists now live in the buffer the last tick wrote
         // 32-bit slot rows: fold long before a row can wrap (<= 32 * 1023 per tick)
         if (!(flags & ASTRO_TICK_NO_STATS) && (b->ticks_since_fold += kc) >= 65536) {
             cudaError_t fe = fold_stats(b, st);
@@ -1521,6 +1558,15 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaFree(b->d_pol);
     cudaFree(b->d_src);
     cudaFree(b->d_single);
+    if (b->slice_ready) {
+        for (int i = 0; i < 8; i++) {
+            cudaEventDestroy(b->ev_slice_in[i]);
+            cudaEventDestroy(b->ev_slice_tick[i]);
+        }
+        cudaEventDestroy(b->ev_slice_start);
+        cudaStreamDestroy(b->slice_in);
+        cudaStreamDestroy(b->slice_out);
+    }
     if (b->pipe_ready) {
         for (int i = 0; i < 2; i++) {
             cudaFree(b->d_actions2[i]);
@@ -1624,11 +1670,55 @@ int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_ho
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)b->n_games;
-    if (actions_host) CUDA_TRY(cudaMemcpyAsync(b->d_actions, actions_host, n * b->S, cudaMemcpyHostToDevice, st));
+    // A closed loop (controls of tick k + 1 depend on the events of tick k) cannot overlap the copies of one tick with the
+    // kernel of another — but games are independent, so the tick is cut into slices of tiles: slice i's controls travel
+    // while slice i - 1 runs and slice i - 2's events travel back (float32 kernel; ASTRO_HOST_SLICES overrides, 1 = off).
+    const char* slices_str = getenv("ASTRO_HOST_SLICES");   // (read on every call: tests switch it)
+    const int slices_env = slices_str ? atoi(slices_str) : 0;
+    const int n_tiles = b->n_games / ASTRO_TILE;
+    int slices = slices_env > 0 ? slices_env : (n_tiles >= 16384 ? 4 : 1);
+    if (slices > kMaxSlices) slices = kMaxSlices;
+    if (slices > 1 && actions_host && events_host && !reward_host && !done_host && b->precision == 32 &&
+        !(flags & ASTRO_TICK_GENERIC_KERNEL) && n_tiles >= slices) {
+        if (!b->slice_ready) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&b->slice_in, cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&b->slice_out, cudaStreamNonBlocking));
+            for (int i = 0; i < kMaxSlices; i++) {
+                CUDA_TRY(cudaEventCreateWithFlags(&b->ev_slice_in[i], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&b->ev_slice_tick[i], cudaEventDisableTiming));
+            }
+            CUDA_TRY(cudaEventCreateWithFlags(&b->ev_slice_start, cudaEventDisableTiming));
+            b->slice_ready = true;
+        }
+        const bool packed = (flags & ASTRO_TICK_PACKED_CONTROLS) != 0, planes = (flags & ASTRO_TICK_EVENT_PLANES) != 0;
+        const size_t a_per_tile = (size_t)ASTRO_TILE * (packed ? 1 : b->S);
+        CUDA_TRY(cudaEventRecord(b->ev_slice_start, st));               // earlier work of the caller's stream comes first
+        CUDA_TRY(cudaStreamWaitEvent(b->slice_in, b->ev_slice_start, 0));
+        for (int i = 0; i < slices; i++) {
+            const int t0 = (int)((int64_t)n_tiles * i / slices), t1 = (int)((int64_t)n_tiles * (i + 1) / slices);
+            CUDA_TRY(cudaMemcpyAsync(b->d_actions + t0 * a_per_tile, actions_host + t0 * a_per_tile, (size_t)(t1 - t0) * a_per_tile,
+                                     cudaMemcpyHostToDevice, b->slice_in));
+            CUDA_TRY(cudaEventRecord(b->ev_slice_in[i], b->slice_in));
+            CUDA_TRY(cudaStreamWaitEvent(st, b->ev_slice_in[i], 0));
+            if (int r = do_ticks(b, b->d_actions, nullptr, nullptr, b->d_events, flags, st, 1, t0, t1 - t0, i == slices - 1)) return r;
+            CUDA_TRY(cudaEventRecord(b->ev_slice_tick[i], st));
+            CUDA_TRY(cudaStreamWaitEvent(b->slice_out, b->ev_slice_tick[i], 0));
+            if (planes)
+                CUDA_TRY(cudaMemcpy2DAsync(events_host + (size_t)t0 * 4, (size_t)n_tiles * 4, b->d_events + (size_t)t0 * 4, (size_t)n_tiles * 4,
+                                           (size_t)(t1 - t0) * 4, 3, cudaMemcpyDeviceToHost, b->slice_out));
+            else
+                CUDA_TRY(cudaMemcpyAsync(events_host + (size_t)t0 * ASTRO_TILE, b->d_events + (size_t)t0 * ASTRO_TILE, (size_t)(t1 - t0) * ASTRO_TILE,
+                                         cudaMemcpyDeviceToHost, b->slice_out));
+        }
+        CUDA_TRY(cudaStreamSynchronize(b->slice_out));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return ASTRO_OK;
+    }
+    if (actions_host) CUDA_TRY(cudaMemcpyAsync(b->d_actions, actions_host, actions_bytes(b, flags), cudaMemcpyHostToDevice, st));
     if (int r = do_tick(b, actions_host ? b->d_actions : nullptr, reward_host ? b->d_reward : nullptr,
                         done_host ? b->d_done : nullptr, events_host ? b->d_events : nullptr, flags, st))
         return r;
-    if (events_host) CUDA_TRY(cudaMemcpyAsync(events_host, b->d_events, n, cudaMemcpyDeviceToHost, st));
+    if (events_host) CUDA_TRY(cudaMemcpyAsync(events_host, b->d_events, events_bytes(b, flags), cudaMemcpyDeviceToHost, st));
     if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, b->d_done, n, cudaMemcpyDeviceToHost, st));
     if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, b->d_reward, n * b->S * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1641,7 +1731,8 @@ int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* even
     if (!actions_host || !events_host || n_ticks < 0) return fail(ASTRO_E_INVALID, "bad rollout arguments");
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)b->n_games, na = n * b->S;
+    if ((flags & ASTRO_TICK_PACKED_CONTROLS) && b->S != 2) return fail(ASTRO_E_INVALID, "ASTRO_TICK_PACKED_CONTROLS is for duel games");
+    const size_t n = events_bytes(b, flags), na = actions_bytes(b, flags);   // bytes per tick: events out, controls in
     // Ticks travel in chunks of C: the controls of C ticks are copied in (one copy per tick: 2 MB copies run at
     // 51 GB/s on the pool's boxes, 16 MB ones at 14 — tools/ubench/pcie.py), the C ticks run as ONE launch
     // (do_ticks: a tile's ticks back to back), their events are copied out.  1M games, 32 ticks per call, e2e
@@ -1653,8 +1744,8 @@ int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* even
         for (int i = 0; i < 2; i++) {
             CUDA_TRY(cudaFree(b->d_actions2[i]));
             CUDA_TRY(cudaFree(b->d_events2[i]));
-            CUDA_TRY(cudaMalloc(&b->d_actions2[i], na * C));
-            CUDA_TRY(cudaMalloc(&b->d_events2[i], n * C));
+            CUDA_TRY(cudaMalloc(&b->d_actions2[i], (size_t)b->n_games * b->S * C));
+            CUDA_TRY(cudaMalloc(&b->d_events2[i], (size_t)b->n_games * C));
         }
         b->pipe_chunk = C;
     }
@@ -1662,8 +1753,8 @@ int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* even
         CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_out, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
-            CUDA_TRY(cudaMalloc(&b->d_actions2[i], na * C));
-            CUDA_TRY(cudaMalloc(&b->d_events2[i], n * C));
+            CUDA_TRY(cudaMalloc(&b->d_actions2[i], (size_t)b->n_games * b->S * C));
+            CUDA_TRY(cudaMalloc(&b->d_events2[i], (size_t)b->n_games * C));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_tick[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_out[i], cudaEventDisableTiming));

@@ -278,13 +278,23 @@ __device__ __forceinline__ TickVar tick_var(const TickParams& p, unsigned k) {
     TickVar v;
     const size_t n = (size_t)p.n_games;
     v.step = p.step + k;
-    v.actions = p.actions ? p.actions + k * n * S : nullptr;
+    v.actions = p.actions ? p.actions + k * (size_t)p.act_stride : nullptr;   // [n][S] bytes, or [n] packed
     v.reward = p.reward ? p.reward + k * n * S : nullptr;
     v.done = p.done ? p.done + k * n : nullptr;
-    v.events = p.events ? p.events + k * n : nullptr;
+    v.events = p.events ? p.events + k * (size_t)p.ev_stride : nullptr;       // [n] bytes, or three bit planes
     v.bullets_in = reinterpret_cast<float4*>((k & 1u) ? p.bullets_out : p.bullets_in);
     v.bullets_out = reinterpret_cast<float4*>((k & 1u) ? p.bullets_in : p.bullets_out);
     return v;
+}
+// The control bytes of game g: two bytes (one per ship), or — ASTRO_TICK_PACKED_CONTROLS — one byte holding both
+// codes (ship 0 in bits 0-2, ship 1 in bits 3-5), expanded to the two-byte form (bits 6-7 land in ship 1's byte and
+// flag the control as bad, like any code above 5).
+template <int S>
+__device__ __forceinline__ uint32_t load_controls(const uint8_t* a, size_t g, bool packed) {
+    if (S == 2 && !packed) return (uint32_t)reinterpret_cast<const uint16_t*>(a)[g];
+    const uint32_t b = (uint32_t)a[g];
+    if (S == 2) return (b & 7u) | ((b & 0xf8u) << 5);
+    return b;
 }
 struct TileIn {
     uint32_t meta;
@@ -314,7 +324,7 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar&
     }
     if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }  // S == 1: the second half of every ship pair mirrors ship 0
     in.ctl_raw = 0;
-    if (v.actions) in.ctl_raw = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(v.actions)[g] : (uint32_t)v.actions[g];
+    if (v.actions) in.ctl_raw = load_controls<S>(v.actions, g, (p.flags & ASTRO_TICK_PACKED_CONTROLS) != 0);
     // Everything above is ONE round trip to HBM only if it is requested before the first use of meta.
     // ptxas is free to hoist meta-dependent code (it drags a later load and its address arithmetic up)
     // above these requests, which then leave a whole round trip late — seen at random from build to
@@ -447,9 +457,9 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     next.shv[0] = shv[0]; next.shv[1] = shv[1];   // (finished games: rows untouched)
     next.sb[0] = sb[0]; next.sb[1] = sb[1];
 #ifdef ASTRO_EXPERIMENTS
-    // experiment builds only (flag 64): the tick's memory traffic without its arithmetic — every load
+    // experiment builds only (flag 1024): the tick's memory traffic without its arithmetic — every load
     // and store of a tick whose games neither move nor end (tools/ab_repeat.sh)
-    const bool freeze = (p.flags & 64) != 0;
+    const bool freeze = (p.flags & 1024) != 0;
     if (freeze && active) {
 #pragma unroll
         for (int s = 0; s < S; s++) {
@@ -751,7 +761,18 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         if (S == 2) reinterpret_cast<float2*>(v.reward)[g] = make_float2(rw[0], rw[1]);
         else v.reward[g] = rw[0];
     }
-    if (v.events) ST_STREAM(&v.events[g], (uint8_t)ev);
+    if (v.events) {
+        if (p.flags & ASTRO_TICK_EVENT_PLANES) {
+            // three bit planes per tick, u32 [3][n_tiles]: bit g % 32 of word g / 32 = game g ended / ship 0 was hit /
+            // ship 1 was hit (a timeout: ended and nobody hit) — 12 bytes per tile instead of 32
+            const unsigned b_done = __ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0);
+            const unsigned b_h0 = __ballot_sync(full, (ev & ASTRO_EV_HIT0) != 0), b_h1 = __ballot_sync(full, (ev & ASTRO_EV_HIT1) != 0);
+            if (lane < 3u)
+                reinterpret_cast<uint32_t*>(v.events)[(size_t)lane * ((unsigned)p.n_games >> 5) + tile_index] = lane == 0u ? b_done : (lane == 1u ? b_h0 : b_h1);
+        } else {
+            ST_STREAM(&v.events[g], (uint8_t)ev);
+        }
+    }
     if (v.done) v.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
 
     if (STATS) {
@@ -773,19 +794,20 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
 template <int S, bool STATS, bool MANY>
 __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
     __shared__ TileScratch s_tiles[kTickWarps];
-    unsigned tile = (blockIdx.x * kTickThreads + threadIdx.x) >> 5;
+    unsigned tile = (blockIdx.x * kTickThreads + threadIdx.x) >> 5;   // among the p.tiles tiles of this launch, from p.tile0
 #if ASTRO_PDL
     if (!MANY) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's CTAs may take the slots this grid frees
         asm volatile("griddepcontrol.wait;" ::: "memory");                // ... and the previous kernel's stores are visible from here
     }
 #endif
-    if ((int)(tile * 32u) >= p.n_games) return;  // whole warps: n_games % 32 == 0
+    if (tile >= (unsigned)p.tiles) return;  // whole warps: n_games % 32 == 0
 #if ASTRO_BOUSTROPHEDON
     // Odd launches walk the tiles backwards: what the previous launch wrote last — still in the 126 MB L2 —
     // is read first, and rewritten there before it ever went to HBM.
-    if (p.step & 1u) tile = ((unsigned)p.n_games >> 5) - 1u - tile;
+    if (p.step & 1u) tile = (unsigned)p.tiles - 1u - tile;
 #endif
+    tile += (unsigned)p.tile0;
     const unsigned lane = threadIdx.x & 31u;
     // n_fused consecutive ticks of this tile, back to back (astro_tick_many): games do not interact, so a
     // tile can run ahead of the others; what tick k wrote is what tick k + 1 reads — from L2, not from HBM.
@@ -803,8 +825,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         uint32_t ctl_next = 0;
         if (MANY && p.actions && k + 1u < (unsigned)p.n_fused) {
             const size_t g = (size_t)tile * 32 + lane;
-            const uint8_t* a = p.actions + (size_t)(k + 1u) * (size_t)p.n_games * S;
-            ctl_next = S == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(a)[g] : (uint32_t)a[g];
+            ctl_next = load_controls<S>(p.actions + (size_t)(k + 1u) * (size_t)p.act_stride, g, (p.flags & ASTRO_TICK_PACKED_CONTROLS) != 0);
         }
         if (MANY) in.fire_word = p.fire_bits[min(ASTRO_META_TICK(in.meta), (uint32_t)p.n_sched_ticks - 1u) >> 5];
         tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);

@@ -13,17 +13,24 @@ by core.create; the population is pre-rolled to its stationary bullet count befo
 state (0.67 GB per GPU) and the controls exceed the 126 MB L2, so no flush is needed between steps.
 
 Numbers on the JSON line:
-  value     whole-job env-steps/s, controls already resident in HBM (a ring of pre-generated
-            [games, 2] u8 arrays, a different one every tick), every tick's events written to HBM;
-            CUDA events, max over ranks.  The ticks go through astro_tick_many, --fuse ticks per
-            launch: games do not interact, so the kernel runs the ticks of a tile back to back and
-            the state travels from one tick to the next through L2.  `per_tick_launch` is the same
-            loop as one launch per tick (what a policy in the loop needs).
-  e2e       the same through BatchedGames.step_host(): pinned HOST controls in, events out,
-            copies inside the timed region.
-  roofline  algorithmic bytes of the tick kernel per launch (from the device counters of the timed
-            region) / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the oracle port of the reference loop on all host cores (rank 0, N=1 only).
+  value     whole-job env-steps/s, controls already resident in HBM (a ring of pre-generated arrays, one control byte
+            per game, a different array every tick), every tick's events written to HBM (three bit planes); CUDA events,
+            max over ranks (`per_rank_ms` lists every rank).  The ticks go through astro_tick_many, --fuse ticks per
+            launch: games do not interact, so the kernel runs the ticks of a tile back to back and the state travels
+            from one tick to the next through L2.  The timed region ends with the episode statistics and their NCCL
+            all-reduce (`collective_us` = that part alone).
+  per_tick_launch  the same loop as one launch per tick (what a policy in the loop needs) with ITS roofline: this is the
+            HBM-bound form (DRAM traffic ~ algorithmic bytes).
+  roofline  the dominant kernel of the timed region: algorithmic bytes per launch (device counters) / average launch
+            duration against MEASURED_PEAKS.json hbm_gbs; `traffic` = DRAM bytes of an ncu capture of the SAME launch
+            shape (or null); `secondary` = the issue-slot numbers of that capture (the fused form is issue-bound).
+  e2e       through BatchedGames.rollout_host(): pinned HOST controls in (1 B/game), event planes out (12 B / 32 games),
+            copies inside the timed region, pipelined; `closed_loop_value` = step_host: copy in, tick, copy out,
+            synchronise on every tick; `byte_form_value` = the round-1 forms (2 + 1 B/game).
+  strong    BASELINE configs[3] as stated: 1,048,576 games in TOTAL over the N GPUs (the headline weak-scales).
+  rollout   BASELINE configs[4]: 16,384 games x 1,000 ticks, observation -> astro.rl network -> step (rank 0).
+  drop_in   astro_b200.core.step on one game, microseconds per call (BASELINE configs[0] shape).
+  cpu_baseline  the oracle port of the reference loop on all host cores (rank 0, every N).
 """
 import argparse
 import json
@@ -63,11 +70,98 @@ def reduce_max(value, device, dist=None):
     return float(t.item())
 
 
-def algorithmic_bytes(st, S, actions_in_hbm=True, with_reward=False):
+def algorithmic_bytes(st, S, packed=False, planes=False, events=True, with_reward=False):
     """Bytes the tick must move per the layout in include/astro_b200.h: every live byte of state
-    read once and written once, controls read, events written.  st = device counters."""
-    per_step = 2 * (4 + 16 * S + 4 * S) + (S if actions_in_hbm else 0) + 1 + ((4 * S + 1) if with_reward else 0)
+    read once and written once, controls read (S bytes per game, 1 when packed), events written (1 byte per game,
+    12 per 32 games as bit planes).  st = device counters."""
+    per_step = (2 * (4 + 16 * S + 4 * S) + (1 if packed else S) + ((12.0 / 32 if planes else 1) if events else 0)
+                + ((4 * S + 1) if with_reward else 0))
     return (st['env_steps'] * per_step + 32 * st['planets_live'] + 16 * (st['bullets_in'] + st['bullets_out']))
+
+
+# --------------------------------------------------------------------------- BASELINE config #5 and the drop-in
+def config5_rollout(args, local, pool):
+    """BASELINE configs[4]: self-play rollout, 16,384 games x 1,000 ticks, observation extraction feeding the astro.rl
+    policy batch every tick, both ships driven by the network (greedy), auto-reset.  Three forms of the same loop:
+    observe() -> PyTorch ValueNetwork -> argmax -> step; observe(shared) -> forward_both; the fused policy kernel
+    inside astro_rollout_device (no observation tensor, no host between ticks)."""
+    import torch
+    from astro_b200 import core, rl
+    from astro_b200.batched import BatchedGames
+    N, T = args.rollout_games, args.rollout_ticks
+    torch.manual_seed(7)
+    net = rl.ValueNetwork(solo=False, nout=6).cuda(local)
+    with torch.no_grad():
+        for prm in net.parameters():
+            prm.mul_(3.0)
+    out = dict(config='BASELINE configs[4]: %d games x %d ticks, observe -> astro.rl ValueNetwork (both ships) -> step, auto-reset' % (N, T),
+               games=N, ticks=T, unit=UNIT)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for form in ('observe+torch', 'observe_shared+forward_both', 'fused policy kernel (rollout_device)'):
+        g = BatchedGames(core.DEFAULT_CONFIG, N, bullet_cap=args.bullet_cap, precision=32, device=local, seed=3)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        g.set_policy(net)
+        buf = {}
+
+        def observe(shared):
+            if 'o' not in buf:
+                buf['o'] = g.observe(shared=shared)          # (N is a multiple of 32: the view is the whole buffer)
+            else:
+                g.observe(shared=shared, out=buf['o'])
+            return buf['o']
+
+        def loop(ticks):
+            with torch.no_grad():
+                if form.startswith('fused'):
+                    g.rollout_device(ticks, bots=('policy', 'policy'), auto_reset=True)
+                    return
+                for _ in range(ticks):
+                    if form.startswith('observe+'):
+                        a = net(observe(False)).argmax(-1).to(torch.uint8)
+                    else:
+                        a = net.forward_both(observe(True)).argmax(-1).to(torch.uint8)
+                    g.step(a, auto_reset=True, want_reward=False)
+        loop(3)
+        g.stats(clear=True)
+        torch.cuda.synchronize()
+        e0.record()
+        loop(T)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        st = g.stats()
+        out[form] = dict(value=st['env_steps'] / (ms * 1e-3), ms_per_tick=ms / T, episodes=st['episodes'])
+        del g
+    return out
+
+
+def drop_in_step(args):
+    """The drop-in astro_b200.core.step on ONE game (BASELINE configs[0] shape: the reference's own CPU-runnable case):
+    microseconds per call of the lean single-game path, beside the oracle port on one host core."""
+    from astro_b200 import core, rng
+    from oracle import astro_oracle as ao
+    cfg = core.DEFAULT_CONFIG
+    state = core.create(cfg)
+    n, t_gpu, k = 0, 0.0, 0
+    for warm in (True, False):
+        state = core.create(cfg)
+        t0 = time.perf_counter()
+        for k in range(400):
+            nxt, _ = core.step(state, rng.actions(5, [0], k, 2)[0], cfg)
+            state = core.create(cfg) if nxt is None else nxt
+        t_gpu = time.perf_counter() - t0
+    sh = np.zeros((2, 5)); pl = np.zeros((1, 4)); sh[:, 0] = (-0.5, 0.5); pl[0, 1] = 0.9
+    t0 = time.perf_counter()
+    for k in range(2000):
+        ao.step_one(cfg, sh, pl, np.zeros((0, 4)), 0.0, 0.0, np.array([2, 2]))
+    t_cpu = time.perf_counter() - t0
+    return dict(api='astro_b200.core.step (one game: pinned record in, import -> tick -> export, record out)',
+                us_per_step=1e6 * t_gpu / 400, steps_per_s=400 / t_gpu,
+                oracle_port_us_per_step=1e6 * t_cpu / 2000,
+                reference_python_us_per_step=202.0,
+                reference_note='astro.core.step measured in the build container (SURVEY section 6: 202 us/tick, 1 core); the Python '
+                               'reference cannot travel to the GPU box')
 
 
 # --------------------------------------------------------------------------- clocks
@@ -124,36 +218,68 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU baseline (oracle)
-def cpu_rollout_rate(n_games, warm_ticks, ticks, threads, seed=0, pool_size=1024):
-    """Times the oracle port of the reference step loop (same workload: duel, default planets,
-    counter-stream random controls, auto-reset from a create() pool)."""
-    from astro_b200 import core, rng
-    from oracle import astro_oracle as ao
-    from astro_b200.pool import make_pool
-    cfg = core.DEFAULT_CONFIG
-    pool = make_pool(cfg, pool_size)
-    b = ao.Batch(n_games, 2, 32)
-    pick = rng.pool_pick(seed, np.arange(n_games), np.zeros(n_games, dtype=np.uint32), pool_size)
-    b.ships[:], b.planets[:], b.np_[:] = pool['ships'][pick], pool['planets'][pick], pool['np'][pick]
-    ao.rollout(cfg, b, pool, seed, 0, 0, warm_ticks, threads=threads)
-    t0 = time.perf_counter()
-    st = ao.rollout(cfg, b, pool, seed, 0, warm_ticks, ticks, threads=threads)
-    dt = time.perf_counter() - t0
-    return float(st[5]) / dt, dt, int(st[5])
+CPU_GAMES = 65536      # the bounded CPU sample: the same workload on 65,536 games (both the cpu_baseline leg and --impl reference)
+
+
+class CpuLoop:
+    """The oracle port of the reference step loop on all host cores (same workload: duel, default planets,
+    counter-stream random controls, auto-reset from a create() pool), warmed up once and timed in segments."""
+
+    def __init__(self, n_games, threads, seed=0, pool_size=1024, warm_ticks=100):
+        from astro_b200 import core, rng
+        from oracle import astro_oracle as ao
+        from astro_b200.pool import make_pool
+        self.ao, self.cfg, self.seed, self.threads, self.n = ao, core.DEFAULT_CONFIG, seed, threads, n_games
+        self.pool = make_pool(self.cfg, pool_size)
+        b = self.b = ao.Batch(n_games, 2, 32)
+        pick = rng.pool_pick(seed, np.arange(n_games), np.zeros(n_games, dtype=np.uint32), pool_size)
+        b.ships[:], b.planets[:], b.np_[:] = self.pool['ships'][pick], self.pool['planets'][pick], self.pool['np'][pick]
+        self.step = 0
+        self.run(warm_ticks)
+
+    def run(self, ticks):
+        """-> (env-steps done, seconds)"""
+        t0 = time.perf_counter()
+        st = self.ao.rollout(self.cfg, self.b, self.pool, self.seed, 0, self.step, ticks, threads=self.threads)
+        dt = time.perf_counter() - t0
+        self.step += ticks
+        return int(st[5]), dt
+
+
+def cpu_baseline(seconds, threads=None):
+    threads = threads or os.cpu_count() or 1
+    loop = CpuLoop(CPU_GAMES, threads)
+    steps, dt = loop.run(40)                                      # calibrate
+    ticks = int(max(100, min(200000, seconds * (steps / dt) / CPU_GAMES)))
+    steps, dt = loop.run(ticks)
+    return dict(value=steps / dt, unit=UNIT, cores=threads, kind='port',
+                sample='%d games x %d ticks of the same workload (%.1f s), oracle C port of astro/core.py step with auto-reset, '
+                       'one thread per host core' % (CPU_GAMES, ticks, dt))
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU step loop (oracle port; the Python reference cannot
-    travel to the GPU box) on all host cores, same metric/config as our arm."""
+    """--impl reference: the reference's CPU step loop (oracle port; the Python reference cannot travel to the GPU box) on
+    all host cores, same metric / config as our arm.  One "step" = a bounded sample of the workload: `ticks_per_step`
+    ticks of CPU_GAMES games, sized after a short calibration so that the timed region lasts >= 2.5 s whatever --steps is
+    (a 25 ms region measured thread start-up, not the loop)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_games = args.ref_games
-    rate, dt, steps = cpu_rollout_rate(n_games, max(args.warmup, 3), args.steps, threads)
-    sample = '%d games x %d ticks (of the %d-games-per-GPU workload), oracle C port of astro/core.py step' % (
-        n_games, args.steps, args.games_per_gpu)
-    line = dict(metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=max(args.warmup, 3),
+    loop = CpuLoop(CPU_GAMES, threads)
+    steps, dt = loop.run(40)
+    rate0 = steps / dt
+    per_step = int(max(1, np.ceil(args.ref_seconds * rate0 / (CPU_GAMES * args.steps))))
+    for _ in range(args.warmup):
+        loop.run(per_step)
+    total, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        total += loop.run(per_step)[0]
+    dt = time.perf_counter() - t0
+    rate = total / dt
+    sample = ('each step = %d ticks of %d games of the %d-games-per-GPU workload (%.1f s timed), oracle C port of astro/core.py step '
+              'with auto-reset, one thread per host core' % (per_step, CPU_GAMES, args.games_per_gpu, dt))
+    line = dict(metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f64', data='synthetic', impl='reference', config=workload_config(args),
                 cpu_baseline=dict(value=rate, unit=UNIT, cores=threads, kind='port', sample=sample),
@@ -168,6 +294,7 @@ def workload_config(args):
                 games_per_gpu=args.games_per_gpu, bullet_cap=args.bullet_cap, reset_pool=args.pool,
                 preroll_ticks=args.preroll, state_precision='fp32 state, fp64-exact predicates',
                 ticks_per_launch=args.fuse,
+                io_form='one control byte per game (both ships), three event bit planes per tick',
                 l2_policy='state (0.67 GB/GPU) and controls exceed the 126 MB L2; no flush between steps; inside a launch the '
                           'ticks of a tile run back to back, so a tile\'s state deliberately stays in L2 from one tick to the next',
                 parallelism='env-parallel shards, one process per GPU, NCCL only for the stats reduce')
@@ -175,7 +302,7 @@ def workload_config(args):
 
 def bind_to_gpu_numa_node(index):
     """Pins this rank to the CPUs NVML lists as local to its GPU, BEFORE the pinned host buffers are allocated
-    (first touch puts them on that NUMA node): the end-to-end leg moves 3 MB per tick and GPU through host memory,
+    (first touch puts them on that NUMA node): the end-to-end leg moves 1.4 MB per tick and GPU through host memory,
     and with several ranks per box a buffer on the far socket costs every copy a trip over the socket link."""
     try:
         import pynvml
@@ -191,6 +318,16 @@ def bind_to_gpu_numa_node(index):
     except Exception:
         pass
     return None
+
+
+def profile_entry(ticks_per_launch):
+    """ncu summary of the tick kernel captured at this launch shape (profiles/tick_kernel_ncu_summary.json, keyed by
+    ticks per launch), or None: DRAM traffic is only printed beside a launch of the shape it was measured on."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'tick_kernel_ncu_summary.json')))
+        return prof.get(str(int(round(ticks_per_launch))))
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------- our arm
@@ -212,169 +349,233 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    plan = shard_plan(world, rank, args.games_per_gpu)
-    n, S, K = plan['n_games'], 2, args.bullet_cap
     cfg = core.DEFAULT_CONFIG
-
+    S, K = 2, args.bullet_cap
     pool = make_pool(cfg, args.pool)     # host: core.create over generate_configs (seed 42)
-    games = BatchedGames(cfg, n, bullet_cap=K, precision=32, device=local, seed=args.seed, first_game=plan['first_game'])
-    games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
-    games.reset_all()
-    flags = nat.TICK_AUTO_RESET | args.tick_flags
-    for _ in range(args.preroll):        # reach the stationary population (device counter-stream controls)
-        games.step_raw(0, flags)
-    torch.cuda.synchronize()
-    flags |= args.timed_flags            # (experiment builds: bits that only apply after the pre-roll)
-
-    # ring of control arrays resident in HBM / in pinned host memory: R different arrays, one per tick
-    R = max(8, args.fuse)
-    gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
-    host_ring = torch.randint(0, 6, (R, games.n_pad, S), dtype=torch.uint8, generator=gen).pin_memory()
-    dev_ring = host_ring.to(dev)
-    ptrs = [dev_ring[i].data_ptr() for i in range(R)]
-    events_host = torch.empty(games.n_pad, dtype=torch.uint8).pin_memory()
-    events_dev = torch.empty((R, games.n_pad), dtype=torch.uint8, device=dev)
-
-    def run_steps(k_steps):
-        """k_steps ticks, args.fuse per launch, tick k reading control array k % R; returns the launches."""
-        done, n_launch = 0, 0
-        while done < k_steps:
-            r0 = done % R
-            t = min(args.fuse, k_steps - done, R - r0)
-            games.step_many_raw(ptrs[r0], events_dev[r0].data_ptr(), t, flags)
-            done += t
-            n_launch += 1
-        return n_launch
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    run_steps(args.warmup)
-    games.stats_tensor(clear=True)
-    launches0 = games.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    n_launches = run_steps(args.steps)
-    st_t = games.stats_tensor(clear=True).clone()
-    reduce_stats(st_t, dist)             # NCCL: the episode-statistics reduction, once per rollout
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    my_ms = e0.elapsed_time(e1)
-    ms = reduce_max(my_ms, dev, dist)
-    launches = games.launches - launches0
-    total = dict(zip(nat.STAT_NAMES, (int(x) for x in st_t.cpu().numpy())))
-    value = total['env_steps'] / (ms * 1e-3)
-
-    # kernel-only roofline of the tick kernel on this rank: one launch per step, back to back
-    games_stats_local = total if world == 1 else None
-    if world > 1:
-        # per-rank counters for the local roofline: re-measure a short local window
-        games.stats_tensor(clear=True)
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        run_steps(args.steps)
-        r1.record()
-        torch.cuda.synchronize()
-        kern_ms = r0.elapsed_time(r1)
-        games_stats_local = games.stats(clear=True)
-    else:
-        kern_ms = my_ms
-    alg = algorithmic_bytes(games_stats_local, S)
+    io_flags = nat.TICK_PACKED_CONTROLS | nat.TICK_EVENT_PLANES
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
     peak = float(peaks.get('hbm_gbs', FALLBACK_HBM_GBS))
-    achieved = alg / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        prof = json.load(open(os.path.join(ROOT, 'profiles', 'tick_kernel_ncu_summary.json')))
-        traffic = prof.get('dram_bytes_per_launch')
-    except Exception:
-        pass
-    roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic,
-                    kernel='tick_f32_kernel<2,true,%s>' % ('true' if args.fuse > 1 else 'false'),
-                    peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
-                    ticks_per_launch=args.steps / n_launches,
-                    algorithmic_bytes_per_launch=alg / n_launches,
-                    bytes_per_env_step=alg / max(1, games_stats_local['env_steps']),
-                    mean_planets=games_stats_local['planets_live'] / max(1, games_stats_local['env_steps']),
-                    mean_bullets=games_stats_local['bullets_in'] / max(1, games_stats_local['env_steps']),
-                    avg_launch_us=1e3 * kern_ms / n_launches,
-                    note='algorithmic bytes = every live byte of state read and written once PER TICK; with several ticks '
-                         'of a tile per launch most of that traffic stays in L2 (traffic = DRAM bytes per launch, ncu)')
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    # the same loop as one launch per tick (a policy between the ticks needs this form)
-    pt_steps = max(R, min(args.steps, 400))
+    def gather_ms(my_ms):
+        """every rank's time, as a list (rank order)"""
+        if world == 1:
+            return [my_ms]
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = my_ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.cpu()]
+
+    def timed_rollout(n_games, first_game, steps, warmup, fuse, collective=True):
+        """The timed region of the headline: `steps` ticks of n_games games on this rank, `fuse` ticks per launch, controls
+        resident in HBM (a different array every tick), every tick's events written, then the episode statistics and their
+        NCCL all-reduce.  -> dict(ms per rank, counters, launches, games)"""
+        games = BatchedGames(cfg, n_games, bullet_cap=K, precision=32, device=local, seed=args.seed, first_game=first_game)
+        games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        games.reset_all()
+        flags = nat.TICK_AUTO_RESET | args.tick_flags
+        for _ in range(args.preroll):        # reach the stationary population (device counter-stream controls)
+            games.step_raw(0, flags)
+        torch.cuda.synchronize()
+        flags |= args.timed_flags | io_flags
+        R = max(8, fuse)
+        gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
+        host_ring = BatchedGames.pack_controls(torch.randint(0, 6, (R, games.n_pad, S), dtype=torch.uint8, generator=gen)).contiguous().pin_memory()
+        dev_ring = host_ring.to(dev)
+        events_dev = torch.empty(games.planes_shape(R), dtype=torch.int32, device=dev)
+
+        def run_steps(k_steps):
+            done, n_launch = 0, 0
+            while done < k_steps:
+                r0 = done % R
+                t = min(fuse, k_steps - done, R - r0)
+                games.step_many_raw(dev_ring[r0].data_ptr(), events_dev[r0].data_ptr(), t, flags)
+                done += t
+                n_launch += 1
+            return n_launch
+        run_steps(warmup)
+        games.stats_tensor(clear=True)
+        launches0 = games.launches
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        n_launches = run_steps(steps)
+        st_t = games.stats_tensor(clear=True)
+        if collective:
+            reduce_stats(st_t, dist)         # NCCL: the episode-statistics reduction, once per rollout
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return dict(games=games, ms=gather_ms(e0.elapsed_time(e1)), stats=dict(zip(nat.STAT_NAMES, (int(x) for x in st_t.cpu().numpy()))),
+                    launches=games.launches - launches0, n_launches=n_launches, run_steps=run_steps, flags=flags,
+                    host_ring=host_ring, dev_ring=dev_ring, R=R)
+
+    plan = shard_plan(world, rank, args.games_per_gpu)
+    n = plan['n_games']
+    sampler = ClockSampler(local)
+    sampler.start()
+    main = timed_rollout(n, plan['first_game'], args.steps, args.warmup, args.fuse)
+    games, flags, R, run_steps = main['games'], main['flags'], main['R'], main['run_steps']
+    ms = max(main['ms'])
+    per_rank_ms, timed_launches = [round(x, 4) for x in main['ms']], main['launches']
+    total = main['stats']
+    value = total['env_steps'] / (ms * 1e-3)
+
+    # the collective alone: episode counters -> device vector -> NCCL all-reduce (what the timed region ends with)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        reduce_stats(games.stats_tensor(clear=False), dist)
+    torch.cuda.synchronize()
+    collective_us = max(gather_ms(1e6 * (time.perf_counter() - t0) / reps))
+
+    # kernel-only window on this rank (no collective inside): the roofline numbers
     games.stats_tensor(clear=True)
     torch.cuda.synchronize()
     e0.record()
-    for k in range(pt_steps):
-        games.step_raw(ptrs[k % R], flags)
+    k_launches = run_steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
-    pt_ms = reduce_max(e0.elapsed_time(e1), dev, dist)
-    pt_stats = games.stats(clear=True)
-    per_tick = dict(value=world * n * pt_steps / (pt_ms * 1e-3), unit=UNIT, ms_per_step=pt_ms / pt_steps, steps=pt_steps,
-                    frac_of_hbm_peak=algorithmic_bytes(pt_stats, S) / (pt_ms * 1e-3) / 1e9 / peak,
-                    kernel='tick_f32_kernel<2,true,false>')
+    kern_ms = e0.elapsed_time(e1)
+    local_stats = games.stats(clear=True)
+    alg = algorithmic_bytes(local_stats, S, packed=True, planes=True)
+    achieved = alg / (kern_ms * 1e-3) / 1e9
+    tpl = args.steps / k_launches
+    prof = profile_entry(tpl)
+    roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                    traffic=(prof or {}).get('dram_bytes_per_launch'),
+                    kernel='tick_f32_kernel<2,true,%s>' % ('true' if args.fuse > 1 else 'false'),
+                    peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
+                    ticks_per_launch=tpl, algorithmic_bytes_per_launch=alg / k_launches,
+                    bytes_per_env_step=alg / max(1, local_stats['env_steps']),
+                    mean_planets=local_stats['planets_live'] / max(1, local_stats['env_steps']),
+                    mean_bullets=local_stats['bullets_in'] / max(1, local_stats['env_steps']),
+                    avg_launch_us=1e3 * kern_ms / k_launches,
+                    traffic_source=('ncu --set full on a launch of %d ticks (profiles/tick_kernel_ncu_summary.json)' % round(tpl)) if prof else
+                                   'no ncu capture at this launch shape: not printed',
+                    kind='ALGORITHMIC bytes (every live byte of state read and written once PER TICK) / time. With several ticks of a tile '
+                         'per launch most of them never leave L2 (compare traffic): frac says how fast the ticks go relative to a tick-by-tick '
+                         'HBM roofline, not how busy DRAM is; the HBM-bound form is per_tick_launch.roofline',
+                    secondary=dict(bound='issue', issue_active_pct=(prof or {}).get('issue_active_pct'),
+                                   warp_instr_per_tile_tick=((prof or {}).get('warp_instructions') or 0) / (n / 32 * max(1, round(tpl))) if prof else None,
+                                   l2_hit_pct=(prof or {}).get('l2_hit_pct'), source='same ncu capture'))
 
-    # e2e: the public API with HOST buffers; every tick's controls are copied in from pinned host
-    # memory and its events copied out, all inside the timed region (copies of neighbouring ticks
-    # overlap the kernel: BatchedGames.rollout_host -> astro_rollout_host)
-    # (a call covers E ticks: E different control arrays in pinned host memory, E event arrays back)
+    # the same loop as one launch per tick (a policy between the ticks needs this form): the HBM-bound kernel
+    pt_steps = max(R, min(args.steps, 400))
+    games.stats_tensor(clear=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(pt_steps):
+        games.step_many_raw(main['dev_ring'][k % R].data_ptr(), 0, 1, flags)
+    e1.record()
+    torch.cuda.synchronize()
+    pt_local = e0.elapsed_time(e1)
+    pt_ms = max(gather_ms(pt_local))
+    pt_stats = games.stats(clear=True)
+    pt_alg = algorithmic_bytes(pt_stats, S, packed=True, planes=False, events=False)
+    prof1 = profile_entry(1)
+    per_tick = dict(value=world * n * pt_steps / (pt_ms * 1e-3), unit=UNIT, ms_per_step=pt_ms / pt_steps, steps=pt_steps,
+                    kernel='tick_f32_kernel<2,true,false>',
+                    roofline=dict(bound='hbm', achieved=pt_alg / (pt_local * 1e-3) / 1e9, peak=peak, unit='GB/s',
+                                  frac=pt_alg / (pt_local * 1e-3) / 1e9 / peak, traffic=(prof1 or {}).get('dram_bytes_per_launch'),
+                                  algorithmic_bytes_per_launch=pt_alg / pt_steps, avg_launch_us=1e3 * pt_local / pt_steps,
+                                  issue_active_pct=(prof1 or {}).get('issue_active_pct')))
+    per_tick['frac_of_hbm_peak'] = per_tick['roofline']['frac']
+
+    # e2e: the public API with HOST buffers; every tick's controls are copied in from pinned host memory and its events
+    # copied out, all inside the timed region (copies of neighbouring ticks overlap the kernel:
+    # BatchedGames.rollout_host -> astro_rollout_host).  One control byte per game in, three bit planes per tick out.
+    host_ring = main['host_ring']
     E = max(R, (args.e2e_call // R) * R) if args.e2e_steps >= args.e2e_call else R
-    e2e_steps = max(E, (max(3, min(args.steps, args.e2e_steps)) // E) * E)
-    e2e_ring = host_ring if E == R else host_ring.repeat(E // R, 1, 1).pin_memory()
-    events_ring = torch.empty((E, games.n_pad), dtype=torch.uint8).pin_memory()
-    games.rollout_host(e2e_ring, events_ring, auto_reset=True)      # warm-up: E ticks
+    e2e_steps = max(E, (max(3, min(max(args.steps, 256), args.e2e_steps)) // E) * E)
+    e2e_ring = host_ring if E == R else host_ring.repeat(E // R, 1).pin_memory()
+    planes_ring = torch.empty(games.planes_shape(E), dtype=torch.int32).pin_memory()
+    games.rollout_host(e2e_ring, planes_ring, auto_reset=True, packed=True, planes=True)      # warm-up: E ticks
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
     for k in range(e2e_steps // E):
-        games.rollout_host(e2e_ring, events_ring, auto_reset=True)
+        games.rollout_host(e2e_ring, planes_ring, auto_reset=True, packed=True, planes=True)
     e1.record()
     torch.cuda.synchronize()
-    e2e_ms = reduce_max(e0.elapsed_time(e1), dev, dist)
+    e2e_ms = max(gather_ms(e0.elapsed_time(e1)))
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
-    # the unpipelined form (copy in, tick, copy out, synchronise, every tick) for reference
+    # closed loop: copy in, tick, copy out, synchronise, EVERY tick (a host policy that needs tick k's events before it
+    # gives tick k + 1's controls); the tick is cut into slices of tiles so that copies overlap kernels within the tick
+    planes_one = torch.empty(games.planes_shape(), dtype=torch.int32).pin_memory()
+    closed_steps = 2 * R
+    for k in range(4):
+        games.step_host(host_ring[k % R], planes_one, auto_reset=True, packed=True, planes=True)
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    for k in range(R):
-        games.step_host(host_ring[k % R], events_host, auto_reset=True)
-    sync_ms = 1e3 * (time.perf_counter() - t0)
-    e2e_sync_value = world * n * R / (reduce_max(sync_ms, dev, dist) * 1e-3)
+    for k in range(closed_steps):
+        games.step_host(host_ring[k % R], planes_one, auto_reset=True, packed=True, planes=True)
+    closed_ms = max(gather_ms(1e3 * (time.perf_counter() - t0)))
+    closed_value = world * n * closed_steps / (closed_ms * 1e-3)
+    # ... and the round-1 byte forms (2 control bytes + 1 event byte per game) through the same calls, for comparison
+    gen = torch.Generator(device='cpu').manual_seed(99 + rank)
+    byte_ring = torch.randint(0, 6, (R, games.n_pad, S), dtype=torch.uint8, generator=gen).pin_memory()
+    byte_events = torch.empty((R, games.n_pad), dtype=torch.uint8).pin_memory()
+    games.rollout_host(byte_ring, byte_events, auto_reset=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(max(1, 128 // R)):
+        games.rollout_host(byte_ring, byte_events, auto_reset=True)
+    e1.record()
+    torch.cuda.synchronize()
+    byte_value = world * n * R * max(1, 128 // R) / (max(gather_ms(e0.elapsed_time(e1))) * 1e-3)
     clocks = sampler.stop()
+    e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=games.n_pad, d2h_bytes_per_step=games.n_tiles * 12, steps=e2e_steps,
+               api='BatchedGames.rollout_host(packed=True, planes=True) -> astro_rollout_host (copies overlap the kernel)',
+               ticks_per_call=E, loop='open: the controls of a call\'s %d ticks are known up front' % E,
+               closed_loop_value=closed_value,
+               closed_loop_api='BatchedGames.step_host(packed=True, planes=True) -> astro_tick_host: copy in, tick, copy out, synchronise, '
+                               'every tick; the tick runs as 4 slices of tiles whose copies overlap the other slices\' kernels',
+               unpipelined_value=closed_value,
+               byte_form_value=byte_value, byte_form_bytes_per_step=[games.n_pad * S, games.n_pad])
+    del games, main
+    torch.cuda.empty_cache()
+
+    # BASELINE config #4 as stated: 1,048,576 games in total, sharded across the GPUs (strong scaling)
+    strong = None
+    if args.strong_total > 0 and args.strong_total % (32 * world) == 0:
+        per = args.strong_total // world
+        sr = timed_rollout(per, rank * per, args.steps, args.warmup, args.fuse)
+        s_ms = max(sr['ms'])
+        strong = dict(config='BASELINE configs[3] as stated: %d games in total, %d per GPU' % (args.strong_total, per),
+                      games_total=args.strong_total, games_per_gpu=per, n_gpus=world, value=sr['stats']['env_steps'] / (s_ms * 1e-3),
+                      unit=UNIT, ms_per_step=s_ms / args.steps, ticks_per_launch=args.fuse, scaling='strong')
+        del sr
+        torch.cuda.empty_cache()
 
     if rank == 0:
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            n_cpu = 16384
-            rate, _, _ = cpu_rollout_rate(n_cpu, 20, 40, threads)           # calibrate
-            ticks = int(max(50, min(100000, args.cpu_seconds * rate / n_cpu)))
-            rate, dt, steps = cpu_rollout_rate(n_cpu, 20, ticks, threads)
-            cpu = dict(value=rate, unit=UNIT, cores=threads, kind='port',
-                       sample='%d games x %d ticks of the same workload (%.1f s), oracle C port of astro/core.py '
-                              'step with auto-reset, one thread per host core' % (n_cpu, ticks, dt))
+        rollout = None if args.no_rollout else config5_rollout(args, local, pool)
+        drop_in = None if args.no_rollout else drop_in_step(args)
+        cpu = None if args.no_cpu_baseline else cpu_baseline(args.cpu_seconds)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f32', data='synthetic', config=workload_config(args), roofline=roofline,
-                    cpu_baseline=cpu, clocks=clocks,
-                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=games.n_pad * S,
-                             d2h_bytes_per_step=games.n_pad, steps=e2e_steps,
-                             api='BatchedGames.rollout_host -> astro_rollout_host (copies overlap the kernel)', ticks_per_call=E,
-                             unpipelined_value=e2e_sync_value, unpipelined_api='BatchedGames.step_host -> astro_tick_host'),
-                    gpu_launches=launches, per_tick_launch=per_tick,
-                    episode_stats={k: total[k] for k in ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'overflow')})
+                    cpu_baseline=cpu, clocks=clocks, e2e=e2e, gpu_launches=timed_launches,
+                    per_tick_launch=per_tick, per_rank_ms=per_rank_ms, collective_us=collective_us, strong=strong, rollout=rollout, drop_in=drop_in,
+                    episode_stats={k: total[k] for k in ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'overflow', 'bad_controls')})
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -391,8 +592,12 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=256)
     ap.add_argument('--e2e-call', type=int, default=128, help='ticks per rollout_host call of the e2e leg')
-    ap.add_argument('--cpu-seconds', type=float, default=20.0)
-    ap.add_argument('--ref-games', type=int, default=65536)
+    ap.add_argument('--cpu-seconds', type=float, default=10.0)
+    ap.add_argument('--ref-seconds', type=float, default=3.0, help='--impl reference: length of the timed region')
+    ap.add_argument('--strong-total', type=int, default=1 << 20, help='BASELINE configs[3] as stated: games in total over all GPUs (0 = skip)')
+    ap.add_argument('--rollout-games', type=int, default=16384)
+    ap.add_argument('--rollout-ticks', type=int, default=1000)
+    ap.add_argument('--no-rollout', action='store_true', help='skip the config #5 / drop-in legs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--fuse', type=int, default=64, help='ticks per launch of the timed loop (astro_tick_many); 1 = one launch per tick')
     ap.add_argument('--tick-flags', type=int, default=0, help='extra ASTRO_TICK_* bits (kernel A/B)')

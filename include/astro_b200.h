@@ -84,6 +84,16 @@ extern "C" {
  * bit.  Without it tick 0 treats its inputs as float64 like every other tick (states canonicalised to float64). */
 #define ASTRO_TICK_CREATE_DTYPES 8
 #define ASTRO_TICK_ALL_CREATE_DTYPES 16
+/* Compact host traffic (astro_tick, astro_tick_many and the _host forms; duel games, the float32 kernel):
+ *   PACKED_CONTROLS  actions are u8 [n_games]: one byte per GAME, ship 0's code in bits 0-2, ship 1's in bits 3-5
+ *                    (the two codes of core.py:220-227 need 6 bits) — half the bytes of [n_games][2].
+ *   EVENT_PLANES     events are u32 [3][n_games / 32] per tick, three bit planes: bit g % 32 of word g / 32 of plane 0 =
+ *                    game g ended this tick, plane 1 = ship 0 was hit, plane 2 = ship 1 was hit (ended with neither:
+ *                    timeout) — everything core.step's (state is None, reward) carries (core.py:253-260), in 12 bytes
+ *                    per 32 games instead of 32.  ASTRO_EV_FIRED is a function of the schedule; overflow / skipped /
+ *                    bad-control ticks are counted by astro_stats. */
+#define ASTRO_TICK_PACKED_CONTROLS 32
+#define ASTRO_TICK_EVENT_PLANES 64
 
 /* error codes */
 #define ASTRO_OK 0

@@ -1358,7 +1358,7 @@ def test_control_codes_above_5_are_flagged_and_flown_as_no_op():
         (a0, e0, s0), (a1, e1, s1) = outs
         flagged = where.any(-1).numpy()
         assert ((e0 & nat.EV_BAD_CONTROL) != 0)[flagged].all() and not ((e0 & nat.EV_BAD_CONTROL) != 0)[~flagged].any()
-        assert (e0 & ~nat.EV_BAD_CONTROL == e1).all() and s0['bad_controls'] == int(flagged.sum()) and s1['bad_controls'] == 0
+        assert ((e0 & (255 ^ nat.EV_BAD_CONTROL)) == e1).all() and s0['bad_controls'] == int(flagged.sum()) and s1['bad_controls'] == 0
         assert H.same_bits(a0['ships'], a1['ships']) and (a0['n_bullets'] == a1['n_bullets']).all()
     with pytest.raises(ValueError):
         core.step(core.create(cfg), np.array([6, 0]), cfg)
@@ -1417,3 +1417,69 @@ def test_explore_process_matches_the_reference_statistics():
         assert hist[5] == 0 and e['hist'][5] == 0
         ref_h = np.array(e['hist'][:5]) / sum(e['hist'])
         assert np.abs(hist[:5] / hist.sum() - ref_h).max() < 0.02
+
+
+def test_packed_controls_and_event_planes_equal_the_byte_forms(monkeypatch):
+    """One control byte per game (ship 0 bits 0-2, ship 1 bits 3-5) and three event bit planes per tick instead of
+    2 + 1 bytes per game: astro_tick_many, astro_rollout_host and astro_tick_host (whole, and cut into slices of tiles
+    whose copies overlap the other slices' kernels) give the same events and leave the same state, in both builds."""
+    import torch
+    cfg, N, K, T = core.DEFAULT_CONFIG, 4096 + 64, 32, 40
+    pool = H.make_pool(cfg, 256)
+    gen = torch.Generator(device='cpu').manual_seed(21)
+
+    def fresh(prec):
+        g = _games(cfg, N, bullet_cap=K, precision=prec, seed=4)
+        g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        g.reset_all()
+        for _ in range(30):
+            g.step(None, auto_reset=True)
+        g.stats(clear=True)
+        return g
+
+    for prec in (32, 64):
+        base = fresh(prec)
+        acts = torch.randint(0, 6, (T, base.n_pad, 2), dtype=torch.uint8, generator=gen)
+        packed = base.pack_controls(acts)
+        assert packed.shape == (T, base.n_pad) and packed.dtype == torch.uint8
+        ev_ref = torch.zeros((T, base.n_pad), dtype=torch.uint8, device='cuda')
+        base.step_many(T, acts.cuda(), events=ev_ref, auto_reset=True)
+        want_ev = ev_ref.cpu().numpy()[:, :N] & 7
+        want = (base.get_arrays(), base.stats())
+        runs = {}
+        # device buffers, several ticks per launch
+        g = fresh(prec)
+        planes = torch.zeros(g.planes_shape(T), dtype=torch.int32, device='cuda')
+        g.step_many(T, packed.cuda(), events=planes, auto_reset=True, packed=True, planes=True)
+        runs['tick_many'] = (g, g.unpack_event_planes(planes))
+        # host buffers, pipelined
+        g = fresh(prec)
+        planes_h = torch.zeros(g.planes_shape(T), dtype=torch.int32).pin_memory()
+        g.rollout_host(packed.pin_memory(), planes_h, auto_reset=True, packed=True, planes=True)
+        runs['rollout_host'] = (g, g.unpack_event_planes(planes_h))
+        # host buffers, tick by tick: unsliced and sliced
+        for slices in (1, 3):
+            monkeypatch.setenv('ASTRO_HOST_SLICES', str(slices))
+            g = fresh(prec)
+            out = np.zeros((T, N), dtype=np.uint8)
+            pk, pl = packed.pin_memory(), torch.zeros(g.planes_shape(), dtype=torch.int32).pin_memory()
+            for k in range(T):
+                g.step_host(pk[k], pl, auto_reset=True, packed=True, planes=True)
+                out[k] = g.unpack_event_planes(pl)
+            runs['step_host/%d' % slices] = (g, out)
+            # ... and the byte forms through the sliced path
+            g = fresh(prec)
+            out = np.zeros((T, N), dtype=np.uint8)
+            ah, eh = acts.pin_memory(), torch.zeros(g.n_pad, dtype=torch.uint8).pin_memory()
+            for k in range(T):
+                g.step_host(ah[k], eh, auto_reset=True)
+                out[k] = eh.numpy()[:N] & 7
+            runs['step_host bytes/%d' % slices] = (g, out)
+        monkeypatch.delenv('ASTRO_HOST_SLICES')
+        for name, (g, ev) in runs.items():
+            assert (ev == want_ev).all(), (prec, name)
+            arr = g.get_arrays()
+            assert g.stats() == want[1], (prec, name)
+            for key in ('ships', 'planets', 'bullets', 'n_bullets', 'n_planets', 'tick', 'episode'):
+                assert (arr[key] == want[0][key]).all(), (prec, name, key)
+        assert want[1]['episodes'] > 300 and (want_ev == 4).sum() == 0 and ((want_ev & 3) != 0).sum() == want[1]['episodes']
