@@ -26,7 +26,7 @@ EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
            'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
            'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer', 'astro_tick_many', 'astro_explore_controls', 'astro_set_exploration',
-           'astro_export_games', 'astro_import_games', 'astro_single_game_bytes', 'astro_step_single_host')
+           'astro_tick_host_begin', 'astro_tick_host_end', 'astro_export_games', 'astro_import_games', 'astro_single_game_bytes', 'astro_step_single_host')
 
 
 class AstroConfig(C.Structure):
@@ -96,6 +96,8 @@ def lib():
     L.astro_tick.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.astro_tick_host.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.astro_tick_many.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+    L.astro_tick_host_begin.argtypes = [vp, vp, vp, i32, vp]
+    L.astro_tick_host_end.argtypes = [vp]
     L.astro_explore_controls.argtypes = [vp, C.c_double, C.c_double, u32, vp, vp, i32, vp]
     L.astro_set_exploration.argtypes = [vp, C.c_double, C.c_double, u32, vp]
     L.astro_rollout_host.argtypes = [vp, vp, vp, i32, i32, vp]

@@ -447,6 +447,20 @@ class BatchedGames:
                                             ptr(events_host), flags, self._stream()))
         self.step_index += 1
 
+    def step_host_begin(self, actions_host, events_host, auto_reset=False, stats=True, packed=False, planes=False, stream=None):
+        """step_host without the wait: enqueues copy in, tick, copy out on `stream` (a torch.cuda.Stream; default: the
+        current one) and returns; step_host_end() blocks until the events are on the host.  For a closed loop over
+        several batches on their own streams (see astro_tick_host_begin)."""
+        def ptr(x):
+            return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
+        flags = self._io_flags(auto_reset, stats, packed, planes)
+        st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        nat.check(nat.lib().astro_tick_host_begin(self._h, ptr(actions_host), ptr(events_host), flags, st))
+        self.step_index += 1
+
+    def step_host_end(self):
+        nat.check(nat.lib().astro_tick_host_end(self._h))
+
     def rollout_host(self, actions_host, events_host, auto_reset=False, stats=True, packed=False, planes=False):
         """Pipelined end-to-end rollout with HOST buffers: actions_host uint8 [T, n_pad, S] ([T, n_pad] with
         packed=True), events_host uint8 [T, n_pad] (int32 [T, 3, n_tiles] with planes=True) — pinned torch tensors

@@ -1272,6 +1272,14 @@ int fail(int code, const char* fmt, ...) {
 
 }  // namespace
 
+struct SingleGraph {      // a captured single-game step (astro_step_single_host)
+    cudaGraphExec_t exec;
+    const void* in;
+    void* out;
+    int32_t flags;
+};
+constexpr int kSingleGraphs = 4;
+
 struct AstroBatch {
     AstroConfig cfg;
     int32_t n_games, K, precision, device, S;
@@ -1293,9 +1301,11 @@ struct AstroBatch {
     cudaStream_t copy_in, copy_out;
     cudaEvent_t ev_in[2], ev_tick[2], ev_out[2];
     bool pipe_ready;
-    // astro_tick_host: the tick cut into slices of tiles (copy streams and ordering events, created lazily)
-    cudaStream_t slice_in, slice_out;
-    cudaEvent_t ev_slice_in[8], ev_slice_tick[8], ev_slice_start;
+    // astro_tick_host: the tick cut into slices of tiles, one stream per slice (created lazily)
+    cudaEvent_t ev_host_done;   // astro_tick_host_begin / _end
+    bool host_pending;
+    cudaStream_t slice_stream[8];
+    cudaEvent_t ev_slice_start;
     bool slice_ready;
     int32_t pipe_chunk;      // ticks per copy of astro_rollout_host
     uint8_t* d_done;
@@ -1308,6 +1318,10 @@ struct AstroBatch {
     int32_t* d_src;       // astro_import_games: game -> row map
     char* d_single;       // astro_step_single_host: device staging, in record then out record
     int64_t single_bytes;
+    cudaStream_t single_stream;
+    cudaEvent_t single_event;
+    SingleGraph single_graph[4];
+    int32_t single_next;
     double explore_t_in, explore_t_out;   // astro_set_exploration (ASTRO_BOT_EXPLORE)
     uint32_t explore_seed;
     int32_t* explore_state;
@@ -1558,14 +1572,13 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaFree(b->d_pol);
     cudaFree(b->d_src);
     cudaFree(b->d_single);
+    for (int i = 0; i < kSingleGraphs; i++)
+        if (b->single_graph[i].exec) cudaGraphExecDestroy(b->single_graph[i].exec);
+    if (b->single_stream) { cudaStreamDestroy(b->single_stream); cudaEventDestroy(b->single_event); }
+    if (b->ev_host_done) cudaEventDestroy(b->ev_host_done);
     if (b->slice_ready) {
-        for (int i = 0; i < 8; i++) {
-            cudaEventDestroy(b->ev_slice_in[i]);
-            cudaEventDestroy(b->ev_slice_tick[i]);
-        }
+        for (int i = 0; i < 8; i++) cudaStreamDestroy(b->slice_stream[i]);
         cudaEventDestroy(b->ev_slice_start);
-        cudaStreamDestroy(b->slice_in);
-        cudaStreamDestroy(b->slice_out);
     }
     if (b->pipe_ready) {
         for (int i = 0; i < 2; i++) {
@@ -1671,47 +1684,40 @@ int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_ho
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)b->n_games;
     // A closed loop (controls of tick k + 1 depend on the events of tick k) cannot overlap the copies of one tick with the
-    // kernel of another — but games are independent, so the tick is cut into slices of tiles: slice i's controls travel
-    // while slice i - 1 runs and slice i - 2's events travel back (float32 kernel; ASTRO_HOST_SLICES overrides, 1 = off).
+    // kernel of another — but games are independent, so the tick is cut into slices of tiles, each with its OWN stream:
+    // copy in, kernel, copy out are stream-ordered inside a slice and overlap the other slices' (float32 kernel;
+    // ASTRO_HOST_SLICES overrides, 1 = off).  (Three shared streams — copies in / kernels / copies out — ordered by
+    // events were measured first and lost: every cross-stream dependency costs microseconds, 130 -> 147 us per tick.)
     const char* slices_str = getenv("ASTRO_HOST_SLICES");   // (read on every call: tests switch it)
     const int slices_env = slices_str ? atoi(slices_str) : 0;
     const int n_tiles = b->n_games / ASTRO_TILE;
-    int slices = slices_env > 0 ? slices_env : (n_tiles >= 16384 ? 4 : 1);
+    int slices = slices_env > 0 ? slices_env : (n_tiles >= 16384 ? 2 : 1);
     if (slices > kMaxSlices) slices = kMaxSlices;
     if (slices > 1 && actions_host && events_host && !reward_host && !done_host && b->precision == 32 &&
         !(flags & ASTRO_TICK_GENERIC_KERNEL) && n_tiles >= slices) {
         if (!b->slice_ready) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&b->slice_in, cudaStreamNonBlocking));
-            CUDA_TRY(cudaStreamCreateWithFlags(&b->slice_out, cudaStreamNonBlocking));
-            for (int i = 0; i < kMaxSlices; i++) {
-                CUDA_TRY(cudaEventCreateWithFlags(&b->ev_slice_in[i], cudaEventDisableTiming));
-                CUDA_TRY(cudaEventCreateWithFlags(&b->ev_slice_tick[i], cudaEventDisableTiming));
-            }
+            for (int i = 0; i < kMaxSlices; i++) CUDA_TRY(cudaStreamCreateWithFlags(&b->slice_stream[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_slice_start, cudaEventDisableTiming));
             b->slice_ready = true;
         }
         const bool packed = (flags & ASTRO_TICK_PACKED_CONTROLS) != 0, planes = (flags & ASTRO_TICK_EVENT_PLANES) != 0;
         const size_t a_per_tile = (size_t)ASTRO_TILE * (packed ? 1 : b->S);
         CUDA_TRY(cudaEventRecord(b->ev_slice_start, st));               // earlier work of the caller's stream comes first
-        CUDA_TRY(cudaStreamWaitEvent(b->slice_in, b->ev_slice_start, 0));
         for (int i = 0; i < slices; i++) {
+            cudaStream_t ss = b->slice_stream[i];
             const int t0 = (int)((int64_t)n_tiles * i / slices), t1 = (int)((int64_t)n_tiles * (i + 1) / slices);
+            CUDA_TRY(cudaStreamWaitEvent(ss, b->ev_slice_start, 0));
             CUDA_TRY(cudaMemcpyAsync(b->d_actions + t0 * a_per_tile, actions_host + t0 * a_per_tile, (size_t)(t1 - t0) * a_per_tile,
-                                     cudaMemcpyHostToDevice, b->slice_in));
-            CUDA_TRY(cudaEventRecord(b->ev_slice_in[i], b->slice_in));
-            CUDA_TRY(cudaStreamWaitEvent(st, b->ev_slice_in[i], 0));
-            if (int r = do_ticks(b, b->d_actions, nullptr, nullptr, b->d_events, flags, st, 1, t0, t1 - t0, i == slices - 1)) return r;
-            CUDA_TRY(cudaEventRecord(b->ev_slice_tick[i], st));
-            CUDA_TRY(cudaStreamWaitEvent(b->slice_out, b->ev_slice_tick[i], 0));
+                                     cudaMemcpyHostToDevice, ss));
+            if (int r = do_ticks(b, b->d_actions, nullptr, nullptr, b->d_events, flags, ss, 1, t0, t1 - t0, i == slices - 1)) return r;
             if (planes)
                 CUDA_TRY(cudaMemcpy2DAsync(events_host + (size_t)t0 * 4, (size_t)n_tiles * 4, b->d_events + (size_t)t0 * 4, (size_t)n_tiles * 4,
-                                           (size_t)(t1 - t0) * 4, 3, cudaMemcpyDeviceToHost, b->slice_out));
+                                           (size_t)(t1 - t0) * 4, 3, cudaMemcpyDeviceToHost, ss));
             else
                 CUDA_TRY(cudaMemcpyAsync(events_host + (size_t)t0 * ASTRO_TILE, b->d_events + (size_t)t0 * ASTRO_TILE, (size_t)(t1 - t0) * ASTRO_TILE,
-                                         cudaMemcpyDeviceToHost, b->slice_out));
+                                         cudaMemcpyDeviceToHost, ss));
         }
-        CUDA_TRY(cudaStreamSynchronize(b->slice_out));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int i = 0; i < slices; i++) CUDA_TRY(cudaStreamSynchronize(b->slice_stream[i]));
         return ASTRO_OK;
     }
     if (actions_host) CUDA_TRY(cudaMemcpyAsync(b->d_actions, actions_host, actions_bytes(b, flags), cudaMemcpyHostToDevice, st));
@@ -1722,6 +1728,29 @@ int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_ho
     if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, b->d_done, n, cudaMemcpyDeviceToHost, st));
     if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, b->d_reward, n * b->S * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return ASTRO_OK;
+}
+
+int astro_tick_host_begin(AstroBatch* b, const uint8_t* actions_host, uint8_t* events_host, int32_t flags, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!actions_host || !events_host) return fail(ASTRO_E_INVALID, "null host buffer");
+    if (b->host_pending) return fail(ASTRO_E_STATE, "astro_tick_host_begin: the previous tick has not been ended (astro_tick_host_end)");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!b->ev_host_done) CUDA_TRY(cudaEventCreateWithFlags(&b->ev_host_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaMemcpyAsync(b->d_actions, actions_host, actions_bytes(b, flags), cudaMemcpyHostToDevice, st));
+    if (int r = do_tick(b, b->d_actions, nullptr, nullptr, b->d_events, flags, st)) return r;
+    CUDA_TRY(cudaMemcpyAsync(events_host, b->d_events, events_bytes(b, flags), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(b->ev_host_done, st));
+    b->host_pending = true;
+    return ASTRO_OK;
+}
+
+int astro_tick_host_end(AstroBatch* b) {
+    if (int r = check(b, true)) return r;
+    if (!b->host_pending) return fail(ASTRO_E_STATE, "astro_tick_host_end without astro_tick_host_begin");
+    b->host_pending = false;
+    CUDA_TRY(cudaEventSynchronize(b->ev_host_done));
     return ASTRO_OK;
 }
 
@@ -2128,6 +2157,43 @@ static AstroGameArrays single_arrays(char* rec, int32_t rows) {
     return a;
 }
 
+// The five operations of a single-game step (record in, import, tick, export, record out) are captured ONCE per
+// (in, out, flags) into a CUDA graph and replayed: one graph launch per step instead of five API calls.  Every
+// parameter of the sequence is fixed — the whole record travels, whatever the game's bullet count, and the lists are
+// put back into bullet buffer 0 before every step.
+static int single_graph_build(AstroBatch* b, const AstroSingleGame* in_host, AstroSingleGame* out_host, int32_t flags, SingleGraph* g) {
+    const int64_t rec = b->single_bytes;
+    char* d_in = b->d_single;
+    char* d_out = b->d_single + rec;
+    cudaStream_t st = b->single_stream;
+    const size_t bytes = (size_t)astro_single_game_bytes(b->K);
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = ASTRO_OK;
+    cudaError_t e = cudaMemcpyAsync(d_in, in_host, bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) rc = fail(ASTRO_E_CUDA, "record upload: %s", cudaGetErrorString(e));
+    b->cur = 0;
+    const AstroGameArrays ain = single_arrays(d_in, b->K);
+    if (!rc) rc = astro_import_games(b, nullptr, 1, &ain, st);
+    AstroSingleGame* g_in = reinterpret_cast<AstroSingleGame*>(d_in);
+    AstroSingleGame* g_out = reinterpret_cast<AstroSingleGame*>(d_out);
+    if (!rc) rc = do_tick(b, g_in->control, nullptr, nullptr, g_out->events, flags | ASTRO_TICK_NO_STATS, st);
+    const AstroGameArrays aout = single_arrays(d_out, b->K);
+    if (!rc) rc = astro_export_games(b, nullptr, 1, &aout, st);
+    if (!rc) {
+        e = cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = fail(ASTRO_E_CUDA, "record download: %s", cudaGetErrorString(e));
+    }
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    g->in = in_host; g->out = out_host; g->flags = flags;
+    return ASTRO_OK;
+}
+
 int astro_step_single_host(AstroBatch* b, const AstroSingleGame* in_host, AstroSingleGame* out_host, int32_t flags, void* stream) {
     if (int r = check(b, true)) return r;
     if (!in_host || !out_host) return fail(ASTRO_E_INVALID, "null record");
@@ -2142,25 +2208,31 @@ int astro_step_single_host(AstroBatch* b, const AstroSingleGame* in_host, AstroS
         if (!(fabs(in_host->ships[s][4]) <= kSinCosRange)) return fail(ASTRO_E_INVALID, "bearing %g of ship %d is beyond the range over which util.direction is reproduced", in_host->ships[s][4], s);
     }
     CUDA_TRY(cudaSetDevice(b->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t rec = (astro_single_game_bytes(b->K) + 63) & ~(int64_t)63;
     if (!b->d_single) {
+        const int64_t rec = (astro_single_game_bytes(b->K) + 63) & ~(int64_t)63;
         CUDA_TRY(cudaMalloc(&b->d_single, (size_t)(2 * rec)));
         b->single_bytes = rec;
+        CUDA_TRY(cudaStreamCreateWithFlags(&b->single_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&b->single_event, cudaEventDisableTiming));
     }
-    char* d_in = b->d_single;
-    char* d_out = b->d_single + rec;
-    CUDA_TRY(cudaMemcpyAsync(d_in, in_host, (size_t)astro_single_game_bytes(nb), cudaMemcpyHostToDevice, st));
-    const AstroGameArrays ain = single_arrays(d_in, nb);
-    if (int r = astro_import_games(b, nullptr, 1, &ain, stream)) return r;
-    AstroSingleGame* g_in = reinterpret_cast<AstroSingleGame*>(d_in);
-    AstroSingleGame* g_out = reinterpret_cast<AstroSingleGame*>(d_out);
-    if (int r = do_tick(b, g_in->control, nullptr, nullptr, g_out->events, flags | ASTRO_TICK_NO_STATS, st)) return r;
-    const int32_t rows_out = nb + b->S < b->K ? nb + b->S : b->K;
-    const AstroGameArrays aout = single_arrays(d_out, rows_out);
-    if (int r = astro_export_games(b, nullptr, 1, &aout, stream)) return r;
-    CUDA_TRY(cudaMemcpyAsync(out_host, d_out, (size_t)astro_single_game_bytes(rows_out), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    SingleGraph* g = nullptr;
+    for (int i = 0; i < kSingleGraphs; i++)
+        if (b->single_graph[i].exec && b->single_graph[i].in == in_host && b->single_graph[i].out == out_host && b->single_graph[i].flags == flags)
+            g = &b->single_graph[i];
+    if (!g) {
+        g = &b->single_graph[b->single_next++ % kSingleGraphs];
+        if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+        if (int r = single_graph_build(b, in_host, out_host, flags, g)) return r;
+    }
+    // earlier work of the caller's stream comes first; the step itself runs on the handle's own stream (a legacy
+    // default stream cannot be captured) and is complete when the call returns
+    CUDA_TRY(cudaEventRecord(b->single_event, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamWaitEvent(b->single_stream, b->single_event, 0));
+    b->cur = 0;
+    CUDA_TRY(cudaGraphLaunch(g->exec, b->single_stream));
+    CUDA_TRY(cudaStreamSynchronize(b->single_stream));
+    b->cur = 1;          // the lists are where the tick wrote them
+    b->launches += 3;
     return ASTRO_OK;
 }
 

@@ -142,13 +142,13 @@ def drop_in_step(args):
     from astro_b200 import core, rng
     from oracle import astro_oracle as ao
     cfg = core.DEFAULT_CONFIG
-    state = core.create(cfg)
-    n, t_gpu, k = 0, 0.0, 0
+    controls = [rng.actions(5, [0], k, 2)[0] for k in range(400)]
+    t_gpu = 0.0
     for warm in (True, False):
         state = core.create(cfg)
         t0 = time.perf_counter()
         for k in range(400):
-            nxt, _ = core.step(state, rng.actions(5, [0], k, 2)[0], cfg)
+            nxt, _ = core.step(state, controls[k], cfg)
             state = core.create(cfg) if nxt is None else nxt
         t_gpu = time.perf_counter() - t0
     sh = np.zeros((2, 5)); pl = np.zeros((1, 4)); sh[:, 0] = (-0.5, 0.5); pl[0, 1] = 0.9
@@ -525,6 +525,37 @@ def run_ours(args):
         games.step_host(host_ring[k % R], planes_one, auto_reset=True, packed=True, planes=True)
     closed_ms = max(gather_ms(1e3 * (time.perf_counter() - t0)))
     closed_value = world * n * closed_steps / (closed_ms * 1e-3)
+    # closed loop over TWO half-batches on their own streams (astro_tick_host_begin / _end): while one half's tick runs, the
+    # other half's events travel back and its next controls travel in; each half still gets its tick k events before it
+    # gives its tick k + 1 controls
+    halves = []
+    for h in range(2):
+        gh = BatchedGames(cfg, n // 2, bullet_cap=K, precision=32, device=local, seed=args.seed, first_game=plan['first_game'] + h * (n // 2))
+        gh.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        gh.reset_all()
+        for _ in range(min(args.preroll, 300)):
+            gh.step_raw(0, nat.TICK_AUTO_RESET)
+        halves.append((gh, torch.cuda.Stream(device=dev), host_ring[:, h * (n // 2):(h + 1) * (n // 2)].contiguous().pin_memory(),
+                       torch.empty(gh.planes_shape(), dtype=torch.int32).pin_memory()))
+    torch.cuda.synchronize()
+
+    def pingpong(steps):
+        for gh, st, ring, pl in halves:
+            gh.step_host_begin(ring[0], pl, auto_reset=True, packed=True, planes=True, stream=st)
+        for k in range(1, steps):
+            for gh, st, ring, pl in halves:
+                gh.step_host_end()              # tick k - 1's events of this half are on the host ...
+                gh.step_host_begin(ring[k % R], pl, auto_reset=True, packed=True, planes=True, stream=st)   # ... before its tick k controls go in
+        for gh, st, ring, pl in halves:
+            gh.step_host_end()
+    pingpong(8)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    pingpong(closed_steps)
+    pp_ms = max(gather_ms(1e3 * (time.perf_counter() - t0)))
+    pingpong_value = world * 2 * (n // 2) * closed_steps / (pp_ms * 1e-3)
+    del halves
     # ... and the round-1 byte forms (2 control bytes + 1 event byte per game) through the same calls, for comparison
     gen = torch.Generator(device='cpu').manual_seed(99 + rank)
     byte_ring = torch.randint(0, 6, (R, games.n_pad, S), dtype=torch.uint8, generator=gen).pin_memory()
@@ -543,9 +574,12 @@ def run_ours(args):
     e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=games.n_pad, d2h_bytes_per_step=games.n_tiles * 12, steps=e2e_steps,
                api='BatchedGames.rollout_host(packed=True, planes=True) -> astro_rollout_host (copies overlap the kernel)',
                ticks_per_call=E, loop='open: the controls of a call\'s %d ticks are known up front' % E,
-               closed_loop_value=closed_value,
-               closed_loop_api='BatchedGames.step_host(packed=True, planes=True) -> astro_tick_host: copy in, tick, copy out, synchronise, '
-                               'every tick; the tick runs as 4 slices of tiles whose copies overlap the other slices\' kernels',
+               closed_loop_value=pingpong_value,
+               closed_loop_api='two half-batches alternating through BatchedGames.step_host_begin / step_host_end (astro_tick_host_begin / '
+                               '_end) on their own streams: every half gets its tick k events on the host before its tick k + 1 controls go in',
+               closed_loop_single_batch_value=closed_value,
+               closed_loop_single_batch_api='BatchedGames.step_host(packed=True, planes=True) -> astro_tick_host: copy in, tick, copy out, '
+                                            'synchronise, every tick, one batch (two slices of tiles on internal streams)',
                unpipelined_value=closed_value,
                byte_form_value=byte_value, byte_form_bytes_per_step=[games.n_pad * S, games.n_pad])
     del games, main

@@ -196,9 +196,19 @@ int astro_tick_many(AstroBatch* b, const uint8_t* actions, float* reward, uint8_
                     int32_t flags, void* stream);
 
 /* Same call with HOST buffers (pinned for full speed): H2D actions, tick, D2H events (and
- * reward/done when not NULL), then synchronises the stream. */
+ * reward/done when not NULL), then synchronises the stream.  Large float32 batches asked for events only run the tick as
+ * two slices of tiles on internal streams, so that one slice's copies overlap the other's kernel. */
 int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_host, uint8_t* done_host,
                     uint8_t* events_host, int32_t flags, void* stream);
+
+/* astro_tick_host in two halves, for a closed loop over SEVERAL batches: _begin enqueues the copy in, the tick and the copy
+ * of the events out on `stream` and returns at once; _end blocks until those events are on the host.  Games are
+ * independent, so a host policy can hold the games as two (or more) batches on their own streams and alternate —
+ * while batch A's tick runs, batch B's events travel back, its policy is evaluated and its next controls travel in
+ * (every batch still sees its tick k events before it gives its tick k + 1 controls: the loop of core.play /
+ * rl.train, core.py:388-404, per batch).  One tick may be pending per handle. */
+int astro_tick_host_begin(AstroBatch* b, const uint8_t* actions_host, uint8_t* events_host, int32_t flags, void* stream);
+int astro_tick_host_end(AstroBatch* b);
 
 /* n_ticks consecutive astro_tick_host calls as one pipelined stream: actions_host u8
  * [n_ticks][n_games][S], events_host u8 [n_ticks][n_games] (pinned).  Ticks travel in chunks of 4: the

@@ -1390,7 +1390,7 @@ def test_explore_process_matches_the_reference_statistics():
     device process on another random stream: enter / leave rates, active fraction, control histogram (never 5)."""
     import torch
     gold = json.load(open(os.path.join(H.G, 'explore.json')))
-    cfg, N, T = core.DEFAULT_CONFIG._replace(max_time=1e4), 4096, 120
+    cfg, N, T = core.DEFAULT_CONFIG._replace(max_time=1000.0), 4096, 120
     pool = H.make_pool(cfg, 64)
     for e in gold:
         g = _games(cfg, N, bullet_cap=32, precision=32, seed=2)
@@ -1476,6 +1476,20 @@ def test_packed_controls_and_event_planes_equal_the_byte_forms(monkeypatch):
                 out[k] = eh.numpy()[:N] & 7
             runs['step_host bytes/%d' % slices] = (g, out)
         monkeypatch.delenv('ASTRO_HOST_SLICES')
+        # begin / end on a stream of its own
+        g = fresh(prec)
+        out = np.zeros((T, N), dtype=np.uint8)
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        pk, pl = packed.pin_memory(), torch.zeros(g.planes_shape(), dtype=torch.int32).pin_memory()
+        for k in range(T):
+            g.step_host_begin(pk[k], pl, auto_reset=True, packed=True, planes=True, stream=st)
+            g.step_host_end()
+            out[k] = g.unpack_event_planes(pl)
+        st.synchronize()
+        runs['begin/end'] = (g, out)
+        with pytest.raises(nat.AstroError):
+            g.step_host_end()
         for name, (g, ev) in runs.items():
             assert (ev == want_ev).all(), (prec, name)
             arr = g.get_arrays()
