@@ -56,7 +56,8 @@ struct TickParams {
     int32_t n_games, K, timeout_tick, n_sched_ticks, pool_size, flags;
     uint32_t seed, step, first_game;
     int32_t n_fused;     // ticks per launch (tick_f32_kernel; 1 everywhere else)
-    uint32_t act_stride, ev_stride;   // bytes from one tick's controls / events to the next tick's
+    uint32_t act_stride, ev_stride;   // bytes from one tick's controls / events to the next tick's (0: no such array)
+    uint32_t rw_stride, done_stride;  // the same for reward / done
     int32_t tile0, tiles;             // tick_f32_kernel: the launch covers tiles tile0 .. tile0 + tiles - 1
     Consts c;
 };
@@ -1472,12 +1473,15 @@ int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done
         const int32_t kc = fused ? (n_ticks - k0 < kMaxFused ? n_ticks - k0 : kMaxFused) : 1;
         TickParams p;
         fill_params(b, p);
-        p.act_stride = (uint32_t)actions_bytes(b, flags);
-        p.ev_stride = (uint32_t)events_bytes(b, flags);
-        p.actions = actions ? actions + (size_t)k0 * p.act_stride : nullptr;
+        const uint32_t a_bytes = (uint32_t)actions_bytes(b, flags), e_bytes = (uint32_t)events_bytes(b, flags);
+        p.actions = actions ? actions + (size_t)k0 * a_bytes : nullptr;
         p.reward = reward ? reward + (size_t)k0 * n * b->S : nullptr;
         p.done = done ? done + (size_t)k0 * n : nullptr;
-        p.events = events ? events + (size_t)k0 * p.ev_stride : nullptr;
+        p.events = events ? events + (size_t)k0 * e_bytes : nullptr;
+        p.act_stride = actions ? a_bytes : 0u;           // (a null array stays null when the kernel advances it)
+        p.ev_stride = events ? e_bytes : 0u;
+        p.rw_stride = reward ? (uint32_t)(n * b->S * sizeof(float)) : 0u;
+        p.done_stride = done ? (uint32_t)n : 0u;
         p.flags = flags;
         p.n_fused = kc;
         p.tile0 = tile0;

@@ -31,6 +31,13 @@ constexpr int kTickWarps = kTickThreads / 32;
 #ifndef ASTRO_STAGE_WINDOWS
 #define ASTRO_STAGE_WINDOWS 8
 #endif
+// Round 2, instruction diet of the fused form (issue-bound; ncu dynamic instruction counts in profiles/r2_ab_diet.md):
+#ifndef ASTRO_OPT_STAGE
+#define ASTRO_OPT_STAGE 1     /* several ticks per launch: staging requests unrolled and predicated, 2-3 instructions per window instead of ~14 */
+#endif
+#ifndef ASTRO_OPT_PTRS
+#define ASTRO_OPT_PTRS 1      /* per-tick pointers = base + tick * stride (stride 0 for an absent array): no null tests, no 64-bit products */
+#endif
 constexpr int kStageWindows = ASTRO_STAGE_WINDOWS;   // bullets staged per round: 8 windows x 32 = 256 (4 KB per warp)
 
 // Per-game entries used by the bullet loop are indexed by the game's rank among the tile's games
@@ -276,12 +283,20 @@ struct TickVar {
 template <int S>
 __device__ __forceinline__ TickVar tick_var(const TickParams& p, unsigned k) {
     TickVar v;
-    const size_t n = (size_t)p.n_games;
     v.step = p.step + k;
-    v.actions = p.actions ? p.actions + k * (size_t)p.act_stride : nullptr;   // [n][S] bytes, or [n] packed
+#if ASTRO_OPT_PTRS
+    // base + tick * stride in 32 x 32 -> 64-bit products; the stride of an absent (null) array is 0
+    v.actions = p.actions + (size_t)k * p.act_stride;     // [n][S] bytes, or [n] packed
+    v.reward = reinterpret_cast<float*>(reinterpret_cast<char*>(p.reward) + (size_t)k * p.rw_stride);
+    v.done = p.done + (size_t)k * p.done_stride;
+    v.events = p.events + (size_t)k * p.ev_stride;        // [n] bytes, or three bit planes
+#else
+    const size_t n = (size_t)p.n_games;
+    v.actions = p.actions ? p.actions + k * (size_t)p.act_stride : nullptr;
     v.reward = p.reward ? p.reward + k * n * S : nullptr;
     v.done = p.done ? p.done + k * n : nullptr;
-    v.events = p.events ? p.events + k * (size_t)p.ev_stride : nullptr;       // [n] bytes, or three bit planes
+    v.events = p.events ? p.events + k * (size_t)p.ev_stride : nullptr;
+#endif
     v.bullets_in = reinterpret_cast<float4*>((k & 1u) ? p.bullets_out : p.bullets_in);
     v.bullets_out = reinterpret_cast<float4*>((k & 1u) ? p.bullets_in : p.bullets_out);
     return v;
@@ -335,7 +350,7 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar&
 // One core.step for the 32 games of one tile, by one warp.
 // `next` receives what the following tick of the same tile would load from the rows this tick wrote (meta, ships,
 // bearings): inside a launch that runs several ticks they are handed on in registers.
-template <int S, bool STATS>
+template <int S, bool STATS, bool MANY>
 // `last` = no further tick of this tile follows in this launch: only then do meta, ships and bearings go to memory
 // (planets and the bullet list always do), and the tile's statistics (`stat_acc`, summed over the launch's ticks).
 __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratch& t, const unsigned lane,
@@ -413,6 +428,23 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     const unsigned bul_s = (unsigned)__cvta_generic_to_shared(&t.bul[lane]);
     auto stage_round = [&](unsigned round_base) {
         const unsigned left = total - round_base;
+#if ASTRO_OPT_STAGE
+        if (MANY) {
+        // every window that holds a list item is requested, unrolled and predicated (one compare + one request each);
+        // the lanes past the end of the list in the last window stage the sentinel.  (Fewer instructions; the one-tick
+        // launch, which waits on HBM rather than on issue slots, is faster with the rolled loop below.)
+        const float4* const src = list_in + round_base + lane;
+#pragma unroll
+        for (unsigned w = 0; w < (unsigned)kStageWindows; w++) {
+            if (w * 32u + lane < left)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bul_s + w * 512u), "l"(src + w * 32u) : "memory");
+        }
+        const unsigned items = left < (unsigned)kStageWindows * 32u ? left : (unsigned)kStageWindows * 32u;
+        if ((items & 31u) != 0u && lane >= (items & 31u)) t.bul[(items & ~31u) + lane] = make_float4(4.0f, 4.0f, 0.0f, 0.0f);
+        cp_async_commit();
+        return;
+        }
+#endif
         const unsigned n_win = left >= (unsigned)kStageWindows * 32u ? (unsigned)kStageWindows : (left + 31u) >> 5;
 #pragma unroll 1
         for (unsigned w = 0; w < n_win; w++) {
@@ -592,6 +624,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     }
     if (lane == 0) t.gstart[__popc(ne)] = (uint16_t)carry;
     __syncwarp();
+    // first survivor of this lane's game in the compacted list, and one past its last
+    const unsigned g_first = nonempty ? (unsigned)t.gstart[cid] : 0u, g_end = nonempty ? (unsigned)t.gstart[cid + 1u] : 0u;
     TL(6);
 
     // ================= 5. terminal logic, spawn, bookkeeping ==========================================
@@ -607,7 +641,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     } else {
         int m = 0;   // survivors of this game
         if (nonempty) {
-            m = (int)t.gstart[cid + 1u] - (int)t.gstart[cid];
+            m = (int)(g_end - g_first);
             hits |= t.hits[cid] & 3u;
         }
 #ifdef ASTRO_EXPERIMENTS
@@ -740,7 +774,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         if (n_born > 0) ST_STREAM(&list_out[oexcl + surv], born[0]);
         if (n_born > 1) ST_STREAM(&list_out[oexcl + surv + 1u], born[1]);
         if (!multi) {
-            if (nonempty) t.shift[cid] = (ev & ASTRO_EV_DONE_MASK) ? kDrop : (int)oexcl - (int)t.gstart[cid];
+            if (nonempty) t.shift[cid] = (ev & ASTRO_EV_DONE_MASK) ? kDrop : (int)oexcl - (int)g_first;
             __syncwarp();
             // (byte offsets from the two shared arrays and the list base: 9 instructions per step)
             const char* const bul_b = reinterpret_cast<const char*>(t.bul);
@@ -753,7 +787,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             }
         } else {
             // (rare) the survivors sit compacted in the list that was read: every lane copies its game's run
-            const unsigned from = nonempty ? (unsigned)t.gstart[cid] : 0u;
+            const unsigned from = g_first;
             for (unsigned k = 0; k < surv; k++) list_out[oexcl + k] = list_in[from + k];
         }
     }
@@ -825,10 +859,11 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         uint32_t ctl_next = 0;
         if (MANY && p.actions && k + 1u < (unsigned)p.n_fused) {
             const size_t g = (size_t)tile * 32 + lane;
-            ctl_next = load_controls<S>(p.actions + (size_t)(k + 1u) * (size_t)p.act_stride, g, (p.flags & ASTRO_TICK_PACKED_CONTROLS) != 0);
+            ctl_next = load_controls<S>(v.actions + p.act_stride, g, (p.flags & ASTRO_TICK_PACKED_CONTROLS) != 0);
         }
         if (MANY) in.fire_word = p.fire_bits[min(ASTRO_META_TICK(in.meta), (uint32_t)p.n_sched_ticks - 1u) >> 5];
-        tick_tile<S, STATS>(p, v, s_tiles[threadIdx.x >> 5], lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
+        // (one-warp CTAs: the scratch is s_tiles[0], every shared address a compile-time constant — no base register)
+        tick_tile<S, STATS, MANY>(p, v, s_tiles[kTickWarps == 1 ? 0 : (threadIdx.x >> 5)], lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
         if (MANY) {
             // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
             // well), so it starts its prefix sums and list requests at once; only the planet rows are loaded.  The
