@@ -12,11 +12,11 @@ MAX_PLANETS = 4
 MAX_BULLET_CAP = 1023
 MAX_TICKS = 262143
 SINCOS_RANGE = 71476       # |bearing| over which util.direction (numpy float32 sin/cos) is reproduced bit for bit
-N_STATS = 13
+N_STATS = 14
 STAT_NAMES = ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'env_steps', 'bullets_spawned',
-              'overflow', 'planets_live', 'bullets_in', 'bullets_out', 'skipped', 'bad_controls')
+              'overflow', 'planets_live', 'bullets_in', 'bullets_out', 'skipped', 'bad_controls', 'awaiting')
 
-EV_HIT0, EV_HIT1, EV_TIMEOUT, EV_FIRED, EV_OVERFLOW, EV_SKIPPED, EV_BAD_CONTROL = 1, 2, 4, 8, 16, 32, 64
+EV_HIT0, EV_HIT1, EV_TIMEOUT, EV_FIRED, EV_OVERFLOW, EV_SKIPPED, EV_BAD_CONTROL, EV_AWAIT = 1, 2, 4, 8, 16, 32, 64, 128
 EV_DONE_MASK = 7
 TICK_AUTO_RESET, TICK_NO_STATS, TICK_GENERIC_KERNEL, TICK_CREATE_DTYPES, TICK_ALL_CREATE_DTYPES = 1, 2, 4, 8, 16
 TICK_PACKED_CONTROLS, TICK_EVENT_PLANES = 32, 64
@@ -26,7 +26,8 @@ EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro
            'astro_tick', 'astro_tick_host', 'astro_rollout_host', 'astro_reset_done', 'astro_observe', 'astro_stats',
            'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
            'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer', 'astro_tick_many', 'astro_explore_controls', 'astro_set_exploration',
-           'astro_tick_host_begin', 'astro_tick_host_end', 'astro_export_games', 'astro_import_games', 'astro_single_game_bytes', 'astro_step_single_host')
+           'astro_tick_host_begin', 'astro_tick_host_end', 'astro_fresh_games_enable', 'astro_fresh_games_reset_all',
+           'astro_fresh_games_refill', 'astro_fresh_games_positions', 'astro_config_seeds', 'astro_export_games', 'astro_import_games', 'astro_single_game_bytes', 'astro_step_single_host')
 
 
 class AstroConfig(C.Structure):
@@ -98,6 +99,11 @@ def lib():
     L.astro_tick_many.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     L.astro_tick_host_begin.argtypes = [vp, vp, vp, i32, vp]
     L.astro_tick_host_end.argtypes = [vp]
+    L.astro_fresh_games_enable.argtypes = [vp, C.POINTER(AstroCreateConfig), u32, i64, i32, vp]
+    L.astro_fresh_games_reset_all.argtypes = [vp, vp]
+    L.astro_fresh_games_refill.argtypes = [vp, vp]
+    L.astro_fresh_games_positions.argtypes = [vp, vp, vp, C.POINTER(i64), vp]
+    L.astro_config_seeds.argtypes = [u32, i64, i64, vp]
     L.astro_explore_controls.argtypes = [vp, C.c_double, C.c_double, u32, vp, vp, i32, vp]
     L.astro_set_exploration.argtypes = [vp, C.c_double, C.c_double, u32, vp]
     L.astro_rollout_host.argtypes = [vp, vp, vp, i32, i32, vp]

@@ -315,6 +315,28 @@ class BatchedGames:
         pool = nat.AstroResetPool(ships.data_ptr(), planets.data_ptr(), n_planets.data_ptr(), int(size), 0)
         nat.check(nat.lib().astro_set_reset_pool(self._h, C.byref(pool)))
 
+    # ---- fresh games without a pool -----------------------------------------------------------------
+    def enable_fresh_games(self, quota=48, skip=0):
+        """Pool-free re-creation (astro_fresh_games_enable): every game that ends under auto_reset is re-created from the
+        NEXT config of core.generate_configs(config) — core.create on the device, seeds from the library's host MT19937 —
+        so no start state is ever re-used (core.py:77-135, rl.py:350,374).  `quota` pre-created games per 32-game tile
+        between refills; `skip`: stream position to start from."""
+        c = self.config
+        cc = nat.AstroCreateConfig(float(c.inner_ship_position), float(c.outer_ship_position), float(c.planet_orbit),
+                                   int(c.max_planets), 0)
+        nat.check(nat.lib().astro_fresh_games_enable(self._h, C.byref(cc), int(c.seed) & 0xFFFFFFFF, int(skip), int(quota), self._stream()))
+        self._fresh = True
+
+    def fresh_positions(self):
+        """(positions int64 [n], tile_used int64 [n_tiles], cursor): the generate_configs stream position of each game's
+        current episode, the records each tile used since the last refill, the positions handed out so far."""
+        torch = _torch()
+        pos = torch.empty((self.n_pad,), dtype=torch.int32, device=self.device)
+        used = torch.empty((self.n_tiles,), dtype=torch.int32, device=self.device)
+        cur = C.c_int64(0)
+        nat.check(nat.lib().astro_fresh_games_positions(self._h, pos.data_ptr(), used.data_ptr(), C.byref(cur), self._stream()))
+        return (pos.cpu().numpy().view(np.uint32)[:self.n].astype(np.int64), used.cpu().numpy().view(np.uint32).astype(np.int64), int(cur.value))
+
     def reset_done(self):
         """Re-create every finished game from the pool (entry = pick(seed, game, current step))."""
         nat.check(nat.lib().astro_reset_done(self._h, self._stream()))
@@ -322,7 +344,14 @@ class BatchedGames:
             self.meta[self.n:] = 1 << 13      # the padding slots of the last tile stay finished (empty)
 
     def reset_all(self):
-        """(Re)start every game from the pool: game g starts as pool[pick(seed, g, key 0)]."""
+        """(Re)start every game from the pool: game g starts as pool[pick(seed, g, key 0)] — or, in fresh-game mode, from
+        the next n games of the generate_configs stream."""
+        if getattr(self, '_fresh', False):
+            nat.check(nat.lib().astro_fresh_games_reset_all(self._h, self._stream()))
+            self.step_index = 0
+            if self.n != self.n_pad:
+                self.meta[self.n:] = 1 << 13
+            return
         self.meta.fill_(1 << 13)
         self.episode.fill_(-1)
         self.set_stream(step=0)

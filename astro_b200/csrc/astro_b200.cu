@@ -18,6 +18,7 @@
 #include <cstring>
 #include <type_traits>
 #include <new>
+#include <vector>
 
 using namespace astro;
 
@@ -59,6 +60,10 @@ struct TickParams {
     uint32_t act_stride, ev_stride;   // bytes from one tick's controls / events to the next tick's (0: no such array)
     uint32_t rw_stride, done_stride;  // the same for reward / done
     int32_t tile0, tiles;             // tick_f32_kernel: the launch covers tiles tile0 .. tile0 + tiles - 1
+    float4* ring;                     // fresh-game mode (astro_fresh_games_enable): [n_tiles][quota] 128-byte records
+    uint32_t* tile_used;              //   records of each tile consumed since the last refill
+    uint32_t* game_pos;               //   [n_games] position in the generate_configs stream of each game's current episode
+    int32_t quota, pad_;
     Consts c;
 };
 
@@ -121,7 +126,7 @@ __device__ __forceinline__ unsigned warp_totals(int lane, int S, uint32_t ev, bo
 #pragma unroll
     for (int k = 0; k < ASTRO_N_STATS; k++) v[k] = 0u;
     // most tiles, most ticks: nobody ended, overflowed or was skipped, nobody fired
-    if (__ballot_sync(full, (ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_OVERFLOW | ASTRO_EV_SKIPPED | ASTRO_EV_BAD_CONTROL)) != 0)) {
+    if (__ballot_sync(full, (ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_OVERFLOW | ASTRO_EV_SKIPPED | ASTRO_EV_BAD_CONTROL | ASTRO_EV_AWAIT)) != 0)) {
         v[0] = __popc(__ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0));
         v[1] = __popc(__ballot_sync(full, S == 2 && coll && !h0));
         v[2] = __popc(__ballot_sync(full, S == 2 && coll && !h1));
@@ -130,6 +135,7 @@ __device__ __forceinline__ unsigned warp_totals(int lane, int S, uint32_t ev, bo
         v[7] = __popc(__ballot_sync(full, (ev & ASTRO_EV_OVERFLOW) != 0));
         v[11] = __popc(__ballot_sync(full, (ev & ASTRO_EV_SKIPPED) != 0));
         v[12] = __popc(__ballot_sync(full, (ev & ASTRO_EV_BAD_CONTROL) != 0));
+        v[13] = __popc(__ballot_sync(full, (ev & ASTRO_EV_AWAIT) != 0));
     }
     v[5] = __popc(__ballot_sync(full, active));
     v[6] = (unsigned)S * __popc(__ballot_sync(full, spawned != 0));
@@ -811,15 +817,19 @@ struct Mt19937Head {
     }
 };
 
-template <typename R, int S>
-__global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__ seeds, R* __restrict__ ships,
-                                                    R* __restrict__ planets, int32_t* __restrict__ np_out,
-                                                    const __grid_constant__ CreateParams q) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q.m) return;
+// One created game in registers: float32 ship positions / bearings and planet positions, float64 planet velocities
+// (the reference's dtypes under numpy >= 2).
+struct CreatedGame {
+    float sx[2][2], sb[2];
+    float px[ASTRO_MAX_PLANETS][2];
+    double pv[ASTRO_MAX_PLANETS][2];
+    int n;
+};
+template <int S>
+__device__ __forceinline__ void create_game(uint32_t seed, const CreateParams& q, CreatedGame& o) {
     const double TWO_PI = 6.283185307179586, PI = 3.141592653589793;
     Mt19937Head mt;
-    mt.seed(seeds[i]);
+    mt.seed(seed);
     const int n = 1 + (int)mt.bounded((uint32_t)(q.max_planets - 1));
     // 1. ships
     const float r0 = (float)mt.rand(), r1 = (float)mt.rand();
@@ -830,30 +840,25 @@ __global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__
     float sn, cs;
     np_sincos_f32((float)__dmul_rn(TWO_PI, mt.rand()), sn, cs);
     const float i0 = __fmul_rn(inner_f, sn), i1 = __fmul_rn(inner_f, cs);
-    float sx[2][2];
     if (n == 1) {
-        sx[0][0] = o0; sx[0][1] = o1; sx[1][0] = -o0; sx[1][1] = -o1;
+        o.sx[0][0] = o0; o.sx[0][1] = o1; o.sx[1][0] = -o0; o.sx[1][1] = -o1;
     } else {
         const bool first = mt.rand() < 0.5;
         if (S == 1) {
-            sx[0][0] = first ? o0 : i0; sx[0][1] = first ? o1 : i1;
-            sx[1][0] = sx[1][1] = 0.f;
+            o.sx[0][0] = first ? o0 : i0; o.sx[0][1] = first ? o1 : i1;
+            o.sx[1][0] = o.sx[1][1] = 0.f;
         } else {
-            sx[0][0] = first ? o0 : i0; sx[0][1] = first ? o1 : i1;
-            sx[1][0] = first ? i0 : o0; sx[1][1] = first ? i1 : o1;
+            o.sx[0][0] = first ? o0 : i0; o.sx[0][1] = first ? o1 : i1;
+            o.sx[1][0] = first ? i0 : o0; o.sx[1][1] = first ? i1 : o1;
         }
     }
     const float two_pi_f = (float)TWO_PI;
+    o.sb[1] = 0.f;
 #pragma unroll
-    for (int s = 0; s < S; s++) {
-        R* o = ships + ((size_t)i * S + s) * 5;
-        o[0] = (R)sx[s][0]; o[1] = (R)sx[s][1]; o[2] = (R)0; o[3] = (R)0;
-        o[4] = (R)__fmul_rn(two_pi_f, (float)mt.rand());
-    }
+    for (int s = 0; s < S; s++) o.sb[s] = __fmul_rn(two_pi_f, (float)mt.rand());
     // 2. planets
-    R* pl = planets + (size_t)i * (ASTRO_MAX_PLANETS * 4);
 #pragma unroll
-    for (int j = 0; j < ASTRO_MAX_PLANETS * 4; j++) pl[j] = (R)0;
+    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) { o.px[j][0] = o.px[j][1] = 0.f; o.pv[j][0] = o.pv[j][1] = 0.0; }
     if (n > 1) {
         const double base = __dmul_rn(TWO_PI, mt.rand());
         const double step = __ddiv_rn(TWO_PI, (double)n);                    // np.linspace(0, 2 pi, n, endpoint=False)
@@ -861,19 +866,158 @@ __global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__
         const double quarter = __ddiv_rn(__dmul_rn(spin, PI), 2.0);
         const double speed = sqrt(__ddiv_rn(__dmul_rn(__dmul_rn(q.gravity, q.planet_mass), (double)(n - 1)), 2.0));
         const float orbit_f = (float)q.orbit;
-        for (int j = 0; j < n && j < ASTRO_MAX_PLANETS; j++) {
-            const double phase = __dadd_rn(base, __dadd_rn(__dmul_rn((double)j, step), 0.0));
-            float s0, c0, s1, c1;
-            np_sincos_f32((float)phase, s0, c0);
-            np_sincos_f32((float)__dadd_rn(phase, quarter), s1, c1);
-            pl[4 * j + 0] = (R)__fmul_rn(orbit_f, s0);
-            pl[4 * j + 1] = (R)__fmul_rn(orbit_f, c0);
-            pl[4 * j + 2] = (R)__dmul_rn(speed, (double)s1);
-            pl[4 * j + 3] = (R)__dmul_rn(speed, (double)c1);
+#pragma unroll
+        for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+            if (j < n) {
+                const double phase = __dadd_rn(base, __dadd_rn(__dmul_rn((double)j, step), 0.0));
+                float s0, c0, s1, c1;
+                np_sincos_f32((float)phase, s0, c0);
+                np_sincos_f32((float)__dadd_rn(phase, quarter), s1, c1);
+                o.px[j][0] = __fmul_rn(orbit_f, s0);
+                o.px[j][1] = __fmul_rn(orbit_f, c0);
+                o.pv[j][0] = __dmul_rn(speed, (double)s1);
+                o.pv[j][1] = __dmul_rn(speed, (double)c1);
+            }
         }
     }
-    np_out[i] = n;
+    o.n = n;
 }
+
+template <typename R, int S>
+__global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__ seeds, R* __restrict__ ships,
+                                                    R* __restrict__ planets, int32_t* __restrict__ np_out,
+                                                    const __grid_constant__ CreateParams q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.m) return;
+    CreatedGame o;
+    create_game<S>(seeds[i], q, o);
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        R* d = ships + ((size_t)i * S + s) * 5;
+        d[0] = (R)o.sx[s][0]; d[1] = (R)o.sx[s][1]; d[2] = (R)0; d[3] = (R)0;
+        d[4] = (R)o.sb[s];
+    }
+    R* pl = planets + (size_t)i * (ASTRO_MAX_PLANETS * 4);
+#pragma unroll
+    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+        pl[4 * j + 0] = (R)o.px[j][0];
+        pl[4 * j + 1] = (R)o.px[j][1];
+        pl[4 * j + 2] = (R)o.pv[j][0];
+        pl[4 * j + 3] = (R)o.pv[j][1];
+    }
+    np_out[i] = o.n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fresh games without a pool (core.generate_configs + core.create, core.py:77-135, for every re-creation): each tile
+// owns `quota` pre-created games (128-byte records, the layout of pack_pool_kernel + word 11 = position in the
+// generate_configs stream, word 12 = seed).  A game that ends takes the tile's next unused record — a warp-local
+// counter, no atomics, no dependent address — and between launches the records that were used are re-created from the
+// NEXT positions of the seed stream (host MT19937, uploaded ahead; positions handed out by a prefix sum in tile order,
+// so a rollout is reproducible): every re-creation consumes a stream position exactly once.
+//   refill_plan_kernel    one CTA: prefix sum of the tiles' used counts -> task list (record index), stream cursor
+//   refill_create_kernel  thread = task: create_game(seed at cursor + task) -> record
+//   fresh_fill_kernel     thread = game: (re)start every game of the batch from consecutive stream positions
+// ------------------------------------------------------------------------------------------
+struct FreshParams {
+    float4* ring;                  // [n_tiles][quota][8]
+    uint32_t* tile_used;           // [n_tiles] records of the tile consumed since the last refill
+    uint32_t* tasks;               // [n_tiles * quota] record indices to re-create
+    unsigned long long* cursor;    // [0] stream positions handed out so far, [1] refills completed, [2] tasks of the last plan
+    const uint32_t* seeds;         // ring of uploaded seeds: position p at p & seed_mask
+    uint32_t seed_mask;
+    int32_t n_tiles, quota, n_games;
+};
+
+template <int S>
+__device__ __forceinline__ void write_record(float4* rec, const CreatedGame& o, uint32_t pos, uint32_t seed) {
+    float w[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) w[i] = 0.f;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        w[5 * s + 0] = o.sx[s][0]; w[5 * s + 1] = o.sx[s][1]; w[5 * s + 4] = o.sb[s];
+    }
+    w[10] = __int_as_float(o.n);
+    w[11] = __uint_as_float(pos);
+    w[12] = __uint_as_float(seed);
+#pragma unroll
+    for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
+        w[16 + 4 * j + 0] = o.px[j][0]; w[16 + 4 * j + 1] = o.px[j][1];
+        w[16 + 4 * j + 2] = (float)o.pv[j][0]; w[16 + 4 * j + 3] = (float)o.pv[j][1];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) rec[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+__global__ void __launch_bounds__(1024) refill_plan_kernel(const __grid_constant__ FreshParams f) {
+    __shared__ unsigned s_sum[1024];
+    const int tid = threadIdx.x;
+    const int per = (f.n_tiles + 1023) / 1024;
+    const int t0 = tid * per, t1 = min(f.n_tiles, t0 + per);
+    unsigned mine = 0;
+    for (int t = t0; t < t1; t++) mine += min(f.tile_used[t], (uint32_t)f.quota);
+    s_sum[tid] = mine;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {               // inclusive scan
+        const unsigned v = tid >= d ? s_sum[tid - d] : 0u;
+        __syncthreads();
+        s_sum[tid] += v;
+        __syncthreads();
+    }
+    unsigned at = s_sum[tid] - mine;
+    for (int t = t0; t < t1; t++) {
+        const unsigned u = min(f.tile_used[t], (uint32_t)f.quota);
+        for (unsigned j = 0; j < u; j++) f.tasks[at + j] = (uint32_t)t * (uint32_t)f.quota + j;
+        at += u;
+        f.tile_used[t] = 0u;
+    }
+    if (tid == 1023) f.cursor[2] = s_sum[1023];
+}
+
+template <int S>
+__global__ void __launch_bounds__(64) refill_create_kernel(const __grid_constant__ FreshParams f, const __grid_constant__ CreateParams q) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n_tasks = (unsigned)f.cursor[2];
+    if (i >= n_tasks) return;
+    const unsigned long long pos = f.cursor[0] + i;
+    const uint32_t seed = f.seeds[(uint32_t)pos & f.seed_mask];
+    CreatedGame o;
+    create_game<S>(seed, q, o);
+    write_record<S>(f.ring + (size_t)f.tasks[i] * 8, o, (uint32_t)pos, seed);
+}
+// (after refill_create_kernel: the cursor moves on — a one-thread kernel, stream-ordered behind it)
+__global__ void refill_commit_kernel(const __grid_constant__ FreshParams f) {
+    f.cursor[0] += f.cursor[2];
+    f.cursor[1] += 1ull;
+    f.cursor[2] = 0ull;
+}
+
+template <int S>
+__global__ void __launch_bounds__(64) fresh_fill_kernel(const __grid_constant__ FreshParams f, const __grid_constant__ CreateParams q,
+                                                        float4* __restrict__ ships, float* __restrict__ ship_b, float4* __restrict__ planets,
+                                                        uint32_t* __restrict__ meta, uint32_t* __restrict__ episode, uint32_t* __restrict__ game_pos) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= f.n_games) return;
+    const unsigned long long pos = f.cursor[0] + (unsigned)g;
+    const uint32_t seed = f.seeds[(uint32_t)pos & f.seed_mask];
+    CreatedGame o;
+    create_game<S>(seed, q, o);
+    const size_t tile = (size_t)(g >> 5);
+    const int lane = g & 31;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        ships[tile * (S * 32) + s * 32 + lane] = make_float4(o.sx[s][0], o.sx[s][1], 0.f, 0.f);
+        ship_b[tile * (S * 32) + s * 32 + lane] = o.sb[s];
+    }
+#pragma unroll
+    for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
+        planets[tile * (ASTRO_MAX_PLANETS * 32) + j * 32 + lane] = make_float4(o.px[j][0], o.px[j][1], (float)o.pv[j][0], (float)o.pv[j][1]);
+    meta[g] = ASTRO_META_PACK(0, o.n, 0, 0);
+    episode[g] = 0u;
+    game_pos[g] = (uint32_t)pos;
+}
+__global__ void fresh_fill_commit_kernel(const __grid_constant__ FreshParams f) { f.cursor[0] += (unsigned)f.n_games; }
 
 // ------------------------------------------------------------------------------------------
 // policy_kernel<R, S>: rl.ValueNetwork.forward (rl.py:140-165) on the features of rl.py:43-72,
@@ -1273,6 +1417,49 @@ int fail(int code, const char* fmt, ...) {
 
 }  // namespace
 
+// numpy's legacy RandomState(seed) word stream (MT19937, init_genrand seeding) on the host: core.generate_configs
+// (core.py:77-83) draws one randint(2**30) per config = one 32-bit word masked to 30 bits (a power-of-two range: the
+// masked rejection never rejects).
+struct HostMt19937 {
+    uint32_t mt[624];
+    int idx;
+    void seed(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int k = 0; k < 624; k++) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t v = mt[idx++];
+        v ^= v >> 11;
+        v ^= (v << 7) & 0x9d2c5680u;
+        v ^= (v << 15) & 0xefc60000u;
+        v ^= v >> 18;
+        return v;
+    }
+};
+
+constexpr int kFreshLead = 3;     // refills the host may run ahead of the device
+struct FreshState {
+    FreshParams f;                // device pointers (ring, tile_used, tasks, cursor, seeds)
+    CreateParams cq;
+    uint32_t* game_pos;           // device [n_games]
+    uint32_t* h_seeds;            // pinned mirror of the seed ring
+    unsigned long long* h_cursor; // pinned: [0] stream positions handed out, [1] refills completed (lagging copies)
+    HostMt19937 mt;
+    unsigned long long generated; // stream positions generated (and uploaded) so far
+    unsigned long long refills;   // refills enqueued so far
+    cudaEvent_t done[kFreshLead]; // refill k's completion = done[k % kFreshLead]
+    int64_t ticks_since_refill;
+    int64_t capacity;             // n_tiles * quota
+};
+
 struct SingleGraph {      // a captured single-game step (astro_step_single_host)
     cudaGraphExec_t exec;
     const void* in;
@@ -1303,6 +1490,8 @@ struct AstroBatch {
     cudaEvent_t ev_in[2], ev_tick[2], ev_out[2];
     bool pipe_ready;
     // astro_tick_host: the tick cut into slices of tiles, one stream per slice (created lazily)
+    // fresh-game mode (astro_fresh_games_enable): per-tile rings of pre-created games fed from the generate_configs stream
+    FreshState* fresh;
     cudaEvent_t ev_host_done;   // astro_tick_host_begin / _end
     bool host_pending;
     cudaStream_t slice_stream[8];
@@ -1389,6 +1578,12 @@ void fill_params(const AstroBatch* b, TickParams& p) {
     p.K = b->K;
     p.timeout_tick = b->timeout_tick;
     p.n_sched_ticks = b->n_sched_ticks;
+    if (b->fresh) {
+        p.ring = b->fresh->f.ring;
+        p.tile_used = b->fresh->f.tile_used;
+        p.game_pos = b->fresh->game_pos;
+        p.quota = b->fresh->f.quota;
+    }
     p.seed = b->seed;
     p.step = b->step;
     p.first_game = (uint32_t)b->first_game;
@@ -1450,6 +1645,48 @@ cudaError_t fold_stats(AstroBatch* b, cudaStream_t st) {
 constexpr int kMaxFused = 256;
 constexpr int kMaxSlices = 8;
 constexpr double kSinCosRange = 71476.0;   // np_sincos_f32 (astro_device.cuh)
+// ---- fresh-game mode: the host side of the seed stream and the refill ---------------------------------------------
+// Stream positions [generated, upto) are drawn from the host MT19937 into the pinned mirror ring and uploaded
+// (stream-ordered) to the device ring.  A slot is overwritten ring-size positions later: the refill protocol keeps
+// `generated` within kFreshLead + 1 capacities of the device's cursor, and the ring holds 2 (kFreshLead + 2) capacities.
+int fresh_upload_seeds(AstroBatch* b, unsigned long long upto, cudaStream_t st) {
+    FreshState* fs = b->fresh;
+    const unsigned long long ring = (unsigned long long)fs->f.seed_mask + 1ull;
+    while (fs->generated < upto) {
+        const unsigned long long at = fs->generated & fs->f.seed_mask;
+        unsigned long long n = upto - fs->generated;
+        if (n > ring - at) n = ring - at;
+        for (unsigned long long i = 0; i < n; i++) fs->h_seeds[at + i] = fs->mt.next() & 0x3fffffffu;   // randint(2**30)
+        CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(fs->f.seeds) + at, fs->h_seeds + at, (size_t)n * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, st));
+        fs->generated += n;
+    }
+    return ASTRO_OK;
+}
+
+// One refill: every record used since the last one is re-created from the next positions of the stream.
+int fresh_refill(AstroBatch* b, cudaStream_t st) {
+    FreshState* fs = b->fresh;
+    // the host runs at most kFreshLead refills ahead of the device: the cursor it reads below is then at most that stale
+    if (fs->refills >= (unsigned long long)kFreshLead) CUDA_TRY(cudaEventSynchronize(fs->done[fs->refills % kFreshLead]));
+    const unsigned long long cursor_seen = fs->h_cursor[0], refills_seen = fs->h_cursor[1];
+    // every refill not yet seen hands out at most `capacity` positions, and so does this one
+    const unsigned long long bound = cursor_seen + (fs->refills - refills_seen + 1ull) * (unsigned long long)fs->capacity;
+    if (int r = fresh_upload_seeds(b, bound, st)) return r;
+    refill_plan_kernel<<<1, 1024, 0, st>>>(fs->f);
+    const int grid = (int)((fs->capacity + 63) / 64);
+    if (b->S == 2) refill_create_kernel<2><<<grid, 64, 0, st>>>(fs->f, fs->cq);
+    else refill_create_kernel<1><<<grid, 64, 0, st>>>(fs->f, fs->cq);
+    refill_commit_kernel<<<1, 1, 0, st>>>(fs->f);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(fs->h_cursor, fs->f.cursor, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(fs->done[fs->refills % kFreshLead], st));
+    fs->refills += 1;
+    fs->ticks_since_refill = 0;
+    b->launches += 3;
+    return ASTRO_OK;
+}
+
 // bytes of one tick's controls / events in the form `flags` selects (include/astro_b200.h)
 size_t actions_bytes(const AstroBatch* b, int32_t flags) {
     return (flags & ASTRO_TICK_PACKED_CONTROLS) && b->S == 2 ? (size_t)b->n_games : (size_t)b->n_games * b->S;
@@ -1465,12 +1702,22 @@ int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done
              cudaStream_t st, int32_t n_ticks, int32_t tile0 = 0, int32_t tiles = 0, bool advance = true) {
     if (b->n_sched_ticks <= 0) return fail(ASTRO_E_STATE, "astro_set_schedule has not been called");
     if ((flags & ASTRO_TICK_PACKED_CONTROLS) && b->S != 2) return fail(ASTRO_E_INVALID, "ASTRO_TICK_PACKED_CONTROLS is for duel games");
-    if ((flags & ASTRO_TICK_AUTO_RESET) && b->pool.size <= 0)
-        return fail(ASTRO_E_STATE, "ASTRO_TICK_AUTO_RESET needs astro_set_reset_pool");
+    if ((flags & ASTRO_TICK_AUTO_RESET) && b->pool.size <= 0 && !b->fresh)
+        return fail(ASTRO_E_STATE, "ASTRO_TICK_AUTO_RESET needs astro_set_reset_pool or astro_fresh_games_enable");
     const bool fused = b->precision == 32 && !(flags & ASTRO_TICK_GENERIC_KERNEL);
+    if (b->fresh && (flags & ASTRO_TICK_AUTO_RESET) && !fused)
+        return fail(ASTRO_E_INVALID, "fresh-game mode re-creates games in the float32 production kernel only");
     const size_t n = (size_t)b->n_games;
     for (int32_t k0 = 0; k0 < n_ticks;) {
         const int32_t kc = fused ? (n_ticks - k0 < kMaxFused ? n_ticks - k0 : kMaxFused) : 1;
+        if (b->fresh && (flags & ASTRO_TICK_AUTO_RESET) && advance) {
+            // top the tiles' rings up once the ticks since the last refill, plus this launch, exceed half a quota (a tile
+            // loses ~0.3 games per tick under random play: ~15 % of its records by then)
+            FreshState* fs = b->fresh;
+            if (fs->ticks_since_refill > 0 && (fs->ticks_since_refill + kc) * 2 > fs->f.quota)
+                if (int r = fresh_refill(b, st)) return r;
+            fs->ticks_since_refill += kc;
+        }
         TickParams p;
         fill_params(b, p);
         const uint32_t a_bytes = (uint32_t)actions_bytes(b, flags), e_bytes = (uint32_t)events_bytes(b, flags);
@@ -1562,6 +1809,8 @@ int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_c
     return ASTRO_OK;
 }
 
+static void fresh_free(AstroBatch* b);
+
 int astro_batch_destroy(AstroBatch* b) {
     if (!b) return ASTRO_OK;
     cudaSetDevice(b->device);
@@ -1576,6 +1825,7 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaFree(b->d_pol);
     cudaFree(b->d_src);
     cudaFree(b->d_single);
+    fresh_free(b);
     for (int i = 0; i < kSingleGraphs; i++)
         if (b->single_graph[i].exec) cudaGraphExecDestroy(b->single_graph[i].exec);
     if (b->single_stream) { cudaStreamDestroy(b->single_stream); cudaEventDestroy(b->single_event); }
@@ -1697,6 +1947,7 @@ int astro_tick_host(AstroBatch* b, const uint8_t* actions_host, float* reward_ho
     const int n_tiles = b->n_games / ASTRO_TILE;
     int slices = slices_env > 0 ? slices_env : (n_tiles >= 16384 ? 2 : 1);
     if (slices > kMaxSlices) slices = kMaxSlices;
+    if (b->fresh) slices = 1;      // (the refill that a launch may trigger must not run beside other slices' kernels)
     if (slices > 1 && actions_host && events_host && !reward_host && !done_host && b->precision == 32 &&
         !(flags & ASTRO_TICK_GENERIC_KERNEL) && n_tiles >= slices) {
         if (!b->slice_ready) {
@@ -2237,6 +2488,126 @@ int astro_step_single_host(AstroBatch* b, const AstroSingleGame* in_host, AstroS
     CUDA_TRY(cudaStreamSynchronize(b->single_stream));
     b->cur = 1;          // the lists are where the tick wrote them
     b->launches += 3;
+    return ASTRO_OK;
+}
+
+static void fresh_free(AstroBatch* b) {
+    FreshState* fs = b->fresh;
+    if (!fs) return;
+    cudaFree(fs->f.ring); cudaFree(fs->f.tile_used); cudaFree(fs->f.tasks); cudaFree(fs->f.cursor);
+    cudaFree(const_cast<uint32_t*>(fs->f.seeds)); cudaFree(fs->game_pos);
+    cudaFreeHost(fs->h_seeds); cudaFreeHost(fs->h_cursor);
+    for (int i = 0; i < kFreshLead; i++) if (fs->done[i]) cudaEventDestroy(fs->done[i]);
+    delete fs;
+    b->fresh = nullptr;
+}
+
+int astro_fresh_games_enable(AstroBatch* b, const AstroCreateConfig* cc, uint32_t config_seed, int64_t skip, int32_t quota, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!cc || cc->max_planets < 1 || cc->max_planets > ASTRO_MAX_PLANETS) return fail(ASTRO_E_INVALID, "bad create config");
+    if (b->precision != 32) return fail(ASTRO_E_INVALID, "fresh-game mode needs the float32 build");
+    if (quota < 1 || quota > 1024 || skip < 0) return fail(ASTRO_E_INVALID, "quota must be 1..1024, skip >= 0");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    fresh_free(b);
+    FreshState* fs = new (std::nothrow) FreshState();
+    if (!fs) return fail(ASTRO_E_NOMEM, "out of host memory");
+    memset(fs, 0, sizeof(*fs));
+    b->fresh = fs;
+    const int n_tiles = b->n_games / ASTRO_TILE;
+    fs->capacity = (int64_t)n_tiles * quota;
+    fs->f.n_tiles = n_tiles; fs->f.quota = quota; fs->f.n_games = b->n_games;
+    // seed ring: holds what the host may be ahead by (kFreshLead + 1 refills, or the initial fill of every game + every record), twice
+    unsigned long long need = 2ull * (unsigned long long)(kFreshLead + 2) * (unsigned long long)fs->capacity;
+    const unsigned long long first = 2ull * ((unsigned long long)b->n_games + (unsigned long long)fs->capacity);
+    if (need < first) need = first;
+    unsigned long long ring = 1024;
+    while (ring < need) ring <<= 1;
+    if (ring > (1ull << 31)) { fresh_free(b); return fail(ASTRO_E_INVALID, "batch too large for the seed ring"); }
+    fs->f.seed_mask = (uint32_t)(ring - 1);
+    fs->cq.inner = cc->inner_ship_position; fs->cq.outer = cc->outer_ship_position; fs->cq.orbit = cc->planet_orbit;
+    fs->cq.gravity = b->cfg.gravity; fs->cq.planet_mass = b->cfg.planet_mass;
+    fs->cq.max_planets = cc->max_planets; fs->cq.solo = b->cfg.solo; fs->cq.m = 0; fs->cq.pad = 0;
+    cudaError_t e = cudaMalloc(&fs->f.ring, (size_t)fs->capacity * 128);
+    if (e == cudaSuccess) e = cudaMalloc(&fs->f.tile_used, sizeof(uint32_t) * (size_t)n_tiles);
+    if (e == cudaSuccess) e = cudaMalloc(&fs->f.tasks, sizeof(uint32_t) * (size_t)fs->capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&fs->f.cursor, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(const_cast<uint32_t**>(&fs->f.seeds), sizeof(uint32_t) * (size_t)ring);
+    if (e == cudaSuccess) e = cudaMalloc(&fs->game_pos, sizeof(uint32_t) * (size_t)b->n_games);
+    if (e == cudaSuccess) e = cudaMallocHost(&fs->h_seeds, sizeof(uint32_t) * (size_t)ring);
+    if (e == cudaSuccess) e = cudaMallocHost(&fs->h_cursor, 4 * sizeof(unsigned long long));
+    for (int i = 0; i < kFreshLead && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&fs->done[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { fresh_free(b); return fail(ASTRO_E_CUDA, "fresh-game buffers: %s", cudaGetErrorString(e)); }
+    fs->mt.seed(config_seed);
+    for (int64_t i = 0; i < skip; i++) fs->mt.next();
+    // the stream positions count from `skip`: position p is generate_configs draw number p
+    fs->generated = (unsigned long long)skip;
+    const unsigned long long start[4] = {(unsigned long long)skip, 0ull, 0ull, 0ull};
+    memcpy(fs->h_cursor, start, sizeof(start));
+    CUDA_TRY(cudaMemcpyAsync(fs->f.cursor, fs->h_cursor, sizeof(start), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(fs->game_pos, 0xff, sizeof(uint32_t) * (size_t)b->n_games, st));
+    // every record is "used": the first refill creates the whole ring
+    std::vector<uint32_t> full((size_t)n_tiles, (uint32_t)quota);
+    CUDA_TRY(cudaMemcpyAsync(fs->f.tile_used, full.data(), sizeof(uint32_t) * (size_t)n_tiles, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // (`full` is pageable and leaves scope)
+    return fresh_refill(b, st);
+}
+
+int astro_fresh_games_reset_all(AstroBatch* b, void* stream) {
+    if (int r = check(b, true)) return r;
+    FreshState* fs = b->fresh;
+    if (!fs) return fail(ASTRO_E_STATE, "astro_fresh_games_enable has not been called");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // the device's cursor is read exactly (a rare call): the next n_games positions start there
+    CUDA_TRY(cudaStreamSynchronize(st));
+    unsigned long long cur[2];
+    CUDA_TRY(cudaMemcpy(cur, fs->f.cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+    fs->h_cursor[0] = cur[0]; fs->h_cursor[1] = cur[1];
+    if (int r = fresh_upload_seeds(b, cur[0] + (unsigned long long)b->n_games + (unsigned long long)fs->capacity, st)) return r;
+    const AstroBuffers& u = b->bufs;
+    const int grid = (b->n_games + 63) / 64;
+    if (b->S == 2) fresh_fill_kernel<2><<<grid, 64, 0, st>>>(fs->f, fs->cq, (float4*)u.ships, (float*)u.ship_b, (float4*)u.planets, u.meta, u.episode, fs->game_pos);
+    else fresh_fill_kernel<1><<<grid, 64, 0, st>>>(fs->f, fs->cq, (float4*)u.ships, (float*)u.ship_b, (float4*)u.planets, u.meta, u.episode, fs->game_pos);
+    fresh_fill_commit_kernel<<<1, 1, 0, st>>>(fs->f);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(fs->h_cursor, fs->f.cursor, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->launches += 2;
+    b->step = 0;
+    return ASTRO_OK;
+}
+
+int astro_fresh_games_refill(AstroBatch* b, void* stream) {
+    if (int r = check(b, true)) return r;
+    if (!b->fresh) return fail(ASTRO_E_STATE, "astro_fresh_games_enable has not been called");
+    CUDA_TRY(cudaSetDevice(b->device));
+    return fresh_refill(b, (cudaStream_t)stream);
+}
+
+int astro_fresh_games_positions(AstroBatch* b, uint32_t* positions_dev, uint32_t* tile_used_dev, int64_t* cursor_host, void* stream) {
+    if (int r = check(b, true)) return r;
+    FreshState* fs = b->fresh;
+    if (!fs) return fail(ASTRO_E_STATE, "astro_fresh_games_enable has not been called");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (positions_dev) CUDA_TRY(cudaMemcpyAsync(positions_dev, fs->game_pos, sizeof(uint32_t) * (size_t)b->n_games, cudaMemcpyDeviceToDevice, st));
+    if (tile_used_dev) CUDA_TRY(cudaMemcpyAsync(tile_used_dev, fs->f.tile_used, sizeof(uint32_t) * (size_t)fs->f.n_tiles, cudaMemcpyDeviceToDevice, st));
+    if (cursor_host) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        unsigned long long cur = 0;
+        CUDA_TRY(cudaMemcpy(&cur, fs->f.cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+        *cursor_host = (int64_t)cur;
+    }
+    return ASTRO_OK;
+}
+
+int astro_config_seeds(uint32_t config_seed, int64_t skip, int64_t count, uint32_t* out_host) {
+    if (!out_host || skip < 0 || count < 0) return fail(ASTRO_E_INVALID, "bad arguments");
+    HostMt19937 mt;
+    mt.seed(config_seed);
+    for (int64_t i = 0; i < skip; i++) mt.next();
+    for (int64_t i = 0; i < count; i++) out_host[i] = mt.next() & 0x3fffffffu;
     return ASTRO_OK;
 }
 

@@ -53,6 +53,7 @@ struct TileScratch {               // per warp
     int32_t shift[32];             // [cid] new list: item j of the compacted list moves to j + shift (kDrop: game over)
     uint16_t gstart[34];           // [cid] first survivor of the game in the compacted list; [n] = survivors of the tile
     uint8_t ref[kStageWindows * 32];   // compacted item -> cid
+    uint32_t used;                     // fresh-game mode: records of the tile's ring consumed since the last refill
 };
 constexpr int kDrop = 0x40000000;
 
@@ -397,7 +398,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // What the END of the tick will need from memory is requested now, off the critical path: the
     // fire-schedule word of this game's tick and, with auto-reset, the planet count of the pool
     // entry that would replace the game (the pick is keyed on the stream step, not on state).
-    const bool auto_reset = (p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0;
+    const bool auto_reset = (p.flags & ASTRO_TICK_AUTO_RESET) && (p.pool_size > 0 || p.ring != nullptr);
     const bool active = !ASTRO_META_FINISHED(meta);
     const int nb = active ? (int)ASTRO_META_NB(meta) : 0;
     const int np = active ? (int)ASTRO_META_NP(meta) : 0;
@@ -566,7 +567,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // A game that ends here and now (ship hit a planet / the other ship, or timeout) will be re-created
     // from its pool record at the end: pull the record towards L2 while the bullet loop runs.
     // (the pick is a few dozen integer instructions: only the rare lanes that need it work it out)
-    if (auto_reset && active && (hits || tick >= (uint32_t)p.timeout_tick)) {
+    if (auto_reset && !p.ring && active && (hits || tick >= (uint32_t)p.timeout_tick)) {
         const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pool_rec + (size_t)k * 8));
     }
@@ -710,46 +711,67 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             m_out = m;
         }
         if (__builtin_expect(bad_ctl, 0)) ev |= ASTRO_EV_BAD_CONTROL;
-        if (ev & ASTRO_EV_DONE_MASK) {
-            if (auto_reset) {
-                // Re-create the game from pool entry pool_k (core.create, core.py:86-135, evaluated
-                // on the host): bullets cleared, tick 0; the per-slot episode counter is bumped with
-                // a fire-and-forget RED.
-                atomicAdd(&p.episode[g], 1u);
-                const uint32_t pool_k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size);
-                const float4* const pool_rec = p.pool_rec + (size_t)pool_k * 8;
-                float4 r[8];   // the 128-byte record: ships (5 floats each), planet count (word 10), planets (floats 16..31)
-#pragma unroll
-                for (int j = 0; j < 8; j++) r[j] = __ldg(&pool_rec[j]);
-                const int np_new = __float_as_int(r[2].z);
-                next.shv[0] = r[0];
-                next.sb[0] = r[1].x;
-                if (last) {
-                    ships[0] = r[0];
-                    ship_b[0] = r[1].x;
-                }
-                if (S == 2) {
-                    next.shv[1] = make_float4(r[1].y, r[1].z, r[1].w, r[2].x);
-                    next.sb[1] = r[2].y;
-                    if (last) {
-                        ships[32] = next.shv[1];
-                        ship_b[32] = next.sb[1];
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
-                    if (j < np_new) planets[j * 32] = r[4 + j];
-                next.meta = ASTRO_META_PACK(0, np_new, 0, 0);
-                if (last) p.meta[g] = next.meta;
-            } else {
-                // Frozen from here on: the later ticks of this launch skip the game without touching its rows,
-                // so the finished word goes to memory now, whichever tick of the launch this is (the ships were
-                // stored by the physics above: without auto-reset every tick stores them) — identical to
-                // separate astro_tick calls.
-                next.meta = ASTRO_META_PACK(0, np, 1, tick);
-                p.meta[g] = next.meta;
+    }
+    // ---- a game that ended is re-created in the same launch (auto-reset) or frozen
+    const bool ended = (ev & ASTRO_EV_DONE_MASK) != 0;       // (a skipped game: no)
+    if (auto_reset) {
+        // Where the new game comes from (core.create, core.py:86-135): a 128-byte record — ships (5 floats each), planet
+        // count (word 10), planets (floats 16..31) — of the reset pool, picked by a hash of (game, stream step); or, in
+        // fresh-game mode, the tile's next unused record of its ring (words 11 / 12: position in the generate_configs
+        // stream, seed): a warp-local count, so every record — every stream position — is consumed exactly once.  A game
+        // that finds the tile's ring empty waits, frozen (tick field = ASTRO_MAX_TICKS), and asks again every tick.
+        const float4* rec = nullptr;
+        if (p.ring) {
+            const bool want = ended | (!active && ASTRO_META_TICK(meta) == (uint32_t)ASTRO_MAX_TICKS);
+            const unsigned wants = __ballot_sync(full, want);
+            if (wants) {
+                const unsigned used = t.used;
+                const unsigned idx = used + __popc(wants & lt_mask);
+                __syncwarp();
+                if (lane == 0) t.used = min(used + (unsigned)__popc(wants), (unsigned)p.quota);
+                if (want && idx < (unsigned)p.quota) rec = p.ring + ((size_t)tile_index * (unsigned)p.quota + idx) * 8;
             }
+        } else if (ended) {
+            rec = p.pool_rec + (size_t)pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size) * 8;
         }
+        if (ended) atomicAdd(&p.episode[g], 1u);      // the per-slot episode counter: a fire-and-forget RED
+        if (rec) {
+            float4 r[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __ldg(&rec[j]);
+            const int np_new = __float_as_int(r[2].z);
+            next.shv[0] = r[0];
+            next.sb[0] = r[1].x;
+            if (last) {
+                ships[0] = r[0];
+                ship_b[0] = r[1].x;
+            }
+            if (S == 2) {
+                next.shv[1] = make_float4(r[1].y, r[1].z, r[1].w, r[2].x);
+                next.sb[1] = r[2].y;
+                if (last) {
+                    ships[32] = next.shv[1];
+                    ship_b[32] = next.sb[1];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < ASTRO_MAX_PLANETS; j++)
+                if (j < np_new) planets[j * 32] = r[4 + j];
+            next.meta = ASTRO_META_PACK(0, np_new, 0, 0);
+            if (last) p.meta[g] = next.meta;
+            if (p.game_pos) p.game_pos[g] = __float_as_uint(r[2].w);
+        } else if (ended) {
+            ev |= ASTRO_EV_AWAIT;
+            next.meta = ASTRO_META_PACK(0, np, 1, ASTRO_MAX_TICKS);
+            p.meta[g] = next.meta;
+        }
+    } else if (ended) {
+        // Frozen from here on: the later ticks of this launch skip the game without touching its rows,
+        // so the finished word goes to memory now, whichever tick of the launch this is (the ships were
+        // stored by the physics above: without auto-reset every tick stores them) — identical to
+        // separate astro_tick calls.
+        next.meta = ASTRO_META_PACK(0, np, 1, tick);
+        p.meta[g] = next.meta;
     }
 
     // ================= 6. the new list: survivors and newborn, dense, into the other buffer =========
@@ -850,6 +872,11 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     // (MANY = false: the one-tick launch, without the loop around it — the loop form costs a single tick 6 %)
     TileIn in, next;
     unsigned stat_acc = 0;
+    TileScratch& scratch = s_tiles[kTickWarps == 1 ? 0 : (threadIdx.x >> 5)];
+    if (p.ring) {   // fresh-game mode: how many of the tile's pre-created games have been used since the last refill
+        if (lane == 0) scratch.used = p.tile_used[tile];
+        __syncwarp();
+    }
     load_tile_in<S>(p, tick_var<S>(p, 0u), tile, lane, in);
 #pragma unroll 1
     for (unsigned k = 0; k < (MANY ? (unsigned)p.n_fused : 1u); k++) {
@@ -863,7 +890,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         }
         if (MANY) in.fire_word = p.fire_bits[min(ASTRO_META_TICK(in.meta), (uint32_t)p.n_sched_ticks - 1u) >> 5];
         // (one-warp CTAs: the scratch is s_tiles[0], every shared address a compile-time constant — no base register)
-        tick_tile<S, STATS, MANY>(p, v, s_tiles[kTickWarps == 1 ? 0 : (threadIdx.x >> 5)], lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
+        tick_tile<S, STATS, MANY>(p, v, scratch, lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
         if (MANY) {
             // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
             // well), so it starts its prefix sums and list requests at once; only the planet rows are loaded.  The
@@ -874,5 +901,9 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
             if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }
             __syncwarp();
         }
+    }
+    if (p.ring) {
+        __syncwarp();
+        if (lane == 0) p.tile_used[tile] = scratch.used;
     }
 }

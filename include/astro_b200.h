@@ -71,6 +71,8 @@ extern "C" {
 #define ASTRO_EV_SKIPPED 32  /* game was already finished; nothing done */
 #define ASTRO_EV_BAD_CONTROL 64 /* a control code above 5 was given (out of the reference's contract, core.py:220-227):
                                    the ship was flown with control 2 (no thrust, no turn) and the tick flagged */
+#define ASTRO_EV_AWAIT 128 /* fresh-game mode: the game ended but its tile had no pre-created game left: it waits, frozen,
+                              and is re-created by the first tick after the next refill (counted in astro_stats) */
 #define ASTRO_EV_DONE_MASK 7
 
 /* astro_tick flags */
@@ -138,12 +140,13 @@ typedef struct AstroCreateConfig {
     int32_t reserved;
 } AstroCreateConfig;
 
-#define ASTRO_N_STATS 13
+#define ASTRO_N_STATS 14
 /* astro_stats counters (int64 each), summed over every astro_tick since the last clear:
  *  0 episodes  1 wins0  2 wins1  3 both_lost (or solo crash)  4 timeouts  5 env_steps
  *  6 bullets_spawned  7 overflow  8 planets_live (sum of np over env-steps)
  *  9 bullets_in (sum of nb read)  10 bullets_out (sum of nb written)  11 skipped
- *  12 bad_controls (env-steps that saw a control code above 5)                          */
+ *  12 bad_controls (env-steps that saw a control code above 5)
+ *  13 awaiting (fresh-game mode: games that ended with their tile's ring of pre-created games empty)  */
 
 typedef struct AstroBatch AstroBatch;
 
@@ -246,6 +249,28 @@ int astro_observe_shared(AstroBatch* b, float* obs, int32_t n_rows, void* stream
  * that re-created games never repeat. */
 int astro_create_games(AstroBatch* b, const AstroCreateConfig* cc, const uint32_t* seeds, int32_t m, void* ships,
                        void* planets, int32_t* n_planets, void* stream);
+
+/* Fresh games without a pool: core.generate_configs + core.create (core.py:77-135) for EVERY re-creation, the way
+ * core.play / rl.train start every episode from the next config of the stream (rl.py:350,374).  float32 build.
+ *   _enable     every tile of 32 games gets a ring of `quota` pre-created games; ASTRO_TICK_AUTO_RESET then re-creates a game
+ *               that ends from its tile's next unused record (a warp-local count: no atomics, no dependent address), and
+ *               between launches the used records are re-created from the NEXT positions of the stream — positions handed
+ *               out by a prefix sum in tile order (reproducible), seeds drawn on the host exactly like
+ *               numpy.random.RandomState(config_seed).randint(2**30) and uploaded ahead of the device.  Every position of
+ *               the stream (from `skip`) is consumed exactly once: no initial state repeats unless the stream itself does.
+ *               A tile that uses its whole quota between two refills (quota 48 covers 64-tick launches of random play)
+ *               leaves the game frozen (ASTRO_EV_AWAIT) until the next refill; nothing is ever re-used.
+ *   _reset_all  (re)starts every game of the batch from the next n_games positions (synchronises the stream).
+ *   _refill     an explicit refill (astro_tick / astro_tick_many refill by themselves, about every quota / 2 ticks).
+ *   _positions  positions_dev u32 [n_games] <- stream position of each game's current episode; tile_used_dev u32 [n_tiles]
+ *               <- records used since the last refill; *cursor_host <- positions handed out so far (synchronises). */
+int astro_fresh_games_enable(AstroBatch* b, const AstroCreateConfig* cc, uint32_t config_seed, int64_t skip, int32_t quota, void* stream);
+int astro_fresh_games_reset_all(AstroBatch* b, void* stream);
+int astro_fresh_games_refill(AstroBatch* b, void* stream);
+int astro_fresh_games_positions(AstroBatch* b, uint32_t* positions_dev, uint32_t* tile_used_dev, int64_t* cursor_host, void* stream);
+/* The seeds of core.generate_configs (core.py:77-83) on the host: RandomState(config_seed).randint(2**30), draws number
+ * skip .. skip + count - 1 (the library's own MT19937; pinned against numpy in the tests). */
+int astro_config_seeds(uint32_t config_seed, int64_t skip, int64_t count, uint32_t* out_host);
 
 /* script.ScriptBot.__call__ (script.py:13-91: _danger, _fly_to) for every ship of every game, each
  * seeing the game from its own perspective (core.roll_ships, core.py:306-327):

@@ -1497,3 +1497,114 @@ def test_packed_controls_and_event_planes_equal_the_byte_forms(monkeypatch):
             for key in ('ships', 'planets', 'bullets', 'n_bullets', 'n_planets', 'tick', 'episode'):
                 assert (arr[key] == want[0][key]).all(), (prec, name, key)
         assert want[1]['episodes'] > 300 and (want_ev == 4).sum() == 0 and ((want_ev & 3) != 0).sum() == want[1]['episodes']
+
+
+# ------------------------------------------------------------------ fresh games without a pool
+
+def _created_rows(cfg, seeds):
+    """core.create for every seed as float32-rounded game-major rows (what a float32 batch holds after a re-creation)."""
+    S = 1 if cfg.solo else 2
+    ships = np.zeros((len(seeds), S, 5))
+    planets = np.zeros((len(seeds), 4, 4))
+    npl = np.zeros(len(seeds), dtype=np.int64)
+    for i, sd in enumerate(seeds):
+        s = core.create(cfg._replace(seed=int(sd)))
+        ships[i, :, 0:2], ships[i, :, 2:4], ships[i, :, 4] = s.ships.x, s.ships.dx, s.ships.b
+        p = s.planets.x.shape[0]
+        planets[i, :p, 0:2], planets[i, :p, 2:4] = s.planets.x, s.planets.dx
+        npl[i] = p
+    return ships.astype(np.float32).astype(np.float64), planets.astype(np.float32).astype(np.float64), npl
+
+
+@pytest.mark.parametrize('N,quota,skip', [(2048, 8, 0), (300, 1, 1000)])
+def test_fresh_games_every_recreation_takes_the_next_unused_config(N, quota, skip):
+    """Fresh-game mode, one launch per tick, teacher-forced against the oracle: every game that ends is re-created from a
+    position of the generate_configs stream that no game has had before, the new state equals core.create(seed at that
+    position) bit for bit (float32-rounded), and the books balance: positions handed out = ring + initial fill + records
+    re-created.  A small quota makes tiles run dry between refills: those games wait (ASTRO_EV_AWAIT) and come back."""
+    cfg, K, S = core.DEFAULT_CONFIG, 32, 2
+    games = _games(cfg, N, bullet_cap=K, precision=32, seed=3)
+    games.enable_fresh_games(quota=quota, skip=skip)
+    games.reset_all()
+    n_tiles = games.n_tiles
+    seeds_of = lambda pos: rng.config_seeds(cfg.seed, int(pos.max()) + 1 - skip, skip)[pos - skip]
+    pos, used, cursor = games.fresh_positions()
+    assert cursor == skip + n_tiles * quota + games.n_pad and (used == 0).all()
+    assert (np.sort(pos) == skip + n_tiles * quota + np.arange(N)).all()
+    arr = games.get_arrays()
+    ships, planets, npl = _created_rows(cfg, seeds_of(pos))
+    assert (arr['ships'] == ships).all() and (arr['n_planets'] == npl).all() and (arr['planets'] == planets).all()
+    seen = set(pos.tolist())
+    ids = np.arange(N)
+    T, n_recreated, n_await = 260, 0, 0
+    for k in range(T):
+        ob, alive = H.oracle_batch_from(arr, S, K)
+        ob.reload[:] = games.schedule.reload[np.minimum(arr['tick'], games.schedule.n_ticks - 1)]
+        ob.t[:] = games.schedule.t[np.minimum(arr['tick'], games.schedule.n_ticks - 1)]
+        o2, rew, done, ev = ao.step_batch(cfg, ob, rng.actions(3, ids, k, S), alive)
+        _, d_gpu, e_gpu = games.step(None, auto_reset=True)
+        e_gpu = e_gpu.cpu().numpy()
+        waiting = arr['finished']                                   # games that were waiting for a record before this tick
+        assert ((e_gpu & 15) == (ev & 15))[~waiting].all(), k
+        new = games.get_arrays()
+        new_pos, used, cursor = games.fresh_positions()
+        ended = (done != 0) & ~waiting
+        took = new_pos != pos                                          # games that got a fresh record this tick
+        await_now = (e_gpu & nat.EV_AWAIT) != 0
+        assert (took | await_now)[ended].all() and not (took & ~(ended | waiting)).any(), k
+        assert (new['finished'] == ((ended | waiting) & ~took)).all(), k
+        if took.any():
+            fresh = new_pos[took]
+            assert len(set(fresh.tolist())) == fresh.size and not (set(fresh.tolist()) & seen), k
+            seen |= set(fresh.tolist())
+            ships, planets, npl = _created_rows(cfg, seeds_of(fresh))
+            assert (new['ships'][took] == ships).all() and (new['planets'][took] == planets).all(), k
+            assert (new['n_planets'][took] == npl).all() and (new['n_bullets'][took] == 0).all() and (new['tick'][took] == 0).all()
+        live = ~(ended | waiting)
+        assert (new['n_bullets'][live] == o2.nb[live]).all() and _close(new['ships'][live], o2.ships[live]).all(), k
+        n_recreated += int(took.sum())
+        n_await += int(await_now.sum())
+        arr, pos = new, new_pos
+    st = games.stats()
+    assert st['awaiting'] == n_await and st['episodes'] == n_recreated + int(arr['finished'].sum())
+    # the books: every position handed out is either in a ring (unused), or was taken by exactly one game
+    assert cursor - skip == n_tiles * quota + games.n_pad + n_recreated - int(used.sum())
+    assert len(seen) == N + n_recreated and max(seen) < cursor
+    if quota == 1:
+        assert n_await > 0          # tiles did run dry — and every waiting game came back or is still waiting, never re-used
+    assert n_recreated > N // 2
+
+
+def test_fresh_games_fused_launches_1M_no_repeats():
+    """BASELINE-size check (1,048,576 games x 600 ticks, 20 ticks per launch, quota 48): no two live games ever share a
+    stream position, positions only grow, and positions handed out = ring + initial fill + games re-created (+ records
+    re-created but not yet used) — every re-creation consumed a config of the generate_configs stream exactly once."""
+    import torch
+    cfg, N, quota = core.DEFAULT_CONFIG, 1 << 20, 48
+    games = _games(cfg, N, bullet_cap=32, precision=32, seed=0)
+    games.enable_fresh_games(quota=quota)
+    games.reset_all()
+    pos0, _, cur0 = games.fresh_positions()
+    prev = pos0
+    seen_max = int(pos0.max())
+    for launch in range(30):
+        games.step_many(20, None, auto_reset=True)
+        pos, used, cursor = games.fresh_positions()
+        assert np.unique(pos).size == N                                   # no two live games share a start state
+        changed = pos != prev
+        assert (pos[changed] > prev[changed]).all()                       # a game only ever moves on to later positions
+        prev = pos
+    st = games.stats()
+    assert st['awaiting'] == 0 and st['env_steps'] == N * 600
+    # positions handed out: the ring, the initial fill, and one per record re-created; records re-created = records used
+    # up to the last refill = episodes - records used since
+    assert cursor == games.n_tiles * quota + N + st['episodes'] - int(used.sum())
+    assert st['episodes'] > 5 * N
+    # spot-check: the current state of games still on their tick 0 equals core.create of their position's seed
+    arr = games.get_arrays(np.arange(0, N, 4099))
+    p_s = pos[::4099]
+    fresh = arr['tick'] == 0
+    if fresh.any():
+        seeds = rng.config_seeds(cfg.seed, int(p_s.max()) + 1, 0)[p_s[fresh]]
+        ships, planets, npl = _created_rows(cfg, seeds)
+        assert (arr['ships'][fresh] == ships).all() and (arr['n_planets'][fresh] == npl).all()

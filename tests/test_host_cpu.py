@@ -264,3 +264,17 @@ def test_value_network_matches_reference_outputs():
                 n_solo += 1
     assert n_duel >= 10 and n_solo >= 1
     assert np.abs(np.load(os.path.join(H.G, 'network.npz'))['g0_q0']).max() > 0.05      # (the outputs are not all ~0)
+
+
+def test_library_seed_stream_equals_generate_configs():
+    """astro_config_seeds (the host MT19937 that feeds fresh-game mode) against numpy's RandomState stream that
+    core.generate_configs draws from (core.py:77-83), and against the reference's first seeds."""
+    L = nat.lib()
+    for seed, skip, n in ((42, 0, 3000), (7, 12345, 5000), (2 ** 31 + 5, 3, 10), (0, 623, 1300)):
+        out = np.zeros(n, dtype=np.uint32)
+        assert L.astro_config_seeds(seed & 0xFFFFFFFF, skip, n, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert (out == rng.config_seeds(seed, n, skip)).all(), (seed, skip)
+    out = np.zeros(4, dtype=np.uint32)
+    L.astro_config_seeds(42, 0, 4, out.ctypes.data_as(ctypes.c_void_p))
+    assert out.tolist() == [534895718, 199900595, 862061404, 787846414]
+    assert [c.seed for c in it.islice(core.generate_configs(core.DEFAULT_CONFIG), 4)] == out.tolist()
