@@ -17,7 +17,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <atomic>
+#include <chrono>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace astro;
@@ -915,7 +918,7 @@ __global__ void __launch_bounds__(64) create_kernel(const uint32_t* __restrict__
 // counter, no atomics, no dependent address — and between launches the records that were used are re-created from the
 // NEXT positions of the seed stream (host MT19937, uploaded ahead; positions handed out by a prefix sum in tile order,
 // so a rollout is reproducible): every re-creation consumes a stream position exactly once.
-//   refill_plan_kernel    one CTA: prefix sum of the tiles' used counts -> task list (record index), stream cursor
+//   refill_scan / refill_tasks   prefix sum of the tiles' used counts -> task list (record index), stream cursor
 //   refill_create_kernel  thread = task: create_game(seed at cursor + task) -> record
 //   fresh_fill_kernel     thread = game: (re)start every game of the batch from consecutive stream positions
 // ------------------------------------------------------------------------------------------
@@ -950,29 +953,67 @@ __device__ __forceinline__ void write_record(float4* rec, const CreatedGame& o, 
     for (int i = 0; i < 8; i++) rec[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
-__global__ void __launch_bounds__(1024) refill_plan_kernel(const __grid_constant__ FreshParams f) {
-    __shared__ unsigned s_sum[1024];
-    const int tid = threadIdx.x;
-    const int per = (f.n_tiles + 1023) / 1024;
-    const int t0 = tid * per, t1 = min(f.n_tiles, t0 + per);
-    unsigned mine = 0;
-    for (int t = t0; t < t1; t++) mine += min(f.tile_used[t], (uint32_t)f.quota);
-    s_sum[tid] = mine;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {               // inclusive scan
-        const unsigned v = tid >= d ? s_sum[tid - d] : 0u;
+// Plan, in two small kernels (deterministic: task numbers follow the tile order).  Chunks of 32 tiles:
+//   refill_scan_kernel   one CTA, thread = chunk: sums the chunk's used counts (one 128-byte run), block-wide exclusive scan
+//                        -> chunk_base[chunk]; the total goes to cursor[2]
+//   refill_tasks_kernel  warp = chunk, lane = tile: exclusive scan inside the chunk, the tile's used records are listed, its
+//                        count cleared
+__global__ void __launch_bounds__(1024) refill_scan_kernel(const __grid_constant__ FreshParams f, uint32_t* __restrict__ chunk_base) {
+    __shared__ unsigned s_warp[32];
+    const int n_chunks = (f.n_tiles + 31) / 32;
+    unsigned running = 0;                                   // (batches beyond 32,768 tiles: several rounds of 1,024 chunks)
+    for (int c0 = 0; c0 < n_chunks; c0 += 1024) {
+        const int c = c0 + threadIdx.x;
+        unsigned mine = 0;
+        if (c < n_chunks) {
+            const int t0 = c * 32, t1 = min(f.n_tiles, t0 + 32);
+            if (t1 - t0 == 32) {                                  // a whole chunk: one 128-byte run, eight independent loads
+                const uint4* u4 = reinterpret_cast<const uint4*>(f.tile_used + t0);
+                uint4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = u4[k];
+                const uint32_t q = (uint32_t)f.quota;
+#pragma unroll
+                for (int k = 0; k < 8; k++) mine += min(v[k].x, q) + min(v[k].y, q) + min(v[k].z, q) + min(v[k].w, q);
+            } else {
+                for (int t = t0; t < t1; t++) mine += min(f.tile_used[t], (uint32_t)f.quota);
+            }
+        }
+        unsigned incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)(threadIdx.x & 31) >= d) incl += v;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
         __syncthreads();
-        s_sum[tid] += v;
+        unsigned wsum = threadIdx.x < 32 ? s_warp[threadIdx.x] : 0u, wincl = wsum;
+        if (threadIdx.x < 32) {
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, wincl, d);
+                if ((int)threadIdx.x >= d) wincl += v;
+            }
+            s_warp[threadIdx.x] = wincl - wsum;             // exclusive warp offsets
+        }
+        __syncthreads();
+        const unsigned base = running + s_warp[threadIdx.x >> 5] + incl - mine;
+        if (c < n_chunks) chunk_base[c] = base;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_warp[0] = base + mine;   // total so far
+        __syncthreads();
+        running = s_warp[0];
         __syncthreads();
     }
-    unsigned at = s_sum[tid] - mine;
-    for (int t = t0; t < t1; t++) {
-        const unsigned u = min(f.tile_used[t], (uint32_t)f.quota);
-        for (unsigned j = 0; j < u; j++) f.tasks[at + j] = (uint32_t)t * (uint32_t)f.quota + j;
-        at += u;
-        f.tile_used[t] = 0u;
-    }
-    if (tid == 1023) f.cursor[2] = s_sum[1023];
+    if (threadIdx.x == 0) f.cursor[2] = running;
+}
+__global__ void __launch_bounds__(256) refill_tasks_kernel(const __grid_constant__ FreshParams f, const uint32_t* __restrict__ chunk_base) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;      // tile (whole warps run: the chunk scan needs every lane)
+    const int lane = threadIdx.x & 31;
+    const unsigned u = t < f.n_tiles ? min(f.tile_used[t], (uint32_t)f.quota) : 0u;
+    unsigned at = chunk_base[min(t >> 5, (f.n_tiles + 31) / 32 - 1)] + warp_exclusive_sum(u, lane);
+    for (unsigned j = 0; j < u; j++) f.tasks[at + j] = (uint32_t)t * (uint32_t)f.quota + j;
+    if (u) f.tile_used[t] = 0u;
 }
 
 template <int S>
@@ -1428,12 +1469,16 @@ struct HostMt19937 {
         for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
         idx = 624;
     }
+    static uint32_t twist(uint32_t a, uint32_t b, uint32_t far) {
+        const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+        return far ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+    }
     uint32_t next() {
-        if (idx >= 624) {
-            for (int k = 0; k < 624; k++) {
-                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
-                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
+        if (idx >= 624) {      // the three runs of the reference generator: no modulo in the loops
+            int k = 0;
+            for (; k < 624 - 397; k++) mt[k] = twist(mt[k], mt[k + 1], mt[k + 397]);
+            for (; k < 623; k++) mt[k] = twist(mt[k], mt[k + 1], mt[k + 397 - 624]);
+            mt[623] = twist(mt[623], mt[0], mt[396]);
             idx = 0;
         }
         uint32_t v = mt[idx++];
@@ -1450,12 +1495,21 @@ struct FreshState {
     FreshParams f;                // device pointers (ring, tile_used, tasks, cursor, seeds)
     CreateParams cq;
     uint32_t* game_pos;           // device [n_games]
+    uint32_t* chunk_base;         // device [n_tiles / 32]: first task of each chunk of 32 tiles (refill plan)
     uint32_t* h_seeds;            // pinned mirror of the seed ring
     unsigned long long* h_cursor; // pinned: [0] stream positions handed out, [1] refills completed (lagging copies)
-    HostMt19937 mt;
-    unsigned long long generated; // stream positions generated (and uploaded) so far
+    HostMt19937 mt;               // (owned by the producer thread once it runs)
+    // A producer thread keeps the pinned mirror topped up so that drawing seeds (a few ns each, ~10 k per tick and million
+    // games) never sits in front of a launch: it draws positions [produced, target) in chunks; the caller raises
+    // `target` one refill ahead and only ever waits when it has overtaken the forecast.
+    std::thread* producer;
+    std::atomic<unsigned long long> produced, target;
+    std::atomic<int> stop;
+    unsigned long long generated; // stream positions uploaded to the device so far
     unsigned long long refills;   // refills enqueued so far
     cudaEvent_t done[kFreshLead]; // refill k's completion = done[k % kFreshLead]
+    cudaStream_t copy;            // seed uploads
+    cudaEvent_t seeds_sent;
     int64_t ticks_since_refill;
     int64_t capacity;             // n_tiles * quota
 };
@@ -1649,14 +1703,28 @@ constexpr double kSinCosRange = 71476.0;   // np_sincos_f32 (astro_device.cuh)
 // Stream positions [generated, upto) are drawn from the host MT19937 into the pinned mirror ring and uploaded
 // (stream-ordered) to the device ring.  A slot is overwritten ring-size positions later: the refill protocol keeps
 // `generated` within kFreshLead + 1 capacities of the device's cursor, and the ring holds 2 (kFreshLead + 2) capacities.
+void fresh_producer_main(FreshState* fs) {
+    for (;;) {
+        const unsigned long long want = fs->target.load(std::memory_order_acquire);
+        unsigned long long have = fs->produced.load(std::memory_order_relaxed);
+        if (fs->stop.load(std::memory_order_acquire)) return;
+        if (have >= want) { std::this_thread::sleep_for(std::chrono::microseconds(50)); continue; }   // (works a refill ahead: no hurry)
+        const unsigned long long n = want - have < 16384ull ? want - have : 16384ull;
+        for (unsigned long long i = 0; i < n; i++) fs->h_seeds[(have + i) & fs->f.seed_mask] = fs->mt.next() & 0x3fffffffu;   // randint(2**30)
+        fs->produced.store(have + n, std::memory_order_release);
+    }
+}
+
 int fresh_upload_seeds(AstroBatch* b, unsigned long long upto, cudaStream_t st) {
     FreshState* fs = b->fresh;
+    if (fs->generated >= upto) return ASTRO_OK;
     const unsigned long long ring = (unsigned long long)fs->f.seed_mask + 1ull;
+    if (fs->target.load(std::memory_order_relaxed) < upto) fs->target.store(upto, std::memory_order_release);
+    while (fs->produced.load(std::memory_order_acquire) < upto) std::this_thread::yield();    // (normally already there)
     while (fs->generated < upto) {
         const unsigned long long at = fs->generated & fs->f.seed_mask;
         unsigned long long n = upto - fs->generated;
         if (n > ring - at) n = ring - at;
-        for (unsigned long long i = 0; i < n; i++) fs->h_seeds[at + i] = fs->mt.next() & 0x3fffffffu;   // randint(2**30)
         CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(fs->f.seeds) + at, fs->h_seeds + at, (size_t)n * sizeof(uint32_t),
                                  cudaMemcpyHostToDevice, st));
         fs->generated += n;
@@ -1672,8 +1740,16 @@ int fresh_refill(AstroBatch* b, cudaStream_t st) {
     const unsigned long long cursor_seen = fs->h_cursor[0], refills_seen = fs->h_cursor[1];
     // every refill not yet seen hands out at most `capacity` positions, and so does this one
     const unsigned long long bound = cursor_seen + (fs->refills - refills_seen + 1ull) * (unsigned long long)fs->capacity;
-    if (int r = fresh_upload_seeds(b, bound, st)) return r;
-    refill_plan_kernel<<<1, 1024, 0, st>>>(fs->f);
+    // The seeds travel on a copy stream of their own, ONE refill ahead of need (what this refill may use was sent during the
+    // previous one), so the copy runs beside the tick launches instead of in front of the refill kernels.
+    CUDA_TRY(cudaStreamWaitEvent(st, fs->seeds_sent, 0));                       // the previous upload (long complete)
+    if (int r = fresh_upload_seeds(b, bound, st)) return r;                     // (only if the device got ahead of the forecast)
+    if (int r = fresh_upload_seeds(b, bound + (unsigned long long)fs->capacity, fs->copy)) return r;
+    CUDA_TRY(cudaEventRecord(fs->seeds_sent, fs->copy));
+    // ... and the producer draws what the NEXT refill will upload while this launch runs
+    fs->target.store(bound + 2ull * (unsigned long long)fs->capacity, std::memory_order_release);
+    refill_scan_kernel<<<1, 1024, 0, st>>>(fs->f, fs->chunk_base);
+    refill_tasks_kernel<<<(fs->f.n_tiles + 255) / 256, 256, 0, st>>>(fs->f, fs->chunk_base);
     const int grid = (int)((fs->capacity + 63) / 64);
     if (b->S == 2) refill_create_kernel<2><<<grid, 64, 0, st>>>(fs->f, fs->cq);
     else refill_create_kernel<1><<<grid, 64, 0, st>>>(fs->f, fs->cq);
@@ -1683,7 +1759,7 @@ int fresh_refill(AstroBatch* b, cudaStream_t st) {
     CUDA_TRY(cudaEventRecord(fs->done[fs->refills % kFreshLead], st));
     fs->refills += 1;
     fs->ticks_since_refill = 0;
-    b->launches += 3;
+    b->launches += 4;
     return ASTRO_OK;
 }
 
@@ -2494,10 +2570,17 @@ int astro_step_single_host(AstroBatch* b, const AstroSingleGame* in_host, AstroS
 static void fresh_free(AstroBatch* b) {
     FreshState* fs = b->fresh;
     if (!fs) return;
+    if (fs->producer) {
+        fs->stop.store(1, std::memory_order_release);
+        fs->producer->join();
+        delete fs->producer;
+    }
     cudaFree(fs->f.ring); cudaFree(fs->f.tile_used); cudaFree(fs->f.tasks); cudaFree(fs->f.cursor);
-    cudaFree(const_cast<uint32_t*>(fs->f.seeds)); cudaFree(fs->game_pos);
+    cudaFree(const_cast<uint32_t*>(fs->f.seeds)); cudaFree(fs->game_pos); cudaFree(fs->chunk_base);
     cudaFreeHost(fs->h_seeds); cudaFreeHost(fs->h_cursor);
     for (int i = 0; i < kFreshLead; i++) if (fs->done[i]) cudaEventDestroy(fs->done[i]);
+    if (fs->copy) cudaStreamDestroy(fs->copy);
+    if (fs->seeds_sent) cudaEventDestroy(fs->seeds_sent);
     delete fs;
     b->fresh = nullptr;
 }
@@ -2510,15 +2593,14 @@ int astro_fresh_games_enable(AstroBatch* b, const AstroCreateConfig* cc, uint32_
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     fresh_free(b);
-    FreshState* fs = new (std::nothrow) FreshState();
+    FreshState* fs = new (std::nothrow) FreshState();      // (value-initialised: every pointer / counter zero)
     if (!fs) return fail(ASTRO_E_NOMEM, "out of host memory");
-    memset(fs, 0, sizeof(*fs));
     b->fresh = fs;
     const int n_tiles = b->n_games / ASTRO_TILE;
     fs->capacity = (int64_t)n_tiles * quota;
     fs->f.n_tiles = n_tiles; fs->f.quota = quota; fs->f.n_games = b->n_games;
-    // seed ring: holds what the host may be ahead by (kFreshLead + 1 refills, or the initial fill of every game + every record), twice
-    unsigned long long need = 2ull * (unsigned long long)(kFreshLead + 2) * (unsigned long long)fs->capacity;
+    // seed ring: holds what the host may be ahead by (kFreshLead + 2 refills, or the initial fill of every game + every record), twice
+    unsigned long long need = 2ull * (unsigned long long)(kFreshLead + 4) * (unsigned long long)fs->capacity;
     const unsigned long long first = 2ull * ((unsigned long long)b->n_games + (unsigned long long)fs->capacity);
     if (need < first) need = first;
     unsigned long long ring = 1024;
@@ -2534,14 +2616,22 @@ int astro_fresh_games_enable(AstroBatch* b, const AstroCreateConfig* cc, uint32_
     if (e == cudaSuccess) e = cudaMalloc(&fs->f.cursor, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(const_cast<uint32_t**>(&fs->f.seeds), sizeof(uint32_t) * (size_t)ring);
     if (e == cudaSuccess) e = cudaMalloc(&fs->game_pos, sizeof(uint32_t) * (size_t)b->n_games);
+    if (e == cudaSuccess) e = cudaMalloc(&fs->chunk_base, sizeof(uint32_t) * (size_t)((n_tiles + 31) / 32 + 1));
     if (e == cudaSuccess) e = cudaMallocHost(&fs->h_seeds, sizeof(uint32_t) * (size_t)ring);
     if (e == cudaSuccess) e = cudaMallocHost(&fs->h_cursor, 4 * sizeof(unsigned long long));
     for (int i = 0; i < kFreshLead && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&fs->done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&fs->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fs->seeds_sent, cudaEventDisableTiming);
     if (e != cudaSuccess) { fresh_free(b); return fail(ASTRO_E_CUDA, "fresh-game buffers: %s", cudaGetErrorString(e)); }
     fs->mt.seed(config_seed);
     for (int64_t i = 0; i < skip; i++) fs->mt.next();
     // the stream positions count from `skip`: position p is generate_configs draw number p
     fs->generated = (unsigned long long)skip;
+    fs->produced.store((unsigned long long)skip);
+    fs->target.store((unsigned long long)skip);
+    fs->stop.store(0);
+    fs->producer = new (std::nothrow) std::thread(fresh_producer_main, fs);
+    if (!fs->producer) { fresh_free(b); return fail(ASTRO_E_NOMEM, "out of host memory"); }
     const unsigned long long start[4] = {(unsigned long long)skip, 0ull, 0ull, 0ull};
     memcpy(fs->h_cursor, start, sizeof(start));
     CUDA_TRY(cudaMemcpyAsync(fs->f.cursor, fs->h_cursor, sizeof(start), cudaMemcpyHostToDevice, st));

@@ -567,9 +567,15 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // A game that ends here and now (ship hit a planet / the other ship, or timeout) will be re-created
     // from its pool record at the end: pull the record towards L2 while the bullet loop runs.
     // (the pick is a few dozen integer instructions: only the rare lanes that need it work it out)
-    if (auto_reset && !p.ring && active && (hits || tick >= (uint32_t)p.timeout_tick)) {
-        const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pool_rec + (size_t)k * 8));
+    if (auto_reset && active && (hits || tick >= (uint32_t)p.timeout_tick)) {
+        if (!p.ring) {
+            const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pool_rec + (size_t)k * 8));
+        } else {
+            // fresh-game mode: which record the game will get depends on who else ends this tick; the tile's next
+            // record is the likely one
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ring + ((size_t)tile_index * (unsigned)p.quota + min(t.used, (unsigned)p.quota - 1u)) * 8));
+        }
     }
 
     // ================= 4. the bullet loop, from shared memory =======================================
@@ -873,11 +879,12 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
     TileIn in, next;
     unsigned stat_acc = 0;
     TileScratch& scratch = s_tiles[kTickWarps == 1 ? 0 : (threadIdx.x >> 5)];
-    if (p.ring) {   // fresh-game mode: how many of the tile's pre-created games have been used since the last refill
-        if (lane == 0) scratch.used = p.tile_used[tile];
-        __syncwarp();
-    }
+    // fresh-game mode: how many of the tile's pre-created games have been used since the last refill — requested with the
+    // tile's rows, parked in shared memory once they are all on their way (a wait here would cost a round trip)
+    unsigned used0 = 0;
+    if (p.ring && lane == 0) used0 = p.tile_used[tile];
     load_tile_in<S>(p, tick_var<S>(p, 0u), tile, lane, in);
+    if (p.ring && lane == 0) scratch.used = used0;
 #pragma unroll 1
     for (unsigned k = 0; k < (MANY ? (unsigned)p.n_fused : 1u); k++) {
         const TickVar v = tick_var<S>(p, MANY ? k : 0u);
