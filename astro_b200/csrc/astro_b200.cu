@@ -67,6 +67,7 @@ struct TickParams {
     uint32_t* tile_used;              //   records of each tile consumed since the last refill
     uint32_t* game_pos;               //   [n_games] position in the generate_configs stream of each game's current episode
     int32_t quota, pad_;
+    const uint32_t* step_base;        // captured launches (the bot loop as a CUDA graph): stream step = *step_base + step
     Consts c;
 };
 
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const __grid_constan
             if (bad_ctl) ev |= ASTRO_EV_BAD_CONTROL;
             if (ev & ASTRO_EV_DONE_MASK) {
                 if ((p.flags & ASTRO_TICK_AUTO_RESET) && p.pool_size > 0) {
-                    recreate_from_pool<R, S>(p, g, p.step + 1u, ships, ship_b, planets);
+                    recreate_from_pool<R, S>(p, g, p.step + (p.step_base ? *p.step_base : 0u) + 1u, ships, ship_b, planets);
                 } else {
                     p.meta[g] = ASTRO_META_PACK(0, np, 1, tick);
                 }
@@ -1278,7 +1279,9 @@ __device__ __forceinline__ uint32_t explore_key(uint32_t seed, uint32_t game, ui
 template <int S>
 __global__ void __launch_bounds__(128) explore_kernel(const uint32_t* __restrict__ meta_, int32_t* __restrict__ state,
                                                       uint8_t* __restrict__ actions, int n_games, int ship_mask, double dt,
-                                                      double t_in, double t_out, uint32_t seed, uint32_t first_game, uint32_t step) {
+                                                      double t_in, double t_out, uint32_t seed, uint32_t first_game, uint32_t step,
+                                                      const uint32_t* __restrict__ step_base) {
+    if (step_base) step += *step_base;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = idx / S, me = idx % S;
     if (g >= n_games || !((ship_mask >> me) & 1)) return;
@@ -1437,6 +1440,10 @@ __global__ void __launch_bounds__(128) import_kernel(void* __restrict__ ships_, 
     }
 }
 
+// the device-resident stream step of captured bot-loop chunks (astro_rollout_device)
+__global__ void step_base_set_kernel(uint32_t* p, uint32_t v) { *p = v; }
+__global__ void step_base_add_kernel(uint32_t* p, uint32_t v) { *p += v; }
+
 // ------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------
@@ -1514,6 +1521,17 @@ struct FreshState {
     int64_t capacity;             // n_tiles * quota
 };
 
+struct LoopGraph {        // a captured chunk of the bot loop (astro_rollout_device)
+    cudaGraphExec_t exec;
+    int32_t modes[2], flags, cur;
+    double avoid_distance, avoid_threshold;
+    uint8_t* actions;
+    uint8_t* events;
+    int64_t epoch;
+    int32_t launches;     // kernels of one replay
+};
+constexpr int kLoopChunk = 16;   // ticks per captured chunk (even: the bullet buffers are back where they started)
+
 struct SingleGraph {      // a captured single-game step (astro_step_single_host)
     cudaGraphExec_t exec;
     const void* in;
@@ -1544,6 +1562,13 @@ struct AstroBatch {
     cudaEvent_t ev_in[2], ev_tick[2], ev_out[2];
     bool pipe_ready;
     // astro_tick_host: the tick cut into slices of tiles, one stream per slice (created lazily)
+    // astro_rollout_device: the bot loop captured as a CUDA graph of kLoopChunk ticks (see there)
+    LoopGraph loop_graph[2];
+    uint32_t* d_step_base;        // device word: the stream step at the start of the chunk being replayed
+    const uint32_t* step_base_now;// = d_step_base while a chunk is being captured, else NULL
+    cudaStream_t loop_stream;
+    cudaEvent_t loop_in, loop_out;
+    int64_t config_epoch;         // bumped by every call that changes what a captured chunk depends on
     // fresh-game mode (astro_fresh_games_enable): per-tile rings of pre-created games fed from the generate_configs stream
     FreshState* fresh;
     cudaEvent_t ev_host_done;   // astro_tick_host_begin / _end
@@ -1640,6 +1665,7 @@ void fill_params(const AstroBatch* b, TickParams& p) {
     }
     p.seed = b->seed;
     p.step = b->step;
+    p.step_base = b->step_base_now;
     p.first_game = (uint32_t)b->first_game;
     p.c = b->c;
 }
@@ -1786,7 +1812,7 @@ int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done
     const size_t n = (size_t)b->n_games;
     for (int32_t k0 = 0; k0 < n_ticks;) {
         const int32_t kc = fused ? (n_ticks - k0 < kMaxFused ? n_ticks - k0 : kMaxFused) : 1;
-        if (b->fresh && (flags & ASTRO_TICK_AUTO_RESET) && advance) {
+        if (b->fresh && (flags & ASTRO_TICK_AUTO_RESET) && advance && !b->step_base_now) {
             // top the tiles' rings up once the ticks since the last refill, plus this launch, exceed half a quota (a tile
             // loses ~0.3 games per tick under random play: ~15 % of its records by then)
             FreshState* fs = b->fresh;
@@ -1823,7 +1849,8 @@ int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done
         b->step += (uint32_t)kc;
         b->cur ^= kc & 1;   // the lists now live in the buffer the last tick wrote
         // 32-bit slot rows: fold long before a row can wrap (<= 32 * 1023 per tick)
-        if (!(flags & ASTRO_TICK_NO_STATS) && (b->ticks_since_fold += kc) >= 65536) {
+        // (launches of >= 8 ticks add their totals straight to the 64-bit counters: nothing to fold)
+        if (!(flags & ASTRO_TICK_NO_STATS) && !(fused && kc >= 8) && (b->ticks_since_fold += kc) >= 65536) {
             cudaError_t fe = fold_stats(b, st);
             if (fe != cudaSuccess) return fail(ASTRO_E_CUDA, "fold_stats_kernel launch: %s", cudaGetErrorString(fe));
         }
@@ -1902,6 +1929,8 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaFree(b->d_src);
     cudaFree(b->d_single);
     fresh_free(b);
+    for (int i = 0; i < 2; i++) if (b->loop_graph[i].exec) cudaGraphExecDestroy(b->loop_graph[i].exec);
+    if (b->d_step_base) { cudaFree(b->d_step_base); cudaStreamDestroy(b->loop_stream); cudaEventDestroy(b->loop_in); cudaEventDestroy(b->loop_out); }
     for (int i = 0; i < kSingleGraphs; i++)
         if (b->single_graph[i].exec) cudaGraphExecDestroy(b->single_graph[i].exec);
     if (b->single_stream) { cudaStreamDestroy(b->single_stream); cudaEventDestroy(b->single_event); }
@@ -1936,6 +1965,7 @@ int astro_batch_bind(AstroBatch* b, const AstroBuffers* bufs) {
     b->bufs = *bufs;
     b->cur = 0;
     b->bound = true;
+    b->config_epoch++;
     return ASTRO_OK;
 }
 
@@ -1958,6 +1988,7 @@ int astro_set_schedule(AstroBatch* b, const uint32_t* fire_bits_host, int32_t n_
     CUDA_TRY(cudaMemcpy(b->d_fire_bits, fire_bits_host, words * sizeof(uint32_t), cudaMemcpyHostToDevice));
     b->n_sched_ticks = n_ticks;
     b->timeout_tick = timeout_tick;
+    b->config_epoch++;
     return ASTRO_OK;
 }
 
@@ -1966,6 +1997,7 @@ int astro_set_stream(AstroBatch* b, uint32_t seed, int64_t first_game, uint32_t 
     b->seed = seed;
     b->first_game = first_game;
     b->step = step;
+    b->config_epoch++;
     return ASTRO_OK;
 }
 
@@ -1975,6 +2007,7 @@ int astro_set_reset_pool(AstroBatch* b, const AstroResetPool* pool) {
         return fail(ASTRO_E_INVALID, "bad reset pool");
     if ((uintptr_t)pool->planets & 15) return fail(ASTRO_E_INVALID, "reset pool planets must be 16-byte aligned");
     b->pool = *pool;
+    b->config_epoch++;
     if (b->precision == 32) {
         // the tick kernel reads a packed snapshot (one 128-byte record per entry)
         CUDA_TRY(cudaSetDevice(b->device));
@@ -2293,6 +2326,7 @@ int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n
     delete w;
     if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "policy weights upload: %s", cudaGetErrorString(e));
     b->policy_nout = nout;
+    b->config_epoch++;
     return ASTRO_OK;
 }
 
@@ -2330,6 +2364,7 @@ int astro_set_exploration(AstroBatch* b, double t_in, double t_out, uint32_t see
     b->explore_t_out = t_out;
     b->explore_seed = seed;
     b->explore_state = state;
+    b->config_epoch++;
     return ASTRO_OK;
 }
 
@@ -2343,12 +2378,80 @@ int astro_explore_controls(AstroBatch* b, double t_in, double t_out, uint32_t se
     cudaStream_t st = (cudaStream_t)stream;
     if (b->S == 2)
         explore_kernel<2><<<grid, 128, 0, st>>>(b->bufs.meta, state, actions, b->n_games, ship_mask, b->cfg.dt, t_in, t_out, seed,
-                                                (uint32_t)b->first_game, b->step);
+                                                (uint32_t)b->first_game, b->step, b->step_base_now);
     else
         explore_kernel<1><<<grid, 128, 0, st>>>(b->bufs.meta, state, actions, b->n_games, ship_mask, b->cfg.dt, t_in, t_out, seed,
-                                                (uint32_t)b->first_game, b->step);
+                                                (uint32_t)b->first_game, b->step, b->step_base_now);
     CUDA_TRY(cudaGetLastError());
     b->launches += 1;
+    return ASTRO_OK;
+}
+
+static int rollout_one_tick(AstroBatch* b, const int* modes, double avoid_distance, double avoid_threshold, uint8_t* actions, uint8_t* events,
+                            int32_t flags, cudaStream_t st);
+
+static int rollout_chunks(AstroBatch* b, int n_chunks, const int* modes, double avoid_distance, double avoid_threshold, uint8_t* actions,
+                          uint8_t* events, int32_t flags, cudaStream_t st) {
+    if (!b->d_step_base) {
+        CUDA_TRY(cudaMalloc(&b->d_step_base, sizeof(uint32_t)));
+        CUDA_TRY(cudaStreamCreateWithFlags(&b->loop_stream, cudaStreamNonBlocking));   // (a legacy default stream cannot be captured)
+        CUDA_TRY(cudaEventCreateWithFlags(&b->loop_in, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b->loop_out, cudaEventDisableTiming));
+    }
+    cudaStream_t ls = b->loop_stream;
+    CUDA_TRY(cudaEventRecord(b->loop_in, st));                 // earlier work of the caller's stream comes first
+    CUDA_TRY(cudaStreamWaitEvent(ls, b->loop_in, 0));
+    step_base_set_kernel<<<1, 1, 0, ls>>>(b->d_step_base, b->step);
+    for (int c = 0; c < n_chunks; c++) {
+        if (b->fresh && (flags & ASTRO_TICK_AUTO_RESET)) {     // fresh-game mode: refills happen between chunks, outside the graph
+            FreshState* fs = b->fresh;
+            if (fs->ticks_since_refill > 0 && (fs->ticks_since_refill + kLoopChunk) * 2 > fs->f.quota)
+                if (int r = fresh_refill(b, ls)) return r;
+            fs->ticks_since_refill += kLoopChunk;
+        }
+        LoopGraph* g = nullptr;
+        for (int i = 0; i < 2; i++) {
+            LoopGraph& q = b->loop_graph[i];
+            if (q.exec && q.epoch == b->config_epoch && q.cur == b->cur && q.flags == flags && q.modes[0] == modes[0] && q.modes[1] == modes[1] &&
+                q.avoid_distance == avoid_distance && q.avoid_threshold == avoid_threshold && q.actions == actions && q.events == events)
+                g = &q;
+        }
+        if (!g) {
+            g = &b->loop_graph[b->cur & 1];
+            if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+            const uint32_t step_saved = b->step;
+            const int32_t cur_saved = b->cur;
+            const int64_t launches_saved = b->launches, fold_saved = b->ticks_since_fold;
+            CUDA_TRY(cudaStreamBeginCapture(ls, cudaStreamCaptureModeThreadLocal));
+            b->step_base_now = b->d_step_base;
+            b->step = 0;                                       // steps inside a chunk are relative to the device word
+            int rc = ASTRO_OK;
+            for (int j = 0; j < kLoopChunk && !rc; j++) rc = rollout_one_tick(b, modes, avoid_distance, avoid_threshold, actions, events, flags, ls);
+            if (!rc) step_base_add_kernel<<<1, 1, 0, ls>>>(b->d_step_base, (uint32_t)kLoopChunk);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(ls, &graph);
+            b->step_base_now = nullptr;
+            b->step = step_saved;
+            b->cur = cur_saved;
+            g->launches = (int32_t)(b->launches - launches_saved) + 1;
+            b->launches = launches_saved;
+            b->ticks_since_fold = fold_saved;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(ASTRO_E_CUDA, "bot-loop capture: %s", cudaGetErrorString(e));
+            const cudaError_t ei = cudaGraphInstantiate(&g->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) { g->exec = nullptr; return fail(ASTRO_E_CUDA, "bot-loop graph: %s", cudaGetErrorString(ei)); }
+            g->epoch = b->config_epoch; g->cur = b->cur; g->flags = flags; g->modes[0] = modes[0]; g->modes[1] = modes[1];
+            g->avoid_distance = avoid_distance; g->avoid_threshold = avoid_threshold; g->actions = actions; g->events = events;
+        }
+        CUDA_TRY(cudaGraphLaunch(g->exec, ls));
+        b->step += (uint32_t)kLoopChunk;
+        b->launches += g->launches;
+        if (!(flags & ASTRO_TICK_NO_STATS)) b->ticks_since_fold += kLoopChunk;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(b->loop_out, ls));
+    CUDA_TRY(cudaStreamWaitEvent(st, b->loop_out, 0));         // ... and the caller's stream carries on behind the chunks
     return ASTRO_OK;
 }
 
@@ -2379,7 +2482,37 @@ int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int
         if (n_ticks > 1) if (int r = do_ticks(b, nullptr, nullptr, nullptr, nullptr, flags, st, n_ticks - 1)) return r;
         return n_ticks > 0 ? do_ticks(b, nullptr, nullptr, nullptr, events, flags, st, 1) : ASTRO_OK;
     }
-    for (int k = 0; k < n_ticks; k++) {
+    // One tick of the loop is 2-4 small launches; at 16,384 games the gaps between them cost as much as the kernels.  Whole
+    // chunks of kLoopChunk ticks are therefore captured ONCE into a CUDA graph and replayed: one graph launch per chunk.
+    // What changes from chunk to chunk — the stream step, which keys the pool picks and the exploration draws — is read
+    // by the kernels from a device word (step_base) that a one-thread node advances at the end of every chunk; the rest
+    // of a chunk's parameters are fixed (an even number of ticks leaves the bullet buffers where they started).
+    // ASTRO_LOOP_GRAPH=0 switches it off.
+    const char* lg = getenv("ASTRO_LOOP_GRAPH");
+    int k_done = 0;
+    if (n_ticks >= kLoopChunk && !(lg && atoi(lg) == 0)) {
+        if (int r = rollout_chunks(b, n_ticks / kLoopChunk, modes, avoid_distance, avoid_threshold, actions, events, flags, st)) return r;
+        k_done = (n_ticks / kLoopChunk) * kLoopChunk;
+    }
+    for (int k = k_done; k < n_ticks; k++) {
+        if (int r = rollout_one_tick(b, modes, avoid_distance, avoid_threshold, actions, events, flags, st)) return r;
+    }
+    return ASTRO_OK;
+}
+
+// (the body of one tick of astro_rollout_device with bots, on stream st)
+static int rollout_one_tick(AstroBatch* b, const int* modes, double avoid_distance, double avoid_threshold, uint8_t* actions, uint8_t* events,
+                     int32_t flags, cudaStream_t st) {
+    void* stream = (void*)st;
+    bool any_script = false, any_policy = false, any_idle = false, any_explore = false;
+    for (int k = 0; k < b->S; k++) {
+        any_script |= modes[k] == ASTRO_BOT_SCRIPT;
+        any_policy |= modes[k] == ASTRO_BOT_POLICY || modes[k] == ASTRO_BOT_EXPLORE;
+        any_explore |= modes[k] == ASTRO_BOT_EXPLORE;
+        any_idle |= modes[k] == ASTRO_BOT_NOTHING;
+    }
+    const bool all_stream = false;
+    {
         // a script bot writes every ship's control, the policy then overwrites the ships it drives
         if (any_script)
             if (int r = astro_script_controls(b, avoid_distance, avoid_threshold, actions, stream)) return r;

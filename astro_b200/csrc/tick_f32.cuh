@@ -569,7 +569,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // (the pick is a few dozen integer instructions: only the rare lanes that need it work it out)
     if (auto_reset && active && (hits || tick >= (uint32_t)p.timeout_tick)) {
         if (!p.ring) {
-            const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size);
+            const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + (p.step_base ? *p.step_base : 0u) + 1u, (uint32_t)p.pool_size);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pool_rec + (size_t)k * 8));
         } else {
             // fresh-game mode: which record the game will get depends on who else ends this tick; the tile's next
@@ -738,7 +738,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 if (want && idx < (unsigned)p.quota) rec = p.ring + ((size_t)tile_index * (unsigned)p.quota + idx) * 8;
             }
         } else if (ended) {
-            rec = p.pool_rec + (size_t)pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + 1u, (uint32_t)p.pool_size) * 8;
+            rec = p.pool_rec + (size_t)pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + (p.step_base ? *p.step_base : 0u) + 1u, (uint32_t)p.pool_size) * 8;
         }
         if (ended) atomicAdd(&p.episode[g], 1u);      // the per-slot episode counter: a fire-and-forget RED
         if (rec) {
@@ -842,8 +842,14 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         // astro_stats() folds the rows
         stat_acc += warp_totals((int)lane, S, ev, active, spawned, np, nb, m_out);
         if (last) {
-            unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
-            if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(slot, stat_acc);  // RED: fire and forget
+            if (MANY && p.n_fused >= 8) {
+                // a launch of many ticks: the tile's totals of the whole launch go straight to the 64-bit counters —
+                // one RED per counter and tile per LAUNCH is cheap, and astro_stats needs no fold pass afterwards
+                if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(&p.stats[lane], (unsigned long long)stat_acc);
+            } else {
+                unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
+                if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(slot, stat_acc);  // RED: fire and forget
+            }
         }
     }
     TL(7);

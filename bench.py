@@ -399,10 +399,17 @@ def run_ours(args):
             return n_launch
         run_steps(warmup)
         games.stats_tensor(clear=True)
+        align = torch.zeros(1, device=dev)
+        if world > 1:
+            dist.all_reduce(align)       # (NCCL warm-up for this size)
         launches0 = games.launches
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            # the ranks leave the host barrier tens of microseconds apart; a tiny all-reduce in front of the first event
+            # lines the STREAMS up, so that the timed region of every rank starts at the same moment on the devices
+            dist.all_reduce(align)
+        torch.cuda.synchronize() if world == 1 else None
         e0.record()
         n_launches = run_steps(steps)
         st_t = games.stats_tensor(clear=True)
