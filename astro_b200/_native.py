@@ -27,7 +27,7 @@ EXPORTS = ('astro_abi_version', 'astro_last_error', 'astro_batch_create', 'astro
            'astro_launch_count', 'astro_script_controls', 'astro_create_games', 'astro_observe_shared', 'astro_policy_set_weights',
            'astro_policy_controls', 'astro_rollout_device', 'astro_bullet_buffer', 'astro_set_bullet_buffer', 'astro_tick_many', 'astro_explore_controls', 'astro_set_exploration',
            'astro_tick_host_begin', 'astro_tick_host_end', 'astro_fresh_games_enable', 'astro_fresh_games_reset_all',
-           'astro_fresh_games_refill', 'astro_fresh_games_positions', 'astro_config_seeds', 'astro_export_games', 'astro_import_games', 'astro_single_game_bytes', 'astro_step_single_host')
+           'astro_fresh_games_refill', 'astro_fresh_games_positions', 'astro_config_seeds', 'astro_nstep_experiences', 'astro_export_games', 'astro_import_games', 'astro_single_game_bytes', 'astro_step_single_host')
 
 
 class AstroConfig(C.Structure):
@@ -104,6 +104,7 @@ def lib():
     L.astro_fresh_games_refill.argtypes = [vp, vp]
     L.astro_fresh_games_positions.argtypes = [vp, vp, vp, C.POINTER(i64), vp]
     L.astro_config_seeds.argtypes = [u32, i64, i64, vp]
+    L.astro_nstep_experiences.argtypes = [vp, vp, i32, i32, C.c_double, vp, vp, vp, vp, vp]
     L.astro_explore_controls.argtypes = [vp, C.c_double, C.c_double, u32, vp, vp, i32, vp]
     L.astro_set_exploration.argtypes = [vp, C.c_double, C.c_double, u32, vp]
     L.astro_rollout_host.argtypes = [vp, vp, vp, i32, i32, vp]

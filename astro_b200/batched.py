@@ -602,6 +602,26 @@ class BatchedGames:
                                                  flags, self._stream()))
         self.step_index += int(n_ticks)
 
+    # ---- n-step replay ingestion ---------------------------------------------------------------------
+    def nstep_experiences(self, events, carry=None, n_steps=100, discount=0.995):
+        """`rl.QBotTrainer.reward` (rl.py:303-328) for every bot over the logged ticks `events` (uint8 cuda [T, n_pad]): which
+        (state, action) pairs enter the replay buffer, with which discounted reward / discount / new state.  Returns
+        (reward f32, discount f32, next i32) cuda tensors [n_steps + T, n_pad, S] (row n_steps + t = the pair of tick t; see
+        astro_nstep_experiences) and the carry tensor int32 [n_pad, S] (pass it to the next window's call)."""
+        torch = _torch()
+        T = int(events.shape[0])
+        if tuple(events.shape) != (T, self.n_pad) or events.dtype != torch.uint8 or not events.is_contiguous():
+            raise ValueError('events must be a contiguous uint8 cuda tensor [T, %d]' % self.n_pad)
+        if carry is None:
+            carry = torch.zeros((self.n_pad, self.S), dtype=torch.int32, device=self.device)
+        shape = (int(n_steps) + T, self.n_pad, self.S)
+        rew = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        dis = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        nxt = torch.full(shape, -3, dtype=torch.int32, device=self.device)
+        nat.check(nat.lib().astro_nstep_experiences(self._h, events.data_ptr(), T, int(n_steps), float(discount), carry.data_ptr(),
+                                                    rew.data_ptr(), dis.data_ptr(), nxt.data_ptr(), self._stream()))
+        return rew, dis, nxt, carry
+
     # ---- statistics ------------------------------------------------------------------------------
     def stats_tensor(self, clear=False):
         """Device int64 [12] counters (see _native.STAT_NAMES) — the input of the NCCL all-reduce."""

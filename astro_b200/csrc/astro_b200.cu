@@ -1440,6 +1440,59 @@ __global__ void __launch_bounds__(128) import_kernel(void* __restrict__ ships_, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// nstep_kernel: the n-step replay ingestion of rl.QBotTrainer.reward (rl.py:303-328) for every bot of every game over a
+// window of T logged ticks — thread = one bot (game, ship).  The reference keeps, per bot, the (features, action) pairs
+// since the last flush and, when the game ends or n_steps pairs are held, turns pair number n of L into
+//     Experience(state_f, action, reward * d, discount * d, new_state_f)     d = discount ** (L - 1 - n)
+// with `reward` the reward of the flushing tick (only terminal ticks have one) and new_state_f = None when the game
+// ended.  Here an entry is identified by its tick (the observation taken before that tick); rows 0 .. H-1 of the outputs
+// stand for the H = n_steps ticks before the window (entries a bot still held when the window began: `carry`), row
+// H + t for tick t.  Per entry: reward * d, discount * d (float32) and `next` = the tick whose observation is the new
+// state (window-relative, t_flush + 1), -1 = terminal (no new state), -2 = still held when the window ends (it comes
+// back as a carried entry of the next window), -3 = no entry (the game was finished and skipped that tick).
+// ------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(128) nstep_kernel(const uint8_t* __restrict__ events, int T, int n_games, int n_steps, double discount,
+                                                    float reward_timeout, int32_t* __restrict__ carry, float* __restrict__ out_reward,
+                                                    float* __restrict__ out_discount, int32_t* __restrict__ out_next) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_games * S) return;
+    const int g = idx / S, me = idx % S;
+    const int H = n_steps;
+    const size_t stride = (size_t)n_games * S;
+    int L = min(max(carry[idx], 0), n_steps - 1);
+    int seg_start = -L;                                    // first held entry, as a window-relative tick
+    for (int r = 0; r < H - L; r++) out_next[(size_t)r * stride + idx] = -3;       // history rows this bot does not hold
+    for (int t = 0; t < T; t++) {
+        const uint32_t ev = events[(size_t)t * n_games + g];
+        if (ev & ASTRO_EV_SKIPPED) {                       // no step was taken: no entry; the bot holds nothing (its game is over)
+            out_next[(size_t)(H + t) * stride + idx] = -3;
+            seg_start = t + 1;
+            continue;
+        }
+        L = t - seg_start + 1;
+        const bool term = (ev & ASTRO_EV_DONE_MASK) != 0;
+        if (term || L >= n_steps) {
+            double reward = 0.0;
+            if (ev & (ASTRO_EV_HIT0 | ASTRO_EV_HIT1)) reward = ((ev >> me) & 1u) ? -1.0 : 1.0;     // core.py:255
+            else if (ev & ASTRO_EV_TIMEOUT) reward = (double)reward_timeout;                        // core.py:260
+            for (int n = seg_start; n <= t; n++) {
+                const double d = pow(discount, (double)(t - n));
+                const size_t row = (size_t)(H + n) * stride + idx;
+                out_reward[row] = (float)(reward * d);
+                out_discount[row] = (float)(discount * d);
+                out_next[row] = term ? -1 : t + 1;
+            }
+            seg_start = t + 1;
+        }
+    }
+    for (int n = seg_start; n < T; n++) out_next[(size_t)(H + n) * stride + idx] = -2;
+    carry[idx] = T - seg_start > 0 ? T - seg_start : 0;
+    // (held entries that began before the window and are still held: the window was shorter than n_steps)
+    for (int n = seg_start; n < 0; n++) out_next[(size_t)(H + n) * stride + idx] = -2;
+}
+
 // the device-resident stream step of captured bot-loop chunks (astro_rollout_device)
 __global__ void step_base_set_kernel(uint32_t* p, uint32_t v) { *p = v; }
 __global__ void step_base_add_kernel(uint32_t* p, uint32_t v) { *p += v; }
@@ -2831,6 +2884,21 @@ int astro_config_seeds(uint32_t config_seed, int64_t skip, int64_t count, uint32
     mt.seed(config_seed);
     for (int64_t i = 0; i < skip; i++) mt.next();
     for (int64_t i = 0; i < count; i++) out_host[i] = mt.next() & 0x3fffffffu;
+    return ASTRO_OK;
+}
+
+int astro_nstep_experiences(AstroBatch* b, const uint8_t* events, int32_t n_ticks, int32_t n_steps, double discount, int32_t* carry,
+                            float* out_reward, float* out_discount, int32_t* out_next, void* stream) {
+    if (int r = check(b, false)) return r;
+    if (!events || !carry || !out_reward || !out_discount || !out_next) return fail(ASTRO_E_INVALID, "null argument");
+    if (n_ticks < 0 || n_steps < 1 || !(discount > 0.0)) return fail(ASTRO_E_INVALID, "bad n-step arguments");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (b->n_games * b->S + 127) / 128;
+    if (b->S == 2) nstep_kernel<2><<<grid, 128, 0, st>>>(events, n_ticks, b->n_games, n_steps, discount, b->c.reward_timeout, carry, out_reward, out_discount, out_next);
+    else nstep_kernel<1><<<grid, 128, 0, st>>>(events, n_ticks, b->n_games, n_steps, discount, b->c.reward_timeout, carry, out_reward, out_discount, out_next);
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
     return ASTRO_OK;
 }
 

@@ -369,6 +369,20 @@ typedef struct AstroSingleGame {
 int64_t astro_single_game_bytes(int32_t bullet_cap);
 int astro_step_single_host(AstroBatch* b, const AstroSingleGame* in_host, AstroSingleGame* out_host, int32_t flags, void* stream);
 
+/* The n-step replay ingestion of rl.QBotTrainer.reward (rl.py:303-328) for every bot (game, ship) over a window of n_ticks
+ * logged ticks: which (state, action) pairs are flushed into the replay buffer when, with which discounted reward, discount
+ * and new state — from the ticks' event bytes alone (the actions and observations of the ticks stay where the caller
+ * logged them; an Experience is identified by its tick).  Device pointers:
+ *   events     u8 [n_ticks][n_games]            the ticks' ASTRO_EV_* bytes (astro_tick_many / astro_rollout_*)
+ *   carry      i32 [n_games][S]  in/out         pairs a bot still holds (before the window / after it); zero-initialised
+ *   out_reward / out_discount f32, out_next i32 [n_steps + n_ticks][n_games][S]: row n_steps + t = the pair of tick t, rows
+ *              below n_steps = the ticks before the window (carried pairs that flush now).  reward = r * d and discount =
+ *              discount * d with d = discount ** (pairs held after this one), r the flushing tick's reward (core.py:255,260);
+ *              next = window-relative tick whose observation is the new state (flush tick + 1), -1 terminal (new state None),
+ *              -2 still held at the end of the window, -3 no pair (the game was finished and skipped the tick). */
+int astro_nstep_experiences(AstroBatch* b, const uint8_t* events, int32_t n_ticks, int32_t n_steps, double discount, int32_t* carry,
+                            float* out_reward, float* out_discount, int32_t* out_next, void* stream);
+
 /* Copies the ASTRO_N_STATS device counters into counters_dev (device pointer, e.g. the input of
  * an NCCL all-reduce) on the stream; clear != 0 zeroes them afterwards. */
 int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream);

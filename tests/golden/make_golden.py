@@ -21,6 +21,7 @@ this file:
   traj_raw.npz/.json  trajectories from core.create's RAW float32 arrays (the first tick's float32 arithmetic)
   network.npz     rl.ValueNetwork (rl.py:115-165) with seeded weights: evaluate / evaluate_batch outputs + state_dict
   explore.json    rl.EpsilonGreedy (rl.py:10-30): empirical transition rates and control histogram
+  nstep.json      rl.QBotTrainer.reward (rl.py:303-328): the Experiences the reference's n-step ingestion appends
 
 Everything downstream (oracle/, tests/) reads only these files.
 """
@@ -520,6 +521,46 @@ def make_explore():
     print('explore', out)
 
 
+def make_nstep():
+    """rl.QBotTrainer.reward (rl.py:303-328) — the n-step replay ingestion — run by the reference itself on the logged
+    ticks of the recorded duel games played back to back by one bot slot per ship (the bot object persists across games,
+    like rl.train's): per (n_steps, discount) setting the Experiences it appended, each identified by the global tick of
+    its state: (tick, action, reward, discount, tick of the new state or -1)."""
+    z = np.load(os.path.join(HERE, 'traj.npz'))
+    meta = json.load(open(os.path.join(HERE, 'traj.json')))
+    games = [m for m in meta if m['kind'] == 'duel_random' and not m['truncated']][:10]
+    ticks = []                                   # (action pair, reward pair, terminal)
+    for m in games:
+        g = m['game']
+        for k in range(m['nticks']):
+            ticks.append((z['g%d_control' % g][k].tolist(), z['g%d_reward' % g][k].tolist(), k == m['nticks'] - 1))
+
+    class Q:
+        @staticmethod
+        def get_features(state):
+            return state                         # (a state stands for itself: its global tick)
+
+    class Trainer:
+        q = Q()
+    out = dict(ticks=ticks, settings=[])
+    for n_steps, discount in ((100, 0.995), (7, 0.9), (1, 0.5)):
+        per_ship = []
+        for me in range(2):
+            bot = rl.QBotTrainer(Trainer(), seed=1)
+            bot.n_steps, bot.discount = n_steps, discount
+            bot._step = lambda: None             # (the optimisation step is not part of the ingestion)
+            for t, (action, reward, terminal) in enumerate(ticks):
+                bot._nstep_buffer.append((t, int(action[me])))          # what __call__ appends (rl.py:254): (features, action)
+                bot.reward(None if terminal else t + 1, reward[me])
+            per_ship.append([[int(x.state_f), int(x.action), float(x.reward), float(x.discount),
+                              -1 if x.new_state_f is None else int(x.new_state_f)] for x in bot._replay_buffer]
+                            + [['held', len(bot._nstep_buffer)]])
+        out['settings'].append(dict(n_steps=n_steps, discount=discount, experiences=per_ship))
+    with open(os.path.join(HERE, 'nstep.json'), 'w') as f:
+        json.dump(out, f)
+    print('nstep', [len(s['experiences'][0]) for s in out['settings']], 'experiences over', len(ticks), 'ticks')
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:          # python make_golden.py make_network make_explore ...: only the named parts
         for name in sys.argv[1:]:
@@ -535,4 +576,5 @@ if __name__ == '__main__':
     make_traj_raw()
     make_network()
     make_explore()
+    make_nstep()
     print('numpy', np.__version__)

@@ -1610,3 +1610,47 @@ def test_fresh_games_fused_launches_1M_no_repeats():
         seeds = rng.config_seeds(cfg.seed, int(p_s.max()) + 1, 0)[p_s[fresh]]
         ships, planets, npl = _created_rows(cfg, seeds)
         assert (arr['ships'][fresh] == ships).all() and (arr['n_planets'][fresh] == npl).all()
+
+
+@pytest.mark.parametrize('window', [964, 50, 7, 1])
+def test_nstep_experiences_match_the_reference_ingestion(window):
+    """astro_nstep_experiences against rl.QBotTrainer.reward run by the reference itself (tests/golden/nstep.json: one bot
+    slot per ship over ten recorded games back to back): every Experience the reference appended — which tick's state,
+    the discounted reward, the discount, the new state's tick or None — comes out once, whatever the window the log is
+    cut into (pairs still held at a window's end are carried into the next)."""
+    import torch
+    gold = json.load(open(os.path.join(H.G, 'nstep.json')))
+    ticks = gold['ticks']
+    T = len(ticks)
+    ev = np.full((T, 32), nat.EV_SKIPPED, dtype=np.uint8)
+    for t, (action, reward, terminal) in enumerate(ticks):
+        e = 0
+        if terminal:
+            e = (1 if reward[0] < 0 else 0) | (2 if reward[1] < 0 else 0)
+            e = e or nat.EV_TIMEOUT
+        ev[t, 0] = e
+    games = _games(core.DEFAULT_CONFIG, 32, bullet_cap=32, precision=32)
+    ev_dev = torch.from_numpy(ev).cuda()
+    for setting in gold['settings']:
+        n_steps, discount = setting['n_steps'], setting['discount']
+        got = [dict(), dict()]
+        carry = None
+        for t0 in range(0, T, window):
+            chunk = ev_dev[t0:t0 + window].contiguous()
+            rew, dis, nxt, carry = games.nstep_experiences(chunk, carry, n_steps=n_steps, discount=discount)
+            rew, dis, nxt = rew.cpu().numpy()[:, 0], dis.cpu().numpy()[:, 0], nxt.cpu().numpy()[:, 0]
+            for row in range(nxt.shape[0]):
+                for me in range(2):
+                    if nxt[row, me] >= -1:
+                        tick = t0 + row - n_steps
+                        assert tick >= 0 and tick not in got[me]
+                        got[me][tick] = (float(rew[row, me]), float(dis[row, me]), -1 if nxt[row, me] < 0 else t0 + int(nxt[row, me]))
+            assert (carry.cpu().numpy()[1:] == 0).all()
+        for me in range(2):
+            want = setting['experiences'][me]
+            assert want[-1][0] == 'held' and int(carry[0, me]) == want[-1][1]
+            assert len(got[me]) == len(want) - 1
+            for tick, action, reward, disc, new in want[:-1]:
+                r, d, n = got[me][tick]
+                assert n == new and abs(r - reward) <= 1e-6 * max(1.0, abs(reward)) and abs(d - disc) <= 1e-6 * disc, (n_steps, tick)
+                assert action == ticks[tick][0][me]
