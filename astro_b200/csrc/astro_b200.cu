@@ -1263,6 +1263,285 @@ policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
 }
 
 // ------------------------------------------------------------------------------------------
+// policy_mma_kernel<R, S>: the same network on the tensor cores.  The three per-object layers are batched GEMMs
+// [row-vectors, 32] x [32, 32]: a warp takes a game's live rows eight objects at a time as ONE 16-row MMA tile — rows 0-7
+// the eight objects seen by ship 0, rows 8-15 the same objects seen by ship 1 — and runs f0, f[0], f[1] as
+// mma.sync.m16n8k8 TF32 tiles with fp32 accumulators (HMMA.1688.F32.TF32).  TF32 keeps 10 mantissa bits, which would move
+// the outputs by 1e-3 and flip near-tied argmaxes, so every product is taken as three: a = a_hi + a_lo, w = w_hi + w_lo
+// (each part exactly representable in TF32), a.w ~ a_lo.w_hi + a_hi.w_lo + a_hi.w_hi — the "3xTF32" scheme: fp32-level
+// results (the outputs stay within 2e-6 of the PyTorch fp32 network, as the CUDA-core kernel's do).
+//   * A fragments come straight from registers: a lane of quad g holds object row g, and the accumulator layout of one
+//     layer (columns 2t, 2t+1 of n-tile nt) IS the A layout of the next layer's k-step nt once the weights' input columns
+//     are permuted to match (k index t <-> unit 8 nt + 2t, t + 4 <-> 8 nt + 2t + 1) — no shuffle, no shared memory between
+//     layers.  The first layer's A fragment (15 features, K padded to 16) is built per lane from the game's ship features
+//     and ONE component of the row's object.
+//   * B fragments (weights, split into hi / lo, permuted, fragment-ordered: one LDS.128 per k-step and n-tile) are staged in
+//     shared memory once per CTA (20 KB).
+//   * max-pool: a running maximum in the accumulator layout, reduced across the quads once per game; the head (two
+//     32 x 32 layers and 32 -> nout on two vectors per game) stays on the CUDA cores, as in policy_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int kMmaWarps = 4;
+constexpr int kPoolStride = 36;      // floats per row of the pooled tile (32 + 4: the A-fragment loads hit 32 different banks)
+struct PolicyFrags {                 // per CTA, in (dynamic) shared memory; B fragments {b0_hi, b1_hi, b0_lo, b1_lo} per lane
+    float4 f0[2][4][32];             // [k-step][n-tile][lane]: per-object layers
+    float4 f1[4][4][32];
+    float4 f2[4][4][32];
+    float4 v1[4][4][32];             // head
+    float4 v2[4][4][32];
+    float4 v0[4][32];                // head output: one n-tile (nout <= 8)
+    float2 bias[5][4][4];            // [f0, f1, f2, v1, v2][n-tile][t] = bias of units 8 nt + 2t, 8 nt + 2t + 1
+    float2 bias_v0[4];               // [t] = bias of outputs 2t, 2t + 1
+    float pool[kMmaWarps][16][kPoolStride];   // per warp: the pooled vectors of 8 games, rows 0-7 ship 0's view, 8-15 ship 1's
+    float4 red[kMmaWarps][8][4][2];  // per warp: max-pool exchange, [quad][t][half of the 16 accumulators as 2 float4]
+    float sf[kMmaWarps][12];         // per warp: the game's ship features, ship 0 then ship 1
+};
+// x = hi + lo for the 3xTF32 scheme.  The tensor core reads only the 19 high bits of an fp32 operand (it truncates), so hi
+// is x itself — no instruction — standing for trunc(x); lo = x - trunc(x) exactly (a mask and a subtraction), and adding
+// half a TF32 ulp to lo's bit pattern makes the hardware's truncation of lo a round-to-nearest: what the pair drops is
+// below 2^-22 |x| and unbiased.  (cvt.rna.tf32.f32 runs on the XU pipe at a quarter rate: the split was half of this
+// kernel's time when it went through it.)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x);
+    lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi & 0xffffe000u))) + 0x1000u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// one k-step of a layer for NT n-tiles: A = (x0, x1, x2, x3) in fp32, split here; B from shared memory
+template <int NT>
+__device__ __forceinline__ void mma_kstep(float (&acc)[NT][4], float x0, float x1, float x2, float x3, const float4* __restrict__ bfrag, int lane) {
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+    split_tf32(x0, h0, l0); split_tf32(x1, h1, l1); split_tf32(x2, h2, l2); split_tf32(x3, h3, l3);
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        const float4 b = bfrag[nt * 32 + lane];
+        const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y), bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
+        mma_tf32(acc[nt], l0, l1, l2, l3, bh0, bh1);      // small terms first
+        mma_tf32(acc[nt], h0, h1, h2, h3, bl0, bl1);
+        mma_tf32(acc[nt], h0, h1, h2, h3, bh0, bh1);
+    }
+}
+// weights w0, w1 as a B-fragment entry: hi = rounded to TF32, lo = the rest rounded to TF32 (once per CTA: the cvt is fine here)
+__device__ __forceinline__ float4 bfrag_entry(float w0, float w1) {
+    uint32_t h0, h1, l0, l1;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(w0));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(w1));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l0) : "f"(__fsub_rn(w0, __uint_as_float(h0))));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l1) : "f"(__fsub_rn(w1, __uint_as_float(h1))));
+    return make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+}
+template <int NT>
+__device__ __forceinline__ void init_bias(float (&acc)[NT][4], const float2 (*bias)[4], int t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        const float2 b2 = bias[nt][t];
+        acc[nt][0] = b2.x; acc[nt][1] = b2.y; acc[nt][2] = b2.x; acc[nt][3] = b2.y;
+    }
+}
+
+#ifndef ASTRO_MMA_MIN_BLOCKS
+#define ASTRO_MMA_MIN_BLOCKS 4
+#endif
+template <typename R, int S>
+__global__ void __launch_bounds__(kMmaWarps * 32, ASTRO_MMA_MIN_BLOCKS)
+policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_, const void* __restrict__ planets_,
+                  const void* __restrict__ bullets_, const uint32_t* __restrict__ meta_, uint8_t* __restrict__ actions,
+                  float* __restrict__ q_out, int n_games, int K, int nout, int ship_mask, const PolicyWeights* __restrict__ pol) {
+    constexpr int DIN = 1 + 5 * S + 4;
+    extern __shared__ float4 s_dyn[];
+    PolicyFrags& s_w = *reinterpret_cast<PolicyFrags*>(s_dyn);
+    const PolicyWeights& g_pol = *pol;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, t = lane & 3;                     // quad = object row of the tile / n column; t = k index
+    // ---- stage the weights as B fragments (hi / lo), once per CTA
+    for (int i = threadIdx.x; i < (2 + 4 + 4 + 4 + 4 + 1) * 4 * 32; i += blockDim.x) {
+        const int l = i & 31, nt = (i >> 5) & 3, kk = i >> 7;   // kk: 0-1 f0, 2-5 f1, 6-9 f2, 10-13 v1, 14-17 v2, 18 v0 (nt = its k-step)
+        const int g_ = l >> 2, t_ = l & 3, n = nt * 8 + g_;
+        if (kk < 2) {                                           // natural K order: columns 8 kk + t, 8 kk + t + 4 (>= DIN: zero)
+            const int c0 = kk * 8 + t_, c1 = c0 + 4;
+            s_w.f0[kk][nt][l] = bfrag_entry(c0 < DIN ? g_pol.f0t[c0][n] : 0.f, c1 < DIN ? g_pol.f0t[c1][n] : 0.f);
+        } else if (kk < 10) {                                   // permuted K order: units 8 k2 + 2t, 8 k2 + 2t + 1 (A = the previous layer's accumulators)
+            const int k2 = (kk - 2) & 3, c0 = k2 * 8 + 2 * t_;
+            if (kk < 6) s_w.f1[k2][nt][l] = bfrag_entry(g_pol.f1t[c0][n], g_pol.f1t[c0 + 1][n]);
+            else s_w.f2[k2][nt][l] = bfrag_entry(g_pol.f2t[c0][n], g_pol.f2t[c0 + 1][n]);
+        } else if (kk < 14) {                                   // v[0]: natural order (A = the pooled tile in shared memory)
+            const int k2 = kk - 10, c0 = k2 * 8 + t_;
+            s_w.v1[k2][nt][l] = bfrag_entry(g_pol.v1t[c0][n], g_pol.v1t[c0 + 4][n]);
+        } else if (kk < 18) {                                   // v[1]: permuted
+            const int k2 = kk - 14, c0 = k2 * 8 + 2 * t_;
+            s_w.v2[k2][nt][l] = bfrag_entry(g_pol.v2t[c0][n], g_pol.v2t[c0 + 1][n]);
+        } else {                                                // v0: permuted, one n-tile of 8 outputs (>= nout: zero); here nt is the k-step
+            const int c0 = nt * 8 + 2 * t_;
+            s_w.v0[nt][l] = bfrag_entry(g_pol.v0t[c0][g_], g_pol.v0t[c0 + 1][g_]);
+        }
+    }
+    for (int i = threadIdx.x; i < 5 * 4 * 4; i += blockDim.x) {
+        const int t_ = i & 3, nt = (i >> 2) & 3, layer = i >> 4;
+        const float* bsrc = layer == 0 ? g_pol.f0b : (layer == 1 ? g_pol.f1b : (layer == 2 ? g_pol.f2b : (layer == 3 ? g_pol.v1b : g_pol.v2b)));
+        s_w.bias[layer][nt][t_] = make_float2(bsrc[nt * 8 + 2 * t_], bsrc[nt * 8 + 2 * t_ + 1]);
+    }
+    if (threadIdx.x < 4) s_w.bias_v0[threadIdx.x] = make_float2(g_pol.v0b[2 * threadIdx.x], g_pol.v0b[2 * threadIdx.x + 1]);
+    __syncthreads();
+    // ---- what this lane's four feature slots (columns t, t + 4, t + 8, t + 12) are: flag / ship feature / object component / zero
+    int ship_idx[4], obj_comp = 0, obj_slot = -1;
+    bool is_flag = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int col = t + 4 * j;
+        ship_idx[j] = -1;
+        if (col == 0) is_flag = true;
+        else if (col <= 5 * S) ship_idx[j] = col - 1;           // feature (col - 1) % 5 of ship (col - 1) / 5, ship 0's perspective
+        else if (col < DIN) { obj_comp = col - 1 - 5 * S; obj_slot = j; }
+    }
+    float (*pool)[kPoolStride] = s_w.pool[warp];
+    // a warp takes 8 consecutive games at a time: their pooled vectors make one 16-row tile for the head
+    const int n_groups = (n_games + 7) >> 3;
+    for (int grp = blockIdx.x * kMmaWarps + warp; grp < n_groups; grp += gridDim.x * kMmaWarps) {
+        unsigned live_mask = 0;
+#pragma unroll 1
+        for (int j8 = 0; j8 < 8; j8++) {
+            const int g = grp * 8 + j8;
+            if (g >= n_games) break;                             // (warp-uniform)
+            const size_t tile = (size_t)(g >> 5);
+            const int gl = g & 31;
+            const uint32_t meta = meta_[g];
+            const bool fin = ASTRO_META_FINISHED(meta);
+            const int np = fin ? 0 : (int)ASTRO_META_NP(meta);
+            const int rows = fin ? 0 : np + (int)ASTRO_META_NB(meta);
+            if (rows > 0) live_mask |= 1u << j8;
+            // ship features (x, y, dx, dy, norm_angle(b) / pi), ship 0 then ship 1
+            if (lane < 5 * S) {
+                const int s_ = lane / 5, c = lane % 5;
+                float feat;
+                if (c < 4) feat = (float)reinterpret_cast<const R*>(ships_)[((size_t)tile * (S * 32) + s_ * 32 + gl) * 4 + c];
+                else feat = norm_angle_over_pi((double)reinterpret_cast<const R*>(ship_b_)[(size_t)tile * (S * 32) + s_ * 32 + gl]);
+                s_w.sf[warp][lane] = feat;
+            }
+            __syncwarp();
+            float xa[4], xb[4];                                  // this lane's feature slots, perspective of ship 0 / ship 1
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                xa[j] = xb[j] = 0.f;
+                if (ship_idx[j] >= 0) {
+                    xa[j] = s_w.sf[warp][ship_idx[j]];
+                    xb[j] = s_w.sf[warp][S == 2 ? (ship_idx[j] + 5) % 10 : ship_idx[j]];    // the ship column groups exchanged
+                }
+            }
+            const Body4<R>* pl = reinterpret_cast<const Body4<R>*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32) + gl;
+            const Body4<R>* bl = reinterpret_cast<const Body4<R>*>(bullets_) + tile * (size_t)(32 * K) + tile_list_offset(meta_ + tile * 32, gl, lane);
+            float best[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) best[nt][i] = -3.0e38f;
+            for (int r0 = 0; r0 < rows; r0 += 8) {
+                const int r = r0 + gq;
+                const bool valid = r < rows;
+                if (valid && obj_slot >= 0) {                    // one component of the row's object: the quad covers its 16 bytes
+                    const R* o = reinterpret_cast<const R*>(r < np ? &pl[r * 32] : &bl[r - np]);
+                    const float v = (float)o[obj_comp];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (j == obj_slot) { xa[j] = v; xb[j] = v; }
+                }
+                if (is_flag) xa[0] = xb[0] = (r < np) ? 0.0f : 1.0f;
+                float acc[4][4], nxt[4][4];
+                init_bias<4>(acc, s_w.bias[0], t);               // f0: K = 16 (15 features), two k-steps
+                mma_kstep<4>(acc, xa[0], xb[0], xa[1], xb[1], &s_w.f0[0][0][0], lane);
+                mma_kstep<4>(acc, xa[2], xb[2], xa[3], xb[3], &s_w.f0[1][0][0], lane);
+#pragma unroll
+                for (int layer = 1; layer <= 2; layer++) {       // f[0], f[1]: h = W softsign(h) + b
+                    const float4* wf = layer == 1 ? &s_w.f1[0][0][0] : &s_w.f2[0][0][0];
+                    init_bias<4>(nxt, s_w.bias[layer], t);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)               // the accumulators of n-tile kk are the A fragment of k-step kk
+                        mma_kstep<4>(nxt, softsign(acc[kk][0]), softsign(acc[kk][2]), softsign(acc[kk][1]), softsign(acc[kk][3]), wf + kk * 128, lane);
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) acc[nt][i] = nxt[nt][i];
+                }
+                if (valid) {
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) best[nt][i] = fmaxf(best[nt][i], acc[nt][i]);
+                }
+            }
+            // max over the object rows = over the quads: through shared memory, transposed — lane u then holds unit u's
+            // maximum for ship 0's view, and for ship 1's (two passes of 8 accumulators: 1 KB per warp)
+            float pooled[2];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {               // half 0: accumulator entries 0-1 (ship 0's view), 1: entries 2-3
+                s_w.red[warp][gq][t][0] = make_float4(best[0][2 * half], best[0][2 * half + 1], best[1][2 * half], best[1][2 * half + 1]);
+                s_w.red[warp][gq][t][1] = make_float4(best[2][2 * half], best[2][2 * half + 1], best[3][2 * half], best[3][2 * half + 1]);
+                __syncwarp();
+                // unit u = 8 nt + 2 t' + e sits at float index 2 nt + e of lane (quad, t')
+                const int nt_u = lane >> 3, t_u = (lane >> 1) & 3, e_u = lane & 1;
+                float m = -3.0e38f;
+#pragma unroll
+                for (int qd = 0; qd < 8; qd++) m = fmaxf(m, reinterpret_cast<const float*>(&s_w.red[warp][qd][t_u][0])[2 * nt_u + e_u]);
+                pooled[half] = m;
+                __syncwarp();
+            }
+            pool[j8][lane] = pooled[0];
+            pool[8 + j8][lane] = pooled[1];
+        }
+        __syncwarp();
+        // ---- head for the 8 games at once: v[0], v[1] (linear -> softsign) as 16 x 32 x 32 MMA tiles, v0 as 16 x 32 x 8
+        float h1[4][4], h2[4][4], q4[1][4];
+        init_bias<4>(h1, s_w.bias[3], t);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+            mma_kstep<4>(h1, pool[gq][kk * 8 + t], pool[gq + 8][kk * 8 + t], pool[gq][kk * 8 + t + 4], pool[gq + 8][kk * 8 + t + 4], &s_w.v1[kk][0][0], lane);
+        init_bias<4>(h2, s_w.bias[4], t);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+            mma_kstep<4>(h2, softsign(h1[kk][0]), softsign(h1[kk][2]), softsign(h1[kk][1]), softsign(h1[kk][3]), &s_w.v2[kk][0][0], lane);
+        {
+            const float2 b2 = s_w.bias_v0[t];
+            q4[0][0] = b2.x; q4[0][1] = b2.y; q4[0][2] = b2.x; q4[0][3] = b2.y;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+            mma_kstep<1>(q4, softsign(h2[kk][0]), softsign(h2[kk][2]), softsign(h2[kk][1]), softsign(h2[kk][3]), &s_w.v0[kk][0], lane);
+        // this lane: game grp * 8 + gq, outputs 2t and 2t + 1, ship 0's view (entries 0-1) and ship 1's (2-3)
+        const int g = grp * 8 + gq;
+        const bool live = (live_mask >> gq) & 1u;
+        float qv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) qv[i] = (2 * t + (i & 1)) < nout ? tanhf(q4[0][i]) : -2.0f;    // outputs >= nout stay below any tanh value
+        // argmax over the quad's 8 outputs, first maximum like torch.argmax
+        float ma = qv[0], mb = qv[2];
+        int ia = 2 * t, ib = 2 * t;
+        if (qv[1] > ma) { ma = qv[1]; ia = 2 * t + 1; }
+        if (qv[3] > mb) { mb = qv[3]; ib = 2 * t + 1; }
+#pragma unroll
+        for (int d = 1; d <= 2; d <<= 1) {
+            const float oa = __shfl_xor_sync(0xffffffffu, ma, d), ob = __shfl_xor_sync(0xffffffffu, mb, d);
+            const int ja = __shfl_xor_sync(0xffffffffu, ia, d), jb = __shfl_xor_sync(0xffffffffu, ib, d);
+            if (oa > ma || (oa == ma && ja < ia)) { ma = oa; ia = ja; }
+            if (ob > mb || (ob == mb && jb < ib)) { mb = ob; ib = jb; }
+        }
+        if (g < n_games) {
+            if (t == 0 && (ship_mask & 1)) actions[(size_t)g * S] = (uint8_t)(live ? ia : 2);    // finished game: the no-op control
+            if (S == 2 && t == 1 && (ship_mask & 2)) actions[(size_t)g * S + 1] = (uint8_t)(live ? ib : 2);
+            if (q_out) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    if (2 * t + e < nout) {
+                        q_out[((size_t)g * S) * nout + 2 * t + e] = live ? qv[e] : 0.0f;
+                        if (S == 2) q_out[((size_t)g * S + 1) * nout + 2 * t + e] = live ? qv[2 + e] : 0.0f;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }  // groups of this warp
+}
+
+// ------------------------------------------------------------------------------------------
 // explore_kernel: rl.EpsilonGreedy.__call__ (rl.py:10-30) for every ship — the random policy that
 // rl.QBotTrainer lays over the greedy network (rl.py:249-258: action = greedy if greedy is not None
 // else argmax q).  Per ship a two-state process: idle -> a random control 0..4 (randint(0, 5): never 5)
@@ -2396,6 +2675,25 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
     }
     cudaStream_t st = (cudaStream_t)stream;
     const AstroBuffers& u = b->bufs;
+    // the tensor-core kernel is the default; ASTRO_POLICY_MMA=0 selects the CUDA-core kernel (A/B, tests)
+    const char* pm = getenv("ASTRO_POLICY_MMA");
+    const bool use_mma = !(pm && atoi(pm) == 0);
+    if (use_mma) {
+        int sms = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+        int mgrid = ((b->n_games + 7) / 8 + kMmaWarps - 1) / kMmaWarps;      // a warp takes 8 games at a time
+        if (mgrid > sms * ASTRO_MMA_MIN_BLOCKS) mgrid = sms * ASTRO_MMA_MIN_BLOCKS;
+        const int msmem = (int)sizeof(PolicyFrags);
+#define LAUNCH_MMA(R, S_) \
+    do { CUDA_TRY(cudaFuncSetAttribute(policy_mma_kernel<R, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem)); \
+    policy_mma_kernel<R, S_><<<mgrid, kMmaWarps * 32, msmem, st>>>(u.ships, u.ship_b, u.planets, current_bullets(b), u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask, b->d_pol); } while (0)
+        if (b->precision == 32) { if (b->S == 2) LAUNCH_MMA(float, 2); else LAUNCH_MMA(float, 1); }
+        else { if (b->S == 2) LAUNCH_MMA(double, 2); else LAUNCH_MMA(double, 1); }
+#undef LAUNCH_MMA
+        CUDA_TRY(cudaGetLastError());
+        b->launches += 1;
+        return ASTRO_OK;
+    }
 #define LAUNCH_POL(R, S_) \
     policy_kernel<R, S_><<<grid, kPolWarps * 32, 0, st>>>(u.ships, u.ship_b, u.planets, current_bullets(b), u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask, b->d_pol)
     if (b->precision == 32) {
