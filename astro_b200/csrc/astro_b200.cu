@@ -1282,7 +1282,7 @@ policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
 // ------------------------------------------------------------------------------------------
 constexpr int kMmaWarps = 4;
 constexpr int kPoolStride = 36;      // floats per row of the pooled tile (32 + 4: the A-fragment loads hit 32 different banks)
-struct PolicyFrags {                 // per CTA, in (dynamic) shared memory; B fragments {b0_hi, b1_hi, b0_lo, b1_lo} per lane
+struct PolicyFragWeights {           // B fragments {b0_hi, b1_hi, b0_lo, b1_lo} per lane, built once by astro_policy_set_weights
     float4 f0[2][4][32];             // [k-step][n-tile][lane]: per-object layers
     float4 f1[4][4][32];
     float4 f2[4][4][32];
@@ -1291,6 +1291,9 @@ struct PolicyFrags {                 // per CTA, in (dynamic) shared memory; B f
     float4 v0[4][32];                // head output: one n-tile (nout <= 8)
     float2 bias[5][4][4];            // [f0, f1, f2, v1, v2][n-tile][t] = bias of units 8 nt + 2t, 8 nt + 2t + 1
     float2 bias_v0[4];               // [t] = bias of outputs 2t, 2t + 1
+};
+struct PolicyFrags {                 // per CTA, in (dynamic) shared memory
+    PolicyFragWeights w;             // copied from global memory, 16 bytes per thread and step
     float pool[kMmaWarps][16][kPoolStride];   // per warp: the pooled vectors of 8 games, rows 0-7 ship 0's view, 8-15 ship 1's
     float4 red[kMmaWarps][8][4][2];  // per warp: max-pool exchange, [quad][t][half of the 16 accumulators as 2 float4]
     float sf[kMmaWarps][12];         // per warp: the game's ship features, ship 0 then ship 1
@@ -1323,15 +1326,6 @@ __device__ __forceinline__ void mma_kstep(float (&acc)[NT][4], float x0, float x
         mma_tf32(acc[nt], h0, h1, h2, h3, bh0, bh1);
     }
 }
-// weights w0, w1 as a B-fragment entry: hi = rounded to TF32, lo = the rest rounded to TF32 (once per CTA: the cvt is fine here)
-__device__ __forceinline__ float4 bfrag_entry(float w0, float w1) {
-    uint32_t h0, h1, l0, l1;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(w0));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(w1));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l0) : "f"(__fsub_rn(w0, __uint_as_float(h0))));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l1) : "f"(__fsub_rn(w1, __uint_as_float(h1))));
-    return make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
-}
 template <int NT>
 __device__ __forceinline__ void init_bias(float (&acc)[NT][4], const float2 (*bias)[4], int t) {
 #pragma unroll
@@ -1348,41 +1342,19 @@ template <typename R, int S>
 __global__ void __launch_bounds__(kMmaWarps * 32, ASTRO_MMA_MIN_BLOCKS)
 policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_, const void* __restrict__ planets_,
                   const void* __restrict__ bullets_, const uint32_t* __restrict__ meta_, uint8_t* __restrict__ actions,
-                  float* __restrict__ q_out, int n_games, int K, int nout, int ship_mask, const PolicyWeights* __restrict__ pol) {
+                  float* __restrict__ q_out, int n_games, int K, int nout, int ship_mask, const PolicyFragWeights* __restrict__ frags) {
     constexpr int DIN = 1 + 5 * S + 4;
     extern __shared__ float4 s_dyn[];
-    PolicyFrags& s_w = *reinterpret_cast<PolicyFrags*>(s_dyn);
-    const PolicyWeights& g_pol = *pol;
+    PolicyFrags& s_all = *reinterpret_cast<PolicyFrags*>(s_dyn);
+    const PolicyFragWeights& s_w = s_all.w;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gq = lane >> 2, t = lane & 3;                     // quad = object row of the tile / n column; t = k index
-    // ---- stage the weights as B fragments (hi / lo), once per CTA
-    for (int i = threadIdx.x; i < (2 + 4 + 4 + 4 + 4 + 1) * 4 * 32; i += blockDim.x) {
-        const int l = i & 31, nt = (i >> 5) & 3, kk = i >> 7;   // kk: 0-1 f0, 2-5 f1, 6-9 f2, 10-13 v1, 14-17 v2, 18 v0 (nt = its k-step)
-        const int g_ = l >> 2, t_ = l & 3, n = nt * 8 + g_;
-        if (kk < 2) {                                           // natural K order: columns 8 kk + t, 8 kk + t + 4 (>= DIN: zero)
-            const int c0 = kk * 8 + t_, c1 = c0 + 4;
-            s_w.f0[kk][nt][l] = bfrag_entry(c0 < DIN ? g_pol.f0t[c0][n] : 0.f, c1 < DIN ? g_pol.f0t[c1][n] : 0.f);
-        } else if (kk < 10) {                                   // permuted K order: units 8 k2 + 2t, 8 k2 + 2t + 1 (A = the previous layer's accumulators)
-            const int k2 = (kk - 2) & 3, c0 = k2 * 8 + 2 * t_;
-            if (kk < 6) s_w.f1[k2][nt][l] = bfrag_entry(g_pol.f1t[c0][n], g_pol.f1t[c0 + 1][n]);
-            else s_w.f2[k2][nt][l] = bfrag_entry(g_pol.f2t[c0][n], g_pol.f2t[c0 + 1][n]);
-        } else if (kk < 14) {                                   // v[0]: natural order (A = the pooled tile in shared memory)
-            const int k2 = kk - 10, c0 = k2 * 8 + t_;
-            s_w.v1[k2][nt][l] = bfrag_entry(g_pol.v1t[c0][n], g_pol.v1t[c0 + 4][n]);
-        } else if (kk < 18) {                                   // v[1]: permuted
-            const int k2 = kk - 14, c0 = k2 * 8 + 2 * t_;
-            s_w.v2[k2][nt][l] = bfrag_entry(g_pol.v2t[c0][n], g_pol.v2t[c0 + 1][n]);
-        } else {                                                // v0: permuted, one n-tile of 8 outputs (>= nout: zero); here nt is the k-step
-            const int c0 = nt * 8 + 2 * t_;
-            s_w.v0[nt][l] = bfrag_entry(g_pol.v0t[c0][g_], g_pol.v0t[c0 + 1][g_]);
-        }
+    // ---- the weights, already split and fragment-ordered (astro_policy_set_weights): one coalesced copy per CTA
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(frags);
+        uint4* dst = reinterpret_cast<uint4*>(&s_all.w);
+        for (int i = threadIdx.x; i < (int)(sizeof(PolicyFragWeights) / 16); i += blockDim.x) dst[i] = src[i];
     }
-    for (int i = threadIdx.x; i < 5 * 4 * 4; i += blockDim.x) {
-        const int t_ = i & 3, nt = (i >> 2) & 3, layer = i >> 4;
-        const float* bsrc = layer == 0 ? g_pol.f0b : (layer == 1 ? g_pol.f1b : (layer == 2 ? g_pol.f2b : (layer == 3 ? g_pol.v1b : g_pol.v2b)));
-        s_w.bias[layer][nt][t_] = make_float2(bsrc[nt * 8 + 2 * t_], bsrc[nt * 8 + 2 * t_ + 1]);
-    }
-    if (threadIdx.x < 4) s_w.bias_v0[threadIdx.x] = make_float2(g_pol.v0b[2 * threadIdx.x], g_pol.v0b[2 * threadIdx.x + 1]);
     __syncthreads();
     // ---- what this lane's four feature slots (columns t, t + 4, t + 8, t + 12) are: flag / ship feature / object component / zero
     int ship_idx[4], obj_comp = 0, obj_slot = -1;
@@ -1395,7 +1367,7 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
         else if (col <= 5 * S) ship_idx[j] = col - 1;           // feature (col - 1) % 5 of ship (col - 1) / 5, ship 0's perspective
         else if (col < DIN) { obj_comp = col - 1 - 5 * S; obj_slot = j; }
     }
-    float (*pool)[kPoolStride] = s_w.pool[warp];
+    float (*pool)[kPoolStride] = s_all.pool[warp];
     // a warp takes 8 consecutive games at a time: their pooled vectors make one 16-row tile for the head
     const int n_groups = (n_games + 7) >> 3;
     for (int grp = blockIdx.x * kMmaWarps + warp; grp < n_groups; grp += gridDim.x * kMmaWarps) {
@@ -1416,8 +1388,8 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
                 const int s_ = lane / 5, c = lane % 5;
                 float feat;
                 if (c < 4) feat = (float)reinterpret_cast<const R*>(ships_)[((size_t)tile * (S * 32) + s_ * 32 + gl) * 4 + c];
-                else feat = norm_angle_over_pi((double)reinterpret_cast<const R*>(ship_b_)[(size_t)tile * (S * 32) + s_ * 32 + gl]);
-                s_w.sf[warp][lane] = feat;
+                else feat = (float)__ddiv_rn(norm_angle_f64((double)reinterpret_cast<const R*>(ship_b_)[(size_t)tile * (S * 32) + s_ * 32 + gl]), 3.141592653589793);
+                s_all.sf[warp][lane] = feat;
             }
             __syncwarp();
             float xa[4], xb[4];                                  // this lane's feature slots, perspective of ship 0 / ship 1
@@ -1425,8 +1397,8 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
             for (int j = 0; j < 4; j++) {
                 xa[j] = xb[j] = 0.f;
                 if (ship_idx[j] >= 0) {
-                    xa[j] = s_w.sf[warp][ship_idx[j]];
-                    xb[j] = s_w.sf[warp][S == 2 ? (ship_idx[j] + 5) % 10 : ship_idx[j]];    // the ship column groups exchanged
+                    xa[j] = s_all.sf[warp][ship_idx[j]];
+                    xb[j] = s_all.sf[warp][S == 2 ? (ship_idx[j] + 5) % 10 : ship_idx[j]];    // the ship column groups exchanged
                 }
             }
             const Body4<R>* pl = reinterpret_cast<const Body4<R>*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32) + gl;
@@ -1474,14 +1446,14 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
             float pooled[2];
 #pragma unroll
             for (int half = 0; half < 2; half++) {               // half 0: accumulator entries 0-1 (ship 0's view), 1: entries 2-3
-                s_w.red[warp][gq][t][0] = make_float4(best[0][2 * half], best[0][2 * half + 1], best[1][2 * half], best[1][2 * half + 1]);
-                s_w.red[warp][gq][t][1] = make_float4(best[2][2 * half], best[2][2 * half + 1], best[3][2 * half], best[3][2 * half + 1]);
+                s_all.red[warp][gq][t][0] = make_float4(best[0][2 * half], best[0][2 * half + 1], best[1][2 * half], best[1][2 * half + 1]);
+                s_all.red[warp][gq][t][1] = make_float4(best[2][2 * half], best[2][2 * half + 1], best[3][2 * half], best[3][2 * half + 1]);
                 __syncwarp();
                 // unit u = 8 nt + 2 t' + e sits at float index 2 nt + e of lane (quad, t')
                 const int nt_u = lane >> 3, t_u = (lane >> 1) & 3, e_u = lane & 1;
                 float m = -3.0e38f;
 #pragma unroll
-                for (int qd = 0; qd < 8; qd++) m = fmaxf(m, reinterpret_cast<const float*>(&s_w.red[warp][qd][t_u][0])[2 * nt_u + e_u]);
+                for (int qd = 0; qd < 8; qd++) m = fmaxf(m, reinterpret_cast<const float*>(&s_all.red[warp][qd][t_u][0])[2 * nt_u + e_u]);
                 pooled[half] = m;
                 __syncwarp();
             }
@@ -1916,6 +1888,7 @@ struct AstroBatch {
     int64_t launches;
     int32_t policy_nout;  // > 0 once astro_policy_set_weights has been called
     PolicyWeights* d_pol; // this batch's network (astro_policy_set_weights)
+    PolicyFragWeights* d_pol_frags;   // ... as tensor-core B fragments (policy_mma_kernel)
     int32_t* d_src;       // astro_import_games: game -> row map
     char* d_single;       // astro_step_single_host: device staging, in record then out record
     int64_t single_bytes;
@@ -2258,6 +2231,7 @@ int astro_batch_destroy(AstroBatch* b) {
     cudaFree(b->d_fire_bits);
     cudaFree(b->d_pool_rec);
     cudaFree(b->d_pol);
+    cudaFree(b->d_pol_frags);
     cudaFree(b->d_src);
     cudaFree(b->d_single);
     fresh_free(b);
@@ -2652,7 +2626,42 @@ int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n
     memcpy(w->v2b, p, sizeof(w->v2b)); p += kPolW;
     for (int u = 0; u < nout; u++) for (int c = 0; c < kPolW; c++) w->v0t[c][u] = *p++;
     memcpy(w->v0b, p, sizeof(float) * nout);
+    // the same weights as tensor-core B fragments for policy_mma_kernel: split into TF32 hi / lo parts (round to nearest,
+    // ties away: cvt.rna.tf32.f32), input columns in the order the A fragments arrive in (see the kernel)
+    PolicyFragWeights* fw = new (std::nothrow) PolicyFragWeights();
+    if (!fw) { delete w; return fail(ASTRO_E_NOMEM, "out of host memory"); }
+    memset(fw, 0, sizeof(*fw));
+    {
+        auto rna = [](float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; float r; memcpy(&r, &u, 4); return r; };
+        auto entry = [&](float w0, float w1) { const float h0 = rna(w0), h1 = rna(w1); return make_float4(h0, h1, rna(w0 - h0), rna(w1 - h1)); };
+        for (int l = 0; l < 32; l++) {
+            const int g_ = l >> 2, t_ = l & 3;
+            for (int nt = 0; nt < 4; nt++) {
+                const int n = nt * 8 + g_;
+                for (int kk = 0; kk < 2; kk++) {                  // f0: natural K order, columns 8 kk + t, 8 kk + t + 4 (>= din: zero)
+                    const int c0 = kk * 8 + t_, c1 = c0 + 4;
+                    fw->f0[kk][nt][l] = entry(c0 < din ? w->f0t[c0][n] : 0.f, c1 < din ? w->f0t[c1][n] : 0.f);
+                }
+                for (int kk = 0; kk < 4; kk++) {
+                    const int cp = kk * 8 + 2 * t_, cn = kk * 8 + t_;     // permuted (A = accumulators) / natural (A = shared memory)
+                    fw->f1[kk][nt][l] = entry(w->f1t[cp][n], w->f1t[cp + 1][n]);
+                    fw->f2[kk][nt][l] = entry(w->f2t[cp][n], w->f2t[cp + 1][n]);
+                    fw->v1[kk][nt][l] = entry(w->v1t[cn][n], w->v1t[cn + 4][n]);
+                    fw->v2[kk][nt][l] = entry(w->v2t[cp][n], w->v2t[cp + 1][n]);
+                }
+            }
+            for (int kk = 0; kk < 4; kk++) fw->v0[kk][l] = entry(w->v0t[kk * 8 + 2 * t_][g_], w->v0t[kk * 8 + 2 * t_ + 1][g_]);
+        }
+        const float* biases[5] = {w->f0b, w->f1b, w->f2b, w->v1b, w->v2b};
+        for (int layer = 0; layer < 5; layer++)
+            for (int nt = 0; nt < 4; nt++)
+                for (int t_ = 0; t_ < 4; t_++) fw->bias[layer][nt][t_] = make_float2(biases[layer][nt * 8 + 2 * t_], biases[layer][nt * 8 + 2 * t_ + 1]);
+        for (int t_ = 0; t_ < 4; t_++) fw->bias_v0[t_] = make_float2(w->v0b[2 * t_], w->v0b[2 * t_ + 1]);
+    }
     cudaError_t e = b->d_pol ? cudaSuccess : cudaMalloc(&b->d_pol, sizeof(PolicyWeights));
+    if (e == cudaSuccess && !b->d_pol_frags) e = cudaMalloc(&b->d_pol_frags, sizeof(PolicyFragWeights));
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_pol_frags, fw, sizeof(*fw), cudaMemcpyHostToDevice);
+    delete fw;
     // (pageable source: the copy has left `w` when the call returns; stream-ordered before later launches)
     if (e == cudaSuccess) e = cudaMemcpy(b->d_pol, w, sizeof(*w), cudaMemcpyHostToDevice);
     delete w;
@@ -2686,7 +2695,7 @@ int astro_policy_controls(AstroBatch* b, uint8_t* actions, float* q_out, int32_t
         const int msmem = (int)sizeof(PolicyFrags);
 #define LAUNCH_MMA(R, S_) \
     do { CUDA_TRY(cudaFuncSetAttribute(policy_mma_kernel<R, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem)); \
-    policy_mma_kernel<R, S_><<<mgrid, kMmaWarps * 32, msmem, st>>>(u.ships, u.ship_b, u.planets, current_bullets(b), u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask, b->d_pol); } while (0)
+    policy_mma_kernel<R, S_><<<mgrid, kMmaWarps * 32, msmem, st>>>(u.ships, u.ship_b, u.planets, current_bullets(b), u.meta, actions, q_out, b->n_games, b->K, b->policy_nout, ship_mask, b->d_pol_frags); } while (0)
         if (b->precision == 32) { if (b->S == 2) LAUNCH_MMA(float, 2); else LAUNCH_MMA(float, 1); }
         else { if (b->S == 2) LAUNCH_MMA(double, 2); else LAUNCH_MMA(double, 1); }
 #undef LAUNCH_MMA

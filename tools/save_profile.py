@@ -1,7 +1,11 @@
 #!/usr/bin/env python
-"""Save the judged summaries of an ncu report under profiles/. usage: tools/save_profile.py rep tag "<note>" """
+"""Save the judged summaries of an ncu report under profiles/.
+usage: tools/save_profile.py rep tag "<note>" [ticks_per_launch]
+With ticks_per_launch the summary is also filed in profiles/tick_kernel_ncu_summary.json under that key: bench.py prints
+`roofline.traffic` only beside a launch of the shape it was measured on."""
 import csv, io, json, os, subprocess, sys
 rep, tag, note = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else '')
+key = sys.argv[4] if len(sys.argv) > 4 else None
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -17,8 +21,18 @@ summ = dict(kernel=r[hdr.index('Kernel Name')], note=note,
             registers_per_thread=get('launch__registers_per_thread'),
             dram_throughput_pct_of_nominal_peak=get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
             issue_active_pct=get('smsp__issue_active.avg.pct_of_peak_sustained_active'),
-            achieved_occupancy_pct=get('sm__warps_active.avg.pct_of_peak_sustained_active'))
-json.dump(summ, open(os.path.join(root, 'profiles', 'tick_kernel_ncu_summary.json'), 'w'), indent=1)
+            achieved_occupancy_pct=get('sm__warps_active.avg.pct_of_peak_sustained_active'),
+            l2_hit_pct=get('lts__t_sector_hit_rate.pct'))
+if key is not None:
+    path = os.path.join(root, 'profiles', 'tick_kernel_ncu_summary.json')
+    try:
+        table = json.load(open(path))
+        if 'kernel' in table:          # (the round-1 file held one summary)
+            table = {}
+    except Exception:
+        table = {}
+    table[str(int(key))] = summ
+    json.dump(table, open(path, 'w'), indent=1)
 json.dump(summ, open(os.path.join(root, 'profiles', '%s_ncu_summary.json' % tag), 'w'), indent=1)
 det = subprocess.run(['ncu', '-i', rep, '--page', 'details', '--csv'], capture_output=True, text=True).stdout
 drows = list(csv.reader(io.StringIO(det))); dh = drows[0]
