@@ -28,6 +28,7 @@ Numbers on the JSON line:
             copies inside the timed region, pipelined; `closed_loop_value` = step_host: copy in, tick, copy out,
             synchronise on every tick; `byte_form_value` = the round-1 forms (2 + 1 B/game).
   strong    BASELINE configs[3] as stated: 1,048,576 games in TOTAL over the N GPUs (the headline weak-scales).
+  fresh_games  the headline loop with pool-free re-creation (every ended game gets the next generate_configs seed).
   rollout   BASELINE configs[4]: 16,384 games x 1,000 ticks, observation -> astro.rl network -> step (rank 0).
   drop_in   astro_b200.core.step on one game, microseconds per call (BASELINE configs[0] shape).
   cpu_baseline  the oracle port of the reference loop on all host cores (rank 0, every N).
@@ -604,6 +605,35 @@ def run_ours(args):
         del sr
         torch.cuda.empty_cache()
 
+    # fresh-game mode (no reset pool: every re-creation takes the next config of the generate_configs stream), same loop
+    fresh = None
+    if not args.no_fresh:
+        gf = BatchedGames(cfg, n, bullet_cap=K, precision=32, device=local, seed=args.seed, first_game=plan['first_game'])
+        gf.enable_fresh_games(quota=48, skip=rank * (1 << 26))
+        gf.reset_all()
+        f_flags = nat.TICK_AUTO_RESET | args.tick_flags
+        for _ in range(min(args.preroll, 300) // 20):
+            gf.step_many_raw(0, 0, 20, f_flags)
+        gf.stats_tensor(clear=True)
+        f_steps = max(args.fuse, (min(max(args.steps, 200), 640) // args.fuse) * args.fuse)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(f_steps // args.fuse):
+            gf.step_many_raw(0, 0, args.fuse, f_flags)
+        e1.record()
+        torch.cuda.synchronize()
+        f_ms = max(gather_ms(e0.elapsed_time(e1)))
+        f_st = gf.stats(clear=True)
+        fresh = dict(value=world * f_st['env_steps'] / (f_ms * 1e-3) if world == 1 else world * n * f_steps / (f_ms * 1e-3), unit=UNIT,
+                     ms_per_step=f_ms / f_steps, steps=f_steps, ticks_per_launch=args.fuse, quota=48, awaiting=f_st['awaiting'],
+                     episodes_rank0=f_st['episodes'],
+                     note='astro_fresh_games_enable: every game that ends is re-created by core.create from the NEXT seed of '
+                          'core.generate_configs (host MT19937 = numpy RandomState); controls from the device counter stream')
+        del gf
+        torch.cuda.empty_cache()
+
     if rank == 0:
         rollout = None if args.no_rollout else config5_rollout(args, local, pool)
         drop_in = None if args.no_rollout else drop_in_step(args)
@@ -612,7 +642,7 @@ def run_ours(args):
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f32', data='synthetic', config=workload_config(args), roofline=roofline,
                     cpu_baseline=cpu, clocks=clocks, e2e=e2e, gpu_launches=timed_launches,
-                    per_tick_launch=per_tick, per_rank_ms=per_rank_ms, collective_us=collective_us, strong=strong, rollout=rollout, drop_in=drop_in,
+                    per_tick_launch=per_tick, per_rank_ms=per_rank_ms, collective_us=collective_us, strong=strong, fresh_games=fresh, rollout=rollout, drop_in=drop_in,
                     episode_stats={k: total[k] for k in ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'overflow', 'bad_controls')})
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -639,6 +669,7 @@ def main():
     ap.add_argument('--rollout-games', type=int, default=16384)
     ap.add_argument('--rollout-ticks', type=int, default=1000)
     ap.add_argument('--no-rollout', action='store_true', help='skip the config #5 / drop-in legs')
+    ap.add_argument('--no-fresh', action='store_true', help='skip the fresh-game-mode leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--fuse', type=int, default=64, help='ticks per launch of the timed loop (astro_tick_many); 1 = one launch per tick')
     ap.add_argument('--tick-flags', type=int, default=0, help='extra ASTRO_TICK_* bits (kernel A/B)')

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of libraries (default + build_ab/*.so): fused value and per-tick-launch value of bench.py (GPU box)
 run() { name=$1; shift
-  out=$(env "$@" python bench.py --steps 640 --warmup 64 --no-cpu-baseline --no-rollout --strong-total 0 --e2e-steps 4 2>&1 | tail -1)
+  out=$(env "$@" python bench.py --steps 640 --warmup 64 --no-cpu-baseline --no-rollout --no-fresh --strong-total 0 --e2e-steps 4 2>&1 | tail -1)
   echo "$name $(echo "$out" | python -c "
 import json,sys
 try:
