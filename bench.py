@@ -634,6 +634,10 @@ def run_ours(args):
         del gf
         torch.cuda.empty_cache()
 
+    # the other ranks are done: they leave before rank 0 times the CPU legs (a rank waiting in a barrier spins on a core)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0:
         rollout = None if args.no_rollout else config5_rollout(args, local, pool)
         drop_in = None if args.no_rollout else drop_in_step(args)
@@ -645,9 +649,6 @@ def run_ours(args):
                     per_tick_launch=per_tick, per_rank_ms=per_rank_ms, collective_us=collective_us, strong=strong, fresh_games=fresh, rollout=rollout, drop_in=drop_in,
                     episode_stats={k: total[k] for k in ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'overflow', 'bad_controls')})
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 def main():
@@ -664,7 +665,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=256)
     ap.add_argument('--e2e-call', type=int, default=128, help='ticks per rollout_host call of the e2e leg')
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
-    ap.add_argument('--ref-seconds', type=float, default=3.0, help='--impl reference: length of the timed region')
+    ap.add_argument('--ref-seconds', type=float, default=4.0, help='--impl reference: length of the timed region')
     ap.add_argument('--strong-total', type=int, default=1 << 20, help='BASELINE configs[3] as stated: games in total over all GPUs (0 = skip)')
     ap.add_argument('--rollout-games', type=int, default=16384)
     ap.add_argument('--rollout-ticks', type=int, default=1000)
