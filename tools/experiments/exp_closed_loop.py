@@ -1,6 +1,6 @@
 """Closed-loop host stepping (astro_tick_host) under different slice counts / io forms: us per tick at 1M games."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from astro_b200 import core
 from astro_b200.batched import BatchedGames

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """astro_tick_many against one launch per tick: us per tick for T ticks per launch (1M games, stationary population)."""
 import argparse, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from astro_b200 import core
 from astro_b200 import _native as nat

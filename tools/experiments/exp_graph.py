@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Experiment: back-to-back astro_tick launches vs the same ticks replayed from a CUDA graph."""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from astro_b200 import core
 from astro_b200 import _native as nat

@@ -2,7 +2,7 @@
 """Is the tick's throughput limit per SM or device-wide?  Time the tick with n SMs taken away by a hog kernel
 (tools/ubench/sm_hog.cu, bounded to 60 ms): per-SM limit -> time scales with 148 / (148 - n); device-wide -> it does not."""
 import ctypes, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from astro_b200 import core
 from astro_b200 import _native as nat

@@ -2,7 +2,7 @@
 """Kernel experiments: time the tick alone for a chosen config / batch shape and report algorithmic GB/s.
 usage: tools/exp_tick.py [--games N] [--cap K] [--reload-time T] [--solo] [--steps S] [--flags F]"""
 import argparse, json, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from astro_b200 import core
 from astro_b200 import _native as nat

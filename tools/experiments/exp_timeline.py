@@ -2,7 +2,7 @@
 """Phase timeline of the tick kernel (needs a library built with -DASTRO_TIMELINE, passed via ASTRO_B200_LIB):
 every warp stamps clock64() at its phase boundaries; prints mean / percentiles of each phase in SM cycles."""
 import argparse, ctypes, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from astro_b200 import core
 from astro_b200 import _native as nat
