@@ -11,6 +11,7 @@
 // the warp (see the layout comment in the header).  HBM-bound; no tensor cores (no contraction).
 #include "../../include/astro_b200.h"
 #include "astro_device.cuh"
+#include <cuda_fp16.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -1282,13 +1283,25 @@ policy_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_,
 // ------------------------------------------------------------------------------------------
 constexpr int kMmaWarps = 4;
 constexpr int kPoolStride = 36;      // floats per row of the pooled tile (32 + 4: the A-fragment loads hit 32 different banks)
+// Two forms of the MMA, selected at build time:
+//   ASTRO_POLICY_F16 = 1 (default)  mma.sync.m16n8k16 FP16 operands (HMMA.16816.F32): 16 input columns per instruction
+//   ASTRO_POLICY_F16 = 0            mma.sync.m16n8k8  TF32 operands (HMMA.1688.F32.TF32): 8 per instruction
+// Both carry 11 significant bits per operand and use the same three-product split (x = hi + lo), so the results agree to
+// fp32 level; the FP16 form halves the MMA and B-fragment-load counts — the TF32 form was bound by the tensor pipe's issue
+// interval.  FP16's range (|x| < 65,504; lo parts below 6e-5 lose relative precision, 3e-8 absolute) is ample for this
+// network: activations sit in (-1, 1), features and pre-activations within a few units.
+#ifndef ASTRO_POLICY_F16
+#define ASTRO_POLICY_F16 1
+#endif
+constexpr int kKs0 = ASTRO_POLICY_F16 ? 1 : 2;   // k-steps of the first layer (16 input columns)
+constexpr int kKs = ASTRO_POLICY_F16 ? 2 : 4;    // k-steps of a 32-wide layer
 struct PolicyFragWeights {           // B fragments {b0_hi, b1_hi, b0_lo, b1_lo} per lane, built once by astro_policy_set_weights
-    float4 f0[2][4][32];             // [k-step][n-tile][lane]: per-object layers
-    float4 f1[4][4][32];
-    float4 f2[4][4][32];
-    float4 v1[4][4][32];             // head
-    float4 v2[4][4][32];
-    float4 v0[4][32];                // head output: one n-tile (nout <= 8)
+    float4 f0[kKs0][4][32];          // [k-step][n-tile][lane]: per-object layers
+    float4 f1[kKs][4][32];
+    float4 f2[kKs][4][32];
+    float4 v1[kKs][4][32];           // head
+    float4 v2[kKs][4][32];
+    float4 v0[kKs][32];              // head output: one n-tile (nout <= 8)
     float2 bias[5][4][4];            // [f0, f1, f2, v1, v2][n-tile][t] = bias of units 8 nt + 2t, 8 nt + 2t + 1
     float2 bias_v0[4];               // [t] = bias of outputs 2t, 2t + 1
 };
@@ -1312,7 +1325,54 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// one k-step of a layer for NT n-tiles: A = (x0, x1, x2, x3) in fp32, split here; B from shared memory
+#if ASTRO_POLICY_F16
+// two fp32 values -> the FP16 pair (hi) and the FP16 pair of what that dropped (lo); lower half = the even column
+__device__ __forceinline__ void split_f16x2(float xe, float xo, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(xo), "f"(xe));
+    float he, ho;
+    asm("{ .reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(he), "=f"(ho) : "r"(hi));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(__fsub_rn(xo, ho)), "f"(__fsub_rn(xe, he)));
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// one k-step (16 input columns) for NT n-tiles.  x = this lane's eight A values: (row g: columns 2t, 2t+1), (row g+8: same),
+// (row g: columns 2t+8, 2t+9), (row g+8: same) — for a 32-wide layer exactly the accumulators of n-tiles 2 kk and 2 kk + 1.
+template <int NT>
+__device__ __forceinline__ void mma_kstep16(float (&acc)[NT][4], const float (&x)[8], const float4* __restrict__ bfrag, int lane) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) split_f16x2(x[2 * i], x[2 * i + 1], h[i], l[i]);
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        const float4 b = bfrag[nt * 32 + lane];
+        const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y), bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
+        mma_f16(acc[nt], l[0], l[1], l[2], l[3], bh0, bh1);      // small terms first
+        mma_f16(acc[nt], h[0], h[1], h[2], h[3], bl0, bl1);
+        mma_f16(acc[nt], h[0], h[1], h[2], h[3], bh0, bh1);
+    }
+}
+// a 32-wide layer: out = bias + W act(in), in / out in the accumulator layout
+template <int NT, bool ACT>
+__device__ __forceinline__ void mma_layer(float (&out)[NT][4], const float (&in)[4][4], const float4* __restrict__ wf, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float v = in[2 * kk + (i >> 2)][i & 3];
+            x[i] = ACT ? softsign(v) : v;
+        }
+        mma_kstep16<NT>(out, x, wf + kk * NT * 32, lane);
+    }
+}
+#else
+template <int NT, bool ACT>
+__device__ __forceinline__ void mma_layer(float (&out)[NT][4], const float (&in)[4][4], const float4* __restrict__ wf, int lane);
+#endif
+// (TF32 form) one k-step of a layer for NT n-tiles: A = (x0, x1, x2, x3) in fp32, split here; B from shared memory
 template <int NT>
 __device__ __forceinline__ void mma_kstep(float (&acc)[NT][4], float x0, float x1, float x2, float x3, const float4* __restrict__ bfrag, int lane) {
     uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
@@ -1326,6 +1386,16 @@ __device__ __forceinline__ void mma_kstep(float (&acc)[NT][4], float x0, float x
         mma_tf32(acc[nt], h0, h1, h2, h3, bh0, bh1);
     }
 }
+#if !ASTRO_POLICY_F16
+template <int NT, bool ACT>
+__device__ __forceinline__ void mma_layer(float (&out)[NT][4], const float (&in)[4][4], const float4* __restrict__ wf, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {     // the accumulators of n-tile kk are the A fragment of k-step kk (input columns permuted to match)
+        const float a = in[kk][0], b = in[kk][2], c = in[kk][1], d = in[kk][3];
+        mma_kstep<NT>(out, ACT ? softsign(a) : a, ACT ? softsign(b) : b, ACT ? softsign(c) : c, ACT ? softsign(d) : d, wf + kk * NT * 32, lane);
+    }
+}
+#endif
 template <int NT>
 __device__ __forceinline__ void init_bias(float (&acc)[NT][4], const float2 (*bias)[4], int t) {
 #pragma unroll
@@ -1357,15 +1427,16 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
     }
     __syncthreads();
     // ---- what this lane's four feature slots (columns t, t + 4, t + 8, t + 12) are: flag / ship feature / object component / zero
-    int ship_idx[4], obj_comp = 0, obj_slot = -1;
-    bool is_flag = false;
+    // (FP16 form: columns 2t, 2t + 1, 2t + 8, 2t + 9 — one k-step of 16; TF32 form: t, t + 4, t + 8, t + 12 — two of 8)
+    int ship_idx[4], obj_idx[4];
+    bool is_flag = false, any_obj = false;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int col = t + 4 * j;
-        ship_idx[j] = -1;
-        if (col == 0) is_flag = true;
+        const int col = ASTRO_POLICY_F16 ? 2 * t + (j & 1) + 8 * (j >> 1) : t + 4 * j;
+        ship_idx[j] = obj_idx[j] = -1;
+        if (col == 0) is_flag = true;                           // (slot 0 of lane t = 0 in both forms)
         else if (col <= 5 * S) ship_idx[j] = col - 1;           // feature (col - 1) % 5 of ship (col - 1) / 5, ship 0's perspective
-        else if (col < DIN) { obj_comp = col - 1 - 5 * S; obj_slot = j; }
+        else if (col < DIN) { obj_idx[j] = col - 1 - 5 * S; any_obj = true; }
     }
     float (*pool)[kPoolStride] = s_all.pool[warp];
     // a warp takes 8 consecutive games at a time: their pooled vectors make one 16-row tile for the head
@@ -1411,24 +1482,28 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
             for (int r0 = 0; r0 < rows; r0 += 8) {
                 const int r = r0 + gq;
                 const bool valid = r < rows;
-                if (valid && obj_slot >= 0) {                    // one component of the row's object: the quad covers its 16 bytes
+                if (valid && any_obj) {                          // this lane's component(s) of the row's object: the quad covers its 16 bytes
                     const R* o = reinterpret_cast<const R*>(r < np ? &pl[r * 32] : &bl[r - np]);
-                    const float v = (float)o[obj_comp];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (j == obj_slot) { xa[j] = v; xb[j] = v; }
+                    for (int j = 0; j < 4; j++) if (obj_idx[j] >= 0) { const float v = (float)o[obj_idx[j]]; xa[j] = v; xb[j] = v; }
                 }
                 if (is_flag) xa[0] = xb[0] = (r < np) ? 0.0f : 1.0f;
                 float acc[4][4], nxt[4][4];
-                init_bias<4>(acc, s_w.bias[0], t);               // f0: K = 16 (15 features), two k-steps
+                init_bias<4>(acc, s_w.bias[0], t);               // f0: K = 16 (15 features)
+#if ASTRO_POLICY_F16
+                {
+                    const float x0[8] = {xa[0], xa[1], xb[0], xb[1], xa[2], xa[3], xb[2], xb[3]};
+                    mma_kstep16<4>(acc, x0, &s_w.f0[0][0][0], lane);
+                }
+#else
                 mma_kstep<4>(acc, xa[0], xb[0], xa[1], xb[1], &s_w.f0[0][0][0], lane);
                 mma_kstep<4>(acc, xa[2], xb[2], xa[3], xb[3], &s_w.f0[1][0][0], lane);
+#endif
 #pragma unroll
                 for (int layer = 1; layer <= 2; layer++) {       // f[0], f[1]: h = W softsign(h) + b
                     const float4* wf = layer == 1 ? &s_w.f1[0][0][0] : &s_w.f2[0][0][0];
                     init_bias<4>(nxt, s_w.bias[layer], t);
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++)               // the accumulators of n-tile kk are the A fragment of k-step kk
-                        mma_kstep<4>(nxt, softsign(acc[kk][0]), softsign(acc[kk][2]), softsign(acc[kk][1]), softsign(acc[kk][3]), wf + kk * 128, lane);
+                    mma_layer<4, true>(nxt, acc, wf, lane);
 #pragma unroll
                     for (int nt = 0; nt < 4; nt++)
 #pragma unroll
@@ -1464,20 +1539,26 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
         // ---- head for the 8 games at once: v[0], v[1] (linear -> softsign) as 16 x 32 x 32 MMA tiles, v0 as 16 x 32 x 8
         float h1[4][4], h2[4][4], q4[1][4];
         init_bias<4>(h1, s_w.bias[3], t);
+#if ASTRO_POLICY_F16
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+            const float2 p0 = *reinterpret_cast<const float2*>(&pool[gq][16 * kk + 2 * t]), p1 = *reinterpret_cast<const float2*>(&pool[gq + 8][16 * kk + 2 * t]);
+            const float2 p2 = *reinterpret_cast<const float2*>(&pool[gq][16 * kk + 2 * t + 8]), p3 = *reinterpret_cast<const float2*>(&pool[gq + 8][16 * kk + 2 * t + 8]);
+            const float x[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+            mma_kstep16<4>(h1, x, &s_w.v1[kk][0][0], lane);
+        }
+#else
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)
             mma_kstep<4>(h1, pool[gq][kk * 8 + t], pool[gq + 8][kk * 8 + t], pool[gq][kk * 8 + t + 4], pool[gq + 8][kk * 8 + t + 4], &s_w.v1[kk][0][0], lane);
+#endif
         init_bias<4>(h2, s_w.bias[4], t);
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++)
-            mma_kstep<4>(h2, softsign(h1[kk][0]), softsign(h1[kk][2]), softsign(h1[kk][1]), softsign(h1[kk][3]), &s_w.v2[kk][0][0], lane);
+        mma_layer<4, true>(h2, h1, &s_w.v2[0][0][0], lane);
         {
             const float2 b2 = s_w.bias_v0[t];
             q4[0][0] = b2.x; q4[0][1] = b2.y; q4[0][2] = b2.x; q4[0][3] = b2.y;
         }
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++)
-            mma_kstep<1>(q4, softsign(h2[kk][0]), softsign(h2[kk][2]), softsign(h2[kk][1]), softsign(h2[kk][3]), &s_w.v0[kk][0], lane);
+        mma_layer<1, true>(q4, h2, &s_w.v0[0][0], lane);
         // this lane: game grp * 8 + gq, outputs 2t and 2t + 1, ship 0's view (entries 0-1) and ship 1's (2-3)
         const int g = grp * 8 + gq;
         const bool live = (live_mask >> gq) & 1u;
@@ -2632,6 +2713,39 @@ int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n
     if (!fw) { delete w; return fail(ASTRO_E_NOMEM, "out of host memory"); }
     memset(fw, 0, sizeof(*fw));
     {
+#if ASTRO_POLICY_F16
+        // FP16 pairs: a fragment register holds input columns (k, k + 1), the even one in the low half; hi = the weight rounded
+        // to FP16, lo = what that dropped, rounded to FP16
+        auto pair = [](float we, float wo, uint32_t& hi, uint32_t& lo) {
+            const __half he = __float2half_rn(we), ho = __float2half_rn(wo);
+            const __half le = __float2half_rn(we - __half2float(he)), lo_ = __float2half_rn(wo - __half2float(ho));
+            hi = (uint32_t)__half_as_ushort(he) | ((uint32_t)__half_as_ushort(ho) << 16);
+            lo = (uint32_t)__half_as_ushort(le) | ((uint32_t)__half_as_ushort(lo_) << 16);
+        };
+        auto entry16 = [&](auto&& weight, int k0) {             // b0: input columns k0, k0 + 1; b1: k0 + 8, k0 + 9
+            uint32_t h0, l0, h1, l1;
+            pair(weight(k0), weight(k0 + 1), h0, l0);
+            pair(weight(k0 + 8), weight(k0 + 9), h1, l1);
+            float4 r;
+            memcpy(&r.x, &h0, 4); memcpy(&r.y, &h1, 4); memcpy(&r.z, &l0, 4); memcpy(&r.w, &l1, 4);
+            return r;
+        };
+        for (int l = 0; l < 32; l++) {
+            const int g_ = l >> 2, t_ = l & 3;
+            for (int nt = 0; nt < 4; nt++) {
+                const int n = nt * 8 + g_;
+                fw->f0[0][nt][l] = entry16([&](int c) { return c < din ? w->f0t[c][n] : 0.f; }, 2 * t_);
+                for (int kk = 0; kk < 2; kk++) {
+                    const int k0 = 16 * kk + 2 * t_;
+                    fw->f1[kk][nt][l] = entry16([&](int c) { return w->f1t[c][n]; }, k0);
+                    fw->f2[kk][nt][l] = entry16([&](int c) { return w->f2t[c][n]; }, k0);
+                    fw->v1[kk][nt][l] = entry16([&](int c) { return w->v1t[c][n]; }, k0);
+                    fw->v2[kk][nt][l] = entry16([&](int c) { return w->v2t[c][n]; }, k0);
+                }
+            }
+            for (int kk = 0; kk < 2; kk++) fw->v0[kk][l] = entry16([&](int c) { return w->v0t[c][g_]; }, 16 * kk + 2 * t_);
+        }
+#else
         auto rna = [](float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; float r; memcpy(&r, &u, 4); return r; };
         auto entry = [&](float w0, float w1) { const float h0 = rna(w0), h1 = rna(w1); return make_float4(h0, h1, rna(w0 - h0), rna(w1 - h1)); };
         for (int l = 0; l < 32; l++) {
@@ -2652,6 +2766,7 @@ int astro_policy_set_weights(AstroBatch* b, const float* weights_host, int32_t n
             }
             for (int kk = 0; kk < 4; kk++) fw->v0[kk][l] = entry(w->v0t[kk * 8 + 2 * t_][g_], w->v0t[kk * 8 + 2 * t_ + 1][g_]);
         }
+#endif
         const float* biases[5] = {w->f0b, w->f1b, w->f2b, w->v1b, w->v2b};
         for (int layer = 0; layer < 5; layer++)
             for (int nt = 0; nt < 4; nt++)
