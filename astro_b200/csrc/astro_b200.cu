@@ -69,6 +69,8 @@ struct TickParams {
     uint32_t* game_pos;               //   [n_games] position in the generate_configs stream of each game's current episode
     int32_t quota, pad_;
     const uint32_t* step_base;        // captured launches (the bot loop as a CUDA graph): stream step = *step_base + step
+    int32_t bot_modes, pad2_;         // bots evaluated inside the tick (tick_f32_kernel<..., BOT>): ASTRO_BOT_* of ship s in bits 4s..4s+3
+    ScriptParams script;
     Consts c;
 };
 
@@ -646,38 +648,6 @@ observe_kernel(const void* __restrict__ ships_, const void* __restrict__ ship_b_
 // Quirk kept: inside _danger the parameter `b` (my bearing) is shadowed by the quadratic
 // coefficient (script.py:54), so `rotation` uses that coefficient.
 // ------------------------------------------------------------------------------------------
-struct ScriptParams {
-    double radius;           // planet_radius + ship_radius                  script.py:53
-    double avoid_distance, avoid_threshold;
-    double ship_thrust, ship_rspeed, bullet_speed, ship_radius;
-    int32_t solo, n_games;
-};
-
-// fmod(a, m) for m > 0 and |a / m| < 2^52, exact like the library routine but in a few operations: with
-// the right integer quotient q, a - q m is representable (it is the result) and fma(-q, m, a) rounds
-// once, i.e. not at all; a quotient off by one after the division's rounding is corrected and redone.
-__device__ __forceinline__ double fmod_small(double a, double m) {
-    const double x = fabs(a);
-    double q = floor(__ddiv_rn(x, m));
-    double r = fma(-q, m, x);
-    if (r < 0.0) { q -= 1.0; r = fma(-q, m, x); }
-    else if (r >= m) { q += 1.0; r = fma(-q, m, x); }
-    return copysign(r, a);   // sign of the dividend (C fmod), -0.0 kept
-}
-__device__ __forceinline__ double norm_angle_f64(double b) {  // util.norm_angle, util.py:125-132
-    const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
-    const double a = __dadd_rn(b, PI);
-    double m = fmod_small(a, TWO_PI);          // numpy's floored remainder (divisor > 0)
-    if (m != 0.0) { if (m < 0.0) m = __dadd_rn(m, TWO_PI); } else m = 0.0;
-    return __dsub_rn(m, PI);
-}
-__device__ __forceinline__ int fly_to(double target, double my_b, double t, bool fwd) {  // script.py:30-39
-    const double angle = norm_angle_f64(__dsub_rn(target, my_b));
-    if (angle < -t) return 0;
-    if (t < angle) return 4;
-    return fwd ? 3 : 2;
-}
-
 // thread = one ship of one game (its own perspective).  The cheap part of _danger — two square
 // roots, two divisions, the discriminant — runs for every planet without divergence and leaves a
 // bit mask of the planets on a collision course; only those go through the atan2 / norm_angle
@@ -703,64 +673,16 @@ __global__ void __launch_bounds__(128, ASTRO_SCRIPT_MIN_BLOCKS) script_kernel(co
     }
     const int np = (int)ASTRO_META_NP(meta);
     const B4 mv = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + me * 32 + lane];
-    const double my[5] = {(double)mv.x, (double)mv.y, (double)mv.dx, (double)mv.dy,
-                          (double)reinterpret_cast<const R*>(ship_b_)[tile * (S * 32) + me * 32 + lane]};
-    unsigned cand = 0;
-    double cx0[ASTRO_MAX_PLANETS], cx1[ASTRO_MAX_PLANETS], cb[ASTRO_MAX_PLANETS], csd[ASTRO_MAX_PLANETS], cspeed[ASTRO_MAX_PLANETS];
-    const double ra = __dadd_rn(q.radius, q.avoid_distance);
-    const double ra2 = __dmul_rn(ra, ra);
+    const R mb = reinterpret_cast<const R*>(ship_b_)[tile * (S * 32) + me * 32 + lane];
+    B4 pl[ASTRO_MAX_PLANETS];
 #pragma unroll
     for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
-        cx0[j] = cx1[j] = cb[j] = csd[j] = cspeed[j] = 0.0;
-        if (j < np) {
-            const B4 v = reinterpret_cast<const B4*>(planets_)[tile * (ASTRO_MAX_PLANETS * 32) + j * 32 + lane];
-            const double x0 = __dsub_rn(my[0], (double)v.x), x1 = __dsub_rn(my[1], (double)v.y);
-            const double v0 = __dsub_rn(my[2], (double)v.dx), v1 = __dsub_rn(my[3], (double)v.dy);
-            const double speed = sqrt(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)));   // util.mag(dx)
-            const double den = __dadd_rn(speed, 1e-12);
-            const double n0 = __ddiv_rn(v0, den), n1 = __ddiv_rn(v1, den);                   // util.norm(dx)
-            const double b = __dmul_rn(2.0, __dadd_rn(__dmul_rn(n0, x0), __dmul_rn(n1, x1)));
-            const double mx = sqrt(__dadd_rn(__dmul_rn(x0, x0), __dmul_rn(x1, x1)));
-            const double cc = __dsub_rn(__dmul_rn(mx, mx), ra2);
-            const double det = __dsub_rn(__dmul_rn(b, b), __dmul_rn(4.0, cc));
-            if (0.0 < det) {
-                const double sd = sqrt(det);
-                if (0.0 <= __dadd_rn(-b, sd)) {       // real roots, at least one positive (script.py:57)
-                    cand |= 1u << j;
-                    cx0[j] = x0; cx1[j] = x1; cb[j] = b; csd[j] = sd; cspeed[j] = speed;
-                }
-            }
-        }
+        pl[j] = B4();
+        if (j < np) pl[j] = reinterpret_cast<const B4*>(planets_)[tile * (ASTRO_MAX_PLANETS * 32) + j * 32 + lane];
     }
-    int ctl = -1;
-    while (cand && ctl < 0) {
-        const int j = __ffs(cand) - 1;
-        cand &= cand - 1u;
-        double x0 = cx0[0], x1 = cx1[0], b = cb[0], sd = csd[0], speed = cspeed[0];
-#pragma unroll
-        for (int k = 1; k < ASTRO_MAX_PLANETS; k++)
-            if (j == k) { x0 = cx0[k]; x1 = cx1[k]; b = cb[k]; sd = csd[k]; speed = cspeed[k]; }
-        const double distance = __dsub_rn(-b, sd);
-        const double bear = atan2(x0, x1);                                        // util.bearing(x)
-        const double rotation = fabs(norm_angle_f64(__dsub_rn(bear, b)));         // (`b` shadowed: script.py:54)
-        const double lim = __dmul_rn(__dadd_rn(__ddiv_rn(speed, q.ship_thrust), __ddiv_rn(q.ship_rspeed, rotation)), speed);
-        if (distance < lim) ctl = fly_to(bear, my[4], q.avoid_threshold, true);
-    }
-    if (ctl < 0) {
-        if (q.solo || S < 2) {
-            ctl = 2;
-        } else {
-            const B4 ev = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + ((me + 1) % S) * 32 + lane];
-            const double en[4] = {(double)ev.x, (double)ev.y, (double)ev.dx, (double)ev.dy};
-            const double e0 = __dsub_rn(en[0], my[0]), e1 = __dsub_rn(en[1], my[1]);
-            const double enemy_distance = sqrt(__dadd_rn(__dmul_rn(e0, e0), __dmul_rn(e1, e1)));
-            const double bullet_time = __ddiv_rn(enemy_distance, q.bullet_speed);
-            const double f0 = __dadd_rn(en[0], __dmul_rn(bullet_time, __dsub_rn(en[2], my[2])));
-            const double f1 = __dadd_rn(en[1], __dmul_rn(bullet_time, __dsub_rn(en[3], my[3])));
-            ctl = fly_to(atan2(__dsub_rn(f0, my[0]), __dsub_rn(f1, my[1])), my[4], __ddiv_rn(q.ship_radius, enemy_distance), false);
-        }
-    }
-    actions[idx] = (uint8_t)ctl;
+    B4 ev = B4();
+    if (S == 2 && !q.solo) ev = reinterpret_cast<const B4*>(ships_)[tile * (S * 32) + ((me + 1) % S) * 32 + lane];
+    actions[idx] = (uint8_t)script_decide<R, S>(mv, mb, ev, pl, np, q);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1316,7 +1238,7 @@ struct PolicyFrags {                 // per CTA, in (dynamic) shared memory
 // half a TF32 ulp to lo's bit pattern makes the hardware's truncation of lo a round-to-nearest: what the pair drops is
 // below 2^-22 |x| and unbiased.  (cvt.rna.tf32.f32 runs on the XU pipe at a quarter rate: the split was half of this
 // kernel's time when it went through it.)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+__device__ __forceinline__ void split_tf32 [[maybe_unused]] (float x, uint32_t& hi, uint32_t& lo) {
     hi = __float_as_uint(x);
     lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi & 0xffffe000u))) + 0x1000u;
 }
@@ -1954,6 +1876,8 @@ struct AstroBatch {
     cudaStream_t loop_stream;
     cudaEvent_t loop_in, loop_out;
     int64_t config_epoch;         // bumped by every call that changes what a captured chunk depends on
+    int32_t bot_modes_now;        // != 0 while astro_rollout_device runs ticks whose bots are evaluated inside the tick kernel
+    ScriptParams script_now;
     // fresh-game mode (astro_fresh_games_enable): per-tile rings of pre-created games fed from the generate_configs stream
     FreshState* fresh;
     cudaEvent_t ev_host_done;   // astro_tick_host_begin / _end
@@ -2071,7 +1995,10 @@ cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
     const int grid = (p.tiles * 32 + kTickThreads - 1) / kTickThreads;
     // experiment knob (tools/exp_tick.py): unused dynamic shared memory caps the resident CTAs per SM
     static const size_t extra = getenv("ASTRO_EXTRA_SMEM") ? (size_t)atoi(getenv("ASTRO_EXTRA_SMEM")) : 0;
-    if (p.n_fused > 1) {
+    if (p.bot_modes) {              // bots inside the tick: the many-tick form, whatever n_fused
+        if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, true, true><<<grid, kTickThreads, extra, st>>>(p);
+        else tick_f32_kernel<S, true, true, true><<<grid, kTickThreads, extra, st>>>(p);
+    } else if (p.n_fused > 1) {
         if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, true><<<grid, kTickThreads, extra, st>>>(p);
         else tick_f32_kernel<S, true, true><<<grid, kTickThreads, extra, st>>>(p);
     } else {
@@ -2221,6 +2148,10 @@ int do_ticks(AstroBatch* b, const uint8_t* actions, float* reward, uint8_t* done
         p.n_fused = kc;
         p.tile0 = tile0;
         p.tiles = tiles > 0 ? tiles : b->n_games / ASTRO_TILE;
+        if (fused && !actions && b->bot_modes_now) {
+            p.bot_modes = b->bot_modes_now;
+            p.script = b->script_now;
+        }
         cudaError_t e;
         if (fused)
             e = b->S == 2 ? launch_tick_f32<2>(p, st) : launch_tick_f32<1>(p, st);
@@ -2956,6 +2887,30 @@ int astro_rollout_device(AstroBatch* b, int32_t n_ticks, int32_t ship0_mode, int
         // no bot between the ticks: the ticks of a tile run back to back inside the launches; `events` keeps the last tick's
         if (n_ticks > 1) if (int r = do_ticks(b, nullptr, nullptr, nullptr, nullptr, flags, st, n_ticks - 1)) return r;
         return n_ticks > 0 ? do_ticks(b, nullptr, nullptr, nullptr, events, flags, st, 1) : ASTRO_OK;
+    }
+    // ScriptBot / NothingBot on every ship (float32 build): the bots are evaluated INSIDE the tick kernel, from the rows a tile's
+    // warp has just loaded, so the ticks of a tile run back to back within a launch — no launch, no control array between ticks
+    // (`actions` is not written).  ASTRO_FUSED_BOTS=0 switches it off.
+    {
+        const char* fb = getenv("ASTRO_FUSED_BOTS");
+        if (!any_policy && b->precision == 32 && !(flags & ASTRO_TICK_GENERIC_KERNEL) && !(fb && atoi(fb) == 0) && n_ticks > 0) {
+            b->bot_modes_now = modes[0] | (modes[1] << 4);
+            ScriptParams& q = b->script_now;
+            q.radius = b->cfg.planet_radius + b->cfg.ship_radius;
+            q.avoid_distance = avoid_distance;
+            q.avoid_threshold = avoid_threshold;
+            q.ship_thrust = b->cfg.ship_thrust;
+            q.ship_rspeed = b->cfg.ship_rspeed;
+            q.bullet_speed = b->cfg.bullet_speed;
+            q.ship_radius = b->cfg.ship_radius;
+            q.solo = b->cfg.solo;
+            q.n_games = b->n_games;
+            int rc = ASTRO_OK;
+            if (n_ticks > 1) rc = do_ticks(b, nullptr, nullptr, nullptr, nullptr, flags, st, n_ticks - 1);
+            if (!rc) rc = do_ticks(b, nullptr, nullptr, nullptr, events, flags, st, 1);      // `events` keeps the last tick's
+            b->bot_modes_now = 0;
+            return rc;
+        }
     }
     // One tick of the loop is 2-4 small launches; at 16,384 games the gaps between them cost as much as the kernels.  Whole
     // chunks of kLoopChunk ticks are therefore captured ONCE into a CUDA graph and replayed: one graph launch per chunk.

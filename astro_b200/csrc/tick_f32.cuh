@@ -351,7 +351,7 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar&
 // One core.step for the 32 games of one tile, by one warp.
 // `next` receives what the following tick of the same tile would load from the rows this tick wrote (meta, ships,
 // bearings): inside a launch that runs several ticks they are handed on in registers.
-template <int S, bool STATS, bool MANY>
+template <int S, bool STATS, bool MANY, bool BOT>
 // `last` = no further tick of this tile follows in this launch: only then do meta, ships and bearings go to memory
 // (planets and the bullet list always do), and the tile's statistics (`stat_acc`, summed over the launch's ticks).
 __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratch& t, const unsigned lane,
@@ -390,10 +390,12 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             if (ctl[0] > 5) ctl[0] = 2;
             if (ctl[1] > 5) ctl[1] = 2;
         }
-    } else {
+    } else if (!BOT) {
         uint32_t h0 = game_key(p.seed, p.first_game + (uint32_t)g);
         ctl[0] = action_from_key(h0, v.step, 0u);
         ctl[1] = S == 2 ? action_from_key(h0, v.step, 1u) : ctl[0];
+    } else {
+        ctl[0] = ctl[1] = 2;      // (bots decide below, once the planets are here)
     }
     // What the END of the tick will need from memory is requested now, off the critical path: the
     // fire-schedule word of this game's tick and, with auto-reset, the planet count of the pool
@@ -408,6 +410,26 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     for (int j = 0; j < ASTRO_MAX_PLANETS; j++) {
         plv[j] = make_float4(kFar, kFar, 0.f, 0.f);
         if (j < np) plv[j] = LD_STREAM(&planets[j * 32]);
+    }
+
+    if (BOT && !v.actions) {
+        // The bots of astro_rollout_device evaluated here, from the rows this lane has just loaded: script.ScriptBot
+        // (script_decide: script.py:67-91, each ship from its own perspective) or script.NothingBot (control 2) per ship —
+        // so that scripted games need no launch between ticks and run many ticks per launch like the counter-stream ones.
+        if (active) {
+            Body4<float> pl4[ASTRO_MAX_PLANETS];
+#pragma unroll
+            for (int j = 0; j < ASTRO_MAX_PLANETS; j++) { pl4[j].x = plv[j].x; pl4[j].y = plv[j].y; pl4[j].dx = plv[j].z; pl4[j].dy = plv[j].w; }
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                if (((p.bot_modes >> (4 * s)) & 15) == ASTRO_BOT_SCRIPT) {
+                    Body4<float> me, en;
+                    me.x = shv[s].x; me.y = shv[s].y; me.dx = shv[s].z; me.dy = shv[s].w;
+                    en.x = shv[S - 1 - s].x; en.y = shv[S - 1 - s].y; en.dx = shv[S - 1 - s].z; en.dy = shv[S - 1 - s].w;
+                    ctl[s] = script_decide<float, S>(me, sb[s], en, pl4, np, p.script);
+                }
+            }
+        }
     }
 
     // ================= 2. flat bullet list of the tile; stage it with cp.async =================
@@ -859,8 +881,9 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
 // One warp (= one CTA) per tile; the block scheduler balances the load.  (Persistent forms — static
 // tile striding, a device-side tile queue with the next tile's rows prefetched, a fully staged
 // software pipeline — were built and measured 12-48 % slower: profiles/r1_ab_v6_experiments.md.)
-template <int S, bool STATS, bool MANY>
-__global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
+// (BOT: the instantiation with the ScriptBot inside — float64 arithmetic of its own, far more registers: fewer CTAs per SM)
+template <int S, bool STATS, bool MANY, bool BOT = false>
+__global__ void __launch_bounds__(kTickThreads, BOT ? 8 : ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
     __shared__ TileScratch s_tiles[kTickWarps];
     unsigned tile = (blockIdx.x * kTickThreads + threadIdx.x) >> 5;   // among the p.tiles tiles of this launch, from p.tile0
 #if ASTRO_PDL
@@ -903,7 +926,7 @@ __global__ void __launch_bounds__(kTickThreads, ASTRO_TICK_MIN_BLOCKS) tick_f32_
         }
         if (MANY) in.fire_word = p.fire_bits[min(ASTRO_META_TICK(in.meta), (uint32_t)p.n_sched_ticks - 1u) >> 5];
         // (one-warp CTAs: the scratch is s_tiles[0], every shared address a compile-time constant — no base register)
-        tick_tile<S, STATS, MANY>(p, v, scratch, lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
+        tick_tile<S, STATS, MANY, BOT>(p, v, scratch, lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
         if (MANY) {
             // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
             // well), so it starts its prefix sums and list requests at once; only the planet rows are loaded.  The
