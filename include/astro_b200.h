@@ -314,7 +314,10 @@ int astro_set_exploration(AstroBatch* b, double t_in, double t_out, uint32_t see
  *               ASTRO_BOT_NOTHING script.NothingBot: control 2
  *               ASTRO_BOT_EXPLORE the greedy network with rl.EpsilonGreedy laid over it, like rl.QBotTrainer
  *                                 (astro_policy_controls, then astro_explore_controls; needs astro_set_exploration)
- *   actions     u8 [n_games][S] device scratch (may be NULL for ASTRO_BOT_STREAM); holds the last tick's controls
+ *   actions     u8 [n_games][S] device scratch (may be NULL for ASTRO_BOT_STREAM); holds the last tick's controls, EXCEPT when
+ *               every ship is SCRIPT or NOTHING on a float32 batch: those bots are evaluated inside the tick kernel from
+ *               the rows it has just loaded (many ticks per launch, no control array) and `actions` is left untouched
+ *               (ASTRO_FUSED_BOTS=0 in the environment restores the bot-kernel -> tick-kernel loop)
  *   events      u8 [n_games] device or NULL: the last tick's events */
 #define ASTRO_BOT_STREAM 0
 #define ASTRO_BOT_SCRIPT 1
