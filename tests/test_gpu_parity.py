@@ -259,6 +259,43 @@ def test_f64_free_running_rollout_matches_oracle_rollout():
         assert st[name] == stats[i], name
 
 
+def test_f32_free_running_statistics_match_the_f64_build():
+    """Free-running float32 against the float64 (reference-arithmetic) build on episode statistics: the same games,
+    pool, counter-stream controls and pool picks for 600 ticks.  Individual float32 trajectories leave the float64
+    ones after some tens of ticks (chaotic dynamics, SURVEY hard part 8), so what must agree is the distribution:
+    episode count, win split, mean episode length and bullet traffic, within the sampling error of ~170,000 episodes
+    (tolerances: 4 standard errors of a binomial share / 1 % on the totals), and the first ticks — before rounding
+    differences can grow — game by game."""
+    cfg, N, K, T, M = core.DEFAULT_CONFIG, 32768, 32, 600, 1024
+    pool = H.make_pool(cfg, M)
+    out = {}
+    for precision in (32, 64):
+        games = _games(cfg, N, bullet_cap=K, precision=precision, seed=21, first_game=4096)
+        games.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
+        games.reset_all()
+        ev_early = []
+        for k in range(30):
+            ev_early.append(games.step(None, auto_reset=True)[2].cpu().numpy().copy())
+        if precision == 32:
+            games.step_many(T - 30, None, auto_reset=True)
+        else:
+            for _ in range(T - 30):
+                games.step(None, auto_reset=True)
+        out[precision] = (games.stats(), np.stack(ev_early))
+    (a, ea), (b, eb) = out[32], out[64]
+    assert a['env_steps'] == b['env_steps'] == N * T
+    # the first 30 ticks: the same discrete events in (all but a handful of knife-edge) games
+    assert (ea != eb).any(axis=0).mean() < 1e-3
+    n = b['episodes']
+    assert n > 100000 and abs(a['episodes'] - n) <= 0.01 * n                     # mean episode length within 1 %
+    for key in ('wins0', 'wins1', 'both_lost'):
+        pa, pb = a[key] / a['episodes'], b[key] / n
+        assert abs(pa - pb) <= 4.0 * np.sqrt(2.0 * pb * (1.0 - pb) / n) + 1e-4, (key, pa, pb)
+    assert a['timeouts'] == b['timeouts'] == 0 or abs(a['timeouts'] - b['timeouts']) <= 0.05 * b['timeouts'] + 5
+    for key in ('bullets_in', 'bullets_out', 'planets_live'):
+        assert abs(a[key] - b[key]) <= 0.01 * b[key], key
+
+
 # ------------------------------------------------------------------ config #3: 65,536 games, full pools
 
 def _stress_fill(K, seed):
