@@ -628,6 +628,44 @@ class BatchedGames:
         nat.check(nat.lib().astro_stats(self._h, self._stats.data_ptr(), int(clear), self._stream()))
         return self._stats
 
+    def stats_peer_init(self, dist):
+        """Maps the exchange buffers of all ranks of `dist`'s default group (one node, one GPU per rank) for
+        stats_allreduce: CUDA IPC handles travel through dist.all_gather.  Collective, and collective-safe: a rank
+        whose create / open step fails still takes part in every exchange, and ALL ranks then return False (the
+        caller keeps NCCL); True = every rank has mapped every buffer."""
+        torch = _torch()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        handle = (C.c_uint8 * 64)()
+        err = None
+        try:
+            nat.check(nat.lib().astro_stats_peer_create(self._h, rank, world, handle))
+        except nat.AstroError as exc:
+            err = str(exc)
+        mine = torch.tensor(list(handle) + [0 if err else 1], dtype=torch.uint8, device=self.device)
+        everyone = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)
+        got = torch.stack(everyone).cpu().numpy()
+        if err is None and got[:, 64].all():
+            try:
+                nat.check(nat.lib().astro_stats_peer_open(self._h, got[:, :64].tobytes()))
+            except nat.AstroError as exc:
+                err = str(exc)
+        elif err is None:
+            err = 'another rank could not create its exchange buffer'
+        ok = torch.tensor([0.0 if err else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # (also the barrier: nobody stores into a buffer that is not mapped and cleared)
+        self.peer_error = err
+        self._peer_ready = bool(float(ok) > 0)
+        return self._peer_ready
+
+    def stats_allreduce(self, clear=False):
+        """The counters summed over all ranks, on the device (int64 [N_STATS]): ONE kernel per rank over peer memory
+        (astro_stats_allreduce); collective, after stats_peer_init."""
+        if not getattr(self, '_peer_ready', False):
+            raise nat.AstroError('stats_allreduce: stats_peer_init has not succeeded on every rank')
+        nat.check(nat.lib().astro_stats_allreduce(self._h, self._stats.data_ptr(), int(clear), self._stream()))
+        return self._stats
+
     def stats(self, clear=False):
         v = self.stats_tensor(clear).cpu().numpy()
         return dict(zip(nat.STAT_NAMES, (int(x) for x in v)))

@@ -38,6 +38,7 @@ namespace {
 #endif
 constexpr int kTickThreads = ASTRO_TICK_THREADS;
 constexpr int kObserveWarps = 8;
+constexpr int kStatReplicas = 64;   // copies of the 64-bit episode counters (16 words = one 128-byte line each), summed by astro_stats
 
 struct TickParams {
     void* ships;
@@ -175,6 +176,72 @@ __global__ void fold_stats_kernel(unsigned* slots, int n_tiles, unsigned long lo
     if (k < ASTRO_N_STATS && sum) atomicAdd(&acc[k], sum);
     __syncthreads();
     if (threadIdx.x < ASTRO_N_STATS && acc[threadIdx.x]) atomicAdd(&stats[threadIdx.x], acc[threadIdx.x]);
+}
+
+// astro_stats: the kStatReplicas copies of the counters summed into `out` (and cleared).
+__global__ void gather_stats_kernel(unsigned long long* stats, long long* out, int clear) {
+    __shared__ unsigned long long acc[16];
+    if (threadIdx.x < 16) acc[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned long long sum = 0;
+    for (int i = threadIdx.x; i < kStatReplicas * 16; i += blockDim.x) {
+        const unsigned long long v = stats[i];
+        if (v) { sum += v; if (clear) stats[i] = 0ull; }
+    }
+    if (sum) atomicAdd(&acc[threadIdx.x & 15], sum);     // (blockDim.x is a multiple of 16: a thread sees one counter)
+    __syncthreads();
+    if (threadIdx.x < ASTRO_N_STATS) out[threadIdx.x] = (long long)acc[threadIdx.x];
+}
+
+// astro_stats_allreduce: the episode counters of N processes (one GPU each, one node) summed in ONE kernel per rank over peer
+// memory — no NCCL launch, no ring: every rank owns an exchange buffer [2][kPeerMax] rows of 16 words (14 counters, word 15 =
+// the call number), mapped into every other process (CUDA IPC); call number n uses half n & 1.
+//   1. this rank's counters = sum of the kStatReplicas copies (cleared on request)
+//   2. thread r stores them into row `rank` of rank r's buffer — P2P stores through NVLink / NVSwitch — and, behind a
+//      system-scope fence, the call number into the row's last word
+//   3. thread r waits for row r of THIS rank's buffer to show the call number (the peers' stores land in local memory: the
+//      poll never leaves the GPU), then the rows are summed into `out`.
+// Two halves are enough: a rank can only be one call ahead of the slowest one (it needs that rank's row of the call to go on).
+// A peer that never arrives (a rank died) ends the wait after ~2 s of polling with every counter set to -1.
+constexpr int kPeerMax = 16;
+struct PeerTable { unsigned long long* buf[kPeerMax]; };
+__global__ void __launch_bounds__(256) stats_allreduce_kernel(unsigned long long* stats, long long* out, int clear, PeerTable peers,
+                                                              int rank, int world, unsigned long long call) {
+    __shared__ unsigned long long acc[16];
+    __shared__ int failed;
+    if (threadIdx.x < 16) acc[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) failed = 0;
+    __syncthreads();
+    unsigned long long sum = 0;
+    for (int i = threadIdx.x; i < kStatReplicas * 16; i += blockDim.x) {
+        const unsigned long long v = stats[i];
+        if (v) { sum += v; if (clear) stats[i] = 0ull; }
+    }
+    if (sum) atomicAdd(&acc[threadIdx.x & 15], sum);
+    __syncthreads();
+    const size_t half = (size_t)(call & 1ull) * kPeerMax * 16;
+    if ((int)threadIdx.x < world) {
+        volatile unsigned long long* row = peers.buf[threadIdx.x] + half + (size_t)rank * 16;
+#pragma unroll
+        for (int k = 0; k < ASTRO_N_STATS; k++) row[k] = acc[k];
+        __threadfence_system();
+        row[15] = call;
+    }
+    if ((int)threadIdx.x < world) {
+        const volatile unsigned long long* row = peers.buf[rank] + half + (size_t)threadIdx.x * 16;
+        const long long t0 = clock64();
+        while (row[15] != call) {
+            if (clock64() - t0 > (4ll << 30)) { failed = 1; break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < ASTRO_N_STATS) {
+        unsigned long long total = 0;
+        const volatile unsigned long long* mine = peers.buf[rank] + half;
+        for (int r = 0; r < world; r++) total += mine[(size_t)r * 16 + threadIdx.x];
+        out[threadIdx.x] = failed ? -1ll : (long long)total;
+    }
 }
 
 // First list item of game `gl` (0..31) of a tile: the bullet counts of the tile's lower games,
@@ -1855,7 +1922,13 @@ struct AstroBatch {
     AstroResetPool pool;
     uint32_t* d_fire_bits;
     int32_t n_sched_ticks, timeout_tick;
-    unsigned long long* d_stats;
+    unsigned long long* d_stats;   // [kStatReplicas][16]
+    // astro_stats_allreduce: this rank's exchange buffer, the peers' (IPC-mapped) and the call counter
+    unsigned long long* d_peer_own;
+    PeerTable peer_table;
+    int32_t peer_rank, peer_world;
+    bool peer_open;
+    unsigned long long peer_calls;
     unsigned* d_stat_slots;  // per-warp partial counters, folded by astro_stats
     int32_t cur;             // which of the two bullet buffers holds the lists (flips every tick)
     float4* d_pool_rec;      // precision 32: packed copy of the reset pool (astro_set_reset_pool)
@@ -2212,8 +2285,8 @@ int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_c
     b->device = device;
     b->S = cfg->solo ? 1 : 2;
     fill_consts(*cfg, b->c);
-    cudaError_t e = cudaMalloc(&b->d_stats, sizeof(unsigned long long) * ASTRO_N_STATS);
-    if (e == cudaSuccess) e = cudaMemset(b->d_stats, 0, sizeof(unsigned long long) * ASTRO_N_STATS);
+    cudaError_t e = cudaMalloc(&b->d_stats, sizeof(unsigned long long) * 16 * kStatReplicas);
+    if (e == cudaSuccess) e = cudaMemset(b->d_stats, 0, sizeof(unsigned long long) * 16 * kStatReplicas);
     const size_t slot_bytes = (size_t)(n_games / ASTRO_TILE) * 16 * sizeof(unsigned);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_stat_slots, slot_bytes);
     if (e == cudaSuccess) e = cudaMemset(b->d_stat_slots, 0, slot_bytes);
@@ -2235,6 +2308,10 @@ int astro_batch_destroy(AstroBatch* b) {
     if (!b) return ASTRO_OK;
     cudaSetDevice(b->device);
     cudaFree(b->d_stats);
+    if (b->peer_open)
+        for (int r = 0; r < b->peer_world; r++)
+            if (r != b->peer_rank && b->peer_table.buf[r]) cudaIpcCloseMemHandle(b->peer_table.buf[r]);
+    cudaFree(b->d_peer_own);
     cudaFree(b->d_stat_slots);
     cudaFree(b->d_actions);
     cudaFree(b->d_events);
@@ -3285,8 +3362,68 @@ int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* strea
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (b->ticks_since_fold > 0) CUDA_TRY(fold_stats(b, st));
-    CUDA_TRY(cudaMemcpyAsync(counters_dev, b->d_stats, sizeof(int64_t) * ASTRO_N_STATS, cudaMemcpyDeviceToDevice, st));
-    if (clear) CUDA_TRY(cudaMemsetAsync(b->d_stats, 0, sizeof(int64_t) * ASTRO_N_STATS, st));
+    gather_stats_kernel<<<1, 256, 0, st>>>(b->d_stats, (long long*)counters_dev, clear ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return ASTRO_OK;
+}
+
+int astro_stats_peer_create(AstroBatch* b, int32_t rank, int32_t world, uint8_t* handle_out) {
+    if (int r = check(b, false)) return r;
+    if (!handle_out) return fail(ASTRO_E_INVALID, "null handle_out");
+    if (world < 1 || world > kPeerMax || rank < 0 || rank >= world) return fail(ASTRO_E_INVALID, "rank %d of %d: 1..%d ranks", rank, world, kPeerMax);
+    if (b->d_peer_own) return fail(ASTRO_E_STATE, "the exchange buffer of this batch exists already");
+    static_assert(sizeof(cudaIpcMemHandle_t) == ASTRO_IPC_HANDLE_BYTES, "ASTRO_IPC_HANDLE_BYTES");
+    CUDA_TRY(cudaSetDevice(b->device));
+    const size_t bytes = sizeof(unsigned long long) * 2 * kPeerMax * 16;
+    CUDA_TRY(cudaMalloc(&b->d_peer_own, bytes));
+    CUDA_TRY(cudaMemset(b->d_peer_own, 0, bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, b->d_peer_own));
+    memcpy(handle_out, &h, sizeof(h));
+    b->peer_rank = rank;
+    b->peer_world = world;
+    b->peer_calls = 0;
+    return ASTRO_OK;
+}
+
+int astro_stats_peer_open(AstroBatch* b, const uint8_t* handles) {
+    if (int r = check(b, false)) return r;
+    if (!handles) return fail(ASTRO_E_INVALID, "null handles");
+    if (!b->d_peer_own) return fail(ASTRO_E_STATE, "astro_stats_peer_create has not been called");
+    if (b->peer_open) return fail(ASTRO_E_STATE, "the peers' buffers are mapped already");
+    CUDA_TRY(cudaSetDevice(b->device));
+    memset(&b->peer_table, 0, sizeof(b->peer_table));
+    for (int r = 0; r < b->peer_world; r++) {
+        if (r == b->peer_rank) { b->peer_table.buf[r] = b->d_peer_own; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * ASTRO_IPC_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; q++)
+                if (q != b->peer_rank && b->peer_table.buf[q]) cudaIpcCloseMemHandle(b->peer_table.buf[q]);
+            memset(&b->peer_table, 0, sizeof(b->peer_table));
+            return fail(ASTRO_E_CUDA, "cudaIpcOpenMemHandle (rank %d): %s", r, cudaGetErrorString(e));
+        }
+        b->peer_table.buf[r] = (unsigned long long*)ptr;
+    }
+    b->peer_open = true;
+    return ASTRO_OK;
+}
+
+int astro_stats_allreduce(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream) {
+    if (int r = check(b, false)) return r;
+    if (!counters_dev) return fail(ASTRO_E_INVALID, "null counters");
+    if (!b->peer_open) return fail(ASTRO_E_STATE, "astro_stats_peer_open has not been called");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b->ticks_since_fold > 0) CUDA_TRY(fold_stats(b, st));
+    b->peer_calls += 1;
+    stats_allreduce_kernel<<<1, 256, 0, st>>>(b->d_stats, (long long*)counters_dev, clear ? 1 : 0, b->peer_table, b->peer_rank, b->peer_world,
+                                             b->peer_calls);
+    CUDA_TRY(cudaGetLastError());
     return ASTRO_OK;
 }
 

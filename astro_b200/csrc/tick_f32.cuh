@@ -866,8 +866,10 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         if (last) {
             if (MANY && p.n_fused >= 8) {
                 // a launch of many ticks: the tile's totals of the whole launch go straight to the 64-bit counters —
-                // one RED per counter and tile per LAUNCH is cheap, and astro_stats needs no fold pass afterwards
-                if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(&p.stats[lane], (unsigned long long)stat_acc);
+                // one RED per counter and tile per LAUNCH is cheap, and astro_stats needs no fold pass afterwards.  The
+                // counters are kept kStatReplicas times (one 128-byte line each, picked by the tile), so that the REDs of
+                // all the tiles do not queue on a single L2 line.
+                if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(&p.stats[(tile_index & (unsigned)(kStatReplicas - 1)) * 16u + lane], (unsigned long long)stat_acc);
             } else {
                 unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
                 if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(slot, stat_acc);  // RED: fire and forget

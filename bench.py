@@ -401,8 +401,17 @@ def run_ours(args):
         run_steps(warmup)
         games.stats_tensor(clear=True)
         align = torch.zeros(1, device=dev)
+        peer = None
         if world > 1:
             dist.all_reduce(align)       # (NCCL warm-up for this size)
+            if collective and args.stats_reduce == 'peer':
+                # the statistics reduction over peer memory (astro_stats_allreduce: one kernel per rank, P2P stores through
+                # NVSwitch); every rank must have mapped the others' buffers, else all of them use NCCL
+                if games.stats_peer_init(dist):
+                    games.stats_allreduce(clear=True)        # (first touch of the peer mappings)
+                    peer = 'peer'
+                else:
+                    peer = 'nccl (peer exchange unavailable: %s)' % str(games.peer_error or 'on another rank')[:120]
         launches0 = games.launches
         if world > 1:
             dist.barrier()
@@ -413,15 +422,18 @@ def run_ours(args):
         torch.cuda.synchronize() if world == 1 else None
         e0.record()
         n_launches = run_steps(steps)
-        st_t = games.stats_tensor(clear=True)
-        if collective:
-            reduce_stats(st_t, dist)         # NCCL: the episode-statistics reduction, once per rollout
+        if peer == 'peer':
+            st_t = games.stats_allreduce(clear=True)     # the episode-statistics reduction, once per rollout: peer memory ...
+        else:
+            st_t = games.stats_tensor(clear=True)
+            if collective:
+                reduce_stats(st_t, dist)                 # ... or NCCL
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         return dict(games=games, ms=gather_ms(e0.elapsed_time(e1)), stats=dict(zip(nat.STAT_NAMES, (int(x) for x in st_t.cpu().numpy()))),
-                    launches=games.launches - launches0, n_launches=n_launches, run_steps=run_steps, flags=flags,
+                    launches=games.launches - launches0, n_launches=n_launches, run_steps=run_steps, flags=flags, stats_reduce=peer or ('nccl' if world > 1 else 'none'),
                     host_ring=host_ring, dev_ring=dev_ring, R=R)
 
     plan = shard_plan(world, rank, args.games_per_gpu)
@@ -445,6 +457,22 @@ def run_ours(args):
         reduce_stats(games.stats_tensor(clear=False), dist)
     torch.cuda.synchronize()
     collective_us = max(gather_ms(1e6 * (time.perf_counter() - t0) / reps))
+    collective = dict(used=main['stats_reduce'], nccl_us=collective_us)
+    if main['stats_reduce'] == 'peer':
+        # the same through astro_stats_allreduce, checked against NCCL on the way
+        want = games.stats_tensor(clear=False).clone()
+        reduce_stats(want, dist)
+        got = games.stats_allreduce(clear=False).clone()
+        assert bool((want == got).all()), 'astro_stats_allreduce disagrees with the NCCL all-reduce'
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            games.stats_allreduce(clear=False)
+        torch.cuda.synchronize()
+        collective['peer_us'] = max(gather_ms(1e6 * (time.perf_counter() - t0) / reps))
+        collective_us = collective['peer_us']
 
     # kernel-only window on this rank (no collective inside): the roofline numbers
     games.stats_tensor(clear=True)
@@ -646,7 +674,7 @@ def run_ours(args):
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f32', data='synthetic', config=workload_config(args), roofline=roofline,
                     cpu_baseline=cpu, clocks=clocks, e2e=e2e, gpu_launches=timed_launches,
-                    per_tick_launch=per_tick, per_rank_ms=per_rank_ms, collective_us=collective_us, strong=strong, fresh_games=fresh, rollout=rollout, drop_in=drop_in,
+                    per_tick_launch=per_tick, per_rank_ms=per_rank_ms, collective_us=collective_us, collective=collective, strong=strong, fresh_games=fresh, rollout=rollout, drop_in=drop_in,
                     episode_stats={k: total[k] for k in ('episodes', 'wins0', 'wins1', 'both_lost', 'timeouts', 'overflow', 'bad_controls')})
         print(json.dumps(line), flush=True)
 
@@ -672,6 +700,7 @@ def main():
     ap.add_argument('--no-rollout', action='store_true', help='skip the config #5 / drop-in legs')
     ap.add_argument('--no-fresh', action='store_true', help='skip the fresh-game-mode leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--stats-reduce', default='peer', choices=['peer', 'nccl'], help='N > 1: the episode-statistics reduction through astro_stats_allreduce (peer memory) or NCCL')
     ap.add_argument('--fuse', type=int, default=64, help='ticks per launch of the timed loop (astro_tick_many); 1 = one launch per tick')
     ap.add_argument('--tick-flags', type=int, default=0, help='extra ASTRO_TICK_* bits (kernel A/B)')
     ap.add_argument('--timed-flags', type=int, default=0, help='extra tick bits after the pre-roll (experiment builds)')

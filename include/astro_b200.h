@@ -390,6 +390,20 @@ int astro_nstep_experiences(AstroBatch* b, const uint8_t* events, int32_t n_tick
  * an NCCL all-reduce) on the stream; clear != 0 zeroes them afterwards. */
 int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream);
 
+/* The same counters summed over the N processes of one node (one GPU each; "NCCL used only for the optional episode-stats
+ * reduction" in the north star — this is that reduction without NCCL): ONE kernel per rank that stores the rank's counters
+ * into every rank's exchange buffer through peer memory (NVLink / NVSwitch, buffers mapped by CUDA IPC), waits for the other
+ * ranks' rows and writes the total to counters_dev — the latency of one P2P store instead of a collective launch.
+ *   astro_stats_peer_create  allocates this rank's exchange buffer; handle_out receives its ASTRO_IPC_HANDLE_BYTES-byte IPC
+ *                            handle, which the caller hands to every rank (e.g. torch.distributed.all_gather)
+ *   astro_stats_peer_open    handles = world x ASTRO_IPC_HANDLE_BYTES bytes in rank order: maps the peers' buffers
+ *   astro_stats_allreduce    collective: every rank calls it the same number of times.  counters_dev as in astro_stats; a
+ *                            peer that does not arrive within ~2 s of polling leaves every counter at -1. */
+#define ASTRO_IPC_HANDLE_BYTES 64
+int astro_stats_peer_create(AstroBatch* b, int32_t rank, int32_t world, uint8_t* handle_out);
+int astro_stats_peer_open(AstroBatch* b, const uint8_t* handles);
+int astro_stats_allreduce(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream);
+
 /* Launch bookkeeping for bench.py: kernels launched by this handle since creation. */
 int64_t astro_launch_count(const AstroBatch* b);
 

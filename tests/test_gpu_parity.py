@@ -6,6 +6,8 @@ validation build and within |d| <= 1e-5 * max(1, |ref|) per tick in the float32 
 import collections
 import json
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -1691,3 +1693,50 @@ def test_nstep_experiences_match_the_reference_ingestion(window):
                 r, d, n = got[me][tick]
                 assert n == new and abs(r - reward) <= 1e-6 * max(1.0, abs(reward)) and abs(d - disc) <= 1e-6 * disc, (n_steps, tick)
                 assert action == ticks[tick][0][me]
+
+
+# ------------------------------------------------------------------ the statistics reduction over peer memory
+
+def test_stats_allreduce_single_rank_equals_stats():
+    """astro_stats_allreduce with a world of one rank (the exchange buffer is the rank's own): the kernel's local
+    gather, row store, wait and sum give exactly astro_stats, with and without clearing."""
+    import ctypes as C
+    import torch
+    cfg, N = core.DEFAULT_CONFIG, 2048
+    games = _games(cfg, N, bullet_cap=32, precision=32, seed=2)
+    games.set_reset_pool_on_device(128)
+    games.reset_all()
+    L = nat.lib()
+    handle = (C.c_uint8 * 64)()
+    out = torch.zeros(nat.N_STATS, dtype=torch.int64, device='cuda')
+    assert L.astro_stats_allreduce(games._h, out.data_ptr(), 0, None) == -3          # before create / open: state error
+    assert L.astro_stats_peer_open(games._h, bytes(64)) == -3
+    assert L.astro_stats_peer_create(games._h, 3, 2, handle) == -1                   # rank out of range
+    nat.check(L.astro_stats_peer_create(games._h, 0, 1, handle))
+    assert L.astro_stats_peer_create(games._h, 0, 1, handle) == -3                   # twice
+    nat.check(L.astro_stats_peer_open(games._h, bytes(handle)))
+    for k in range(3):
+        games.step_many(24, None, auto_reset=True)
+        games.step(None, auto_reset=True)                                            # (slot rows: folded on the way)
+        want = games.stats_tensor(clear=False).clone()
+        nat.check(L.astro_stats_allreduce(games._h, out.data_ptr(), int(k == 1), None))
+        assert (out == want).all() and int(want[nat.STAT_NAMES.index('env_steps')]) > 0
+        if k == 1:
+            assert games.stats()['env_steps'] == 0
+
+
+def test_stats_allreduce_over_peer_memory_equals_nccl():
+    """Two ranks (two GPUs of one box) through torch.distributed.run: astro_stats_allreduce == the NCCL all-reduce of the
+    same counters, six rounds with the ranks arriving at different times, alternating clear."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'peer_worker.py')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29655', script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    res = [json.loads(line) for line in r.stdout.splitlines() if line.startswith('{"rank"')]
+    assert len(res) == 2
+    for x in res:
+        assert x['ok'], x
+        assert len(x['rounds']) == 7 and all(x['rounds']), x
