@@ -35,7 +35,8 @@ def main():
             rounds.append(bool((want == got).all()) and int(got[nat.STAT_NAMES.index('env_steps')]) > 0)
         after_clear = games.stats()
         rounds.append(after_clear['env_steps'] == 0)
-    print(json.dumps(dict(rank=rank, ok=ok, error=games.peer_error, rounds=rounds)), flush=True)
+    with open(os.path.join(os.environ['ASTRO_PEER_OUT'], 'rank%d.json' % rank), 'w') as f:      # (the ranks' stdout interleaves)
+        json.dump(dict(rank=rank, ok=ok, error=games.peer_error, rounds=rounds), f)
     dist.barrier()
     dist.destroy_process_group()
 

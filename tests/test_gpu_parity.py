@@ -1725,7 +1725,7 @@ def test_stats_allreduce_single_rank_equals_stats():
             assert games.stats()['env_steps'] == 0
 
 
-def test_stats_allreduce_over_peer_memory_equals_nccl():
+def test_stats_allreduce_over_peer_memory_equals_nccl(tmp_path):
     """Two ranks (two GPUs of one box) through torch.distributed.run: astro_stats_allreduce == the NCCL all-reduce of the
     same counters, six rounds with the ranks arriving at different times, alternating clear."""
     import torch
@@ -1733,10 +1733,10 @@ def test_stats_allreduce_over_peer_memory_equals_nccl():
         pytest.skip('needs two GPUs')
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'peer_worker.py')
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
-                        '--master-port', '29655', script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+                        '--master-port', '29655', script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
+                       env=dict(os.environ, ASTRO_PEER_OUT=str(tmp_path)))
     assert r.returncode == 0, r.stdout[-3000:]
-    res = [json.loads(line) for line in r.stdout.splitlines() if line.startswith('{"rank"')]
-    assert len(res) == 2
+    res = [json.load(open(os.path.join(str(tmp_path), 'rank%d.json' % k))) for k in range(2)]
     for x in res:
         assert x['ok'], x
         assert len(x['rounds']) == 7 and all(x['rounds']), x
