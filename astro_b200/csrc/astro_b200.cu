@@ -1298,7 +1298,7 @@ struct PolicyFrags {                 // per CTA, in (dynamic) shared memory
     PolicyFragWeights w;             // copied from global memory, 16 bytes per thread and step
     float pool[kMmaWarps][16][kPoolStride];   // per warp: the pooled vectors of 8 games, rows 0-7 ship 0's view, 8-15 ship 1's
     float4 red[kMmaWarps][8][4][2];  // per warp: max-pool exchange, [quad][t][half of the 16 accumulators as 2 float4]
-    float sf[kMmaWarps][12];         // per warp: the game's ship features, ship 0 then ship 1
+    float sf[kMmaWarps][8][12];      // per warp: the ship features of its 8 games, ship 0 then ship 1
 };
 // x = hi + lo for the 3xTF32 scheme.  The tensor core reads only the 19 high bits of an fp32 operand (it truncates), so hi
 // is x itself — no instruction — standing for trunc(x); lo = x - trunc(x) exactly (a mask and a subtraction), and adding
@@ -1428,41 +1428,75 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
         else if (col < DIN) { obj_idx[j] = col - 1 - 5 * S; any_obj = true; }
     }
     float (*pool)[kPoolStride] = s_all.pool[warp];
-    // a warp takes 8 consecutive games at a time: their pooled vectors make one 16-row tile for the head
-    const int n_groups = (n_games + 7) >> 3;
+    // a warp takes 8 consecutive games at a time (one quarter of a tile: n_games is a multiple of 32): their pooled vectors
+    // make one 16-row tile for the head
+    const int n_groups = n_games >> 3;
     for (int grp = blockIdx.x * kMmaWarps + warp; grp < n_groups; grp += gridDim.x * kMmaWarps) {
-        unsigned live_mask = 0;
+        // ---- everything the 8 games need that does not depend on the network, for all of them at once (one round of
+        // loads per kind instead of one per game: a game's chain below starts with its rows already on their way)
+        const size_t tile = (size_t)(grp >> 2);
+        const int gl0 = (grp & 3) * 8;
+        const uint32_t meta_l = meta_[tile * 32 + lane];                      // the tile's 32 meta words: list offsets, np, rows
+        const bool fin_l = ASTRO_META_FINISHED(meta_l);
+        const unsigned nb_l = fin_l ? 0u : ASTRO_META_NB(meta_l);
+        unsigned incl = nb_l;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const unsigned off_l = incl - nb_l;                                  // first list item of lane's game (tile_list_offset)
+        const int np_l = fin_l ? 0 : (int)ASTRO_META_NP(meta_l);
+        const int rows_l = fin_l ? 0 : np_l + (int)nb_l;
+        const unsigned live_mask = (__ballot_sync(0xffffffffu, rows_l > 0) >> gl0) & 0xffu;
+        // ship features (x, y, dx, dy, norm_angle(b) / pi), ship 0 then ship 1, of the 8 games: the float64 bearings by
+        // 8 S lanes in ONE pass, the 32 S plain components in S passes
+        if (lane < 8 * S) {
+            const int j8 = lane / S, s_ = lane % S;
+            s_all.sf[warp][j8][5 * s_ + 4] = (float)__ddiv_rn(norm_angle_f64((double)reinterpret_cast<const R*>(ship_b_)[tile * (S * 32) + s_ * 32 + gl0 + j8]), 3.141592653589793);
+        }
+#pragma unroll
+        for (int s_ = 0; s_ < S; s_++) {
+            const int j8 = lane >> 2, c = lane & 3;
+            s_all.sf[warp][j8][5 * s_ + c] = (float)reinterpret_cast<const R*>(ships_)[(tile * (S * 32) + s_ * 32 + gl0 + j8) * 4 + c];
+        }
+        __syncwarp();
+        const Body4<R>* const pl_tile = reinterpret_cast<const Body4<R>*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32);
+        const Body4<R>* const bl_tile = reinterpret_cast<const Body4<R>*>(bullets_) + tile * (size_t)(32 * K);
+        // this lane's object component(s) of row gq of a game's first 8 rows (the quad covers the object's 16 bytes)
+        auto load_first_rows = [&](int j8, float (&ov)[4]) {
+            const int np = __shfl_sync(0xffffffffu, np_l, gl0 + j8), rows = __shfl_sync(0xffffffffu, rows_l, gl0 + j8);
+            const unsigned off = __shfl_sync(0xffffffffu, off_l, gl0 + j8);
+#pragma unroll
+            for (int j = 0; j < 4; j++) ov[j] = 0.f;
+            if (gq < rows && any_obj) {
+                const R* o = reinterpret_cast<const R*>(gq < np ? &pl_tile[gq * 32 + gl0 + j8] : &bl_tile[off + (unsigned)(gq - np)]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (obj_idx[j] >= 0) ov[j] = (float)o[obj_idx[j]];
+            }
+        };
+        float ov_next[4];
+        load_first_rows(0, ov_next);
 #pragma unroll 1
         for (int j8 = 0; j8 < 8; j8++) {
-            const int g = grp * 8 + j8;
-            if (g >= n_games) break;                             // (warp-uniform)
-            const size_t tile = (size_t)(g >> 5);
-            const int gl = g & 31;
-            const uint32_t meta = meta_[g];
-            const bool fin = ASTRO_META_FINISHED(meta);
-            const int np = fin ? 0 : (int)ASTRO_META_NP(meta);
-            const int rows = fin ? 0 : np + (int)ASTRO_META_NB(meta);
-            if (rows > 0) live_mask |= 1u << j8;
-            // ship features (x, y, dx, dy, norm_angle(b) / pi), ship 0 then ship 1
-            if (lane < 5 * S) {
-                const int s_ = lane / 5, c = lane % 5;
-                float feat;
-                if (c < 4) feat = (float)reinterpret_cast<const R*>(ships_)[((size_t)tile * (S * 32) + s_ * 32 + gl) * 4 + c];
-                else feat = (float)__ddiv_rn(norm_angle_f64((double)reinterpret_cast<const R*>(ship_b_)[(size_t)tile * (S * 32) + s_ * 32 + gl]), 3.141592653589793);
-                s_all.sf[warp][lane] = feat;
-            }
-            __syncwarp();
+            const int gl = gl0 + j8;
+            const int np = __shfl_sync(0xffffffffu, np_l, gl), rows = __shfl_sync(0xffffffffu, rows_l, gl);
+            const unsigned off = __shfl_sync(0xffffffffu, off_l, gl);
+            float ov[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) ov[j] = ov_next[j];
+            if (j8 < 7) load_first_rows(j8 + 1, ov_next);        // the next game's rows travel while this game's layers run
             float xa[4], xb[4];                                  // this lane's feature slots, perspective of ship 0 / ship 1
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 xa[j] = xb[j] = 0.f;
                 if (ship_idx[j] >= 0) {
-                    xa[j] = s_all.sf[warp][ship_idx[j]];
-                    xb[j] = s_all.sf[warp][S == 2 ? (ship_idx[j] + 5) % 10 : ship_idx[j]];    // the ship column groups exchanged
+                    xa[j] = s_all.sf[warp][j8][ship_idx[j]];
+                    xb[j] = s_all.sf[warp][j8][S == 2 ? (ship_idx[j] + 5) % 10 : ship_idx[j]];    // the ship column groups exchanged
                 }
             }
-            const Body4<R>* pl = reinterpret_cast<const Body4<R>*>(planets_) + tile * (ASTRO_MAX_PLANETS * 32) + gl;
-            const Body4<R>* bl = reinterpret_cast<const Body4<R>*>(bullets_) + tile * (size_t)(32 * K) + tile_list_offset(meta_ + tile * 32, gl, lane);
+            const Body4<R>* pl = pl_tile + gl;
+            const Body4<R>* bl = bl_tile + off;
             float best[4][4];
 #pragma unroll
             for (int nt = 0; nt < 4; nt++)
@@ -1471,7 +1505,10 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
             for (int r0 = 0; r0 < rows; r0 += 8) {
                 const int r = r0 + gq;
                 const bool valid = r < rows;
-                if (valid && any_obj) {                          // this lane's component(s) of the row's object: the quad covers its 16 bytes
+                if (r0 == 0) {                                   // (loaded one game ahead)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (obj_idx[j] >= 0) { xa[j] = ov[j]; xb[j] = ov[j]; }
+                } else if (valid && any_obj) {                   // this lane's component(s) of the row's object: the quad covers its 16 bytes
                     const R* o = reinterpret_cast<const R*>(r < np ? &pl[r * 32] : &bl[r - np]);
 #pragma unroll
                     for (int j = 0; j < 4; j++) if (obj_idx[j] >= 0) { const float v = (float)o[obj_idx[j]]; xa[j] = v; xb[j] = v; }
