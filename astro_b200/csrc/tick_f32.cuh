@@ -28,8 +28,20 @@ constexpr int kTickWarps = kTickThreads / 32;
 #define ASTRO_PREFETCH_PLANETS 4
 #endif
 
+// Bullets staged per round: W windows x 32 (512 bytes each).  The launch of several ticks is bound by issue slots and takes every
+// warp it can get: 7 windows (224 bullets, 7,216 bytes per warp) let 28 one-warp CTAs share an SM's shared memory — also what the
+// registers allow (72 x 32 x 28) — against 26 with 8; the one-tick launch is bound by HBM and is slower with more address streams
+// open at once (A/B at 1,048,576 games, 7 windows + 28 CTAs against 8 + 26: several ticks per launch 59.7 -> 59.2 us per tick,
+// 131,072 games — 4,096 tiles, ONE wave of 4,144 resident CTAs instead of 3,848 + 248 — 12.6 -> 11.4; one launch per tick
+// 67.8 -> 70.2), so each form keeps its own.  (A tile with more bullets than a round holds takes a second round: correct, rare.)
 #ifndef ASTRO_STAGE_WINDOWS
 #define ASTRO_STAGE_WINDOWS 8
+#endif
+#ifndef ASTRO_STAGE_WINDOWS_MANY
+#define ASTRO_STAGE_WINDOWS_MANY 7
+#endif
+#ifndef ASTRO_TICK_MIN_BLOCKS_MANY
+#define ASTRO_TICK_MIN_BLOCKS_MANY 28
 #endif
 // Round 2, instruction diet of the fused form (issue-bound; ncu dynamic instruction counts in profiles/r2_ab_diet.md):
 #ifndef ASTRO_OPT_STAGE
@@ -38,12 +50,12 @@ constexpr int kTickWarps = kTickThreads / 32;
 #ifndef ASTRO_OPT_PTRS
 #define ASTRO_OPT_PTRS 1      /* per-tick pointers = base + tick * stride (stride 0 for an absent array): no null tests, no 64-bit products */
 #endif
-constexpr int kStageWindows = ASTRO_STAGE_WINDOWS;   // bullets staged per round: 8 windows x 32 = 256 (4 KB per warp)
 
 // Per-game entries used by the bullet loop are indexed by the game's rank among the tile's games
 // that own bullets (`cid`): item -> cid comes out of one ballot per window, no lookup table.
-struct TileScratch {               // per warp
-    float4 bul[kStageWindows * 32];  // the tile's bullet list, staged by cp.async; survivors are compacted here
+template <int W>
+struct TileScratchT {              // per warp
+    float4 bul[W * 32];            // the tile's bullet list, staged by cp.async; survivors are compacted here
     float4 fsxy[32];               // [cid] OLD ship0.xy, ship1.xy          } what the bullet loop reads
     float4 fpxy[2][32];            // [cid] OLD planet0.xy planet1.xy / 2,3 } (transposed pairs)
     float4 sxy[32];                // [lane] OLD ship positions  }
@@ -52,7 +64,7 @@ struct TileScratch {               // per warp
     uint32_t hits[32];             // [cid] bits 0-1: ship hits found by the bullet loop; bits 8+: np
     int32_t shift[32];             // [cid] new list: item j of the compacted list moves to j + shift (kDrop: game over)
     uint16_t gstart[34];           // [cid] first survivor of the game in the compacted list; [n] = survivors of the tile
-    uint8_t ref[kStageWindows * 32];   // compacted item -> cid
+    uint8_t ref[W * 32];               // compacted item -> cid
     uint32_t used;                     // fresh-game mode: records of the tile's ring consumed since the last refill
 };
 constexpr int kDrop = 0x40000000;
@@ -354,10 +366,11 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar&
 template <int S, bool STATS, bool MANY, bool BOT>
 // `last` = no further tick of this tile follows in this launch: only then do meta, ships and bearings go to memory
 // (planets and the bullet list always do), and the tile's statistics (`stat_acc`, summed over the launch's ticks).
-__device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratch& t, const unsigned lane,
+__device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratchT<MANY ? ASTRO_STAGE_WINDOWS_MANY : ASTRO_STAGE_WINDOWS>& t, const unsigned lane,
                                           const unsigned tile_index, const TileIn& in, TileIn& next, const bool last,
                                           unsigned& stat_acc, const bool have_fire_word) {
     using B4 = Body4<float>;
+    constexpr int kStageWindows = MANY ? ASTRO_STAGE_WINDOWS_MANY : ASTRO_STAGE_WINDOWS;
     const unsigned full = 0xffffffffu;
     const int g = (int)(tile_index * 32u + lane);
     const Consts& c = p.c;
@@ -869,7 +882,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 // one RED per counter and tile per LAUNCH is cheap, and astro_stats needs no fold pass afterwards.  The
                 // counters are kept kStatReplicas times (one 128-byte line each, picked by the tile), so that the REDs of
                 // all the tiles do not queue on a single L2 line.
-                if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(&p.stats[(tile_index & (unsigned)(kStatReplicas - 1)) * 16u + lane], (unsigned long long)stat_acc);
+                if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(&p.stats[(blockIdx.x & (unsigned)(kStatReplicas - 1)) * 16u + lane], (unsigned long long)stat_acc);   // (blockIdx: no live register)
             } else {
                 unsigned* slot = p.stat_slots + ((size_t)(g >> 5) * 16u + lane);
                 if (lane < ASTRO_N_STATS && stat_acc) atomicAdd(slot, stat_acc);  // RED: fire and forget
@@ -885,7 +898,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
 // software pipeline — were built and measured 12-48 % slower: profiles/r1_ab_v6_experiments.md.)
 // (BOT: the instantiation with the ScriptBot inside — float64 arithmetic of its own, far more registers: fewer CTAs per SM)
 template <int S, bool STATS, bool MANY, bool BOT = false>
-__global__ void __launch_bounds__(kTickThreads, BOT ? 8 : ASTRO_TICK_MIN_BLOCKS) tick_f32_kernel(const __grid_constant__ TickParams p) {
+__global__ void __launch_bounds__(kTickThreads, BOT ? 8 : (MANY ? ASTRO_TICK_MIN_BLOCKS_MANY : ASTRO_TICK_MIN_BLOCKS)) tick_f32_kernel(const __grid_constant__ TickParams p) {
+    using TileScratch = TileScratchT<MANY ? ASTRO_STAGE_WINDOWS_MANY : ASTRO_STAGE_WINDOWS>;
     __shared__ TileScratch s_tiles[kTickWarps];
     unsigned tile = (blockIdx.x * kTickThreads + threadIdx.x) >> 5;   // among the p.tiles tiles of this launch, from p.tile0
 #if ASTRO_PDL

@@ -11,7 +11,7 @@ except Exception as e: print('FAILED', e)")" | tee -a gpurun_out/ab_env.log
 }
 for r in $(seq ${REPS:-1}); do
   for steps in ${STEPS:-20 64}; do
-    for f in build_ab/*.so; do [ -f $f ] && run "$(basename $f)" $steps ASTRO_B200_LIB=$PWD/$f; done
+    for f in build_ab/*.so; do if [ -f $f ]; then run "$(basename $f)" $steps ASTRO_B200_LIB=$PWD/$f; fi; done
     for cfg in $1; do
       run "$cfg" $steps $(echo $cfg | tr ',' ' ')
     done
