@@ -778,11 +778,21 @@ struct Mt19937Head {
     uint32_t lo[kCreateWords + 1], hi[kCreateWords];
     int k;
     __device__ void seed(uint32_t x) {
+        // init_genrand: 436 dependent steps of three instructions (shift, xor, multiply-add).  Three loops, so that the
+        // long middle stretch carries no store and no test (one loop with both predicates compiled to ~12 instructions per
+        // step: 32 M warp-instructions per refill of 200,000 games, 57 us; now ~9 M).
         lo[0] = x;
-        for (int j = 1; j < 397 + kCreateWords; j++) {
+#pragma unroll
+        for (int j = 1; j <= kCreateWords; j++) {
             x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)j;
-            if (j <= kCreateWords) lo[j] = x;
-            if (j >= 397) hi[j - 397] = x;
+            lo[j] = x;
+        }
+#pragma unroll 4
+        for (int j = kCreateWords + 1; j < 397; j++) x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)j;
+#pragma unroll
+        for (int j = 397; j < 397 + kCreateWords; j++) {
+            x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)j;
+            hi[j - 397] = x;
         }
         k = 0;
     }
@@ -1007,22 +1017,31 @@ __global__ void __launch_bounds__(256) refill_tasks_kernel(const __grid_constant
     if (u) f.tile_used[t] = 0u;
 }
 
+// (a grid that covers the device a few times over, striding over the tasks: the number of tasks is only known on the
+// device, and a grid sized for the whole ring — 24,576 CTAs at 1M games, nearly all of them empty — cost 17 us by itself.
+// The CTA that finishes last moves the cursor on: f.cursor[3] counts the finished CTAs.)
 template <int S>
 __global__ void __launch_bounds__(64) refill_create_kernel(const __grid_constant__ FreshParams f, const __grid_constant__ CreateParams q) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned n_tasks = (unsigned)f.cursor[2];
-    if (i >= n_tasks) return;
-    const unsigned long long pos = f.cursor[0] + i;
-    const uint32_t seed = f.seeds[(uint32_t)pos & f.seed_mask];
-    CreatedGame o;
-    create_game<S>(seed, q, o);
-    write_record<S>(f.ring + (size_t)f.tasks[i] * 8, o, (uint32_t)pos, seed);
-}
-// (after refill_create_kernel: the cursor moves on — a one-thread kernel, stream-ordered behind it)
-__global__ void refill_commit_kernel(const __grid_constant__ FreshParams f) {
-    f.cursor[0] += f.cursor[2];
-    f.cursor[1] += 1ull;
-    f.cursor[2] = 0ull;
+    const unsigned long long base = f.cursor[0];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tasks; i += gridDim.x * blockDim.x) {
+        const unsigned long long pos = base + i;
+        const uint32_t seed = f.seeds[(uint32_t)pos & f.seed_mask];
+        CreatedGame o;
+        create_game<S>(seed, q, o);
+        write_record<S>(f.ring + (size_t)f.tasks[i] * 8, o, (uint32_t)pos, seed);
+    }
+    __syncthreads();                       // every thread of the CTA has read the cursor and written its records
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&f.cursor[3], 1ull) + 1ull == (unsigned long long)gridDim.x) {
+            f.cursor[0] = base + n_tasks;
+            f.cursor[1] += 1ull;
+            f.cursor[2] = 0ull;
+            f.cursor[3] = 0ull;
+            __threadfence();
+        }
+    }
 }
 
 template <int S>
@@ -1959,6 +1978,7 @@ struct AstroBatch {
     AstroResetPool pool;
     uint32_t* d_fire_bits;
     int32_t n_sched_ticks, timeout_tick;
+    int32_t sm_count;
     unsigned long long* d_stats;   // [kStatReplicas][16]
     // astro_stats_allreduce: this rank's exchange buffer, the peers' (IPC-mapped) and the call counter
     unsigned long long* d_peer_own;
@@ -2199,16 +2219,15 @@ int fresh_refill(AstroBatch* b, cudaStream_t st) {
     fs->target.store(bound + 2ull * (unsigned long long)fs->capacity, std::memory_order_release);
     refill_scan_kernel<<<1, 1024, 0, st>>>(fs->f, fs->chunk_base);
     refill_tasks_kernel<<<(fs->f.n_tiles + 255) / 256, 256, 0, st>>>(fs->f, fs->chunk_base);
-    const int grid = (int)((fs->capacity + 63) / 64);
+    const int grid = (int)std::min<int64_t>((fs->capacity + 63) / 64, (int64_t)b->sm_count * 32);
     if (b->S == 2) refill_create_kernel<2><<<grid, 64, 0, st>>>(fs->f, fs->cq);
     else refill_create_kernel<1><<<grid, 64, 0, st>>>(fs->f, fs->cq);
-    refill_commit_kernel<<<1, 1, 0, st>>>(fs->f);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(fs->h_cursor, fs->f.cursor, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(fs->done[fs->refills % kFreshLead], st));
     fs->refills += 1;
     fs->ticks_since_refill = 0;
-    b->launches += 4;
+    b->launches += 3;
     return ASTRO_OK;
 }
 
@@ -2322,6 +2341,7 @@ int astro_batch_create(const AstroConfig* cfg, int32_t n_games, int32_t bullet_c
     b->device = device;
     b->S = cfg->solo ? 1 : 2;
     fill_consts(*cfg, b->c);
+    if (cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || b->sm_count <= 0) b->sm_count = 148;
     cudaError_t e = cudaMalloc(&b->d_stats, sizeof(unsigned long long) * 16 * kStatReplicas);
     if (e == cudaSuccess) e = cudaMemset(b->d_stats, 0, sizeof(unsigned long long) * 16 * kStatReplicas);
     const size_t slot_bytes = (size_t)(n_games / ASTRO_TILE) * 16 * sizeof(unsigned);
