@@ -43,6 +43,9 @@ constexpr int kTickWarps = kTickThreads / 32;
 #ifndef ASTRO_TICK_MIN_BLOCKS_MANY
 #define ASTRO_TICK_MIN_BLOCKS_MANY 28
 #endif
+#ifndef ASTRO_TICK_MIN_BLOCKS_BOT
+#define ASTRO_TICK_MIN_BLOCKS_BOT 12    /* the instantiation with the ScriptBot inside: float64 chains, 160 registers */
+#endif
 // Round 2, instruction diet of the fused form (issue-bound; ncu dynamic instruction counts in profiles/r2_ab_diet.md):
 #ifndef ASTRO_OPT_STAGE
 #define ASTRO_OPT_STAGE 1     /* several ticks per launch: staging requests unrolled and predicated, 2-3 instructions per window instead of ~14 */
@@ -898,7 +901,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
 // software pipeline — were built and measured 12-48 % slower: profiles/r1_ab_v6_experiments.md.)
 // (BOT: the instantiation with the ScriptBot inside — float64 arithmetic of its own, far more registers: fewer CTAs per SM)
 template <int S, bool STATS, bool MANY, bool BOT = false>
-__global__ void __launch_bounds__(kTickThreads, BOT ? 8 : (MANY ? ASTRO_TICK_MIN_BLOCKS_MANY : ASTRO_TICK_MIN_BLOCKS)) tick_f32_kernel(const __grid_constant__ TickParams p) {
+__global__ void __launch_bounds__(kTickThreads, BOT ? ASTRO_TICK_MIN_BLOCKS_BOT : (MANY ? ASTRO_TICK_MIN_BLOCKS_MANY : ASTRO_TICK_MIN_BLOCKS)) tick_f32_kernel(const __grid_constant__ TickParams p) {
     using TileScratch = TileScratchT<MANY ? ASTRO_STAGE_WINDOWS_MANY : ASTRO_STAGE_WINDOWS>;
     __shared__ TileScratch s_tiles[kTickWarps];
     unsigned tile = (blockIdx.x * kTickThreads + threadIdx.x) >> 5;   // among the p.tiles tiles of this launch, from p.tile0
