@@ -550,6 +550,26 @@ class BatchedGames:
         self.policy_nout = int(net.v0.weight.shape[0])
         nat.check(nat.lib().astro_policy_set_weights(self._h, w.ctypes.data_as(C.c_void_p), int(w.size), self.policy_nout))
 
+    def value_forward(self, features, out=None):
+        """`rl.ValueNetwork.forward` (rl.py:140-165) of the loaded network on a feature batch — float32 cuda
+        [..., rows, D] as `observe()` / `get_features_batch` give it — in one tensor-core kernel (astro_value_forward);
+        inference only.  Returns float32 [..., nout]."""
+        torch = _torch()
+        if not (features.is_cuda and features.dtype == torch.float32 and features.dim() >= 2):
+            raise ValueError('value_forward needs a float32 cuda tensor [..., rows, D]')
+        if features.shape[-1] != 1 + 5 * self.S + 4:
+            raise ValueError('feature width %d does not match this batch (%d)' % (features.shape[-1], 1 + 5 * self.S + 4))
+        x = features.contiguous()
+        lead, rows = x.shape[:-2], int(x.shape[-2])
+        n = 1
+        for d in lead:
+            n *= int(d)
+        nout = self.policy_nout
+        if out is None:
+            out = torch.empty(tuple(lead) + (nout,), dtype=torch.float32, device=x.device)
+        nat.check(nat.lib().astro_value_forward(self._h, x.data_ptr(), n, rows, out.data_ptr(), self._stream()))
+        return out
+
     def policy_controls(self, out=None, q_out=None, ships=None):
         """Greedy controls argmax_a Q(s, a) of the loaded network for every ship of every game, each
         from its own perspective (rl.QBot, rl.py:168-200) — features and network fused in one

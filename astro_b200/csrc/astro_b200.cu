@@ -1640,6 +1640,184 @@ policy_mma_kernel(const void* __restrict__ ships_, const void* __restrict__ ship
 }
 
 // ------------------------------------------------------------------------------------------
+// value_forward_kernel<DIN>: rl.ValueNetwork.forward (rl.py:140-165) on a FEATURE batch — what astro.rl's own callers
+// hold (get_features_batch / BatchedGames.observe() output) — for inference: features [n][rows][DIN] -> q [n][nout].
+// The network of policy_mma_kernel, same weights (fragments), same three-product FP16 split, fed from the tensor instead
+// of from the game state: a 16-row MMA tile = 8 consecutive rows of item A (tile rows 0-7) and of item B (rows 8-15); a
+// warp takes 16 items at a time — pairs (j, j + 8) — so that their pooled vectors make the head's 16-row tile.
+//   pooling = the reference's masked_max (rl.py:115-128): max over ALL rows of x - 1e9 * pad, pad = (features[row][0] < 0).
+//   A chunk of 8 rows that is padding for both items is skipped once each item has shown a live row (its maximum can no
+//   longer come from a padding row: pre-activations are far below 1e9); an item without any live row takes every chunk,
+//   exactly the reference's arithmetic.
+// ------------------------------------------------------------------------------------------
+#if ASTRO_POLICY_F16
+template <int DIN>
+__global__ void __launch_bounds__(kMmaWarps * 32, ASTRO_MMA_MIN_BLOCKS)
+value_forward_kernel(const float* __restrict__ features, float* __restrict__ q_out, int n_items, int rows, int nout,
+                     const PolicyFragWeights* __restrict__ frags) {
+    extern __shared__ float4 s_dyn[];
+    PolicyFrags& s_all = *reinterpret_cast<PolicyFrags*>(s_dyn);
+    const PolicyFragWeights& s_w = s_all.w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, t = lane & 3;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(frags);
+        uint4* dst = reinterpret_cast<uint4*>(&s_all.w);
+        for (int i = threadIdx.x; i < (int)(sizeof(PolicyFragWeights) / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    int col[4];                                   // this lane's feature columns: 2t, 2t + 1, 2t + 8, 2t + 9 (>= DIN: zero)
+#pragma unroll
+    for (int j = 0; j < 4; j++) col[j] = 2 * t + (j & 1) + 8 * (j >> 1);
+    float (*pool)[kPoolStride] = s_all.pool[warp];
+    const int n_groups = (n_items + 15) >> 4;
+    const size_t item_stride = (size_t)rows * DIN;
+    for (int grp = blockIdx.x * kMmaWarps + warp; grp < n_groups; grp += gridDim.x * kMmaWarps) {
+#pragma unroll 1
+        for (int j8 = 0; j8 < 8; j8++) {
+            const int ia = grp * 16 + j8, ib = ia + 8;
+            const bool has_a = ia < n_items, has_b = ib < n_items;       // (warp-uniform)
+            const float* fa = features + (size_t)(has_a ? ia : 0) * item_stride;
+            const float* fb = features + (size_t)(has_b ? ib : 0) * item_stride;
+            float best[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) best[nt][i] = -3.0e38f;
+            bool seen_a = !has_a, seen_b = !has_b;
+            for (int r0 = 0; r0 < rows; r0 += 8) {
+                const int r = r0 + gq;
+                const bool in_range = r < rows;
+                // the type flags first (column 0: lanes t == 0), handed to the quad
+                float flag_a = -1.f, flag_b = -1.f;
+                if (t == 0 && in_range) {
+                    if (has_a) flag_a = fa[(size_t)r * DIN];
+                    if (has_b) flag_b = fb[(size_t)r * DIN];
+                }
+                flag_a = __shfl_sync(0xffffffffu, flag_a, lane & ~3);
+                flag_b = __shfl_sync(0xffffffffu, flag_b, lane & ~3);
+                const bool live_a = in_range && has_a && !(flag_a < 0.f), live_b = in_range && has_b && !(flag_b < 0.f);
+                const bool any_live = __ballot_sync(0xffffffffu, live_a | live_b) != 0u;
+                if (!any_live && seen_a && seen_b) continue;             // padding only, and nobody's maximum can be there
+                seen_a |= __ballot_sync(0xffffffffu, live_a) != 0u;
+                seen_b |= __ballot_sync(0xffffffffu, live_b) != 0u;
+                float xa[4], xb[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    xa[j] = xb[j] = 0.f;
+                    if (col[j] < DIN && in_range) {
+                        if (has_a) xa[j] = (col[j] == 0) ? flag_a : fa[(size_t)r * DIN + col[j]];
+                        if (has_b) xb[j] = (col[j] == 0) ? flag_b : fb[(size_t)r * DIN + col[j]];
+                    }
+                }
+                float acc[4][4], nxt[4][4];
+                init_bias<4>(acc, s_w.bias[0], t);
+                {
+                    const float x0[8] = {xa[0], xa[1], xb[0], xb[1], xa[2], xa[3], xb[2], xb[3]};
+                    mma_kstep16<4>(acc, x0, &s_w.f0[0][0][0], lane);
+                }
+#pragma unroll
+                for (int layer = 1; layer <= 2; layer++) {
+                    const float4* wf = layer == 1 ? &s_w.f1[0][0][0] : &s_w.f2[0][0][0];
+                    init_bias<4>(nxt, s_w.bias[layer], t);
+                    mma_layer<4, true>(nxt, acc, wf, lane);
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) acc[nt][i] = nxt[nt][i];
+                }
+                // masked_max: x - 1e9 * pad (float32, as torch computes it), rows past the tensor excluded
+                const float pen_a = live_a ? 0.f : 1.0e9f, pen_b = live_b ? 0.f : 1.0e9f;
+                if (in_range) {
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
+                        if (has_a) { best[nt][0] = fmaxf(best[nt][0], __fsub_rn(acc[nt][0], pen_a)); best[nt][1] = fmaxf(best[nt][1], __fsub_rn(acc[nt][1], pen_a)); }
+                        if (has_b) { best[nt][2] = fmaxf(best[nt][2], __fsub_rn(acc[nt][2], pen_b)); best[nt][3] = fmaxf(best[nt][3], __fsub_rn(acc[nt][3], pen_b)); }
+                    }
+                }
+            }
+            float pooled[2];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                s_all.red[warp][gq][t][0] = make_float4(best[0][2 * half], best[0][2 * half + 1], best[1][2 * half], best[1][2 * half + 1]);
+                s_all.red[warp][gq][t][1] = make_float4(best[2][2 * half], best[2][2 * half + 1], best[3][2 * half], best[3][2 * half + 1]);
+                __syncwarp();
+                const int nt_u = lane >> 3, t_u = (lane >> 1) & 3, e_u = lane & 1;
+                float m = -3.0e38f;
+#pragma unroll
+                for (int qd = 0; qd < 8; qd++) m = fmaxf(m, reinterpret_cast<const float*>(&s_all.red[warp][qd][t_u][0])[2 * nt_u + e_u]);
+                pooled[half] = m;
+                __syncwarp();
+            }
+            pool[j8][lane] = (has_a && rows > 0) ? pooled[0] : 0.f;
+            pool[8 + j8][lane] = (has_b && rows > 0) ? pooled[1] : 0.f;
+        }
+        __syncwarp();
+        // The pooled vector of an item WITHOUT a live row is the reference's x - 1e9 (masked_max): far outside FP16's range.
+        // The first head layer is therefore taken per tile row on a power-of-two scaled copy of the row (exact), its
+        // accumulators scaled back and the bias added last; rows of ordinary magnitude keep scale 1.
+        float h1[4][4], h2[4][4], q4[1][4];
+        float xs[2][8];
+        float mx_a = 0.f, mx_b = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+            const float2 p0 = *reinterpret_cast<const float2*>(&pool[gq][16 * kk + 2 * t]), p1 = *reinterpret_cast<const float2*>(&pool[gq + 8][16 * kk + 2 * t]);
+            const float2 p2 = *reinterpret_cast<const float2*>(&pool[gq][16 * kk + 2 * t + 8]), p3 = *reinterpret_cast<const float2*>(&pool[gq + 8][16 * kk + 2 * t + 8]);
+            xs[kk][0] = p0.x; xs[kk][1] = p0.y; xs[kk][2] = p1.x; xs[kk][3] = p1.y; xs[kk][4] = p2.x; xs[kk][5] = p2.y; xs[kk][6] = p3.x; xs[kk][7] = p3.y;
+            mx_a = fmaxf(mx_a, fmaxf(fmaxf(fabsf(p0.x), fabsf(p0.y)), fmaxf(fabsf(p2.x), fabsf(p2.y))));
+            mx_b = fmaxf(mx_b, fmaxf(fmaxf(fabsf(p1.x), fabsf(p1.y)), fmaxf(fabsf(p3.x), fabsf(p3.y))));
+        }
+#pragma unroll
+        for (int d = 1; d <= 2; d <<= 1) {
+            mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, d));
+            mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, d));
+        }
+        // scale 2^-e with 2^e the power of two above max / 1024 (1 for rows below 1024)
+        // (max in [2^k, 2^(k+1)), biased exponent E = k + 127: scale 2^(9 - k) = bits (263 - E) << 23, its inverse (E - 9) << 23)
+        const uint32_t ea = __float_as_uint(mx_a) >> 23, eb = __float_as_uint(mx_b) >> 23;
+        const bool big_a = mx_a > 1024.f && mx_a < 3.0e38f, big_b = mx_b > 1024.f && mx_b < 3.0e38f;
+        const float sc_a = big_a ? __uint_as_float((263u - ea) << 23) : 1.f, inv_a = big_a ? __uint_as_float((ea - 9u) << 23) : 1.f;
+        const float sc_b = big_b ? __uint_as_float((263u - eb) << 23) : 1.f, inv_b = big_b ? __uint_as_float((eb - 9u) << 23) : 1.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) h1[nt][i] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+            const float x[8] = {xs[kk][0] * sc_a, xs[kk][1] * sc_a, xs[kk][2] * sc_b, xs[kk][3] * sc_b, xs[kk][4] * sc_a, xs[kk][5] * sc_a, xs[kk][6] * sc_b, xs[kk][7] * sc_b};
+            mma_kstep16<4>(h1, x, &s_w.v1[kk][0][0], lane);
+        }
+        {
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const float2 b2 = s_w.bias[3][nt][t];
+                h1[nt][0] = __fmaf_rn(h1[nt][0], inv_a, b2.x); h1[nt][1] = __fmaf_rn(h1[nt][1], inv_a, b2.y);
+                h1[nt][2] = __fmaf_rn(h1[nt][2], inv_b, b2.x); h1[nt][3] = __fmaf_rn(h1[nt][3], inv_b, b2.y);
+            }
+        }
+        // v[0], v[1]: h = softsign(W h + b) (rl.py:160-162) — the activation follows the layer here
+        init_bias<4>(h2, s_w.bias[4], t);
+        mma_layer<4, true>(h2, h1, &s_w.v2[0][0][0], lane);
+        {
+            const float2 b2 = s_w.bias_v0[t];
+            q4[0][0] = b2.x; q4[0][1] = b2.y; q4[0][2] = b2.x; q4[0][3] = b2.y;
+        }
+        mma_layer<1, true>(q4, h2, &s_w.v0[0][0], lane);
+        // this lane: outputs 2t, 2t + 1 of item grp * 16 + gq (entries 0-1) and of item grp * 16 + 8 + gq (entries 2-3)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            if (2 * t + e < nout) {
+                const int ia = grp * 16 + gq, ib = ia + 8;
+                if (ia < n_items) q_out[(size_t)ia * nout + 2 * t + e] = tanhf(q4[0][e]);
+                if (ib < n_items) q_out[(size_t)ib * nout + 2 * t + e] = tanhf(q4[0][2 + e]);
+            }
+        }
+        __syncwarp();
+    }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // explore_kernel: rl.EpsilonGreedy.__call__ (rl.py:10-30) for every ship — the random policy that
 // rl.QBotTrainer lays over the greedy network (rl.py:249-258: action = greedy if greedy is not None
 // else argmax q).  Per ship a two-state process: idle -> a random control 0..4 (randint(0, 5): never 5)
@@ -3422,6 +3600,34 @@ int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* strea
     gather_stats_kernel<<<1, 256, 0, st>>>(b->d_stats, (long long*)counters_dev, clear ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     return ASTRO_OK;
+}
+
+int astro_value_forward(AstroBatch* b, const float* features, int32_t n_items, int32_t rows, float* q_out, void* stream) {
+    if (int r = check(b, false)) return r;
+    if (b->policy_nout <= 0 || !b->d_pol_frags) return fail(ASTRO_E_STATE, "astro_policy_set_weights has not been called");
+    if (!features || !q_out) return fail(ASTRO_E_INVALID, "null argument");
+    if (n_items < 0 || rows < 1) return fail(ASTRO_E_INVALID, "n_items >= 0 and rows >= 1");
+    if (n_items == 0) return ASTRO_OK;
+#if ASTRO_POLICY_F16
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = ((n_items + 15) / 16 + kMmaWarps - 1) / kMmaWarps;      // a warp takes 16 items at a time
+    if (grid > b->sm_count * ASTRO_MMA_MIN_BLOCKS) grid = b->sm_count * ASTRO_MMA_MIN_BLOCKS;
+    const int smem = (int)sizeof(PolicyFrags);
+    if (b->S == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(value_forward_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        value_forward_kernel<15><<<grid, kMmaWarps * 32, smem, st>>>(features, q_out, n_items, rows, b->policy_nout, b->d_pol_frags);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(value_forward_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        value_forward_kernel<10><<<grid, kMmaWarps * 32, smem, st>>>(features, q_out, n_items, rows, b->policy_nout, b->d_pol_frags);
+    }
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 1;
+    return ASTRO_OK;
+#else
+    (void)stream;
+    return fail(ASTRO_E_STATE, "astro_value_forward needs the FP16 tensor-core build (ASTRO_POLICY_F16=1)");
+#endif
 }
 
 int astro_stats_peer_create(AstroBatch* b, int32_t rank, int32_t world, uint8_t* handle_out) {

@@ -84,7 +84,8 @@ def algorithmic_bytes(st, S, packed=False, planes=False, events=True, with_rewar
 def config5_rollout(args, local, pool):
     """BASELINE configs[4]: self-play rollout, 16,384 games x 1,000 ticks, observation extraction feeding the astro.rl
     policy batch every tick, both ships driven by the network (greedy), auto-reset.  Three forms of the same loop:
-    observe() -> PyTorch ValueNetwork -> argmax -> step; observe(shared) -> forward_both; the fused policy kernel
+    observe() -> PyTorch ValueNetwork -> argmax -> step; observe(shared) -> forward_both; observe() -> the same forward as ONE
+    tensor-core kernel (ValueNetwork.forward under no_grad = astro_value_forward); the fused policy kernel
     inside astro_rollout_device (no observation tensor, no host between ticks)."""
     import torch
     from astro_b200 import core, rl
@@ -98,7 +99,8 @@ def config5_rollout(args, local, pool):
     out = dict(config='BASELINE configs[4]: %d games x %d ticks, observe -> astro.rl ValueNetwork (both ships) -> step, auto-reset' % (N, T),
                games=N, ticks=T, unit=UNIT)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for form in ('observe+torch', 'observe_shared+forward_both', 'fused policy kernel (rollout_device)'):
+    for form in ('observe+torch', 'observe_shared+forward_both', 'observe -> ValueNetwork.forward (astro_value_forward kernel)',
+                 'fused policy kernel (rollout_device)'):
         g = BatchedGames(core.DEFAULT_CONFIG, N, bullet_cap=args.bullet_cap, precision=32, device=local, seed=3)
         g.set_reset_pool_arrays(pool['ships'], pool['planets'], pool['np'])
         g.reset_all()
@@ -119,7 +121,9 @@ def config5_rollout(args, local, pool):
                     return
                 for _ in range(ticks):
                     if form.startswith('observe+'):
-                        a = net(observe(False)).argmax(-1).to(torch.uint8)
+                        a = net.forward_torch(observe(False)).argmax(-1).to(torch.uint8)
+                    elif form.startswith('observe ->'):
+                        a = net(observe(False)).argmax(-1).to(torch.uint8)     # (no_grad, cuda float32: the fused inference kernel)
                     else:
                         a = net.forward_both(observe(True)).argmax(-1).to(torch.uint8)
                     g.step(a, auto_reset=True, want_reward=False)

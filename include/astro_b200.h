@@ -390,6 +390,14 @@ int astro_nstep_experiences(AstroBatch* b, const uint8_t* events, int32_t n_tick
  * an NCCL all-reduce) on the stream; clear != 0 zeroes them afterwards. */
 int astro_stats(AstroBatch* b, int64_t* counters_dev, int32_t clear, void* stream);
 
+/* rl.ValueNetwork.forward (rl.py:140-165) on a feature batch — the tensor astro.rl's own callers hold (get_features_batch,
+ * rl.py:101-112, or astro_observe's output) — for inference, with the batch's network (astro_policy_set_weights): the three
+ * per-object layers, masked_max over the rows (rl.py:115-128: max of x - 1e9 * (features[row][0] < 0)), the head, tanh.
+ *   features f32 [n_items][rows][din] device, din = 15 (duel) / 10 (solo), contiguous
+ *   q_out    f32 [n_items][nout] device
+ * Tensor-core kernel (FP16 three-product split, fp32 accumulation): within 2e-6 of the PyTorch fp32 network. */
+int astro_value_forward(AstroBatch* b, const float* features, int32_t n_items, int32_t rows, float* q_out, void* stream);
+
 /* The same counters summed over the N processes of one node (one GPU each; "NCCL used only for the optional episode-stats
  * reduction" in the north star — this is that reduction without NCCL): ONE kernel per rank that stores the rank's counters
  * into every rank's exchange buffer through peer memory (NVLink / NVSwitch, buffers mapped by CUDA IPC), waits for the other

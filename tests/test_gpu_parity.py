@@ -440,7 +440,7 @@ def test_value_network_single_vs_batch_and_padding_neutral():
     assert float((batch - net.evaluate_batch(states[::-1]).flip(0)).abs().max()) < 1e-6
     games = _games(core.DEFAULT_CONFIG, len(states), bullet_cap=32, precision=64)
     games.set_states(states, ticks=np.zeros(len(states), dtype=np.int64))
-    q = net(games.observe())                     # [n, 2, 6]: 36 rows incl. all -1 padding rows
+    q = net.forward_torch(games.observe())       # [n, 2, 6]: 36 rows incl. all -1 padding rows
     assert float((q[:, 0] - batch).abs().max()) < 1e-6
     rolled = net.evaluate_batch([core.roll_ships(s, 1) for s in states])
     assert float((q[:, 1] - rolled).abs().max()) < 1e-6
@@ -720,7 +720,7 @@ def test_observe_shared_and_forward_both():
     torch.manual_seed(0)
     net = rl.ValueNetwork(solo=False, nout=6).to(full.device)
     with torch.no_grad():
-        q_full = net(full)                   # [N, 2, 6]
+        q_full = net.forward_torch(full)     # [N, 2, 6]
         q_both = net.forward_both(shared)    # [N, 2, 6]
     assert q_both.shape == q_full.shape
     assert float((q_both - q_full).abs().max()) <= 1e-6
@@ -798,7 +798,7 @@ def test_policy_kernel_matches_value_network(solo):
     with torch.no_grad():
         for prm in net.parameters():              # livelier than the default init: spread the outputs
             prm.mul_(3.0)
-        want = net(games.observe())               # [N, S, 6]
+        want = net.forward_torch(games.observe())  # [N, S, 6]
     games.set_policy(net)
     q = torch.empty((games.n_pad, S, 6), dtype=torch.float32, device=games.device)
     act = games.policy_controls(q_out=q)
@@ -843,7 +843,7 @@ def test_policy_rollout_equals_torch_rollout(N, T):
         same = 0
         for k in range(T):
             with torch.no_grad():
-                a_torch = net(games.observe()).argmax(-1).to(torch.uint8)
+                a_torch = net.forward_torch(games.observe()).argmax(-1).to(torch.uint8)
             a_fused = games.policy_controls()[:N]
             same += int((a_torch == a_fused).sum())
             games.step(a_fused if fused else a_torch, auto_reset=True)
@@ -962,7 +962,7 @@ def test_policy_kernel_float64_state():
     q = torch.empty((games.n_pad, 2, 6), dtype=torch.float32, device='cuda')
     games.policy_controls(q_out=q)
     with torch.no_grad():
-        want = net(games.observe())
+        want = net.forward_torch(games.observe())
     assert float((q[:N] - want).abs().max()) <= 2e-6
 
 
@@ -1278,7 +1278,8 @@ def test_policy_kernel_matches_reference_network_outputs(precision):
         net = net.cuda()
         with torch.no_grad():
             obs = games.observe()
-            assert float((net(obs)[:len(states)].cpu() - torch.from_numpy(want)).abs().max()) <= tol
+            assert float((net.forward_torch(obs)[:len(states)].cpu() - torch.from_numpy(want)).abs().max()) <= tol
+            assert float((net(obs)[:len(states)].cpu() - torch.from_numpy(want)).abs().max()) <= tol      # the fused kernel (astro_value_forward)
             if not solo:
                 both = net.forward_both(games.observe(shared=True))
                 assert float((both[:len(states)].cpu() - torch.from_numpy(want)).abs().max()) <= tol
@@ -1304,7 +1305,7 @@ def test_two_batches_hold_two_networks():
         q = torch.empty((g.n_pad, 2, 6), dtype=torch.float32, device='cuda')
         g.policy_controls(q_out=q)
         with torch.no_grad():
-            assert float((q[:256] - net(g.observe())).abs().max()) <= 2e-6
+            assert float((q[:256] - net.forward_torch(g.observe())).abs().max()) <= 2e-6
         outs.append(q)
     assert float((outs[0] - outs[1]).abs().max()) > 1e-3
 
@@ -1740,3 +1741,68 @@ def test_stats_allreduce_over_peer_memory_equals_nccl(tmp_path):
     for x in res:
         assert x['ok'], x
         assert len(x['rounds']) == 7 and all(x['rounds']), x
+
+
+# ------------------------------------------------------------------ the network on a feature batch (astro_value_forward)
+
+@pytest.mark.parametrize('solo', [False, True])
+def test_value_forward_kernel_matches_the_torch_network(solo):
+    """rl.ValueNetwork.forward on cuda float32 feature batches under no_grad = value_forward_kernel: within 2e-6 of the
+    layer-by-layer PyTorch forward (the reference's, rl.py:140-165) on real observations (both perspectives, -1 padding),
+    on ragged shapes (item counts off the 16-item groups, row counts off the 8-row chunks), on batches whose masked rows
+    hold arbitrary values or that have no live row at all (masked_max's x - 1e9 * pad arithmetic, rl.py:115-128), and
+    with autograd on it falls back to PyTorch (gradients flow)."""
+    import torch
+    from astro_b200 import rl
+    cfg = core.SOLO_CONFIG if solo else core.DEFAULT_CONFIG
+    S, D = (1, 10) if solo else (2, 15)
+    torch.manual_seed(3)
+    net = rl.ValueNetwork(solo=solo, nout=6).cuda()
+    with torch.no_grad():
+        for prm in net.parameters():
+            prm.mul_(2.0)
+    games = _games(cfg, 4096, bullet_cap=32, precision=32, seed=4)
+    games.set_reset_pool_on_device(256)
+    games.reset_all()
+    games.step_many(200, None, auto_reset=True)
+    obs = games.observe()                                     # [n, S, 36, D]
+    with torch.no_grad():
+        want = net.forward_torch(obs)
+        got = net(obs)
+        assert got.shape == want.shape and float((got - want).abs().max()) <= 2e-6
+        # ragged: 37 items (two groups and a bit), 13 rows; a single item; rows < 8
+        for n_items, rows in ((37, 13), (1, 36), (16, 5), (33, 8)):
+            x = obs[:n_items, 0, :rows].contiguous()
+            assert float((net(x) - net.forward_torch(x)).abs().max()) <= 2e-6, (n_items, rows)
+        # masked rows with arbitrary contents, live rows anywhere (not a prefix), items without a live row
+        g = torch.Generator(device='cuda').manual_seed(5)
+        x = torch.randn((101, 19, D), device='cuda', generator=g)
+        x[..., 0] = (torch.rand((101, 19), device='cuda', generator=g) < 0.4).float() * 2 - 1     # flag +1 live / -1 masked
+        x[7, :, 0] = -1.0
+        x[64, :, 0] = -1.0
+        w, gt = net.forward_torch(x), net(x)
+        assert float((gt - w).abs().max()) <= 2e-6
+        # the parameters change: the next call uploads them again
+        for prm in net.parameters():
+            prm.mul_(0.5)
+        assert float((net(obs) - net.forward_torch(obs)).abs().max()) <= 2e-6
+    # with autograd the PyTorch path runs
+    q = net(obs[:8])
+    q.sum().backward()
+    assert net.f0.weight.grad is not None and float(net.f0.weight.grad.abs().sum()) > 0
+
+
+def test_value_forward_abi_errors():
+    import torch
+    games = _games(core.DEFAULT_CONFIG, 64, bullet_cap=32, precision=32)
+    L = nat.lib()
+    x = torch.zeros((4, 8, 15), device='cuda')
+    q = torch.zeros((4, 6), device='cuda')
+    assert L.astro_value_forward(games._h, x.data_ptr(), 4, 8, q.data_ptr(), None) == -3      # no weights yet
+    from astro_b200 import rl
+    games.set_policy(rl.ValueNetwork(solo=False, nout=6))
+    assert L.astro_value_forward(games._h, None, 4, 8, q.data_ptr(), None) == -1
+    assert L.astro_value_forward(games._h, x.data_ptr(), 4, 0, q.data_ptr(), None) == -1
+    assert L.astro_value_forward(games._h, x.data_ptr(), 0, 8, q.data_ptr(), None) == 0
+    with pytest.raises(ValueError):
+        games.value_forward(torch.zeros((4, 8, 10), device='cuda'))
