@@ -2303,11 +2303,21 @@ cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
     const int grid = (p.tiles * 32 + kTickThreads - 1) / kTickThreads;
     // experiment knob (tools/exp_tick.py): unused dynamic shared memory caps the resident CTAs per SM
     static const size_t extra = getenv("ASTRO_EXTRA_SMEM") ? (size_t)atoi(getenv("ASTRO_EXTRA_SMEM")) : 0;
+    // The production rollout's options — duel games, packed controls in, event planes out, no reward / done arrays, auto-reset
+    // from the pool — have instantiations of their own (tick_f32.cuh, FIX) in which those options are compile-time constants:
+    // 56.4 against 60.8 us per tick at 20 ticks per launch (same box).  ASTRO_TICK_NO_FIX=1: the generic instantiations (A/B).
+    static const bool no_fix = getenv("ASTRO_TICK_NO_FIX") && atoi(getenv("ASTRO_TICK_NO_FIX")) != 0;
+    const bool fix = S == 2 && !no_fix && !p.bot_modes && p.actions && p.events && !p.reward && !p.done && !p.ring && !p.step_base && !p.game_pos && p.pool_size > 0 &&
+                     (p.flags & (ASTRO_TICK_PACKED_CONTROLS | ASTRO_TICK_EVENT_PLANES | ASTRO_TICK_AUTO_RESET)) ==
+                         (ASTRO_TICK_PACKED_CONTROLS | ASTRO_TICK_EVENT_PLANES | ASTRO_TICK_AUTO_RESET) && !(p.flags & 1024);
     if (p.bot_modes) {              // bots inside the tick: the many-tick form, whatever n_fused
         if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, true, true><<<grid, kTickThreads, extra, st>>>(p);
         else tick_f32_kernel<S, true, true, true><<<grid, kTickThreads, extra, st>>>(p);
     } else if (p.n_fused > 1) {
-        if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, true><<<grid, kTickThreads, extra, st>>>(p);
+        if (fix) {
+            if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<2, false, true, false, true><<<grid, kTickThreads, extra, st>>>(p);
+            else tick_f32_kernel<2, true, true, false, true><<<grid, kTickThreads, extra, st>>>(p);
+        } else if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, true><<<grid, kTickThreads, extra, st>>>(p);
         else tick_f32_kernel<S, true, true><<<grid, kTickThreads, extra, st>>>(p);
     } else {
 #if ASTRO_PDL
@@ -2323,10 +2333,17 @@ cudaError_t launch_tick_f32(const TickParams& p, cudaStream_t st) {
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        if (fix) {
+            if (p.flags & ASTRO_TICK_NO_STATS) return cudaLaunchKernelEx(&cfg, tick_f32_kernel<2, false, false, false, true>, p);
+            return cudaLaunchKernelEx(&cfg, tick_f32_kernel<2, true, false, false, true>, p);
+        }
         if (p.flags & ASTRO_TICK_NO_STATS) return cudaLaunchKernelEx(&cfg, tick_f32_kernel<S, false, false>, p);
         return cudaLaunchKernelEx(&cfg, tick_f32_kernel<S, true, false>, p);
 #else
-        if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, false><<<grid, kTickThreads, extra, st>>>(p);
+        if (fix) {
+            if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<2, false, false, false, true><<<grid, kTickThreads, extra, st>>>(p);
+            else tick_f32_kernel<2, true, false, false, true><<<grid, kTickThreads, extra, st>>>(p);
+        } else if (p.flags & ASTRO_TICK_NO_STATS) tick_f32_kernel<S, false, false><<<grid, kTickThreads, extra, st>>>(p);
         else tick_f32_kernel<S, true, false><<<grid, kTickThreads, extra, st>>>(p);
 #endif
     }

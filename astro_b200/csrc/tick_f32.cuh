@@ -334,7 +334,7 @@ struct TileIn {
     uint32_t ctl_raw;   // the tile's control bytes of this lane's game (S bytes), when actions are given
     uint32_t fire_word; // (several ticks per launch) the fire-schedule word of this game's tick, requested at the top
 };
-template <int S, bool WARM_PLANETS = true>
+template <int S, bool FIX = false, bool WARM_PLANETS = true>
 __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar& v, unsigned tile, unsigned lane, TileIn& in) {
     const size_t g = (size_t)tile * 32 + lane;
     in.meta = LD_STREAM(&p.meta[g]);
@@ -355,7 +355,7 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar&
     }
     if (S == 1) { in.shv[1] = in.shv[0]; in.sb[1] = in.sb[0]; }  // S == 1: the second half of every ship pair mirrors ship 0
     in.ctl_raw = 0;
-    if (v.actions) in.ctl_raw = load_controls<S>(v.actions, g, (p.flags & ASTRO_TICK_PACKED_CONTROLS) != 0);
+    if (FIX || v.actions) in.ctl_raw = load_controls<S>(v.actions, g, FIX || (p.flags & ASTRO_TICK_PACKED_CONTROLS) != 0);
     // Everything above is ONE round trip to HBM only if it is requested before the first use of meta.
     // ptxas is free to hoist meta-dependent code (it drags a later load and its address arithmetic up)
     // above these requests, which then leave a whole round trip late — seen at random from build to
@@ -366,7 +366,10 @@ __device__ __forceinline__ void load_tile_in(const TickParams& p, const TickVar&
 // One core.step for the 32 games of one tile, by one warp.
 // `next` receives what the following tick of the same tile would load from the rows this tick wrote (meta, ships,
 // bearings): inside a launch that runs several ticks they are handed on in registers.
-template <int S, bool STATS, bool MANY, bool BOT>
+// FIX = the launch's options are the production rollout's, known at compile time (launch_tick_f32 checks them): duel games,
+// packed controls given, event planes written, no reward / done arrays, auto-reset from the pool (no ring, no captured
+// step base) — the tests of those options and the address arithmetic of the absent arrays fold away.
+template <int S, bool STATS, bool MANY, bool BOT, bool FIX>
 // `last` = no further tick of this tile follows in this launch: only then do meta, ships and bearings go to memory
 // (planets and the bullet list always do), and the tile's statistics (`stat_acc`, summed over the launch's ticks).
 __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratchT<MANY ? ASTRO_STAGE_WINDOWS_MANY : ASTRO_STAGE_WINDOWS>& t, const unsigned lane,
@@ -396,7 +399,9 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     float sb[2] = {in.sb[0], in.sb[1]};
     int ctl[2];
     bool bad_ctl = false;
-    if (v.actions) {
+    const bool has_ring = !FIX && p.ring != nullptr;
+    const uint32_t step_base = FIX ? 0u : (p.step_base ? *p.step_base : 0u);
+    if (FIX || v.actions) {
         ctl[0] = (int)(in.ctl_raw & 0xffu);
         ctl[1] = S == 2 ? (int)(in.ctl_raw >> 8) : ctl[0];
         // codes above 5 are outside the reference's table (core.py:220-227): no-op control, tick flagged.
@@ -416,7 +421,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // What the END of the tick will need from memory is requested now, off the critical path: the
     // fire-schedule word of this game's tick and, with auto-reset, the planet count of the pool
     // entry that would replace the game (the pick is keyed on the stream step, not on state).
-    const bool auto_reset = (p.flags & ASTRO_TICK_AUTO_RESET) && (p.pool_size > 0 || p.ring != nullptr);
+    const bool auto_reset = FIX || ((p.flags & ASTRO_TICK_AUTO_RESET) && (p.pool_size > 0 || p.ring != nullptr));
     const bool active = !ASTRO_META_FINISHED(meta);
     const int nb = active ? (int)ASTRO_META_NB(meta) : 0;
     const int np = active ? (int)ASTRO_META_NP(meta) : 0;
@@ -428,7 +433,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         if (j < np) plv[j] = LD_STREAM(&planets[j * 32]);
     }
 
-    if (BOT && !v.actions) {
+    if (BOT && !FIX && !v.actions) {
         // The bots of astro_rollout_device evaluated here, from the rows this lane has just loaded: script.ScriptBot
         // (script_decide: script.py:67-91, each ship from its own perspective) or script.NothingBot (control 2) per ship —
         // so that scripted games need no launch between ticks and run many ticks per launch like the counter-stream ones.
@@ -606,8 +611,8 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // from its pool record at the end: pull the record towards L2 while the bullet loop runs.
     // (the pick is a few dozen integer instructions: only the rare lanes that need it work it out)
     if (auto_reset && active && (hits || tick >= (uint32_t)p.timeout_tick)) {
-        if (!p.ring) {
-            const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + (p.step_base ? *p.step_base : 0u) + 1u, (uint32_t)p.pool_size);
+        if (!has_ring) {
+            const uint32_t k = pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + step_base + 1u, (uint32_t)p.pool_size);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pool_rec + (size_t)k * 8));
         } else {
             // fresh-game mode: which record the game will get depends on who else ends this tick; the tile's next
@@ -626,46 +631,55 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     unsigned carry = 0, c0 = 0;
     const bool multi = total > (unsigned)kStageWindows * 32u;
     TL(4);  // physics done, new ship / planet state stored
-    for (unsigned round_base = 0; round_base < total; round_base += (unsigned)kStageWindows * 32u) {
-        if (round_base) {
-            __syncwarp();
-            stage_round(round_base);
-        }
-        cp_async_wait_all();
-        __syncwarp();
-        if (round_base == 0) TL(5);  // bullets have arrived
-        const unsigned left = total - round_base;
-        const unsigned n_win = left >= (unsigned)kStageWindows * 32u ? (unsigned)kStageWindows : (left + 31u) >> 5;
-#pragma unroll 1
-        for (unsigned w = 0; w < n_win; w++) {
-            // item -> game: bit r of `starts` = a game's first bullet is item r of this window; c0 =
-            // games that started before it (warp-uniform)
-            const unsigned rel = start_key - (round_base + w * 32u);   // >= 32 unless this lane's game starts here
-            const unsigned starts = __reduce_or_sync(full, rel < 32u ? (1u << rel) : 0u);
-            const unsigned gi = c0 + __popc(starts & le_mask) - 1u;    // (items past the end: the last game)
-            c0 += __popc(starts);
-            float4 bv = t.bul[w * 32u + lane];
-            const float4 sT = t.fsxy[gi], pA = t.fpxy[0][gi], pB = t.fpxy[1][gi];
-            unsigned sh_hits = 0;
-#ifdef ASTRO_EXPERIMENTS
-            const bool keep = freeze ? (bv.x + sT.x + pA.x + pB.x != 123456.0f) : bullet_step_t<S>(bv, sT, pA, pB, t.hits, gi, c, sh_hits);
-#else
-            const bool keep = bullet_step_t<S>(bv, sT, pA, pB, t.hits, gi, c, sh_hits);
-#endif
-            if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
-            const unsigned kb = __ballot_sync(full, keep);   // (every lane has loaded its window item by now)
-            const unsigned pos = carry + __popc(kb & lt_mask);
-            if (keep) {
-                if (!multi) {
-                    t.bul[pos] = bv;
-                    t.ref[pos] = (uint8_t)gi;
-                } else {
-                    list_in[pos] = bv;
-                }
+    // (two copies of the loops, one per value of `multi`: the common one — a single round, survivors into shared memory —
+    // carries neither the test nor the round loop)
+    auto bullet_rounds = [&](auto multi_c) {
+        constexpr bool MULTI = decltype(multi_c)::value;
+        for (unsigned round_base = 0; round_base < (MULTI ? total : 1u); round_base += (unsigned)kStageWindows * 32u) {
+            if (MULTI && round_base) {
+                __syncwarp();
+                stage_round(round_base);
             }
-            if ((starts >> lane) & 1u) t.gstart[gi] = (uint16_t)pos;
-            carry += __popc(kb);
+            cp_async_wait_all();
+            __syncwarp();
+            if (round_base == 0) TL(5);  // bullets have arrived
+            const unsigned left = total - round_base;
+            const unsigned n_win = (MULTI && left >= (unsigned)kStageWindows * 32u) ? (unsigned)kStageWindows : (left + 31u) >> 5;
+#pragma unroll 1
+            for (unsigned w = 0; w < n_win; w++) {
+                // item -> game: bit r of `starts` = a game's first bullet is item r of this window; c0 =
+                // games that started before it (warp-uniform)
+                const unsigned rel = start_key - (round_base + w * 32u);   // >= 32 unless this lane's game starts here
+                const unsigned starts = __reduce_or_sync(full, rel < 32u ? (1u << rel) : 0u);
+                const unsigned gi = c0 + __popc(starts & le_mask) - 1u;    // (items past the end: the last game)
+                c0 += __popc(starts);
+                float4 bv = t.bul[w * 32u + lane];
+                const float4 sT = t.fsxy[gi], pA = t.fpxy[0][gi], pB = t.fpxy[1][gi];
+                unsigned sh_hits = 0;
+#ifdef ASTRO_EXPERIMENTS
+                const bool keep = freeze ? (bv.x + sT.x + pA.x + pB.x != 123456.0f) : bullet_step_t<S>(bv, sT, pA, pB, t.hits, gi, c, sh_hits);
+#else
+                const bool keep = bullet_step_t<S>(bv, sT, pA, pB, t.hits, gi, c, sh_hits);
+#endif
+                if (sh_hits) atomicOr(&t.hits[gi], sh_hits);
+                const unsigned kb = __ballot_sync(full, keep);   // (every lane has loaded its window item by now)
+                const unsigned pos = carry + __popc(kb & lt_mask);
+                if (keep) {
+                    if (!MULTI) {
+                        t.bul[pos] = bv;
+                        t.ref[pos] = (uint8_t)gi;
+                    } else {
+                        list_in[pos] = bv;
+                    }
+                }
+                if ((starts >> lane) & 1u) t.gstart[gi] = (uint16_t)pos;
+                carry += __popc(kb);
+            }
         }
+    };
+    if (total != 0u) {
+        if (__builtin_expect(multi, 0)) bullet_rounds(std::true_type{});
+        else bullet_rounds(std::false_type{});
     }
     if (lane == 0) t.gstart[__popc(ne)] = (uint16_t)carry;
     __syncwarp();
@@ -765,7 +779,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         // stream, seed): a warp-local count, so every record — every stream position — is consumed exactly once.  A game
         // that finds the tile's ring empty waits, frozen (tick field = ASTRO_MAX_TICKS), and asks again every tick.
         const float4* rec = nullptr;
-        if (p.ring) {
+        if (has_ring) {
             const bool want = ended | (!active && ASTRO_META_TICK(meta) == (uint32_t)ASTRO_MAX_TICKS);
             const unsigned wants = __ballot_sync(full, want);
             if (wants) {
@@ -776,7 +790,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 if (want && idx < (unsigned)p.quota) rec = p.ring + ((size_t)tile_index * (unsigned)p.quota + idx) * 8;
             }
         } else if (ended) {
-            rec = p.pool_rec + (size_t)pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + (p.step_base ? *p.step_base : 0u) + 1u, (uint32_t)p.pool_size) * 8;
+            rec = p.pool_rec + (size_t)pool_pick(p.seed, p.first_game + (uint32_t)g, v.step + step_base + 1u, (uint32_t)p.pool_size) * 8;
         }
         if (ended) atomicAdd(&p.episode[g], 1u);      // the per-slot episode counter: a fire-and-forget RED
         if (rec) {
@@ -803,7 +817,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 if (j < np_new) planets[j * 32] = r[4 + j];
             next.meta = ASTRO_META_PACK(0, np_new, 0, 0);
             if (last) p.meta[g] = next.meta;
-            if (p.game_pos) p.game_pos[g] = __float_as_uint(r[2].w);
+            if (!FIX && p.game_pos) p.game_pos[g] = __float_as_uint(r[2].w);
         } else if (ended) {
             ev |= ASTRO_EV_AWAIT;
             next.meta = ASTRO_META_PACK(0, np, 1, ASTRO_MAX_TICKS);
@@ -857,12 +871,12 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             for (unsigned k = 0; k < surv; k++) list_out[oexcl + k] = list_in[from + k];
         }
     }
-    if (v.reward) {
+    if (!FIX && v.reward) {
         if (S == 2) reinterpret_cast<float2*>(v.reward)[g] = make_float2(rw[0], rw[1]);
         else v.reward[g] = rw[0];
     }
-    if (v.events) {
-        if (p.flags & ASTRO_TICK_EVENT_PLANES) {
+    if (FIX || v.events) {
+        if (FIX || (p.flags & ASTRO_TICK_EVENT_PLANES)) {
             // three bit planes per tick, u32 [3][n_tiles]: bit g % 32 of word g / 32 = game g ended / ship 0 was hit /
             // ship 1 was hit (a timeout: ended and nobody hit) — 12 bytes per tile instead of 32
             const unsigned b_done = __ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0);
@@ -873,7 +887,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
             ST_STREAM(&v.events[g], (uint8_t)ev);
         }
     }
-    if (v.done) v.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
+    if (!FIX && v.done) v.done[g] = (uint8_t)((ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_SKIPPED)) ? 1 : 0);
 
     if (STATS) {
         // warp totals -> this warp's private slot row in HBM (no block barrier, no contention);
@@ -900,7 +914,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
 // tile striding, a device-side tile queue with the next tile's rows prefetched, a fully staged
 // software pipeline — were built and measured 12-48 % slower: profiles/r1_ab_v6_experiments.md.)
 // (BOT: the instantiation with the ScriptBot inside — float64 arithmetic of its own, far more registers: fewer CTAs per SM)
-template <int S, bool STATS, bool MANY, bool BOT = false>
+template <int S, bool STATS, bool MANY, bool BOT = false, bool FIX = false>
 __global__ void __launch_bounds__(kTickThreads, BOT ? ASTRO_TICK_MIN_BLOCKS_BOT : (MANY ? ASTRO_TICK_MIN_BLOCKS_MANY : ASTRO_TICK_MIN_BLOCKS)) tick_f32_kernel(const __grid_constant__ TickParams p) {
     using TileScratch = TileScratchT<MANY ? ASTRO_STAGE_WINDOWS_MANY : ASTRO_STAGE_WINDOWS>;
     __shared__ TileScratch s_tiles[kTickWarps];
@@ -930,22 +944,23 @@ __global__ void __launch_bounds__(kTickThreads, BOT ? ASTRO_TICK_MIN_BLOCKS_BOT 
     // fresh-game mode: how many of the tile's pre-created games have been used since the last refill — requested with the
     // tile's rows, parked in shared memory once they are all on their way (a wait here would cost a round trip)
     unsigned used0 = 0;
-    if (p.ring && lane == 0) used0 = p.tile_used[tile];
-    load_tile_in<S>(p, tick_var<S>(p, 0u), tile, lane, in);
-    if (p.ring && lane == 0) scratch.used = used0;
+    const bool has_ring = !FIX && p.ring != nullptr;
+    if (has_ring && lane == 0) used0 = p.tile_used[tile];
+    load_tile_in<S, FIX>(p, tick_var<S>(p, 0u), tile, lane, in);
+    if (has_ring && lane == 0) scratch.used = used0;
 #pragma unroll 1
     for (unsigned k = 0; k < (MANY ? (unsigned)p.n_fused : 1u); k++) {
         const TickVar v = tick_var<S>(p, MANY ? k : 0u);
         // (several ticks per launch) the NEXT tick's controls are requested now — a different array every tick,
         // straight from HBM — so that they have arrived when this tick is done
         uint32_t ctl_next = 0;
-        if (MANY && p.actions && k + 1u < (unsigned)p.n_fused) {
+        if (MANY && (FIX || p.actions) && k + 1u < (unsigned)p.n_fused) {
             const size_t g = (size_t)tile * 32 + lane;
-            ctl_next = load_controls<S>(v.actions + p.act_stride, g, (p.flags & ASTRO_TICK_PACKED_CONTROLS) != 0);
+            ctl_next = load_controls<S>(v.actions + p.act_stride, g, FIX || (p.flags & ASTRO_TICK_PACKED_CONTROLS) != 0);
         }
         if (MANY) in.fire_word = p.fire_bits[min(ASTRO_META_TICK(in.meta), (uint32_t)p.n_sched_ticks - 1u) >> 5];
         // (one-warp CTAs: the scratch is s_tiles[0], every shared address a compile-time constant — no base register)
-        tick_tile<S, STATS, MANY, BOT>(p, v, scratch, lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
+        tick_tile<S, STATS, MANY, BOT, FIX>(p, v, scratch, lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
         if (MANY) {
             // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
             // well), so it starts its prefix sums and list requests at once; only the planet rows are loaded.  The
@@ -957,7 +972,7 @@ __global__ void __launch_bounds__(kTickThreads, BOT ? ASTRO_TICK_MIN_BLOCKS_BOT 
             __syncwarp();
         }
     }
-    if (p.ring) {
+    if (has_ring) {
         __syncwarp();
         if (lane == 0) p.tile_used[tile] = scratch.used;
     }

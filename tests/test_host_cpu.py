@@ -215,7 +215,7 @@ def test_tick_kernel_requests_its_rows_before_it_uses_meta():
     if not os.path.exists(cuobjdump):
         pytest.skip('cuobjdump not available')
     sass = subprocess.run([cuobjdump, '-sass', nat.LIB_PATH], capture_output=True, text=True).stdout
-    for name in ('tick_f32_kernelILi2ELb1ELb0ELb0', 'tick_f32_kernelILi2ELb1ELb1ELb0', 'tick_f32_kernelILi2ELb0ELb0ELb0', 'tick_f32_kernelILi1ELb1ELb0ELb0'):
+    for name in ('tick_f32_kernelILi2ELb1ELb0ELb0ELb0', 'tick_f32_kernelILi2ELb1ELb1ELb0ELb0', 'tick_f32_kernelILi2ELb1ELb1ELb0ELb1', 'tick_f32_kernelILi2ELb0ELb0ELb0ELb0', 'tick_f32_kernelILi1ELb1ELb0ELb0ELb0'):
         body = sass.split('Function : ')
         body = [b for b in body if name in b.split('\n', 1)[0]]
         assert len(body) == 1, name
