@@ -72,6 +72,23 @@ struct TileScratchT {              // per warp
 };
 constexpr int kDrop = 0x40000000;
 
+// Shared-memory accesses of the bullet loop through explicit 32-bit addresses off ONE base register (ASTRO_SMEM_ASM): ptxas
+// otherwise re-derives the base (S2R SR_CgaCtaId + MOV + LEA, predicated, twice per window) behind the loop's rare float64
+// block, which clobbers it.  The base goes through a shuffle, which cannot be re-materialised.
+#ifndef ASTRO_SMEM_ASM
+#define ASTRO_SMEM_ASM 1
+#endif
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts8(unsigned a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -630,6 +647,10 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // reading instead — writes only land on items already consumed — and copies from there.
     unsigned carry = 0, c0 = 0;
     const bool multi = total > (unsigned)kStageWindows * 32u;
+    using Scratch = TileScratchT<kStageWindows>;
+#if ASTRO_SMEM_ASM
+    const unsigned sbase = __shfl_sync(full, (unsigned)__cvta_generic_to_shared(&t), 0);
+#endif
     TL(4);  // physics done, new ship / planet state stored
     // (two copies of the loops, one per value of `multi`: the common one — a single round, survivors into shared memory —
     // carries neither the test nor the round loop)
@@ -653,8 +674,15 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 const unsigned starts = __reduce_or_sync(full, rel < 32u ? (1u << rel) : 0u);
                 const unsigned gi = c0 + __popc(starts & le_mask) - 1u;    // (items past the end: the last game)
                 c0 += __popc(starts);
+#if ASTRO_SMEM_ASM
+                float4 bv = lds128(sbase + (unsigned)offsetof(Scratch, bul) + (w * 32u + lane) * 16u);
+                const unsigned fr = sbase + gi * 16u;
+                const float4 sT = lds128(fr + (unsigned)offsetof(Scratch, fsxy)), pA = lds128(fr + (unsigned)offsetof(Scratch, fpxy)),
+                             pB = lds128(fr + (unsigned)offsetof(Scratch, fpxy) + 512u);
+#else
                 float4 bv = t.bul[w * 32u + lane];
                 const float4 sT = t.fsxy[gi], pA = t.fpxy[0][gi], pB = t.fpxy[1][gi];
+#endif
                 unsigned sh_hits = 0;
 #ifdef ASTRO_EXPERIMENTS
                 const bool keep = freeze ? (bv.x + sT.x + pA.x + pB.x != 123456.0f) : bullet_step_t<S>(bv, sT, pA, pB, t.hits, gi, c, sh_hits);
@@ -666,13 +694,22 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 const unsigned pos = carry + __popc(kb & lt_mask);
                 if (keep) {
                     if (!MULTI) {
+#if ASTRO_SMEM_ASM
+                        sts128(sbase + (unsigned)offsetof(Scratch, bul) + pos * 16u, bv);
+                        sts8(sbase + (unsigned)offsetof(Scratch, ref) + pos, gi);
+#else
                         t.bul[pos] = bv;
                         t.ref[pos] = (uint8_t)gi;
+#endif
                     } else {
                         list_in[pos] = bv;
                     }
                 }
+#if ASTRO_SMEM_ASM
+                if ((starts >> lane) & 1u) sts16(sbase + (unsigned)offsetof(Scratch, gstart) + gi * 2u, pos);
+#else
                 if ((starts >> lane) & 1u) t.gstart[gi] = (uint16_t)pos;
+#endif
                 carry += __popc(kb);
             }
         }
