@@ -155,30 +155,6 @@ __device__ __forceinline__ unsigned warp_totals(int lane, int S, uint32_t ev, bo
     for (int k = 0; k < ASTRO_N_STATS; k++) mine = (lane == k) ? v[k] : mine;
     return mine;
 }
-// The rare half of warp_totals alone (somebody ended, overflowed, was skipped ...): tick_f32_kernel's launches of several ticks
-// keep the every-tick sums per LANE, packed (see there), and reduce them once per launch.
-__device__ __forceinline__ unsigned warp_totals_rare(int lane, int S, uint32_t ev) {
-    const unsigned full = 0xffffffffu;
-    if (!__ballot_sync(full, (ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_OVERFLOW | ASTRO_EV_SKIPPED | ASTRO_EV_BAD_CONTROL | ASTRO_EV_AWAIT)) != 0)) return 0u;
-    const bool coll = (ev & (ASTRO_EV_HIT0 | ASTRO_EV_HIT1)) != 0;
-    const bool h0 = ev & ASTRO_EV_HIT0, h1 = ev & ASTRO_EV_HIT1;
-    unsigned v[ASTRO_N_STATS];
-#pragma unroll
-    for (int k = 0; k < ASTRO_N_STATS; k++) v[k] = 0u;
-    v[0] = __popc(__ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0));
-    v[1] = __popc(__ballot_sync(full, S == 2 && coll && !h0));
-    v[2] = __popc(__ballot_sync(full, S == 2 && coll && !h1));
-    v[3] = __popc(__ballot_sync(full, coll && (S == 1 || (h0 && h1))));
-    v[4] = __popc(__ballot_sync(full, (ev & ASTRO_EV_TIMEOUT) != 0));
-    v[7] = __popc(__ballot_sync(full, (ev & ASTRO_EV_OVERFLOW) != 0));
-    v[11] = __popc(__ballot_sync(full, (ev & ASTRO_EV_SKIPPED) != 0));
-    v[12] = __popc(__ballot_sync(full, (ev & ASTRO_EV_BAD_CONTROL) != 0));
-    v[13] = __popc(__ballot_sync(full, (ev & ASTRO_EV_AWAIT) != 0));
-    unsigned mine = 0;
-#pragma unroll
-    for (int k = 0; k < ASTRO_N_STATS; k++) mine = (lane == k) ? v[k] : mine;
-    return mine;
-}
 __device__ __forceinline__ void warp_stats(unsigned* s_stats, int lane, int S, uint32_t ev, bool active,
                                            int spawned, int np, int nb, int m_out) {
     unsigned mine = warp_totals(lane, S, ev, active, spawned, np, nb, m_out);

@@ -391,8 +391,7 @@ template <int S, bool STATS, bool MANY, bool BOT, bool FIX>
 // (planets and the bullet list always do), and the tile's statistics (`stat_acc`, summed over the launch's ticks).
 __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v, TileScratchT<MANY ? ASTRO_STAGE_WINDOWS_MANY : ASTRO_STAGE_WINDOWS>& t, const unsigned lane,
                                           const unsigned tile_index, const TileIn& in, TileIn& next, const bool last,
-                                          unsigned& stat_acc, unsigned& lane_acc_a, unsigned& lane_acc_b, const bool flush_lane_acc,
-                                          const bool have_fire_word) {
+                                          unsigned& stat_acc, const bool have_fire_word) {
     using B4 = Body4<float>;
     constexpr int kStageWindows = MANY ? ASTRO_STAGE_WINDOWS_MANY : ASTRO_STAGE_WINDOWS;
     const unsigned full = 0xffffffffu;
@@ -930,25 +929,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     if (STATS) {
         // warp totals -> this warp's private slot row in HBM (no block barrier, no contention);
         // astro_stats() folds the rows
-        if (!MANY) {
-            stat_acc += warp_totals((int)lane, S, ev, active, spawned, np, nb, m_out);
-        } else {
-            // Launches of several ticks: what every tick contributes — live planets, bullets in / out, env-steps, games that
-            // fired — is summed per LANE in two packed words (three instructions a tick instead of five warp reductions and
-            // fourteen selects) and reduced when the launch ends, or every 64 ticks, whichever comes first:
-            //   a = planets (9 bits: <= 4 x 64) | bullets in << 9 (16 bits: <= 1,023 x 64) | env-steps << 25 (7 bits: <= 64)
-            //   b = bullets out (16 bits) | fired << 16
-            lane_acc_a += (unsigned)np + ((unsigned)nb << 9) + (active ? (1u << 25) : 0u);
-            lane_acc_b += (unsigned)m_out + (spawned ? (1u << 16) : 0u);
-            stat_acc += warp_totals_rare((int)lane, S, ev);
-            if (flush_lane_acc) {
-                const unsigned v5 = __reduce_add_sync(full, lane_acc_a >> 25), v8 = __reduce_add_sync(full, lane_acc_a & 511u);
-                const unsigned v9 = __reduce_add_sync(full, (lane_acc_a >> 9) & 0xffffu), v10 = __reduce_add_sync(full, lane_acc_b & 0xffffu);
-                const unsigned v6 = (unsigned)S * __reduce_add_sync(full, lane_acc_b >> 16);
-                stat_acc += lane == 5u ? v5 : (lane == 6u ? v6 : (lane == 8u ? v8 : (lane == 9u ? v9 : (lane == 10u ? v10 : 0u))));
-                lane_acc_a = lane_acc_b = 0u;
-            }
-        }
+        stat_acc += warp_totals((int)lane, S, ev, active, spawned, np, nb, m_out);
         if (last) {
             if (MANY && p.n_fused >= 8) {
                 // a launch of many ticks: the tile's totals of the whole launch go straight to the 64-bit counters —
@@ -995,7 +976,7 @@ __global__ void __launch_bounds__(kTickThreads, BOT ? ASTRO_TICK_MIN_BLOCKS_BOT 
     // barrier orders those accesses.
     // (MANY = false: the one-tick launch, without the loop around it — the loop form costs a single tick 6 %)
     TileIn in, next;
-    unsigned stat_acc = 0, lane_acc_a = 0, lane_acc_b = 0;
+    unsigned stat_acc = 0;
     TileScratch& scratch = s_tiles[kTickWarps == 1 ? 0 : (threadIdx.x >> 5)];
     // fresh-game mode: how many of the tile's pre-created games have been used since the last refill — requested with the
     // tile's rows, parked in shared memory once they are all on their way (a wait here would cost a round trip)
@@ -1016,8 +997,7 @@ __global__ void __launch_bounds__(kTickThreads, BOT ? ASTRO_TICK_MIN_BLOCKS_BOT 
         }
         if (MANY) in.fire_word = p.fire_bits[min(ASTRO_META_TICK(in.meta), (uint32_t)p.n_sched_ticks - 1u) >> 5];
         // (one-warp CTAs: the scratch is s_tiles[0], every shared address a compile-time constant — no base register)
-        tick_tile<S, STATS, MANY, BOT, FIX>(p, v, scratch, lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, lane_acc_a, lane_acc_b,
-                                            k + 1u == (unsigned)p.n_fused || (k & 63u) == 63u, MANY);
+        tick_tile<S, STATS, MANY, BOT, FIX>(p, v, scratch, lane, tile, in, next, !MANY || k + 1u == (unsigned)p.n_fused, stat_acc, MANY);
         if (MANY) {
             // The next tick of this tile: meta, ships and bearings are handed on in registers (they were stored as
             // well), so it starts its prefix sums and list requests at once; only the planet rows are loaded.  The
