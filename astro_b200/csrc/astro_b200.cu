@@ -126,33 +126,34 @@ __global__ void pack_pool_kernel(const float* __restrict__ ships, const float* _
 // ballots / REDUX give warp-uniform totals, lane k keeps counter k, ONE shared atomic per warp.
 // (32-bit shared counters: a block's per-tick totals are < 2^19.)
 __device__ __forceinline__ unsigned warp_totals(int lane, int S, uint32_t ev, bool active, int spawned, int np,
-                                               int nb, int m_out) {
+                                               int nb, int m_out, bool have_nb_total = false, unsigned nb_total = 0u) {
     const unsigned full = 0xffffffffu;
-    const bool coll = (ev & (ASTRO_EV_HIT0 | ASTRO_EV_HIT1)) != 0;
-    const bool h0 = ev & ASTRO_EV_HIT0, h1 = ev & ASTRO_EV_HIT1;
-    unsigned v[ASTRO_N_STATS];
-#pragma unroll
-    for (int k = 0; k < ASTRO_N_STATS; k++) v[k] = 0u;
-    // most tiles, most ticks: nobody ended, overflowed or was skipped, nobody fired
-    if (__ballot_sync(full, (ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_OVERFLOW | ASTRO_EV_SKIPPED | ASTRO_EV_BAD_CONTROL | ASTRO_EV_AWAIT)) != 0)) {
-        v[0] = __popc(__ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0));
-        v[1] = __popc(__ballot_sync(full, S == 2 && coll && !h0));
-        v[2] = __popc(__ballot_sync(full, S == 2 && coll && !h1));
-        v[3] = __popc(__ballot_sync(full, coll && (S == 1 || (h0 && h1))));
-        v[4] = __popc(__ballot_sync(full, (ev & ASTRO_EV_TIMEOUT) != 0));
-        v[7] = __popc(__ballot_sync(full, (ev & ASTRO_EV_OVERFLOW) != 0));
-        v[11] = __popc(__ballot_sync(full, (ev & ASTRO_EV_SKIPPED) != 0));
-        v[12] = __popc(__ballot_sync(full, (ev & ASTRO_EV_BAD_CONTROL) != 0));
-        v[13] = __popc(__ballot_sync(full, (ev & ASTRO_EV_AWAIT) != 0));
-    }
-    v[5] = __popc(__ballot_sync(full, active));
-    v[6] = (unsigned)S * __popc(__ballot_sync(full, spawned != 0));
-    v[8] = __reduce_add_sync(full, (unsigned)np);
-    v[9] = __reduce_add_sync(full, (unsigned)nb);
-    v[10] = __reduce_add_sync(full, (unsigned)m_out);
     unsigned mine = 0;
-#pragma unroll
-    for (int k = 0; k < ASTRO_N_STATS; k++) mine = (lane == k) ? v[k] : mine;
+    // most tiles, most ticks: nobody ended, overflowed or was skipped — the nine counters of those events (and the selects
+    // that hand each to its lane) sit behind one ballot
+    if (__ballot_sync(full, (ev & (ASTRO_EV_DONE_MASK | ASTRO_EV_OVERFLOW | ASTRO_EV_SKIPPED | ASTRO_EV_BAD_CONTROL | ASTRO_EV_AWAIT)) != 0)) {
+        const bool coll = (ev & (ASTRO_EV_HIT0 | ASTRO_EV_HIT1)) != 0;
+        const bool h0 = ev & ASTRO_EV_HIT0, h1 = ev & ASTRO_EV_HIT1;
+        const unsigned v0 = __popc(__ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0));
+        const unsigned v1 = __popc(__ballot_sync(full, S == 2 && coll && !h0));
+        const unsigned v2 = __popc(__ballot_sync(full, S == 2 && coll && !h1));
+        const unsigned v3 = __popc(__ballot_sync(full, coll && (S == 1 || (h0 && h1))));
+        const unsigned v4 = __popc(__ballot_sync(full, (ev & ASTRO_EV_TIMEOUT) != 0));
+        const unsigned v7 = __popc(__ballot_sync(full, (ev & ASTRO_EV_OVERFLOW) != 0));
+        const unsigned v11 = __popc(__ballot_sync(full, (ev & ASTRO_EV_SKIPPED) != 0));
+        const unsigned v12 = __popc(__ballot_sync(full, (ev & ASTRO_EV_BAD_CONTROL) != 0));
+        const unsigned v13 = __popc(__ballot_sync(full, (ev & ASTRO_EV_AWAIT) != 0));
+        mine = lane == 0 ? v0 : mine; mine = lane == 1 ? v1 : mine; mine = lane == 2 ? v2 : mine; mine = lane == 3 ? v3 : mine;
+        mine = lane == 4 ? v4 : mine; mine = lane == 7 ? v7 : mine; mine = lane == 11 ? v11 : mine; mine = lane == 12 ? v12 : mine;
+        mine = lane == 13 ? v13 : mine;
+    }
+    const unsigned v5 = __popc(__ballot_sync(full, active));
+    const unsigned v6 = (unsigned)S * __popc(__ballot_sync(full, spawned != 0));
+    const unsigned v8 = __reduce_add_sync(full, (unsigned)np);
+    const unsigned v9 = have_nb_total ? nb_total : __reduce_add_sync(full, (unsigned)nb);     // (the tick has this sum already)
+    const unsigned v10 = __reduce_add_sync(full, (unsigned)m_out);
+    mine = lane == 5 ? v5 : mine; mine = lane == 6 ? v6 : mine; mine = lane == 8 ? v8 : mine; mine = lane == 9 ? v9 : mine;
+    mine = lane == 10 ? v10 : mine;
     return mine;
 }
 __device__ __forceinline__ void warp_stats(unsigned* s_stats, int lane, int S, uint32_t ev, bool active,
