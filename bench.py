@@ -611,6 +611,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     byte_value = world * n * R * max(1, 128 // R) / (max(gather_ms(e0.elapsed_time(e1))) * 1e-3)
     clocks = sampler.stop()
+    # the fused form's own roofline: instruction issue.  Warp-instructions per tile and tick of the ncu capture of this launch shape x
+    # the tiles and ticks of the timed launch / its live duration, against one instruction per scheduler (4 per SM) and clock
+    sec = roofline.get('secondary') or {}
+    if sec.get('warp_instr_per_tile_tick') and clocks and clocks.get('sm_mhz'):
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        peak_issue = 4.0 * sms * float(clocks['sm_mhz']) * 1e6
+        got = sec['warp_instr_per_tile_tick'] * (n / 32) * tpl / (roofline['avg_launch_us'] * 1e-6)
+        sec.update(achieved_warp_instr_per_s=got, peak_warp_instr_per_s=peak_issue, frac=got / peak_issue,
+                   peak_source='4 schedulers x %d SMs x the SM clock sampled under load (clocks.sm_mhz)' % sms)
     e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=games.n_pad, d2h_bytes_per_step=games.n_tiles * 12, steps=e2e_steps,
                api='BatchedGames.rollout_host(packed=True, planes=True) -> astro_rollout_host (copies overlap the kernel)',
                ticks_per_call=E, loop='open: the controls of a call\'s %d ticks are known up front' % E,
