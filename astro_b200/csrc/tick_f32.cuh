@@ -674,7 +674,9 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 // item -> game: bit r of `starts` = a game's first bullet is item r of this window; c0 =
                 // games that started before it (warp-uniform)
                 const unsigned rel = start_key - (round_base + w * 32u);   // >= 32 unless this lane's game starts here
-                const unsigned starts = __reduce_or_sync(full, rel < 32u ? (1u << rel) : 0u);
+                unsigned start_bit;      // 1 << rel, 0 for rel >= 32: PTX shl clamps the shift amount (C++ needs a test and a select)
+                asm("shl.b32 %0, 1, %1;" : "=r"(start_bit) : "r"(rel));
+                const unsigned starts = __reduce_or_sync(full, start_bit);
                 const unsigned gi = c0 + __popc(starts & le_mask) - 1u;    // (items past the end: the last game)
                 c0 += __popc(starts);
 #if ASTRO_SMEM_ASM
