@@ -393,12 +393,17 @@ def run_ours(args):
         dev_ring = host_ring.to(dev)
         events_dev = torch.empty(games.planes_shape(R), dtype=torch.int32, device=dev)
 
+        # (device addresses worked out once: indexing a tensor costs the host microseconds that the timed region of a single
+        # launch would count while the GPU idles)
+        ring_ptr, ring_stride = dev_ring.data_ptr(), dev_ring[0].numel() * dev_ring.element_size()
+        ev_ptr, ev_stride = events_dev.data_ptr(), events_dev[0].numel() * events_dev.element_size()
+
         def run_steps(k_steps):
             done, n_launch = 0, 0
             while done < k_steps:
                 r0 = done % R
                 t = min(fuse, k_steps - done, R - r0)
-                games.step_many_raw(dev_ring[r0].data_ptr(), events_dev[r0].data_ptr(), t, flags)
+                games.step_many_raw(ring_ptr + r0 * ring_stride, ev_ptr + r0 * ev_stride, t, flags)
                 done += t
                 n_launch += 1
             return n_launch
