@@ -78,6 +78,9 @@ constexpr int kDrop = 0x40000000;
 #ifndef ASTRO_SMEM_ASM
 #define ASTRO_SMEM_ASM 1
 #endif
+#ifndef ASTRO_OPAQUE_LANE
+#define ASTRO_OPAQUE_LANE 1
+#endif
 #ifndef ASTRO_OPAQUE_TILE
 #define ASTRO_OPAQUE_TILE 1
 #endif
@@ -980,7 +983,13 @@ __global__ void __launch_bounds__(kTickThreads, BOT ? ASTRO_TICK_MIN_BLOCKS_BOT 
     // cheaper statistics; without the backwards walk at all: 51.7.)
     if (MANY) tile = __shfl_sync(0xffffffffu, tile, 0);
 #endif
+#if ASTRO_OPAQUE_LANE
+    // (several ticks per launch: ptxas re-reads %tid.x a dozen times per tick instead of keeping the lane id; a value that came
+    // through a shuffle it keeps)
+    const unsigned lane = MANY ? __shfl_sync(0xffffffffu, threadIdx.x & 31u, threadIdx.x & 31u) : (threadIdx.x & 31u);
+#else
     const unsigned lane = threadIdx.x & 31u;
+#endif
     // n_fused consecutive ticks of this tile, back to back (astro_tick_many): games do not interact, so a
     // tile can run ahead of the others; what tick k wrote is what tick k + 1 reads — from L2, not from HBM.
     // The rows are lane-private; the bullet list is written by some lanes and read by others: the warp
