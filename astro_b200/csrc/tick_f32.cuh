@@ -92,6 +92,10 @@ __device__ __forceinline__ float4 lds128(unsigned a) {
 __device__ __forceinline__ void sts128(unsigned a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ unsigned lds32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ unsigned lds16(unsigned a) { unsigned v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ unsigned lds8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts8(unsigned a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
@@ -486,13 +490,25 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     const bool nonempty = nb > 0;
     const unsigned ne = __ballot_sync(full, nonempty);
     const unsigned cid = __popc(ne & lt_mask);                    // this game's rank among the games with bullets
+    using Scratch = TileScratchT<kStageWindows>;
+#if ASTRO_SMEM_ASM
+    // every hot shared-memory access of the tick goes off this one base register (see lds128 above)
+    const unsigned sbase = __shfl_sync(full, (unsigned)__cvta_generic_to_shared(&t), 0);
+#define SOFF(field) (sbase + (unsigned)offsetof(Scratch, field))
+    if (nonempty) sts32(SOFF(hits) + cid * 4u, (unsigned)np << 8);
+#else
     if (nonempty) t.hits[cid] = (unsigned)np << 8;
+#endif
     // One window = 32 consecutive list items = 512 contiguous bytes; a round = up to kStageWindows
     // windows, all requested at once (16-byte cp.async each) and as early as possible — nothing
     // else sits between the arrival of meta and these requests (measured: working out the item ->
     // game labels here instead of in the bullet loop costs 10 % of the tick).  Lanes past the end of
     // the list stage a bullet that is certainly culled (no `valid` flag in the loop below).
+#if ASTRO_SMEM_ASM
+    const unsigned bul_s = SOFF(bul) + lane * 16u;
+#else
     const unsigned bul_s = (unsigned)__cvta_generic_to_shared(&t.bul[lane]);
+#endif
     auto stage_round = [&](unsigned round_base) {
         const unsigned left = total - round_base;
 #if ASTRO_OPT_STAGE
@@ -507,7 +523,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bul_s + w * 512u), "l"(src + w * 32u) : "memory");
         }
         const unsigned items = left < (unsigned)kStageWindows * 32u ? left : (unsigned)kStageWindows * 32u;
+#if ASTRO_SMEM_ASM
+        if ((items & 31u) != 0u && lane >= (items & 31u)) sts128(bul_s + (items & ~31u) * 16u, make_float4(4.0f, 4.0f, 0.0f, 0.0f));
+#else
         if ((items & 31u) != 0u && lane >= (items & 31u)) t.bul[(items & ~31u) + lane] = make_float4(4.0f, 4.0f, 0.0f, 0.0f);
+#endif
         cp_async_commit();
         return;
         }
@@ -541,6 +561,15 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // the packed distance code wants); the new ship / planet state goes straight to HBM.  (A
     // game that ends is re-created below; without auto-reset its ships and planets are left in
     // this post-step state: the state of a finished game is unspecified, the reference has none.)
+#if ASTRO_SMEM_ASM
+    sts128(SOFF(sxy) + lane * 16u, make_float4(shv[0].x, shv[1].x, shv[0].y, shv[1].y));
+    sts128(SOFF(svel) + lane * 16u, make_float4(shv[0].z, shv[0].w, shv[1].z, shv[1].w));
+    if (nonempty) {
+        sts128(SOFF(fsxy) + cid * 16u, make_float4(shv[0].x, shv[1].x, shv[0].y, shv[1].y));
+        sts128(SOFF(fpxy) + cid * 16u, make_float4(plv[0].x, plv[1].x, plv[0].y, plv[1].y));
+        sts128(SOFF(fpxy) + 512u + cid * 16u, make_float4(plv[2].x, plv[3].x, plv[2].y, plv[3].y));
+    }
+#else
     t.sxy[lane] = make_float4(shv[0].x, shv[1].x, shv[0].y, shv[1].y);
     t.svel[lane] = make_float4(shv[0].z, shv[0].w, shv[1].z, shv[1].w);
     if (nonempty) {
@@ -548,6 +577,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         t.fpxy[0][cid] = make_float4(plv[0].x, plv[1].x, plv[0].y, plv[1].y);
         t.fpxy[1][cid] = make_float4(plv[2].x, plv[3].x, plv[2].y, plv[3].y);
     }
+#endif
 #ifdef ASTRO_TIMELINE
     if (__shfl_xor_sync(full, __float_as_uint(shv[0].x) ^ __float_as_uint(sb[1]) ^ __float_as_uint(plv[0].x) ^ __float_as_uint(plv[3].x), 1) == 0xdeadbeefu) return;
     TL(3);  // ships and planets have arrived
@@ -579,7 +609,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         float dirs[4];
         if (S == 2) np_sincos_f32x2(sb[0], sb[1], dirs[0], dirs[1], dirs[2], dirs[3]);
         else { np_sincos_f32(sb[0], dirs[0], dirs[1]); dirs[2] = dirs[0]; dirs[3] = dirs[1]; }
+#if ASTRO_SMEM_ASM
+        sts128(SOFF(dir) + lane * 16u, make_float4(dirs[0], dirs[1], dirs[2], dirs[3]));
+#else
         t.dir[lane] = make_float4(dirs[0], dirs[1], dirs[2], dirs[3]);
+#endif
         // direction, gravity, ship-planet and ship-ship collisions on the old state
 #pragma unroll
         for (int s = 0; s < S; s++) {
@@ -653,10 +687,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     // reading instead — writes only land on items already consumed — and copies from there.
     unsigned carry = 0, c0 = 0;
     const bool multi = total > (unsigned)kStageWindows * 32u;
-    using Scratch = TileScratchT<kStageWindows>;
-#if ASTRO_SMEM_ASM
-    const unsigned sbase = __shfl_sync(full, (unsigned)__cvta_generic_to_shared(&t), 0);
-#endif
+
     TL(4);  // physics done, new ship / planet state stored
     // (two copies of the loops, one per value of `multi`: the common one — a single round, survivors into shared memory —
     // carries neither the test nor the round loop)
@@ -683,7 +714,7 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
                 const unsigned gi = c0 + __popc(starts & le_mask) - 1u;    // (items past the end: the last game)
                 c0 += __popc(starts);
 #if ASTRO_SMEM_ASM
-                float4 bv = lds128(sbase + (unsigned)offsetof(Scratch, bul) + (w * 32u + lane) * 16u);
+                float4 bv = lds128(bul_s + w * 512u);
                 const unsigned fr = sbase + gi * 16u;
                 const float4 sT = lds128(fr + (unsigned)offsetof(Scratch, fsxy)), pA = lds128(fr + (unsigned)offsetof(Scratch, fpxy)),
                              pB = lds128(fr + (unsigned)offsetof(Scratch, fpxy) + 512u);
@@ -726,10 +757,17 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         if (__builtin_expect(multi, 0)) bullet_rounds(std::true_type{});
         else bullet_rounds(std::false_type{});
     }
+#if ASTRO_SMEM_ASM
+    if (lane == 0) sts16(SOFF(gstart) + (unsigned)__popc(ne) * 2u, carry);
+    __syncwarp();
+    // first survivor of this lane's game in the compacted list, and one past its last
+    const unsigned g_first = nonempty ? lds16(SOFF(gstart) + cid * 2u) : 0u, g_end = nonempty ? lds16(SOFF(gstart) + cid * 2u + 2u) : 0u;
+#else
     if (lane == 0) t.gstart[__popc(ne)] = (uint16_t)carry;
     __syncwarp();
     // first survivor of this lane's game in the compacted list, and one past its last
     const unsigned g_first = nonempty ? (unsigned)t.gstart[cid] : 0u, g_end = nonempty ? (unsigned)t.gstart[cid + 1u] : 0u;
+#endif
     TL(6);
 
     // ================= 5. terminal logic, spawn, bookkeeping ==========================================
@@ -746,7 +784,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         int m = 0;   // survivors of this game
         if (nonempty) {
             m = (int)(g_end - g_first);
+#if ASTRO_SMEM_ASM
+            hits |= lds32(SOFF(hits) + cid * 4u) & 3u;
+#else
             hits |= t.hits[cid] & 3u;
+#endif
         }
 #ifdef ASTRO_EXPERIMENTS
         const bool timeout = !freeze && tick >= (uint32_t)p.timeout_tick;
@@ -771,7 +813,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
 #endif
             if (fire) {  // core.py:267-280, from the OLD ship state
                 ev |= ASTRO_EV_FIRED;
+#if ASTRO_SMEM_ASM
+                const float4 dv = lds128(SOFF(dir) + lane * 16u), oxy = lds128(SOFF(sxy) + lane * 16u), ov = lds128(SOFF(svel) + lane * 16u);
+#else
                 const float4 dv = t.dir[lane], oxy = t.sxy[lane], ov = t.svel[lane];
+#endif
 #pragma unroll
                 for (int s = 0; s < S; s++) {
                     const float d0 = s == 0 ? dv.x : dv.z, d1 = s == 0 ? dv.y : dv.w;
@@ -887,7 +933,11 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
     const bool moves = __ballot_sync(full, (ev & ASTRO_EV_DONE_MASK) != 0 || n_born != 0) != 0;
     if (!moves && !multi) {
 #pragma unroll 1
+#if ASTRO_SMEM_ASM
+        for (unsigned j = lane; j < n_surv; j += 32u) ST_STREAM(&list_out[j], lds128(SOFF(bul) + j * 16u));
+#else
         for (unsigned j = lane; j < n_surv; j += 32u) ST_STREAM(&list_out[j], t.bul[j]);
+#endif
     } else {
         unsigned oincl = (unsigned)m_out;
 #pragma unroll
@@ -899,15 +949,24 @@ __device__ __forceinline__ void tick_tile(const TickParams& p, const TickVar& v,
         if (n_born > 0) ST_STREAM(&list_out[oexcl + surv], born[0]);
         if (n_born > 1) ST_STREAM(&list_out[oexcl + surv + 1u], born[1]);
         if (!multi) {
+#if ASTRO_SMEM_ASM
+            if (nonempty) sts32(SOFF(shift) + cid * 4u, (unsigned)((ev & ASTRO_EV_DONE_MASK) ? kDrop : (int)oexcl - (int)g_first));
+#else
             if (nonempty) t.shift[cid] = (ev & ASTRO_EV_DONE_MASK) ? kDrop : (int)oexcl - (int)g_first;
+#endif
             __syncwarp();
             // (byte offsets from the two shared arrays and the list base: 9 instructions per step)
             const char* const bul_b = reinterpret_cast<const char*>(t.bul);
             char* const out_b = reinterpret_cast<char*>(list_out);
 #pragma unroll 1
             for (unsigned j = lane; j < n_surv; j += 32u) {
+#if ASTRO_SMEM_ASM
+                const int sh = (int)lds32(SOFF(shift) + lds8(SOFF(ref) + j) * 4u);
+                const float4 bv = lds128(SOFF(bul) + j * 16u);
+#else
                 const int sh = t.shift[t.ref[j]];
                 const float4 bv = *reinterpret_cast<const float4*>(bul_b + j * 16u);
+#endif
                 if (sh != kDrop) ST_STREAM(reinterpret_cast<float4*>(out_b + (size_t)((j + (unsigned)sh) * 16u)), bv);
             }
         } else {
