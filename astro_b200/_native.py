@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('ASTRO_B200_LIB') or os.path.join(HERE, 'libastro_b200.so')   # env: A/B builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TILE = 32
 MAX_PLANETS = 4
 MAX_BULLET_CAP = 1023

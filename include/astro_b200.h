@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define ASTRO_ABI_VERSION 3
+#define ASTRO_ABI_VERSION 4   /* 4: astro_stats_peer_*, astro_stats_allreduce, astro_value_forward */
 #define ASTRO_TILE 32
 #define ASTRO_MAX_SHIPS 2
 #define ASTRO_MAX_PLANETS 4
