@@ -2780,7 +2780,9 @@ int astro_rollout_host(AstroBatch* b, const uint8_t* actions_host, uint8_t* even
     // env-steps/s: C = 1 1.42e10, 4 1.48e10, 8 1.35e10, 16 1.13e10 (the pipeline is two chunks deep: large
     // chunks leave little to overlap within a call).  ASTRO_ROLLOUT_CHUNK overrides.
     static const int chunk_env = getenv("ASTRO_ROLLOUT_CHUNK") ? atoi(getenv("ASTRO_ROLLOUT_CHUNK")) : 0;
-    const int C = chunk_env > 0 ? chunk_env : 4;
+    // (round 2, 128 ticks per call, packed controls + event planes: C = 4 1.95e10, 8 2.00e10, 16 1.95e10, 32 1.84e10; byte forms:
+    // 1.75e10 / 1.70e10 / 1.53e10 / 1.25e10 — half the bytes per tick move the optimum up one step)
+    const int C = chunk_env > 0 ? chunk_env : ((flags & ASTRO_TICK_PACKED_CONTROLS) ? 8 : 4);
     if (b->pipe_ready && b->pipe_chunk != C) {
         for (int i = 0; i < 2; i++) {
             CUDA_TRY(cudaFree(b->d_actions2[i]));
