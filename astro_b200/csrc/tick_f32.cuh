@@ -18,6 +18,17 @@
 //     survivors and newborn, dense again — is written to the tile's run in the other buffer.
 //  B. SHIPS AND PLANETS, thread-per-game from the staged copies: direction, gravity, collisions,
 //     terminal logic, spawn, integration, reset — all coalesced 128-bit accesses.
+//
+// Instantiations, tick_f32_kernel<S, STATS, MANY, BOT, FIX>:
+//   MANY  several ticks of a tile per launch (astro_tick_many): meta / ships / bearings handed from tick to tick in registers,
+//         7 staging windows and 28 one-warp CTAs per SM (the one-tick launch: 8 and 26) — this form is bound by instruction issue
+//   BOT   script.ScriptBot / NothingBot evaluated inside the tick (astro_rollout_device)
+//   FIX   the production rollout's options fixed at compile time: packed controls given, event planes written, no reward / done
+//         arrays, auto-reset from the pool.  launch_tick_f32 (astro_b200.cu) picks it when the launch's options match.
+// What the issue-bound form paid for, and no longer does (profiles/r2_ab_diet.md): option tests and the address arithmetic of
+// absent arrays (FIX); a test and a round loop around the common bullet loop (duplicated per value of `multi`); values ptxas
+// re-derived instead of keeping — the shared-memory base behind every rare float64 block, the tile index, the lane id — which now
+// go through a shuffle once (a shuffle's result cannot be re-materialised).
 #pragma once
 
 // Dead planet slots sit at kFar: the squared distance overflows to +inf, so a dead slot is never
